@@ -1,0 +1,234 @@
+/*
+ * mars_ode_b200.h -- C ABI of the B200-native batched rigid-body step.
+ *
+ * Drop-in boundary for the hot path behind WorldPhysics::stepTheWorld
+ * (reference src/WorldPhysics.cpp:349-421).  The reference reaches that path through the ODE
+ * C API; every entry point below names the ODE call (and the reference call site) it replaces.
+ * One *arena* holds a scene template (bodies, joints, geoms) replicated over `num_worlds`
+ * independent worlds in structure-of-arrays device buffers; `world` arguments select one
+ * replica, B2P_ALL_WORLDS broadcasts.
+ *
+ * All functions return 0 (or a non-negative id) on success and a negative B2P_E* code on
+ * failure; b2p_last_error() returns a description.  No exceptions cross this boundary, no
+ * torch / C++ types appear in it.  There is no CPU fallback: without a CUDA device every
+ * arena call fails with B2P_ENODEVICE.
+ */
+#ifndef MARS_ODE_B200_H
+#define MARS_ODE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2P_ALL_WORLDS (-1)
+#define B2P_STATIC_BODY (-1)
+
+/* error codes */
+#define B2P_OK 0
+#define B2P_EINVAL (-1)
+#define B2P_ENODEVICE (-2)
+#define B2P_ECUDA (-3)
+#define B2P_ECAPACITY (-4)
+#define B2P_EUNSUPPORTED (-5)
+#define B2P_EREJECTED (-6) /* contact between joint-connected bodies (WorldPhysics.cpp:461) */
+
+/* joint types: numeric values follow the ORDER of mars::interfaces::JointType as used by the
+ * switch statements in reference src/joints/Joint.cpp */
+enum {
+    B2P_JOINT_HINGE = 1,  /* dJointCreateHinge   -- src/joints/HingeJoint.cpp:33 */
+    B2P_JOINT_HINGE2 = 2, /* dJointCreateHinge2  -- src/joints/Hinge2Joint.cpp:37 */
+    B2P_JOINT_SLIDER = 3, /* dJointCreateSlider  -- src/joints/SliderJoint.cpp:34 */
+    B2P_JOINT_FIXED = 6   /* dJointCreateFixed   -- src/joints/FixedJoint.cpp:35 */
+};
+
+/* dParam* names used at src/joints/Joint.cpp:315-374,618-703,1176-1464 */
+enum {
+    B2P_PARAM_LO_STOP = 0,
+    B2P_PARAM_HI_STOP,
+    B2P_PARAM_VEL,
+    B2P_PARAM_LO_VEL,
+    B2P_PARAM_HI_VEL,
+    B2P_PARAM_FMAX,
+    B2P_PARAM_FUDGE_FACTOR,
+    B2P_PARAM_BOUNCE,
+    B2P_PARAM_CFM,
+    B2P_PARAM_STOP_ERP,
+    B2P_PARAM_STOP_CFM,
+    B2P_PARAM_SUSPENSION_ERP,
+    B2P_PARAM_SUSPENSION_CFM,
+    B2P_PARAM_ERP,
+    B2P_PARAM_GROUP2 = 0x100 /* dParam*2 */
+};
+
+/* dContact surface mode bits honoured by the device path (the ones Frame::addContact can set,
+ * src/objects/Frame.cpp:1038-1079) */
+enum {
+    B2P_CONTACT_MU2 = 0x001,
+    B2P_CONTACT_SOFT_ERP = 0x008,
+    B2P_CONTACT_SOFT_CFM = 0x010,
+    B2P_CONTACT_ROLLING = 0x400,
+    B2P_CONTACT_APPROX1_1 = 0x1000,
+    B2P_CONTACT_APPROX1_2 = 0x2000,
+    B2P_CONTACT_APPROX1_N = 0x4000,
+    B2P_CONTACT_APPROX1 = 0x7000
+};
+
+/* SOR row ordering inside the sweep */
+enum {
+    B2P_REORDER_RANDOMLY = 0, /* ODE 0.16 default: LCG shuffles at iterations 8, 16, ... */
+    B2P_REORDER_NONE = 1
+};
+
+/* geom classes for the device collision path (dCreate* -- absent from the reference tree,
+ * SURVEY.md section 8 a13) */
+enum {
+    B2P_GEOM_SPHERE = 0,
+    B2P_GEOM_BOX = 1,
+    B2P_GEOM_CAPSULE = 2,
+    B2P_GEOM_CYLINDER = 3,
+    B2P_GEOM_PLANE = 4,
+    B2P_GEOM_HEIGHTFIELD = 5
+};
+
+/* The dContact subset filled by Frame::addContact (src/objects/Frame.cpp:1023-1079).
+ * This 16-word record is also what the device narrowphase emits. */
+typedef struct b2p_contact_desc {
+    double pos[3];
+    double normal[3];
+    double depth;
+    int mode;
+    double mu, mu2;
+    double rho, rho2, rhoN;
+    double soft_erp, soft_cfm;
+} b2p_contact_desc;
+
+/* surface parameters attached to a geom; the collision kernels copy them into the contact
+ * stream (reference: ContactData::c_params, src/objects/Frame.cpp:1047-1071) */
+typedef struct b2p_surface {
+    double mu, mu2;
+    double rho, rho2, rhoN;
+    double soft_erp, soft_cfm;
+} b2p_surface;
+
+typedef struct b2p_arena b2p_arena;
+
+const char *b2p_last_error(void);
+int b2p_version(void);
+int b2p_device_count(void);
+
+/* ---- arena / world (dWorldCreate, dWorldDestroy: src/WorldPhysics.cpp:171,228) ---- */
+int b2p_arena_create(int num_worlds, int device, b2p_arena **out);
+void b2p_arena_destroy(b2p_arena *a);
+int b2p_arena_num_worlds(const b2p_arena *a);
+/* use an existing CUDA stream (cudaStream_t) for all copies and launches; NULL = default */
+int b2p_arena_set_stream(b2p_arena *a, void *cuda_stream);
+/* capacity knobs; must be called before the first step */
+int b2p_arena_set_max_contacts(b2p_arena *a, int max_contacts_per_world);
+int b2p_arena_enable_rolling_friction(b2p_arena *a, int on);
+
+int b2p_world_set_gravity(b2p_arena *a, double x, double y, double z);      /* dWorldSetGravity :194 */
+int b2p_world_set_cfm(b2p_arena *a, double cfm);                            /* dWorldSetCFM :195 */
+int b2p_world_set_erp(b2p_arena *a, double erp);                            /* dWorldSetERP :196 */
+int b2p_world_set_max_angular_speed(b2p_arena *a, double s);                /* dWorldSetMaxAngularSpeed :197 */
+int b2p_world_set_contact_max_correcting_vel(b2p_arena *a, double v);       /* dWorldSetContactMaxCorrectingVel :198 */
+int b2p_world_set_contact_surface_layer(b2p_arena *a, double d);
+int b2p_world_set_quickstep_num_iterations(b2p_arena *a, int n);
+int b2p_world_set_quickstep_w(b2p_arena *a, double w);
+int b2p_world_set_reorder_method(b2p_arena *a, int method);
+int b2p_world_rand_set_seed(b2p_arena *a, uint32_t seed);                   /* dRandSetSeed :169 (per world) */
+int b2p_world_rand_get_seed(b2p_arena *a, int world, uint32_t *seed);
+
+/* ---- bodies (dBody*: src/objects/Frame.cpp passim) ---- */
+int b2p_body_create(b2p_arena *a);                                          /* dBodyCreate :190,609 */
+int b2p_body_set_mass(b2p_arena *a, int body, double mass, const double I[9]); /* dBodySetMass :850 */
+int b2p_body_set_position(b2p_arena *a, int body, int world, double x, double y, double z);
+int b2p_body_set_quaternion(b2p_arena *a, int body, int world, double w, double x, double y, double z);
+int b2p_body_set_linear_vel(b2p_arena *a, int body, int world, double x, double y, double z);
+int b2p_body_set_angular_vel(b2p_arena *a, int body, int world, double x, double y, double z);
+int b2p_body_set_force(b2p_arena *a, int body, int world, double x, double y, double z);
+int b2p_body_set_torque(b2p_arena *a, int body, int world, double x, double y, double z);
+int b2p_body_add_force(b2p_arena *a, int body, int world, double x, double y, double z);
+int b2p_body_add_torque(b2p_arena *a, int body, int world, double x, double y, double z);
+int b2p_body_add_force_at_pos(b2p_arena *a, int body, int world, double fx, double fy, double fz,
+                              double px, double py, double pz);
+int b2p_body_set_gravity_mode(b2p_arena *a, int body, int on);
+int b2p_body_set_gyroscopic_mode(b2p_arena *a, int body, int on);
+int b2p_body_get_position(b2p_arena *a, int body, int world, double out[3]);
+int b2p_body_get_quaternion(b2p_arena *a, int body, int world, double out[4]);
+int b2p_body_get_rotation(b2p_arena *a, int body, int world, double out[9]);
+int b2p_body_get_linear_vel(b2p_arena *a, int body, int world, double out[3]);
+int b2p_body_get_angular_vel(b2p_arena *a, int body, int world, double out[3]);
+int b2p_body_get_force(b2p_arena *a, int body, int world, double out[3]);
+int b2p_body_get_torque(b2p_arena *a, int body, int world, double out[3]);
+/* 13 values: pos3, quat4 (w,x,y,z), lvel3, avel3 */
+int b2p_body_get_state(b2p_arena *a, int body, int world, double out[13]);
+int b2p_body_set_state(b2p_arena *a, int body, int world, const double in[13]);
+
+/* batched state I/O in the device layout: float[num_bodies][13][num_worlds] */
+int b2p_state_upload(b2p_arena *a, const float *host_state);
+int b2p_state_download(b2p_arena *a, float *host_state);
+/* device pointers (float, layout [field][padded_worlds]) for zero-copy consumers */
+int b2p_padded_worlds(const b2p_arena *a);
+void *b2p_device_state(b2p_arena *a);       /* [nb*13][Wp] */
+void *b2p_device_joint_cmd(b2p_arena *a);   /* [nj*4][Wp]: vel1,fmax1,vel2,fmax2 */
+void *b2p_device_joint_obs(b2p_arena *a);   /* [nj*4][Wp]: angle1,rate1,angle2,rate2 */
+
+/* ---- joints (dJoint*: src/joints/*.cpp) ---- */
+int b2p_joint_create(b2p_arena *a, int type, int body1, int body2);         /* dJointCreate* + dJointAttach */
+int b2p_joint_set_anchor(b2p_arena *a, int joint, double x, double y, double z);
+int b2p_joint_set_axis1(b2p_arena *a, int joint, double x, double y, double z);
+int b2p_joint_set_axis2(b2p_arena *a, int joint, double x, double y, double z);
+int b2p_joint_set_fixed(b2p_arena *a, int joint);                           /* dJointSetFixed */
+/* VEL and FMAX (both axes) may be set per world; all other parameters are per template */
+int b2p_joint_set_param(b2p_arena *a, int joint, int world, int param, double value);
+int b2p_joint_get_param(b2p_arena *a, int joint, int world, int param, double *value);
+/* batched motor commands: float[num_worlds] per call */
+int b2p_joint_set_param_batch(b2p_arena *a, int joint, int param, const float *values);
+int b2p_joint_get_anchor(b2p_arena *a, int joint, int world, double out[3]);
+int b2p_joint_get_anchor2(b2p_arena *a, int joint, int world, double out[3]);
+int b2p_joint_get_axis1(b2p_arena *a, int joint, int world, double out[3]);
+int b2p_joint_get_axis2(b2p_arena *a, int joint, int world, double out[3]);
+int b2p_joint_get_angle1(b2p_arena *a, int joint, int world, double *out);       /* dJointGetHingeAngle / SliderPosition / Hinge2Angle1 */
+int b2p_joint_get_angle1_rate(b2p_arena *a, int joint, int world, double *out);
+int b2p_joint_get_angle2(b2p_arena *a, int joint, int world, double *out);
+int b2p_joint_get_angle2_rate(b2p_arena *a, int joint, int world, double *out);
+int b2p_joint_add_torque(b2p_arena *a, int joint, int world, double t);          /* dJointAddHingeTorque / dJointAddSliderForce */
+/* dJointFeedback incl. the patched `lambda`: f1 t1 f2 t2 lambda = 13 doubles (Joint.cpp:268,900) */
+int b2p_joint_get_feedback(b2p_arena *a, int joint, int world, double out[13]);
+int b2p_joint_get_num_rows(b2p_arena *a, int joint, int world, int *rows);
+int b2p_are_connected_excluding_contacts(b2p_arena *a, int body1, int body2);    /* dAreConnectedExcluding :461 */
+
+/* ---- host-injected contacts (dJointCreateContact: src/WorldPhysics.cpp:458-468) ---- */
+int b2p_contacts_clear(b2p_arena *a, int world);                                 /* dJointGroupEmpty :317 */
+int b2p_contact_add(b2p_arena *a, int world, int body1, int body2, const b2p_contact_desc *c);
+int b2p_contact_count(b2p_arena *a, int world, int *count);
+int b2p_contact_get_feedback(b2p_arena *a, int world, int contact, double f1[3]);
+/* read back a contact record of the current stream (host-injected or device-generated) */
+int b2p_contact_get(b2p_arena *a, int world, int contact, int *body1, int *body2, b2p_contact_desc *c);
+
+/* ---- device collision path (dSpaceCollide + dCollide) ---- */
+int b2p_geom_create(b2p_arena *a, int geom_class, int body, const double dims[4],
+                    const double local_pos[3], const double local_quat[4], const b2p_surface *s);
+/* heights: row-major [ny][nx] floats, sample spacing dx, origin (x0,y0), shared by all worlds */
+int b2p_geom_create_heightfield(b2p_arena *a, const float *heights, int nx, int ny, double dx,
+                                double x0, double y0, const b2p_surface *s);
+/* run broadphase + narrowphase on the device, replacing the contact stream of every world */
+int b2p_collide(b2p_arena *a);
+/* broadphase pair list of one world, sorted by (min geom, max geom); returns pair count */
+int b2p_collide_get_pairs(b2p_arena *a, int world, int *pairs, int max_pairs);
+
+/* ---- the step (dWorldQuickStep: src/WorldPhysics.cpp:365) ---- */
+int b2p_step(b2p_arena *a, double step_size);
+int b2p_sync(b2p_arena *a);
+/* diagnostics of the last step */
+int b2p_world_last_num_rows(b2p_arena *a, int world, int *rows);
+int b2p_kernel_launch_count(const b2p_arena *a); /* kernels launched by this arena so far */
+/* algorithmic bytes one step of one world moves */
+double b2p_algorithmic_bytes_per_world_step(const b2p_arena *a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

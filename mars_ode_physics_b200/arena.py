@@ -1,0 +1,326 @@
+"""Thin object wrapper over the C ABI (one method per entry point, same argument meaning).
+
+PyTorch is not needed here; bench.py uses torch only for streams/events and pinned memory.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import ALL_WORLDS, B2PError
+
+
+class Arena:
+    """A scene template replicated over ``num_worlds`` independent worlds on one B200."""
+
+    def __init__(self, num_worlds, device=0, strict=False):
+        self.lib = capi.load(strict)
+        self.h = C.c_void_p()
+        self._check(self.lib.b2p_arena_create(int(num_worlds), int(device), C.byref(self.h)))
+        self.num_worlds = int(num_worlds)
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc < 0:
+            raise B2PError(rc, self.lib.b2p_last_error().decode())
+        return rc
+
+    def close(self):
+        if self.h:
+            self.lib.b2p_arena_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _out(n):
+        return (C.c_double * n)()
+
+    # -- world ------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_handle):
+        self._check(self.lib.b2p_arena_set_stream(self.h, C.c_void_p(cuda_stream_handle)))
+
+    def set_max_contacts(self, n):
+        self._check(self.lib.b2p_arena_set_max_contacts(self.h, n))
+
+    def enable_rolling_friction(self, on=True):
+        self._check(self.lib.b2p_arena_enable_rolling_friction(self.h, int(on)))
+
+    def set_gravity(self, x, y, z):
+        self._check(self.lib.b2p_world_set_gravity(self.h, x, y, z))
+
+    def set_cfm(self, v):
+        self._check(self.lib.b2p_world_set_cfm(self.h, v))
+
+    def set_erp(self, v):
+        self._check(self.lib.b2p_world_set_erp(self.h, v))
+
+    def set_max_angular_speed(self, v):
+        self._check(self.lib.b2p_world_set_max_angular_speed(self.h, v))
+
+    def set_contact_max_correcting_vel(self, v):
+        self._check(self.lib.b2p_world_set_contact_max_correcting_vel(self.h, v))
+
+    def set_contact_surface_layer(self, v):
+        self._check(self.lib.b2p_world_set_contact_surface_layer(self.h, v))
+
+    def set_quickstep_num_iterations(self, n):
+        self._check(self.lib.b2p_world_set_quickstep_num_iterations(self.h, n))
+
+    def set_quickstep_w(self, v):
+        self._check(self.lib.b2p_world_set_quickstep_w(self.h, v))
+
+    def set_reorder_method(self, m):
+        self._check(self.lib.b2p_world_set_reorder_method(self.h, m))
+
+    def rand_set_seed(self, seed):
+        self._check(self.lib.b2p_world_rand_set_seed(self.h, seed))
+
+    def rand_get_seed(self, world):
+        s = C.c_uint32()
+        self._check(self.lib.b2p_world_rand_get_seed(self.h, world, C.byref(s)))
+        return s.value
+
+    # -- bodies -----------------------------------------------------------------------------
+    def body_create(self):
+        return self._check(self.lib.b2p_body_create(self.h))
+
+    def body_set_mass(self, b, mass, I):
+        arr = (C.c_double * 9)(*[float(x) for x in np.asarray(I, dtype=float).reshape(9)])
+        self._check(self.lib.b2p_body_set_mass(self.h, b, mass, arr))
+
+    def body_set_position(self, b, p, world=ALL_WORLDS):
+        self._check(self.lib.b2p_body_set_position(self.h, b, world, *map(float, p)))
+
+    def body_set_quaternion(self, b, q, world=ALL_WORLDS):
+        self._check(self.lib.b2p_body_set_quaternion(self.h, b, world, *map(float, q)))
+
+    def body_set_linear_vel(self, b, v, world=ALL_WORLDS):
+        self._check(self.lib.b2p_body_set_linear_vel(self.h, b, world, *map(float, v)))
+
+    def body_set_angular_vel(self, b, v, world=ALL_WORLDS):
+        self._check(self.lib.b2p_body_set_angular_vel(self.h, b, world, *map(float, v)))
+
+    def body_set_force(self, b, v, world=ALL_WORLDS):
+        self._check(self.lib.b2p_body_set_force(self.h, b, world, *map(float, v)))
+
+    def body_set_torque(self, b, v, world=ALL_WORLDS):
+        self._check(self.lib.b2p_body_set_torque(self.h, b, world, *map(float, v)))
+
+    def body_add_force(self, b, v, world=ALL_WORLDS):
+        self._check(self.lib.b2p_body_add_force(self.h, b, world, *map(float, v)))
+
+    def body_add_torque(self, b, v, world=ALL_WORLDS):
+        self._check(self.lib.b2p_body_add_torque(self.h, b, world, *map(float, v)))
+
+    def body_add_force_at_pos(self, b, f, p, world=ALL_WORLDS):
+        self._check(self.lib.b2p_body_add_force_at_pos(self.h, b, world, *map(float, f), *map(float, p)))
+
+    def body_set_gravity_mode(self, b, on):
+        self._check(self.lib.b2p_body_set_gravity_mode(self.h, b, int(on)))
+
+    def body_set_gyroscopic_mode(self, b, on):
+        self._check(self.lib.b2p_body_set_gyroscopic_mode(self.h, b, int(on)))
+
+    def _get(self, fn, n, *ids):
+        out = self._out(n)
+        self._check(fn(self.h, *ids, out))
+        return np.array(out[:], dtype=float)
+
+    def body_get_position(self, b, world=0):
+        return self._get(self.lib.b2p_body_get_position, 3, b, world)
+
+    def body_get_quaternion(self, b, world=0):
+        return self._get(self.lib.b2p_body_get_quaternion, 4, b, world)
+
+    def body_get_rotation(self, b, world=0):
+        return self._get(self.lib.b2p_body_get_rotation, 9, b, world)
+
+    def body_get_linear_vel(self, b, world=0):
+        return self._get(self.lib.b2p_body_get_linear_vel, 3, b, world)
+
+    def body_get_angular_vel(self, b, world=0):
+        return self._get(self.lib.b2p_body_get_angular_vel, 3, b, world)
+
+    def body_get_force(self, b, world=0):
+        return self._get(self.lib.b2p_body_get_force, 3, b, world)
+
+    def body_get_torque(self, b, world=0):
+        return self._get(self.lib.b2p_body_get_torque, 3, b, world)
+
+    def body_get_state(self, b, world=0):
+        return self._get(self.lib.b2p_body_get_state, 13, b, world)
+
+    def body_set_state(self, b, s, world=ALL_WORLDS):
+        arr = (C.c_double * 13)(*map(float, s))
+        self._check(self.lib.b2p_body_set_state(self.h, b, world, arr))
+
+    def state_upload(self, host_state):
+        a = np.ascontiguousarray(host_state, dtype=np.float32)
+        self._check(self.lib.b2p_state_upload(self.h, a.ctypes.data_as(C.c_void_p)))
+
+    def state_download(self, num_bodies, out=None):
+        if out is None:
+            out = np.empty((num_bodies, 13, self.num_worlds), dtype=np.float32)
+        self._check(self.lib.b2p_state_download(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # -- joints -----------------------------------------------------------------------------
+    def joint_create(self, jtype, b1, b2):
+        return self._check(self.lib.b2p_joint_create(self.h, jtype, b1, b2))
+
+    def joint_set_anchor(self, j, p):
+        self._check(self.lib.b2p_joint_set_anchor(self.h, j, *map(float, p)))
+
+    def joint_set_axis1(self, j, a):
+        self._check(self.lib.b2p_joint_set_axis1(self.h, j, *map(float, a)))
+
+    def joint_set_axis2(self, j, a):
+        self._check(self.lib.b2p_joint_set_axis2(self.h, j, *map(float, a)))
+
+    def joint_set_fixed(self, j):
+        self._check(self.lib.b2p_joint_set_fixed(self.h, j))
+
+    def joint_set_param(self, j, param, value, world=ALL_WORLDS):
+        self._check(self.lib.b2p_joint_set_param(self.h, j, world, param, float(value)))
+
+    def joint_get_param(self, j, param, world=0):
+        v = C.c_double()
+        self._check(self.lib.b2p_joint_get_param(self.h, j, world, param, C.byref(v)))
+        return v.value
+
+    def joint_set_param_batch(self, j, param, values):
+        a = np.ascontiguousarray(values, dtype=np.float32)
+        assert a.shape == (self.num_worlds,)
+        self._check(self.lib.b2p_joint_set_param_batch(self.h, j, param, a.ctypes.data_as(C.c_void_p)))
+
+    def joint_set_param_batch_ptr(self, j, param, host_ptr):
+        self._check(self.lib.b2p_joint_set_param_batch(self.h, j, param, C.c_void_p(host_ptr)))
+
+    def joint_get_anchor(self, j, world=0):
+        return self._get(self.lib.b2p_joint_get_anchor, 3, j, world)
+
+    def joint_get_anchor2(self, j, world=0):
+        return self._get(self.lib.b2p_joint_get_anchor2, 3, j, world)
+
+    def joint_get_axis1(self, j, world=0):
+        return self._get(self.lib.b2p_joint_get_axis1, 3, j, world)
+
+    def joint_get_axis2(self, j, world=0):
+        return self._get(self.lib.b2p_joint_get_axis2, 3, j, world)
+
+    def _scalar(self, fn, j, world):
+        v = C.c_double()
+        self._check(fn(self.h, j, world, C.byref(v)))
+        return v.value
+
+    def joint_get_angle1(self, j, world=0):
+        return self._scalar(self.lib.b2p_joint_get_angle1, j, world)
+
+    def joint_get_angle1_rate(self, j, world=0):
+        return self._scalar(self.lib.b2p_joint_get_angle1_rate, j, world)
+
+    def joint_get_angle2(self, j, world=0):
+        return self._scalar(self.lib.b2p_joint_get_angle2, j, world)
+
+    def joint_get_angle2_rate(self, j, world=0):
+        return self._scalar(self.lib.b2p_joint_get_angle2_rate, j, world)
+
+    def joint_add_torque(self, j, t, world=ALL_WORLDS):
+        self._check(self.lib.b2p_joint_add_torque(self.h, j, world, float(t)))
+
+    def joint_get_feedback(self, j, world=0):
+        return self._get(self.lib.b2p_joint_get_feedback, 13, j, world)
+
+    def joint_get_num_rows(self, j, world=0):
+        v = C.c_int()
+        self._check(self.lib.b2p_joint_get_num_rows(self.h, j, world, C.byref(v)))
+        return v.value
+
+    # -- contacts ---------------------------------------------------------------------------
+    def contacts_clear(self, world=ALL_WORLDS):
+        self._check(self.lib.b2p_contacts_clear(self.h, world))
+
+    def contact_add(self, world, b1, b2, **kw):
+        """Returns the contact id, or -1 when the bodies are joint-connected (rejected)."""
+        d = capi.ContactDesc()
+        d.pos[:] = [float(x) for x in kw["pos"]]
+        d.normal[:] = [float(x) for x in kw["normal"]]
+        d.depth = float(kw["depth"])
+        d.mode = int(kw["mode"])
+        for k in ("mu", "mu2", "rho", "rho2", "rhoN", "soft_erp", "soft_cfm"):
+            setattr(d, k, float(kw.get(k, 0.0)))
+        rc = self.lib.b2p_contact_add(self.h, world, b1, b2, C.byref(d))
+        if rc == capi.E_REJECTED:
+            return -1
+        return self._check(rc)
+
+    def contact_count(self, world=0):
+        v = C.c_int()
+        self._check(self.lib.b2p_contact_count(self.h, world, C.byref(v)))
+        return v.value
+
+    def contact_get_feedback(self, world, c):
+        return self._get(self.lib.b2p_contact_get_feedback, 3, world, c)
+
+    def contact_get(self, world, c):
+        b1, b2, d = C.c_int(), C.c_int(), capi.ContactDesc()
+        self._check(self.lib.b2p_contact_get(self.h, world, c, C.byref(b1), C.byref(b2), C.byref(d)))
+        return b1.value, b2.value, d
+
+    # -- geoms / collision ------------------------------------------------------------------
+    @staticmethod
+    def _surface(s):
+        if s is None:
+            return None
+        out = capi.Surface()
+        for k in ("mu", "mu2", "rho", "rho2", "rhoN", "soft_erp", "soft_cfm"):
+            setattr(out, k, float(s.get(k, 0.0)))
+        return out
+
+    def geom_create(self, cls, body, dims, lpos=(0, 0, 0), lquat=(1, 0, 0, 0), surface=None):
+        d = (C.c_double * 4)(*([float(x) for x in dims] + [0.0] * (4 - len(dims))))
+        p = (C.c_double * 3)(*map(float, lpos))
+        q = (C.c_double * 4)(*map(float, lquat))
+        s = self._surface(surface)
+        return self._check(self.lib.b2p_geom_create(self.h, cls, body, d, p, q, C.byref(s) if s else None))
+
+    def geom_create_heightfield(self, heights, dx, x0, y0, surface=None):
+        hts = np.ascontiguousarray(heights, dtype=np.float32)
+        ny, nx = hts.shape
+        s = self._surface(surface)
+        return self._check(self.lib.b2p_geom_create_heightfield(
+            self.h, hts.ctypes.data_as(C.c_void_p), nx, ny, dx, x0, y0, C.byref(s) if s else None))
+
+    def collide(self):
+        self._check(self.lib.b2p_collide(self.h))
+
+    def collide_get_pairs(self, world, max_pairs=4096):
+        buf = (C.c_int * max_pairs)()
+        n = self._check(self.lib.b2p_collide_get_pairs(self.h, world, buf, max_pairs))
+        return [(v & 0xffff, v >> 16) for v in buf[:n]]
+
+    # -- step -------------------------------------------------------------------------------
+    def step(self, h):
+        self._check(self.lib.b2p_step(self.h, float(h)))
+
+    def sync(self):
+        self._check(self.lib.b2p_sync(self.h))
+
+    def last_num_rows(self, world=0):
+        v = C.c_int()
+        self._check(self.lib.b2p_world_last_num_rows(self.h, world, C.byref(v)))
+        return v.value
+
+    def kernel_launch_count(self):
+        return self.lib.b2p_kernel_launch_count(self.h)
+
+    def algorithmic_bytes_per_world_step(self):
+        return self.lib.b2p_algorithmic_bytes_per_world_step(self.h)
+
+    def padded_worlds(self):
+        return self.lib.b2p_padded_worlds(self.h)

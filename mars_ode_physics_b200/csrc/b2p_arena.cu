@@ -1,0 +1,1759 @@
+// b2p_arena.cu -- host side of the C ABI declared in include/mars_ode_b200.h.
+//
+// An arena is a scene template (bodies, joints, geoms) replicated over W worlds.  Per-world data
+// lives in SoA device buffers (layout in b2p_dev.h); small host mirrors with dirty flags make the
+// one-world-at-a-time accessors of the reference API (Frame::getPosition, Joint::setVelocity ...)
+// work without the caller managing transfers.  Creation-time joint geometry (anchors/axes in body
+// frames, relative rotations) is evaluated here in double precision from the template poses, as
+// ODE does inside dJointSet*Anchor / dJointSet*Axis.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/mars_ode_b200.h"
+#include "b2p_dev.h"
+
+extern "C" size_t b2p_step_smem_bytes(int nb, int nj, int maxc, int rpc);
+extern "C" int b2p_step_block_dim(void);
+extern "C" cudaError_t b2p_launch_step(const StepParams *P, size_t smem, cudaStream_t stream);
+extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, cudaStream_t stream);
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) return fail(B2P_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+const double kInf = std::numeric_limits<double>::infinity();
+
+// ---------------- double-precision helpers for creation-time geometry ----------------
+struct D3 {
+    double v[3];
+};
+void q_to_R(const double *q, double *R)
+{
+    double qq1 = 2 * q[1] * q[1], qq2 = 2 * q[2] * q[2], qq3 = 2 * q[3] * q[3];
+    R[0] = 1 - qq2 - qq3;
+    R[1] = 2 * (q[1] * q[2] - q[0] * q[3]);
+    R[2] = 2 * (q[1] * q[3] + q[0] * q[2]);
+    R[3] = 2 * (q[1] * q[2] + q[0] * q[3]);
+    R[4] = 1 - qq1 - qq3;
+    R[5] = 2 * (q[2] * q[3] - q[0] * q[1]);
+    R[6] = 2 * (q[1] * q[3] - q[0] * q[2]);
+    R[7] = 2 * (q[2] * q[3] + q[0] * q[1]);
+    R[8] = 1 - qq1 - qq2;
+}
+void Rv(double *r, const double *R, const double *v)
+{
+    double x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+    double y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+    double z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+    r[0] = x, r[1] = y, r[2] = z;
+}
+void Rtv(double *r, const double *R, const double *v)
+{
+    double x = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
+    double y = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+    double z = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+    r[0] = x, r[1] = y, r[2] = z;
+}
+double dot(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+void cross(double *r, const double *a, const double *b)
+{
+    double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    r[0] = x, r[1] = y, r[2] = z;
+}
+void norm3(double *a)
+{
+    double l = dot(a, a);
+    if (l > 0) {
+        l = 1 / std::sqrt(l);
+        a[0] *= l, a[1] *= l, a[2] *= l;
+    } else {
+        a[0] = 1, a[1] = 0, a[2] = 0;
+    }
+}
+void norm4(double *a)
+{
+    double l = a[0] * a[0] + a[1] * a[1] + a[2] * a[2] + a[3] * a[3];
+    if (l > 0) {
+        l = 1 / std::sqrt(l);
+        for (int i = 0; i < 4; i++) a[i] *= l;
+    } else {
+        a[0] = 1, a[1] = a[2] = a[3] = 0;
+    }
+}
+void qmul1(double *r, const double *b, const double *c) // b^-1 c
+{
+    double t[4];
+    t[0] = b[0] * c[0] + b[1] * c[1] + b[2] * c[2] + b[3] * c[3];
+    t[1] = b[0] * c[1] - b[1] * c[0] - b[2] * c[3] + b[3] * c[2];
+    t[2] = b[0] * c[2] - b[2] * c[0] - b[3] * c[1] + b[1] * c[3];
+    t[3] = b[0] * c[3] - b[3] * c[0] - b[1] * c[2] + b[2] * c[1];
+    memcpy(r, t, sizeof(t));
+}
+void qmul2(double *r, const double *b, const double *c) // b c^-1
+{
+    double t[4];
+    t[0] = b[0] * c[0] + b[1] * c[1] + b[2] * c[2] + b[3] * c[3];
+    t[1] = -b[0] * c[1] + b[1] * c[0] - b[2] * c[3] + b[3] * c[2];
+    t[2] = -b[0] * c[2] + b[2] * c[0] - b[3] * c[1] + b[1] * c[3];
+    t[3] = -b[0] * c[3] + b[3] * c[0] - b[1] * c[2] + b[2] * c[1];
+    memcpy(r, t, sizeof(t));
+}
+void qmul3(double *r, const double *b, const double *c) // b^-1 c^-1
+{
+    double t[4];
+    t[0] = b[0] * c[0] - b[1] * c[1] - b[2] * c[2] - b[3] * c[3];
+    t[1] = -b[0] * c[1] - b[1] * c[0] + b[2] * c[3] - b[3] * c[2];
+    t[2] = -b[0] * c[2] - b[2] * c[0] + b[3] * c[1] - b[1] * c[3];
+    t[3] = -b[0] * c[3] - b[3] * c[0] + b[1] * c[2] - b[2] * c[1];
+    memcpy(r, t, sizeof(t));
+}
+bool invert33(double *dst, const double *m)
+{
+    double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+    double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    if (det == 0) return false;
+    double r = 1 / det, t[9];
+    t[0] = c00 * r;
+    t[1] = (m[2] * m[7] - m[1] * m[8]) * r;
+    t[2] = (m[1] * m[5] - m[2] * m[4]) * r;
+    t[3] = c01 * r;
+    t[4] = (m[0] * m[8] - m[2] * m[6]) * r;
+    t[5] = (m[2] * m[3] - m[0] * m[5]) * r;
+    t[6] = c02 * r;
+    t[7] = (m[1] * m[6] - m[0] * m[7]) * r;
+    t[8] = (m[0] * m[4] - m[1] * m[3]) * r;
+    memcpy(dst, t, sizeof(t));
+    return true;
+}
+
+struct HLimot {
+    double lostop = -kInf, histop = kInf, fudge = 1, normal_cfm = 0, stop_erp = 0, stop_cfm = 0, bounce = 0;
+    double vel = 0, fmax = 0; // template value of the per-world commands
+};
+
+struct HBody {
+    double mass = 1, I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, invI[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    int gyroscopic = 1, nogravity = 0, has_max_ang = 0;
+    double max_angular_speed = kInf;
+    double pos[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0}; // template pose (world 0 / broadcast)
+};
+
+struct HJoint {
+    int type = 0, b[2] = {-1, -1}, reverse = 0;
+    double anchor1[3] = {0, 0, 0}, anchor2[3] = {0, 0, 0}, axis1[3] = {1, 0, 0}, axis2[3] = {1, 0, 0};
+    double qrel[4] = {1, 0, 0, 0}, offset[3] = {0, 0, 0};
+    HLimot limot1, limot2;
+    double c0 = 0, s0 = 0, v1[3] = {1, 0, 0}, v2[3] = {0, 1, 0}, w1[3] = {1, 0, 0}, w2[3] = {0, 1, 0};
+    double susp_erp = 0, susp_cfm = 0, erp = 0, cfm = 0;
+};
+
+struct HGeom {
+    int cls = 0, body = -1;
+    double dims[4] = {0, 0, 0, 0}, lpos[3] = {0, 0, 0}, lquat[4] = {1, 0, 0, 0};
+    b2p_surface s{};
+};
+
+// A per-world SoA buffer with a host mirror and coherence flags.
+template <typename T> struct Mirror {
+    std::vector<T> host;
+    T *dev = nullptr;
+    size_t dev_elems = 0;
+    bool host_newer = false, dev_newer = false;
+    size_t fields = 0;
+};
+
+} // namespace
+
+struct b2p_arena {
+    int W = 0, Wp = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    double gravity[3] = {0, 0, 0}, erp = 0.2, cfm = 1e-5, max_ang = kInf, contact_max_vel = kInf, min_depth = 0,
+           sor_w = 1.3;
+    int iters = 20, reorder = B2P_REORDER_RANDOMLY;
+    std::vector<HBody> bodies;
+    std::vector<HJoint> joints;
+    std::vector<HGeom> geoms;
+    int maxc = 8, rolling = 0;
+    bool tmpl_dirty = true;
+    DevTemplate *dT = nullptr;
+    std::vector<float> hf_heights;
+    float *d_hf = nullptr;
+    int hf_nx = 0, hf_ny = 0;
+    double hf_dx = 0, hf_x0 = 0, hf_y0 = 0;
+    bool has_hf = false;
+    b2p_surface hf_surface{};
+
+    Mirror<float> state, force, jcmd, jobs, jfb, crec, cfb;
+    Mirror<int> ccount, nrows;
+    Mirror<uint32_t> seed;
+    Mirror<uint8_t> jrows;
+    // solver scratch (device only)
+    float4 *d_rows = nullptr;
+    float *d_lambda = nullptr, *d_rowad = nullptr, *d_invIw = nullptr;
+    size_t scratch_rows = 0, scratch_nb = 0;
+    int *d_pairs = nullptr, *d_npairs = nullptr;
+    int maxpairs = 0;
+    int launches = 0;
+    bool stepped = false;
+};
+
+namespace {
+
+template <typename T> int mirror_resize(b2p_arena *a, Mirror<T> &m, size_t fields, T fill)
+{
+    const size_t n = fields * (size_t)a->Wp;
+    if (m.fields == fields && m.host.size() == n) return 0;
+    // device content (if newer) must come home before the host vector is regrown
+    if (m.dev_newer && m.dev && m.dev_elems) {
+        CUDA_TRY(cudaMemcpyAsync(m.host.data(), m.dev, sizeof(T) * std::min(m.dev_elems, m.host.size()),
+                                 cudaMemcpyDeviceToHost, a->stream));
+        CUDA_TRY(cudaStreamSynchronize(a->stream));
+        m.dev_newer = false;
+    }
+    m.host.resize(n, fill);
+    m.fields = fields;
+    m.host_newer = true;
+    return 0;
+}
+
+template <typename T> int mirror_to_device(b2p_arena *a, Mirror<T> &m)
+{
+    const size_t n = m.host.size();
+    if (m.dev_elems != n) {
+        if (m.dev) CUDA_TRY(cudaFree(m.dev));
+        m.dev = nullptr;
+        m.dev_elems = 0;
+        if (n) {
+            CUDA_TRY(cudaMalloc(&m.dev, sizeof(T) * n));
+            m.dev_elems = n;
+        }
+        m.host_newer = true;
+    }
+    if (m.host_newer && n) {
+        CUDA_TRY(cudaMemcpyAsync(m.dev, m.host.data(), sizeof(T) * n, cudaMemcpyHostToDevice, a->stream));
+        m.host_newer = false;
+    }
+    return 0;
+}
+
+template <typename T> int mirror_to_host(b2p_arena *a, Mirror<T> &m)
+{
+    if (m.dev_newer && m.dev && m.dev_elems) {
+        CUDA_TRY(cudaMemcpyAsync(m.host.data(), m.dev, sizeof(T) * m.dev_elems, cudaMemcpyDeviceToHost, a->stream));
+        CUDA_TRY(cudaStreamSynchronize(a->stream));
+    }
+    m.dev_newer = false;
+    return 0;
+}
+
+template <typename T> void mirror_free(Mirror<T> &m)
+{
+    if (m.dev) cudaFree(m.dev);
+    m.dev = nullptr;
+}
+
+// set a field for one world or all worlds
+template <typename T> void mset(b2p_arena *a, Mirror<T> &m, size_t field, int world, T v)
+{
+    T *row = m.host.data() + field * (size_t)a->Wp;
+    if (world == B2P_ALL_WORLDS) {
+        for (int w = 0; w < a->W; w++) row[w] = v;
+    } else {
+        row[world] = v;
+    }
+    m.host_newer = true;
+}
+
+int check_world(const b2p_arena *a, int world, bool allow_all)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    if (world == B2P_ALL_WORLDS && allow_all) return 0;
+    if (world < 0 || world >= a->W) return fail(B2P_EINVAL, "world index %d out of range [0,%d)", world, a->W);
+    return 0;
+}
+int check_body(const b2p_arena *a, int body)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    if (body < 0 || body >= (int)a->bodies.size()) return fail(B2P_EINVAL, "body id %d out of range", body);
+    return 0;
+}
+int check_joint(const b2p_arena *a, int j)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    if (j < 0 || j >= (int)a->joints.size()) return fail(B2P_EINVAL, "joint id %d out of range", j);
+    return 0;
+}
+
+int rpc_of(const b2p_arena *a) { return a->rolling ? 6 : 3; }
+
+// host view of a body's pose in one world (double from the float mirror)
+int body_pose(b2p_arena *a, int body, int world, double *pos, double *q)
+{
+    int rc = mirror_to_host(a, a->state);
+    if (rc) return rc;
+    const float *s = a->state.host.data();
+    const size_t f = (size_t)body * B2P_STATE_FIELDS;
+    for (int i = 0; i < 3; i++) pos[i] = s[(f + i) * a->Wp + world];
+    for (int i = 0; i < 4; i++) q[i] = s[(f + 3 + i) * a->Wp + world];
+    return 0;
+}
+
+int body_vec(b2p_arena *a, Mirror<float> &m, size_t field0, int world, int n, double *out)
+{
+    int rc = mirror_to_host(a, m);
+    if (rc) return rc;
+    for (int i = 0; i < n; i++) out[i] = m.host[(field0 + i) * a->Wp + world];
+    return 0;
+}
+
+void fill_limot(DevLimot &d, const HLimot &h)
+{
+    d.lostop = (float)h.lostop;
+    d.histop = (float)h.histop;
+    d.fudge_factor = (float)h.fudge;
+    d.normal_cfm = (float)h.normal_cfm;
+    d.stop_erp = (float)h.stop_erp;
+    d.stop_cfm = (float)h.stop_cfm;
+    d.bounce = (float)h.bounce;
+    d.pad = 0;
+}
+
+bool limot_has_stops(const HLimot &l) { return (l.lostop > -kInf || l.histop < kInf) && l.lostop < l.histop; }
+
+// (re)build the device template and size every buffer
+int finalize(b2p_arena *a)
+{
+    const int nb = (int)a->bodies.size(), nj = (int)a->joints.size(), ng = (int)a->geoms.size();
+    if (nb > B2P_MAX_BODIES) return fail(B2P_ECAPACITY, "too many bodies (%d > %d)", nb, B2P_MAX_BODIES);
+    if (nj > B2P_MAX_JOINTS) return fail(B2P_ECAPACITY, "too many joints (%d > %d)", nj, B2P_MAX_JOINTS);
+    if (ng > B2P_MAX_GEOMS) return fail(B2P_ECAPACITY, "too many geoms (%d > %d)", ng, B2P_MAX_GEOMS);
+    const int rpc = rpc_of(a);
+    const int njslots = nj * B2P_ROWS_PER_JOINT, maxrows = njslots + a->maxc * rpc;
+    if (maxrows > 255) return fail(B2P_ECAPACITY, "too many constraint rows per world (%d > 255)", maxrows);
+    if (a->tmpl_dirty) {
+        std::vector<char> buf(sizeof(DevTemplate), 0);
+        DevTemplate *T = reinterpret_cast<DevTemplate *>(buf.data());
+        T->nb = nb;
+        T->nj = nj;
+        T->ng = ng;
+        T->maxc = a->maxc;
+        T->rpc = rpc;
+        T->njslots = njslots;
+        T->maxrows = maxrows;
+        T->has_limit_motors = 0;
+        for (int b = 0; b < nb; b++) {
+            const HBody &h = a->bodies[b];
+            DevBody &d = T->bodies[b];
+            d.mass = (float)h.mass;
+            d.invMass = (float)(1.0 / h.mass);
+            for (int i = 0; i < 9; i++) {
+                d.I[i] = (float)h.I[i];
+                d.invI[i] = (float)h.invI[i];
+            }
+            d.gyroscopic = h.gyroscopic;
+            d.nogravity = h.nogravity;
+            d.has_max_ang = h.has_max_ang;
+            d.max_angular_speed = (float)h.max_angular_speed;
+        }
+        for (int j = 0; j < nj; j++) {
+            const HJoint &h = a->joints[j];
+            DevJoint &d = T->joints[j];
+            d.type = h.type;
+            d.b0 = h.b[0];
+            d.b1 = h.b[1];
+            d.reverse = h.reverse;
+            d.slot_base = j * B2P_ROWS_PER_JOINT;
+            for (int i = 0; i < 3; i++) {
+                d.anchor1[i] = (float)h.anchor1[i];
+                d.anchor2[i] = (float)h.anchor2[i];
+                d.axis1[i] = (float)h.axis1[i];
+                d.axis2[i] = (float)h.axis2[i];
+                d.offset[i] = (float)h.offset[i];
+                d.v1[i] = (float)h.v1[i];
+                d.v2[i] = (float)h.v2[i];
+                d.w1[i] = (float)h.w1[i];
+                d.w2[i] = (float)h.w2[i];
+            }
+            for (int i = 0; i < 4; i++) d.qrel[i] = (float)h.qrel[i];
+            fill_limot(d.limot1, h.limot1);
+            fill_limot(d.limot2, h.limot2);
+            d.c0 = (float)h.c0;
+            d.s0 = (float)h.s0;
+            d.susp_erp = (float)h.susp_erp;
+            d.susp_cfm = (float)h.susp_cfm;
+            d.erp = (float)h.erp;
+            d.cfm = (float)h.cfm;
+            if (h.type != B2P_JOINT_FIXED && limot_has_stops(h.limot1)) T->has_limit_motors = 1;
+            if (h.b[0] >= 0 && h.b[1] >= 0) {
+                T->connected[h.b[0]] |= 1u << h.b[1];
+                T->connected[h.b[1]] |= 1u << h.b[0];
+            }
+        }
+        for (int g = 0; g < ng; g++) {
+            const HGeom &h = a->geoms[g];
+            DevGeom &d = T->geoms[g];
+            d.cls = h.cls;
+            d.body = h.body;
+            for (int i = 0; i < 4; i++) {
+                d.dims[i] = (float)h.dims[i];
+                d.lquat[i] = (float)h.lquat[i];
+            }
+            for (int i = 0; i < 3; i++) d.lpos[i] = (float)h.lpos[i];
+            d.has_offset = (h.lpos[0] != 0 || h.lpos[1] != 0 || h.lpos[2] != 0 || h.lquat[0] != 1);
+            d.mu = (float)h.s.mu;
+            d.mu2 = (float)h.s.mu2;
+            d.rho = (float)h.s.rho;
+            d.rho2 = (float)h.s.rho2;
+            d.rhoN = (float)h.s.rhoN;
+            d.soft_erp = (float)h.s.soft_erp;
+            d.soft_cfm = (float)h.s.soft_cfm;
+        }
+        if (a->has_hf) {
+            if (!a->d_hf) {
+                CUDA_TRY(cudaMalloc(&a->d_hf, sizeof(float) * a->hf_heights.size()));
+                CUDA_TRY(cudaMemcpyAsync(a->d_hf, a->hf_heights.data(), sizeof(float) * a->hf_heights.size(),
+                                         cudaMemcpyHostToDevice, a->stream));
+            }
+            T->hf.heights = a->d_hf;
+            T->hf.nx = a->hf_nx;
+            T->hf.ny = a->hf_ny;
+            T->hf.dx = (float)a->hf_dx;
+            T->hf.x0 = (float)a->hf_x0;
+            T->hf.y0 = (float)a->hf_y0;
+            float mn = 1e30f, mx = -1e30f;
+            for (float v : a->hf_heights) {
+                mn = std::min(mn, v);
+                mx = std::max(mx, v);
+            }
+            T->hf.hmin = mn;
+            T->hf.hmax = mx;
+        }
+        if (!a->dT) CUDA_TRY(cudaMalloc(&a->dT, sizeof(DevTemplate)));
+        CUDA_TRY(cudaMemcpyAsync(a->dT, T, sizeof(DevTemplate), cudaMemcpyHostToDevice, a->stream));
+        CUDA_TRY(cudaStreamSynchronize(a->stream)); // buf goes out of scope
+        a->tmpl_dirty = false;
+    }
+    int rc;
+    if ((rc = mirror_resize(a, a->crec, (size_t)a->maxc * B2P_CONTACT_FIELDS, 0.f))) return rc;
+    if ((rc = mirror_resize(a, a->cfb, (size_t)a->maxc * 3, 0.f))) return rc;
+    if ((rc = mirror_resize(a, a->ccount, 1, 0))) return rc;
+    if ((rc = mirror_resize(a, a->nrows, 1, 0))) return rc;
+    if ((rc = mirror_resize(a, a->jobs, (size_t)nj * 4, 0.f))) return rc;
+    if ((rc = mirror_resize(a, a->jfb, (size_t)nj * 13, 0.f))) return rc;
+    if ((rc = mirror_resize(a, a->jrows, (size_t)nj, (uint8_t)0))) return rc;
+    if ((rc = mirror_to_device(a, a->state))) return rc;
+    if ((rc = mirror_to_device(a, a->force))) return rc;
+    if ((rc = mirror_to_device(a, a->jcmd))) return rc;
+    if ((rc = mirror_to_device(a, a->crec))) return rc;
+    if ((rc = mirror_to_device(a, a->ccount))) return rc;
+    if ((rc = mirror_to_device(a, a->seed))) return rc;
+    // outputs: make sure device buffers exist (content irrelevant)
+    if ((rc = mirror_to_device(a, a->jobs))) return rc;
+    if ((rc = mirror_to_device(a, a->jfb))) return rc;
+    if ((rc = mirror_to_device(a, a->cfb))) return rc;
+    if ((rc = mirror_to_device(a, a->nrows))) return rc;
+    if ((rc = mirror_to_device(a, a->jrows))) return rc;
+    if (a->scratch_rows != (size_t)maxrows || a->scratch_nb != (size_t)nb) {
+        if (a->d_rows) cudaFree(a->d_rows);
+        if (a->d_lambda) cudaFree(a->d_lambda);
+        if (a->d_rowad) cudaFree(a->d_rowad);
+        if (a->d_invIw) cudaFree(a->d_invIw);
+        a->d_rows = nullptr;
+        a->d_lambda = a->d_rowad = a->d_invIw = nullptr;
+        const size_t mr = (size_t)std::max(maxrows, 1), Wp = (size_t)a->Wp;
+        CUDA_TRY(cudaMalloc(&a->d_rows, sizeof(float4) * mr * 7 * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_lambda, sizeof(float) * mr * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_rowad, sizeof(float) * mr * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_invIw, sizeof(float) * (size_t)std::max(nb, 1) * 9 * Wp));
+        CUDA_TRY(cudaMemsetAsync(a->d_lambda, 0, sizeof(float) * mr * Wp, a->stream));
+        a->scratch_rows = (size_t)maxrows;
+        a->scratch_nb = (size_t)nb;
+    }
+    return 0;
+}
+
+// ---- creation-time joint geometry (ODE joint.cpp setAnchors / setAxes etc.) ----
+void set_anchors(b2p_arena *a, HJoint &j, double x, double y, double z)
+{
+    if (j.b[0] < 0) return;
+    const HBody &b0 = a->bodies[j.b[0]];
+    double R[9], q[3] = {x - b0.pos[0], y - b0.pos[1], z - b0.pos[2]};
+    q_to_R(b0.q, R);
+    Rtv(j.anchor1, R, q);
+    if (j.b[1] >= 0) {
+        const HBody &b1 = a->bodies[j.b[1]];
+        double q2[3] = {x - b1.pos[0], y - b1.pos[1], z - b1.pos[2]};
+        q_to_R(b1.q, R);
+        Rtv(j.anchor2, R, q2);
+    } else {
+        j.anchor2[0] = x, j.anchor2[1] = y, j.anchor2[2] = z;
+    }
+}
+void set_axes(b2p_arena *a, HJoint &j, double x, double y, double z, double *axis1, double *axis2)
+{
+    if (j.b[0] < 0) return;
+    double q[3] = {x, y, z}, R[9];
+    norm3(q);
+    if (axis1) {
+        q_to_R(a->bodies[j.b[0]].q, R);
+        Rtv(axis1, R, q);
+    }
+    if (axis2) {
+        if (j.b[1] >= 0) {
+            q_to_R(a->bodies[j.b[1]].q, R);
+            Rtv(axis2, R, q);
+        } else {
+            axis2[0] = q[0], axis2[1] = q[1], axis2[2] = q[2];
+        }
+    }
+}
+void initial_relative_rotation(b2p_arena *a, HJoint &j)
+{
+    if (j.b[0] < 0) return;
+    const HBody &b0 = a->bodies[j.b[0]];
+    if (j.b[1] >= 0) {
+        qmul1(j.qrel, b0.q, a->bodies[j.b[1]].q);
+    } else {
+        j.qrel[0] = b0.q[0];
+        for (int i = 1; i < 4; i++) j.qrel[i] = -b0.q[i];
+    }
+}
+void hinge2_axes_world(b2p_arena *a, const HJoint &j, double *ax1, double *ax2)
+{
+    double R[9];
+    q_to_R(a->bodies[j.b[0]].q, R);
+    Rv(ax1, R, j.axis1);
+    q_to_R(a->bodies[j.b[1]].q, R);
+    Rv(ax2, R, j.axis2);
+}
+void hinge2_axis_info(b2p_arena *a, HJoint &j)
+{
+    double ax1[3], ax2[3], ax[3];
+    hinge2_axes_world(a, j, ax1, ax2);
+    cross(ax, ax1, ax2);
+    j.s0 = std::sqrt(dot(ax, ax));
+    j.c0 = dot(ax1, ax2);
+}
+bool same3(const double *x, const double *y) { return x[0] == y[0] && x[1] == y[1] && x[2] == y[2]; }
+bool zero3(const double *x) { return x[0] == 0 && x[1] == 0 && x[2] == 0; }
+void hinge2_make_v(b2p_arena *a, HJoint &j)
+{
+    if (j.b[0] < 0 || j.b[1] < 0) return;
+    double ax1[3], ax2[3], v[3], R[9];
+    hinge2_axes_world(a, j, ax1, ax2);
+    if (zero3(ax1) || zero3(ax2) || same3(ax1, ax2)) return;
+    double k = dot(ax1, ax2);
+    for (int i = 0; i < 3; i++) ax2[i] -= k * ax1[i];
+    norm3(ax2);
+    cross(v, ax1, ax2);
+    q_to_R(a->bodies[j.b[0]].q, R);
+    Rtv(j.v1, R, ax2);
+    Rtv(j.v2, R, v);
+}
+void hinge2_make_w(b2p_arena *a, HJoint &j)
+{
+    if (j.b[0] < 0 || j.b[1] < 0) return;
+    double ax1[3], ax2[3], v[3], R[9];
+    hinge2_axes_world(a, j, ax1, ax2);
+    if (zero3(ax1) || zero3(ax2) || same3(ax1, ax2)) return;
+    double k = dot(ax2, ax1);
+    for (int i = 0; i < 3; i++) ax1[i] -= k * ax2[i];
+    norm3(ax1);
+    cross(v, ax2, ax1);
+    q_to_R(a->bodies[j.b[1]].q, R);
+    Rtv(j.w1, R, ax1);
+    Rtv(j.w2, R, v);
+}
+
+HLimot *limot_for(HJoint &j, int param, int *num)
+{
+    if ((param & 0xff00) == B2P_PARAM_GROUP2) {
+        *num = param & 0xff;
+        return &j.limot2;
+    }
+    *num = param;
+    return &j.limot1;
+}
+
+// ---- measurement of joint coordinates on the host (getters) ----
+double hinge_angle_host(const HJoint &j, const double *q0, const double *q1)
+{
+    double qrel[4];
+    if (j.b[1] >= 0) {
+        double qq[4];
+        qmul1(qq, q0, q1);
+        qmul2(qrel, qq, j.qrel);
+    } else {
+        qmul3(qrel, q0, j.qrel);
+    }
+    double cost2 = qrel[0], sint2 = std::sqrt(qrel[1] * qrel[1] + qrel[2] * qrel[2] + qrel[3] * qrel[3]);
+    double theta = (dot(qrel + 1, j.axis1) >= 0) ? 2 * std::atan2(sint2, cost2) : 2 * std::atan2(sint2, -cost2);
+    if (theta > M_PI) theta -= 2 * M_PI;
+    return -theta;
+}
+
+} // namespace
+
+// =====================================================================================
+extern "C" {
+
+const char *b2p_last_error(void) { return g_err.c_str(); }
+int b2p_version(void) { return 1; }
+
+int b2p_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int b2p_arena_create(int num_worlds, int device, b2p_arena **out)
+{
+    if (!out) return fail(B2P_EINVAL, "out is null");
+    *out = nullptr;
+    if (num_worlds <= 0) return fail(B2P_EINVAL, "num_worlds must be positive");
+    int n = b2p_device_count();
+    if (n <= 0) return fail(B2P_ENODEVICE, "no CUDA device: the batched step has no CPU fallback");
+    if (device < 0 || device >= n) return fail(B2P_EINVAL, "device %d out of range [0,%d)", device, n);
+    CUDA_TRY(cudaSetDevice(device));
+    b2p_arena *a = new b2p_arena();
+    a->W = num_worlds;
+    a->Wp = (num_worlds + 31) & ~31;
+    a->device = device;
+    a->seed.fields = 1;
+    a->seed.host.assign((size_t)a->Wp, 0u);
+    a->seed.host_newer = true;
+    *out = a;
+    return 0;
+}
+
+void b2p_arena_destroy(b2p_arena *a)
+{
+    if (!a) return;
+    cudaSetDevice(a->device);
+    cudaStreamSynchronize(a->stream);
+    mirror_free(a->state);
+    mirror_free(a->force);
+    mirror_free(a->jcmd);
+    mirror_free(a->jobs);
+    mirror_free(a->jfb);
+    mirror_free(a->crec);
+    mirror_free(a->cfb);
+    mirror_free(a->ccount);
+    mirror_free(a->nrows);
+    mirror_free(a->seed);
+    mirror_free(a->jrows);
+    if (a->d_rows) cudaFree(a->d_rows);
+    if (a->d_lambda) cudaFree(a->d_lambda);
+    if (a->d_rowad) cudaFree(a->d_rowad);
+    if (a->d_invIw) cudaFree(a->d_invIw);
+    if (a->dT) cudaFree(a->dT);
+    if (a->d_hf) cudaFree(a->d_hf);
+    if (a->d_pairs) cudaFree(a->d_pairs);
+    if (a->d_npairs) cudaFree(a->d_npairs);
+    delete a;
+}
+
+int b2p_arena_num_worlds(const b2p_arena *a) { return a ? a->W : 0; }
+int b2p_padded_worlds(const b2p_arena *a) { return a ? a->Wp : 0; }
+
+int b2p_arena_set_stream(b2p_arena *a, void *s)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    cudaStreamSynchronize(a->stream);
+    a->stream = (cudaStream_t)s;
+    return 0;
+}
+
+int b2p_arena_set_max_contacts(b2p_arena *a, int n)
+{
+    if (!a || n < 0) return fail(B2P_EINVAL, "bad max_contacts");
+    if (a->stepped) return fail(B2P_EINVAL, "max_contacts must be set before the first step");
+    a->maxc = n;
+    a->tmpl_dirty = true;
+    return 0;
+}
+
+int b2p_arena_enable_rolling_friction(b2p_arena *a, int on)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    if (a->stepped) return fail(B2P_EINVAL, "rolling friction must be selected before the first step");
+    a->rolling = on ? 1 : 0;
+    a->tmpl_dirty = true;
+    return 0;
+}
+
+int b2p_world_set_gravity(b2p_arena *a, double x, double y, double z)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    a->gravity[0] = x, a->gravity[1] = y, a->gravity[2] = z;
+    return 0;
+}
+int b2p_world_set_cfm(b2p_arena *a, double v) { return a ? (a->cfm = v, 0) : fail(B2P_EINVAL, "null arena"); }
+int b2p_world_set_erp(b2p_arena *a, double v) { return a ? (a->erp = v, 0) : fail(B2P_EINVAL, "null arena"); }
+int b2p_world_set_max_angular_speed(b2p_arena *a, double v)
+{
+    return a ? (a->max_ang = v, 0) : fail(B2P_EINVAL, "null arena");
+}
+int b2p_world_set_contact_max_correcting_vel(b2p_arena *a, double v)
+{
+    return a ? (a->contact_max_vel = v, 0) : fail(B2P_EINVAL, "null arena");
+}
+int b2p_world_set_contact_surface_layer(b2p_arena *a, double v)
+{
+    return a ? (a->min_depth = v, 0) : fail(B2P_EINVAL, "null arena");
+}
+int b2p_world_set_quickstep_num_iterations(b2p_arena *a, int n)
+{
+    if (!a || n < 0) return fail(B2P_EINVAL, "bad iteration count");
+    a->iters = n;
+    return 0;
+}
+int b2p_world_set_quickstep_w(b2p_arena *a, double v) { return a ? (a->sor_w = v, 0) : fail(B2P_EINVAL, "null arena"); }
+int b2p_world_set_reorder_method(b2p_arena *a, int m)
+{
+    if (!a || (m != B2P_REORDER_RANDOMLY && m != B2P_REORDER_NONE)) return fail(B2P_EINVAL, "bad reorder method");
+    a->reorder = m;
+    return 0;
+}
+int b2p_world_rand_set_seed(b2p_arena *a, uint32_t seed)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    a->seed.dev_newer = false;
+    mset(a, a->seed, 0, B2P_ALL_WORLDS, seed);
+    return 0;
+}
+int b2p_world_rand_get_seed(b2p_arena *a, int world, uint32_t *seed)
+{
+    int rc = check_world(a, world, false);
+    if (rc) return rc;
+    if ((rc = mirror_to_host(a, a->seed))) return rc;
+    *seed = a->seed.host[(size_t)world];
+    return 0;
+}
+
+// ---------------- bodies ----------------
+int b2p_body_create(b2p_arena *a)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    if ((int)a->bodies.size() >= B2P_MAX_BODIES) return fail(B2P_ECAPACITY, "too many bodies");
+    HBody b;
+    b.has_max_ang = a->max_ang < kInf; // inherited from the world at creation (dBodyCreate)
+    b.max_angular_speed = a->max_ang;
+    a->bodies.push_back(b);
+    const int id = (int)a->bodies.size() - 1;
+    int rc;
+    if ((rc = mirror_resize(a, a->state, (size_t)(id + 1) * B2P_STATE_FIELDS, 0.f))) return rc;
+    if ((rc = mirror_resize(a, a->force, (size_t)(id + 1) * 6, 0.f))) return rc;
+    mset(a, a->state, (size_t)id * B2P_STATE_FIELDS + 3, B2P_ALL_WORLDS, 1.0f);
+    // padded lanes get a valid quaternion too
+    for (int w = a->W; w < a->Wp; w++) a->state.host[((size_t)id * B2P_STATE_FIELDS + 3) * a->Wp + w] = 1.0f;
+    a->tmpl_dirty = true;
+    return id;
+}
+
+int b2p_body_set_mass(b2p_arena *a, int body, double mass, const double I[9])
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    if (!(mass > 0)) return fail(B2P_EINVAL, "mass must be positive");
+    HBody &b = a->bodies[body];
+    b.mass = mass;
+    memcpy(b.I, I, sizeof(b.I));
+    if (!invert33(b.invI, b.I)) return fail(B2P_EINVAL, "inertia tensor is singular");
+    a->tmpl_dirty = true;
+    return 0;
+}
+
+static int set3(b2p_arena *a, Mirror<float> &m, size_t field0, int body, int world, double x, double y, double z,
+                bool add)
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, true))) return rc;
+    if ((rc = mirror_to_host(a, m))) return rc;
+    const double v[3] = {x, y, z};
+    for (int i = 0; i < 3; i++) {
+        float *row = m.host.data() + (field0 + i) * (size_t)a->Wp;
+        if (world == B2P_ALL_WORLDS) {
+            for (int w = 0; w < a->W; w++) row[w] = add ? row[w] + (float)v[i] : (float)v[i];
+        } else {
+            row[world] = add ? row[world] + (float)v[i] : (float)v[i];
+        }
+    }
+    m.host_newer = true;
+    return 0;
+}
+
+int b2p_body_set_position(b2p_arena *a, int body, int world, double x, double y, double z)
+{
+    int rc = set3(a, a->state, (size_t)body * B2P_STATE_FIELDS + 0, body, world, x, y, z, false);
+    if (rc) return rc;
+    if (world == B2P_ALL_WORLDS || world == 0) {
+        HBody &b = a->bodies[body];
+        b.pos[0] = x, b.pos[1] = y, b.pos[2] = z;
+    }
+    return 0;
+}
+
+int b2p_body_set_quaternion(b2p_arena *a, int body, int world, double qw, double qx, double qy, double qz)
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, true))) return rc;
+    if ((rc = mirror_to_host(a, a->state))) return rc;
+    double q[4] = {qw, qx, qy, qz};
+    norm4(q); // dBodySetQuaternion normalises
+    for (int i = 0; i < 4; i++) mset(a, a->state, (size_t)body * B2P_STATE_FIELDS + 3 + i, world, (float)q[i]);
+    if (world == B2P_ALL_WORLDS || world == 0) memcpy(a->bodies[body].q, q, sizeof(q));
+    return 0;
+}
+
+int b2p_body_set_linear_vel(b2p_arena *a, int body, int world, double x, double y, double z)
+{
+    return set3(a, a->state, (size_t)body * B2P_STATE_FIELDS + 7, body, world, x, y, z, false);
+}
+int b2p_body_set_angular_vel(b2p_arena *a, int body, int world, double x, double y, double z)
+{
+    return set3(a, a->state, (size_t)body * B2P_STATE_FIELDS + 10, body, world, x, y, z, false);
+}
+int b2p_body_set_force(b2p_arena *a, int body, int world, double x, double y, double z)
+{
+    return set3(a, a->force, (size_t)body * 6 + 0, body, world, x, y, z, false);
+}
+int b2p_body_set_torque(b2p_arena *a, int body, int world, double x, double y, double z)
+{
+    return set3(a, a->force, (size_t)body * 6 + 3, body, world, x, y, z, false);
+}
+int b2p_body_add_force(b2p_arena *a, int body, int world, double x, double y, double z)
+{
+    return set3(a, a->force, (size_t)body * 6 + 0, body, world, x, y, z, true);
+}
+int b2p_body_add_torque(b2p_arena *a, int body, int world, double x, double y, double z)
+{
+    return set3(a, a->force, (size_t)body * 6 + 3, body, world, x, y, z, true);
+}
+int b2p_body_add_force_at_pos(b2p_arena *a, int body, int world, double fx, double fy, double fz, double px,
+                              double py, double pz)
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, true))) return rc;
+    const int w0 = world == B2P_ALL_WORLDS ? 0 : world, w1 = world == B2P_ALL_WORLDS ? a->W : world + 1;
+    for (int w = w0; w < w1; w++) {
+        double pos[3], q[4];
+        if ((rc = body_pose(a, body, w, pos, q))) return rc;
+        const double f[3] = {fx, fy, fz}, r[3] = {px - pos[0], py - pos[1], pz - pos[2]};
+        double t[3];
+        cross(t, r, f);
+        if ((rc = set3(a, a->force, (size_t)body * 6 + 0, body, w, f[0], f[1], f[2], true))) return rc;
+        if ((rc = set3(a, a->force, (size_t)body * 6 + 3, body, w, t[0], t[1], t[2], true))) return rc;
+    }
+    return 0;
+}
+int b2p_body_set_gravity_mode(b2p_arena *a, int body, int on)
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    a->bodies[body].nogravity = !on;
+    a->tmpl_dirty = true;
+    return 0;
+}
+int b2p_body_set_gyroscopic_mode(b2p_arena *a, int body, int on)
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    a->bodies[body].gyroscopic = on ? 1 : 0;
+    a->tmpl_dirty = true;
+    return 0;
+}
+
+static int get_n(b2p_arena *a, Mirror<float> &m, size_t field0, int body, int world, int n, double *out)
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    return body_vec(a, m, field0, world, n, out);
+}
+int b2p_body_get_position(b2p_arena *a, int body, int world, double out[3])
+{
+    return get_n(a, a->state, (size_t)body * B2P_STATE_FIELDS + 0, body, world, 3, out);
+}
+int b2p_body_get_quaternion(b2p_arena *a, int body, int world, double out[4])
+{
+    return get_n(a, a->state, (size_t)body * B2P_STATE_FIELDS + 3, body, world, 4, out);
+}
+int b2p_body_get_rotation(b2p_arena *a, int body, int world, double out[9])
+{
+    double q[4];
+    int rc = b2p_body_get_quaternion(a, body, world, q);
+    if (rc) return rc;
+    q_to_R(q, out);
+    return 0;
+}
+int b2p_body_get_linear_vel(b2p_arena *a, int body, int world, double out[3])
+{
+    return get_n(a, a->state, (size_t)body * B2P_STATE_FIELDS + 7, body, world, 3, out);
+}
+int b2p_body_get_angular_vel(b2p_arena *a, int body, int world, double out[3])
+{
+    return get_n(a, a->state, (size_t)body * B2P_STATE_FIELDS + 10, body, world, 3, out);
+}
+int b2p_body_get_force(b2p_arena *a, int body, int world, double out[3])
+{
+    return get_n(a, a->force, (size_t)body * 6 + 0, body, world, 3, out);
+}
+int b2p_body_get_torque(b2p_arena *a, int body, int world, double out[3])
+{
+    return get_n(a, a->force, (size_t)body * 6 + 3, body, world, 3, out);
+}
+int b2p_body_get_state(b2p_arena *a, int body, int world, double out[13])
+{
+    return get_n(a, a->state, (size_t)body * B2P_STATE_FIELDS, body, world, 13, out);
+}
+int b2p_body_set_state(b2p_arena *a, int body, int world, const double in[13])
+{
+    int rc;
+    if ((rc = b2p_body_set_position(a, body, world, in[0], in[1], in[2]))) return rc;
+    if ((rc = b2p_body_set_quaternion(a, body, world, in[3], in[4], in[5], in[6]))) return rc;
+    if ((rc = b2p_body_set_linear_vel(a, body, world, in[7], in[8], in[9]))) return rc;
+    return b2p_body_set_angular_vel(a, body, world, in[10], in[11], in[12]);
+}
+
+int b2p_state_upload(b2p_arena *a, const float *host_state)
+{
+    if (!a || !host_state) return fail(B2P_EINVAL, "null argument");
+    const size_t nf = a->bodies.size() * B2P_STATE_FIELDS;
+    int rc = mirror_to_device(a, a->state); // allocates
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(a->state.dev, sizeof(float) * a->Wp, host_state, sizeof(float) * a->W,
+                               sizeof(float) * a->W, nf, cudaMemcpyHostToDevice, a->stream));
+    a->state.dev_newer = true;
+    a->state.host_newer = false;
+    return 0;
+}
+
+int b2p_state_download(b2p_arena *a, float *host_state)
+{
+    if (!a || !host_state) return fail(B2P_EINVAL, "null argument");
+    const size_t nf = a->bodies.size() * B2P_STATE_FIELDS;
+    int rc = mirror_to_device(a, a->state);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(host_state, sizeof(float) * a->W, a->state.dev, sizeof(float) * a->Wp,
+                               sizeof(float) * a->W, nf, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    return 0;
+}
+
+void *b2p_device_state(b2p_arena *a) { return a ? a->state.dev : nullptr; }
+void *b2p_device_joint_cmd(b2p_arena *a) { return a ? a->jcmd.dev : nullptr; }
+void *b2p_device_joint_obs(b2p_arena *a) { return a ? a->jobs.dev : nullptr; }
+
+// ---------------- joints ----------------
+int b2p_joint_create(b2p_arena *a, int type, int body1, int body2)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    if (type != B2P_JOINT_HINGE && type != B2P_JOINT_HINGE2 && type != B2P_JOINT_SLIDER && type != B2P_JOINT_FIXED)
+        return fail(B2P_EUNSUPPORTED, "joint type %d is not supported", type);
+    if (body1 >= (int)a->bodies.size() || body2 >= (int)a->bodies.size() || body1 < -1 || body2 < -1)
+        return fail(B2P_EINVAL, "joint body id out of range");
+    if (type == B2P_JOINT_HINGE2 && (body1 < 0 || body2 < 0))
+        return fail(B2P_EINVAL, "a hinge2 joint needs two bodies");
+    if ((int)a->joints.size() >= B2P_MAX_JOINTS) return fail(B2P_ECAPACITY, "too many joints");
+    HJoint j;
+    j.type = type;
+    if (body1 < 0 && body2 >= 0) { // dJointAttach: swap and flag dJOINT_REVERSE
+        j.b[0] = body2;
+        j.b[1] = -1;
+        j.reverse = 1;
+    } else {
+        j.b[0] = body1;
+        j.b[1] = body2;
+    }
+    HLimot l;
+    l.normal_cfm = a->cfm;
+    l.stop_erp = a->erp;
+    l.stop_cfm = a->cfm;
+    j.limot1 = j.limot2 = l;
+    j.erp = a->erp;
+    j.cfm = a->cfm;
+    j.susp_erp = a->erp;
+    j.susp_cfm = a->cfm;
+    if (type == B2P_JOINT_HINGE2) {
+        j.axis2[0] = 0;
+        j.axis2[1] = 1;
+    }
+    a->joints.push_back(j);
+    const int id = (int)a->joints.size() - 1;
+    int rc = mirror_resize(a, a->jcmd, (size_t)(id + 1) * 4, 0.f);
+    if (rc) return rc;
+    a->tmpl_dirty = true;
+    return id;
+}
+
+int b2p_joint_set_anchor(b2p_arena *a, int ji, double x, double y, double z)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    HJoint &j = a->joints[ji];
+    if (j.type == B2P_JOINT_HINGE) {
+        set_anchors(a, j, x, y, z);
+        initial_relative_rotation(a, j);
+    } else if (j.type == B2P_JOINT_HINGE2) {
+        set_anchors(a, j, x, y, z);
+        hinge2_make_v(a, j);
+        hinge2_make_w(a, j);
+    }
+    a->tmpl_dirty = true;
+    return 0;
+}
+
+int b2p_joint_set_axis1(b2p_arena *a, int ji, double x, double y, double z)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    HJoint &j = a->joints[ji];
+    if (j.type == B2P_JOINT_HINGE) {
+        set_axes(a, j, x, y, z, j.axis1, j.axis2);
+        initial_relative_rotation(a, j);
+    } else if (j.type == B2P_JOINT_SLIDER) {
+        set_axes(a, j, x, y, z, j.axis1, nullptr);
+        // computeOffset
+        if (j.b[1] >= 0) {
+            const HBody &b0 = a->bodies[j.b[0]], &b1 = a->bodies[j.b[1]];
+            double c[3] = {b0.pos[0] - b1.pos[0], b0.pos[1] - b1.pos[1], b0.pos[2] - b1.pos[2]}, R[9];
+            q_to_R(b1.q, R);
+            Rtv(j.offset, R, c);
+        } else if (j.b[0] >= 0) {
+            memcpy(j.offset, a->bodies[j.b[0]].pos, sizeof(j.offset));
+        }
+        initial_relative_rotation(a, j);
+    } else if (j.type == B2P_JOINT_HINGE2) {
+        set_axes(a, j, x, y, z, j.axis1, nullptr);
+        hinge2_axis_info(a, j);
+        hinge2_make_v(a, j);
+        hinge2_make_w(a, j);
+    }
+    a->tmpl_dirty = true;
+    return 0;
+}
+
+int b2p_joint_set_axis2(b2p_arena *a, int ji, double x, double y, double z)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    HJoint &j = a->joints[ji];
+    if (j.type == B2P_JOINT_HINGE2) {
+        set_axes(a, j, x, y, z, nullptr, j.axis2);
+        hinge2_axis_info(a, j);
+        hinge2_make_v(a, j);
+        hinge2_make_w(a, j);
+        a->tmpl_dirty = true;
+    }
+    return 0;
+}
+
+int b2p_joint_set_fixed(b2p_arena *a, int ji)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    HJoint &j = a->joints[ji];
+    if (j.b[0] < 0) return 0;
+    const HBody &b0 = a->bodies[j.b[0]];
+    if (j.b[1] >= 0) {
+        const HBody &b1 = a->bodies[j.b[1]];
+        double ofs[3] = {b0.pos[0] - b1.pos[0], b0.pos[1] - b1.pos[1], b0.pos[2] - b1.pos[2]}, R[9];
+        q_to_R(b0.q, R);
+        Rtv(j.offset, R, ofs);
+    } else {
+        memcpy(j.offset, b0.pos, sizeof(j.offset));
+    }
+    initial_relative_rotation(a, j);
+    a->tmpl_dirty = true;
+    return 0;
+}
+
+int b2p_joint_set_param(b2p_arena *a, int ji, int world, int param, double value)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, true))) return rc;
+    HJoint &j = a->joints[ji];
+    if (j.type == B2P_JOINT_FIXED) {
+        if (param == B2P_PARAM_CFM) j.cfm = value;
+        else if (param == B2P_PARAM_ERP) j.erp = value;
+        a->tmpl_dirty = true;
+        return 0;
+    }
+    if (param == B2P_PARAM_SUSPENSION_ERP || param == B2P_PARAM_SUSPENSION_CFM) {
+        (param == B2P_PARAM_SUSPENSION_ERP ? j.susp_erp : j.susp_cfm) = value;
+        a->tmpl_dirty = true;
+        return 0;
+    }
+    int num;
+    HLimot *l = limot_for(j, param, &num);
+    const int axis = (l == &j.limot2) ? 1 : 0;
+    if (num == B2P_PARAM_VEL || num == B2P_PARAM_FMAX) {
+        if (num == B2P_PARAM_FMAX && value < 0) return 0; // ODE ignores negative fmax
+        if ((rc = mirror_to_host(a, a->jcmd))) return rc;
+        mset(a, a->jcmd, (size_t)ji * 4 + axis * 2 + (num == B2P_PARAM_FMAX ? 1 : 0), world, (float)value);
+        if (world == B2P_ALL_WORLDS || world == 0) (num == B2P_PARAM_VEL ? l->vel : l->fmax) = value;
+        return 0;
+    }
+    if (world != B2P_ALL_WORLDS && a->W > 1)
+        return fail(B2P_EUNSUPPORTED, "only VEL and FMAX can differ between worlds; use B2P_ALL_WORLDS");
+    switch (num) {
+    case B2P_PARAM_LO_STOP: l->lostop = value; break;
+    case B2P_PARAM_HI_STOP: l->histop = value; break;
+    case B2P_PARAM_FUDGE_FACTOR:
+        if (value >= 0 && value <= 1) l->fudge = value;
+        break;
+    case B2P_PARAM_BOUNCE:
+        if (value != 0) return fail(B2P_EUNSUPPORTED, "dParamBounce is not supported by the device path");
+        break;
+    case B2P_PARAM_CFM: l->normal_cfm = value; break;
+    case B2P_PARAM_STOP_ERP: l->stop_erp = value; break;
+    case B2P_PARAM_STOP_CFM: l->stop_cfm = value; break;
+    default: break;
+    }
+    a->tmpl_dirty = true;
+    return 0;
+}
+
+int b2p_joint_get_param(b2p_arena *a, int ji, int world, int param, double *value)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if (world == B2P_ALL_WORLDS) world = 0;
+    if ((rc = check_world(a, world, false))) return rc;
+    HJoint &j = a->joints[ji];
+    *value = 0;
+    if (j.type == B2P_JOINT_FIXED) {
+        if (param == B2P_PARAM_CFM) *value = j.cfm;
+        if (param == B2P_PARAM_ERP) *value = j.erp;
+        return 0;
+    }
+    if (param == B2P_PARAM_SUSPENSION_ERP) return *value = j.susp_erp, 0;
+    if (param == B2P_PARAM_SUSPENSION_CFM) return *value = j.susp_cfm, 0;
+    int num;
+    HLimot *l = limot_for(j, param, &num);
+    const int axis = (l == &j.limot2) ? 1 : 0;
+    switch (num) {
+    case B2P_PARAM_VEL:
+    case B2P_PARAM_FMAX:
+        if ((rc = mirror_to_host(a, a->jcmd))) return rc;
+        *value = a->jcmd.host[((size_t)ji * 4 + axis * 2 + (num == B2P_PARAM_FMAX ? 1 : 0)) * a->Wp + world];
+        break;
+    case B2P_PARAM_LO_STOP: *value = l->lostop; break;
+    case B2P_PARAM_HI_STOP: *value = l->histop; break;
+    case B2P_PARAM_FUDGE_FACTOR: *value = l->fudge; break;
+    case B2P_PARAM_BOUNCE: *value = l->bounce; break;
+    case B2P_PARAM_CFM: *value = l->normal_cfm; break;
+    case B2P_PARAM_STOP_ERP: *value = l->stop_erp; break;
+    case B2P_PARAM_STOP_CFM: *value = l->stop_cfm; break;
+    default: break;
+    }
+    return 0;
+}
+
+int b2p_joint_set_param_batch(b2p_arena *a, int ji, int param, const float *values)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if (!values) return fail(B2P_EINVAL, "values is null");
+    const int num = param & 0xff, axis = ((param & 0xff00) == B2P_PARAM_GROUP2) ? 1 : 0;
+    if (num != B2P_PARAM_VEL && num != B2P_PARAM_FMAX)
+        return fail(B2P_EUNSUPPORTED, "only VEL and FMAX can be set per world");
+    if ((rc = mirror_to_device(a, a->jcmd))) return rc; // device copy current
+    const size_t field = (size_t)ji * 4 + axis * 2 + (num == B2P_PARAM_FMAX ? 1 : 0);
+    CUDA_TRY(cudaMemcpyAsync(a->jcmd.dev + field * a->Wp, values, sizeof(float) * a->W, cudaMemcpyHostToDevice,
+                             a->stream));
+    a->jcmd.dev_newer = true;
+    return 0;
+}
+
+static int joint_poses(b2p_arena *a, const HJoint &j, int world, double *p0, double *q0, double *p1, double *q1)
+{
+    int rc;
+    if (j.b[0] >= 0 && (rc = body_pose(a, j.b[0], world, p0, q0))) return rc;
+    if (j.b[1] >= 0 && (rc = body_pose(a, j.b[1], world, p1, q1))) return rc;
+    return 0;
+}
+
+int b2p_joint_get_anchor(b2p_arena *a, int ji, int world, double out[3])
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    const HJoint &j = a->joints[ji];
+    out[0] = out[1] = out[2] = 0;
+    if (j.b[0] < 0) return 0;
+    double p0[3], q0[4], p1[3], q1[4], R[9];
+    if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
+    q_to_R(q0, R);
+    Rv(out, R, j.anchor1);
+    for (int i = 0; i < 3; i++) out[i] += p0[i];
+    return 0;
+}
+
+int b2p_joint_get_anchor2(b2p_arena *a, int ji, int world, double out[3])
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    const HJoint &j = a->joints[ji];
+    memcpy(out, j.anchor2, 3 * sizeof(double));
+    if (j.b[1] < 0) return 0;
+    double p0[3], q0[4], p1[3], q1[4], R[9];
+    if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
+    q_to_R(q1, R);
+    Rv(out, R, j.anchor2);
+    for (int i = 0; i < 3; i++) out[i] += p1[i];
+    return 0;
+}
+
+int b2p_joint_get_axis1(b2p_arena *a, int ji, int world, double out[3])
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    const HJoint &j = a->joints[ji];
+    out[0] = out[1] = out[2] = 0;
+    if (j.b[0] < 0) return 0;
+    double p0[3], q0[4], p1[3], q1[4], R[9];
+    if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
+    q_to_R(q0, R);
+    Rv(out, R, j.axis1);
+    if (j.type == B2P_JOINT_SLIDER && j.reverse)
+        for (int i = 0; i < 3; i++) out[i] = -out[i];
+    return 0;
+}
+
+int b2p_joint_get_axis2(b2p_arena *a, int ji, int world, double out[3])
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    const HJoint &j = a->joints[ji];
+    out[0] = out[1] = out[2] = 0;
+    if (j.b[1] < 0) return 0;
+    double p0[3], q0[4], p1[3], q1[4], R[9];
+    if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
+    q_to_R(q1, R);
+    Rv(out, R, j.axis2);
+    return 0;
+}
+
+int b2p_joint_get_angle1(b2p_arena *a, int ji, int world, double *out)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    const HJoint &j = a->joints[ji];
+    *out = 0;
+    if (j.b[0] < 0) return 0;
+    double p0[3], q0[4], p1[3] = {0, 0, 0}, q1[4] = {1, 0, 0, 0}, R0[9], R1[9];
+    if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
+    q_to_R(q0, R0);
+    q_to_R(q1, R1);
+    if (j.type == B2P_JOINT_HINGE) {
+        double ang = hinge_angle_host(j, q0, q1);
+        *out = j.reverse ? -ang : ang;
+    } else if (j.type == B2P_JOINT_SLIDER) {
+        double ax1[3], q[3];
+        Rv(ax1, R0, j.axis1);
+        if (j.b[1] >= 0) {
+            Rv(q, R1, j.offset);
+            for (int i = 0; i < 3; i++) q[i] = p0[i] - q[i] - p1[i];
+        } else {
+            for (int i = 0; i < 3; i++) q[i] = p0[i] - j.offset[i];
+            if (j.reverse)
+                for (int i = 0; i < 3; i++) ax1[i] = -ax1[i];
+        }
+        *out = dot(ax1, q);
+    } else if (j.type == B2P_JOINT_HINGE2) {
+        double p[3], q[3];
+        Rv(p, R1, j.axis2);
+        Rtv(q, R0, p);
+        *out = -std::atan2(dot(j.v2, q), dot(j.v1, q));
+    }
+    return 0;
+}
+
+int b2p_joint_get_angle1_rate(b2p_arena *a, int ji, int world, double *out)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    const HJoint &j = a->joints[ji];
+    *out = 0;
+    if (j.b[0] < 0 || j.type == B2P_JOINT_FIXED) return 0;
+    double p0[3], q0[4], p1[3], q1[4], R0[9], axis[3], lv0[3], av0[3], lv1[3] = {0, 0, 0}, av1[3] = {0, 0, 0};
+    if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
+    q_to_R(q0, R0);
+    Rv(axis, R0, j.axis1);
+    b2p_body_get_linear_vel(a, j.b[0], world, lv0);
+    b2p_body_get_angular_vel(a, j.b[0], world, av0);
+    if (j.b[1] >= 0) {
+        b2p_body_get_linear_vel(a, j.b[1], world, lv1);
+        b2p_body_get_angular_vel(a, j.b[1], world, av1);
+    }
+    if (j.type == B2P_JOINT_HINGE || j.type == B2P_JOINT_HINGE2) {
+        double rate = dot(axis, av0);
+        if (j.b[1] >= 0) rate -= dot(axis, av1);
+        if (j.type == B2P_JOINT_HINGE && j.reverse) rate = -rate;
+        *out = rate;
+    } else if (j.type == B2P_JOINT_SLIDER) {
+        if (j.b[1] >= 0) {
+            *out = dot(axis, lv0) - dot(axis, lv1);
+        } else {
+            double rate = dot(axis, lv0);
+            *out = j.reverse ? -rate : rate;
+        }
+    }
+    return 0;
+}
+
+int b2p_joint_get_angle2(b2p_arena *a, int ji, int world, double *out)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    const HJoint &j = a->joints[ji];
+    *out = 0;
+    if (j.type != B2P_JOINT_HINGE2) return 0;
+    double p0[3], q0[4], p1[3], q1[4], R0[9], R1[9], p[3], q[3];
+    if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
+    q_to_R(q0, R0);
+    q_to_R(q1, R1);
+    Rv(p, R0, j.axis1);
+    Rtv(q, R1, p);
+    *out = -std::atan2(dot(j.w2, q), dot(j.w1, q));
+    return 0;
+}
+
+int b2p_joint_get_angle2_rate(b2p_arena *a, int ji, int world, double *out)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    const HJoint &j = a->joints[ji];
+    *out = 0;
+    if (j.type != B2P_JOINT_HINGE2) return 0;
+    double p0[3], q0[4], p1[3], q1[4], R1[9], axis[3], av0[3], av1[3];
+    if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
+    q_to_R(q1, R1);
+    Rv(axis, R1, j.axis2);
+    b2p_body_get_angular_vel(a, j.b[0], world, av0);
+    b2p_body_get_angular_vel(a, j.b[1], world, av1);
+    *out = dot(axis, av0) - dot(axis, av1);
+    return 0;
+}
+
+int b2p_joint_add_torque(b2p_arena *a, int ji, int world, double t)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, true))) return rc;
+    const HJoint &j = a->joints[ji];
+    if (j.b[0] < 0) return 0;
+    if (j.type != B2P_JOINT_HINGE && j.type != B2P_JOINT_SLIDER)
+        return fail(B2P_EUNSUPPORTED, "add_torque is defined for hinge and slider joints");
+    const int w0 = world == B2P_ALL_WORLDS ? 0 : world, w1 = world == B2P_ALL_WORLDS ? a->W : world + 1;
+    for (int w = w0; w < w1; w++) {
+        double p0[3], q0[4], p1[3], q1[4], R0[9], axis[3];
+        if ((rc = joint_poses(a, j, w, p0, q0, p1, q1))) return rc;
+        q_to_R(q0, R0);
+        Rv(axis, R0, j.axis1);
+        const double torque = j.reverse ? -t : t;
+        for (int i = 0; i < 3; i++) axis[i] *= torque;
+        if (j.type == B2P_JOINT_HINGE) {
+            b2p_body_add_torque(a, j.b[0], w, axis[0], axis[1], axis[2]);
+            if (j.b[1] >= 0) b2p_body_add_torque(a, j.b[1], w, -axis[0], -axis[1], -axis[2]);
+        } else {
+            if (j.b[1] >= 0) {
+                double c[3], ltd[3];
+                for (int i = 0; i < 3; i++) c[i] = 0.5 * (p1[i] - p0[i]);
+                cross(ltd, c, axis);
+                b2p_body_add_torque(a, j.b[0], w, ltd[0], ltd[1], ltd[2]);
+                b2p_body_add_torque(a, j.b[1], w, ltd[0], ltd[1], ltd[2]);
+                b2p_body_add_force(a, j.b[1], w, -axis[0], -axis[1], -axis[2]);
+            }
+            b2p_body_add_force(a, j.b[0], w, axis[0], axis[1], axis[2]);
+        }
+    }
+    return 0;
+}
+
+int b2p_joint_get_feedback(b2p_arena *a, int ji, int world, double out[13])
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    for (int i = 0; i < 13; i++) out[i] = 0;
+    if (a->jfb.fields < (size_t)(ji + 1) * 13) return 0; // never stepped
+    return body_vec(a, a->jfb, (size_t)ji * 13, world, 13, out);
+}
+
+int b2p_joint_get_num_rows(b2p_arena *a, int ji, int world, int *rows)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    *rows = 0;
+    if (a->jrows.fields <= (size_t)ji) return 0;
+    if ((rc = mirror_to_host(a, a->jrows))) return rc;
+    *rows = a->jrows.host[(size_t)ji * a->Wp + world];
+    return 0;
+}
+
+int b2p_are_connected_excluding_contacts(b2p_arena *a, int b1, int b2)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    if (b1 < 0 || b2 < 0) return 0;
+    for (const HJoint &j : a->joints)
+        if ((j.b[0] == b1 && j.b[1] == b2) || (j.b[0] == b2 && j.b[1] == b1)) return 1;
+    return 0;
+}
+
+// ---------------- contacts ----------------
+static int ensure_contact_mirrors(b2p_arena *a)
+{
+    int rc;
+    if ((rc = mirror_resize(a, a->crec, (size_t)a->maxc * B2P_CONTACT_FIELDS, 0.f))) return rc;
+    if ((rc = mirror_resize(a, a->ccount, 1, 0))) return rc;
+    if ((rc = mirror_to_host(a, a->crec))) return rc;
+    return mirror_to_host(a, a->ccount);
+}
+
+int b2p_contacts_clear(b2p_arena *a, int world)
+{
+    int rc = check_world(a, world, true);
+    if (rc) return rc;
+    if ((rc = ensure_contact_mirrors(a))) return rc;
+    mset(a, a->ccount, 0, world, 0);
+    return 0;
+}
+
+int b2p_contact_add(b2p_arena *a, int world, int body1, int body2, const b2p_contact_desc *c)
+{
+    int rc = check_world(a, world, false);
+    if (rc) return rc;
+    if (!c) return fail(B2P_EINVAL, "contact is null");
+    const int nb = (int)a->bodies.size();
+    if (body1 >= nb || body2 >= nb || (body1 < 0 && body2 < 0)) return fail(B2P_EINVAL, "bad contact bodies");
+    if (body1 >= 0 && body2 >= 0 && b2p_are_connected_excluding_contacts(a, body1, body2))
+        return fail(B2P_EREJECTED, "bodies %d and %d are connected by a joint", body1, body2);
+    if ((c->mode & B2P_CONTACT_ROLLING) && !a->rolling)
+        return fail(B2P_EUNSUPPORTED, "rolling friction needs b2p_arena_enable_rolling_friction(1)");
+    if ((rc = ensure_contact_mirrors(a))) return rc;
+    int &n = a->ccount.host[(size_t)world];
+    if (n >= a->maxc) return fail(B2P_ECAPACITY, "contact capacity (%d) of world %d exhausted", a->maxc, world);
+    double sign = 1.0;
+    int b0 = body1, b1 = body2;
+    if (b0 < 0) { // dJointAttach swap + dJOINT_REVERSE: the normal is negated in getInfo2
+        b0 = body2;
+        b1 = -1;
+        sign = -1.0;
+    }
+    float rec[B2P_CONTACT_FIELDS];
+    const int ids = (b0 & 0xff) | ((b1 < 0 ? 0xff : b1) << 8);
+    memcpy(&rec[CR_IDS], &ids, 4);
+    for (int i = 0; i < 3; i++) {
+        rec[CR_PX + i] = (float)c->pos[i];
+        rec[CR_NX + i] = (float)(sign * c->normal[i]);
+    }
+    rec[CR_DEPTH] = (float)c->depth;
+    rec[CR_MU] = (float)c->mu;
+    rec[CR_MU2] = (float)c->mu2;
+    rec[CR_SOFT_ERP] = (float)c->soft_erp;
+    rec[CR_SOFT_CFM] = (float)c->soft_cfm;
+    rec[CR_RHO] = (float)c->rho;
+    rec[CR_RHO2] = (float)c->rho2;
+    rec[CR_RHON] = (float)c->rhoN;
+    memcpy(&rec[CR_MODE], &c->mode, 4);
+    for (int f = 0; f < B2P_CONTACT_FIELDS; f++)
+        a->crec.host[((size_t)n * B2P_CONTACT_FIELDS + f) * a->Wp + world] = rec[f];
+    a->crec.host_newer = true;
+    a->ccount.host_newer = true;
+    return n++;
+}
+
+int b2p_contact_count(b2p_arena *a, int world, int *count)
+{
+    int rc = check_world(a, world, false);
+    if (rc) return rc;
+    *count = 0;
+    if (a->ccount.fields == 0) return 0;
+    if ((rc = mirror_to_host(a, a->ccount))) return rc;
+    *count = a->ccount.host[(size_t)world];
+    return 0;
+}
+
+int b2p_contact_get_feedback(b2p_arena *a, int world, int contact, double f1[3])
+{
+    int rc = check_world(a, world, false);
+    if (rc) return rc;
+    f1[0] = f1[1] = f1[2] = 0;
+    if (contact < 0 || contact >= a->maxc) return fail(B2P_EINVAL, "contact id out of range");
+    if (a->cfb.fields == 0) return 0;
+    return body_vec(a, a->cfb, (size_t)contact * 3, world, 3, f1);
+}
+
+int b2p_contact_get(b2p_arena *a, int world, int contact, int *body1, int *body2, b2p_contact_desc *c)
+{
+    int rc = check_world(a, world, false);
+    if (rc) return rc;
+    if (contact < 0 || contact >= a->maxc || a->crec.fields == 0) return fail(B2P_EINVAL, "contact id out of range");
+    if ((rc = mirror_to_host(a, a->crec))) return rc;
+    float rec[B2P_CONTACT_FIELDS];
+    for (int f = 0; f < B2P_CONTACT_FIELDS; f++)
+        rec[f] = a->crec.host[((size_t)contact * B2P_CONTACT_FIELDS + f) * a->Wp + world];
+    int ids, mode;
+    memcpy(&ids, &rec[CR_IDS], 4);
+    memcpy(&mode, &rec[CR_MODE], 4);
+    if (body1) *body1 = ids & 0xff;
+    if (body2) *body2 = ((ids >> 8) & 0xff) == 0xff ? -1 : ((ids >> 8) & 0xff);
+    if (c) {
+        for (int i = 0; i < 3; i++) {
+            c->pos[i] = rec[CR_PX + i];
+            c->normal[i] = rec[CR_NX + i];
+        }
+        c->depth = rec[CR_DEPTH];
+        c->mode = mode;
+        c->mu = rec[CR_MU];
+        c->mu2 = rec[CR_MU2];
+        c->rho = rec[CR_RHO];
+        c->rho2 = rec[CR_RHO2];
+        c->rhoN = rec[CR_RHON];
+        c->soft_erp = rec[CR_SOFT_ERP];
+        c->soft_cfm = rec[CR_SOFT_CFM];
+    }
+    return 0;
+}
+
+// ---------------- geoms / collision ----------------
+int b2p_geom_create(b2p_arena *a, int cls, int body, const double dims[4], const double lpos[3],
+                    const double lquat[4], const b2p_surface *s)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    if (cls < B2P_GEOM_SPHERE || cls > B2P_GEOM_PLANE) return fail(B2P_EINVAL, "bad geom class %d", cls);
+    if (body >= (int)a->bodies.size() || body < -1) return fail(B2P_EINVAL, "bad geom body");
+    if (cls == B2P_GEOM_PLANE && body >= 0) return fail(B2P_EINVAL, "planes are static");
+    if ((int)a->geoms.size() >= B2P_MAX_GEOMS) return fail(B2P_ECAPACITY, "too many geoms");
+    HGeom g;
+    g.cls = cls;
+    g.body = body;
+    if (dims) memcpy(g.dims, dims, sizeof(g.dims));
+    if (lpos) memcpy(g.lpos, lpos, sizeof(g.lpos));
+    if (lquat) {
+        memcpy(g.lquat, lquat, sizeof(g.lquat));
+        norm4(g.lquat);
+    }
+    if (s) g.s = *s;
+    a->geoms.push_back(g);
+    a->tmpl_dirty = true;
+    return (int)a->geoms.size() - 1;
+}
+
+int b2p_geom_create_heightfield(b2p_arena *a, const float *heights, int nx, int ny, double dx, double x0, double y0,
+                                const b2p_surface *s)
+{
+    if (!a || !heights || nx < 2 || ny < 2 || !(dx > 0)) return fail(B2P_EINVAL, "bad heightfield");
+    if (a->has_hf) return fail(B2P_ECAPACITY, "one heightfield per arena");
+    if ((int)a->geoms.size() >= B2P_MAX_GEOMS) return fail(B2P_ECAPACITY, "too many geoms");
+    a->hf_heights.assign(heights, heights + (size_t)nx * ny);
+    a->hf_nx = nx;
+    a->hf_ny = ny;
+    a->hf_dx = dx;
+    a->hf_x0 = x0;
+    a->hf_y0 = y0;
+    a->has_hf = true;
+    HGeom g;
+    g.cls = B2P_GEOM_HEIGHTFIELD;
+    g.body = -1;
+    if (s) g.s = *s;
+    a->geoms.push_back(g);
+    a->tmpl_dirty = true;
+    return (int)a->geoms.size() - 1;
+}
+
+int b2p_collide(b2p_arena *a)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    CUDA_TRY(cudaSetDevice(a->device));
+    int rc = finalize(a);
+    if (rc) return rc;
+    const int ng = (int)a->geoms.size();
+    const int maxpairs = ng * (ng - 1) / 2;
+    if (maxpairs > a->maxpairs) {
+        if (a->d_pairs) cudaFree(a->d_pairs);
+        if (a->d_npairs) cudaFree(a->d_npairs);
+        a->d_pairs = a->d_npairs = nullptr;
+        CUDA_TRY(cudaMalloc(&a->d_pairs, sizeof(int) * (size_t)maxpairs * a->Wp));
+        CUDA_TRY(cudaMalloc(&a->d_npairs, sizeof(int) * (size_t)a->Wp));
+        a->maxpairs = maxpairs;
+    }
+    CollideParams P;
+    P.T = a->dT;
+    P.W = a->W;
+    P.Wp = a->Wp;
+    P.state = a->state.dev;
+    P.crec = a->crec.dev;
+    P.ccount = a->ccount.dev;
+    P.pairs = a->d_pairs;
+    P.npairs = a->d_npairs;
+    P.maxpairs = a->maxpairs;
+    CUDA_TRY(b2p_launch_collide(&P, a->stream));
+    a->launches++;
+    a->crec.dev_newer = true;
+    a->ccount.dev_newer = true;
+    a->crec.host_newer = false;
+    a->ccount.host_newer = false;
+    return 0;
+}
+
+int b2p_collide_get_pairs(b2p_arena *a, int world, int *pairs, int max_pairs)
+{
+    int rc = check_world(a, world, false);
+    if (rc) return rc;
+    if (!a->d_pairs) return 0;
+    std::vector<int> col((size_t)a->maxpairs);
+    int n = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n, a->d_npairs + world, sizeof(int), cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(col.data(), sizeof(int), a->d_pairs + world, sizeof(int) * a->Wp, sizeof(int),
+                               (size_t)a->maxpairs, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    if (n > a->maxpairs) n = a->maxpairs;
+    for (int i = 0; i < n && i < max_pairs; i++) pairs[i] = col[(size_t)i];
+    return n;
+}
+
+// ---------------- the step ----------------
+int b2p_step(b2p_arena *a, double step_size)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    if (!(step_size > 0)) return fail(B2P_EINVAL, "step size must be positive");
+    CUDA_TRY(cudaSetDevice(a->device));
+    int rc = finalize(a);
+    if (rc) return rc;
+    StepParams P;
+    memset(&P, 0, sizeof(P));
+    P.T = a->dT;
+    P.W = a->W;
+    P.Wp = a->Wp;
+    P.h = (float)step_size;
+    for (int i = 0; i < 3; i++) P.gravity[i] = (float)a->gravity[i];
+    P.erp = (float)a->erp;
+    P.cfm = (float)a->cfm;
+    P.contact_max_vel = (float)a->contact_max_vel;
+    P.contact_min_depth = (float)a->min_depth;
+    P.sor_w = (float)a->sor_w;
+    P.iters = a->iters;
+    P.reorder = a->reorder;
+    P.state = a->state.dev;
+    P.force = a->force.dev;
+    P.jcmd = a->jcmd.dev;
+    P.jobs = a->jobs.dev;
+    P.jfb = a->jfb.dev;
+    P.crec = a->crec.dev;
+    P.cfb = a->cfb.dev;
+    P.lambda = a->d_lambda;
+    P.rowad = a->d_rowad;
+    P.invIw = a->d_invIw;
+    P.rows = a->d_rows;
+    P.jrows = a->jrows.dev;
+    P.ccount = a->ccount.dev;
+    P.nrows = a->nrows.dev;
+    P.seed = a->seed.dev;
+    const size_t smem = b2p_step_smem_bytes((int)a->bodies.size(), (int)a->joints.size(), a->maxc, rpc_of(a));
+    if (smem > 227 * 1024) return fail(B2P_ECAPACITY, "scene needs %zu bytes of shared memory per CTA", smem);
+    CUDA_TRY(b2p_launch_step(&P, smem, a->stream));
+    a->launches++;
+    a->stepped = true;
+    a->state.dev_newer = true;
+    a->jobs.dev_newer = a->jfb.dev_newer = a->cfb.dev_newer = true;
+    a->nrows.dev_newer = a->seed.dev_newer = a->jrows.dev_newer = true;
+    // the step zeroes the force accumulators on the device (ODE: "zero all force accumulators")
+    std::fill(a->force.host.begin(), a->force.host.end(), 0.f);
+    a->force.host_newer = false;
+    a->force.dev_newer = false;
+    return 0;
+}
+
+int b2p_sync(b2p_arena *a)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    CUDA_TRY(cudaSetDevice(a->device));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    return 0;
+}
+
+int b2p_world_last_num_rows(b2p_arena *a, int world, int *rows)
+{
+    int rc = check_world(a, world, false);
+    if (rc) return rc;
+    *rows = 0;
+    if (a->nrows.fields == 0) return 0;
+    if ((rc = mirror_to_host(a, a->nrows))) return rc;
+    *rows = a->nrows.host[(size_t)world];
+    return 0;
+}
+
+int b2p_kernel_launch_count(const b2p_arena *a) { return a ? a->launches : 0; }
+
+// body 212 B, hinge 160 B, fixed 88 B, slider 132 B, hinge2 212 B,
+// contact 76 B (+128 B when the record was produced on the device), geom 48 B.
+double b2p_algorithmic_bytes_per_world_step(const b2p_arena *ca)
+{
+    b2p_arena *a = const_cast<b2p_arena *>(ca);
+    if (!a) return 0;
+    double bytes = 212.0 * a->bodies.size();
+    for (const HJoint &j : a->joints) {
+        switch (j.type) {
+        case B2P_JOINT_HINGE: bytes += 160; break;
+        case B2P_JOINT_FIXED: bytes += 88; break;
+        case B2P_JOINT_SLIDER: bytes += 132; break;
+        case B2P_JOINT_HINGE2: bytes += 212; break;
+        default: break;
+        }
+    }
+    double mean_contacts = 0;
+    if (a->ccount.fields && mirror_to_host(a, a->ccount) == 0) {
+        for (int w = 0; w < a->W; w++) mean_contacts += a->ccount.host[(size_t)w];
+        mean_contacts /= a->W;
+    }
+    const bool device_contacts = !a->geoms.empty();
+    bytes += mean_contacts * (76.0 + (device_contacts ? 128.0 : 0.0));
+    bytes += 48.0 * a->geoms.size();
+    return bytes;
+}
+
+} // extern "C"

@@ -1,0 +1,114 @@
+// b2p_dev.h -- structures shared by the host arena and the sm_100a kernels.
+//
+// Device memory layout (all per-world arrays are structure-of-arrays with the world index
+// fastest, padded to a multiple of 32 worlds = Wp, so that a warp of 32 consecutive worlds
+// touches one 128-byte line per field):
+//   state   float[nb*13][Wp]   pos3 quat4(w,x,y,z) lvel3 avel3   (dBody state)
+//   force   float[nb*6][Wp]    facc3 tacc3                        (dBodyAddForce accumulators)
+//   jcmd    float[nj*4][Wp]    vel1 fmax1 vel2 fmax2              (dParamVel / dParamFMax)
+//   jobs    float[nj*4][Wp]    angle1 rate1 angle2 rate2          (dJointGet*Angle / *Rate)
+//   jfb     float[nj*13][Wp]   f1 t1 f2 t2 lambda                 (dJointFeedback)
+//   jrows   uint8[nj][Wp]      rows used by each joint in the last step
+//   ccount  int[Wp]            contacts in the stream of each world
+//   crec    float[maxc*16][Wp] the 16-word contact record         (dContact subset)
+//   cfb     float[maxc*3][Wp]  contact feedback f1
+//   seed    uint32[Wp]         per-world LCG state                (dRandSetSeed)
+//   rows    float4[maxrows*7][Wp]  solver scratch: J(12) iMJ(12) rhs Adcfm lo hi
+//   lambda  float[maxrows][Wp], rowad float[maxrows][Wp], invIw float[nb*9][Wp]
+#pragma once
+#include <stdint.h>
+
+#define B2P_MAX_BODIES 32
+#define B2P_MAX_JOINTS 48
+#define B2P_MAX_GEOMS 48
+#define B2P_ROWS_PER_JOINT 6
+#define B2P_STATE_FIELDS 13
+#define B2P_CONTACT_FIELDS 16
+
+// contact record field indices
+enum {
+    CR_IDS = 0, // int: body0 | body1<<8 (0xFF = static)
+    CR_PX, CR_PY, CR_PZ,
+    CR_NX, CR_NY, CR_NZ,
+    CR_DEPTH,
+    CR_MU, CR_MU2,
+    CR_SOFT_ERP, CR_SOFT_CFM,
+    CR_RHO, CR_RHO2, CR_RHON,
+    CR_MODE // int
+};
+
+struct DevLimot {
+    float lostop, histop, fudge_factor, normal_cfm, stop_erp, stop_cfm, bounce;
+    float pad;
+};
+
+struct DevBody {
+    float mass, invMass;
+    float I[9];
+    float invI[9];
+    int gyroscopic, nogravity, has_max_ang;
+    float max_angular_speed;
+};
+
+struct DevJoint {
+    int type, b0, b1, reverse;
+    int slot_base; // first solver row slot
+    int pad0, pad1, pad2;
+    float anchor1[3], anchor2[3], axis1[3], axis2[3], qrel[4], offset[3];
+    DevLimot limot1, limot2;
+    float c0, s0, v1[3], v2[3], w1[3], w2[3], susp_erp, susp_cfm;
+    float erp, cfm; // fixed joint
+};
+
+struct DevGeom {
+    int cls, body; // body = -1: static
+    float dims[4]; // sphere r | box lx ly lz | capsule r len | cylinder r len | plane a b c d
+    float lpos[3], lquat[4];
+    int has_offset;
+    float mu, mu2, rho, rho2, rhoN, soft_erp, soft_cfm;
+};
+
+struct DevHeightfield {
+    const float *heights;
+    int nx, ny;
+    float dx, x0, y0;
+    float hmin, hmax;
+};
+
+struct DevTemplate {
+    int nb, nj, ng, maxc;
+    int rpc;     // rows per contact (3, or 6 with rolling friction)
+    int njslots; // nj * B2P_ROWS_PER_JOINT
+    int maxrows; // njslots + maxc*rpc
+    int has_limit_motors;
+    DevBody bodies[B2P_MAX_BODIES];
+    DevJoint joints[B2P_MAX_JOINTS];
+    DevGeom geoms[B2P_MAX_GEOMS];
+    uint32_t connected[B2P_MAX_BODIES]; // bit b set: joined to body b by a non-contact joint
+    DevHeightfield hf;
+};
+
+struct StepParams {
+    const DevTemplate *T;
+    int W, Wp;
+    float h;
+    float gravity[3];
+    float erp, cfm, contact_max_vel, contact_min_depth, sor_w;
+    int iters, reorder;
+    float *state, *force, *jcmd, *jobs, *jfb, *crec, *cfb, *lambda, *rowad, *invIw;
+    float4 *rows;
+    uint8_t *jrows;
+    int *ccount;
+    int *nrows;
+    uint32_t *seed;
+};
+
+struct CollideParams {
+    const DevTemplate *T;
+    int W, Wp;
+    float *state, *crec;
+    int *ccount;
+    int *pairs; // optional debug: int[maxpairs][Wp] packed g1 | g2<<16, or null
+    int *npairs;
+    int maxpairs;
+};

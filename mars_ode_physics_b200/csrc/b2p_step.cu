@@ -1,0 +1,1117 @@
+// b2p_step.cu -- the fused per-world step kernel for sm_100a.
+//
+// One thread owns one world (worlds are independent: reference src/WorldPhysics.hpp:99 gives each
+// WorldPhysics its own dWorldID), one warp owns 32 consecutive worlds, and every global access is
+// a world-fastest SoA access, i.e. one fully used 128-byte line per field per warp.
+//
+// What it computes is what dWorldQuickStep computes for the reference at
+// src/WorldPhysics.cpp:365 (ODE 0.16 quickstep: body preparation with implicit gyroscopic
+// torque, joint/contact constraint rows, SOR-LCP with ODE's row order and LCG shuffles,
+// velocity update, dxStepBody), followed by the per-joint feedback the reference reads in
+// Joint::update (src/joints/Joint.cpp:859-1019).
+//
+// Phases (all inside one launch so the row scratch written in phase 2 is still L2-resident when
+// phase 3 streams it `iters` times):
+//   1 bodies:   R(q), invI_world, gyroscopic torque, gravity; tmp1 = v/h + invM*fe -> smem
+//   2 rows:     per joint / per contact: J, c, cfm, lo, hi -> rhs, iMJ, Ad; scaled row -> gmem
+//   3 SOR:      order[] in smem (per world, so per-world contact counts and RNG states are
+//               allowed to differ); fc[] in smem, lane-interleaved => bank-conflict free for any
+//               per-lane body index
+//   4 epilogue: v += h*fc + h*invM*fe, clamp |w|, integrate pose, feedback, joint angles
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "b2p_dev.h"
+#include "b2p_math.cuh"
+
+namespace {
+
+constexpr int BD = 128; // threads (= worlds) per CTA
+
+struct Smem {
+    float *fc;     // [nb*6][BD]   fe -> tmp1 -> fc
+    uint8_t *ord;  // [maxrows][BD]
+    uint8_t *jm;   // [nj][BD]     rows of joint j in this world
+    int8_t *jl;    // [nj][BD]     local limot row feeding feedback.lambda, or -1
+    uint8_t *cm;   // [maxc][BD]   rows of contact c
+    uint16_t *cb;  // [maxc][BD]   body0 | body1<<8
+    int *jmeta;    // [njslots]    body0 | body1<<8 of each joint slot (shared by the CTA)
+};
+
+#define G(arr, field) (arr)[(size_t)(field) * Wp + w]
+
+struct BodyPose {
+    float pos[3], q[4], R[9];
+};
+
+__device__ __forceinline__ void load_pose(const StepParams &P, int b, int w, BodyPose &bp)
+{
+    const int Wp = P.Wp;
+    const int f = b * B2P_STATE_FIELDS;
+    bp.pos[0] = G(P.state, f + 0);
+    bp.pos[1] = G(P.state, f + 1);
+    bp.pos[2] = G(P.state, f + 2);
+    bp.q[0] = G(P.state, f + 3);
+    bp.q[1] = G(P.state, f + 4);
+    bp.q[2] = G(P.state, f + 5);
+    bp.q[3] = G(P.state, f + 6);
+    q_to_R(bp.q, bp.R);
+}
+
+__device__ __forceinline__ void load_invIw(const StepParams &P, int b, int w, float *I)
+{
+    const int Wp = P.Wp;
+#pragma unroll
+    for (int k = 0; k < 9; k++) I[k] = G(P.invIw, b * 9 + k);
+}
+
+// One constraint row under construction.
+struct Row {
+    float J[12];
+    float c, cfm, lo, hi;
+};
+
+__device__ __forceinline__ void row_init(Row &r, float world_cfm)
+{
+#pragma unroll
+    for (int k = 0; k < 12; k++) r.J[k] = 0.f;
+    r.c = 0.f;
+    r.cfm = world_cfm;
+    r.lo = -INFINITY;
+    r.hi = INFINITY;
+}
+
+struct PairCtx {
+    int b0, b1; // b1 < 0: static
+    float im0, im1;
+    float I0[9], I1[9];
+};
+
+// rhs = c/h - J.tmp1 ; iMJ = invM J^T ; Ad = w/(J iMJ + cfm/h) ; scale ; store.
+// Follows ODE quickstep stage 2c / SOR_LCP setup, same operation order as oracle/orc_quickstep.c.
+__device__ __forceinline__ void emit_row(const StepParams &P, const Smem &S, int w, int tid, int slot, Row &r,
+                                         const PairCtx &pc)
+{
+    const int Wp = P.Wp;
+    const float hinv = 1.0f / P.h;
+    float rhs = r.c * hinv;
+    const float cfm = r.cfm * hinv;
+    float s = 0.f;
+    {
+        const float *t = S.fc + (size_t)(pc.b0 * 6) * BD + tid;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s += r.J[k] * t[k * BD];
+    }
+    if (pc.b1 >= 0) {
+        const float *t = S.fc + (size_t)(pc.b1 * 6) * BD + tid;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s += r.J[6 + k] * t[k * BD];
+    }
+    rhs -= s;
+    float o[12];
+    o[0] = pc.im0 * r.J[0];
+    o[1] = pc.im0 * r.J[1];
+    o[2] = pc.im0 * r.J[2];
+    mul_R_v(o + 3, pc.I0, r.J + 3);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; k++) sum += o[k] * r.J[k];
+    if (pc.b1 >= 0) {
+        o[6] = pc.im1 * r.J[6];
+        o[7] = pc.im1 * r.J[7];
+        o[8] = pc.im1 * r.J[8];
+        mul_R_v(o + 9, pc.I1, r.J + 9);
+#pragma unroll
+        for (int k = 6; k < 12; k++) sum += o[k] * r.J[k];
+    } else {
+#pragma unroll
+        for (int k = 6; k < 12; k++) o[k] = 0.f;
+    }
+    const float Ad = P.sor_w / (sum + cfm);
+#pragma unroll
+    for (int k = 0; k < 6; k++) r.J[k] *= Ad;
+    if (pc.b1 >= 0) {
+#pragma unroll
+        for (int k = 6; k < 12; k++) r.J[k] *= Ad;
+    }
+    rhs *= Ad;
+    const float Adcfm = Ad * cfm;
+    float4 *dst = P.rows + (size_t)(slot * 7) * Wp + w;
+    dst[0 * (size_t)Wp] = make_float4(r.J[0], r.J[1], r.J[2], r.J[3]);
+    dst[1 * (size_t)Wp] = make_float4(r.J[4], r.J[5], r.J[6], r.J[7]);
+    dst[2 * (size_t)Wp] = make_float4(r.J[8], r.J[9], r.J[10], r.J[11]);
+    dst[3 * (size_t)Wp] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[4 * (size_t)Wp] = make_float4(o[4], o[5], o[6], o[7]);
+    dst[5 * (size_t)Wp] = make_float4(o[8], o[9], o[10], o[11]);
+    dst[6 * (size_t)Wp] = make_float4(rhs, Adcfm, r.lo, r.hi);
+    G(P.lambda, slot) = 0.f;
+    G(P.rowad, slot) = Ad;
+}
+
+struct LimotState {
+    int limit;
+    float limit_err;
+};
+
+// dxJointLimitMotor::testRotationalLimit
+__device__ __forceinline__ void limot_test(const DevLimot &l, float value, LimotState &st)
+{
+    if (value <= l.lostop) {
+        st.limit = 1;
+        st.limit_err = value - l.lostop;
+    } else if (value >= l.histop) {
+        st.limit = 2;
+        st.limit_err = value - l.histop;
+    } else {
+        st.limit = 0;
+        st.limit_err = 0.f;
+    }
+}
+
+// getHingeAngle (ODE joint.cpp), unsigned by dJOINT_REVERSE
+__device__ __forceinline__ float hinge_angle(const DevJoint &jc, const float *q0, const float *q1, bool has_b1)
+{
+    float qrel[4];
+    if (has_b1) {
+        float qq[4];
+        qmul1(qq, q0, q1);
+        qmul2(qrel, qq, jc.qrel);
+    } else {
+        qmul3(qrel, q0, jc.qrel);
+    }
+    const float cost2 = qrel[0];
+    const float sint2 = sqrtf(qrel[1] * qrel[1] + qrel[2] * qrel[2] + qrel[3] * qrel[3]);
+    float theta = (qrel[1] * jc.axis1[0] + qrel[2] * jc.axis1[1] + qrel[3] * jc.axis1[2] >= 0.f)
+                      ? (2.f * atan2f(sint2, cost2))
+                      : (2.f * atan2f(sint2, -cost2));
+    if (theta > 3.14159265358979323846f) theta -= 2.f * 3.14159265358979323846f;
+    return -theta;
+}
+
+__device__ __forceinline__ float slider_position(const DevJoint &jc, const BodyPose &p0, const BodyPose &p1,
+                                                 bool has_b1)
+{
+    float ax1[3], q[3];
+    mul_R_v(ax1, p0.R, jc.axis1);
+    if (has_b1) {
+        mul_R_v(q, p1.R, jc.offset);
+#pragma unroll
+        for (int i = 0; i < 3; i++) q[i] = p0.pos[i] - q[i] - p1.pos[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++) q[i] = p0.pos[i] - jc.offset[i];
+        if (jc.reverse) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) ax1[i] = -ax1[i];
+        }
+    }
+    return dot3(ax1, q);
+}
+
+__device__ __forceinline__ float hinge2_angle1(const DevJoint &jc, const BodyPose &p0, const BodyPose &p1)
+{
+    float p[3], q[3];
+    mul_R_v(p, p1.R, jc.axis2);
+    mul_Rt_v(q, p0.R, p);
+    const float x = dot3(jc.v1, q);
+    const float y = dot3(jc.v2, q);
+    return -atan2f(y, x);
+}
+
+__device__ __forceinline__ float hinge2_angle2(const DevJoint &jc, const BodyPose &p0, const BodyPose &p1)
+{
+    float p[3], q[3];
+    mul_R_v(p, p0.R, jc.axis1);
+    mul_Rt_v(q, p1.R, p);
+    const float x = dot3(jc.w1, q);
+    const float y = dot3(jc.w2, q);
+    return -atan2f(y, x);
+}
+
+// Limit state of limot 1 of joint jc in this world (getInfo1 part that looks at the pose).
+__device__ __forceinline__ void joint_limit_state(const DevJoint &jc, const BodyPose &p0, const BodyPose &p1,
+                                                  LimotState &st)
+{
+    st.limit = 0;
+    st.limit_err = 0.f;
+    const DevLimot &l = jc.limot1;
+    const float PI = 3.14159265358979323846f;
+    if (jc.type == 1) { // hinge
+        if ((l.lostop >= -PI || l.histop <= PI) && l.lostop <= l.histop)
+            limot_test(l, hinge_angle(jc, p0.q, p1.q, jc.b1 >= 0), st);
+    } else if (jc.type == 3) { // slider
+        if ((l.lostop > -INFINITY || l.histop < INFINITY) && l.lostop <= l.histop)
+            limot_test(l, slider_position(jc, p0, p1, jc.b1 >= 0), st);
+    } else if (jc.type == 2) { // hinge2
+        if ((l.lostop >= -PI || l.histop <= PI) && l.lostop <= l.histop)
+            limot_test(l, hinge2_angle1(jc, p0, p1), st);
+    }
+}
+
+// dxJointLimitMotor::addLimot, row part.  Returns 1 if the row is used.
+// The "powered while at a limit" force injection is done by limot_prepass() before tmp1 exists.
+__device__ __forceinline__ int add_limot_row(const StepParams &P, const DevLimot &l, float vel, float fmax,
+                                             const LimotState &st, Row &r, const float *ax1, int rotational,
+                                             const BodyPose &p0, const BodyPose &p1, bool has_b1)
+{
+    int powered = fmax > 0.f;
+    if (!(powered || st.limit)) return 0;
+    float *J1 = rotational ? r.J + 3 : r.J;
+    float *J2 = rotational ? r.J + 9 : r.J + 6;
+#pragma unroll
+    for (int i = 0; i < 3; i++) J1[i] = ax1[i];
+    if (has_b1) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) J2[i] = -ax1[i];
+    }
+    if (!rotational && has_b1) {
+        float c[3], ltd[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) c[i] = 0.5f * (p1.pos[i] - p0.pos[i]);
+        cross3(ltd, c, ax1);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            r.J[3 + i] = ltd[i];
+            r.J[9 + i] = ltd[i];
+        }
+    }
+    if (st.limit && (l.lostop == l.histop)) powered = 0;
+    if (powered) {
+        r.cfm = l.normal_cfm;
+        if (!st.limit) {
+            r.c = vel;
+            r.lo = -fmax;
+            r.hi = fmax;
+        }
+    }
+    if (st.limit) {
+        const float k = (1.0f / P.h) * l.stop_erp;
+        r.c = -k * st.limit_err;
+        r.cfm = l.stop_cfm;
+        if (l.lostop == l.histop) {
+            r.lo = -INFINITY;
+            r.hi = INFINITY;
+        } else if (st.limit == 1) {
+            r.lo = 0.f;
+            r.hi = INFINITY;
+        } else {
+            r.lo = -INFINITY;
+            r.hi = 0.f;
+        }
+        // dParamBounce is never set by the reference; not supported on the device path.
+    }
+    return 1;
+}
+
+// setFixedOrientation (ODE joint.cpp): three angular rows, rhs from the quaternion error
+__device__ __forceinline__ void fixed_orientation_rhs(const DevJoint &jc, const BodyPose &p0, const BodyPose &p1,
+                                                      bool has_b1, float k2, float *c3)
+{
+    float qerr[4], e[3];
+    if (has_b1) {
+        float qq[4];
+        qmul1(qq, p0.q, p1.q);
+        qmul2(qerr, qq, jc.qrel);
+    } else {
+        qmul3(qerr, p0.q, jc.qrel);
+    }
+    if (qerr[0] < 0.f) {
+        qerr[1] = -qerr[1];
+        qerr[2] = -qerr[2];
+        qerr[3] = -qerr[3];
+    }
+    mul_R_v(e, p0.R, qerr + 1);
+#pragma unroll
+    for (int i = 0; i < 3; i++) c3[i] = k2 * e[i];
+}
+
+__global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevTemplate *__restrict__ T = P.T;
+    const int nb = T->nb, nj = T->nj, maxc = T->maxc, rpc = T->rpc, njslots = T->njslots, maxrows = T->maxrows;
+    Smem S;
+    {
+        unsigned char *p = smem_raw;
+        S.fc = (float *)p;
+        p += sizeof(float) * (size_t)nb * 6 * BD;
+        S.jmeta = (int *)p;
+        p += sizeof(int) * (size_t)njslots;
+        S.cb = (uint16_t *)p;
+        p += sizeof(uint16_t) * (size_t)maxc * BD;
+        S.ord = p;
+        p += (size_t)maxrows * BD;
+        S.jm = p;
+        p += (size_t)nj * BD;
+        S.jl = (int8_t *)p;
+        p += (size_t)nj * BD;
+        S.cm = p;
+    }
+    const int tid = threadIdx.x;
+    for (int s = tid; s < njslots; s += BD) {
+        const DevJoint &jc = T->joints[s / B2P_ROWS_PER_JOINT];
+        S.jmeta[s] = (jc.b0 & 0xff) | ((jc.b1 < 0 ? 0xff : jc.b1) << 8);
+    }
+    __syncthreads();
+    const int w = blockIdx.x * BD + tid;
+    if (w >= P.W) return;
+    const int Wp = P.Wp;
+    const float h = P.h, hinv = 1.0f / P.h;
+
+    // ---------------- phase 1: bodies ----------------
+    for (int b = 0; b < nb; b++) {
+        const DevBody &bc = T->bodies[b];
+        BodyPose bp;
+        load_pose(P, b, w, bp);
+        const int f = b * B2P_STATE_FIELDS;
+        float avel[3] = {G(P.state, f + 10), G(P.state, f + 11), G(P.state, f + 12)};
+        float facc[3] = {G(P.force, b * 6 + 0), G(P.force, b * 6 + 1), G(P.force, b * 6 + 2)};
+        float tacc[3] = {G(P.force, b * 6 + 3), G(P.force, b * 6 + 4), G(P.force, b * 6 + 5)};
+        float tmp[9], Iw[9];
+        mul33_bt(tmp, bc.invI, bp.R);
+        mul33(Iw, bp.R, tmp);
+#pragma unroll
+        for (int k = 0; k < 9; k++) G(P.invIw, b * 9 + k) = Iw[k];
+        if (bc.gyroscopic) {
+            // implicit gyroscopic torque (ODE 0.16 quickstep stage0, Lacoursiere 2006)
+            float I[9], L[3], It[9], itInv[9];
+            mul33_bt(tmp, bc.I, bp.R);
+            mul33(I, bp.R, tmp);
+            mul_R_v(L, I, avel);
+            It[0] = I[0];
+            It[1] = I[1] + h * L[2];
+            It[2] = I[2] - h * L[1];
+            It[3] = I[3] - h * L[2];
+            It[4] = I[4];
+            It[5] = I[5] + h * L[0];
+            It[6] = I[6] + h * L[1];
+            It[7] = I[7] - h * L[0];
+            It[8] = I[8];
+#pragma unroll
+            for (int k = 0; k < 3; k++) L[k] *= hinv;
+            if (invert33(itInv, It) != 0.f) {
+                float M[9], tau[3];
+                mul33(M, I, itInv);
+                M[0] -= 1.f;
+                M[4] -= 1.f;
+                M[8] -= 1.f;
+                mul_R_v(tau, M, L);
+#pragma unroll
+                for (int k = 0; k < 3; k++) tacc[k] += tau[k];
+            }
+        }
+        if (!bc.nogravity) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) facc[k] += bc.mass * P.gravity[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            S.fc[(size_t)(b * 6 + k) * BD + tid] = facc[k];
+            S.fc[(size_t)(b * 6 + 3 + k) * BD + tid] = tacc[k];
+        }
+    }
+
+    // ---------------- phase 1a: limit motors powered into a stop add forces (rare) -------------
+    if (T->has_limit_motors) {
+        for (int j = 0; j < nj; j++) {
+            const DevJoint &jc = T->joints[j];
+            if (jc.type == 6 || jc.b0 < 0) continue;
+            BodyPose p0, p1;
+            load_pose(P, jc.b0, w, p0);
+            const bool has_b1 = jc.b1 >= 0;
+            if (has_b1) load_pose(P, jc.b1, w, p1);
+            LimotState st;
+            joint_limit_state(jc, p0, p1, st);
+            const float vel = G(P.jcmd, j * 4 + 0), fmax = G(P.jcmd, j * 4 + 1);
+            const DevLimot &l = jc.limot1;
+            if (fmax > 0.f && st.limit && l.lostop != l.histop) {
+                float fm = fmax;
+                if ((vel > 0.f) || (vel == 0.f && st.limit == 2)) fm = -fm;
+                if ((st.limit == 1 && vel > 0.f) || (st.limit == 2 && vel < 0.f)) fm *= l.fudge_factor;
+                float ax1[3];
+                mul_R_v(ax1, p0.R, jc.axis1);
+                float *f0 = S.fc + (size_t)(jc.b0 * 6) * BD + tid;
+                float *f1 = has_b1 ? S.fc + (size_t)(jc.b1 * 6) * BD + tid : nullptr;
+                if (jc.type == 3) { // slider: linear force (+ torque decoupling)
+                    if (jc.reverse && !has_b1) {
+#pragma unroll
+                        for (int i = 0; i < 3; i++) ax1[i] = -ax1[i];
+                    }
+                    if (has_b1) {
+                        float c[3], ltd[3];
+#pragma unroll
+                        for (int i = 0; i < 3; i++) c[i] = 0.5f * (p1.pos[i] - p0.pos[i]);
+                        cross3(ltd, c, ax1);
+#pragma unroll
+                        for (int i = 0; i < 3; i++) {
+                            f0[(3 + i) * BD] -= fm * ltd[i];
+                            f1[(3 + i) * BD] -= fm * ltd[i];
+                            f1[i * BD] += fm * ax1[i];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; i++) f0[i * BD] -= fm * ax1[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        if (has_b1) f1[(3 + i) * BD] += fm * ax1[i];
+                        f0[(3 + i) * BD] -= fm * ax1[i];
+                    }
+                }
+            }
+        }
+    }
+
+    // ---------------- phase 1b: fe -> gmem (needed by the epilogue), tmp1 -> smem --------------
+    for (int b = 0; b < nb; b++) {
+        const DevBody &bc = T->bodies[b];
+        const int f = b * B2P_STATE_FIELDS;
+        float Iw[9], fe[6], t3[3];
+        load_invIw(P, b, w, Iw);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            fe[k] = S.fc[(size_t)(b * 6 + k) * BD + tid];
+            G(P.force, b * 6 + k) = fe[k];
+        }
+        mul_R_v(t3, Iw, fe + 3);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float lv = G(P.state, f + 7 + k), av = G(P.state, f + 10 + k);
+            S.fc[(size_t)(b * 6 + k) * BD + tid] = fe[k] * bc.invMass + lv * hinv;
+            S.fc[(size_t)(b * 6 + 3 + k) * BD + tid] = t3[k] + av * hinv;
+        }
+    }
+
+    // ---------------- phase 2: constraint rows ----------------
+    // ODE orders rows with findex < 0 first (in row order) and friction-dependent rows last.
+    // Head rows are appended as they are emitted; dependent rows are recorded per contact in a bit
+    // mask and appended after all contacts are known.
+    int nhead = 0;
+    auto push_head = [&](int slot) { S.ord[(size_t)nhead++ * BD + tid] = (uint8_t)slot; };
+
+    for (int j = 0; j < nj; j++) {
+        const DevJoint &jc = T->joints[j];
+        int mrows = 0, limot_row = -1;
+        if (jc.b0 >= 0) {
+            const bool has_b1 = jc.b1 >= 0;
+            BodyPose p0, p1;
+            PairCtx pc;
+            pc.b0 = jc.b0;
+            pc.b1 = jc.b1;
+            load_pose(P, jc.b0, w, p0);
+            load_invIw(P, jc.b0, w, pc.I0);
+            pc.im0 = T->bodies[jc.b0].invMass;
+            pc.im1 = 0.f;
+            if (has_b1) {
+                load_pose(P, jc.b1, w, p1);
+                load_invIw(P, jc.b1, w, pc.I1);
+                pc.im1 = T->bodies[jc.b1].invMass;
+            }
+            const int base = jc.slot_base;
+            const float kerp = hinv * P.erp;
+            Row r;
+            if (jc.type == 1) {
+                // ---- hinge: setBall + two angular rows + limot (ODE hinge.cpp getInfo2)
+                float a1[3], a2[3], cb[3];
+                mul_R_v(a1, p0.R, jc.anchor1);
+                if (has_b1) {
+                    mul_R_v(a2, p1.R, jc.anchor2);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) cb[i] = kerp * (a2[i] + p1.pos[i] - a1[i] - p0.pos[i]);
+                } else {
+                    a2[0] = a2[1] = a2[2] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 3; i++) cb[i] = kerp * (jc.anchor2[i] - a1[i] - p0.pos[i]);
+                }
+                // row 0
+                row_init(r, P.cfm);
+                r.J[0] = 1.f; r.J[4] = a1[2]; r.J[5] = -a1[1];
+                if (has_b1) { r.J[6] = -1.f; r.J[10] = -a2[2]; r.J[11] = a2[1]; }
+                r.c = cb[0];
+                emit_row(P, S, w, tid, base + 0, r, pc); push_head(base + 0);
+                row_init(r, P.cfm);
+                r.J[1] = 1.f; r.J[3] = -a1[2]; r.J[5] = a1[0];
+                if (has_b1) { r.J[7] = -1.f; r.J[9] = a2[2]; r.J[11] = -a2[0]; }
+                r.c = cb[1];
+                emit_row(P, S, w, tid, base + 1, r, pc); push_head(base + 1);
+                row_init(r, P.cfm);
+                r.J[2] = 1.f; r.J[3] = a1[1]; r.J[4] = -a1[0];
+                if (has_b1) { r.J[8] = -1.f; r.J[9] = -a2[1]; r.J[10] = a2[0]; }
+                r.c = cb[2];
+                emit_row(P, S, w, tid, base + 2, r, pc); push_head(base + 2);
+                float ax1[3], pv[3], qv[3], ax2[3], bv[3];
+                mul_R_v(ax1, p0.R, jc.axis1);
+                plane_space(ax1, pv, qv);
+                if (has_b1) mul_R_v(ax2, p1.R, jc.axis2);
+                else { ax2[0] = jc.axis2[0]; ax2[1] = jc.axis2[1]; ax2[2] = jc.axis2[2]; }
+                cross3(bv, ax1, ax2);
+                row_init(r, P.cfm);
+                r.J[3] = pv[0]; r.J[4] = pv[1]; r.J[5] = pv[2];
+                if (has_b1) { r.J[9] = -pv[0]; r.J[10] = -pv[1]; r.J[11] = -pv[2]; }
+                r.c = kerp * dot3(bv, pv);
+                emit_row(P, S, w, tid, base + 3, r, pc); push_head(base + 3);
+                row_init(r, P.cfm);
+                r.J[3] = qv[0]; r.J[4] = qv[1]; r.J[5] = qv[2];
+                if (has_b1) { r.J[9] = -qv[0]; r.J[10] = -qv[1]; r.J[11] = -qv[2]; }
+                r.c = kerp * dot3(bv, qv);
+                emit_row(P, S, w, tid, base + 4, r, pc); push_head(base + 4);
+                mrows = 5;
+                LimotState st;
+                joint_limit_state(jc, p0, p1, st);
+                row_init(r, P.cfm);
+                if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 1, p0, p1,
+                                  has_b1)) {
+                    emit_row(P, S, w, tid, base + 5, r, pc); push_head(base + 5);
+                    limot_row = 5;
+                    mrows = 6;
+                }
+            } else if (jc.type == 6) {
+                // ---- fixed (ODE fixed.cpp getInfo2): rows 0-2 position, rows 3-5 orientation
+                float ofs[3], cl[3], ca[3];
+                mul_R_v(ofs, p0.R, jc.offset);
+                const float k = hinv * jc.erp;
+                if (has_b1) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) cl[i] = k * (p1.pos[i] - p0.pos[i] + ofs[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) cl[i] = k * (jc.offset[i] - p0.pos[i]);
+                }
+                fixed_orientation_rhs(jc, p0, p1, has_b1, hinv * P.erp * 2.f, ca);
+                row_init(r, P.cfm);
+                r.J[0] = 1.f;
+                if (has_b1) { r.J[4] = -ofs[2]; r.J[5] = ofs[1]; r.J[6] = -1.f; }
+                r.c = cl[0]; r.cfm = jc.cfm;
+                emit_row(P, S, w, tid, base + 0, r, pc); push_head(base + 0);
+                row_init(r, P.cfm);
+                r.J[1] = 1.f;
+                if (has_b1) { r.J[3] = ofs[2]; r.J[5] = -ofs[0]; r.J[7] = -1.f; }
+                r.c = cl[1]; r.cfm = jc.cfm;
+                emit_row(P, S, w, tid, base + 1, r, pc); push_head(base + 1);
+                row_init(r, P.cfm);
+                r.J[2] = 1.f;
+                if (has_b1) { r.J[3] = -ofs[1]; r.J[4] = ofs[0]; r.J[8] = -1.f; }
+                r.c = cl[2]; r.cfm = jc.cfm;
+                emit_row(P, S, w, tid, base + 2, r, pc); push_head(base + 2);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    row_init(r, P.cfm);
+                    r.J[3 + i] = 1.f;
+                    if (has_b1) r.J[9 + i] = -1.f;
+                    r.c = ca[i];
+                    emit_row(P, S, w, tid, base + 3 + i, r, pc); push_head(base + 3 + i);
+                }
+                mrows = 6;
+            } else if (jc.type == 3) {
+                // ---- slider (ODE slider.cpp getInfo2)
+                float ca[3];
+                fixed_orientation_rhs(jc, p0, p1, has_b1, hinv * P.erp * 2.f, ca);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    row_init(r, P.cfm);
+                    r.J[3 + i] = 1.f;
+                    if (has_b1) r.J[9 + i] = -1.f;
+                    r.c = ca[i];
+                    emit_row(P, S, w, tid, base + i, r, pc); push_head(base + i);
+                }
+                float c[3] = {0.f, 0.f, 0.f}, ax1[3], pv[3], qv[3];
+                if (has_b1) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) c[i] = p1.pos[i] - p0.pos[i];
+                }
+                mul_R_v(ax1, p0.R, jc.axis1);
+                plane_space(ax1, pv, qv);
+                float c3, c4, tp[3], tq[3];
+                if (has_b1) {
+                    cross3(tp, c, pv);
+                    cross3(tq, c, qv);
+                    float ofs[3];
+                    mul_R_v(ofs, p1.R, jc.offset);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) c[i] += ofs[i];
+                    c3 = kerp * dot3(pv, c);
+                    c4 = kerp * dot3(qv, c);
+                } else {
+                    float ofs[3];
+#pragma unroll
+                    for (int i = 0; i < 3; i++) ofs[i] = jc.offset[i] - p0.pos[i];
+                    c3 = kerp * dot3(pv, ofs);
+                    c4 = kerp * dot3(qv, ofs);
+                    if (jc.reverse) {
+#pragma unroll
+                        for (int i = 0; i < 3; i++) ax1[i] = -ax1[i];
+                    }
+                }
+                row_init(r, P.cfm);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    r.J[i] = pv[i];
+                    if (has_b1) { r.J[3 + i] = 0.5f * tp[i]; r.J[9 + i] = 0.5f * tp[i]; r.J[6 + i] = -pv[i]; }
+                }
+                r.c = c3;
+                emit_row(P, S, w, tid, base + 3, r, pc); push_head(base + 3);
+                row_init(r, P.cfm);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    r.J[i] = qv[i];
+                    if (has_b1) { r.J[3 + i] = 0.5f * tq[i]; r.J[9 + i] = 0.5f * tq[i]; r.J[6 + i] = -qv[i]; }
+                }
+                r.c = c4;
+                emit_row(P, S, w, tid, base + 4, r, pc); push_head(base + 4);
+                mrows = 5;
+                LimotState st;
+                joint_limit_state(jc, p0, p1, st);
+                row_init(r, P.cfm);
+                if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 0, p0, p1,
+                                  has_b1)) {
+                    emit_row(P, S, w, tid, base + 5, r, pc); push_head(base + 5);
+                    limot_row = 5;
+                    mrows = 6;
+                }
+            } else if (jc.type == 2 && has_b1) {
+                // ---- hinge2 (ODE hinge2.cpp getInfo2): setBall2 along axis1 + one angular row + limots
+                float ax1[3], ax2[3], qv[3];
+                mul_R_v(ax1, p0.R, jc.axis1);
+                mul_R_v(ax2, p1.R, jc.axis2);
+                cross3(qv, ax1, ax2);
+                const float sn = sqrtf(dot3(qv, qv));
+                const float cs = dot3(ax1, ax2);
+                normalize3(qv);
+                float q1[3], q2[3], a1[3], a2[3], d[3];
+                plane_space(ax1, q1, q2);
+                mul_R_v(a1, p0.R, jc.anchor1);
+                mul_R_v(a2, p1.R, jc.anchor2);
+                float a1w[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) a1w[i] = a1[i] + p0.pos[i];
+#pragma unroll
+                for (int i = 0; i < 3; i++) d[i] = a2[i] + p1.pos[i] - a1w[i];
+                const float k1 = hinv * jc.susp_erp;
+                const float *dirs[3] = {ax1, q1, q2};
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    row_init(r, P.cfm);
+                    const float *dv = dirs[i];
+                    r.J[0] = dv[0]; r.J[1] = dv[1]; r.J[2] = dv[2];
+                    cross3(r.J + 3, a1, dv);
+                    r.J[6] = -dv[0]; r.J[7] = -dv[1]; r.J[8] = -dv[2];
+                    cross3(r.J + 9, dv, a2);
+                    r.c = (i == 0 ? k1 : kerp) * dot3(dv, d);
+                    if (i == 0) r.cfm = jc.susp_cfm;
+                    emit_row(P, S, w, tid, base + i, r, pc); push_head(base + i);
+                }
+                row_init(r, P.cfm);
+#pragma unroll
+                for (int i = 0; i < 3; i++) { r.J[3 + i] = qv[i]; r.J[9 + i] = -qv[i]; }
+                r.c = kerp * (jc.c0 * sn - jc.s0 * cs);
+                emit_row(P, S, w, tid, base + 3, r, pc); push_head(base + 3);
+                mrows = 4;
+                LimotState st;
+                joint_limit_state(jc, p0, p1, st);
+                row_init(r, P.cfm);
+                if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 1, p0, p1,
+                                  true)) {
+                    emit_row(P, S, w, tid, base + mrows, r, pc); push_head(base + mrows);
+                    limot_row = mrows;
+                    mrows++;
+                }
+                LimotState st2;
+                st2.limit = 0;
+                st2.limit_err = 0.f;
+                row_init(r, P.cfm);
+                if (add_limot_row(P, jc.limot2, G(P.jcmd, j * 4 + 2), G(P.jcmd, j * 4 + 3), st2, r, ax2, 1, p0, p1,
+                                  true)) {
+                    emit_row(P, S, w, tid, base + mrows, r, pc); push_head(base + mrows);
+                    if (limot_row < 0) limot_row = mrows;
+                    mrows++;
+                }
+            }
+        }
+        S.jm[(size_t)j * BD + tid] = (uint8_t)mrows;
+        S.jl[(size_t)j * BD + tid] = (int8_t)limot_row;
+        G(P.jrows, j) = (uint8_t)mrows;
+    }
+
+    // ---- contacts (ODE contact.cpp getInfo1/getInfo2 for the mode bits Frame::addContact sets)
+    int nc = G(P.ccount, 0);
+    if (nc > maxc) nc = maxc;
+    for (int c = 0; c < nc; c++) {
+        const int ids = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_IDS));
+        const int b0 = ids & 0xff;
+        const int b1 = ((ids >> 8) & 0xff) == 0xff ? -1 : ((ids >> 8) & 0xff);
+        S.cb[(size_t)c * BD + tid] = (uint16_t)(ids & 0xffff);
+        const int mode = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_MODE));
+        float pos[3] = {G(P.crec, c * B2P_CONTACT_FIELDS + CR_PX), G(P.crec, c * B2P_CONTACT_FIELDS + CR_PY),
+                        G(P.crec, c * B2P_CONTACT_FIELDS + CR_PZ)};
+        float n[3] = {G(P.crec, c * B2P_CONTACT_FIELDS + CR_NX), G(P.crec, c * B2P_CONTACT_FIELDS + CR_NY),
+                      G(P.crec, c * B2P_CONTACT_FIELDS + CR_NZ)};
+        float depth = G(P.crec, c * B2P_CONTACT_FIELDS + CR_DEPTH) - P.contact_min_depth;
+        float mu = G(P.crec, c * B2P_CONTACT_FIELDS + CR_MU);
+        float mu2 = G(P.crec, c * B2P_CONTACT_FIELDS + CR_MU2);
+        const float soft_erp = G(P.crec, c * B2P_CONTACT_FIELDS + CR_SOFT_ERP);
+        const float soft_cfm = G(P.crec, c * B2P_CONTACT_FIELDS + CR_SOFT_CFM);
+        if (depth < 0.f) depth = 0.f;
+        if (mu < 0.f) mu = 0.f;
+        if (mu2 < 0.f) mu2 = 0.f;
+        PairCtx pc;
+        pc.b0 = b0;
+        pc.b1 = b1;
+        BodyPose p0, p1;
+        load_pose(P, b0, w, p0);
+        load_invIw(P, b0, w, pc.I0);
+        pc.im0 = T->bodies[b0].invMass;
+        pc.im1 = 0.f;
+        if (b1 >= 0) {
+            load_pose(P, b1, w, p1);
+            load_invIw(P, b1, w, pc.I1);
+            pc.im1 = T->bodies[b1].invMass;
+        }
+        const int base = njslots + c * rpc;
+        const float erp = (mode & 0x008) ? soft_erp : P.erp;
+        const float pushout = hinv * erp * depth;
+        float c1[3], c2[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 3; i++) c1[i] = pos[i] - p0.pos[i];
+        Row r;
+        row_init(r, P.cfm);
+        r.J[0] = n[0]; r.J[1] = n[1]; r.J[2] = n[2];
+        cross3(r.J + 3, c1, n);
+        if (b1 >= 0) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) { c2[i] = pos[i] - p1.pos[i]; r.J[6 + i] = -n[i]; }
+            cross3(r.J + 9, n, c2);
+        }
+        r.c = pushout > P.contact_max_vel ? P.contact_max_vel : pushout;
+        if (mode & 0x010) r.cfm = soft_cfm;
+        r.lo = 0.f;
+        r.hi = INFINITY;
+        emit_row(P, S, w, tid, base, r, pc);
+        push_head(base);
+        int row = 1, depmask = 0;
+        float t1[3], t2[3];
+        plane_space(n, t1, t2);
+        const bool axisdep = (mode & 0x001) != 0;
+        const bool fr1 = mu > 0.f;
+        const float mu2e = axisdep ? mu2 : mu;
+        const bool fr2 = axisdep ? (mu2 > 0.f) : (mu > 0.f);
+        if (fr1) {
+            row_init(r, P.cfm);
+            r.J[0] = t1[0]; r.J[1] = t1[1]; r.J[2] = t1[2];
+            cross3(r.J + 3, c1, t1);
+            if (b1 >= 0) { r.J[6] = -t1[0]; r.J[7] = -t1[1]; r.J[8] = -t1[2]; cross3(r.J + 9, t1, c2); }
+            r.lo = -mu;
+            r.hi = mu;
+            emit_row(P, S, w, tid, base + row, r, pc);
+            if (mode & 0x1000) depmask |= 1 << (row - 1); else push_head(base + row);
+            row++;
+        }
+        if (fr2) {
+            row_init(r, P.cfm);
+            r.J[0] = t2[0]; r.J[1] = t2[1]; r.J[2] = t2[2];
+            cross3(r.J + 3, c1, t2);
+            if (b1 >= 0) { r.J[6] = -t2[0]; r.J[7] = -t2[1]; r.J[8] = -t2[2]; cross3(r.J + 9, t2, c2); }
+            r.lo = -mu2e;
+            r.hi = mu2e;
+            emit_row(P, S, w, tid, base + row, r, pc);
+            if (mode & 0x2000) depmask |= 1 << (row - 1); else push_head(base + row);
+            row++;
+        }
+        if ((mode & 0x400) && rpc >= 6) {
+            float rho[3];
+            rho[0] = G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHO);
+            if (axisdep) {
+                rho[1] = G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHO2);
+                rho[2] = G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHON);
+            } else {
+                rho[1] = rho[0];
+                rho[2] = rho[0];
+            }
+            const float *ax[3] = {t1, t2, n};
+            const int bits[3] = {0x1000, 0x2000, 0x4000};
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                if (rho[i] > 0.f) {
+                    row_init(r, P.cfm);
+                    r.J[3] = ax[i][0]; r.J[4] = ax[i][1]; r.J[5] = ax[i][2];
+                    if (b1 >= 0) { r.J[9] = -ax[i][0]; r.J[10] = -ax[i][1]; r.J[11] = -ax[i][2]; }
+                    r.lo = -rho[i];
+                    r.hi = rho[i];
+                    emit_row(P, S, w, tid, base + row, r, pc);
+                    if (mode & bits[i]) depmask |= 1 << (row - 1); else push_head(base + row);
+                    row++;
+                }
+            }
+        }
+        S.cm[(size_t)c * BD + tid] = (uint8_t)(row | (depmask << 3));
+    }
+
+    int m = nhead;
+    for (int c = 0; c < nc; c++) {
+        const int v = S.cm[(size_t)c * BD + tid];
+        const int rows_c = v & 7, depmask = v >> 3;
+        for (int k = 1; k < rows_c; k++)
+            if (depmask & (1 << (k - 1))) S.ord[(size_t)m++ * BD + tid] = (uint8_t)(njslots + c * rpc + k);
+    }
+    G(P.nrows, 0) = m;
+
+    // tmp1 -> gmem? not needed: epilogue uses fe from gmem.  fc = 0
+    for (int k = 0; k < nb * 6; k++) S.fc[(size_t)k * BD + tid] = 0.f;
+
+    // ---------------- phase 3: SOR-LCP sweep ----------------
+    uint32_t seed = G(P.seed, 0);
+    for (int it = 0; it < P.iters; it++) {
+        if (P.reorder == 0 && it >= 8 && (it & 7) == 0) {
+            // ODE ConstraintsReorderingHelper on [0,nhead) and [nhead,m)
+            for (int idx = 1; idx < nhead; idx++) {
+                const int sw = rand_int(seed, idx + 1);
+                const uint8_t a = S.ord[(size_t)idx * BD + tid], bq = S.ord[(size_t)sw * BD + tid];
+                S.ord[(size_t)idx * BD + tid] = bq;
+                S.ord[(size_t)sw * BD + tid] = a;
+            }
+            for (int idx = nhead + 1; idx < m; idx++) {
+                const int sw = rand_int(seed, idx - nhead + 1) + nhead;
+                const uint8_t a = S.ord[(size_t)idx * BD + tid], bq = S.ord[(size_t)sw * BD + tid];
+                S.ord[(size_t)idx * BD + tid] = bq;
+                S.ord[(size_t)sw * BD + tid] = a;
+            }
+        }
+        for (int k = 0; k < m; k++) {
+            const int i = S.ord[(size_t)k * BD + tid];
+            const float4 *src = P.rows + (size_t)(i * 7) * Wp + w;
+            const float4 j0 = src[0 * (size_t)Wp], j1 = src[1 * (size_t)Wp], j2 = src[2 * (size_t)Wp];
+            const float4 m0 = src[3 * (size_t)Wp], m1 = src[4 * (size_t)Wp], m2 = src[5 * (size_t)Wp];
+            const float4 sc = src[6 * (size_t)Wp];
+            int b0, b1;
+            int fslot = -1;
+            if (i < njslots) {
+                const int meta = S.jmeta[i];
+                b0 = meta & 0xff;
+                b1 = (meta >> 8) & 0xff;
+            } else {
+                const int c = (i - njslots) / rpc;
+                const int meta = S.cb[(size_t)c * BD + tid];
+                b0 = meta & 0xff;
+                b1 = (meta >> 8) & 0xff;
+                fslot = njslots + c * rpc;
+            }
+            float *f0 = S.fc + (size_t)(b0 * 6) * BD + tid;
+            float *f1 = (b1 != 0xff) ? S.fc + (size_t)(b1 * 6) * BD + tid : nullptr;
+            const float old = G(P.lambda, i);
+            float delta = sc.x - old * sc.y;
+            delta -= f0[0 * BD] * j0.x + f0[1 * BD] * j0.y + f0[2 * BD] * j0.z + f0[3 * BD] * j0.w +
+                     f0[4 * BD] * j1.x + f0[5 * BD] * j1.y;
+            if (f1)
+                delta -= f1[0 * BD] * j1.z + f1[1 * BD] * j1.w + f1[2 * BD] * j2.x + f1[3 * BD] * j2.y +
+                         f1[4 * BD] * j2.z + f1[5 * BD] * j2.w;
+            float lo_act = sc.z, hi_act = sc.w;
+            if (k >= nhead) {
+                hi_act = fabsf(sc.w * G(P.lambda, fslot));
+                lo_act = -hi_act;
+            }
+            float nl = old + delta;
+            if (nl < lo_act) {
+                delta = lo_act - old;
+                nl = lo_act;
+            } else if (nl > hi_act) {
+                delta = hi_act - old;
+                nl = hi_act;
+            }
+            G(P.lambda, i) = nl;
+            f0[0 * BD] += delta * m0.x;
+            f0[1 * BD] += delta * m0.y;
+            f0[2 * BD] += delta * m0.z;
+            f0[3 * BD] += delta * m0.w;
+            f0[4 * BD] += delta * m1.x;
+            f0[5 * BD] += delta * m1.y;
+            if (f1) {
+                f1[0 * BD] += delta * m1.z;
+                f1[1 * BD] += delta * m1.w;
+                f1[2 * BD] += delta * m2.x;
+                f1[3 * BD] += delta * m2.y;
+                f1[4 * BD] += delta * m2.z;
+                f1[5 * BD] += delta * m2.w;
+            }
+        }
+    }
+    G(P.seed, 0) = seed;
+
+    // ---------------- phase 4a: joint / contact feedback from the unscaled Jacobian ------------
+    for (int j = 0; j < nj; j++) {
+        const DevJoint &jc = T->joints[j];
+        const int mrows = S.jm[(size_t)j * BD + tid];
+        const int lrow = S.jl[(size_t)j * BD + tid];
+        float data[12];
+#pragma unroll
+        for (int q = 0; q < 12; q++) data[q] = 0.f;
+        float flam = 0.f;
+        for (int k = 0; k < mrows; k++) {
+            const int slot = jc.slot_base + k;
+            const float4 *src = P.rows + (size_t)(slot * 7) * Wp + w;
+            const float4 j0 = src[0], j1 = src[(size_t)Wp], j2 = src[2 * (size_t)Wp];
+            const float lam = G(P.lambda, slot);
+            const float s = lam / G(P.rowad, slot);
+            data[0] += j0.x * s; data[1] += j0.y * s; data[2] += j0.z * s; data[3] += j0.w * s;
+            data[4] += j1.x * s; data[5] += j1.y * s; data[6] += j1.z * s; data[7] += j1.w * s;
+            data[8] += j2.x * s; data[9] += j2.y * s; data[10] += j2.z * s; data[11] += j2.w * s;
+            if (k == lrow) flam = lam;
+        }
+        if (jc.b1 < 0) {
+#pragma unroll
+            for (int q = 6; q < 12; q++) data[q] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 12; q++) G(P.jfb, j * 13 + q) = data[q];
+        G(P.jfb, j * 13 + 12) = flam;
+    }
+    for (int c = 0; c < nc; c++) {
+        const int mrows = S.cm[(size_t)c * BD + tid] & 7;
+        float f[3] = {0.f, 0.f, 0.f};
+        for (int k = 0; k < mrows; k++) {
+            const int slot = njslots + c * rpc + k;
+            const float4 j0 = P.rows[(size_t)(slot * 7) * Wp + w];
+            const float s = G(P.lambda, slot) / G(P.rowad, slot);
+            f[0] += j0.x * s;
+            f[1] += j0.y * s;
+            f[2] += j0.z * s;
+        }
+        G(P.cfb, c * 3 + 0) = f[0];
+        G(P.cfb, c * 3 + 1) = f[1];
+        G(P.cfb, c * 3 + 2) = f[2];
+    }
+
+    // ---------------- phase 4b: velocity update + dxStepBody ----------------
+    for (int b = 0; b < nb; b++) {
+        const DevBody &bc = T->bodies[b];
+        const int f = b * B2P_STATE_FIELDS;
+        float pos[3], q[4], lv[3], av[3], fe[6], Iw[9], t3[3];
+        pos[0] = G(P.state, f + 0); pos[1] = G(P.state, f + 1); pos[2] = G(P.state, f + 2);
+        q[0] = G(P.state, f + 3); q[1] = G(P.state, f + 4); q[2] = G(P.state, f + 5); q[3] = G(P.state, f + 6);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lv[k] = G(P.state, f + 7 + k);
+            av[k] = G(P.state, f + 10 + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) fe[k] = G(P.force, b * 6 + k);
+        load_invIw(P, b, w, Iw);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lv[k] += h * S.fc[(size_t)(b * 6 + k) * BD + tid];
+            av[k] += h * S.fc[(size_t)(b * 6 + 3 + k) * BD + tid];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lv[k] += h * bc.invMass * fe[k];
+            fe[3 + k] *= h;
+        }
+        mul_R_v(t3, Iw, fe + 3);
+#pragma unroll
+        for (int k = 0; k < 3; k++) av[k] += t3[k];
+        if (bc.has_max_ang) {
+            const float aspeed = dot3(av, av);
+            if (aspeed > bc.max_angular_speed * bc.max_angular_speed) {
+                const float coef = bc.max_angular_speed / sqrtf(aspeed);
+#pragma unroll
+                for (int k = 0; k < 3; k++) av[k] *= coef;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) pos[k] += h * lv[k];
+        float dq[4];
+        dq[0] = 0.5f * (-av[0] * q[1] - av[1] * q[2] - av[2] * q[3]);
+        dq[1] = 0.5f * (av[0] * q[0] + av[1] * q[3] - av[2] * q[2]);
+        dq[2] = 0.5f * (-av[0] * q[3] + av[1] * q[0] + av[2] * q[1]);
+        dq[3] = 0.5f * (av[0] * q[2] - av[1] * q[1] + av[2] * q[0]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) q[k] += h * dq[k];
+        normalize4(q);
+        G(P.state, f + 0) = pos[0]; G(P.state, f + 1) = pos[1]; G(P.state, f + 2) = pos[2];
+        G(P.state, f + 3) = q[0]; G(P.state, f + 4) = q[1]; G(P.state, f + 5) = q[2]; G(P.state, f + 6) = q[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            G(P.state, f + 7 + k) = lv[k];
+            G(P.state, f + 10 + k) = av[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) G(P.force, b * 6 + k) = 0.f;
+    }
+
+    // ---------------- phase 4c: joint observations from the new state ----------------
+    for (int j = 0; j < nj; j++) {
+        const DevJoint &jc = T->joints[j];
+        float a1 = 0.f, r1 = 0.f, a2 = 0.f, r2 = 0.f;
+        if (jc.b0 >= 0 && jc.type != 6) {
+            const bool has_b1 = jc.b1 >= 0;
+            BodyPose p0, p1;
+            load_pose(P, jc.b0, w, p0);
+            float lv0[3], av0[3], lv1[3] = {0.f, 0.f, 0.f}, av1[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                lv0[k] = G(P.state, jc.b0 * B2P_STATE_FIELDS + 7 + k);
+                av0[k] = G(P.state, jc.b0 * B2P_STATE_FIELDS + 10 + k);
+            }
+            if (has_b1) {
+                load_pose(P, jc.b1, w, p1);
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    lv1[k] = G(P.state, jc.b1 * B2P_STATE_FIELDS + 7 + k);
+                    av1[k] = G(P.state, jc.b1 * B2P_STATE_FIELDS + 10 + k);
+                }
+            }
+            float axis[3];
+            mul_R_v(axis, p0.R, jc.axis1);
+            if (jc.type == 1) {
+                a1 = hinge_angle(jc, p0.q, p1.q, has_b1);
+                r1 = dot3(axis, av0);
+                if (has_b1) r1 -= dot3(axis, av1);
+                if (jc.reverse) { a1 = -a1; r1 = -r1; }
+            } else if (jc.type == 3) {
+                a1 = slider_position(jc, p0, p1, has_b1);
+                if (has_b1) r1 = dot3(axis, lv0) - dot3(axis, lv1);
+                else { r1 = dot3(axis, lv0); if (jc.reverse) r1 = -r1; }
+            } else if (jc.type == 2 && has_b1) {
+                a1 = hinge2_angle1(jc, p0, p1);
+                r1 = dot3(axis, av0) - dot3(axis, av1);
+                a2 = hinge2_angle2(jc, p0, p1);
+                float axis2[3];
+                mul_R_v(axis2, p1.R, jc.axis2);
+                r2 = dot3(axis2, av0) - dot3(axis2, av1);
+            }
+        }
+        G(P.jobs, j * 4 + 0) = a1;
+        G(P.jobs, j * 4 + 1) = r1;
+        G(P.jobs, j * 4 + 2) = a2;
+        G(P.jobs, j * 4 + 3) = r2;
+    }
+}
+
+} // namespace
+
+extern "C" size_t b2p_step_smem_bytes(int nb, int nj, int maxc, int rpc)
+{
+    const int njslots = nj * B2P_ROWS_PER_JOINT;
+    const int maxrows = njslots + maxc * rpc;
+    size_t s = sizeof(float) * (size_t)nb * 6 * BD;
+    s += sizeof(int) * (size_t)njslots;
+    s += sizeof(uint16_t) * (size_t)maxc * BD;
+    s += (size_t)maxrows * BD;
+    s += (size_t)nj * BD * 2;
+    s += (size_t)maxc * BD;
+    return (s + 15) & ~(size_t)15;
+}
+
+extern "C" int b2p_step_block_dim(void) { return BD; }
+
+extern "C" cudaError_t b2p_launch_step(const StepParams *P, size_t smem, cudaStream_t stream)
+{
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(b2p_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int grid = (P->W + BD - 1) / BD;
+    b2p_step_kernel<<<grid, BD, smem, stream>>>(*P);
+    return cudaGetLastError();
+}

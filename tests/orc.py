@@ -1,0 +1,427 @@
+"""ctypes access to the CPU oracle (oracle/build/liborc_f64.so / liborc_f32.so).
+
+TEST INFRASTRUCTURE: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference leg may import this module.  It is never on the product path.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+JOINT_HINGE, JOINT_HINGE2, JOINT_SLIDER, JOINT_FIXED, JOINT_CONTACT = 1, 2, 3, 6, 100
+ORDER_WORLD_BLOCK, ORDER_ODE_ISLANDS = 0, 1
+REORDER_RANDOMLY, REORDER_NONE = 0, 1
+
+
+class ContactDesc(C.Structure):
+    _fields_ = [("pos", C.c_double * 3), ("normal", C.c_double * 3), ("depth", C.c_double),
+                ("mode", C.c_int), ("mu", C.c_double), ("mu2", C.c_double), ("rho", C.c_double),
+                ("rho2", C.c_double), ("rhoN", C.c_double), ("bounce", C.c_double),
+                ("bounce_vel", C.c_double), ("soft_erp", C.c_double), ("soft_cfm", C.c_double),
+                ("motion1", C.c_double), ("motion2", C.c_double), ("motionN", C.c_double),
+                ("slip1", C.c_double), ("slip2", C.c_double)]
+
+
+class Mass(C.Structure):
+    _fields_ = [("mass", C.c_double), ("c", C.c_double * 3), ("I", C.c_double * 9)]
+
+
+class MarsContact(C.Structure):
+    _fields_ = [("frame1", C.c_int), ("frame2", C.c_int), ("pos", C.c_double * 3),
+                ("normal", C.c_double * 3), ("depth", C.c_double), ("cfm", C.c_double),
+                ("erp", C.c_double), ("friction1", C.c_double), ("friction2", C.c_double),
+                ("rolling_friction", C.c_double), ("rolling_friction2", C.c_double),
+                ("spinning_friction", C.c_double), ("bounce", C.c_double), ("bounce_vel", C.c_double),
+                ("motion1", C.c_double), ("motion2", C.c_double), ("fds1", C.c_double),
+                ("fds2", C.c_double)]
+
+
+class MarsJointCfg(C.Structure):
+    _fields_ = [("type", C.c_int), ("parent", C.c_int), ("child", C.c_int),
+                ("anchor", C.c_double * 3), ("axis1", C.c_double * 3), ("axis2", C.c_double * 3),
+                ("has_spring_damping", C.c_int), ("has_spring_stiffness", C.c_int),
+                ("has_joint_cfm", C.c_int), ("has_friction", C.c_int),
+                ("spring_damping", C.c_double), ("spring_stiffness", C.c_double),
+                ("joint_cfm", C.c_double), ("friction_coefficient", C.c_double)]
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+
+
+_libs = {}
+
+
+def load(single=False):
+    if single in _libs:
+        return _libs[single]
+    path = os.path.join(ORACLE_DIR, "build", "liborc_f32.so" if single else "liborc_f64.so")
+    if not os.path.exists(path):
+        build()
+    lib = C.CDLL(path)
+    P, D, I = C.c_void_p, C.c_double, C.c_int
+    DP = C.POINTER(C.c_double)
+    sig = {
+        "orc_real_size": (I, []),
+        "orc_world_create": (P, []), "orc_world_destroy": (None, [P]),
+        "orc_world_set_gravity": (None, [P, D, D, D]), "orc_world_set_erp": (None, [P, D]),
+        "orc_world_set_cfm": (None, [P, D]), "orc_world_set_max_angular_speed": (None, [P, D]),
+        "orc_world_set_contact_max_correcting_vel": (None, [P, D]),
+        "orc_world_set_contact_surface_layer": (None, [P, D]),
+        "orc_world_set_quickstep_num_iterations": (None, [P, I]),
+        "orc_world_set_quickstep_w": (None, [P, D]), "orc_world_set_order_mode": (None, [P, I]),
+        "orc_world_set_reorder_method": (None, [P, I]),
+        "orc_world_rand_set_seed": (None, [P, C.c_uint32]), "orc_world_rand_get_seed": (C.c_uint32, [P]),
+        "orc_world_quickstep": (None, [P, D]), "orc_world_last_num_rows": (I, [P]),
+        "orc_world_last_num_islands": (I, [P]), "orc_world_last_residual": (D, [P]),
+        "orc_world_num_bodies": (I, [P]), "orc_world_num_joints": (I, [P]),
+        "orc_world_num_contacts": (I, [P]),
+        "orc_rand_next": (C.c_uint32, [C.POINTER(C.c_uint32)]),
+        "orc_rand_int": (I, [C.POINTER(C.c_uint32), I]),
+        "orc_body_create": (I, [P]), "orc_body_set_mass": (None, [P, I, D, DP]),
+        "orc_body_get_mass": (None, [P, I, DP, DP]),
+        "orc_body_set_position": (None, [P, I, D, D, D]),
+        "orc_body_set_quaternion": (None, [P, I, D, D, D, D]),
+        "orc_body_set_linear_vel": (None, [P, I, D, D, D]),
+        "orc_body_set_angular_vel": (None, [P, I, D, D, D]),
+        "orc_body_set_force": (None, [P, I, D, D, D]), "orc_body_set_torque": (None, [P, I, D, D, D]),
+        "orc_body_add_force": (None, [P, I, D, D, D]), "orc_body_add_torque": (None, [P, I, D, D, D]),
+        "orc_body_add_force_at_pos": (None, [P, I, D, D, D, D, D, D]),
+        "orc_body_set_gravity_mode": (None, [P, I, I]), "orc_body_set_gyroscopic_mode": (None, [P, I, I]),
+        "orc_body_get_position": (None, [P, I, DP]), "orc_body_get_quaternion": (None, [P, I, DP]),
+        "orc_body_get_rotation": (None, [P, I, DP]), "orc_body_get_linear_vel": (None, [P, I, DP]),
+        "orc_body_get_angular_vel": (None, [P, I, DP]), "orc_body_get_force": (None, [P, I, DP]),
+        "orc_body_get_torque": (None, [P, I, DP]), "orc_body_get_state": (None, [P, I, DP]),
+        "orc_body_set_state": (None, [P, I, DP]),
+        "orc_joint_create": (I, [P, I, I, I]), "orc_joint_set_anchor": (None, [P, I, D, D, D]),
+        "orc_joint_set_axis1": (None, [P, I, D, D, D]), "orc_joint_set_axis2": (None, [P, I, D, D, D]),
+        "orc_joint_set_fixed": (None, [P, I]), "orc_joint_set_param": (None, [P, I, I, D]),
+        "orc_joint_get_param": (D, [P, I, I]), "orc_joint_get_anchor": (None, [P, I, DP]),
+        "orc_joint_get_anchor2": (None, [P, I, DP]), "orc_joint_get_axis1": (None, [P, I, DP]),
+        "orc_joint_get_axis2": (None, [P, I, DP]), "orc_joint_get_angle1": (D, [P, I]),
+        "orc_joint_get_angle1_rate": (D, [P, I]), "orc_joint_get_angle2": (D, [P, I]),
+        "orc_joint_get_angle2_rate": (D, [P, I]), "orc_joint_add_torque": (None, [P, I, D]),
+        "orc_joint_get_feedback": (None, [P, I, DP]), "orc_joint_get_num_rows": (I, [P, I]),
+        "orc_are_connected_excluding": (I, [P, I, I, I]),
+        "orc_contacts_clear": (None, [P]), "orc_contact_add": (I, [P, I, I, C.POINTER(ContactDesc)]),
+        "orc_contact_get_feedback": (None, [P, I, DP]),
+        "orc_mass_set_zero": (None, [C.POINTER(Mass)]),
+        "orc_mass_set_box_total": (None, [C.POINTER(Mass), D, D, D, D]),
+        "orc_mass_set_box": (None, [C.POINTER(Mass), D, D, D, D]),
+        "orc_mass_set_sphere_total": (None, [C.POINTER(Mass), D, D]),
+        "orc_mass_set_sphere": (None, [C.POINTER(Mass), D, D]),
+        "orc_mass_set_capsule_total": (None, [C.POINTER(Mass), D, I, D, D]),
+        "orc_mass_set_capsule": (None, [C.POINTER(Mass), D, I, D, D]),
+        "orc_mass_set_cylinder_total": (None, [C.POINTER(Mass), D, I, D, D]),
+        "orc_mass_set_cylinder": (None, [C.POINTER(Mass), D, I, D, D]),
+        "orc_mass_adjust": (None, [C.POINTER(Mass), D]),
+        "orc_mass_rotate": (None, [C.POINTER(Mass), DP]),
+        "orc_mass_translate": (None, [C.POINTER(Mass), D, D, D]),
+        "orc_mass_add": (None, [C.POINTER(Mass), C.POINTER(Mass)]),
+        "orc_mass_check": (I, [C.POINTER(Mass)]),
+        "orc_plane_space": (None, [DP, DP, DP]), "orc_q_to_R": (None, [DP, DP]),
+        # mars glue
+        "orc_mars_create": (P, []), "orc_mars_destroy": (None, [P]),
+        "orc_mars_init_the_world": (None, [P]), "orc_mars_world": (P, [P]),
+        "orc_mars_set_step_size": (None, [P, D]), "orc_mars_get_step_size": (D, [P]),
+        "orc_mars_clear_previous_step": (None, [P]), "orc_mars_step_the_world": (None, [P]),
+        "orc_mars_create_frame": (I, [P, D, D]),
+        "orc_mars_frame_add_object": (None, [P, I, C.POINTER(Mass), DP, DP]),
+        "orc_mars_frame_body": (I, [P, I]), "orc_mars_frame_acquire_body": (I, [P, I]),
+        "orc_mars_frame_get_position": (None, [P, I, DP]),
+        "orc_mars_frame_set_position": (None, [P, I, DP]),
+        "orc_mars_frame_get_rotation": (None, [P, I, DP]),
+        "orc_mars_frame_set_rotation": (None, [P, I, DP]),
+        "orc_mars_frame_get_linear_acceleration": (None, [P, I, DP]),
+        "orc_mars_frame_get_contact_force": (None, [P, I, DP]),
+        "orc_mars_frame_get_mass": (None, [P, I, DP, DP]),
+        "orc_mars_frame_add_contact": (I, [P, I, C.POINTER(MarsContact)]),
+        "orc_mars_create_joint": (I, [P, C.POINTER(MarsJointCfg)]),
+        "orc_mars_joint_set_force_limit": (None, [P, I, D]),
+        "orc_mars_joint_set_velocity": (None, [P, I, D]),
+        "orc_mars_joint_set_velocity2": (None, [P, I, D]),
+        "orc_mars_joint_set_joint_as_motor": (None, [P, I, I]),
+        "orc_mars_joint_get_position": (D, [P, I]), "orc_mars_joint_get_velocity": (D, [P, I]),
+        "orc_mars_joint_get_motor_torque": (D, [P, I]),
+        "orc_mars_joint_get_axis_torque": (None, [P, I, DP]),
+        "orc_mars_joint_get_joint_load": (None, [P, I, DP]),
+        "orc_mars_joint_ode_id": (I, [P, I]),
+        "orc_mars_build_reproducable_scene": (None, [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "orc_mars_reproducable_tick": (I, [P, C.POINTER(C.c_int), C.POINTER(C.c_int), D]),
+        "orc_mars_run_reproducable_test": (I, [C.c_char_p, D, I, DP]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _libs[single] = lib
+    return lib
+
+
+def _d(n):
+    return (C.c_double * n)()
+
+
+class OracleBatch:
+    """W independent oracle worlds behind the method names of mars_ode_physics_b200.Arena."""
+
+    def __init__(self, num_worlds, single=False):
+        self.lib = load(single)
+        self.num_worlds = num_worlds
+        self.worlds = [self.lib.orc_world_create() for _ in range(num_worlds)]
+        self.max_contacts = 8
+
+    def close(self):
+        for w in self.worlds:
+            self.lib.orc_world_destroy(w)
+        self.worlds = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _sel(self, world):
+        return self.worlds if world == -1 else [self.worlds[world]]
+
+    def _all(self, fn, *a):
+        r = None
+        for w in self.worlds:
+            r = fn(w, *a)
+        return r
+
+    # world
+    def set_max_contacts(self, n):
+        self.max_contacts = n
+
+    def enable_rolling_friction(self, on=True):
+        pass
+
+    def set_gravity(self, x, y, z):
+        self._all(self.lib.orc_world_set_gravity, x, y, z)
+
+    def set_cfm(self, v):
+        self._all(self.lib.orc_world_set_cfm, v)
+
+    def set_erp(self, v):
+        self._all(self.lib.orc_world_set_erp, v)
+
+    def set_max_angular_speed(self, v):
+        self._all(self.lib.orc_world_set_max_angular_speed, v)
+
+    def set_contact_max_correcting_vel(self, v):
+        self._all(self.lib.orc_world_set_contact_max_correcting_vel, v)
+
+    def set_contact_surface_layer(self, v):
+        self._all(self.lib.orc_world_set_contact_surface_layer, v)
+
+    def set_quickstep_num_iterations(self, n):
+        self._all(self.lib.orc_world_set_quickstep_num_iterations, n)
+
+    def set_quickstep_w(self, v):
+        self._all(self.lib.orc_world_set_quickstep_w, v)
+
+    def set_reorder_method(self, m):
+        self._all(self.lib.orc_world_set_reorder_method, m)
+
+    def set_order_mode(self, m):
+        self._all(self.lib.orc_world_set_order_mode, m)
+
+    def rand_set_seed(self, seed):
+        self._all(self.lib.orc_world_rand_set_seed, seed)
+
+    def rand_get_seed(self, world):
+        return self.lib.orc_world_rand_get_seed(self.worlds[world])
+
+    # bodies
+    def body_create(self):
+        return self._all(self.lib.orc_body_create)
+
+    def body_set_mass(self, b, mass, I):
+        arr = (C.c_double * 9)(*[float(x) for x in np.asarray(I, dtype=float).reshape(9)])
+        self._all(self.lib.orc_body_set_mass, b, mass, arr)
+
+    def _set(self, fn, b, v, world):
+        for w in self._sel(world):
+            fn(w, b, *map(float, v))
+
+    def body_set_position(self, b, p, world=-1):
+        self._set(self.lib.orc_body_set_position, b, p, world)
+
+    def body_set_quaternion(self, b, q, world=-1):
+        self._set(self.lib.orc_body_set_quaternion, b, q, world)
+
+    def body_set_linear_vel(self, b, v, world=-1):
+        self._set(self.lib.orc_body_set_linear_vel, b, v, world)
+
+    def body_set_angular_vel(self, b, v, world=-1):
+        self._set(self.lib.orc_body_set_angular_vel, b, v, world)
+
+    def body_set_force(self, b, v, world=-1):
+        self._set(self.lib.orc_body_set_force, b, v, world)
+
+    def body_set_torque(self, b, v, world=-1):
+        self._set(self.lib.orc_body_set_torque, b, v, world)
+
+    def body_add_force(self, b, v, world=-1):
+        self._set(self.lib.orc_body_add_force, b, v, world)
+
+    def body_add_torque(self, b, v, world=-1):
+        self._set(self.lib.orc_body_add_torque, b, v, world)
+
+    def body_add_force_at_pos(self, b, f, p, world=-1):
+        for w in self._sel(world):
+            self.lib.orc_body_add_force_at_pos(w, b, *map(float, f), *map(float, p))
+
+    def body_set_gravity_mode(self, b, on):
+        self._all(self.lib.orc_body_set_gravity_mode, b, int(on))
+
+    def body_set_gyroscopic_mode(self, b, on):
+        self._all(self.lib.orc_body_set_gyroscopic_mode, b, int(on))
+
+    def _get(self, fn, n, world, *ids):
+        out = _d(n)
+        fn(self.worlds[world], *ids, out)
+        return np.array(out[:], dtype=float)
+
+    def body_get_position(self, b, world=0):
+        return self._get(self.lib.orc_body_get_position, 3, world, b)
+
+    def body_get_quaternion(self, b, world=0):
+        return self._get(self.lib.orc_body_get_quaternion, 4, world, b)
+
+    def body_get_rotation(self, b, world=0):
+        return self._get(self.lib.orc_body_get_rotation, 9, world, b)
+
+    def body_get_linear_vel(self, b, world=0):
+        return self._get(self.lib.orc_body_get_linear_vel, 3, world, b)
+
+    def body_get_angular_vel(self, b, world=0):
+        return self._get(self.lib.orc_body_get_angular_vel, 3, world, b)
+
+    def body_get_force(self, b, world=0):
+        return self._get(self.lib.orc_body_get_force, 3, world, b)
+
+    def body_get_torque(self, b, world=0):
+        return self._get(self.lib.orc_body_get_torque, 3, world, b)
+
+    def body_get_state(self, b, world=0):
+        return self._get(self.lib.orc_body_get_state, 13, world, b)
+
+    def body_set_state(self, b, s, world=-1):
+        arr = (C.c_double * 13)(*map(float, s))
+        for w in self._sel(world):
+            self.lib.orc_body_set_state(w, b, arr)
+
+    def state_download(self, num_bodies, out=None):
+        if out is None:
+            out = np.empty((num_bodies, 13, self.num_worlds), dtype=np.float64)
+        buf = _d(13)
+        for wi, w in enumerate(self.worlds):
+            for b in range(num_bodies):
+                self.lib.orc_body_get_state(w, b, buf)
+                out[b, :, wi] = buf[:]
+        return out
+
+    # joints
+    def joint_create(self, jtype, b1, b2):
+        return self._all(self.lib.orc_joint_create, jtype, b1, b2)
+
+    def joint_set_anchor(self, j, p):
+        self._all(self.lib.orc_joint_set_anchor, j, *map(float, p))
+
+    def joint_set_axis1(self, j, a):
+        self._all(self.lib.orc_joint_set_axis1, j, *map(float, a))
+
+    def joint_set_axis2(self, j, a):
+        self._all(self.lib.orc_joint_set_axis2, j, *map(float, a))
+
+    def joint_set_fixed(self, j):
+        self._all(self.lib.orc_joint_set_fixed, j)
+
+    def joint_set_param(self, j, param, value, world=-1):
+        for w in self._sel(world):
+            self.lib.orc_joint_set_param(w, j, param, float(value))
+
+    def joint_get_param(self, j, param, world=0):
+        return self.lib.orc_joint_get_param(self.worlds[world], j, param)
+
+    def joint_set_param_batch(self, j, param, values):
+        for w, v in zip(self.worlds, values):
+            self.lib.orc_joint_set_param(w, j, param, float(v))
+
+    def joint_get_anchor(self, j, world=0):
+        return self._get(self.lib.orc_joint_get_anchor, 3, world, j)
+
+    def joint_get_anchor2(self, j, world=0):
+        return self._get(self.lib.orc_joint_get_anchor2, 3, world, j)
+
+    def joint_get_axis1(self, j, world=0):
+        return self._get(self.lib.orc_joint_get_axis1, 3, world, j)
+
+    def joint_get_axis2(self, j, world=0):
+        return self._get(self.lib.orc_joint_get_axis2, 3, world, j)
+
+    def joint_get_angle1(self, j, world=0):
+        return self.lib.orc_joint_get_angle1(self.worlds[world], j)
+
+    def joint_get_angle1_rate(self, j, world=0):
+        return self.lib.orc_joint_get_angle1_rate(self.worlds[world], j)
+
+    def joint_get_angle2(self, j, world=0):
+        return self.lib.orc_joint_get_angle2(self.worlds[world], j)
+
+    def joint_get_angle2_rate(self, j, world=0):
+        return self.lib.orc_joint_get_angle2_rate(self.worlds[world], j)
+
+    def joint_add_torque(self, j, t, world=-1):
+        for w in self._sel(world):
+            self.lib.orc_joint_add_torque(w, j, float(t))
+
+    def joint_get_feedback(self, j, world=0):
+        return self._get(self.lib.orc_joint_get_feedback, 13, world, j)
+
+    def joint_get_num_rows(self, j, world=0):
+        return self.lib.orc_joint_get_num_rows(self.worlds[world], j)
+
+    # contacts
+    def contacts_clear(self, world=-1):
+        for w in self._sel(world):
+            self.lib.orc_contacts_clear(w)
+
+    def contact_add(self, world, b1, b2, **kw):
+        d = ContactDesc()
+        d.pos[:] = [float(x) for x in kw["pos"]]
+        d.normal[:] = [float(x) for x in kw["normal"]]
+        d.depth = float(kw["depth"])
+        d.mode = int(kw["mode"])
+        for k in ("mu", "mu2", "rho", "rho2", "rhoN", "soft_erp", "soft_cfm"):
+            setattr(d, k, float(kw.get(k, 0.0)))
+        return self.lib.orc_contact_add(self.worlds[world], b1, b2, C.byref(d))
+
+    def contact_count(self, world=0):
+        return self.lib.orc_world_num_contacts(self.worlds[world])
+
+    def contact_get_feedback(self, world, c):
+        out = _d(12)
+        self.lib.orc_contact_get_feedback(self.worlds[world], c, out)
+        return np.array(out[:3], dtype=float)
+
+    # step
+    def step(self, h):
+        for w in self.worlds:
+            self.lib.orc_world_quickstep(w, float(h))
+
+    def sync(self):
+        pass
+
+    def last_num_rows(self, world=0):
+        return self.lib.orc_world_last_num_rows(self.worlds[world])
+
+    def last_residual(self, world=0):
+        return self.lib.orc_world_last_residual(self.worlds[world])

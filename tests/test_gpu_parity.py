@@ -1,0 +1,142 @@
+"""GPU parity: the CUDA step (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bars (north_star): row / contact counts and RNG state exact (integer work); poses and velocities
+within a stated floating-point tolerance over a fixed short horizon; LCP residual bounded.
+The device computes in fp32; the oracle is built in fp64 (the reference) and fp32 (same
+arithmetic width, used to separate algorithmic mismatch from rounding).
+"""
+import math
+
+import numpy as np
+import pytest
+
+import orc
+from mars_ode_physics_b200 import Arena, capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+H = 0.001
+
+
+def _max_state_err(a, b, nb):
+    sa = a.state_download(nb).astype(np.float64)
+    sb = b.state_download(nb).astype(np.float64)
+    # quaternion sign ambiguity cannot occur (same integration), compare directly
+    d = np.abs(sa - sb)
+    return {"pos": d[:, 0:3].max(), "quat": d[:, 3:7].max(), "lvel": d[:, 7:10].max(), "avel": d[:, 10:13].max()}
+
+
+def test_free_bodies_ballistic(cuda_lib):
+    W = 40
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    for be in (ar, oc):
+        scenes.setup_world(be)
+        be.set_max_contacts(0)
+        for i in range(3):
+            b = scenes.add_body(be, 1.0 + i, scenes.inertia_box(1.0 + i, 0.3, 0.2, 0.1), (i, 0, 1))
+        for w in range(W):
+            for b in range(3):
+                be.body_set_linear_vel(b, (0.1 * w, -0.2 * b, 1.0), w)
+                be.body_set_angular_vel(b, (0.5 * b, 0.3 * w, -1.0), w)
+    for _ in range(100):
+        ar.step(H)
+        oc.step(H)
+    e = _max_state_err(ar, oc, 3)
+    assert e["pos"] < 2e-6 and e["quat"] < 2e-6 and e["lvel"] < 2e-5 and e["avel"] < 2e-5, e
+
+
+def test_pendulum_chain_parity(cuda_lib):
+    W = 33  # not a multiple of 32 on purpose (padded lanes)
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    for be in (ar, oc):
+        sc = scenes.pendulum_chain(be, 3)
+        for w in range(W):
+            be.body_set_angular_vel(sc["bodies"][2], (0, 0.05 * w, 0.0), w)
+    nb = 3
+    for step in range(200):
+        ar.step(H)
+        oc.step(H)
+        if step in (0, 9, 199):
+            for w in (0, 7, W - 1):
+                assert ar.last_num_rows(w) == oc.last_num_rows(w) == 15
+                assert ar.rand_get_seed(w) == oc.rand_get_seed(w)
+    e = _max_state_err(ar, oc, nb)
+    # tolerance: fp32 device vs fp64 oracle over 200 steps
+    assert e["pos"] < 1e-4 and e["quat"] < 1e-4 and e["lvel"] < 2e-3 and e["avel"] < 5e-3, e
+    # feedback of the first hinge (holds the chain against gravity)
+    fa, fo = ar.joint_get_feedback(0, 3), oc.joint_get_feedback(0, 3)
+    assert np.allclose(fa, fo, rtol=2e-3, atol=2e-3), (fa, fo)
+    assert abs(ar.joint_get_angle1(1, 5) - oc.joint_get_angle1(1, 5)) < 1e-4
+
+
+def _run_quadruped(ar, oc, W, steps, check_every=1):
+    scs = []
+    for be in (ar, oc):
+        scs.append(scenes.quadruped(be))
+    sa, so = scs
+    phases = [0.37 * w for w in range(W)]
+    nb = len(sa["bodies"])
+    worst = {"pos": 0.0, "quat": 0.0, "lvel": 0.0, "avel": 0.0}
+    t = 0.0
+    for step in range(steps):
+        for be, sc in ((ar, sa), (oc, so)):
+            be.contacts_clear()
+            for w in range(W):
+                scenes.quadruped_control(be, sc, t, w, phases[w])
+                scenes.sphere_plane_contacts(be, sc["feet"], sc["foot_radius"], w)
+        # integer parity before the step: contact sets
+        for w in range(W):
+            assert ar.contact_count(w) == oc.contact_count(w), (step, w)
+        ar.step(H)
+        oc.step(H)
+        t += H
+        if step % check_every == 0:
+            for w in range(W):
+                assert ar.last_num_rows(w) == oc.last_num_rows(w), (step, w)
+                assert ar.rand_get_seed(w) == oc.rand_get_seed(w), (step, w)
+            e = _max_state_err(ar, oc, nb)
+            for k in worst:
+                worst[k] = max(worst[k], e[k])
+    return worst, sa, so
+
+
+def test_quadruped_parity_f64_oracle(cuda_lib):
+    """Config C topology, 8 worlds with different gait phases, 150 steps, fp32 device vs fp64 oracle."""
+    W = 8
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    worst, sa, so = _run_quadruped(ar, oc, W, 150, check_every=10)
+    print("quadruped fp32-vs-fp64 worst errors:", worst)
+    assert worst["pos"] < 5e-4 and worst["quat"] < 2e-3 and worst["lvel"] < 5e-2 and worst["avel"] < 0.5, worst
+    # residual of the oracle's LCP after 20 iterations stays bounded
+    assert max(oc.last_residual(w) for w in range(W)) < 50.0
+    # feedback / contact force parity on the last step
+    for w in (0, W - 1):
+        for c in range(ar.contact_count(w)):
+            fa, fo = ar.contact_get_feedback(w, c), oc.contact_get_feedback(w, c)
+            assert np.allclose(fa, fo, rtol=5e-2, atol=5e-2), (fa, fo)
+
+
+def test_quadruped_parity_strict_f32_oracle(cuda_lib):
+    """Same scene, -fmad=false build vs the float build of the oracle: same arithmetic width and
+    operation order, so the trajectories must agree much more tightly than fp32-vs-fp64."""
+    W = 4
+    ar, oc = Arena(W, strict=True), orc.OracleBatch(W, single=True)
+    worst, _, _ = _run_quadruped(ar, oc, W, 60, check_every=5)
+    print("quadruped strict-fp32-vs-fp32-oracle worst errors:", worst)
+    assert worst["pos"] < 2e-5 and worst["quat"] < 1e-4 and worst["lvel"] < 5e-3 and worst["avel"] < 5e-2, worst
+
+
+def test_determinism_bitwise(cuda_lib):
+    """The reference's own criterion (scripts/reproducable_test.sh): two runs, identical output."""
+    outs = []
+    for _ in range(2):
+        ar = Arena(64)
+        sc = scenes.quadruped(ar)
+        for step in range(30):
+            ar.contacts_clear()
+            for w in range(0, 64, 9):
+                scenes.sphere_plane_contacts(ar, sc["feet"], sc["foot_radius"], w)
+            ar.step(H)
+        outs.append(ar.state_download(len(sc["bodies"])).copy())
+        ar.close()
+    assert np.array_equal(outs[0], outs[1])
