@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- batched world-steps/sec of the stepTheWorld hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # CPU path on the host cores
+
+Workload (config D of BASELINE.json / SURVEY.md section 8d): 65536 worlds PER GPU of a wheeled rover --
+chassis box + 4 wheels on hinge2 joints (steer axis locked by stops, drive axis motorised) --
+driving on one heightfield (256x256 @ 0.1 m) shared by all worlds; dt 1 ms, 20 SOR iterations,
+ODE row order with LCG shuffles.  One "step" = device collision (broadphase + narrowphase, which
+regenerates the contact stream) + the fused assemble / SOR-LCP / integrate kernel over all worlds.
+Worlds shard over GPUs with no collective on the step path (weak scaling: per-GPU work fixed).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the
+C ABI with host buffers (pinned H2D of the per-world wheel commands and D2H of the chassis state
+inside the timed region).  The per-step working set (row scratch ~0.4 GB per 65536 worlds) is
+larger than the 126 MB L2, so no explicit L2 flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = 0.001
+WORLDS_PER_GPU = 65536
+METRIC = "batched world-steps/sec"
+UNIT = "world-steps/s"
+WORKLOAD = "D: hinge2 rover (5 bodies, 4 hinge2, sphere wheels) on shared 256x256 heightfield, dt=1ms, 20 SOR iters"
+
+
+def build_rover_worlds(be, num_worlds, world_offset=0, torch_free=True):
+    """Config D scene on any backend; per-world placement / wheel speed from splitmix64(0xD ^ id)."""
+    from mars_ode_physics_b200 import capi, scenes
+    sc = scenes.rover(be, with_geoms=True)
+    heights, x0, y0 = scenes.terrain_heights()
+    be.geom_create_heightfield(heights, 0.1, x0, y0,
+                               surface={"mu": 1.0, "mu2": 1.0, "soft_erp": 0.2, "soft_cfm": 1e-5})
+    ids = np.arange(world_offset, world_offset + num_worlds, dtype=np.uint64)
+    ux = np.array([scenes.uniform01(0xD, int(i), 1) for i in ids]) if num_worlds <= 4096 else \
+        scenes.uniform01_array(0xD, world_offset + num_worlds, 1)[world_offset:]
+    uy = np.array([scenes.uniform01(0xD, int(i), 2) for i in ids]) if num_worlds <= 4096 else \
+        scenes.uniform01_array(0xD, world_offset + num_worlds, 2)[world_offset:]
+    uv = np.array([scenes.uniform01(0xD, int(i), 3) for i in ids]) if num_worlds <= 4096 else \
+        scenes.uniform01_array(0xD, world_offset + num_worlds, 3)[world_offset:]
+    dx, dy = 16.0 * ux - 8.0, 16.0 * uy - 8.0
+    vel = (2.0 + 4.0 * uv).astype(np.float32)
+    nb = len(sc["bodies"])
+    st = be.state_download(nb)
+    st = np.array(st, dtype=st.dtype)
+    st[:, 0, :] += dx.astype(st.dtype)
+    st[:, 1, :] += dy.astype(st.dtype)
+    st[:, 2, :] += 0.12
+    if hasattr(be, "state_upload"):
+        be.state_upload(st)
+    else:
+        for w in range(num_worlds):
+            for b in range(nb):
+                be.body_set_state(b, st[b, :, w], w)
+    for j in sc["joints"]:
+        be.joint_set_param_batch(j, capi.PARAM_VEL | capi.PARAM_GROUP2, vel)
+    sc["vel"] = vel
+    return sc
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [p.strip() for p in out.stdout.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.15)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples), "power_w_max": max(float(s[2]) for s in self.samples)}
+
+
+def cpu_baseline(sample_worlds, steps, threads):
+    """The oracle (CPU restatement of ODE quickstep + the collision spec) on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc  # test infrastructure; used here only as the reported CPU baseline
+    from concurrent.futures import ThreadPoolExecutor
+    oc = orc.OracleBatch(sample_worlds)
+    build_rover_worlds(oc, sample_worlds)
+    per = (sample_worlds + threads - 1) // threads
+    chunks = [(i, min(i + per, sample_worlds)) for i in range(0, sample_worlds, per)]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(lambda c: oc.bench_run(c[0], c[1], 5, H, 1), chunks))  # warm-up
+        t0 = time.perf_counter()
+        list(ex.map(lambda c: oc.bench_run(c[0], c[1], steps, H, 1), chunks))
+        dt = time.perf_counter() - t0
+    return sample_worlds * steps / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path (libode is not available, so this is the
+    oracle port of ODE-0.16 quickstep) on all host threads, same config / metric, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 32 * cores
+    steps_per = 60
+    vals = []
+    for _ in range(max(1, args.warmup)):
+        cpu_baseline(sample, 10, cores)
+    t_total = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_baseline(sample, steps_per, cores)
+        vals.append(v)
+        t_total += dt
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "worlds_per_sample": sample, "world_steps_per_step": sample * steps_per},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} worlds x {steps_per} steps per bench step, oracle f64, {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from mars_ode_physics_b200 import Arena, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W = args.worlds
+    ar = Arena(W, device=local_rank)
+    stream = torch.cuda.current_stream()
+    ar.set_stream(stream.cuda_stream)
+    sc = build_rover_worlds(ar, W, world_offset=rank * W)
+    nb, nj = len(sc["bodies"]), len(sc["joints"])
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident loop ----------------
+    for _ in range(max(args.warmup, 3)):
+        ar.collide()
+        ar.step(H)
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    launches0 = ar.kernel_launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(stream)
+    for k in range(K):
+        ev[k][0].record(stream)
+        ar.collide()
+        ev[k][1].record(stream)
+        ar.step(H)
+        ev[k][2].record(stream)
+    end.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms = start.elapsed_time(end)
+    launches = ar.kernel_launch_count() - launches0
+    collide_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+    step_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+
+    # ---------------- end-to-end loop through the C ABI with host buffers ----------------
+    cmd = torch.empty((nj, W), dtype=torch.float32).pin_memory()
+    cmd[:] = torch.from_numpy(sc["vel"])[None, :]
+    obs = torch.empty((13, W), dtype=torch.float32).pin_memory()
+    param = capi.PARAM_VEL | capi.PARAM_GROUP2
+    for _ in range(3):
+        for ji, j in enumerate(sc["joints"]):
+            ar.joint_set_param_batch_ptr(j, param, cmd[ji].data_ptr())
+        ar.collide()
+        ar.step(H)
+        ar.body_get_state_batch_ptr(sc["chassis"], obs.data_ptr())
+        ar.sync()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(K):
+        cmd.add_(0.001)  # new commands every step (host side)
+        for ji, j in enumerate(sc["joints"]):
+            ar.joint_set_param_batch_ptr(j, param, cmd[ji].data_ptr())
+        ar.collide()
+        ar.step(H)
+        ar.body_get_state_batch_ptr(sc["chassis"], obs.data_ptr())
+        ar.sync()  # the caller reads the observation before issuing the next command
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+    ms_e2e = e0.elapsed_time(e1)
+    assert np.isfinite(obs.numpy()).all(), "non-finite chassis state"
+
+    # ---------------- reduce over ranks (max time) ----------------
+    t = torch.tensor([ms, ms_e2e, step_ms, collide_ms], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e, step_ms, collide_ms = [float(x) for x in t.cpu()]
+    total_worlds = W * world_size
+    value = total_worlds * K / (ms * 1e-3)
+    e2e_value = total_worlds * K / (ms_e2e * 1e-3)
+
+    balg = ar.algorithmic_bytes_per_world_step()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = balg * W / (step_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("step_kernel_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "worlds_per_gpu": W, "total_worlds": total_worlds,
+                       "sharding": f"worlds/{world_size} GPUs, no collective on the step path",
+                       "l2": "per-step working set (row scratch) > L2; no flush needed",
+                       "mean_rows_per_world": float(np.mean([ar.last_num_rows(w) for w in range(0, W, max(1, W // 64))])),
+                       "kernel_ms": {"collide": collide_ms, "step": step_ms}},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nj * W * 4),
+                    "d2h_bytes_per_step": int(13 * W * 4), "ms_per_step": ms_e2e / K},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "b2p_step_kernel",
+                         "algorithmic_bytes_per_world_step": balg,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+            "clocks": sampler.summary(),
+            "wall_s": t_wall,
+        }
+        if not args.no_cpu_baseline and world_size == 1:
+            cores = os.cpu_count() or 1
+            sample = 32 * cores
+            v, dt = cpu_baseline(sample, 100, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{sample} worlds x 100 steps of the same workload, oracle f64 "
+                                              f"(CPU restatement, not libode), {cores} threads, {dt:.1f} s"}
+        print(json.dumps(line))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--worlds", type=int, default=WORLDS_PER_GPU, help="worlds per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

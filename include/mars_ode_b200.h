@@ -169,6 +169,9 @@ int b2p_body_set_state(b2p_arena *a, int body, int world, const double in[13]);
 /* batched state I/O in the device layout: float[num_bodies][13][num_worlds] */
 int b2p_state_upload(b2p_arena *a, const float *host_state);
 int b2p_state_download(b2p_arena *a, float *host_state);
+/* one body of every world: float[13][num_worlds] (asynchronous on the arena stream; call
+ * b2p_sync before reading the host buffer) */
+int b2p_body_get_state_batch(b2p_arena *a, int body, float *host_out);
 /* device pointers (float, layout [field][padded_worlds]) for zero-copy consumers */
 int b2p_padded_worlds(const b2p_arena *a);
 void *b2p_device_state(b2p_arena *a);       /* [nb*13][Wp] */

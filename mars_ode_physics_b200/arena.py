@@ -169,6 +169,10 @@ class Arena:
         self._check(self.lib.b2p_state_download(self.h, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def body_get_state_batch_ptr(self, b, host_ptr):
+        """Asynchronous D2H of float[13][num_worlds] into (pinned) host memory; sync() before reading."""
+        self._check(self.lib.b2p_body_get_state_batch(self.h, b, C.c_void_p(host_ptr)))
+
     # -- joints -----------------------------------------------------------------------------
     def joint_create(self, jtype, b1, b2):
         return self._check(self.lib.b2p_joint_create(self.h, jtype, b1, b2))

@@ -93,6 +93,7 @@ SIGNATURES = {
     "b2p_body_set_state": (_I, [_P, _I, _I, _DP]),
     "b2p_state_upload": (_I, [_P, _P]),
     "b2p_state_download": (_I, [_P, _P]),
+    "b2p_body_get_state_batch": (_I, [_P, _I, _P]),
     "b2p_padded_worlds": (_I, [_P]),
     "b2p_device_state": (_P, [_P]),
     "b2p_device_joint_cmd": (_P, [_P]),

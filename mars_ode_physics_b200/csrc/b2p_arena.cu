@@ -22,7 +22,7 @@
 extern "C" size_t b2p_step_smem_bytes(int nb, int nj, int maxc, int rpc);
 extern "C" int b2p_step_block_dim(void);
 extern "C" cudaError_t b2p_launch_step(const StepParams *P, size_t smem, cudaStream_t stream);
-extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, cudaStream_t stream);
+extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, cudaStream_t stream);
 
 namespace {
 
@@ -972,6 +972,18 @@ int b2p_state_download(b2p_arena *a, float *host_state)
     return 0;
 }
 
+int b2p_body_get_state_batch(b2p_arena *a, int body, float *host_out)
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    if (!host_out) return fail(B2P_EINVAL, "host_out is null");
+    if ((rc = mirror_to_device(a, a->state))) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(host_out, sizeof(float) * a->W,
+                               a->state.dev + (size_t)body * B2P_STATE_FIELDS * a->Wp, sizeof(float) * a->Wp,
+                               sizeof(float) * a->W, B2P_STATE_FIELDS, cudaMemcpyDeviceToHost, a->stream));
+    return 0;
+}
+
 void *b2p_device_state(b2p_arena *a) { return a ? a->state.dev : nullptr; }
 void *b2p_device_joint_cmd(b2p_arena *a) { return a ? a->jcmd.dev : nullptr; }
 void *b2p_device_joint_obs(b2p_arena *a) { return a ? a->jobs.dev : nullptr; }
@@ -1613,11 +1625,11 @@ int b2p_collide(b2p_arena *a)
     if (rc) return rc;
     const int ng = (int)a->geoms.size();
     const int maxpairs = ng * (ng - 1) / 2;
-    if (maxpairs > a->maxpairs) {
+    if (maxpairs > a->maxpairs || !a->d_npairs) {
         if (a->d_pairs) cudaFree(a->d_pairs);
         if (a->d_npairs) cudaFree(a->d_npairs);
         a->d_pairs = a->d_npairs = nullptr;
-        CUDA_TRY(cudaMalloc(&a->d_pairs, sizeof(int) * (size_t)maxpairs * a->Wp));
+        CUDA_TRY(cudaMalloc(&a->d_pairs, sizeof(int) * (size_t)std::max(maxpairs, 1) * a->Wp));
         CUDA_TRY(cudaMalloc(&a->d_npairs, sizeof(int) * (size_t)a->Wp));
         a->maxpairs = maxpairs;
     }
@@ -1631,7 +1643,8 @@ int b2p_collide(b2p_arena *a)
     P.pairs = a->d_pairs;
     P.npairs = a->d_npairs;
     P.maxpairs = a->maxpairs;
-    CUDA_TRY(b2p_launch_collide(&P, a->stream));
+    if ((size_t)ng * 6 * 128 * sizeof(float) > 200 * 1024) return fail(B2P_ECAPACITY, "too many geoms for the collide kernel");
+    CUDA_TRY(b2p_launch_collide(&P, ng, a->stream));
     a->launches++;
     a->crec.dev_newer = true;
     a->ccount.dev_newer = true;

@@ -217,6 +217,25 @@ void orc_mass_translate(orc_mass *m, double x, double y, double z);
 void orc_mass_add(orc_mass *a, const orc_mass *b);
 int orc_mass_check(const orc_mass *m);
 
+/* ---- collision (orc_collide.c): defines the semantics the device kernels are checked against ---- */
+typedef struct orc_surface {
+    double mu, mu2;
+    double rho, rho2, rhoN;
+    double soft_erp, soft_cfm;
+} orc_surface;
+/* cls: 0 sphere(r) 1 box(lx,ly,lz) 2 capsule(r,len) 3 cylinder(r,len) 4 plane(a,b,c,d) 5 heightfield */
+int orc_geom_create(orc_world *w, int cls, int body, const double dims[4], const double lpos[3],
+                    const double lquat[4], const orc_surface *s);
+int orc_geom_create_heightfield(orc_world *w, const float *heights, int nx, int ny, double dx, double x0,
+                                double y0, const orc_surface *s);
+void orc_world_set_max_contacts(orc_world *w, int n);
+int orc_collide(orc_world *w); /* replaces the contact group; returns the number of contacts */
+int orc_collide_get_pairs(const orc_world *w, int *pairs, int max_pairs); /* g1 | g2<<16, sorted */
+int orc_contact_get(const orc_world *w, int c, int *b1, int *b2, orc_contact_desc *out);
+
+/* timing helper for bench.py's cpu_baseline: collide (optional) + quickstep, `steps` times over n worlds */
+void orc_bench_run(orc_world **worlds, int n, int steps, double h, int do_collide);
+
 /* small math helpers exposed for unit tests */
 void orc_plane_space(const double n[3], double p[3], double q[3]);
 void orc_q_to_R(const double q[4], double R[9]);

@@ -16,21 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#ifdef ORC_SINGLE
-typedef float real;
-#define R_SQRT sqrtf
-#define R_FABS fabsf
-#define R_ATAN2 atan2f
-#define ORC_DEFAULT_CFM 1e-5
-#else
-typedef double real;
-#define R_SQRT sqrt
-#define R_FABS fabs
-#define R_ATAN2 atan2
-#define ORC_DEFAULT_CFM 1e-10
-#endif
-
-#define R_INF ((real)INFINITY)
+#include "orc_internal.h"
 #define R_PI ((real)3.14159265358979323846)
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -250,60 +236,6 @@ int orc_rand_int(uint32_t *seed, int n)
     return (int)(r % un);
 }
 
-/* ------------------------------------------------------------------ */
-/* data                                                                */
-
-typedef struct {
-    real vel, fmax, lostop, histop, fudge_factor, normal_cfm, stop_erp, stop_cfm, bounce;
-    int limit;
-    real limit_err;
-} limot_t;
-
-typedef struct {
-    real pos[3], q[4], R[9], lvel[3], avel[3], facc[3], tacc[3];
-    real mass, invMass, I[9], invI[9];
-    int gyroscopic, nogravity, has_max_ang;
-    real max_angular_speed;
-    /* per-step scratch */
-    real invI_w[9];
-    int tag;
-} body_t;
-
-typedef struct {
-    int type;
-    int b[2]; /* node[0].body, node[1].body after attach (index or -1) */
-    int reverse;
-    unsigned creation_serial; /* attach order, for the island DFS */
-    real anchor1[3], anchor2[3], axis1[3], axis2[3], qrel[4], offset[3];
-    limot_t limot1, limot2;
-    /* hinge2 */
-    real c0, s0, v1[3], v2[3], w1[3], w2[3], susp_erp, susp_cfm;
-    /* fixed */
-    real erp, cfm;
-    /* contact */
-    orc_contact_desc contact;
-    /* outputs */
-    real fb_f1[3], fb_t1[3], fb_f2[3], fb_t2[3], fb_lambda;
-    int last_m;
-    int limot_row; /* local row of the limot that feeds fb_lambda, or -1 */
-    int tag;
-} joint_t;
-
-struct orc_world {
-    real gravity[3], erp, cfm, max_angular_speed, contact_max_vel, contact_min_depth, sor_w;
-    int iters, order_mode, reorder_method;
-    uint32_t seed;
-    body_t *bodies;
-    int nb, capb;
-    joint_t *joints;
-    int nj, capj;
-    joint_t *contacts;
-    int nc, capc;
-    unsigned serial;
-    int last_m, last_islands;
-    real last_residual;
-};
-
 int orc_real_size(void) { return (int)sizeof(real); }
 
 static void limot_init(limot_t *l, const orc_world *w)
@@ -389,6 +321,7 @@ orc_world *orc_world_create(void)
     w->order_mode = ORC_ORDER_WORLD_BLOCK;
     w->reorder_method = ORC_REORDER_RANDOMLY;
     w->seed = 0;
+    w->max_contacts = 8;
     return w;
 }
 
@@ -398,6 +331,9 @@ void orc_world_destroy(orc_world *w)
     free(w->bodies);
     free(w->joints);
     free(w->contacts);
+    free(w->geoms);
+    free(w->hf_heights);
+    free(w->pairs);
     free(w);
 }
 
@@ -2176,4 +2112,16 @@ void orc_q_to_R(const double q[4], double R[9])
     real rq[4] = {(real)q[0], (real)q[1], (real)q[2], (real)q[3]}, rR[9];
     q_to_R(rq, rR);
     for (int i = 0; i < 9; i++) R[i] = rR[i];
+}
+
+/* ------------------------------------------------------------------ */
+/* bench helper: collide + quickstep `steps` times over `n` worlds (one call = one thread's share) */
+int orc_collide(orc_world *w);
+void orc_bench_run(orc_world **worlds, int n, int steps, double h, int do_collide)
+{
+    for (int s = 0; s < steps; s++)
+        for (int i = 0; i < n; i++) {
+            if (do_collide) orc_collide(worlds[i]);
+            orc_world_quickstep(worlds[i], h);
+        }
 }

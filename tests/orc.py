@@ -26,6 +26,11 @@ class ContactDesc(C.Structure):
                 ("slip1", C.c_double), ("slip2", C.c_double)]
 
 
+class Surface(C.Structure):
+    _fields_ = [("mu", C.c_double), ("mu2", C.c_double), ("rho", C.c_double), ("rho2", C.c_double),
+                ("rhoN", C.c_double), ("soft_erp", C.c_double), ("soft_cfm", C.c_double)]
+
+
 class Mass(C.Structure):
     _fields_ = [("mass", C.c_double), ("c", C.c_double * 3), ("I", C.c_double * 9)]
 
@@ -109,6 +114,13 @@ def load(single=False):
         "orc_are_connected_excluding": (I, [P, I, I, I]),
         "orc_contacts_clear": (None, [P]), "orc_contact_add": (I, [P, I, I, C.POINTER(ContactDesc)]),
         "orc_contact_get_feedback": (None, [P, I, DP]),
+        "orc_geom_create": (I, [P, I, I, DP, DP, DP, C.POINTER(Surface)]),
+        "orc_geom_create_heightfield": (I, [P, P, I, I, D, D, D, C.POINTER(Surface)]),
+        "orc_world_set_max_contacts": (None, [P, I]),
+        "orc_collide": (I, [P]),
+        "orc_collide_get_pairs": (I, [P, C.POINTER(C.c_int), I]),
+        "orc_contact_get": (I, [P, I, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(ContactDesc)]),
+        "orc_bench_run": (None, [C.POINTER(P), I, I, D, I]),
         "orc_mass_set_zero": (None, [C.POINTER(Mass)]),
         "orc_mass_set_box_total": (None, [C.POINTER(Mass), D, D, D, D]),
         "orc_mass_set_box": (None, [C.POINTER(Mass), D, D, D, D]),
@@ -198,6 +210,7 @@ class OracleBatch:
     # world
     def set_max_contacts(self, n):
         self.max_contacts = n
+        self._all(self.lib.orc_world_set_max_contacts, n)
 
     def enable_rolling_friction(self, on=True):
         pass
@@ -412,6 +425,45 @@ class OracleBatch:
         self.lib.orc_contact_get_feedback(self.worlds[world], c, out)
         return np.array(out[:3], dtype=float)
 
+    def contact_get(self, world, c):
+        b1, b2, d = C.c_int(), C.c_int(), ContactDesc()
+        rc = self.lib.orc_contact_get(self.worlds[world], c, C.byref(b1), C.byref(b2), C.byref(d))
+        assert rc == 0
+        return b1.value, b2.value, d
+
+    # geoms / collision
+    @staticmethod
+    def _surface(s):
+        if s is None:
+            return None
+        out = Surface()
+        for k in ("mu", "mu2", "rho", "rho2", "rhoN", "soft_erp", "soft_cfm"):
+            setattr(out, k, float(s.get(k, 0.0)))
+        return out
+
+    def geom_create(self, cls, body, dims, lpos=(0, 0, 0), lquat=(1, 0, 0, 0), surface=None):
+        d = (C.c_double * 4)(*([float(x) for x in dims] + [0.0] * (4 - len(dims))))
+        p = (C.c_double * 3)(*map(float, lpos))
+        q = (C.c_double * 4)(*map(float, lquat))
+        s = self._surface(surface)
+        return self._all(self.lib.orc_geom_create, cls, body, d, p, q, C.byref(s) if s else None)
+
+    def geom_create_heightfield(self, heights, dx, x0, y0, surface=None):
+        hts = np.ascontiguousarray(heights, dtype=np.float32)
+        ny, nx = hts.shape
+        s = self._surface(surface)
+        return self._all(self.lib.orc_geom_create_heightfield, hts.ctypes.data_as(C.c_void_p), nx, ny, dx, x0, y0,
+                         C.byref(s) if s else None)
+
+    def collide(self):
+        for w in self.worlds:
+            self.lib.orc_collide(w)
+
+    def collide_get_pairs(self, world, max_pairs=4096):
+        buf = (C.c_int * max_pairs)()
+        n = self.lib.orc_collide_get_pairs(self.worlds[world], buf, max_pairs)
+        return [(v & 0xffff, v >> 16) for v in buf[:n]]
+
     # step
     def step(self, h):
         for w in self.worlds:
@@ -419,6 +471,12 @@ class OracleBatch:
 
     def sync(self):
         pass
+
+    def bench_run(self, lo, hi, steps, h, do_collide):
+        """C loop over worlds[lo:hi] (ctypes releases the GIL, so threads run in parallel)."""
+        n = hi - lo
+        arr = (C.c_void_p * n)(*self.worlds[lo:hi])
+        self.lib.orc_bench_run(arr, n, steps, float(h), int(do_collide))
 
     def last_num_rows(self, world=0):
         return self.lib.orc_world_last_num_rows(self.worlds[world])

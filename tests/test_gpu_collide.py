@@ -1,0 +1,207 @@
+"""GPU parity of the device collision path (broadphase pair lists + narrowphase contact records)
+against oracle/orc_collide.c, which defines the collision semantics (the reference tree has none).
+
+Bars: broadphase pair lists and contact counts bit-exact (integer work) -- except where a
+candidate lies within fp32 rounding of the decision threshold, which the comparator reports and
+bounds; contact records within fp32 tolerance.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import orc
+from mars_ode_physics_b200 import Arena, capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+SURF = {"mu": 0.8, "mu2": 0.8, "soft_erp": 0.2, "soft_cfm": 1e-5}
+
+
+def _rand_quat(rng):
+    q = rng.normal(size=4)
+    return q / np.linalg.norm(q)
+
+
+def _compare_contacts(ar, oc, W, borderline=2e-5):
+    """Returns (#worlds compared exactly, #borderline worlds)."""
+    exact = border = 0
+    for w in range(W):
+        na, no = ar.contact_count(w), oc.contact_count(w)
+        ca = [ar.contact_get(w, c) for c in range(na)]
+        co = [oc.contact_get(w, c) for c in range(no)]
+        if na != no or any(a[0] != o[0] or a[1] != o[1] for a, o in zip(ca, co)):
+            # acceptable only if some involved contact is borderline (depth ~ 0)
+            depths = [c[2].depth for c in ca] + [c[2].depth for c in co]
+            assert min(depths) < borderline, (w, na, no, depths)
+            border += 1
+            continue
+        for a, o in zip(ca, co):
+            da, do = a[2], o[2]
+            if abs(da.depth - do.depth) > 1e-4 and min(da.depth, do.depth) < borderline:
+                border += 1
+                break
+            assert abs(da.depth - do.depth) < 2e-5, (w, da.depth, do.depth)
+            assert np.allclose(da.pos[:], do.pos[:], atol=5e-5), (w, da.pos[:], do.pos[:])
+            assert np.allclose(da.normal[:], do.normal[:], atol=2e-4), (w, da.normal[:], do.normal[:])
+            assert da.mode == do.mode
+            assert abs(da.mu - do.mu) < 1e-6 and abs(da.soft_cfm - do.soft_cfm) < 1e-9
+        else:
+            exact += 1
+    return exact, border
+
+
+def _build_pair_scene(be, cls_a, dims_a, cls_b, dims_b, static_plane=False):
+    scenes.setup_world(be)
+    be.set_max_contacts(8)
+    a = scenes.add_body(be, 1.0, np.eye(3) * 0.01, (0, 0, 0))
+    be.geom_create(cls_a, a, dims_a, surface=SURF)
+    if static_plane:
+        be.geom_create(capi.GEOM_PLANE, -1, dims_b, surface=SURF)
+    else:
+        b = scenes.add_body(be, 1.0, np.eye(3) * 0.01, (0, 0, 0))
+        be.geom_create(cls_b, b, dims_b, surface=SURF)
+
+
+@pytest.mark.parametrize("cls,dims", [
+    (capi.GEOM_SPHERE, (0.1,)), (capi.GEOM_BOX, (0.2, 0.3, 0.1)),
+    (capi.GEOM_CAPSULE, (0.05, 0.3)), (capi.GEOM_CYLINDER, (0.1, 0.25))])
+def test_primitive_vs_plane(cuda_lib, cls, dims):
+    W = 96
+    rng = np.random.default_rng(1234 + cls)
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    n = np.array([0.1, -0.2, 1.0])
+    n /= np.linalg.norm(n)
+    for be in (ar, oc):
+        _build_pair_scene(be, cls, dims, capi.GEOM_PLANE, (*n, 0.05), static_plane=True)
+    for w in range(W):
+        p = rng.uniform(-0.2, 0.2, size=3)
+        q = _rand_quat(rng)
+        if w % 8 == 0:  # resting poses: axis aligned with the normal
+            q = np.array([1.0, 0, 0, 0])
+        for be in (ar, oc):
+            be.body_set_position(0, p, w)
+            be.body_set_quaternion(0, q, w)
+    ar.collide()
+    oc.collide()
+    for w in range(W):
+        assert ar.collide_get_pairs(w) == oc.collide_get_pairs(w)
+    exact, border = _compare_contacts(ar, oc, W)
+    assert exact >= W - 4, (exact, border)
+    assert sum(oc.contact_count(w) for w in range(W)) > W // 4  # the test actually produced contacts
+
+
+@pytest.mark.parametrize("ca,da,cb,db", [
+    (capi.GEOM_SPHERE, (0.1,), capi.GEOM_SPHERE, (0.15,)),
+    (capi.GEOM_SPHERE, (0.1,), capi.GEOM_BOX, (0.3, 0.2, 0.25)),
+    (capi.GEOM_BOX, (0.3, 0.2, 0.25), capi.GEOM_SPHERE, (0.1,)),
+    (capi.GEOM_CAPSULE, (0.05, 0.3), capi.GEOM_SPHERE, (0.1,)),
+    (capi.GEOM_SPHERE, (0.1,), capi.GEOM_CAPSULE, (0.05, 0.3)),
+    (capi.GEOM_CAPSULE, (0.05, 0.3), capi.GEOM_CAPSULE, (0.07, 0.2))])
+def test_primitive_pairs(cuda_lib, ca, da, cb, db):
+    W = 128
+    rng = np.random.default_rng(77 + 10 * ca + cb)
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    for be in (ar, oc):
+        _build_pair_scene(be, ca, da, cb, db)
+    for w in range(W):
+        pa, pb = rng.uniform(-0.15, 0.15, size=3), rng.uniform(-0.15, 0.15, size=3)
+        qa, qb = _rand_quat(rng), _rand_quat(rng)
+        for be in (ar, oc):
+            be.body_set_position(0, pa, w)
+            be.body_set_quaternion(0, qa, w)
+            be.body_set_position(1, pb, w)
+            be.body_set_quaternion(1, qb, w)
+    ar.collide()
+    oc.collide()
+    for w in range(W):
+        assert ar.collide_get_pairs(w) == oc.collide_get_pairs(w)
+    exact, border = _compare_contacts(ar, oc, W)
+    assert exact >= W - 4, (exact, border)
+    assert sum(oc.contact_count(w) for w in range(W)) > W // 8
+
+
+def test_joint_connected_pairs_are_excluded(cuda_lib):
+    """WorldPhysics::createContact rejects contacts between joint-connected bodies (:461)."""
+    W = 4
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    for be in (ar, oc):
+        scenes.setup_world(be)
+        be.set_max_contacts(8)
+        a = scenes.add_body(be, 1.0, np.eye(3) * 0.01, (0, 0, 0))
+        b = scenes.add_body(be, 1.0, np.eye(3) * 0.01, (0.1, 0, 0))
+        c = scenes.add_body(be, 1.0, np.eye(3) * 0.01, (0.0, 0.1, 0))
+        for body in (a, b, c):
+            be.geom_create(capi.GEOM_SPHERE, body, (0.1,), surface=SURF)
+        scenes.add_hinge(be, a, b, (0.05, 0, 0), (0, 0, 1))
+    ar.collide()
+    oc.collide()
+    for w in range(W):
+        assert ar.collide_get_pairs(w) == oc.collide_get_pairs(w) == [(0, 2), (1, 2)]
+        assert ar.contact_count(w) == oc.contact_count(w) == 2
+
+
+def test_rover_on_heightfield_trajectory(cuda_lib):
+    """Config D scene (hinge2 rover, shared heightfield), device collide + step vs oracle."""
+    W = 16
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    heights, x0, y0 = scenes.terrain_heights()
+    for be in (ar, oc):
+        sc = scenes.rover(be, with_geoms=True)
+        be.geom_create_heightfield(heights, 0.1, x0, y0, surface={"mu": 1.0, "mu2": 1.0, "soft_erp": 0.2, "soft_cfm": 1e-5})
+        for w in range(W):
+            dx, dy = 3.0 * scenes.uniform01(0xD, w, 1) - 1.5, 3.0 * scenes.uniform01(0xD, w, 2) - 1.5
+            for b in sc["bodies"]:
+                p = be.body_get_position(b, 0 if w == 0 else w)
+            # shift the whole rover
+        for w in range(W):
+            dx, dy = 3.0 * scenes.uniform01(0xD, w, 1) - 1.5, 3.0 * scenes.uniform01(0xD, w, 2) - 1.5
+            for b in sc["bodies"]:
+                p = be.body_get_position(b, w)
+                be.body_set_position(b, (p[0] + dx, p[1] + dy, p[2] + 0.1), w)
+            for j in sc["joints"]:
+                be.joint_set_param(j, capi.PARAM_VEL | capi.PARAM_GROUP2, 2.0 + 4.0 * scenes.uniform01(0xD, w, 3), w)
+    nb = 5
+    mismatch_steps = 0
+    for step in range(400):
+        ar.collide()
+        oc.collide()
+        if step % 20 == 0:
+            for w in range(W):
+                assert ar.collide_get_pairs(w) == oc.collide_get_pairs(w), (step, w)
+            exact, border = _compare_contacts(ar, oc, W, borderline=1e-4)
+            mismatch_steps += border
+        ar.step(0.001)
+        oc.step(0.001)
+    sa = ar.state_download(nb).astype(np.float64)
+    so = oc.state_download(nb)
+    err = np.abs(sa - so)
+    print("rover/heightfield 400 steps: max pos err", err[:, :3].max(), "quat", err[:, 3:7].max(),
+          "lvel", err[:, 7:10].max(), "borderline worlds", mismatch_steps)
+    assert mismatch_steps <= 2
+    assert err[:, :3].max() < 2e-3 and err[:, 3:7].max() < 5e-3
+    assert sum(oc.contact_count(w) for w in range(W)) >= W  # wheels are on the ground
+
+
+def test_box_on_heightfield(cuda_lib):
+    W = 64
+    rng = np.random.default_rng(5)
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    heights, x0, y0 = scenes.terrain_heights()
+    for be in (ar, oc):
+        scenes.setup_world(be)
+        be.set_max_contacts(8)
+        a = scenes.add_body(be, 1.0, np.eye(3) * 0.01, (0, 0, 0))
+        be.geom_create(capi.GEOM_BOX, a, (0.4, 0.3, 0.2), surface=SURF)
+        be.geom_create_heightfield(heights, 0.1, x0, y0, surface=SURF)
+    for w in range(W):
+        p = np.array([rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-0.05, 0.2)])
+        q = _rand_quat(rng)
+        for be in (ar, oc):
+            be.body_set_position(0, p, w)
+            be.body_set_quaternion(0, q, w)
+    ar.collide()
+    oc.collide()
+    exact, border = _compare_contacts(ar, oc, W)
+    assert exact >= W - 4, (exact, border)
+    assert sum(oc.contact_count(w) for w in range(W)) > W // 2
