@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 H = 0.001
 WORLDS_PER_GPU = 65536
+SETTLE_STEPS = 600  # untimed: the rovers are dropped from 0.12 m and must be driving on the terrain
 METRIC = "batched world-steps/sec"
 UNIT = "world-steps/s"
 WORKLOAD = "D: hinge2 rover (5 bodies, 4 hinge2, sphere wheels) on shared 256x256 heightfield, dt=1ms, 20 SOR iters"
@@ -104,21 +105,34 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "power_w_max": max(float(s[2]) for s in self.samples)}
 
 
-def cpu_baseline(sample_worlds, steps, threads):
-    """The oracle (CPU restatement of ODE quickstep + the collision spec) on the host cores."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import orc  # test infrastructure; used here only as the reported CPU baseline
-    from concurrent.futures import ThreadPoolExecutor
-    oc = orc.OracleBatch(sample_worlds)
-    build_rover_worlds(oc, sample_worlds)
-    per = (sample_worlds + threads - 1) // threads
-    chunks = [(i, min(i + per, sample_worlds)) for i in range(0, sample_worlds, per)]
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        list(ex.map(lambda c: oc.bench_run(c[0], c[1], 5, H, 1), chunks))  # warm-up
+class CpuBaseline:
+    """The oracle (CPU restatement of ODE quickstep + the collision spec) on the host cores:
+    `sample_worlds` worlds of the same workload, settled, then timed over bounded samples."""
+
+    def __init__(self, sample_worlds, threads):
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import orc  # test infrastructure; used here only as the reported CPU baseline
+        from concurrent.futures import ThreadPoolExecutor
+        self.n, self.threads = sample_worlds, threads
+        self.oc = orc.OracleBatch(sample_worlds)
+        build_rover_worlds(self.oc, sample_worlds)
+        per = (sample_worlds + threads - 1) // threads
+        self.chunks = [(i, min(i + per, sample_worlds)) for i in range(0, sample_worlds, per)]
+        self.ex = ThreadPoolExecutor(max_workers=threads)
+        self.run(SETTLE_STEPS)
+
+    def run(self, steps):
         t0 = time.perf_counter()
-        list(ex.map(lambda c: oc.bench_run(c[0], c[1], steps, H, 1), chunks))
+        list(self.ex.map(lambda c: self.oc.bench_run(c[0], c[1], steps, H, 1), self.chunks))
         dt = time.perf_counter() - t0
-    return sample_worlds * steps / dt, dt
+        return self.n * steps / dt, dt
+
+    def run_for(self, seconds):
+        """Time about `seconds` of CPU work; returns (world-steps/s, steps, seconds)."""
+        rate, _ = self.run(20)
+        steps = max(20, int(seconds * rate / self.n))
+        rate, dt = self.run(steps)
+        return rate, steps, dt
 
 
 def run_reference(args):
@@ -128,24 +142,30 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 32 * cores
-    steps_per = 60
-    vals = []
-    for _ in range(max(1, args.warmup)):
-        cpu_baseline(sample, 10, cores)
-    t_total = 0.0
+    sample = 64 * cores
+    cb = CpuBaseline(sample, cores)
+    rate, _ = cb.run(20)
+    # each bench "step" is a bounded sample: `steps_per` steps of `sample` worlds; the whole run
+    # (warmup + steps) is sized to stay within ~2 minutes
+    budget_s = min(120.0, 1.0 * (args.steps + args.warmup))
+    steps_per = max(5, int(budget_s * rate / sample / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cb.run(steps_per)
+    vals, t_total = [], 0.0
     for _ in range(args.steps):
-        v, dt = cpu_baseline(sample, steps_per, cores)
+        v, dt = cb.run(steps_per)
         vals.append(v)
         t_total += dt
-    value = float(np.mean(vals))
+    value = float(sample * steps_per * args.steps / t_total)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "worlds_per_sample": sample, "world_steps_per_step": sample * steps_per},
+        "config": {"workload": WORKLOAD, "worlds_per_sample": sample, "world_steps_per_step": sample * steps_per,
+                   "settle_steps": SETTLE_STEPS},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} worlds x {steps_per} steps per bench step, oracle f64, {cores} threads"},
+                         "sample": f"{sample} settled worlds x {steps_per} steps per bench step, oracle f64 "
+                                   f"(CPU restatement of ODE-0.16 quickstep, not libode), {cores} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -177,6 +197,10 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident loop ----------------
+    for _ in range(SETTLE_STEPS):
+        ar.collide()
+        ar.step(H)
+    ar.sync()
     for _ in range(max(args.warmup, 3)):
         ar.collide()
         ar.step(H)
@@ -265,6 +289,7 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "worlds_per_gpu": W, "total_worlds": total_worlds,
                        "sharding": f"worlds/{world_size} GPUs, no collective on the step path",
                        "l2": "per-step working set (row scratch) > L2; no flush needed",
+                       "settle_steps": SETTLE_STEPS,
                        "mean_rows_per_world": float(np.mean([ar.last_num_rows(w) for w in range(0, W, max(1, W // 64))])),
                        "kernel_ms": {"collide": collide_ms, "step": step_ms}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nj * W * 4),
@@ -279,11 +304,12 @@ def run_b200(args):
         }
         if not args.no_cpu_baseline and world_size == 1:
             cores = os.cpu_count() or 1
-            sample = 32 * cores
-            v, dt = cpu_baseline(sample, 100, cores)
+            sample = 128 * cores  # enough worlds that ~12 s of CPU work stays within a few thousand steps
+            v, nsteps, dt = CpuBaseline(sample, cores).run_for(12.0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{sample} worlds x 100 steps of the same workload, oracle f64 "
-                                              f"(CPU restatement, not libode), {cores} threads, {dt:.1f} s"}
+                                    "sample": f"{sample} settled worlds x {nsteps} steps of the same workload, "
+                                              f"oracle f64 (CPU restatement of ODE-0.16 quickstep, not libode), "
+                                              f"{cores} threads, {dt:.1f} s"}
         print(json.dumps(line))
     if world_size > 1:
         dist.destroy_process_group()

@@ -21,7 +21,7 @@
 
 extern "C" size_t b2p_step_smem_bytes(int nb, int nj, int maxc, int rpc);
 extern "C" int b2p_step_block_dim(void);
-extern "C" cudaError_t b2p_launch_step(const StepParams *P, size_t smem, cudaStream_t stream);
+extern "C" cudaError_t b2p_launch_step(const StepParams *P, int nb, int nj, int maxc, int rpc, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, cudaStream_t stream);
 
 namespace {
@@ -485,7 +485,7 @@ int finalize(b2p_arena *a)
         a->d_rows = nullptr;
         a->d_lambda = a->d_rowad = a->d_invIw = nullptr;
         const size_t mr = (size_t)std::max(maxrows, 1), Wp = (size_t)a->Wp;
-        CUDA_TRY(cudaMalloc(&a->d_rows, sizeof(float4) * mr * 7 * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_rows, sizeof(float4) * mr * 4 * Wp));
         CUDA_TRY(cudaMalloc(&a->d_lambda, sizeof(float) * mr * Wp));
         CUDA_TRY(cudaMalloc(&a->d_rowad, sizeof(float) * mr * Wp));
         CUDA_TRY(cudaMalloc(&a->d_invIw, sizeof(float) * (size_t)std::max(nb, 1) * 9 * Wp));
@@ -1708,7 +1708,7 @@ int b2p_step(b2p_arena *a, double step_size)
     P.seed = a->seed.dev;
     const size_t smem = b2p_step_smem_bytes((int)a->bodies.size(), (int)a->joints.size(), a->maxc, rpc_of(a));
     if (smem > 227 * 1024) return fail(B2P_ECAPACITY, "scene needs %zu bytes of shared memory per CTA", smem);
-    CUDA_TRY(b2p_launch_step(&P, smem, a->stream));
+    CUDA_TRY(b2p_launch_step(&P, (int)a->bodies.size(), (int)a->joints.size(), a->maxc, rpc_of(a), a->stream));
     a->launches++;
     a->stepped = true;
     a->state.dev_newer = true;

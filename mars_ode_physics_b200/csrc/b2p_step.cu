@@ -27,10 +27,15 @@
 
 namespace {
 
-constexpr int BD = 128; // threads (= worlds) per CTA
+constexpr int BD = 64;   // threads (= worlds) per CTA: 8 CTAs/SM at <=128 registers, fine-grained waves
+constexpr int ROWV = 4; // float4 per stored row: one 64-byte line per (world,row)
 
 struct Smem {
     float *fc;     // [nb*6][BD]   fe -> tmp1 -> fc
+    float *iw;     // [nb*6][BD]   symmetric invI_world (xx xy xz yy yz zz) for the sweep
+    float *im;     // [nb]         invMass (shared by the CTA)
+    float *lam;    // [maxrows][BD] lambda (only when it fits; else it lives in the row line)
+    float *lamn;   // [maxc][BD]   lambda of each contact's normal row (read by its friction rows)
     uint8_t *ord;  // [maxrows][BD]
     uint8_t *jm;   // [nj][BD]     rows of joint j in this world
     int8_t *jl;    // [nj][BD]     local limot row feeding feedback.lambda, or -1
@@ -70,6 +75,7 @@ __device__ __forceinline__ void load_invIw(const StepParams &P, int b, int w, fl
 struct Row {
     float J[12];
     float c, cfm, lo, hi;
+    int fslot; // slot of the normal row this (friction) row depends on, or 0xFF
 };
 
 __device__ __forceinline__ void row_init(Row &r, float world_cfm)
@@ -80,6 +86,7 @@ __device__ __forceinline__ void row_init(Row &r, float world_cfm)
     r.cfm = world_cfm;
     r.lo = -INFINITY;
     r.hi = INFINITY;
+    r.fslot = 0xFF;
 }
 
 struct PairCtx {
@@ -93,7 +100,7 @@ struct PairCtx {
 __device__ __forceinline__ void emit_row(const StepParams &P, const Smem &S, int w, int tid, int slot, Row &r,
                                          const PairCtx &pc)
 {
-    const int Wp = P.Wp;
+    (void)0;
     const float hinv = 1.0f / P.h;
     float rhs = r.c * hinv;
     const float cfm = r.cfm * hinv;
@@ -129,24 +136,24 @@ __device__ __forceinline__ void emit_row(const StepParams &P, const Smem &S, int
         for (int k = 6; k < 12; k++) o[k] = 0.f;
     }
     const float Ad = P.sor_w / (sum + cfm);
-#pragma unroll
-    for (int k = 0; k < 6; k++) r.J[k] *= Ad;
-    if (pc.b1 >= 0) {
-#pragma unroll
-        for (int k = 6; k < 12; k++) r.J[k] *= Ad;
-    }
-    rhs *= Ad;
-    const float Adcfm = Ad * cfm;
-    float4 *dst = P.rows + (size_t)(slot * 7) * Wp + w;
-    dst[0 * (size_t)Wp] = make_float4(r.J[0], r.J[1], r.J[2], r.J[3]);
-    dst[1 * (size_t)Wp] = make_float4(r.J[4], r.J[5], r.J[6], r.J[7]);
-    dst[2 * (size_t)Wp] = make_float4(r.J[8], r.J[9], r.J[10], r.J[11]);
-    dst[3 * (size_t)Wp] = make_float4(o[0], o[1], o[2], o[3]);
-    dst[4 * (size_t)Wp] = make_float4(o[4], o[5], o[6], o[7]);
-    dst[5 * (size_t)Wp] = make_float4(o[8], o[9], o[10], o[11]);
-    dst[6 * (size_t)Wp] = make_float4(rhs, Adcfm, r.lo, r.hi);
-    G(P.lambda, slot) = 0.f;
-    G(P.rowad, slot) = Ad;
+    // Stored row (13 words): unscaled J1l J1a J2a (J2l = -J1l for every joint type of this path),
+    // rhs, cfm/h, the (lo,hi) pair folded into one word, and Ad.  The sweep evaluates
+    // delta = Ad*(rhs - lambda*cfm - J.fc) and rebuilds iMJ = invM*J from invI_world (L1-resident),
+    // which cuts the bytes streamed per row-iteration from 128 to 60.
+    float hi_enc;
+    if (r.lo == 0.f && r.hi == INFINITY) hi_enc = __int_as_float(0xFFFFFFFF);       // [0, +inf)
+    else if (r.lo == -INFINITY && r.hi == 0.f) hi_enc = __int_as_float(0xFFFFFFFE); // (-inf, 0]
+    else hi_enc = r.hi;                                                               // [-hi, hi]
+    // Rows are stored world-major: the 64-byte line of (world, slot) holds the whole row, so a lane
+    // that follows its own (shuffled) row order still uses every byte of every sector it touches.
+    float4 *dst = P.rows + ((size_t)w * P.T->maxrows + slot) * ROWV;
+    dst[0] = make_float4(r.J[0], r.J[1], r.J[2], r.J[3]);
+    dst[1] = make_float4(r.J[4], r.J[5], r.J[9], r.J[10]);
+    dst[2] = make_float4(r.J[11], rhs, cfm, hi_enc);
+    // .y = lambda (when not in shared memory); .z = body0 | body1<<8 | fslot<<16, where a row with one
+    // body points its second half at the all-zero dummy body `nb` (branch-free sweep)
+    const int meta = (pc.b0 & 0xff) | ((pc.b1 < 0 ? P.T->nb : pc.b1) << 8) | (r.fslot << 16);
+    dst[3] = make_float4(Ad, 0.f, __int_as_float(meta), 0.f);
 }
 
 struct LimotState {
@@ -326,7 +333,7 @@ __device__ __forceinline__ void fixed_orientation_rhs(const DevJoint &jc, const 
     for (int i = 0; i < 3; i++) c3[i] = k2 * e[i];
 }
 
-__global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
+template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevTemplate *__restrict__ T = P.T;
@@ -335,7 +342,11 @@ __global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
     {
         unsigned char *p = smem_raw;
         S.fc = (float *)p;
-        p += sizeof(float) * (size_t)nb * 6 * BD;
+        p += sizeof(float) * (size_t)(nb + 1) * 6 * BD;
+        S.iw = (float *)p;
+        p += sizeof(float) * (size_t)(nb + 1) * 6 * BD;
+        S.im = (float *)p;
+        p += sizeof(float) * (size_t)(nb + 1);
         S.jmeta = (int *)p;
         p += sizeof(int) * (size_t)njslots;
         S.cb = (uint16_t *)p;
@@ -347,12 +358,18 @@ __global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
         S.jl = (int8_t *)p;
         p += (size_t)nj * BD;
         S.cm = p;
+        p += (size_t)maxc * BD;
+        p = (unsigned char *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+        S.lamn = (float *)p;
+        p += sizeof(float) * (size_t)maxc * BD;
+        S.lam = (float *)p;
     }
     const int tid = threadIdx.x;
     for (int s = tid; s < njslots; s += BD) {
         const DevJoint &jc = T->joints[s / B2P_ROWS_PER_JOINT];
         S.jmeta[s] = (jc.b0 & 0xff) | ((jc.b1 < 0 ? 0xff : jc.b1) << 8);
     }
+    for (int b = tid; b <= nb; b += BD) S.im[b] = b < nb ? T->bodies[b].invMass : 0.f;
     __syncthreads();
     const int w = blockIdx.x * BD + tid;
     if (w >= P.W) return;
@@ -373,6 +390,12 @@ __global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
         mul33(Iw, bp.R, tmp);
 #pragma unroll
         for (int k = 0; k < 9; k++) G(P.invIw, b * 9 + k) = Iw[k];
+        S.iw[(size_t)(b * 6 + 0) * BD + tid] = Iw[0];
+        S.iw[(size_t)(b * 6 + 1) * BD + tid] = Iw[1];
+        S.iw[(size_t)(b * 6 + 2) * BD + tid] = Iw[2];
+        S.iw[(size_t)(b * 6 + 3) * BD + tid] = Iw[4];
+        S.iw[(size_t)(b * 6 + 4) * BD + tid] = Iw[5];
+        S.iw[(size_t)(b * 6 + 5) * BD + tid] = Iw[8];
         if (bc.gyroscopic) {
             // implicit gyroscopic torque (ODE 0.16 quickstep stage0, Lacoursiere 2006)
             float I[9], L[3], It[9], itInv[9];
@@ -802,6 +825,7 @@ __global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
             if (b1 >= 0) { r.J[6] = -t1[0]; r.J[7] = -t1[1]; r.J[8] = -t1[2]; cross3(r.J + 9, t1, c2); }
             r.lo = -mu;
             r.hi = mu;
+            if (mode & 0x1000) r.fslot = base;
             emit_row(P, S, w, tid, base + row, r, pc);
             if (mode & 0x1000) depmask |= 1 << (row - 1); else push_head(base + row);
             row++;
@@ -813,6 +837,7 @@ __global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
             if (b1 >= 0) { r.J[6] = -t2[0]; r.J[7] = -t2[1]; r.J[8] = -t2[2]; cross3(r.J + 9, t2, c2); }
             r.lo = -mu2e;
             r.hi = mu2e;
+            if (mode & 0x2000) r.fslot = base;
             emit_row(P, S, w, tid, base + row, r, pc);
             if (mode & 0x2000) depmask |= 1 << (row - 1); else push_head(base + row);
             row++;
@@ -837,6 +862,7 @@ __global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
                     if (b1 >= 0) { r.J[9] = -ax[i][0]; r.J[10] = -ax[i][1]; r.J[11] = -ax[i][2]; }
                     r.lo = -rho[i];
                     r.hi = rho[i];
+                    if (mode & bits[i]) r.fslot = base;
                     emit_row(P, S, w, tid, base + row, r, pc);
                     if (mode & bits[i]) depmask |= 1 << (row - 1); else push_head(base + row);
                     row++;
@@ -856,7 +882,11 @@ __global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
     G(P.nrows, 0) = m;
 
     // tmp1 -> gmem? not needed: epilogue uses fe from gmem.  fc = 0
-    for (int k = 0; k < nb * 6; k++) S.fc[(size_t)k * BD + tid] = 0.f;
+    for (int k = 0; k < (nb + 1) * 6; k++) S.fc[(size_t)k * BD + tid] = 0.f;
+    for (int k = nb * 6; k < (nb + 1) * 6; k++) S.iw[(size_t)k * BD + tid] = 0.f;
+    if (LAM_SMEM)
+        for (int k = 0; k < maxrows; k++) S.lam[(size_t)k * BD + tid] = 0.f;
+    for (int k = 0; k < maxc; k++) S.lamn[(size_t)k * BD + tid] = 0.f;
 
     // ---------------- phase 3: SOR-LCP sweep ----------------
     uint32_t seed = G(P.seed, 0);
@@ -876,61 +906,99 @@ __global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
                 S.ord[(size_t)sw * BD + tid] = a;
             }
         }
-        for (int k = 0; k < m; k++) {
-            const int i = S.ord[(size_t)k * BD + tid];
-            const float4 *src = P.rows + (size_t)(i * 7) * Wp + w;
-            const float4 j0 = src[0 * (size_t)Wp], j1 = src[1 * (size_t)Wp], j2 = src[2 * (size_t)Wp];
-            const float4 m0 = src[3 * (size_t)Wp], m1 = src[4 * (size_t)Wp], m2 = src[5 * (size_t)Wp];
-            const float4 sc = src[6 * (size_t)Wp];
-            int b0, b1;
-            int fslot = -1;
-            if (i < njslots) {
-                const int meta = S.jmeta[i];
-                b0 = meta & 0xff;
-                b1 = (meta >> 8) & 0xff;
-            } else {
-                const int c = (i - njslots) / rpc;
-                const int meta = S.cb[(size_t)c * BD + tid];
-                b0 = meta & 0xff;
-                b1 = (meta >> 8) & 0xff;
-                fslot = njslots + c * rpc;
-            }
+        // Software pipeline: while one row is processed the next one is already in flight (row loads
+        // do not depend on the sequential fc/lambda state).  Two register sets ping-pong so that no
+        // moves are needed.  The sweep body is branch-free: one-body rows use the zero dummy body.
+        struct Pre {
+            float4 a, b, c, d;
+            int i;
+        };
+        float4 *const rowbase = P.rows + (size_t)w * maxrows * ROWV;
+        auto fetch = [&](int pos, Pre &r) {
+            r.i = S.ord[(size_t)pos * BD + tid];
+            const float4 *src = rowbase + r.i * ROWV;
+            r.a = __ldcs(src);
+            r.b = __ldcs(src + 1);
+            r.c = __ldcs(src + 2);
+            r.d = LAM_SMEM ? __ldcs(src + 3) : __ldcg(src + 3);
+        };
+        auto process = [&](const Pre &r) {
+            const float4 c0 = r.a, c1 = r.b, c2 = r.c;
+            const int meta = __float_as_int(r.d.z);
+            const int b0 = meta & 0xff, b1 = (meta >> 8) & 0xff, fslot = (meta >> 16) & 0xff;
             float *f0 = S.fc + (size_t)(b0 * 6) * BD + tid;
-            float *f1 = (b1 != 0xff) ? S.fc + (size_t)(b1 * 6) * BD + tid : nullptr;
-            const float old = G(P.lambda, i);
-            float delta = sc.x - old * sc.y;
-            delta -= f0[0 * BD] * j0.x + f0[1 * BD] * j0.y + f0[2 * BD] * j0.z + f0[3 * BD] * j0.w +
-                     f0[4 * BD] * j1.x + f0[5 * BD] * j1.y;
-            if (f1)
-                delta -= f1[0 * BD] * j1.z + f1[1 * BD] * j1.w + f1[2 * BD] * j2.x + f1[3 * BD] * j2.y +
-                         f1[4 * BD] * j2.z + f1[5 * BD] * j2.w;
-            float lo_act = sc.z, hi_act = sc.w;
-            if (k >= nhead) {
-                hi_act = fabsf(sc.w * G(P.lambda, fslot));
+            float *f1 = S.fc + (size_t)(b1 * 6) * BD + tid;
+            const float lam_old = LAM_SMEM ? S.lam[(size_t)r.i * BD + tid] : r.d.y;
+            // unscaled J: J1l = c0.xyz, J1a = (c0.w, c1.x, c1.y), J2l = -J1l, J2a = (c1.z, c1.w, c2.x)
+            const float dl = (f0[0 * BD] - f1[0 * BD]) * c0.x + (f0[1 * BD] - f1[1 * BD]) * c0.y +
+                             (f0[2 * BD] - f1[2 * BD]) * c0.z;
+            const float da = f0[3 * BD] * c0.w + f0[4 * BD] * c1.x + f0[5 * BD] * c1.y + f1[3 * BD] * c1.z +
+                             f1[4 * BD] * c1.w + f1[5 * BD] * c2.x;
+            float delta = r.d.x * (c2.y - lam_old * c2.z - (dl + da));
+            float lo_act, hi_act;
+            const int enc = __float_as_int(c2.w);
+            if (fslot != 0xff) {
+                // friction row: bounds follow the normal row's current lambda (same sweep), which is
+                // mirrored in shared memory so that this is not a dependent global load
+                const float lam_n = S.lamn[(size_t)((fslot - njslots) / rpc) * BD + tid];
+                hi_act = fabsf(c2.w * lam_n);
                 lo_act = -hi_act;
+            } else {
+                hi_act = enc == (int)0xFFFFFFFF ? INFINITY : (enc == (int)0xFFFFFFFE ? 0.f : c2.w);
+                lo_act = enc == (int)0xFFFFFFFF ? 0.f : (enc == (int)0xFFFFFFFE ? -INFINITY : -c2.w);
             }
-            float nl = old + delta;
-            if (nl < lo_act) {
-                delta = lo_act - old;
-                nl = lo_act;
-            } else if (nl > hi_act) {
-                delta = hi_act - old;
-                nl = hi_act;
+            const float un = lam_old + delta;
+            const float nl = fminf(fmaxf(un, lo_act), hi_act);
+            delta = (nl == un) ? delta : nl - lam_old;
+            if (r.i >= njslots && (r.i - njslots) % rpc == 0) S.lamn[(size_t)((r.i - njslots) / rpc) * BD + tid] = nl;
+            if (LAM_SMEM) S.lam[(size_t)r.i * BD + tid] = nl;
+            else __stcg(reinterpret_cast<float *>(rowbase + r.i * ROWV + 3) + 1, nl);
+            // fc += delta * invM J^T, with invI_world (symmetric) from shared memory
+            {
+                const float dm = delta * S.im[b0];
+                const float *Iw = S.iw + (size_t)(b0 * 6) * BD + tid;
+                const float a0 = delta * c0.w, a1 = delta * c1.x, a2 = delta * c1.y;
+                const float ixx = Iw[0], ixy = Iw[BD], ixz = Iw[2 * BD], iyy = Iw[3 * BD], iyz = Iw[4 * BD],
+                            izz = Iw[5 * BD];
+                f0[0 * BD] += dm * c0.x;
+                f0[1 * BD] += dm * c0.y;
+                f0[2 * BD] += dm * c0.z;
+                f0[3 * BD] += ixx * a0 + ixy * a1 + ixz * a2;
+                f0[4 * BD] += ixy * a0 + iyy * a1 + iyz * a2;
+                f0[5 * BD] += ixz * a0 + iyz * a1 + izz * a2;
             }
-            G(P.lambda, i) = nl;
-            f0[0 * BD] += delta * m0.x;
-            f0[1 * BD] += delta * m0.y;
-            f0[2 * BD] += delta * m0.z;
-            f0[3 * BD] += delta * m0.w;
-            f0[4 * BD] += delta * m1.x;
-            f0[5 * BD] += delta * m1.y;
-            if (f1) {
-                f1[0 * BD] += delta * m1.z;
-                f1[1 * BD] += delta * m1.w;
-                f1[2 * BD] += delta * m2.x;
-                f1[3 * BD] += delta * m2.y;
-                f1[4 * BD] += delta * m2.z;
-                f1[5 * BD] += delta * m2.w;
+            {
+                const float dm = delta * S.im[b1];
+                const float *Iw = S.iw + (size_t)(b1 * 6) * BD + tid;
+                const float a0 = delta * c1.z, a1 = delta * c1.w, a2 = delta * c2.x;
+                const float ixx = Iw[0], ixy = Iw[BD], ixz = Iw[2 * BD], iyy = Iw[3 * BD], iyz = Iw[4 * BD],
+                            izz = Iw[5 * BD];
+                f1[0 * BD] -= dm * c0.x;
+                f1[1 * BD] -= dm * c0.y;
+                f1[2 * BD] -= dm * c0.z;
+                f1[3 * BD] += ixx * a0 + ixy * a1 + ixz * a2;
+                f1[4 * BD] += ixy * a0 + iyy * a1 + iyz * a2;
+                f1[5 * BD] += ixz * a0 + iyz * a1 + izz * a2;
+            }
+        };
+        Pre ra, rb, rc, rd;
+        if (m > 0) fetch(0, ra);
+        if (m > 1) fetch(1, rb);
+        if (m > 2) fetch(2, rc);
+        for (int k = 0; k < m; k += 4) {
+            if (k + 3 < m) fetch(k + 3, rd);
+            process(ra);
+            if (k + 1 < m) {
+                if (k + 4 < m) fetch(k + 4, ra);
+                process(rb);
+            }
+            if (k + 2 < m) {
+                if (k + 5 < m) fetch(k + 5, rb);
+                process(rc);
+            }
+            if (k + 3 < m) {
+                if (k + 6 < m) fetch(k + 6, rc);
+                process(rd);
             }
         }
     }
@@ -947,13 +1015,13 @@ __global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
         float flam = 0.f;
         for (int k = 0; k < mrows; k++) {
             const int slot = jc.slot_base + k;
-            const float4 *src = P.rows + (size_t)(slot * 7) * Wp + w;
-            const float4 j0 = src[0], j1 = src[(size_t)Wp], j2 = src[2 * (size_t)Wp];
-            const float lam = G(P.lambda, slot);
-            const float s = lam / G(P.rowad, slot);
-            data[0] += j0.x * s; data[1] += j0.y * s; data[2] += j0.z * s; data[3] += j0.w * s;
-            data[4] += j1.x * s; data[5] += j1.y * s; data[6] += j1.z * s; data[7] += j1.w * s;
-            data[8] += j2.x * s; data[9] += j2.y * s; data[10] += j2.z * s; data[11] += j2.w * s;
+            const float4 *src = P.rows + ((size_t)w * maxrows + slot) * ROWV;
+            const float4 j0 = src[0], j1 = src[1], j2 = src[2];
+            const float lam = LAM_SMEM ? S.lam[(size_t)slot * BD + tid] : reinterpret_cast<const float *>(src + 3)[1];
+            data[0] += j0.x * lam; data[1] += j0.y * lam; data[2] += j0.z * lam;
+            data[3] += j0.w * lam; data[4] += j1.x * lam; data[5] += j1.y * lam;
+            data[6] -= j0.x * lam; data[7] -= j0.y * lam; data[8] -= j0.z * lam;
+            data[9] += j1.z * lam; data[10] += j1.w * lam; data[11] += j2.x * lam;
             if (k == lrow) flam = lam;
         }
         if (jc.b1 < 0) {
@@ -969,11 +1037,12 @@ __global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
         float f[3] = {0.f, 0.f, 0.f};
         for (int k = 0; k < mrows; k++) {
             const int slot = njslots + c * rpc + k;
-            const float4 j0 = P.rows[(size_t)(slot * 7) * Wp + w];
-            const float s = G(P.lambda, slot) / G(P.rowad, slot);
-            f[0] += j0.x * s;
-            f[1] += j0.y * s;
-            f[2] += j0.z * s;
+            const float4 *src = P.rows + ((size_t)w * maxrows + slot) * ROWV;
+            const float4 j0 = src[0];
+            const float lam = LAM_SMEM ? S.lam[(size_t)slot * BD + tid] : reinterpret_cast<const float *>(src + 3)[1];
+            f[0] += j0.x * lam;
+            f[1] += j0.y * lam;
+            f[2] += j0.z * lam;
         }
         G(P.cfb, c * 3 + 0) = f[0];
         G(P.cfb, c * 3 + 1) = f[1];
@@ -1088,30 +1157,53 @@ __global__ void __launch_bounds__(BD) b2p_step_kernel(const StepParams P)
 
 } // namespace
 
-extern "C" size_t b2p_step_smem_bytes(int nb, int nj, int maxc, int rpc)
+static size_t smem_base_bytes(int nb, int nj, int maxc, int rpc)
 {
     const int njslots = nj * B2P_ROWS_PER_JOINT;
     const int maxrows = njslots + maxc * rpc;
-    size_t s = sizeof(float) * (size_t)nb * 6 * BD;
+    size_t s = sizeof(float) * (size_t)(nb + 1) * 12 * BD + sizeof(float) * (size_t)(nb + 1);
     s += sizeof(int) * (size_t)njslots;
     s += sizeof(uint16_t) * (size_t)maxc * BD;
     s += (size_t)maxrows * BD;
     s += (size_t)nj * BD * 2;
     s += (size_t)maxc * BD;
-    return (s + 15) & ~(size_t)15;
+    s = (s + 15) & ~(size_t)15;
+    s += sizeof(float) * (size_t)maxc * BD;
+    return s;
+}
+
+// lambda goes to shared memory when that still leaves >= 7 resident CTAs per SM (7 x 64 threads x
+// 148 SMs >= 65536 worlds in a single wave)
+static bool lambda_in_smem(int nb, int nj, int maxc, int rpc)
+{
+    const int maxrows = nj * B2P_ROWS_PER_JOINT + maxc * rpc;
+    const size_t s = smem_base_bytes(nb, nj, maxc, rpc) + sizeof(float) * (size_t)maxrows * BD + 1024;
+    return s * 7 <= 227 * 1024;
+}
+
+extern "C" size_t b2p_step_smem_bytes(int nb, int nj, int maxc, int rpc)
+{
+    const int maxrows = nj * B2P_ROWS_PER_JOINT + maxc * rpc;
+    size_t s = smem_base_bytes(nb, nj, maxc, rpc);
+    if (lambda_in_smem(nb, nj, maxc, rpc)) s += sizeof(float) * (size_t)maxrows * BD;
+    return s;
 }
 
 extern "C" int b2p_step_block_dim(void) { return BD; }
 
-extern "C" cudaError_t b2p_launch_step(const StepParams *P, size_t smem, cudaStream_t stream)
+extern "C" cudaError_t b2p_launch_step(const StepParams *P, int nb, int nj, int maxc, int rpc, cudaStream_t stream)
 {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(b2p_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static size_t configured[2] = {0, 0};
+    const bool ls = lambda_in_smem(nb, nj, maxc, rpc);
+    const size_t smem = b2p_step_smem_bytes(nb, nj, maxc, rpc);
+    if (smem > configured[ls]) {
+        cudaError_t e = ls ? cudaFuncSetAttribute(b2p_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(b2p_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[ls] = smem;
     }
     const int grid = (P->W + BD - 1) / BD;
-    b2p_step_kernel<<<grid, BD, smem, stream>>>(*P);
+    if (ls) b2p_step_kernel<true><<<grid, BD, smem, stream>>>(*P);
+    else b2p_step_kernel<false><<<grid, BD, smem, stream>>>(*P);
     return cudaGetLastError();
 }
