@@ -212,8 +212,9 @@ struct b2p_arena {
     Mirror<uint32_t> seed;
     Mirror<uint8_t> jrows;
     // solver scratch (device only)
-    float4 *d_rows = nullptr;
-    float *d_lambda = nullptr, *d_rowad = nullptr, *d_invIw = nullptr;
+    float4 *d_rows = nullptr, *d_rowsB = nullptr;
+    float *d_lambda = nullptr, *d_rowad = nullptr, *d_invIw = nullptr, *d_lambdaB = nullptr;
+    uint8_t *d_ord = nullptr;
     size_t scratch_rows = 0, scratch_nb = 0;
     int *d_pairs = nullptr, *d_npairs = nullptr;
     int maxpairs = 0;
@@ -479,13 +480,21 @@ int finalize(b2p_arena *a)
     if ((rc = mirror_to_device(a, a->jrows))) return rc;
     if (a->scratch_rows != (size_t)maxrows || a->scratch_nb != (size_t)nb) {
         if (a->d_rows) cudaFree(a->d_rows);
+        if (a->d_rowsB) cudaFree(a->d_rowsB);
+        if (a->d_lambdaB) cudaFree(a->d_lambdaB);
+        if (a->d_ord) cudaFree(a->d_ord);
+        a->d_lambdaB = nullptr;
+        a->d_ord = nullptr;
         if (a->d_lambda) cudaFree(a->d_lambda);
         if (a->d_rowad) cudaFree(a->d_rowad);
         if (a->d_invIw) cudaFree(a->d_invIw);
-        a->d_rows = nullptr;
+        a->d_rows = a->d_rowsB = nullptr;
         a->d_lambda = a->d_rowad = a->d_invIw = nullptr;
         const size_t mr = (size_t)std::max(maxrows, 1), Wp = (size_t)a->Wp;
         CUDA_TRY(cudaMalloc(&a->d_rows, sizeof(float4) * mr * 4 * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_rowsB, sizeof(float4) * mr * 4 * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_lambdaB, sizeof(float) * mr * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_ord, mr * Wp));
         CUDA_TRY(cudaMalloc(&a->d_lambda, sizeof(float) * mr * Wp));
         CUDA_TRY(cudaMalloc(&a->d_rowad, sizeof(float) * mr * Wp));
         CUDA_TRY(cudaMalloc(&a->d_invIw, sizeof(float) * (size_t)std::max(nb, 1) * 9 * Wp));
@@ -671,6 +680,9 @@ void b2p_arena_destroy(b2p_arena *a)
     mirror_free(a->seed);
     mirror_free(a->jrows);
     if (a->d_rows) cudaFree(a->d_rows);
+    if (a->d_rowsB) cudaFree(a->d_rowsB);
+    if (a->d_lambdaB) cudaFree(a->d_lambdaB);
+    if (a->d_ord) cudaFree(a->d_ord);
     if (a->d_lambda) cudaFree(a->d_lambda);
     if (a->d_rowad) cudaFree(a->d_rowad);
     if (a->d_invIw) cudaFree(a->d_invIw);
@@ -1702,6 +1714,9 @@ int b2p_step(b2p_arena *a, double step_size)
     P.rowad = a->d_rowad;
     P.invIw = a->d_invIw;
     P.rows = a->d_rows;
+    P.rowsB = a->d_rowsB;
+    P.lambdaB = a->d_lambdaB;
+    P.ord = a->d_ord;
     P.jrows = a->jrows.dev;
     P.ccount = a->ccount.dev;
     P.nrows = a->nrows.dev;

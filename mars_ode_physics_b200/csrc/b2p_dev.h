@@ -13,8 +13,9 @@
 //   crec    float[maxc*16][Wp] the 16-word contact record         (dContact subset)
 //   cfb     float[maxc*3][Wp]  contact feedback f1
 //   seed    uint32[Wp]         per-world LCG state                (dRandSetSeed)
-//   rows    float4[maxrows*7][Wp]  solver scratch: J(12) iMJ(12) rhs Adcfm lo hi
-//   lambda  float[maxrows][Wp], rowad float[maxrows][Wp], invIw float[nb*9][Wp]
+//   rows    float4[maxrows*4][Wp]  solver scratch A, slot-major: J1l J1a J2a rhs cfm hi Ad - meta -
+//   rowsB   float4[maxrows*4][Wp]  solver scratch B, position-major (rows in sweep order) + lambda
+//   lambda  float[maxrows][Wp] (by slot), invIw float[nb*9][Wp]
 #pragma once
 #include <stdint.h>
 
@@ -96,7 +97,10 @@ struct StepParams {
     float erp, cfm, contact_max_vel, contact_min_depth, sor_w;
     int iters, reorder;
     float *state, *force, *jcmd, *jobs, *jfb, *crec, *cfb, *lambda, *rowad, *invIw;
-    float4 *rows;
+    float4 *rows;  // scratch A: slot-major [slot][4][Wp]
+    float4 *rowsB; // scratch B: position-major [pos][4][Wp] (rows in sweep order)
+    float *lambdaB; // lambda by sweep position [pos][Wp]
+    uint8_t *ord;   // row order [pos][Wp] -> slot
     uint8_t *jrows;
     int *ccount;
     int *nrows;

@@ -28,23 +28,34 @@
 namespace {
 
 constexpr int BD = 64;   // threads (= worlds) per CTA: 8 CTAs/SM at <=128 registers, fine-grained waves
+constexpr int STAGES = 3; // cp.async ring depth: STAGES-1 rows in flight per thread
 constexpr int ROWV = 4; // float4 per stored row: one 64-byte line per (world,row)
 
 struct Smem {
     float *fc;     // [nb*6][BD]   fe -> tmp1 -> fc
     float *iw;     // [nb*6][BD]   symmetric invI_world (xx xy xz yy yz zz) for the sweep
     float *im;     // [nb]         invMass (shared by the CTA)
-    float *lam;    // [maxrows][BD] lambda (only when it fits; else it lives in the row line)
     float *lamn;   // [maxc][BD]   lambda of each contact's normal row (read by its friction rows)
-    uint8_t *ord;  // [maxrows][BD]
+    float4 *ring;  // [STAGES][4][BD] cp.async ring of rows in sweep order
+    float *lring;  // [STAGES][BD]    ... and of their lambdas
     uint8_t *jm;   // [nj][BD]     rows of joint j in this world
     int8_t *jl;    // [nj][BD]     local limot row feeding feedback.lambda, or -1
-    uint8_t *cm;   // [maxc][BD]   rows of contact c
-    uint16_t *cb;  // [maxc][BD]   body0 | body1<<8
-    int *jmeta;    // [njslots]    body0 | body1<<8 of each joint slot (shared by the CTA)
+    uint8_t *cm;   // [maxc][BD]   rows of contact c | dependency mask << 3
 };
 
 #define G(arr, field) (arr)[(size_t)(field) * Wp + w]
+
+// Ampere-style asynchronous copies (LDGSTS): completion is tracked per thread by async groups.
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g));
+}
+__device__ __forceinline__ void cp_async4(uint32_t smem_addr, const void *g)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(g));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 struct BodyPose {
     float pos[3], q[4], R[9];
@@ -75,7 +86,7 @@ __device__ __forceinline__ void load_invIw(const StepParams &P, int b, int w, fl
 struct Row {
     float J[12];
     float c, cfm, lo, hi;
-    int fslot; // slot of the normal row this (friction) row depends on, or 0xFF
+    int fr, nr; // contact index + 1 if this is a friction-dependent row / a contact normal row, else 0
 };
 
 __device__ __forceinline__ void row_init(Row &r, float world_cfm)
@@ -86,7 +97,8 @@ __device__ __forceinline__ void row_init(Row &r, float world_cfm)
     r.cfm = world_cfm;
     r.lo = -INFINITY;
     r.hi = INFINITY;
-    r.fslot = 0xFF;
+    r.fr = 0;
+    r.nr = 0;
 }
 
 struct PairCtx {
@@ -98,9 +110,9 @@ struct PairCtx {
 // rhs = c/h - J.tmp1 ; iMJ = invM J^T ; Ad = w/(J iMJ + cfm/h) ; scale ; store.
 // Follows ODE quickstep stage 2c / SOR_LCP setup, same operation order as oracle/orc_quickstep.c.
 __device__ __forceinline__ void emit_row(const StepParams &P, const Smem &S, int w, int tid, int slot, Row &r,
-                                         const PairCtx &pc)
+                                         const PairCtx &pc, int bpos = -1)
 {
-    (void)0;
+    const int Wp = P.Wp;
     const float hinv = 1.0f / P.h;
     float rhs = r.c * hinv;
     const float cfm = r.cfm * hinv;
@@ -144,16 +156,30 @@ __device__ __forceinline__ void emit_row(const StepParams &P, const Smem &S, int
     if (r.lo == 0.f && r.hi == INFINITY) hi_enc = __int_as_float(0xFFFFFFFF);       // [0, +inf)
     else if (r.lo == -INFINITY && r.hi == 0.f) hi_enc = __int_as_float(0xFFFFFFFE); // (-inf, 0]
     else hi_enc = r.hi;                                                               // [-hi, hi]
-    // Rows are stored world-major: the 64-byte line of (world, slot) holds the whole row, so a lane
-    // that follows its own (shuffled) row order still uses every byte of every sector it touches.
-    float4 *dst = P.rows + ((size_t)w * P.T->maxrows + slot) * ROWV;
-    dst[0] = make_float4(r.J[0], r.J[1], r.J[2], r.J[3]);
-    dst[1] = make_float4(r.J[4], r.J[5], r.J[9], r.J[10]);
-    dst[2] = make_float4(r.J[11], rhs, cfm, hi_enc);
-    // .y = lambda (when not in shared memory); .z = body0 | body1<<8 | fslot<<16, where a row with one
-    // body points its second half at the all-zero dummy body `nb` (branch-free sweep)
-    const int meta = (pc.b0 & 0xff) | ((pc.b1 < 0 ? P.T->nb : pc.b1) << 8) | (r.fslot << 16);
-    dst[3] = make_float4(Ad, 0.f, __int_as_float(meta), 0.f);
+    // Scratch A is slot-major SoA ([slot][4][world], coalesced when the slot is warp-uniform, as it is
+    // here and in the feedback pass).  .w of the last vector packs body0 | body1<<8 | fr<<16 | nr<<24:
+    // body1 = 0xff marks a one-body row;
+    // fr / nr = contact index + 1 for a friction-dependent row / a contact normal row.
+    const int meta = (pc.b0 & 0xff) | ((pc.b1 < 0 ? 0xff : pc.b1) << 8) | (r.fr << 16) | (r.nr << 24);
+    const float4 q0 = make_float4(r.J[0], r.J[1], r.J[2], r.J[3]);
+    const float4 q1 = make_float4(r.J[4], r.J[5], r.J[9], r.J[10]);
+    const float4 q2 = make_float4(r.J[11], rhs, cfm, hi_enc);
+    const float4 q3 = make_float4(Ad, 0.f, __int_as_float(meta), 0.f);
+    float4 *dst = P.rows + (size_t)(slot * ROWV) * Wp + w;
+    dst[0 * (size_t)Wp] = q0;
+    dst[1 * (size_t)Wp] = q1;
+    dst[2 * (size_t)Wp] = q2;
+    dst[3 * (size_t)Wp] = q3;
+    G(P.lambda, slot) = 0.f;
+    if (bpos >= 0) {
+        // independent rows already know their sweep position (ODE: rows with findex < 0 first, in row
+        // order), so they go straight into scratch B as well
+        float4 *db = P.rowsB + (size_t)(bpos * ROWV) * Wp + w;
+        db[0 * (size_t)Wp] = q0;
+        db[1 * (size_t)Wp] = q1;
+        db[2 * (size_t)Wp] = q2;
+        db[3 * (size_t)Wp] = q3;
+    }
 }
 
 struct LimotState {
@@ -333,43 +359,34 @@ __device__ __forceinline__ void fixed_orientation_rhs(const DevJoint &jc, const 
     for (int i = 0; i < 3; i++) c3[i] = k2 * e[i];
 }
 
-template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
+__global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevTemplate *__restrict__ T = P.T;
-    const int nb = T->nb, nj = T->nj, maxc = T->maxc, rpc = T->rpc, njslots = T->njslots, maxrows = T->maxrows;
+    const int nb = T->nb, nj = T->nj, maxc = T->maxc, rpc = T->rpc, njslots = T->njslots;
     Smem S;
     {
         unsigned char *p = smem_raw;
+        S.ring = (float4 *)p;
+        p += sizeof(float4) * (size_t)STAGES * ROWV * BD;
+        S.lring = (float *)p;
+        p += sizeof(float) * (size_t)STAGES * BD;
         S.fc = (float *)p;
-        p += sizeof(float) * (size_t)(nb + 1) * 6 * BD;
+        p += sizeof(float) * (size_t)nb * 6 * BD;
         S.iw = (float *)p;
-        p += sizeof(float) * (size_t)(nb + 1) * 6 * BD;
+        p += sizeof(float) * (size_t)nb * 6 * BD;
+        S.lamn = (float *)p;
+        p += sizeof(float) * (size_t)maxc * BD;
         S.im = (float *)p;
-        p += sizeof(float) * (size_t)(nb + 1);
-        S.jmeta = (int *)p;
-        p += sizeof(int) * (size_t)njslots;
-        S.cb = (uint16_t *)p;
-        p += sizeof(uint16_t) * (size_t)maxc * BD;
-        S.ord = p;
-        p += (size_t)maxrows * BD;
+        p += sizeof(float) * (size_t)nb;
         S.jm = p;
         p += (size_t)nj * BD;
         S.jl = (int8_t *)p;
         p += (size_t)nj * BD;
         S.cm = p;
-        p += (size_t)maxc * BD;
-        p = (unsigned char *)(((uintptr_t)p + 15) & ~(uintptr_t)15);
-        S.lamn = (float *)p;
-        p += sizeof(float) * (size_t)maxc * BD;
-        S.lam = (float *)p;
     }
     const int tid = threadIdx.x;
-    for (int s = tid; s < njslots; s += BD) {
-        const DevJoint &jc = T->joints[s / B2P_ROWS_PER_JOINT];
-        S.jmeta[s] = (jc.b0 & 0xff) | ((jc.b1 < 0 ? 0xff : jc.b1) << 8);
-    }
-    for (int b = tid; b <= nb; b += BD) S.im[b] = b < nb ? T->bodies[b].invMass : 0.f;
+    for (int b = tid; b < nb; b += BD) S.im[b] = T->bodies[b].invMass;
     __syncthreads();
     const int w = blockIdx.x * BD + tid;
     if (w >= P.W) return;
@@ -511,7 +528,7 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
     // Head rows are appended as they are emitted; dependent rows are recorded per contact in a bit
     // mask and appended after all contacts are known.
     int nhead = 0;
-    auto push_head = [&](int slot) { S.ord[(size_t)nhead++ * BD + tid] = (uint8_t)slot; };
+    auto push_head = [&](int slot) { G(P.ord, nhead++) = (uint8_t)slot; };
 
     for (int j = 0; j < nj; j++) {
         const DevJoint &jc = T->joints[j];
@@ -552,17 +569,17 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
                 r.J[0] = 1.f; r.J[4] = a1[2]; r.J[5] = -a1[1];
                 if (has_b1) { r.J[6] = -1.f; r.J[10] = -a2[2]; r.J[11] = a2[1]; }
                 r.c = cb[0];
-                emit_row(P, S, w, tid, base + 0, r, pc); push_head(base + 0);
+                emit_row(P, S, w, tid, base + 0, r, pc, nhead); push_head(base + 0);
                 row_init(r, P.cfm);
                 r.J[1] = 1.f; r.J[3] = -a1[2]; r.J[5] = a1[0];
                 if (has_b1) { r.J[7] = -1.f; r.J[9] = a2[2]; r.J[11] = -a2[0]; }
                 r.c = cb[1];
-                emit_row(P, S, w, tid, base + 1, r, pc); push_head(base + 1);
+                emit_row(P, S, w, tid, base + 1, r, pc, nhead); push_head(base + 1);
                 row_init(r, P.cfm);
                 r.J[2] = 1.f; r.J[3] = a1[1]; r.J[4] = -a1[0];
                 if (has_b1) { r.J[8] = -1.f; r.J[9] = -a2[1]; r.J[10] = a2[0]; }
                 r.c = cb[2];
-                emit_row(P, S, w, tid, base + 2, r, pc); push_head(base + 2);
+                emit_row(P, S, w, tid, base + 2, r, pc, nhead); push_head(base + 2);
                 float ax1[3], pv[3], qv[3], ax2[3], bv[3];
                 mul_R_v(ax1, p0.R, jc.axis1);
                 plane_space(ax1, pv, qv);
@@ -573,19 +590,19 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
                 r.J[3] = pv[0]; r.J[4] = pv[1]; r.J[5] = pv[2];
                 if (has_b1) { r.J[9] = -pv[0]; r.J[10] = -pv[1]; r.J[11] = -pv[2]; }
                 r.c = kerp * dot3(bv, pv);
-                emit_row(P, S, w, tid, base + 3, r, pc); push_head(base + 3);
+                emit_row(P, S, w, tid, base + 3, r, pc, nhead); push_head(base + 3);
                 row_init(r, P.cfm);
                 r.J[3] = qv[0]; r.J[4] = qv[1]; r.J[5] = qv[2];
                 if (has_b1) { r.J[9] = -qv[0]; r.J[10] = -qv[1]; r.J[11] = -qv[2]; }
                 r.c = kerp * dot3(bv, qv);
-                emit_row(P, S, w, tid, base + 4, r, pc); push_head(base + 4);
+                emit_row(P, S, w, tid, base + 4, r, pc, nhead); push_head(base + 4);
                 mrows = 5;
                 LimotState st;
                 joint_limit_state(jc, p0, p1, st);
                 row_init(r, P.cfm);
                 if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 1, p0, p1,
                                   has_b1)) {
-                    emit_row(P, S, w, tid, base + 5, r, pc); push_head(base + 5);
+                    emit_row(P, S, w, tid, base + 5, r, pc, nhead); push_head(base + 5);
                     limot_row = 5;
                     mrows = 6;
                 }
@@ -606,24 +623,24 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
                 r.J[0] = 1.f;
                 if (has_b1) { r.J[4] = -ofs[2]; r.J[5] = ofs[1]; r.J[6] = -1.f; }
                 r.c = cl[0]; r.cfm = jc.cfm;
-                emit_row(P, S, w, tid, base + 0, r, pc); push_head(base + 0);
+                emit_row(P, S, w, tid, base + 0, r, pc, nhead); push_head(base + 0);
                 row_init(r, P.cfm);
                 r.J[1] = 1.f;
                 if (has_b1) { r.J[3] = ofs[2]; r.J[5] = -ofs[0]; r.J[7] = -1.f; }
                 r.c = cl[1]; r.cfm = jc.cfm;
-                emit_row(P, S, w, tid, base + 1, r, pc); push_head(base + 1);
+                emit_row(P, S, w, tid, base + 1, r, pc, nhead); push_head(base + 1);
                 row_init(r, P.cfm);
                 r.J[2] = 1.f;
                 if (has_b1) { r.J[3] = -ofs[1]; r.J[4] = ofs[0]; r.J[8] = -1.f; }
                 r.c = cl[2]; r.cfm = jc.cfm;
-                emit_row(P, S, w, tid, base + 2, r, pc); push_head(base + 2);
+                emit_row(P, S, w, tid, base + 2, r, pc, nhead); push_head(base + 2);
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
                     row_init(r, P.cfm);
                     r.J[3 + i] = 1.f;
                     if (has_b1) r.J[9 + i] = -1.f;
                     r.c = ca[i];
-                    emit_row(P, S, w, tid, base + 3 + i, r, pc); push_head(base + 3 + i);
+                    emit_row(P, S, w, tid, base + 3 + i, r, pc, nhead); push_head(base + 3 + i);
                 }
                 mrows = 6;
             } else if (jc.type == 3) {
@@ -636,7 +653,7 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
                     r.J[3 + i] = 1.f;
                     if (has_b1) r.J[9 + i] = -1.f;
                     r.c = ca[i];
-                    emit_row(P, S, w, tid, base + i, r, pc); push_head(base + i);
+                    emit_row(P, S, w, tid, base + i, r, pc, nhead); push_head(base + i);
                 }
                 float c[3] = {0.f, 0.f, 0.f}, ax1[3], pv[3], qv[3];
                 if (has_b1) {
@@ -673,7 +690,7 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
                     if (has_b1) { r.J[3 + i] = 0.5f * tp[i]; r.J[9 + i] = 0.5f * tp[i]; r.J[6 + i] = -pv[i]; }
                 }
                 r.c = c3;
-                emit_row(P, S, w, tid, base + 3, r, pc); push_head(base + 3);
+                emit_row(P, S, w, tid, base + 3, r, pc, nhead); push_head(base + 3);
                 row_init(r, P.cfm);
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
@@ -681,14 +698,14 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
                     if (has_b1) { r.J[3 + i] = 0.5f * tq[i]; r.J[9 + i] = 0.5f * tq[i]; r.J[6 + i] = -qv[i]; }
                 }
                 r.c = c4;
-                emit_row(P, S, w, tid, base + 4, r, pc); push_head(base + 4);
+                emit_row(P, S, w, tid, base + 4, r, pc, nhead); push_head(base + 4);
                 mrows = 5;
                 LimotState st;
                 joint_limit_state(jc, p0, p1, st);
                 row_init(r, P.cfm);
                 if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 0, p0, p1,
                                   has_b1)) {
-                    emit_row(P, S, w, tid, base + 5, r, pc); push_head(base + 5);
+                    emit_row(P, S, w, tid, base + 5, r, pc, nhead); push_head(base + 5);
                     limot_row = 5;
                     mrows = 6;
                 }
@@ -722,20 +739,20 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
                     cross3(r.J + 9, dv, a2);
                     r.c = (i == 0 ? k1 : kerp) * dot3(dv, d);
                     if (i == 0) r.cfm = jc.susp_cfm;
-                    emit_row(P, S, w, tid, base + i, r, pc); push_head(base + i);
+                    emit_row(P, S, w, tid, base + i, r, pc, nhead); push_head(base + i);
                 }
                 row_init(r, P.cfm);
 #pragma unroll
                 for (int i = 0; i < 3; i++) { r.J[3 + i] = qv[i]; r.J[9 + i] = -qv[i]; }
                 r.c = kerp * (jc.c0 * sn - jc.s0 * cs);
-                emit_row(P, S, w, tid, base + 3, r, pc); push_head(base + 3);
+                emit_row(P, S, w, tid, base + 3, r, pc, nhead); push_head(base + 3);
                 mrows = 4;
                 LimotState st;
                 joint_limit_state(jc, p0, p1, st);
                 row_init(r, P.cfm);
                 if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 1, p0, p1,
                                   true)) {
-                    emit_row(P, S, w, tid, base + mrows, r, pc); push_head(base + mrows);
+                    emit_row(P, S, w, tid, base + mrows, r, pc, nhead); push_head(base + mrows);
                     limot_row = mrows;
                     mrows++;
                 }
@@ -745,7 +762,7 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
                 row_init(r, P.cfm);
                 if (add_limot_row(P, jc.limot2, G(P.jcmd, j * 4 + 2), G(P.jcmd, j * 4 + 3), st2, r, ax2, 1, p0, p1,
                                   true)) {
-                    emit_row(P, S, w, tid, base + mrows, r, pc); push_head(base + mrows);
+                    emit_row(P, S, w, tid, base + mrows, r, pc, nhead); push_head(base + mrows);
                     if (limot_row < 0) limot_row = mrows;
                     mrows++;
                 }
@@ -763,7 +780,6 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
         const int ids = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_IDS));
         const int b0 = ids & 0xff;
         const int b1 = ((ids >> 8) & 0xff) == 0xff ? -1 : ((ids >> 8) & 0xff);
-        S.cb[(size_t)c * BD + tid] = (uint16_t)(ids & 0xffff);
         const int mode = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_MODE));
         float pos[3] = {G(P.crec, c * B2P_CONTACT_FIELDS + CR_PX), G(P.crec, c * B2P_CONTACT_FIELDS + CR_PY),
                         G(P.crec, c * B2P_CONTACT_FIELDS + CR_PZ)};
@@ -809,7 +825,8 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
         if (mode & 0x010) r.cfm = soft_cfm;
         r.lo = 0.f;
         r.hi = INFINITY;
-        emit_row(P, S, w, tid, base, r, pc);
+        r.nr = c + 1;
+        emit_row(P, S, w, tid, base, r, pc, nhead);
         push_head(base);
         int row = 1, depmask = 0;
         float t1[3], t2[3];
@@ -825,9 +842,14 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
             if (b1 >= 0) { r.J[6] = -t1[0]; r.J[7] = -t1[1]; r.J[8] = -t1[2]; cross3(r.J + 9, t1, c2); }
             r.lo = -mu;
             r.hi = mu;
-            if (mode & 0x1000) r.fslot = base;
-            emit_row(P, S, w, tid, base + row, r, pc);
-            if (mode & 0x1000) depmask |= 1 << (row - 1); else push_head(base + row);
+            if (mode & 0x1000) r.fr = c + 1;
+            if (mode & 0x1000) {
+                depmask |= 1 << (row - 1);
+                emit_row(P, S, w, tid, base + row, r, pc);
+            } else {
+                emit_row(P, S, w, tid, base + row, r, pc, nhead);
+                push_head(base + row);
+            }
             row++;
         }
         if (fr2) {
@@ -837,9 +859,14 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
             if (b1 >= 0) { r.J[6] = -t2[0]; r.J[7] = -t2[1]; r.J[8] = -t2[2]; cross3(r.J + 9, t2, c2); }
             r.lo = -mu2e;
             r.hi = mu2e;
-            if (mode & 0x2000) r.fslot = base;
-            emit_row(P, S, w, tid, base + row, r, pc);
-            if (mode & 0x2000) depmask |= 1 << (row - 1); else push_head(base + row);
+            if (mode & 0x2000) r.fr = c + 1;
+            if (mode & 0x2000) {
+                depmask |= 1 << (row - 1);
+                emit_row(P, S, w, tid, base + row, r, pc);
+            } else {
+                emit_row(P, S, w, tid, base + row, r, pc, nhead);
+                push_head(base + row);
+            }
             row++;
         }
         if ((mode & 0x400) && rpc >= 6) {
@@ -862,9 +889,14 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
                     if (b1 >= 0) { r.J[9] = -ax[i][0]; r.J[10] = -ax[i][1]; r.J[11] = -ax[i][2]; }
                     r.lo = -rho[i];
                     r.hi = rho[i];
-                    if (mode & bits[i]) r.fslot = base;
-                    emit_row(P, S, w, tid, base + row, r, pc);
-                    if (mode & bits[i]) depmask |= 1 << (row - 1); else push_head(base + row);
+                    if (mode & bits[i]) r.fr = c + 1;
+                    if (mode & bits[i]) {
+                        depmask |= 1 << (row - 1);
+                        emit_row(P, S, w, tid, base + row, r, pc);
+                    } else {
+                        emit_row(P, S, w, tid, base + row, r, pc, nhead);
+                        push_head(base + row);
+                    }
                     row++;
                 }
             }
@@ -877,71 +909,117 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
         const int v = S.cm[(size_t)c * BD + tid];
         const int rows_c = v & 7, depmask = v >> 3;
         for (int k = 1; k < rows_c; k++)
-            if (depmask & (1 << (k - 1))) S.ord[(size_t)m++ * BD + tid] = (uint8_t)(njslots + c * rpc + k);
+            if (depmask & (1 << (k - 1))) G(P.ord, m++) = (uint8_t)(njslots + c * rpc + k);
     }
     G(P.nrows, 0) = m;
 
     // tmp1 -> gmem? not needed: epilogue uses fe from gmem.  fc = 0
-    for (int k = 0; k < (nb + 1) * 6; k++) S.fc[(size_t)k * BD + tid] = 0.f;
-    for (int k = nb * 6; k < (nb + 1) * 6; k++) S.iw[(size_t)k * BD + tid] = 0.f;
-    if (LAM_SMEM)
-        for (int k = 0; k < maxrows; k++) S.lam[(size_t)k * BD + tid] = 0.f;
+    for (int k = 0; k < nb * 6; k++) S.fc[(size_t)k * BD + tid] = 0.f;
     for (int k = 0; k < maxc; k++) S.lamn[(size_t)k * BD + tid] = 0.f;
 
     // ---------------- phase 3: SOR-LCP sweep ----------------
+    // Each world follows its own row order (per-world contact count and RNG state).  Reading rows
+    // through a per-lane index would make every warp load touch 32 different lines, and L1TEX then
+    // serialises 32 wavefronts per instruction (measured: profiles/r1_v4_*).  Instead the rows are
+    // physically permuted into sweep order whenever the order changes (iteration 0 and ODE's
+    // reshuffles at 8, 16): scratch B is POSITION-major SoA, so position k of all 32 worlds of a warp
+    // is one coalesced line per vector even though every lane holds a different constraint there.
+    // The scattered traffic is paid 3 times per step instead of 20.
     uint32_t seed = G(P.seed, 0);
+    float4 *const Bq = P.rowsB + w;  // B[pos][v][world]
+    float *const Lq = P.lambdaB + w; // lambda by sweep position: L[pos][world]
+    // lambda by position -> lambda by slot (scattered 4-byte stores; 3 times per step)
+    auto writeback_lambda = [&]() {
+        for (int pos = 0; pos < m; pos++) G(P.lambda, G(P.ord, pos)) = Lq[(size_t)pos * Wp];
+    };
+    // A (slot-major) -> B (position-major) for positions [start, m): reads are scattered by the per-lane
+    // slot index (32 lines per warp load), which is why this is done per reshuffle and not per sweep.
+    // (Keeping four rows in flight per thread did not help: the pass is L1TEX-wavefront bound.)
+    auto permute_rows = [&](int start) {
+        for (int pos = start; pos < m; pos++) {
+            const int i = G(P.ord, pos);
+            const float4 *src = P.rows + (size_t)(i * ROWV) * Wp + w;
+            const float4 q0 = src[0], q1 = src[(size_t)Wp], q2 = src[2 * (size_t)Wp], q3 = src[3 * (size_t)Wp];
+            float4 *dst = Bq + (size_t)(pos * ROWV) * Wp;
+            dst[0] = q0;
+            dst[(size_t)Wp] = q1;
+            dst[2 * (size_t)Wp] = q2;
+            dst[3 * (size_t)Wp] = q3;
+            Lq[(size_t)pos * Wp] = G(P.lambda, i);
+        }
+    };
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(S.ring + tid);
+    const uint32_t lring_s = (uint32_t)__cvta_generic_to_shared(S.lring + tid);
     for (int it = 0; it < P.iters; it++) {
-        if (P.reorder == 0 && it >= 8 && (it & 7) == 0) {
+        const bool reshuffle = P.reorder == 0 && it >= 8 && (it & 7) == 0;
+        if (reshuffle) {
+            writeback_lambda();
             // ODE ConstraintsReorderingHelper on [0,nhead) and [nhead,m)
             for (int idx = 1; idx < nhead; idx++) {
                 const int sw = rand_int(seed, idx + 1);
-                const uint8_t a = S.ord[(size_t)idx * BD + tid], bq = S.ord[(size_t)sw * BD + tid];
-                S.ord[(size_t)idx * BD + tid] = bq;
-                S.ord[(size_t)sw * BD + tid] = a;
+                const uint8_t a = G(P.ord, idx), bq = G(P.ord, sw);
+                G(P.ord, idx) = bq;
+                G(P.ord, sw) = a;
             }
             for (int idx = nhead + 1; idx < m; idx++) {
                 const int sw = rand_int(seed, idx - nhead + 1) + nhead;
-                const uint8_t a = S.ord[(size_t)idx * BD + tid], bq = S.ord[(size_t)sw * BD + tid];
-                S.ord[(size_t)idx * BD + tid] = bq;
-                S.ord[(size_t)sw * BD + tid] = a;
+                const uint8_t a = G(P.ord, idx), bq = G(P.ord, sw);
+                G(P.ord, idx) = bq;
+                G(P.ord, sw) = a;
             }
         }
-        // Software pipeline: while one row is processed the next one is already in flight (row loads
-        // do not depend on the sequential fc/lambda state).  Two register sets ping-pong so that no
-        // moves are needed.  The sweep body is branch-free: one-body rows use the zero dummy body.
-        struct Pre {
-            float4 a, b, c, d;
-            int i;
+        if (it == 0 || reshuffle) {
+            // at iteration 0 the head rows are already in place (written by emit_row)
+            permute_rows(it == 0 ? nhead : 0);
+            if (it == 0)
+                for (int pos = 0; pos < nhead; pos++) Lq[(size_t)pos * Wp] = 0.f;
+        }
+        // Sweep.  Rows stream through a per-thread cp.async ring in shared memory (STAGES-1 rows in
+        // flight per thread, tracked by async groups rather than by the six scoreboard slots, which is
+        // what limited register prefetching: profiles/r1_v6_*).  Row loads do not depend on the
+        // sequential fc/lambda state, so the ring runs ahead freely.
+        auto issue = [&](int pos) {
+            const int st = pos % STAGES;
+            const float4 *src = Bq + (size_t)(pos * ROWV) * Wp;
+            const uint32_t d = ring_s + (uint32_t)(st * ROWV * BD * 16);
+            cp_async16(d, src);
+            cp_async16(d + BD * 16, src + (size_t)Wp);
+            cp_async16(d + 2 * BD * 16, src + 2 * (size_t)Wp);
+            cp_async16(d + 3 * BD * 16, src + 3 * (size_t)Wp);
+            cp_async4(lring_s + (uint32_t)(st * BD * 4), Lq + (size_t)pos * Wp);
         };
-        float4 *const rowbase = P.rows + (size_t)w * maxrows * ROWV;
-        auto fetch = [&](int pos, Pre &r) {
-            r.i = S.ord[(size_t)pos * BD + tid];
-            const float4 *src = rowbase + r.i * ROWV;
-            r.a = __ldcs(src);
-            r.b = __ldcs(src + 1);
-            r.c = __ldcs(src + 2);
-            r.d = LAM_SMEM ? __ldcs(src + 3) : __ldcg(src + 3);
-        };
-        auto process = [&](const Pre &r) {
-            const float4 c0 = r.a, c1 = r.b, c2 = r.c;
-            const int meta = __float_as_int(r.d.z);
-            const int b0 = meta & 0xff, b1 = (meta >> 8) & 0xff, fslot = (meta >> 16) & 0xff;
+#pragma unroll
+        for (int p0 = 0; p0 < STAGES - 1; p0++) {
+            if (p0 < m) issue(p0);
+            cp_async_commit();
+        }
+        for (int k = 0; k < m; k++) {
+            if (k + STAGES - 1 < m) issue(k + STAGES - 1);
+            cp_async_commit();
+            cp_async_wait<STAGES - 1>();
+            const int st = k % STAGES;
+            const float4 *rq = S.ring + (size_t)(st * ROWV) * BD + tid;
+            const float4 c0 = rq[0], c1 = rq[BD], c2 = rq[2 * BD], c3 = rq[3 * BD];
+            const float lam_old = S.lring[(size_t)st * BD + tid];
+            const int meta = __float_as_int(c3.z);
+            const int b0 = meta & 0xff, b1r = (meta >> 8) & 0xff, fr = (meta >> 16) & 0xff, nr = (meta >> 24) & 0xff;
+            const bool two = b1r != 0xff;
+            const int b1 = two ? b1r : b0;
+            const float s2 = two ? 1.f : 0.f;
             float *f0 = S.fc + (size_t)(b0 * 6) * BD + tid;
             float *f1 = S.fc + (size_t)(b1 * 6) * BD + tid;
-            const float lam_old = LAM_SMEM ? S.lam[(size_t)r.i * BD + tid] : r.d.y;
             // unscaled J: J1l = c0.xyz, J1a = (c0.w, c1.x, c1.y), J2l = -J1l, J2a = (c1.z, c1.w, c2.x)
-            const float dl = (f0[0 * BD] - f1[0 * BD]) * c0.x + (f0[1 * BD] - f1[1 * BD]) * c0.y +
-                             (f0[2 * BD] - f1[2 * BD]) * c0.z;
+            const float dl = (f0[0 * BD] - s2 * f1[0 * BD]) * c0.x + (f0[1 * BD] - s2 * f1[1 * BD]) * c0.y +
+                             (f0[2 * BD] - s2 * f1[2 * BD]) * c0.z;
             const float da = f0[3 * BD] * c0.w + f0[4 * BD] * c1.x + f0[5 * BD] * c1.y + f1[3 * BD] * c1.z +
-                             f1[4 * BD] * c1.w + f1[5 * BD] * c2.x;
-            float delta = r.d.x * (c2.y - lam_old * c2.z - (dl + da));
+                             f1[4 * BD] * c1.w + f1[5 * BD] * c2.x; // J2a == 0 for one-body rows
+            float delta = c3.x * (c2.y - lam_old * c2.z - (dl + da));
             float lo_act, hi_act;
             const int enc = __float_as_int(c2.w);
-            if (fslot != 0xff) {
-                // friction row: bounds follow the normal row's current lambda (same sweep), which is
-                // mirrored in shared memory so that this is not a dependent global load
-                const float lam_n = S.lamn[(size_t)((fslot - njslots) / rpc) * BD + tid];
-                hi_act = fabsf(c2.w * lam_n);
+            if (fr) {
+                // friction row: bounds follow the normal row's current lambda (same sweep), mirrored in
+                // shared memory by contact index
+                hi_act = fabsf(c2.w * S.lamn[(size_t)(fr - 1) * BD + tid]);
                 lo_act = -hi_act;
             } else {
                 hi_act = enc == (int)0xFFFFFFFF ? INFINITY : (enc == (int)0xFFFFFFFE ? 0.f : c2.w);
@@ -950,9 +1028,8 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
             const float un = lam_old + delta;
             const float nl = fminf(fmaxf(un, lo_act), hi_act);
             delta = (nl == un) ? delta : nl - lam_old;
-            if (r.i >= njslots && (r.i - njslots) % rpc == 0) S.lamn[(size_t)((r.i - njslots) / rpc) * BD + tid] = nl;
-            if (LAM_SMEM) S.lam[(size_t)r.i * BD + tid] = nl;
-            else __stcg(reinterpret_cast<float *>(rowbase + r.i * ROWV + 3) + 1, nl);
+            if (nr) S.lamn[(size_t)(nr - 1) * BD + tid] = nl;
+            Lq[(size_t)k * Wp] = nl;
             // fc += delta * invM J^T, with invI_world (symmetric) from shared memory
             {
                 const float dm = delta * S.im[b0];
@@ -967,7 +1044,7 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
                 f0[4 * BD] += ixy * a0 + iyy * a1 + iyz * a2;
                 f0[5 * BD] += ixz * a0 + iyz * a1 + izz * a2;
             }
-            {
+            if (two) {
                 const float dm = delta * S.im[b1];
                 const float *Iw = S.iw + (size_t)(b1 * 6) * BD + tid;
                 const float a0 = delta * c1.z, a1 = delta * c1.w, a2 = delta * c2.x;
@@ -980,28 +1057,10 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
                 f1[4 * BD] += ixy * a0 + iyy * a1 + iyz * a2;
                 f1[5 * BD] += ixz * a0 + iyz * a1 + izz * a2;
             }
-        };
-        Pre ra, rb, rc, rd;
-        if (m > 0) fetch(0, ra);
-        if (m > 1) fetch(1, rb);
-        if (m > 2) fetch(2, rc);
-        for (int k = 0; k < m; k += 4) {
-            if (k + 3 < m) fetch(k + 3, rd);
-            process(ra);
-            if (k + 1 < m) {
-                if (k + 4 < m) fetch(k + 4, ra);
-                process(rb);
-            }
-            if (k + 2 < m) {
-                if (k + 5 < m) fetch(k + 5, rb);
-                process(rc);
-            }
-            if (k + 3 < m) {
-                if (k + 6 < m) fetch(k + 6, rc);
-                process(rd);
-            }
         }
+        cp_async_wait<0>();
     }
+    writeback_lambda();
     G(P.seed, 0) = seed;
 
     // ---------------- phase 4a: joint / contact feedback from the unscaled Jacobian ------------
@@ -1015,9 +1074,9 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
         float flam = 0.f;
         for (int k = 0; k < mrows; k++) {
             const int slot = jc.slot_base + k;
-            const float4 *src = P.rows + ((size_t)w * maxrows + slot) * ROWV;
-            const float4 j0 = src[0], j1 = src[1], j2 = src[2];
-            const float lam = LAM_SMEM ? S.lam[(size_t)slot * BD + tid] : reinterpret_cast<const float *>(src + 3)[1];
+            const float4 *src = P.rows + (size_t)(slot * ROWV) * Wp + w;
+            const float4 j0 = src[0], j1 = src[(size_t)Wp], j2 = src[2 * (size_t)Wp];
+            const float lam = G(P.lambda, slot);
             data[0] += j0.x * lam; data[1] += j0.y * lam; data[2] += j0.z * lam;
             data[3] += j0.w * lam; data[4] += j1.x * lam; data[5] += j1.y * lam;
             data[6] -= j0.x * lam; data[7] -= j0.y * lam; data[8] -= j0.z * lam;
@@ -1037,9 +1096,8 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
         float f[3] = {0.f, 0.f, 0.f};
         for (int k = 0; k < mrows; k++) {
             const int slot = njslots + c * rpc + k;
-            const float4 *src = P.rows + ((size_t)w * maxrows + slot) * ROWV;
-            const float4 j0 = src[0];
-            const float lam = LAM_SMEM ? S.lam[(size_t)slot * BD + tid] : reinterpret_cast<const float *>(src + 3)[1];
+            const float4 j0 = P.rows[(size_t)(slot * ROWV) * Wp + w];
+            const float lam = G(P.lambda, slot);
             f[0] += j0.x * lam;
             f[1] += j0.y * lam;
             f[2] += j0.z * lam;
@@ -1159,51 +1217,30 @@ template <bool LAM_SMEM> __global__ void __launch_bounds__(BD, 8) b2p_step_kerne
 
 static size_t smem_base_bytes(int nb, int nj, int maxc, int rpc)
 {
-    const int njslots = nj * B2P_ROWS_PER_JOINT;
-    const int maxrows = njslots + maxc * rpc;
-    size_t s = sizeof(float) * (size_t)(nb + 1) * 12 * BD + sizeof(float) * (size_t)(nb + 1);
-    s += sizeof(int) * (size_t)njslots;
-    s += sizeof(uint16_t) * (size_t)maxc * BD;
-    s += (size_t)maxrows * BD;
+    (void)rpc;
+    size_t s = sizeof(float4) * (size_t)STAGES * ROWV * BD + sizeof(float) * (size_t)STAGES * BD;
+    s += sizeof(float) * (size_t)nb * 12 * BD;
+    s += sizeof(float) * (size_t)maxc * BD;
+    s += sizeof(float) * (size_t)nb;
     s += (size_t)nj * BD * 2;
     s += (size_t)maxc * BD;
-    s = (s + 15) & ~(size_t)15;
-    s += sizeof(float) * (size_t)maxc * BD;
-    return s;
+    return (s + 15) & ~(size_t)15;
 }
 
-// lambda goes to shared memory when that still leaves >= 7 resident CTAs per SM (7 x 64 threads x
-// 148 SMs >= 65536 worlds in a single wave)
-static bool lambda_in_smem(int nb, int nj, int maxc, int rpc)
-{
-    const int maxrows = nj * B2P_ROWS_PER_JOINT + maxc * rpc;
-    const size_t s = smem_base_bytes(nb, nj, maxc, rpc) + sizeof(float) * (size_t)maxrows * BD + 1024;
-    return s * 7 <= 227 * 1024;
-}
-
-extern "C" size_t b2p_step_smem_bytes(int nb, int nj, int maxc, int rpc)
-{
-    const int maxrows = nj * B2P_ROWS_PER_JOINT + maxc * rpc;
-    size_t s = smem_base_bytes(nb, nj, maxc, rpc);
-    if (lambda_in_smem(nb, nj, maxc, rpc)) s += sizeof(float) * (size_t)maxrows * BD;
-    return s;
-}
+extern "C" size_t b2p_step_smem_bytes(int nb, int nj, int maxc, int rpc) { return smem_base_bytes(nb, nj, maxc, rpc); }
 
 extern "C" int b2p_step_block_dim(void) { return BD; }
 
 extern "C" cudaError_t b2p_launch_step(const StepParams *P, int nb, int nj, int maxc, int rpc, cudaStream_t stream)
 {
-    static size_t configured[2] = {0, 0};
-    const bool ls = lambda_in_smem(nb, nj, maxc, rpc);
+    static size_t configured = 0;
     const size_t smem = b2p_step_smem_bytes(nb, nj, maxc, rpc);
-    if (smem > configured[ls]) {
-        cudaError_t e = ls ? cudaFuncSetAttribute(b2p_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(b2p_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(b2p_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[ls] = smem;
+        configured = smem;
     }
     const int grid = (P->W + BD - 1) / BD;
-    if (ls) b2p_step_kernel<true><<<grid, BD, smem, stream>>>(*P);
-    else b2p_step_kernel<false><<<grid, BD, smem, stream>>>(*P);
+    b2p_step_kernel<<<grid, BD, smem, stream>>>(*P);
     return cudaGetLastError();
 }
