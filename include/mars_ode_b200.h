@@ -178,7 +178,7 @@ void *b2p_device_state(b2p_arena *a);       /* [nb*13][Wp] */
 void *b2p_device_joint_cmd(b2p_arena *a);   /* [nj*4][Wp]: vel1,fmax1,vel2,fmax2 */
 void *b2p_device_joint_obs(b2p_arena *a);   /* [nj*4][Wp]: angle1,rate1,angle2,rate2 */
 
-/* ---- joints (dJoint*: src/joints/*.cpp) ---- */
+/* ---- joints (dJoint*: reference src/joints/) ---- */
 int b2p_joint_create(b2p_arena *a, int type, int body1, int body2);         /* dJointCreate* + dJointAttach */
 int b2p_joint_set_anchor(b2p_arena *a, int joint, double x, double y, double z);
 int b2p_joint_set_axis1(b2p_arena *a, int joint, double x, double y, double z);

@@ -1,0 +1,248 @@
+// WorldPhysics.cpp -- see WorldPhysics.hpp.  Behaviour follows reference src/WorldPhysics.cpp; the ODE
+// calls are replaced by the b2p_* C ABI (include/mars_ode_b200.h).
+#include "WorldPhysics.hpp"
+
+#include <cstdio>
+#include <iostream>
+
+#include "Frame.hpp"
+#include "Joints.hpp"
+#include "Objects.hpp"
+
+namespace mars {
+namespace ode_physics {
+
+using namespace utils;
+using namespace interfaces;
+
+PhysicsError WorldPhysics::error = PHYSICS_NO_ERROR;
+
+void checkB2P(int rc, const char *what)
+{
+    if (rc < 0) {
+        WorldPhysics::error = PHYSICS_ERROR;
+        throw std::runtime_error(std::string(what) + ": " + b2p_last_error());
+    }
+}
+
+// defaults of reference src/WorldPhysics.cpp:80-99
+WorldPhysics::WorldPhysics() : interfaces::PhysicsInterface()
+{
+    fast_step = 0;
+    world_cfm = 1e-10;
+    world_erp = 0.1;
+    world_gravity = Vector{0.0, 0.0, -9.81};
+    ground_friction = 20;
+    ground_cfm = 0.00000001;
+    ground_erp = 0.1;
+    arena = nullptr;
+    world_init = false;
+    max_angular_speed = 10.0;
+    max_correcting_vel = 5.0;
+    step_size = 0.01;
+    num_worlds = 1;
+    device = 0;
+    max_contacts = 8;
+    warned_dense_step = false;
+}
+
+WorldPhysics::~WorldPhysics(void) { freeTheWorld(); }
+
+std::string WorldPhysics::getLibName(void) { return "mars_ode_physics"; }
+
+void WorldPhysics::setNumWorlds(int n)
+{
+    if (world_init) throw std::runtime_error("WorldPhysics::setNumWorlds: call before initTheWorld");
+    num_worlds = n;
+}
+
+// reference :162-203: seed 11211, gravity / cfm / erp / max angular speed / max correcting velocity
+void WorldPhysics::initTheWorld(void)
+{
+    const MutexLocker locker{&iMutex};
+    if (world_init) return;
+    checkB2P(b2p_arena_create(num_worlds, device, &arena), "WorldPhysics::initTheWorld");
+    b2p_arena_set_max_contacts(arena, max_contacts);
+    b2p_world_rand_set_seed(arena, 11211u);
+    old_gravity = world_gravity;
+    old_cfm = world_cfm;
+    old_erp = world_erp;
+    b2p_world_set_gravity(arena, world_gravity.x(), world_gravity.y(), world_gravity.z());
+    b2p_world_set_cfm(arena, world_cfm);
+    b2p_world_set_erp(arena, world_erp);
+    b2p_world_set_max_angular_speed(arena, max_angular_speed);
+    b2p_world_set_contact_max_correcting_vel(arena, max_correcting_vel);
+    world_init = true;
+}
+
+void WorldPhysics::freeTheWorld(void)
+{
+    clearObjects();
+    const MutexLocker locker{&iMutex};
+    if (world_init) {
+        b2p_arena_destroy(arena);
+        arena = nullptr;
+        world_init = false;
+    }
+}
+
+bool WorldPhysics::existsWorld(void) const { return world_init; }
+
+void WorldPhysics::preStepChecks(void)
+{
+    if (old_gravity != world_gravity) {
+        old_gravity = world_gravity;
+        b2p_world_set_gravity(arena, world_gravity.x(), world_gravity.y(), world_gravity.z());
+    }
+    if (old_cfm != world_cfm) {
+        old_cfm = world_cfm;
+        b2p_world_set_cfm(arena, world_cfm);
+    }
+    if (old_erp != world_erp) {
+        old_erp = world_erp;
+        b2p_world_set_erp(arena, world_erp);
+    }
+}
+
+void WorldPhysics::clearPreviousStep(void)
+{
+    if (!world_init) return;
+    b2p_contacts_clear(arena, B2P_ALL_WORLDS);
+    for (auto &pair : frameMap)
+        if (auto f = pair.second.lock()) f->clearContactData();
+}
+
+void WorldPhysics::computeContactForces()
+{
+    for (auto &pair : frameMap)
+        if (auto f = pair.second.lock()) f->computeContactForce();
+}
+
+// reference :349-421.  Only the quickstep path exists on the device; fast_step == false (dWorldStep,
+// a dense LCP) is out of scope and is served by the same quickstep kernel
+// after a one-time warning.
+void WorldPhysics::stepTheWorld(void)
+{
+    const MutexLocker locker{&iMutex};
+    if (!(world_init && step_size > 0)) return;
+    preStepChecks();
+    if (!fast_step && !warned_dense_step) {
+        fprintf(stderr, "mars_ode_physics_b200: fast_step == false (dWorldStep) is not implemented; using quickstep\n");
+        warned_dense_step = true;
+    }
+    try {
+        checkB2P(b2p_step(arena, step_size), "WorldPhysics::stepTheWorld");
+        for (auto it = jointMap.begin(); it != jointMap.end();) {
+            if (auto joint = it->second.lock()) {
+                joint->update();
+                ++it;
+            } else {
+                it = jointMap.erase(it);
+            }
+        }
+        for (auto it = frameMap.begin(); it != frameMap.end();) {
+            if (auto frame = it->second.lock()) {
+                frame->update();
+                ++it;
+            } else {
+                it = frameMap.erase(it);
+            }
+        }
+        computeContactForces();
+    } catch (const std::exception &e) {
+        fprintf(stderr, "WorldPhysics::stepTheWorld: %s\n", e.what());
+    }
+    if (WorldPhysics::error) WorldPhysics::error = PHYSICS_NO_ERROR;
+}
+
+b2p_arena *WorldPhysics::getWorld(void) const { return arena; }
+sReal WorldPhysics::getWorldStep(void) { return step_size; }
+
+void WorldPhysics::exportWorld() { std::cout << "EXPORT WORLD (not supported by the device arena)" << std::endl; }
+
+int WorldPhysics::createContact(const b2p_contact_desc &c, int body1, int body2, int world)
+{
+    const int rc = b2p_contact_add(arena, world, body1, body2, &c);
+    if (rc == B2P_EREJECTED) return -1; // joint-connected bodies (reference :461)
+    checkB2P(rc, "WorldPhysics::createContact");
+    return rc;
+}
+
+const Vector WorldPhysics::getCenterOfMass(const std::vector<std::shared_ptr<NodeInterface>> &) const { return Vector(); }
+
+std::shared_ptr<DynamicObject> WorldPhysics::createFrame(data_broker::DataBrokerInterface *dataBroker,
+                                                         configmaps::ConfigMap &config)
+{
+    auto frame = std::make_shared<Frame>(this, dataBroker, config);
+    addFrame(frame);
+    return frame;
+}
+
+void WorldPhysics::addFrame(std::shared_ptr<Frame> frame)
+{
+    const std::string &name = frame->getName();
+    if (frameMap.find(name) == frameMap.end() || frameMap[name].expired()) frameMap[name] = frame;
+}
+
+void WorldPhysics::removeFrame(const std::string &name) { frameMap.erase(name); }
+
+std::shared_ptr<Frame> WorldPhysics::getFrameIntern(const std::string &name)
+{
+    const auto it = frameMap.find(name);
+    return it != frameMap.end() ? it->second.lock() : nullptr;
+}
+
+std::shared_ptr<DynamicObject> WorldPhysics::getFrame(const std::string &name) { return getFrameIntern(name); }
+
+// error behaviour of reference :575-603 (schema validation itself is out of scope)
+void WorldPhysics::createObject(configmaps::ConfigMap &config)
+{
+    const std::string type = config["type"].toString();
+    if (!ObjectFactory::Instance().hasObjectType(type)) {
+        const std::string msg = "WorldPhysics::createObject: could not create object " + type + ": missing schema file.";
+        fprintf(stderr, "%s\n", msg.c_str());
+        throw std::runtime_error{msg};
+    }
+    const auto frame = getFrameIntern(config["parentFrame"].toString());
+    if (frame == nullptr) {
+        const std::string msg = "WorldPhysics::createObject: could not create object " + type +
+                                ": missing frame: " + config["parentFrame"].toString() + ".";
+        fprintf(stderr, "%s\n", msg.c_str());
+        throw std::runtime_error{msg};
+    }
+    Object *o = ObjectFactory::Instance().createObject(frame, type, config);
+    if (o) objects.push_back(o);
+}
+
+std::shared_ptr<JointInterface> WorldPhysics::createJoint(data_broker::DataBrokerInterface *dataBroker,
+                                                          configmaps::ConfigMap &config)
+{
+    const std::string name = config["name"].toString();
+    const std::string type = config["type"].toString();
+    if (!JointFactory::Instance().hasJointType(type)) {
+        const std::string msg = "WorldPhysics::createJoint: could not create joint " + type + ": missing schema file.";
+        fprintf(stderr, "%s\n", msg.c_str());
+        throw std::runtime_error{msg};
+    }
+    auto newJoint = JointFactory::Instance().createJoint(this, dataBroker, config);
+    jointMap[name] = newJoint;
+    return newJoint;
+}
+
+void WorldPhysics::destroyJoint(const std::string &jointName) { jointMap.erase(jointName); }
+
+std::shared_ptr<JointInterface> WorldPhysics::getJoint(std::string name)
+{
+    const auto it = jointMap.find(name);
+    return it != jointMap.end() ? it->second.lock() : nullptr;
+}
+
+void WorldPhysics::clearObjects()
+{
+    const MutexLocker locker{&iMutex};
+    for (auto o : objects) delete o;
+    objects.clear();
+}
+
+} // namespace ode_physics
+} // namespace mars

@@ -1,0 +1,54 @@
+"""The reference's own test scene (test/reproducable_test.cpp) driven through the C++ facade
+(WorldPhysics / Frame / Joint with the reference's interfaces) on the GPU, against the oracle's
+restatement of the same scene (oracle/orc_mars.c).
+
+The reference's criterion is determinism of the "%g" CSV (scripts/reproducable_test.sh); on top
+of that the CSV is compared with the oracle's over a short horizon (fp32 device vs fp64 oracle:
+the gait is chaotic, so the comparison horizon is bounded and the tolerance grows with it).
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "mars_ode_physics_b200", "lib", "reproducable_test")
+
+
+def _run(path, t_end, worlds=1):
+    assert os.path.exists(BIN), "facade test binary missing: run __graft_entry__.build()"
+    subprocess.run([BIN, path, str(t_end), str(worlds)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return np.loadtxt(path, delimiter=",", skiprows=1)
+
+
+def test_reproducable_scene_deterministic(cuda_lib, tmp_path):
+    a, b = str(tmp_path / "1.csv"), str(tmp_path / "2.csv")
+    _run(a, 1.0)
+    _run(b, 1.0)
+    assert open(a).read() == open(b).read()  # scripts/reproducable_test.sh: `diff 1.csv i.csv`
+    assert len(open(a).read().splitlines()) == 1001 + 1 or len(open(a).read().splitlines()) == 1000 + 1
+
+
+def test_reproducable_scene_matches_oracle(cuda_lib, orc_lib, tmp_path):
+    gpu = _run(str(tmp_path / "gpu.csv"), 0.5)
+    ocsv = str(tmp_path / "orc.csv")
+    rows = orc_lib.orc_mars_run_reproducable_test(ocsv.encode(), 0.5, orc.ORDER_WORLD_BLOCK, None)
+    ora = np.loadtxt(ocsv, delimiter=",", skiprows=1)
+    assert rows == len(ora) == len(gpu)
+    assert np.array_equal(gpu[:, 0], ora[:, 0])  # identical time column (same double accumulation)
+    err = np.abs(gpu[:, 1:] - ora[:, 1:])
+    print("facade vs oracle: max |dx| over 0.1 s", err[:100].max(), " over 0.5 s", err.max())
+    assert err[:100].max() < 2e-4
+    assert err.max() < 5e-3
+    assert np.abs(ora[-1, 1:]).max() > 1e-3  # the robot actually moved
+
+
+def test_facade_replicas_agree(cuda_lib, tmp_path):
+    """num_worlds > 1 replicates the template: world 0 of a 33-world arena = the one-world run."""
+    one = _run(str(tmp_path / "one.csv"), 0.2, 1)
+    many = _run(str(tmp_path / "many.csv"), 0.2, 33)
+    assert np.array_equal(one, many)
