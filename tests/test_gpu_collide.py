@@ -205,3 +205,28 @@ def test_box_on_heightfield(cuda_lib):
     exact, border = _compare_contacts(ar, oc, W)
     assert exact >= W - 4, (exact, border)
     assert sum(oc.contact_count(w) for w in range(W)) > W // 2
+
+
+def test_rover_against_committed_golden(cuda_lib):
+    """The committed fixture (tests/golden/rover_terrain_oracle_f64.npz, produced by the oracle with
+    tests/golden/make_golden.py) pins contact counts, RNG state and the final state."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rover_terrain_oracle_f64.npz"))
+    W = 4
+    ar = Arena(W)
+    sc = scenes.rover(ar, with_geoms=True)
+    h, x0, y0 = scenes.terrain_heights()
+    ar.geom_create_heightfield(h, 0.1, x0, y0, surface={"mu": 1.0, "mu2": 1.0, "soft_erp": 0.2, "soft_cfm": 1e-5})
+    for w in range(W):
+        for b in sc["bodies"]:
+            p = ar.body_get_position(b, w)
+            ar.body_set_position(b, (p[0] + 0.7 * w, p[1] - 0.4 * w, p[2] + 0.1), w)
+    counts = []
+    for _ in range(200):
+        ar.collide()
+        counts.append([ar.contact_count(w) for w in range(W)])
+        ar.step(0.001)
+    assert np.array_equal(np.array(counts), g["counts"])
+    assert [ar.rand_get_seed(w) for w in range(W)] == list(g["seeds"])
+    err = np.abs(ar.state_download(5).astype(np.float64) - g["state"])
+    assert err[:, :3].max() < 1e-4 and err[:, 3:7].max() < 1e-4, (err[:, :3].max(), err[:, 3:7].max())
