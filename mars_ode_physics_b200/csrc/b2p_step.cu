@@ -28,6 +28,7 @@
 namespace {
 
 constexpr int BD = 64;   // threads (= worlds) per CTA: 8 CTAs/SM at <=128 registers, fine-grained waves
+constexpr int L2_AHEAD = 8; // rows of L2 prefetch distance in the sweep
 constexpr int STAGES = 3; // cp.async ring depth: STAGES-1 rows in flight per thread
 constexpr int ROWV = 4; // float4 per stored row: one 64-byte line per (world,row)
 
@@ -45,17 +46,18 @@ struct Smem {
 
 #define G(arr, field) (arr)[(size_t)(field) * Wp + w]
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Ampere-style asynchronous copies (LDGSTS): completion is tracked per thread by async groups.
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *g)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
 }
 __device__ __forceinline__ void cp_async4(uint32_t smem_addr, const void *g)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(g));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(g) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct BodyPose {
     float pos[3], q[4], R[9];
@@ -170,7 +172,6 @@ __device__ __forceinline__ void emit_row(const StepParams &P, const Smem &S, int
     dst[1 * (size_t)Wp] = q1;
     dst[2 * (size_t)Wp] = q2;
     dst[3 * (size_t)Wp] = q3;
-    G(P.lambda, slot) = 0.f;
     if (bpos >= 0) {
         // independent rows already know their sweep position (ODE: rows with findex < 0 first, in row
         // order), so they go straight into scratch B as well
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevTemplate *__restrict__ T = P.T;
-    const int nb = T->nb, nj = T->nj, maxc = T->maxc, rpc = T->rpc, njslots = T->njslots;
+    const int nb = T->nb, nj = T->nj, maxc = T->maxc, rpc = T->rpc, njslots = T->njslots, maxrows_c = T->maxrows;
     Smem S;
     {
         unsigned char *p = smem_raw;
@@ -928,16 +929,45 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
     uint32_t seed = G(P.seed, 0);
     float4 *const Bq = P.rowsB + w;  // B[pos][v][world]
     float *const Lq = P.lambdaB + w; // lambda by sweep position: L[pos][world]
-    // lambda by position -> lambda by slot (scattered 4-byte stores; 3 times per step)
+    // The row order lives in global memory ([pos][world] bytes) and is mirrored into the (idle) ring
+    // buffer of shared memory while it is being shuffled / used for permuting: the Fisher-Yates swaps
+    // are dependent random accesses, far too slow against global memory.
+    // The mirror must stay inside THIS thread's ring slots (float4 index (j*BD + tid), j < STAGES*ROWV):
+    // warps of a CTA are in different phases, so a [pos][BD] byte layout would let one warp's order
+    // bytes land in the ring slots another warp is streaming rows through.
+    uint8_t *const sbase = reinterpret_cast<uint8_t *>(S.ring + tid);
+    auto sord = [&](int pos) -> uint8_t & { return sbase[(size_t)(pos >> 4) * BD * 16 + (pos & 15)]; };
+    const bool ord_fits = maxrows_c <= STAGES * ROWV * 16;
+    auto ord_load = [&]() {
+        if (ord_fits)
+            for (int pos = 0; pos < m; pos++) sord(pos) = G(P.ord, pos);
+    };
+    auto ord_at = [&](int pos) -> int { return ord_fits ? (int)sord(pos) : (int)G(P.ord, pos); };
+    auto ord_swap = [&](int a, int b) {
+        if (ord_fits) {
+            const uint8_t x = sord(a), y = sord(b);
+            sord(a) = y;
+            sord(b) = x;
+        } else {
+            const uint8_t x = G(P.ord, a), y = G(P.ord, b);
+            G(P.ord, a) = y;
+            G(P.ord, b) = x;
+        }
+    };
+    auto ord_store = [&]() {
+        if (ord_fits)
+            for (int pos = 0; pos < m; pos++) G(P.ord, pos) = sord(pos);
+    };
+    // lambda by position -> the row's slot in scratch A (scattered 4-byte stores; 3 times per step)
     auto writeback_lambda = [&]() {
-        for (int pos = 0; pos < m; pos++) G(P.lambda, G(P.ord, pos)) = Lq[(size_t)pos * Wp];
+        for (int pos = 0; pos < m; pos++)
+            reinterpret_cast<float *>(P.rows + (size_t)(ord_at(pos) * ROWV + 3) * Wp + w)[1] = Lq[(size_t)pos * Wp];
     };
     // A (slot-major) -> B (position-major) for positions [start, m): reads are scattered by the per-lane
     // slot index (32 lines per warp load), which is why this is done per reshuffle and not per sweep.
-    // (Keeping four rows in flight per thread did not help: the pass is L1TEX-wavefront bound.)
     auto permute_rows = [&](int start) {
         for (int pos = start; pos < m; pos++) {
-            const int i = G(P.ord, pos);
+            const int i = ord_at(pos);
             const float4 *src = P.rows + (size_t)(i * ROWV) * Wp + w;
             const float4 q0 = src[0], q1 = src[(size_t)Wp], q2 = src[2 * (size_t)Wp], q3 = src[3 * (size_t)Wp];
             float4 *dst = Bq + (size_t)(pos * ROWV) * Wp;
@@ -945,7 +975,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
             dst[(size_t)Wp] = q1;
             dst[2 * (size_t)Wp] = q2;
             dst[3 * (size_t)Wp] = q3;
-            Lq[(size_t)pos * Wp] = G(P.lambda, i);
+            Lq[(size_t)pos * Wp] = q3.y;
         }
     };
     const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(S.ring + tid);
@@ -953,26 +983,18 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
     for (int it = 0; it < P.iters; it++) {
         const bool reshuffle = P.reorder == 0 && it >= 8 && (it & 7) == 0;
         if (reshuffle) {
+            ord_load();
             writeback_lambda();
             // ODE ConstraintsReorderingHelper on [0,nhead) and [nhead,m)
-            for (int idx = 1; idx < nhead; idx++) {
-                const int sw = rand_int(seed, idx + 1);
-                const uint8_t a = G(P.ord, idx), bq = G(P.ord, sw);
-                G(P.ord, idx) = bq;
-                G(P.ord, sw) = a;
-            }
-            for (int idx = nhead + 1; idx < m; idx++) {
-                const int sw = rand_int(seed, idx - nhead + 1) + nhead;
-                const uint8_t a = G(P.ord, idx), bq = G(P.ord, sw);
-                G(P.ord, idx) = bq;
-                G(P.ord, sw) = a;
-            }
-        }
-        if (it == 0 || reshuffle) {
-            // at iteration 0 the head rows are already in place (written by emit_row)
-            permute_rows(it == 0 ? nhead : 0);
-            if (it == 0)
-                for (int pos = 0; pos < nhead; pos++) Lq[(size_t)pos * Wp] = 0.f;
+            for (int idx = 1; idx < nhead; idx++) ord_swap(idx, rand_int(seed, idx + 1));
+            for (int idx = nhead + 1; idx < m; idx++) ord_swap(idx, rand_int(seed, idx - nhead + 1) + nhead);
+            ord_store();
+            permute_rows(0);
+        } else if (it == 0) {
+            // the head rows are already in place (written by emit_row)
+            ord_load();
+            permute_rows(nhead);
+            for (int pos = 0; pos < nhead; pos++) Lq[(size_t)pos * Wp] = 0.f;
         }
         // Sweep.  Rows stream through a per-thread cp.async ring in shared memory (STAGES-1 rows in
         // flight per thread, tracked by async groups rather than by the six scoreboard slots, which is
@@ -996,6 +1018,18 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
         for (int k = 0; k < m; k++) {
             if (k + STAGES - 1 < m) issue(k + STAGES - 1);
             cp_async_commit();
+            {
+                // pull a row several positions ahead into L2 (wraps into the next sweep)
+                int pp = k + L2_AHEAD;
+                if (pp >= m) pp -= m;
+                if (pp < m) {
+                    const float4 *src = Bq + (size_t)(pp * ROWV) * Wp;
+                    prefetch_l2(src);
+                    prefetch_l2(src + (size_t)Wp);
+                    prefetch_l2(src + 2 * (size_t)Wp);
+                    prefetch_l2(src + 3 * (size_t)Wp);
+                }
+            }
             cp_async_wait<STAGES - 1>();
             const int st = k % STAGES;
             const float4 *rq = S.ring + (size_t)(st * ROWV) * BD + tid;
@@ -1060,6 +1094,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
         }
         cp_async_wait<0>();
     }
+    ord_load();
     writeback_lambda();
     G(P.seed, 0) = seed;
 
@@ -1076,7 +1111,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
             const int slot = jc.slot_base + k;
             const float4 *src = P.rows + (size_t)(slot * ROWV) * Wp + w;
             const float4 j0 = src[0], j1 = src[(size_t)Wp], j2 = src[2 * (size_t)Wp];
-            const float lam = G(P.lambda, slot);
+            const float lam = src[3 * (size_t)Wp].y;
             data[0] += j0.x * lam; data[1] += j0.y * lam; data[2] += j0.z * lam;
             data[3] += j0.w * lam; data[4] += j1.x * lam; data[5] += j1.y * lam;
             data[6] -= j0.x * lam; data[7] -= j0.y * lam; data[8] -= j0.z * lam;
@@ -1097,7 +1132,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
         for (int k = 0; k < mrows; k++) {
             const int slot = njslots + c * rpc + k;
             const float4 j0 = P.rows[(size_t)(slot * ROWV) * Wp + w];
-            const float lam = G(P.lambda, slot);
+            const float lam = P.rows[(size_t)(slot * ROWV + 3) * Wp + w].y;
             f[0] += j0.x * lam;
             f[1] += j0.y * lam;
             f[2] += j0.z * lam;
