@@ -28,7 +28,6 @@
 namespace {
 
 constexpr int BD = 64;   // threads (= worlds) per CTA: 8 CTAs/SM at <=128 registers, fine-grained waves
-constexpr int L2_AHEAD = 8; // rows of L2 prefetch distance in the sweep
 constexpr int STAGES = 3; // cp.async ring depth: STAGES-1 rows in flight per thread
 constexpr int ROWV = 4; // float4 per stored row: one 64-byte line per (world,row)
 
@@ -46,7 +45,6 @@ struct Smem {
 
 #define G(arr, field) (arr)[(size_t)(field) * Wp + w]
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Ampere-style asynchronous copies (LDGSTS): completion is tracked per thread by async groups.
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *g)
 {
@@ -1018,18 +1016,6 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
         for (int k = 0; k < m; k++) {
             if (k + STAGES - 1 < m) issue(k + STAGES - 1);
             cp_async_commit();
-            {
-                // pull a row several positions ahead into L2 (wraps into the next sweep)
-                int pp = k + L2_AHEAD;
-                if (pp >= m) pp -= m;
-                if (pp < m) {
-                    const float4 *src = Bq + (size_t)(pp * ROWV) * Wp;
-                    prefetch_l2(src);
-                    prefetch_l2(src + (size_t)Wp);
-                    prefetch_l2(src + 2 * (size_t)Wp);
-                    prefetch_l2(src + 3 * (size_t)Wp);
-                }
-            }
             cp_async_wait<STAGES - 1>();
             const int st = k % STAGES;
             const float4 *rq = S.ring + (size_t)(st * ROWV) * BD + tid;
