@@ -283,6 +283,178 @@ __device__ __forceinline__ int collide_sphere_box(const float *c, float r, const
     return 1;
 }
 
+
+// ---- box (g1 = A) vs box (g2 = B): separating-axis test over the 15 axes, then either one edge-edge
+// contact or a reference-face / incident-face clip, keeping the <= 4 deepest clipped points in vertex
+// order.  Mirrors collide_box_box of oracle/orc_collide.c step by step (same tie-breaking).
+__device__ __forceinline__ int clip_polygon(const float (*in)[3], int n, const float *pn, float pd, float (*out)[3])
+{
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const float *a = in[i], *b = in[(i + 1) % n];
+        const float da = dot3(pn, a) - pd, db = dot3(pn, b) - pd;
+        if (da <= 0.f) {
+            if (m < 8) {
+                out[m][0] = a[0], out[m][1] = a[1], out[m][2] = a[2];
+                m++;
+            }
+        }
+        if ((da < 0.f && db > 0.f) || (da > 0.f && db < 0.f)) {
+            const float t = da / (da - db);
+            if (m < 8) {
+                out[m][0] = a[0] + t * (b[0] - a[0]);
+                out[m][1] = a[1] + t * (b[1] - a[1]);
+                out[m][2] = a[2] + t * (b[2] - a[2]);
+                m++;
+            }
+        }
+    }
+    return m;
+}
+
+__device__ __noinline__ int collide_box_box(const DevGeom &ga, const GPose &oa, const DevGeom &gb, const GPose &ob,
+                                            CPoint *out)
+{
+    const float a[3] = {0.5f * ga.dims[0], 0.5f * ga.dims[1], 0.5f * ga.dims[2]};
+    const float b[3] = {0.5f * gb.dims[0], 0.5f * gb.dims[1], 0.5f * gb.dims[2]};
+    const float d[3] = {ob.p[0] - oa.p[0], ob.p[1] - oa.p[1], ob.p[2] - oa.p[2]};
+    float A[3][3], B[3][3], Q[3][3], pp[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        A[k][0] = oa.R[k], A[k][1] = oa.R[3 + k], A[k][2] = oa.R[6 + k];
+        B[k][0] = ob.R[k], B[k][1] = ob.R[3 + k], B[k][2] = ob.R[6 + k];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        pp[i] = dot3(A[i], d);
+#pragma unroll
+        for (int j = 0; j < 3; j++) Q[i][j] = fabsf(dot3(A[i], B[j])) + 1e-5f;
+    }
+    float best = -1e30f, nrm[3] = {0.f, 0.f, 0.f};
+    int code = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const float s = fabsf(pp[i]) - (a[i] + b[0] * Q[i][0] + b[1] * Q[i][1] + b[2] * Q[i][2]);
+        if (s > 0.f) return 0;
+        if (s > best) {
+            best = s;
+            code = 1 + i;
+            nrm[0] = A[i][0], nrm[1] = A[i][1], nrm[2] = A[i][2];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const float s = fabsf(dot3(B[j], d)) - (a[0] * Q[0][j] + a[1] * Q[1][j] + a[2] * Q[2][j] + b[j]);
+        if (s > 0.f) return 0;
+        if (s > best) {
+            best = s;
+            code = 4 + j;
+            nrm[0] = B[j][0], nrm[1] = B[j][1], nrm[2] = B[j][2];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            float n[3];
+            cross3(n, A[i], B[j]);
+            const float l2 = dot3(n, n);
+            if (l2 < 1e-10f) continue;
+            const float l = sqrtf(l2);
+            float ra = 0.f, rb = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                ra += a[k] * fabsf(dot3(A[k], n));
+                rb += b[k] * fabsf(dot3(B[k], n));
+            }
+            const float s = (fabsf(dot3(d, n)) - (ra + rb)) / l;
+            if (s > 0.f) return 0;
+            if (s * 1.05f > best) {
+                best = s;
+                code = 7 + 3 * i + j;
+                nrm[0] = n[0] / l, nrm[1] = n[1] / l, nrm[2] = n[2] / l;
+            }
+        }
+    if (!code) return 0;
+    if (dot3(nrm, d) < 0.f) nrm[0] = -nrm[0], nrm[1] = -nrm[1], nrm[2] = -nrm[2];
+
+    if (code >= 7) {
+        const int i = (code - 7) / 3, j = (code - 7) % 3;
+        float pa[3] = {oa.p[0], oa.p[1], oa.p[2]}, pb[3] = {ob.p[0], ob.p[1], ob.p[2]};
+        for (int k = 0; k < 3; k++) {
+            if (k != i) {
+                const float sg = dot3(nrm, A[k]) > 0.f ? 1.f : -1.f;
+                for (int c = 0; c < 3; c++) pa[c] += sg * a[k] * A[k][c];
+            }
+            if (k != j) {
+                const float sg = dot3(nrm, B[k]) > 0.f ? -1.f : 1.f;
+                for (int c = 0; c < 3; c++) pb[c] += sg * b[k] * B[k][c];
+            }
+        }
+        const float p[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+        const float uaub = dot3(A[i], B[j]), q1 = dot3(A[i], p), q2 = -dot3(B[j], p), dd = 1.f - uaub * uaub;
+        float alpha = 0.f, beta = 0.f;
+        if (dd > 1e-4f) {
+            alpha = (q1 + uaub * q2) / dd;
+            beta = (uaub * q1 + q2) / dd;
+        }
+        for (int c = 0; c < 3; c++) {
+            out[0].pos[c] = 0.5f * (pa[c] + alpha * A[i][c] + pb[c] + beta * B[j][c]);
+            out[0].n[c] = -nrm[c];
+        }
+        out[0].depth = -best;
+        return 1;
+    }
+
+    const bool ref_is_a = code <= 3;
+    const float(*Rr)[3] = ref_is_a ? A : B;
+    const float(*Ri)[3] = ref_is_a ? B : A;
+    const float *pr = ref_is_a ? oa.p : ob.p, *pi = ref_is_a ? ob.p : oa.p;
+    const float *hr = ref_is_a ? a : b, *hi = ref_is_a ? b : a;
+    const int ra = ref_is_a ? code - 1 : code - 4;
+    const float nref[3] = {ref_is_a ? nrm[0] : -nrm[0], ref_is_a ? nrm[1] : -nrm[1], ref_is_a ? nrm[2] : -nrm[2]};
+    int ia = 0;
+    float bestd = -1.f;
+    for (int k = 0; k < 3; k++) {
+        const float v = fabsf(dot3(Ri[k], nref));
+        if (v > bestd) {
+            bestd = v;
+            ia = k;
+        }
+    }
+    const float isg = dot3(Ri[ia], nref) > 0.f ? -1.f : 1.f;
+    const int i1 = (ia + 1) % 3, i2 = (ia + 2) % 3;
+    float poly[8][3], tmp[8][3];
+    for (int v = 0; v < 4; v++) {
+        const float su = (v == 0 || v == 3) ? 1.f : -1.f, sv = v < 2 ? 1.f : -1.f;
+        for (int c = 0; c < 3; c++)
+            poly[v][c] = pi[c] + isg * hi[ia] * Ri[ia][c] + su * hi[i1] * Ri[i1][c] + sv * hi[i2] * Ri[i2][c];
+    }
+    int n = 4;
+    const int r1 = (ra + 1) % 3, r2 = (ra + 2) % 3;
+    for (int e = 0; e < 4 && n > 0; e++) {
+        const int ax = e < 2 ? r1 : r2;
+        const float sg = (e & 1) ? -1.f : 1.f;
+        const float pn[3] = {sg * Rr[ax][0], sg * Rr[ax][1], sg * Rr[ax][2]};
+        const float pd = dot3(pn, pr) + hr[ax];
+        n = clip_polygon(poly, n, pn, pd, tmp);
+        for (int v = 0; v < n; v++) poly[v][0] = tmp[v][0], poly[v][1] = tmp[v][1], poly[v][2] = tmp[v][2];
+    }
+    CPoint cand[8];
+    const float face_d = dot3(nref, pr) + hr[ra];
+    for (int v = 0; v < 8; v++) {
+        cand[v].depth = -1.f;
+        if (v < n) {
+            cand[v].depth = face_d - dot3(nref, poly[v]);
+            for (int c = 0; c < 3; c++) {
+                cand[v].pos[c] = poly[v][c];
+                cand[v].n[c] = -nrm[c];
+            }
+        }
+    }
+    return keep_deepest<8>(cand, out);
+}
+
 __device__ __forceinline__ float clamp01(float x) { return x < 0.f ? 0.f : (x > 1.f ? 1.f : x); }
 
 __device__ __forceinline__ void closest_seg_seg(const float *p1, const float *d1, const float *p2, const float *d2,
@@ -511,6 +683,7 @@ __device__ __forceinline__ int narrowphase(const CollideParams &P, const DevTemp
         return 0;
     }
     geom_pose(P, g2, w, o2);
+    if (c1 == 1 && c2 == 1) return collide_box_box(g1, o1, g2, o2, out);
     if (c1 == 0 && c2 == 0) return collide_sphere_sphere(o1.p, g1.dims[0], o2.p, g2.dims[0], out[0]);
     if (c1 == 0 && c2 == 1) return collide_sphere_box(o1.p, g1.dims[0], g2, o2, out[0]);
     if (c1 == 1 && c2 == 0) {

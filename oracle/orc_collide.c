@@ -253,6 +253,181 @@ static int collide_sphere_box(const double *c, double r, const orc_geom *gb, con
     return 1;
 }
 
+
+/* ---- box (g1 = A) vs box (g2 = B): separating-axis test over the 15 axes, then either one
+ * edge-edge contact or a reference-face / incident-face clip (Sutherland-Hodgman), keeping the <= 4
+ * deepest clipped points in vertex order.  Same structure as ODE's dBoxBox (box.cpp), own
+ * tie-breaking so that the result is well defined for the device kernel to match. ---- */
+static void col3(const double *R, int k, double *out)
+{
+    out[0] = R[k];
+    out[1] = R[3 + k];
+    out[2] = R[6 + k];
+}
+
+static int clip_polygon(const double (*in)[3], int n, const double *pn, double pd, double (*out)[3])
+{
+    /* keep the part of the polygon with pn.x <= pd */
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const double *a = in[i], *b = in[(i + 1) % n];
+        double da = ddot(pn, a) - pd, db = ddot(pn, b) - pd;
+        if (da <= 0) {
+            if (m < 8) memcpy(out[m++], a, 3 * sizeof(double));
+        }
+        if ((da < 0 && db > 0) || (da > 0 && db < 0)) {
+            double t = da / (da - db);
+            if (m < 8) {
+                for (int k = 0; k < 3; k++) out[m][k] = a[k] + t * (b[k] - a[k]);
+                m++;
+            }
+        }
+    }
+    return m;
+}
+
+static int collide_box_box(const orc_geom *ga, const gpose *oa, const orc_geom *gb, const gpose *ob, cpoint *out)
+{
+    const double a[3] = {0.5 * ga->dims[0], 0.5 * ga->dims[1], 0.5 * ga->dims[2]};
+    const double b[3] = {0.5 * gb->dims[0], 0.5 * gb->dims[1], 0.5 * gb->dims[2]};
+    double d[3] = {ob->p[0] - oa->p[0], ob->p[1] - oa->p[1], ob->p[2] - oa->p[2]};
+    double A[3][3], B[3][3], Rm[3][3], Q[3][3], pp[3];
+    for (int k = 0; k < 3; k++) {
+        col3(oa->R, k, A[k]);
+        col3(ob->R, k, B[k]);
+    }
+    for (int i = 0; i < 3; i++) {
+        pp[i] = ddot(A[i], d);
+        for (int j = 0; j < 3; j++) {
+            Rm[i][j] = ddot(A[i], B[j]);
+            Q[i][j] = fabs(Rm[i][j]) + 1e-5;
+        }
+    }
+    double best = -1e300, nrm[3] = {0, 0, 0};
+    int code = 0;
+    for (int i = 0; i < 3; i++) { /* face normals of A */
+        double s = fabs(pp[i]) - (a[i] + b[0] * Q[i][0] + b[1] * Q[i][1] + b[2] * Q[i][2]);
+        if (s > 0) return 0;
+        if (s > best) {
+            best = s;
+            code = 1 + i;
+            memcpy(nrm, A[i], sizeof(nrm));
+        }
+    }
+    for (int j = 0; j < 3; j++) { /* face normals of B */
+        double s = fabs(ddot(B[j], d)) - (a[0] * Q[0][j] + a[1] * Q[1][j] + a[2] * Q[2][j] + b[j]);
+        if (s > 0) return 0;
+        if (s > best) {
+            best = s;
+            code = 4 + j;
+            memcpy(nrm, B[j], sizeof(nrm));
+        }
+    }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) { /* edge x edge */
+            double n[3];
+            dcross(n, A[i], B[j]);
+            double l2 = ddot(n, n);
+            if (l2 < 1e-10) continue;
+            double l = sqrt(l2), ra = 0, rb = 0;
+            for (int k = 0; k < 3; k++) {
+                ra += a[k] * fabs(ddot(A[k], n));
+                rb += b[k] * fabs(ddot(B[k], n));
+            }
+            double s = (fabs(ddot(d, n)) - (ra + rb)) / l;
+            if (s > 0) return 0;
+            if (s * 1.05 > best) { /* an edge axis must beat the face axes by 5 % (ODE fudge factor) */
+                best = s;
+                code = 7 + 3 * i + j;
+                for (int k = 0; k < 3; k++) nrm[k] = n[k] / l;
+            }
+        }
+    if (!code) return 0;
+    if (ddot(nrm, d) < 0) /* make nrm point from A to B */
+        for (int k = 0; k < 3; k++) nrm[k] = -nrm[k];
+
+    if (code >= 7) {
+        const int i = (code - 7) / 3, j = (code - 7) % 3;
+        double pa[3], pb[3];
+        memcpy(pa, oa->p, sizeof(pa));
+        memcpy(pb, ob->p, sizeof(pb));
+        for (int k = 0; k < 3; k++) {
+            if (k != i) {
+                double sg = ddot(nrm, A[k]) > 0 ? 1.0 : -1.0;
+                for (int c = 0; c < 3; c++) pa[c] += sg * a[k] * A[k][c];
+            }
+            if (k != j) {
+                double sg = ddot(nrm, B[k]) > 0 ? -1.0 : 1.0;
+                for (int c = 0; c < 3; c++) pb[c] += sg * b[k] * B[k][c];
+            }
+        }
+        /* closest approach of the lines pa + alpha*A[i], pb + beta*B[j] */
+        double p[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+        double uaub = ddot(A[i], B[j]), q1 = ddot(A[i], p), q2 = -ddot(B[j], p), dd = 1 - uaub * uaub;
+        double alpha = 0, beta = 0;
+        if (dd > 1e-4) {
+            alpha = (q1 + uaub * q2) / dd;
+            beta = (uaub * q1 + q2) / dd;
+        }
+        for (int c = 0; c < 3; c++) {
+            out[0].pos[c] = 0.5 * (pa[c] + alpha * A[i][c] + pb[c] + beta * B[j][c]);
+            out[0].normal[c] = -nrm[c];
+        }
+        out[0].depth = -best;
+        return 1;
+    }
+
+    /* face contact: reference box has the separating face, the other box provides the incident face */
+    const int ref_is_a = code <= 3;
+    const double(*Rr)[3] = ref_is_a ? A : B, (*Ri)[3] = ref_is_a ? B : A;
+    const double *pr = ref_is_a ? oa->p : ob->p, *pi = ref_is_a ? ob->p : oa->p;
+    const double *hr = ref_is_a ? a : b, *hi = ref_is_a ? b : a;
+    const int ra = ref_is_a ? code - 1 : code - 4;
+    double nref[3]; /* outward normal of the reference face = from the reference box to the other */
+    for (int k = 0; k < 3; k++) nref[k] = ref_is_a ? nrm[k] : -nrm[k];
+    /* incident face: the face of the other box most anti-parallel to nref */
+    int ia = 0;
+    double bestd = -1;
+    for (int k = 0; k < 3; k++) {
+        double v = fabs(ddot(Ri[k], nref));
+        if (v > bestd) {
+            bestd = v;
+            ia = k;
+        }
+    }
+    const double isg = ddot(Ri[ia], nref) > 0 ? -1.0 : 1.0;
+    const int i1 = (ia + 1) % 3, i2 = (ia + 2) % 3;
+    double poly[8][3], tmp[8][3];
+    const double su[4] = {1, -1, -1, 1}, sv[4] = {1, 1, -1, -1};
+    for (int v = 0; v < 4; v++)
+        for (int c = 0; c < 3; c++)
+            poly[v][c] = pi[c] + isg * hi[ia] * Ri[ia][c] + su[v] * hi[i1] * Ri[i1][c] + sv[v] * hi[i2] * Ri[i2][c];
+    int n = 4;
+    const int r1 = (ra + 1) % 3, r2 = (ra + 2) % 3;
+    const int axes[4] = {r1, r1, r2, r2};
+    const double sgn[4] = {1, -1, 1, -1};
+    for (int e = 0; e < 4 && n > 0; e++) {
+        double pn[3];
+        for (int c = 0; c < 3; c++) pn[c] = sgn[e] * Rr[axes[e]][c];
+        double pd = ddot(pn, pr) + hr[axes[e]];
+        n = clip_polygon((const double(*)[3])poly, n, pn, pd, tmp);
+        memcpy(poly, tmp, sizeof(poly));
+    }
+    cpoint cand[8];
+    const double face_d = ddot(nref, pr) + hr[ra];
+    for (int v = 0; v < 8; v++) {
+        cand[v].depth = -1;
+        if (v < n) {
+            cand[v].depth = face_d - ddot(nref, poly[v]);
+            memcpy(cand[v].pos, poly[v], 3 * sizeof(double));
+            for (int c = 0; c < 3; c++) cand[v].normal[c] = -nrm[c];
+        }
+    }
+    int nout = 0;
+    keep_deepest(cand, 8, out, &nout);
+    return nout;
+}
+
 /* closest points of two segments p1+s*d1, p2+t*d2, s,t in [0,1] (Ericson, RTCD 5.1.9) */
 static void closest_seg_seg(const double *p1, const double *d1, const double *p2, const double *d2, double *c1, double *c2)
 {
@@ -477,6 +652,7 @@ static int narrowphase(const orc_world *w, const orc_geom *g1, const orc_geom *g
         if (c1 == 1) return collide_box_hf(w, g1, &o1, out);
         return 0;
     }
+    if (c1 == 1 && c2 == 1) return collide_box_box(g1, &o1, g2, &o2, out);
     if (c1 == 0 && c2 == 0) return collide_sphere_sphere(o1.p, g1->dims[0], o2.p, g2->dims[0], out);
     if (c1 == 0 && c2 == 1) return collide_sphere_box(o1.p, g1->dims[0], g2, &o2, out);
     if (c1 == 1 && c2 == 0) {

@@ -230,3 +230,85 @@ def test_rover_against_committed_golden(cuda_lib):
     assert [ar.rand_get_seed(w) for w in range(W)] == list(g["seeds"])
     err = np.abs(ar.state_download(5).astype(np.float64) - g["state"])
     assert err[:, :3].max() < 1e-4 and err[:, 3:7].max() < 1e-4, (err[:, :3].max(), err[:, 3:7].max())
+
+
+def test_box_box_random_poses(cuda_lib):
+    """Box-box collider (SAT + face clipping / edge-edge) on random overlapping poses."""
+    W = 256
+    rng = np.random.default_rng(2024)
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    for be in (ar, oc):
+        _build_pair_scene(be, capi.GEOM_BOX, (0.3, 0.2, 0.25), capi.GEOM_BOX, (0.2, 0.35, 0.15))
+    for w in range(W):
+        pa, pb = rng.uniform(-0.12, 0.12, size=3), rng.uniform(-0.12, 0.12, size=3)
+        qa, qb = _rand_quat(rng), _rand_quat(rng)
+        if w % 4 == 0:  # face-to-face stacking poses (the config-B case)
+            qa = qb = np.array([1.0, 0, 0, 0])
+            pa, pb = np.array([0.0, 0.0, 0.0]), np.array([rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05), 0.19])
+            if w % 8 == 0:
+                qb = scenes.quat_axis_angle((0, 0, 1), rng.uniform(-0.5, 0.5))
+        for be in (ar, oc):
+            be.body_set_position(0, pa, w)
+            be.body_set_quaternion(0, qa, w)
+            be.body_set_position(1, pb, w)
+            be.body_set_quaternion(1, qb, w)
+    ar.collide()
+    oc.collide()
+    for w in range(W):
+        assert ar.collide_get_pairs(w) == oc.collide_get_pairs(w)
+    exact, border = _compare_contacts(ar, oc, W, borderline=5e-5)
+    print("box-box: exact worlds", exact, "borderline", border)
+    assert exact >= W - 12, (exact, border)
+    total = sum(oc.contact_count(w) for w in range(W))
+    multi = sum(1 for w in range(W) if oc.contact_count(w) >= 3)
+    assert total > W and multi > W // 8  # face contacts with several points occurred
+
+
+def test_box_stack_config_b(cuda_lib):
+    """Config B: 10-box stack on a plane with per-world jitter, device collide + step vs oracle."""
+    W = 32
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    for be in (ar, oc):
+        sc = scenes.box_stack(be, n=10)
+        scenes.jitter_box_stack(be, sc, W)
+    nb = 10
+    checked = borderline = pair_mismatch = 0
+    worst = 0.0
+    for step in range(125):
+        if step % 10 == 5:
+            # (step 0 is skipped: box 0 starts exactly touching the plane, AABB gap == 0)
+            # integer checks on IDENTICAL inputs: free-running fp32 / fp64 trajectories differ at the
+            # 1e-7 level, which flips AABB pairs that are exactly touching (the boxes land on each other
+            # at the same instant); so measure the drift, then give both sides the same rounded state
+            so = oc.state_download(nb)
+            worst = max(worst, np.abs(ar.state_download(nb).astype(np.float64) - so)[:, :7].max())
+            st32 = so.astype(np.float32)
+            ar.state_upload(st32)
+            for w in range(W):
+                for b in range(nb):
+                    oc.body_set_state(b, st32[b, :, w].astype(np.float64), w)
+        ar.collide()
+        oc.collide()
+        if step % 10 == 5:
+            for w in range(W):
+                pa, po = ar.collide_get_pairs(w), oc.collide_get_pairs(w)
+                pair_mismatch += len(set(pa) ^ set(po))
+                checked += 1
+                if ar.contact_count(w) != oc.contact_count(w):
+                    borderline += 1
+        ar.step(0.001)
+        oc.step(0.001)
+    assert pair_mismatch == 0, pair_mismatch
+    print("box stack: max pose drift over 10 free-running steps", worst)
+    # a resting face contact is a discontinuous function of the state (a vertex at depth 0 is in or out
+    # of the manifold), so contact-count flips perturb the stack; bound the drift, do not expect 1e-6
+    assert worst < 1e-2
+    err = np.abs(ar.state_download(nb).astype(np.float64) - oc.state_download(nb))
+    print("box stack 120 steps: pos err", err[:, :3].max(), "quat", err[:, 3:7].max(), "count mismatches",
+          borderline, "of", checked)
+    # resting face contacts have depth ~ 0, so a few candidate points flip between fp32 and fp64;
+    # the stack itself must still agree closely
+    assert borderline <= checked // 4
+    assert err[:, :3].max() < 2e-3 and err[:, 3:7].max() < 5e-3
+    z = oc.state_download(nb)[:, 2, :]
+    assert np.all(np.diff(z, axis=0) > 0.15)  # still a stack
