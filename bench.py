@@ -71,6 +71,53 @@ def build_rover_worlds(be, num_worlds, world_offset=0, torch_free=True):
     return sc
 
 
+def build_box_stack_worlds(be, num_worlds, world_offset=0):
+    """Config B: 10-box stack on a plane, per-world jitter from splitmix64(0xB200 ^ id)."""
+    from mars_ode_physics_b200 import scenes
+    sc = scenes.box_stack(be, n=10, max_contacts=48)
+    nb = len(sc["bodies"])
+    st = np.array(be.state_download(nb))
+    n = world_offset + num_worlds
+    for i in range(nb):
+        x = -0.01 + 0.02 * scenes.uniform01_array(0xB200, n, 3 * i + 0)[world_offset:]
+        y = -0.01 + 0.02 * scenes.uniform01_array(0xB200, n, 3 * i + 1)[world_offset:]
+        yaw = -0.1 + 0.2 * scenes.uniform01_array(0xB200, n, 3 * i + 2)[world_offset:]
+        st[i, 0, :] = x
+        st[i, 1, :] = y
+        st[i, 3, :] = np.cos(0.5 * yaw)
+        st[i, 6, :] = np.sin(0.5 * yaw)
+    be.state_upload(st) if hasattr(be, "state_upload") else [
+        be.body_set_state(b, st[b, :, w], w) for w in range(num_worlds) for b in range(nb)]
+    sc["vel"] = None
+    sc["chassis"] = sc["bodies"][-1]
+    return sc
+
+
+def build_quadruped_worlds(be, num_worlds, world_offset=0):
+    """Config C: 12-hinge legged robot, foot spheres on a plane, constant per-world joint speeds."""
+    from mars_ode_physics_b200 import capi, scenes
+    sc = scenes.quadruped(be, max_contacts=8)
+    s = {"mu": 0.8, "mu2": 0.8, "soft_erp": 0.2, "soft_cfm": 1e-5}
+    be.geom_create(capi.GEOM_PLANE, -1, (0, 0, 1, 0), surface=s)
+    for f in sc["feet"]:
+        be.geom_create(capi.GEOM_SPHERE, f, (sc["foot_radius"],), surface=s)
+    be.geom_create(capi.GEOM_BOX, sc["torso"], (0.4, 0.2, 0.05), surface=s)
+    n = world_offset + num_worlds
+    vel = (-0.5 + scenes.uniform01_array(0xC, n, 1)[world_offset:]).astype(np.float32)
+    for j in sc["hip"] + sc["knee"]:
+        be.joint_set_param_batch(j, capi.PARAM_VEL, vel)
+    sc["vel"] = vel
+    sc["chassis"] = sc["torso"]
+    return sc
+
+
+BUILDERS = {"D": None, "B": build_box_stack_worlds, "C": build_quadruped_worlds}
+WORKLOADS = {
+    "B": "B: 10-box stack on a plane (box-box + box-plane contacts), dt=1ms, 20 SOR iters",
+    "C": "C: 12-hinge legged robot (13 bodies), foot spheres on a plane, dt=1ms, 20 SOR iters",
+}
+
+
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -188,8 +235,12 @@ def run_b200(args):
     ar = Arena(W, device=local_rank)
     stream = torch.cuda.current_stream()
     ar.set_stream(stream.cuda_stream)
-    sc = build_rover_worlds(ar, W, world_offset=rank * W)
+    if args.workload == "D":
+        sc = build_rover_worlds(ar, W, world_offset=rank * W)
+    else:
+        sc = BUILDERS[args.workload](ar, W, world_offset=rank * W)
     nb, nj = len(sc["bodies"]), len(sc["joints"])
+    cmd_joints = sc["joints"] if sc["vel"] is not None else []
 
     def barrier():
         if world_size > 1:
@@ -228,12 +279,12 @@ def run_b200(args):
     step_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
 
     # ---------------- end-to-end loop through the C ABI with host buffers ----------------
-    cmd = torch.empty((nj, W), dtype=torch.float32).pin_memory()
-    cmd[:] = torch.from_numpy(sc["vel"])[None, :]
+    cmd = torch.empty((max(nj, 1), W), dtype=torch.float32).pin_memory()
+    cmd[:] = torch.from_numpy(sc["vel"])[None, :] if sc["vel"] is not None else 0.0
     obs = torch.empty((13, W), dtype=torch.float32).pin_memory()
-    param = capi.PARAM_VEL | capi.PARAM_GROUP2
+    param = (capi.PARAM_VEL | capi.PARAM_GROUP2) if args.workload == "D" else capi.PARAM_VEL
     for _ in range(3):
-        for ji, j in enumerate(sc["joints"]):
+        for ji, j in enumerate(cmd_joints):
             ar.joint_set_param_batch_ptr(j, param, cmd[ji].data_ptr())
         ar.collide()
         ar.step(H)
@@ -244,7 +295,7 @@ def run_b200(args):
     e0.record(stream)
     for k in range(K):
         cmd.add_(0.001)  # new commands every step (host side)
-        for ji, j in enumerate(sc["joints"]):
+        for ji, j in enumerate(cmd_joints):
             ar.joint_set_param_batch_ptr(j, param, cmd[ji].data_ptr())
         ar.collide()
         ar.step(H)
@@ -286,13 +337,14 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "worlds_per_gpu": W, "total_worlds": total_worlds,
+            "config": {"workload": WORKLOAD if args.workload == "D" else WORKLOADS[args.workload],
+                       "worlds_per_gpu": W, "total_worlds": total_worlds,
                        "sharding": f"worlds/{world_size} GPUs, no collective on the step path",
                        "l2": "per-step working set (row scratch) > L2; no flush needed",
                        "settle_steps": SETTLE_STEPS,
                        "mean_rows_per_world": float(np.mean([ar.last_num_rows(w) for w in range(0, W, max(1, W // 64))])),
                        "kernel_ms": {"collide": collide_ms, "step": step_ms}},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nj * W * 4),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(len(cmd_joints) * W * 4),
                     "d2h_bytes_per_step": int(13 * W * 4), "ms_per_step": ms_e2e / K},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -302,7 +354,7 @@ def run_b200(args):
             "clocks": sampler.summary(),
             "wall_s": t_wall,
         }
-        if not args.no_cpu_baseline and world_size == 1:
+        if not args.no_cpu_baseline and world_size == 1 and args.workload == "D":
             cores = os.cpu_count() or 1
             sample = 128 * cores  # enough worlds that ~12 s of CPU work stays within a few thousand steps
             v, nsteps, dt = CpuBaseline(sample, cores).run_for(12.0)
@@ -323,6 +375,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--worlds", type=int, default=WORLDS_PER_GPU, help="worlds per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="D", choices=["B", "C", "D"],
+                    help="D (default) is the headline configuration; B and C are extra data points")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
