@@ -239,6 +239,10 @@ def run_b200(args):
         sc = build_rover_worlds(ar, W, world_offset=rank * W)
     else:
         sc = BUILDERS[args.workload](ar, W, world_offset=rank * W)
+    if args.wpl:
+        ar.set_worlds_per_launch(args.wpl)
+    if args.reorder == "none":
+        ar.set_reorder_method(capi.REORDER_NONE)
     nb, nj = len(sc["bodies"]), len(sc["joints"])
     cmd_joints = sc["joints"] if sc["vel"] is not None else []
 
@@ -341,7 +345,7 @@ def run_b200(args):
                        "worlds_per_gpu": W, "total_worlds": total_worlds,
                        "sharding": f"worlds/{world_size} GPUs, no collective on the step path",
                        "l2": "per-step working set (row scratch) > L2; no flush needed",
-                       "settle_steps": SETTLE_STEPS,
+                       "settle_steps": SETTLE_STEPS, "row_reordering": args.reorder,
                        "mean_rows_per_world": float(np.mean([ar.last_num_rows(w) for w in range(0, W, max(1, W // 64))])),
                        "kernel_ms": {"collide": collide_ms, "step": step_ms}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(len(cmd_joints) * W * 4),
@@ -375,6 +379,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--worlds", type=int, default=WORLDS_PER_GPU, help="worlds per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wpl", type=int, default=0, help="tuning: worlds per step sub-launch (0 = all)")
+    ap.add_argument("--reorder", default="random", choices=["random", "none"],
+                    help="SOR row reordering: ODE 0.16 default (random) or REORDERING_METHOD__DONT_REORDER")
     ap.add_argument("--workload", default="D", choices=["B", "C", "D"],
                     help="D (default) is the headline configuration; B and C are extra data points")
     args = ap.parse_args()

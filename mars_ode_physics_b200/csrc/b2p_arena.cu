@@ -219,6 +219,8 @@ struct b2p_arena {
     int *d_pairs = nullptr, *d_npairs = nullptr;
     int maxpairs = 0;
     int launches = 0;
+    int worlds_per_launch = 0; // 0 = all worlds in one launch
+    long long *d_phase = nullptr;
     bool stepped = false;
 };
 
@@ -690,6 +692,7 @@ void b2p_arena_destroy(b2p_arena *a)
     if (a->d_hf) cudaFree(a->d_hf);
     if (a->d_pairs) cudaFree(a->d_pairs);
     if (a->d_npairs) cudaFree(a->d_npairs);
+    if (a->d_phase) cudaFree(a->d_phase);
     delete a;
 }
 
@@ -1721,10 +1724,21 @@ int b2p_step(b2p_arena *a, double step_size)
     P.ccount = a->ccount.dev;
     P.nrows = a->nrows.dev;
     P.seed = a->seed.dev;
+    P.phase_cycles = a->d_phase;
     const size_t smem = b2p_step_smem_bytes((int)a->bodies.size(), (int)a->joints.size(), a->maxc, rpc_of(a));
     if (smem > 227 * 1024) return fail(B2P_ECAPACITY, "scene needs %zu bytes of shared memory per CTA", smem);
-    CUDA_TRY(b2p_launch_step(&P, (int)a->bodies.size(), (int)a->joints.size(), a->maxc, rpc_of(a), a->stream));
-    a->launches++;
+    // optional sub-launches over world ranges: fewer concurrent worlds keep the row scratch L2-resident
+    // and leave shared memory for a deeper cp.async ring
+    const int wpl = a->worlds_per_launch > 0 ? ((a->worlds_per_launch + 31) & ~31) : a->W;
+    for (int w0 = 0; w0 < a->W; w0 += wpl) {
+        StepParams Q = P;
+        Q.W = std::min(wpl, a->W - w0);
+        Q.state += w0, Q.force += w0, Q.jcmd += w0, Q.jobs += w0, Q.jfb += w0, Q.crec += w0, Q.cfb += w0;
+        Q.lambda += w0, Q.invIw += w0, Q.rows += w0, Q.rowsB += w0, Q.lambdaB += w0, Q.ord += w0;
+        Q.jrows += w0, Q.ccount += w0, Q.nrows += w0, Q.seed += w0;
+        CUDA_TRY(b2p_launch_step(&Q, (int)a->bodies.size(), (int)a->joints.size(), a->maxc, rpc_of(a), a->stream));
+        a->launches++;
+    }
     a->stepped = true;
     a->state.dev_newer = true;
     a->jobs.dev_newer = a->jfb.dev_newer = a->cfb.dev_newer = true;
@@ -1756,6 +1770,37 @@ int b2p_world_last_num_rows(b2p_arena *a, int world, int *rows)
 }
 
 int b2p_kernel_launch_count(const b2p_arena *a) { return a ? a->launches : 0; }
+
+int b2p_arena_set_worlds_per_launch(b2p_arena *a, int n)
+{
+    if (!a || n < 0) return fail(B2P_EINVAL, "bad worlds_per_launch");
+    a->worlds_per_launch = n;
+    return 0;
+}
+
+// diagnostics: enable (and reset) per-phase cycle counters of the step kernel; read them back as
+// out[0..4] = mean cycles per warp of {assembly, reshuffle+permute, sweeps, write-back, epilogue},
+// out[5] = number of warp-steps accumulated
+int b2p_debug_phase_cycles(b2p_arena *a, int enable, double out[6])
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    CUDA_TRY(cudaSetDevice(a->device));
+    if (a->d_phase && out) {
+        long long h[6];
+        CUDA_TRY(cudaStreamSynchronize(a->stream));
+        CUDA_TRY(cudaMemcpy(h, a->d_phase, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 5; i++) out[i] = h[5] ? (double)h[i] / (double)h[5] : 0.0;
+        out[5] = (double)h[5];
+    }
+    if (enable) {
+        if (!a->d_phase) CUDA_TRY(cudaMalloc(&a->d_phase, 6 * sizeof(long long)));
+        CUDA_TRY(cudaMemset(a->d_phase, 0, 6 * sizeof(long long)));
+    } else if (a->d_phase) {
+        cudaFree(a->d_phase);
+        a->d_phase = nullptr;
+    }
+    return 0;
+}
 
 // body 212 B, hinge 160 B, fixed 88 B, slider 132 B, hinge2 212 B,
 // contact 76 B (+128 B when the record was produced on the device), geom 48 B.

@@ -105,6 +105,7 @@ struct StepParams {
     int *ccount;
     int *nrows;
     uint32_t *seed;
+    long long *phase_cycles; // optional diagnostics: summed clock64 cycles per phase (6 slots), or null
 };
 
 struct CollideParams {

@@ -28,7 +28,8 @@
 namespace {
 
 constexpr int BD = 64;   // threads (= worlds) per CTA: 8 CTAs/SM at <=128 registers, fine-grained waves
-constexpr int STAGES = 3; // cp.async ring depth: STAGES-1 rows in flight per thread
+// The cp.async ring depth (STAGES-1 rows in flight per thread) is a template parameter: the launcher
+// picks the deepest ring whose shared memory still lets all worlds of the launch be resident at once.
 constexpr int ROWV = 4; // float4 per stored row: one 64-byte line per (world,row)
 
 struct Smem {
@@ -358,7 +359,7 @@ __device__ __forceinline__ void fixed_orientation_rhs(const DevJoint &jc, const 
     for (int i = 0; i < 3; i++) c3[i] = k2 * e[i];
 }
 
-__global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
+template <int STAGES> __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevTemplate *__restrict__ T = P.T;
@@ -392,6 +393,9 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
     const int Wp = P.Wp;
     const float h = P.h, hinv = 1.0f / P.h;
 
+    long long t_ph[5] = {0, 0, 0, 0, 0};
+    long long t_mark = clock64();
+#define PH_MARK(i) do { const long long t_now = clock64(); t_ph[i] += t_now - t_mark; t_mark = t_now; } while (0)
     // ---------------- phase 1: bodies ----------------
     for (int b = 0; b < nb; b++) {
         const DevBody &bc = T->bodies[b];
@@ -916,6 +920,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
     for (int k = 0; k < nb * 6; k++) S.fc[(size_t)k * BD + tid] = 0.f;
     for (int k = 0; k < maxc; k++) S.lamn[(size_t)k * BD + tid] = 0.f;
 
+    PH_MARK(0);
     // ---------------- phase 3: SOR-LCP sweep ----------------
     // Each world follows its own row order (per-world contact count and RNG state).  Reading rows
     // through a per-lane index would make every warp load touch 32 different lines, and L1TEX then
@@ -980,6 +985,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
     const uint32_t lring_s = (uint32_t)__cvta_generic_to_shared(S.lring + tid);
     for (int it = 0; it < P.iters; it++) {
         const bool reshuffle = P.reorder == 0 && it >= 8 && (it & 7) == 0;
+        PH_MARK(2);
         if (reshuffle) {
             ord_load();
             writeback_lambda();
@@ -994,6 +1000,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
             permute_rows(nhead);
             for (int pos = 0; pos < nhead; pos++) Lq[(size_t)pos * Wp] = 0.f;
         }
+        PH_MARK(1);
         // Sweep.  Rows stream through a per-thread cp.async ring in shared memory (STAGES-1 rows in
         // flight per thread, tracked by async groups rather than by the six scoreboard slots, which is
         // what limited register prefetching: profiles/r1_v6_*).  Row loads do not depend on the
@@ -1080,9 +1087,11 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
         }
         cp_async_wait<0>();
     }
+    PH_MARK(2);
     ord_load();
     writeback_lambda();
     G(P.seed, 0) = seed;
+    PH_MARK(3);
 
     // ---------------- phase 4a: joint / contact feedback from the unscaled Jacobian ------------
     for (int j = 0; j < nj; j++) {
@@ -1232,14 +1241,18 @@ __global__ void __launch_bounds__(BD, 8) b2p_step_kernel(const StepParams P)
         G(P.jobs, j * 4 + 2) = a2;
         G(P.jobs, j * 4 + 3) = r2;
     }
+    PH_MARK(4);
+    if (P.phase_cycles && (tid & 31) == 0) {
+        for (int i = 0; i < 5; i++) atomicAdd((unsigned long long *)&P.phase_cycles[i], (unsigned long long)t_ph[i]);
+        atomicAdd((unsigned long long *)&P.phase_cycles[5], 1ull);
+    }
 }
 
 } // namespace
 
-static size_t smem_base_bytes(int nb, int nj, int maxc, int rpc)
+static size_t smem_bytes_for(int nb, int nj, int maxc, int stages)
 {
-    (void)rpc;
-    size_t s = sizeof(float4) * (size_t)STAGES * ROWV * BD + sizeof(float) * (size_t)STAGES * BD;
+    size_t s = sizeof(float4) * (size_t)stages * ROWV * BD + sizeof(float) * (size_t)stages * BD;
     s += sizeof(float) * (size_t)nb * 12 * BD;
     s += sizeof(float) * (size_t)maxc * BD;
     s += sizeof(float) * (size_t)nb;
@@ -1248,20 +1261,53 @@ static size_t smem_base_bytes(int nb, int nj, int maxc, int rpc)
     return (s + 15) & ~(size_t)15;
 }
 
-extern "C" size_t b2p_step_smem_bytes(int nb, int nj, int maxc, int rpc) { return smem_base_bytes(nb, nj, maxc, rpc); }
+static const int kStageChoices[] = {12, 8, 6, 4, 3, 2};
+
+// deepest ring such that ceil(worlds / (64 * 148)) CTAs fit on an SM (all worlds resident: one wave)
+static int pick_stages(int nb, int nj, int maxc, int worlds)
+{
+    const int num_sms = 148;
+    int ctas_per_sm = (worlds + BD * num_sms - 1) / (BD * num_sms);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 8) ctas_per_sm = 8; // register limit; larger launches run in waves
+    const size_t budget = (size_t)227 * 1024 / ctas_per_sm - 1024;
+    for (int st : kStageChoices)
+        if (smem_bytes_for(nb, nj, maxc, st) <= budget) return st;
+    return 2;
+}
+
+extern "C" size_t b2p_step_smem_bytes(int nb, int nj, int maxc, int rpc)
+{
+    (void)rpc;
+    return smem_bytes_for(nb, nj, maxc, 2);
+}
 
 extern "C" int b2p_step_block_dim(void) { return BD; }
 
-extern "C" cudaError_t b2p_launch_step(const StepParams *P, int nb, int nj, int maxc, int rpc, cudaStream_t stream)
+template <int STAGES> static cudaError_t launch_t(const StepParams *P, size_t smem, cudaStream_t stream)
 {
     static size_t configured = 0;
-    const size_t smem = b2p_step_smem_bytes(nb, nj, maxc, rpc);
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(b2p_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(b2p_step_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     const int grid = (P->W + BD - 1) / BD;
-    b2p_step_kernel<<<grid, BD, smem, stream>>>(*P);
+    b2p_step_kernel<STAGES><<<grid, BD, smem, stream>>>(*P);
     return cudaGetLastError();
+}
+
+extern "C" cudaError_t b2p_launch_step(const StepParams *P, int nb, int nj, int maxc, int rpc, cudaStream_t stream)
+{
+    (void)rpc;
+    const int st = pick_stages(nb, nj, maxc, P->W);
+    const size_t smem = smem_bytes_for(nb, nj, maxc, st);
+    switch (st) {
+    case 12: return launch_t<12>(P, smem, stream);
+    case 8: return launch_t<8>(P, smem, stream);
+    case 6: return launch_t<6>(P, smem, stream);
+    case 4: return launch_t<4>(P, smem, stream);
+    case 3: return launch_t<3>(P, smem, stream);
+    default: return launch_t<2>(P, smem, stream);
+    }
 }
