@@ -239,8 +239,8 @@ def run_b200(args):
         sc = build_rover_worlds(ar, W, world_offset=rank * W)
     else:
         sc = BUILDERS[args.workload](ar, W, world_offset=rank * W)
-    if args.wpl:
-        ar.set_worlds_per_launch(args.wpl)
+    if args.resident_rows:
+        ar.set_resident_rows(args.resident_rows)
     if args.reorder == "none":
         ar.set_reorder_method(capi.REORDER_NONE)
     nb, nj = len(sc["bodies"]), len(sc["joints"])
@@ -281,6 +281,14 @@ def run_b200(args):
     launches = ar.kernel_launch_count() - launches0
     collide_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
     step_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    # per-kernel durations of the step (CUDA events on the arena's stream between its three launches;
+    # a separate pass because every step then synchronises)
+    ar.debug_kernel_times(True)
+    for _ in range(K):
+        ar.collide()
+        ar.step(H)
+    kt = ar.debug_kernel_times(False)
+    asm_ms, sor_ms, int_ms = float(kt[0]), float(kt[1]), float(kt[2])
 
     # ---------------- end-to-end loop through the C ABI with host buffers ----------------
     cmd = torch.empty((max(nj, 1), W), dtype=torch.float32).pin_memory()
@@ -313,10 +321,10 @@ def run_b200(args):
     assert np.isfinite(obs.numpy()).all(), "non-finite chassis state"
 
     # ---------------- reduce over ranks (max time) ----------------
-    t = torch.tensor([ms, ms_e2e, step_ms, collide_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, ms_e2e, step_ms, collide_ms, asm_ms, sor_ms, int_ms], dtype=torch.float64, device="cuda")
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, step_ms, collide_ms = [float(x) for x in t.cpu()]
+    ms, ms_e2e, step_ms, collide_ms, asm_ms, sor_ms, int_ms = [float(x) for x in t.cpu()]
     total_worlds = W * world_size
     value = total_worlds * K / (ms * 1e-3)
     e2e_value = total_worlds * K / (ms_e2e * 1e-3)
@@ -329,6 +337,9 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = balg * W / (step_ms * 1e-3) / 1e9
+    mean_rows = float(np.mean([ar.last_num_rows(w) for w in range(0, W, max(1, W // 256))]))
+    # compulsory traffic of the SOR kernel per world: rows in (64 B), lambda out (4 B), fch out, counters
+    sor_bytes = mean_rows * 68.0 + nb * 24.0 + 12.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -346,14 +357,19 @@ def run_b200(args):
                        "sharding": f"worlds/{world_size} GPUs, no collective on the step path",
                        "l2": "per-step working set (row scratch) > L2; no flush needed",
                        "settle_steps": SETTLE_STEPS, "row_reordering": args.reorder,
-                       "mean_rows_per_world": float(np.mean([ar.last_num_rows(w) for w in range(0, W, max(1, W // 64))])),
-                       "kernel_ms": {"collide": collide_ms, "step": step_ms}},
+                       "mean_rows_per_world": mean_rows,
+                       "kernel_ms": {"collide": collide_ms, "step": step_ms, "assemble": asm_ms, "sor": sor_ms,
+                                     "integrate": int_ms}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(len(cmd_joints) * W * 4),
                     "d2h_bytes_per_step": int(13 * W * 4), "ms_per_step": ms_e2e / K},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "kernel": "b2p_step_kernel",
+                         "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "one step = b2p_assemble_kernel + b2p_sor_kernel + b2p_integrate_kernel",
                          "algorithmic_bytes_per_world_step": balg,
+                         "sor_kernel": {"ms": sor_ms, "io_bytes_per_world": sor_bytes,
+                                        "io_gbs": sor_bytes * W / (sor_ms * 1e-3) / 1e9 if sor_ms > 0 else None,
+                                        "row_iterations_per_s": mean_rows * 20 * W / (sor_ms * 1e-3) if sor_ms > 0 else None},
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
             "clocks": sampler.summary(),
             "wall_s": t_wall,
@@ -379,7 +395,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--worlds", type=int, default=WORLDS_PER_GPU, help="worlds per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--wpl", type=int, default=0, help="tuning: worlds per step sub-launch (0 = all)")
+    ap.add_argument("--resident-rows", type=int, default=0,
+                    help="tuning: constraint rows per world kept in shared memory by the SOR kernel (0 = auto)")
     ap.add_argument("--reorder", default="random", choices=["random", "none"],
                     help="SOR row reordering: ODE 0.16 default (random) or REORDERING_METHOD__DONT_REORDER")
     ap.add_argument("--workload", default="D", choices=["B", "C", "D"],

@@ -127,8 +127,8 @@ int b2p_arena_set_stream(b2p_arena *a, void *cuda_stream);
 /* capacity knobs; must be called before the first step */
 int b2p_arena_set_max_contacts(b2p_arena *a, int max_contacts_per_world);
 int b2p_arena_enable_rolling_friction(b2p_arena *a, int on);
-/* tuning: split b2p_step into sub-launches of at most n worlds (0 = one launch) */
-int b2p_arena_set_worlds_per_launch(b2p_arena *a, int n);
+/* tuning: constraint rows per world the SOR kernel keeps in shared memory (0 = automatic) */
+int b2p_arena_set_resident_rows(b2p_arena *a, int n);
 
 int b2p_world_set_gravity(b2p_arena *a, double x, double y, double z);      /* dWorldSetGravity :194 */
 int b2p_world_set_cfm(b2p_arena *a, double cfm);                            /* dWorldSetCFM :195 */
@@ -230,10 +230,9 @@ int b2p_sync(b2p_arena *a);
 /* diagnostics of the last step */
 int b2p_world_last_num_rows(b2p_arena *a, int world, int *rows);
 int b2p_kernel_launch_count(const b2p_arena *a); /* kernels launched by this arena so far */
-/* diagnostics: per-phase clock64 cycle counters of the step kernel (enable resets them); out[0..4] =
- * mean cycles per warp-step of assembly / reshuffle+permute / sweeps / lambda write-back / epilogue,
- * out[5] = warp-steps accumulated.  Off by default (no cost when disabled). */
-int b2p_debug_phase_cycles(b2p_arena *a, int enable, double out[6]);
+/* diagnostics: per-kernel CUDA-event timing of b2p_step (enable resets; every step then synchronises);
+ * out[0..2] = mean milliseconds of the assemble / SOR / integrate kernels, out[3] = steps accumulated. */
+int b2p_debug_kernel_times(b2p_arena *a, int enable, double out[4]);
 /* algorithmic bytes one step of one world moves */
 double b2p_algorithmic_bytes_per_world_step(const b2p_arena *a);
 

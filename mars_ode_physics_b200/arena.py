@@ -50,8 +50,8 @@ class Arena:
     def enable_rolling_friction(self, on=True):
         self._check(self.lib.b2p_arena_enable_rolling_friction(self.h, int(on)))
 
-    def set_worlds_per_launch(self, n):
-        self._check(self.lib.b2p_arena_set_worlds_per_launch(self.h, int(n)))
+    def set_resident_rows(self, n):
+        self._check(self.lib.b2p_arena_set_resident_rows(self.h, int(n)))
 
     def set_gravity(self, x, y, z):
         self._check(self.lib.b2p_world_set_gravity(self.h, x, y, z))
@@ -326,9 +326,10 @@ class Arena:
     def kernel_launch_count(self):
         return self.lib.b2p_kernel_launch_count(self.h)
 
-    def debug_phase_cycles(self, enable=True):
-        out = self._out(6)
-        self._check(self.lib.b2p_debug_phase_cycles(self.h, int(enable), out))
+    def debug_kernel_times(self, enable=True):
+        """mean ms of the (assemble, SOR, integrate) kernels since timing was enabled, steps counted"""
+        out = self._out(4)
+        self._check(self.lib.b2p_debug_kernel_times(self.h, int(enable), out))
         return np.array(out[:], dtype=float)
 
     def algorithmic_bytes_per_world_step(self):

@@ -58,7 +58,7 @@ SIGNATURES = {
     "b2p_arena_set_stream": (_I, [_P, _P]),
     "b2p_arena_set_max_contacts": (_I, [_P, _I]),
     "b2p_arena_enable_rolling_friction": (_I, [_P, _I]),
-    "b2p_arena_set_worlds_per_launch": (_I, [_P, _I]),
+    "b2p_arena_set_resident_rows": (_I, [_P, _I]),
     "b2p_world_set_gravity": (_I, [_P, _D, _D, _D]),
     "b2p_world_set_cfm": (_I, [_P, _D]),
     "b2p_world_set_erp": (_I, [_P, _D]),
@@ -132,7 +132,7 @@ SIGNATURES = {
     "b2p_sync": (_I, [_P]),
     "b2p_world_last_num_rows": (_I, [_P, _I, _IP]),
     "b2p_kernel_launch_count": (_I, [_P]),
-    "b2p_debug_phase_cycles": (_I, [_P, _I, _DP]),
+    "b2p_debug_kernel_times": (_I, [_P, _I, _DP]),
     "b2p_algorithmic_bytes_per_world_step": (_D, [_P]),
 }
 

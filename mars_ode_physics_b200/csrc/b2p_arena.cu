@@ -19,9 +19,12 @@
 #include "../../include/mars_ode_b200.h"
 #include "b2p_dev.h"
 
-extern "C" size_t b2p_step_smem_bytes(int nb, int nj, int maxc, int rpc);
-extern "C" int b2p_step_block_dim(void);
-extern "C" cudaError_t b2p_launch_step(const StepParams *P, int nb, int nj, int maxc, int rpc, cudaStream_t stream);
+extern "C" size_t b2p_assemble_smem_bytes(int nb);
+extern "C" size_t b2p_integrate_smem_bytes(int nb);
+extern "C" size_t b2p_sor_smem_bytes(int nb, int maxrows, int rows_resident);
+extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, cudaStream_t stream);
+extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
+extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, cudaStream_t stream);
 
 namespace {
@@ -212,15 +215,19 @@ struct b2p_arena {
     Mirror<uint32_t> seed;
     Mirror<uint8_t> jrows;
     // solver scratch (device only)
-    float4 *d_rows = nullptr, *d_rowsB = nullptr;
-    float *d_lambda = nullptr, *d_rowad = nullptr, *d_invIw = nullptr, *d_lambdaB = nullptr;
-    uint8_t *d_ord = nullptr;
-    size_t scratch_rows = 0, scratch_nb = 0;
+    float4 *d_rows = nullptr;
+    float *d_lambda = nullptr, *d_rowS = nullptr, *d_invIw = nullptr, *d_fcacc = nullptr;
+    uint32_t *d_cmap = nullptr;
+    size_t scratch_rows = 0, scratch_nb = 0, scratch_maxc = 0;
+    int rows_resident = 0; // 0 = automatic
+    // optional per-kernel timing (bench / profiling): events around the three launches of a step
+    bool timing = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double kernel_ms[3] = {0, 0, 0};
+    long long timed_steps = 0;
     int *d_pairs = nullptr, *d_npairs = nullptr;
     int maxpairs = 0;
     int launches = 0;
-    int worlds_per_launch = 0; // 0 = all worlds in one launch
-    long long *d_phase = nullptr;
     bool stepped = false;
 };
 
@@ -347,6 +354,62 @@ void fill_limot(DevLimot &d, const HLimot &h)
 
 bool limot_has_stops(const HLimot &l) { return (l.lostop > -kInf || l.histop < kInf) && l.lostop < l.histop; }
 
+void free_scratch(b2p_arena *a)
+{
+    if (a->d_rows) cudaFree(a->d_rows);
+    if (a->d_lambda) cudaFree(a->d_lambda);
+    if (a->d_rowS) cudaFree(a->d_rowS);
+    if (a->d_invIw) cudaFree(a->d_invIw);
+    if (a->d_fcacc) cudaFree(a->d_fcacc);
+    if (a->d_cmap) cudaFree(a->d_cmap);
+    a->d_rows = nullptr;
+    a->d_lambda = a->d_rowS = a->d_invIw = a->d_fcacc = nullptr;
+    a->d_cmap = nullptr;
+    a->scratch_rows = a->scratch_nb = a->scratch_maxc = 0;
+}
+
+// Square root of a symmetric positive (semi)definite 3x3 matrix (row-major) by cyclic Jacobi rotations:
+// A = V diag(e) V^T  ->  sqrt(A) = V diag(sqrt(e)) V^T.  Used for the mass-scaled row form M^-1/2.
+void sym_sqrt33(const double *A, double *out)
+{
+    double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) a[i][j] = 0.5 * (A[i * 3 + j] + A[j * 3 + i]);
+    for (int sweep = 0; sweep < 64; sweep++) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+        if (off <= 1e-34 * diag || off == 0.0) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                if (a[p][q] == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; k++) { // A <- A G
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - sn * akq;
+                    a[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 3; k++) { // A <- G^T A
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - sn * aqk;
+                    a[q][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; k++) { // V <- V G
+                    const double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = c * vkp - sn * vkq;
+                    v[k][q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double x = 0;
+            for (int k = 0; k < 3; k++) x += v[i][k] * std::sqrt(std::max(a[k][k], 0.0)) * v[j][k];
+            out[i * 3 + j] = x;
+        }
+}
+
 // (re)build the device template and size every buffer
 int finalize(b2p_arena *a)
 {
@@ -376,6 +439,17 @@ int finalize(b2p_arena *a)
             for (int i = 0; i < 9; i++) {
                 d.I[i] = (float)h.I[i];
                 d.invI[i] = (float)h.invI[i];
+            }
+            d.sqrtInvMass = (float)std::sqrt(1.0 / h.mass);
+            d.sqrtMass = (float)std::sqrt(h.mass);
+            {
+                double sI[9], sInvI[9];
+                sym_sqrt33(h.I, sI);
+                sym_sqrt33(h.invI, sInvI);
+                for (int i = 0; i < 9; i++) {
+                    d.sqrtI[i] = (float)sI[i];
+                    d.sqrtInvI[i] = (float)sInvI[i];
+                }
             }
             d.gyroscopic = h.gyroscopic;
             d.nogravity = h.nogravity;
@@ -480,29 +554,21 @@ int finalize(b2p_arena *a)
     if ((rc = mirror_to_device(a, a->cfb))) return rc;
     if ((rc = mirror_to_device(a, a->nrows))) return rc;
     if ((rc = mirror_to_device(a, a->jrows))) return rc;
-    if (a->scratch_rows != (size_t)maxrows || a->scratch_nb != (size_t)nb) {
-        if (a->d_rows) cudaFree(a->d_rows);
-        if (a->d_rowsB) cudaFree(a->d_rowsB);
-        if (a->d_lambdaB) cudaFree(a->d_lambdaB);
-        if (a->d_ord) cudaFree(a->d_ord);
-        a->d_lambdaB = nullptr;
-        a->d_ord = nullptr;
-        if (a->d_lambda) cudaFree(a->d_lambda);
-        if (a->d_rowad) cudaFree(a->d_rowad);
-        if (a->d_invIw) cudaFree(a->d_invIw);
-        a->d_rows = a->d_rowsB = nullptr;
-        a->d_lambda = a->d_rowad = a->d_invIw = nullptr;
+    if (a->scratch_rows != (size_t)maxrows || a->scratch_nb != (size_t)nb || a->scratch_maxc != (size_t)a->maxc) {
+        free_scratch(a);
         const size_t mr = (size_t)std::max(maxrows, 1), Wp = (size_t)a->Wp;
         CUDA_TRY(cudaMalloc(&a->d_rows, sizeof(float4) * mr * 4 * Wp));
-        CUDA_TRY(cudaMalloc(&a->d_rowsB, sizeof(float4) * mr * 4 * Wp));
-        CUDA_TRY(cudaMalloc(&a->d_lambdaB, sizeof(float) * mr * Wp));
-        CUDA_TRY(cudaMalloc(&a->d_ord, mr * Wp));
         CUDA_TRY(cudaMalloc(&a->d_lambda, sizeof(float) * mr * Wp));
-        CUDA_TRY(cudaMalloc(&a->d_rowad, sizeof(float) * mr * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_rowS, sizeof(float) * mr * Wp));
         CUDA_TRY(cudaMalloc(&a->d_invIw, sizeof(float) * (size_t)std::max(nb, 1) * 9 * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_fcacc, sizeof(float) * (size_t)std::max(nb, 1) * 6 * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_cmap, sizeof(uint32_t) * (size_t)std::max(a->maxc, 1) * Wp));
+        // padded worlds (w >= W) and unused slots are read but never used: keep them finite
+        CUDA_TRY(cudaMemsetAsync(a->d_rows, 0, sizeof(float4) * mr * 4 * Wp, a->stream));
         CUDA_TRY(cudaMemsetAsync(a->d_lambda, 0, sizeof(float) * mr * Wp, a->stream));
         a->scratch_rows = (size_t)maxrows;
         a->scratch_nb = (size_t)nb;
+        a->scratch_maxc = (size_t)a->maxc;
     }
     return 0;
 }
@@ -681,18 +747,13 @@ void b2p_arena_destroy(b2p_arena *a)
     mirror_free(a->nrows);
     mirror_free(a->seed);
     mirror_free(a->jrows);
-    if (a->d_rows) cudaFree(a->d_rows);
-    if (a->d_rowsB) cudaFree(a->d_rowsB);
-    if (a->d_lambdaB) cudaFree(a->d_lambdaB);
-    if (a->d_ord) cudaFree(a->d_ord);
-    if (a->d_lambda) cudaFree(a->d_lambda);
-    if (a->d_rowad) cudaFree(a->d_rowad);
-    if (a->d_invIw) cudaFree(a->d_invIw);
+    free_scratch(a);
+    for (cudaEvent_t e : a->ev)
+        if (e) cudaEventDestroy(e);
     if (a->dT) cudaFree(a->dT);
     if (a->d_hf) cudaFree(a->d_hf);
     if (a->d_pairs) cudaFree(a->d_pairs);
     if (a->d_npairs) cudaFree(a->d_npairs);
-    if (a->d_phase) cudaFree(a->d_phase);
     delete a;
 }
 
@@ -1457,7 +1518,7 @@ int b2p_joint_get_num_rows(b2p_arena *a, int ji, int world, int *rows)
     *rows = 0;
     if (a->jrows.fields <= (size_t)ji) return 0;
     if ((rc = mirror_to_host(a, a->jrows))) return rc;
-    *rows = a->jrows.host[(size_t)ji * a->Wp + world];
+    *rows = a->jrows.host[(size_t)ji * a->Wp + world] & 7; // high nibble: limit/motor row (device use)
     return 0;
 }
 
@@ -1685,6 +1746,26 @@ int b2p_collide_get_pairs(b2p_arena *a, int world, int *pairs, int max_pairs)
 }
 
 // ---------------- the step ----------------
+namespace {
+constexpr size_t kSmemMax = 227 * 1024;
+
+// Rows per world the SOR kernel keeps in shared memory.  All of them if at least two CTAs (64 worlds) still
+// fit on an SM; otherwise as many as fit next to the per-world lambda / order / fch arrays (the rest is
+// read from L2 in place).  b2p_arena_set_resident_rows overrides the choice.
+int pick_rows_resident(const b2p_arena *a, int nb, int maxrows)
+{
+    const size_t fixed = b2p_sor_smem_bytes(nb, maxrows, 0), per_row = b2p_sor_smem_bytes(nb, maxrows, 1) - fixed;
+    auto fit = [&](int ctas) -> int {
+        const size_t budget = kSmemMax / ctas - 1024;
+        if (budget <= fixed) return 0;
+        return (int)std::min<size_t>((size_t)maxrows, (budget - fixed) / per_row);
+    };
+    if (a->rows_resident > 0) return std::min(std::min(a->rows_resident, maxrows), fit(1));
+    const int r2 = fit(2);
+    return r2 >= maxrows ? r2 : std::max(r2, std::min(fit(1), maxrows) / 2);
+}
+} // namespace
+
 int b2p_step(b2p_arena *a, double step_size)
 {
     if (!a) return fail(B2P_EINVAL, "null arena");
@@ -1714,30 +1795,37 @@ int b2p_step(b2p_arena *a, double step_size)
     P.crec = a->crec.dev;
     P.cfb = a->cfb.dev;
     P.lambda = a->d_lambda;
-    P.rowad = a->d_rowad;
+    P.rowS = a->d_rowS;
     P.invIw = a->d_invIw;
+    P.fcacc = a->d_fcacc;
     P.rows = a->d_rows;
-    P.rowsB = a->d_rowsB;
-    P.lambdaB = a->d_lambdaB;
-    P.ord = a->d_ord;
+    P.cmap = a->d_cmap;
     P.jrows = a->jrows.dev;
     P.ccount = a->ccount.dev;
     P.nrows = a->nrows.dev;
     P.seed = a->seed.dev;
-    P.phase_cycles = a->d_phase;
-    const size_t smem = b2p_step_smem_bytes((int)a->bodies.size(), (int)a->joints.size(), a->maxc, rpc_of(a));
-    if (smem > 227 * 1024) return fail(B2P_ECAPACITY, "scene needs %zu bytes of shared memory per CTA", smem);
-    // optional sub-launches over world ranges: fewer concurrent worlds keep the row scratch L2-resident
-    // and leave shared memory for a deeper cp.async ring
-    const int wpl = a->worlds_per_launch > 0 ? ((a->worlds_per_launch + 31) & ~31) : a->W;
-    for (int w0 = 0; w0 < a->W; w0 += wpl) {
-        StepParams Q = P;
-        Q.W = std::min(wpl, a->W - w0);
-        Q.state += w0, Q.force += w0, Q.jcmd += w0, Q.jobs += w0, Q.jfb += w0, Q.crec += w0, Q.cfb += w0;
-        Q.lambda += w0, Q.invIw += w0, Q.rows += w0, Q.rowsB += w0, Q.lambdaB += w0, Q.ord += w0;
-        Q.jrows += w0, Q.ccount += w0, Q.nrows += w0, Q.seed += w0;
-        CUDA_TRY(b2p_launch_step(&Q, (int)a->bodies.size(), (int)a->joints.size(), a->maxc, rpc_of(a), a->stream));
-        a->launches++;
+    const int nb = (int)a->bodies.size();
+    const int maxrows = (int)a->joints.size() * B2P_ROWS_PER_JOINT + a->maxc * rpc_of(a);
+    P.rows_resident = pick_rows_resident(a, nb, maxrows);
+    if (b2p_assemble_smem_bytes(nb) > kSmemMax || b2p_integrate_smem_bytes(nb) > kSmemMax ||
+        b2p_sor_smem_bytes(nb, maxrows, P.rows_resident) > kSmemMax)
+        return fail(B2P_ECAPACITY, "scene needs more than %zu bytes of shared memory per CTA", kSmemMax);
+    if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[0], a->stream));
+    CUDA_TRY(b2p_launch_assemble(&P, nb, a->stream));
+    if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[1], a->stream));
+    CUDA_TRY(b2p_launch_sor(&P, nb, maxrows, a->stream));
+    if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[2], a->stream));
+    CUDA_TRY(b2p_launch_integrate(&P, nb, a->stream));
+    a->launches += 3;
+    if (a->timing) {
+        CUDA_TRY(cudaEventRecord(a->ev[3], a->stream));
+        CUDA_TRY(cudaEventSynchronize(a->ev[3]));
+        for (int i = 0; i < 3; i++) {
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, a->ev[i], a->ev[i + 1]));
+            a->kernel_ms[i] += ms;
+        }
+        a->timed_steps++;
     }
     a->stepped = true;
     a->state.dev_newer = true;
@@ -1765,40 +1853,35 @@ int b2p_world_last_num_rows(b2p_arena *a, int world, int *rows)
     *rows = 0;
     if (a->nrows.fields == 0) return 0;
     if ((rc = mirror_to_host(a, a->nrows))) return rc;
-    *rows = a->nrows.host[(size_t)world];
+    *rows = a->nrows.host[(size_t)world] & 0xffff; // high half: independent rows (device use)
     return 0;
 }
 
 int b2p_kernel_launch_count(const b2p_arena *a) { return a ? a->launches : 0; }
 
-int b2p_arena_set_worlds_per_launch(b2p_arena *a, int n)
+int b2p_arena_set_resident_rows(b2p_arena *a, int n)
 {
-    if (!a || n < 0) return fail(B2P_EINVAL, "bad worlds_per_launch");
-    a->worlds_per_launch = n;
+    if (!a || n < 0) return fail(B2P_EINVAL, "bad resident row count");
+    a->rows_resident = n;
     return 0;
 }
 
-// diagnostics: enable (and reset) per-phase cycle counters of the step kernel; read them back as
-// out[0..4] = mean cycles per warp of {assembly, reshuffle+permute, sweeps, write-back, epilogue},
-// out[5] = number of warp-steps accumulated
-int b2p_debug_phase_cycles(b2p_arena *a, int enable, double out[6])
+// diagnostics: enable (and reset) per-kernel timing of b2p_step; while enabled every step synchronises.
+// out[0..2] = mean milliseconds of the assemble / SOR / integrate kernels, out[3] = steps accumulated.
+int b2p_debug_kernel_times(b2p_arena *a, int enable, double out[4])
 {
     if (!a) return fail(B2P_EINVAL, "null arena");
     CUDA_TRY(cudaSetDevice(a->device));
-    if (a->d_phase && out) {
-        long long h[6];
-        CUDA_TRY(cudaStreamSynchronize(a->stream));
-        CUDA_TRY(cudaMemcpy(h, a->d_phase, sizeof(h), cudaMemcpyDeviceToHost));
-        for (int i = 0; i < 5; i++) out[i] = h[5] ? (double)h[i] / (double)h[5] : 0.0;
-        out[5] = (double)h[5];
+    if (out) {
+        for (int i = 0; i < 3; i++) out[i] = a->timed_steps ? a->kernel_ms[i] / (double)a->timed_steps : 0.0;
+        out[3] = (double)a->timed_steps;
     }
-    if (enable) {
-        if (!a->d_phase) CUDA_TRY(cudaMalloc(&a->d_phase, 6 * sizeof(long long)));
-        CUDA_TRY(cudaMemset(a->d_phase, 0, 6 * sizeof(long long)));
-    } else if (a->d_phase) {
-        cudaFree(a->d_phase);
-        a->d_phase = nullptr;
-    }
+    a->timing = enable != 0;
+    a->timed_steps = 0;
+    a->kernel_ms[0] = a->kernel_ms[1] = a->kernel_ms[2] = 0;
+    if (enable)
+        for (cudaEvent_t &e : a->ev)
+            if (!e) CUDA_TRY(cudaEventCreate(&e));
     return 0;
 }
 

@@ -1,0 +1,733 @@
+// b2p_assemble.cu -- kernel 1 of the step: body preparation and constraint-row assembly (sm_100a).
+//
+// One thread owns one world; every global access is a world-fastest SoA access (one fully used
+// 128-byte line per field per warp).  It computes stages 0-2 of dWorldQuickStep as the reference
+// calls it at src/WorldPhysics.cpp:365 (ODE 0.16 quickstep.cpp): invI_world, implicit gyroscopic
+// torque, gravity, tmp1 = v/h + invM*fe, then getInfo1/getInfo2 of every joint (hinge, fixed, slider,
+// hinge2 incl. dxJointLimitMotor) and of every contact in the stream (mode bits as
+// src/objects/Frame.cpp:1046-1071 sets them).
+//
+// Row form handed to the SOR kernel (b2p_sor.cu).  ODE keeps, per row, J (12), iMJ = invM J^T (12),
+// rhs, Ad, cfm, lo, hi, findex and sweeps  delta = Ad*(rhs - cfm*lambda - J.fc); fc += delta*iMJ.
+// Here the row is scaled once so that the sweep needs a single 12-vector:
+//     Jh   = sqrt(Ad) * J * M^-1/2          (M^-1/2 = diag(sqrt(invMass) I3, R sqrt(invI_body) R^T))
+//     lam' = lambda / sqrt(Ad),  rhs' = sqrt(Ad)*rhs,  cfm' = Ad*cfm,  bounds / sqrt(Ad)
+//     fch  = M^-1/2 J^T lambda  (so that invM J^T lambda = M^-1/2 fch)
+//     sweep:  delta' = rhs' - cfm'*lam' - Jh.fch ;  fch += delta' * Jh
+// which is the same Gauss-Seidel iteration in different coordinates (Ad = w / (|J M^-1/2|^2 + cfm)).
+// A friction row's bound mu*lambda_n becomes (mu*sqrt(Ad_n/Ad_f)) * lam'_n.
+//
+// Rows are stored in ODE's initial sweep order (rows with findex < 0 first, in creation order, then the
+// friction-dependent rows), so that the order array of iteration 0 is the identity.
+#include "b2p_kern.cuh"
+
+namespace {
+
+constexpr int BD = 64; // threads (= worlds) per CTA
+
+struct Smem {
+    float *t1; // [nb*6][BD]  fe -> tmp1 = v/h + invM fe
+    float *sw; // [nb*6][BD]  symmetric sqrt(invI_world): xx xy xz yy yz zz
+};
+
+// One constraint row under construction (ODE Info2 view).
+struct Row {
+    float J[12];
+    float c, cfm, lo, hi;
+    int fr;     // slot of the contact's normal row + 1 if this row's bounds follow it (findex), else 0
+    float sn;   // sqrt(Ad) of that normal row
+};
+
+__device__ __forceinline__ void row_init(Row &r, float world_cfm)
+{
+#pragma unroll
+    for (int k = 0; k < 12; k++) r.J[k] = 0.f;
+    r.c = 0.f;
+    r.cfm = world_cfm;
+    r.lo = -INFINITY;
+    r.hi = INFINITY;
+    r.fr = 0;
+    r.sn = 1.f;
+}
+
+struct PairCtx {
+    int b0, b1;      // b1 < 0: static
+    float sm0, sm1;  // sqrt(invMass)
+    float S0[6], S1[6];
+};
+
+__device__ __forceinline__ void pair_ctx(PairCtx &pc, const DevTemplate *T, const Smem &S, int tid)
+{
+    pc.sm0 = T->bodies[pc.b0].sqrtInvMass;
+#pragma unroll
+    for (int k = 0; k < 6; k++) pc.S0[k] = S.sw[(size_t)(pc.b0 * 6 + k) * BD + tid];
+    pc.sm1 = 0.f;
+    if (pc.b1 >= 0) {
+        pc.sm1 = T->bodies[pc.b1].sqrtInvMass;
+#pragma unroll
+        for (int k = 0; k < 6; k++) pc.S1[k] = S.sw[(size_t)(pc.b1 * 6 + k) * BD + tid];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) pc.S1[k] = 0.f;
+    }
+}
+
+__device__ __forceinline__ void sym_mul(float *o, const float *Ssym, const float *v)
+{
+    o[0] = Ssym[0] * v[0] + Ssym[1] * v[1] + Ssym[2] * v[2];
+    o[1] = Ssym[1] * v[0] + Ssym[3] * v[1] + Ssym[4] * v[2];
+    o[2] = Ssym[2] * v[0] + Ssym[4] * v[1] + Ssym[5] * v[2];
+}
+
+// rhs = c/h - J.tmp1 ; Jt = J M^-1/2 ; Ad = w/(|Jt|^2 + cfm/h) ; scale by sqrt(Ad) ; store at `slot`.
+// Returns sqrt(Ad).
+__device__ __forceinline__ float emit_row(const StepParams &P, const Smem &S, int w, int tid, int slot, const Row &r,
+                                          const PairCtx &pc)
+{
+    const int Wp = P.Wp;
+    const float hinv = 1.0f / P.h;
+    float rhs = r.c * hinv;
+    const float cfm = r.cfm * hinv;
+    float s = 0.f;
+    {
+        const float *t = S.t1 + (size_t)(pc.b0 * 6) * BD + tid;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s += r.J[k] * t[k * BD];
+    }
+    if (pc.b1 >= 0) {
+        const float *t = S.t1 + (size_t)(pc.b1 * 6) * BD + tid;
+#pragma unroll
+        for (int k = 0; k < 6; k++) s += r.J[6 + k] * t[k * BD];
+    }
+    rhs -= s;
+    float o[12];
+    o[0] = pc.sm0 * r.J[0];
+    o[1] = pc.sm0 * r.J[1];
+    o[2] = pc.sm0 * r.J[2];
+    sym_mul(o + 3, pc.S0, r.J + 3);
+    o[6] = pc.sm1 * r.J[6];
+    o[7] = pc.sm1 * r.J[7];
+    o[8] = pc.sm1 * r.J[8];
+    sym_mul(o + 9, pc.S1, r.J + 9);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; k++) sum += o[k] * o[k];
+    const float Ad = P.sor_w / (sum + cfm);
+    const float sa = sqrtf(Ad), rsa = 1.0f / sa;
+    // bound word: 0xFFFFFFFF = [0,+inf), 0xFFFFFFFE = (-inf,0], otherwise [-b,b] with b = hi/sqrt(Ad)
+    // (b = +inf: unbounded); for a friction-dependent row b = mu*sqrt(Ad_n/Ad_f), multiplied by the normal
+    // row's current lam' in the sweep (ODE: hi = |hicopy * lambda[findex]|).
+    float bound;
+    if (r.fr) bound = r.hi * r.sn * rsa;
+    else if (r.lo == 0.f && r.hi == INFINITY) bound = __int_as_float(0xFFFFFFFF);
+    else if (r.lo == -INFINITY && r.hi == 0.f) bound = __int_as_float(0xFFFFFFFE);
+    else bound = r.hi * rsa;
+    // meta: body0 | body1<<8 (0xff = one-body row) | fr<<16
+    const int meta = (pc.b0 & 0xff) | ((pc.b1 < 0 ? 0xff : pc.b1) << 8) | (r.fr << 16);
+    float4 *dst = P.rows + (size_t)(slot * 4) * Wp + w;
+    dst[0 * (size_t)Wp] = make_float4(sa * o[0], sa * o[1], sa * o[2], sa * o[3]);
+    dst[1 * (size_t)Wp] = make_float4(sa * o[4], sa * o[5], sa * o[6], sa * o[7]);
+    dst[2 * (size_t)Wp] = make_float4(sa * o[8], sa * o[9], sa * o[10], sa * o[11]);
+    dst[3 * (size_t)Wp] = make_float4(sa * rhs, cfm * Ad, bound, __int_as_float(meta));
+    P.rowS[(size_t)slot * Wp + w] = sa;
+    return sa;
+}
+
+// dxJointLimitMotor::addLimot, row part.  Returns 1 if the row is used.
+// The "powered while at a limit" force injection is done by limot_prepass() before tmp1 exists.
+__device__ __forceinline__ int add_limot_row(const StepParams &P, const DevLimot &l, float vel, float fmax,
+                                             const LimotState &st, Row &r, const float *ax1, int rotational,
+                                             const BodyPose &p0, const BodyPose &p1, bool has_b1)
+{
+    int powered = fmax > 0.f;
+    if (!(powered || st.limit)) return 0;
+    float *J1 = rotational ? r.J + 3 : r.J;
+    float *J2 = rotational ? r.J + 9 : r.J + 6;
+#pragma unroll
+    for (int i = 0; i < 3; i++) J1[i] = ax1[i];
+    if (has_b1) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) J2[i] = -ax1[i];
+    }
+    if (!rotational && has_b1) {
+        float c[3], ltd[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) c[i] = 0.5f * (p1.pos[i] - p0.pos[i]);
+        cross3(ltd, c, ax1);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            r.J[3 + i] = ltd[i];
+            r.J[9 + i] = ltd[i];
+        }
+    }
+    if (st.limit && (l.lostop == l.histop)) powered = 0;
+    if (powered) {
+        r.cfm = l.normal_cfm;
+        if (!st.limit) {
+            r.c = vel;
+            r.lo = -fmax;
+            r.hi = fmax;
+        }
+    }
+    if (st.limit) {
+        const float k = (1.0f / P.h) * l.stop_erp;
+        r.c = -k * st.limit_err;
+        r.cfm = l.stop_cfm;
+        if (l.lostop == l.histop) {
+            r.lo = -INFINITY;
+            r.hi = INFINITY;
+        } else if (st.limit == 1) {
+            r.lo = 0.f;
+            r.hi = INFINITY;
+        } else {
+            r.lo = -INFINITY;
+            r.hi = 0.f;
+        }
+        // dParamBounce is never set by the reference; not supported on the device path.
+    }
+    return 1;
+}
+
+__global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DevTemplate *__restrict__ T = P.T;
+    const int nb = T->nb, nj = T->nj, maxc = T->maxc, rpc = T->rpc;
+    Smem S;
+    S.t1 = (float *)smem_raw;
+    S.sw = S.t1 + (size_t)nb * 6 * BD;
+    const int tid = threadIdx.x;
+    const int w = blockIdx.x * BD + tid;
+    if (w >= P.W) return;
+    const int Wp = P.Wp;
+    const float h = P.h, hinv = 1.0f / P.h;
+
+    // ---------------- phase 1: bodies ----------------
+    for (int b = 0; b < nb; b++) {
+        const DevBody &bc = T->bodies[b];
+        BodyPose bp;
+        load_pose(P, b, w, bp);
+        const int f = b * B2P_STATE_FIELDS;
+        float avel[3] = {G(P.state, f + 10), G(P.state, f + 11), G(P.state, f + 12)};
+        float facc[3] = {G(P.force, b * 6 + 0), G(P.force, b * 6 + 1), G(P.force, b * 6 + 2)};
+        float tacc[3] = {G(P.force, b * 6 + 3), G(P.force, b * 6 + 4), G(P.force, b * 6 + 5)};
+        float tmp[9], Iw[9];
+        mul33_bt(tmp, bc.invI, bp.R);
+        mul33(Iw, bp.R, tmp);
+#pragma unroll
+        for (int k = 0; k < 9; k++) G(P.invIw, b * 9 + k) = Iw[k];
+        {
+            // S_w = R sqrt(invI_body) R^T: the angular block of M^-1/2 in the world frame
+            float Sw[9];
+            mul33_bt(tmp, bc.sqrtInvI, bp.R);
+            mul33(Sw, bp.R, tmp);
+            S.sw[(size_t)(b * 6 + 0) * BD + tid] = Sw[0];
+            S.sw[(size_t)(b * 6 + 1) * BD + tid] = Sw[1];
+            S.sw[(size_t)(b * 6 + 2) * BD + tid] = Sw[2];
+            S.sw[(size_t)(b * 6 + 3) * BD + tid] = Sw[4];
+            S.sw[(size_t)(b * 6 + 4) * BD + tid] = Sw[5];
+            S.sw[(size_t)(b * 6 + 5) * BD + tid] = Sw[8];
+        }
+        if (bc.gyroscopic) {
+            // implicit gyroscopic torque (ODE 0.16 quickstep stage0, Lacoursiere 2006)
+            float I[9], L[3], It[9], itInv[9];
+            mul33_bt(tmp, bc.I, bp.R);
+            mul33(I, bp.R, tmp);
+            mul_R_v(L, I, avel);
+            It[0] = I[0];
+            It[1] = I[1] + h * L[2];
+            It[2] = I[2] - h * L[1];
+            It[3] = I[3] - h * L[2];
+            It[4] = I[4];
+            It[5] = I[5] + h * L[0];
+            It[6] = I[6] + h * L[1];
+            It[7] = I[7] - h * L[0];
+            It[8] = I[8];
+#pragma unroll
+            for (int k = 0; k < 3; k++) L[k] *= hinv;
+            if (invert33(itInv, It) != 0.f) {
+                float M[9], tau[3];
+                mul33(M, I, itInv);
+                M[0] -= 1.f;
+                M[4] -= 1.f;
+                M[8] -= 1.f;
+                mul_R_v(tau, M, L);
+#pragma unroll
+                for (int k = 0; k < 3; k++) tacc[k] += tau[k];
+            }
+        }
+        if (!bc.nogravity) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) facc[k] += bc.mass * P.gravity[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            S.t1[(size_t)(b * 6 + k) * BD + tid] = facc[k];
+            S.t1[(size_t)(b * 6 + 3 + k) * BD + tid] = tacc[k];
+        }
+    }
+
+    // ---------------- phase 1a: limit motors powered into a stop add forces (rare) -------------
+    if (T->has_limit_motors) {
+        for (int j = 0; j < nj; j++) {
+            const DevJoint &jc = T->joints[j];
+            if (jc.type == 6 || jc.b0 < 0) continue;
+            BodyPose p0, p1;
+            load_pose(P, jc.b0, w, p0);
+            const bool has_b1 = jc.b1 >= 0;
+            if (has_b1) load_pose(P, jc.b1, w, p1);
+            LimotState st;
+            joint_limit_state(jc, p0, p1, st);
+            const float vel = G(P.jcmd, j * 4 + 0), fmax = G(P.jcmd, j * 4 + 1);
+            const DevLimot &l = jc.limot1;
+            if (fmax > 0.f && st.limit && l.lostop != l.histop) {
+                float fm = fmax;
+                if ((vel > 0.f) || (vel == 0.f && st.limit == 2)) fm = -fm;
+                if ((st.limit == 1 && vel > 0.f) || (st.limit == 2 && vel < 0.f)) fm *= l.fudge_factor;
+                float ax1[3];
+                mul_R_v(ax1, p0.R, jc.axis1);
+                float *f0 = S.t1 + (size_t)(jc.b0 * 6) * BD + tid;
+                float *f1 = has_b1 ? S.t1 + (size_t)(jc.b1 * 6) * BD + tid : nullptr;
+                if (jc.type == 3) { // slider: linear force (+ torque decoupling)
+                    if (jc.reverse && !has_b1) {
+#pragma unroll
+                        for (int i = 0; i < 3; i++) ax1[i] = -ax1[i];
+                    }
+                    if (has_b1) {
+                        float c[3], ltd[3];
+#pragma unroll
+                        for (int i = 0; i < 3; i++) c[i] = 0.5f * (p1.pos[i] - p0.pos[i]);
+                        cross3(ltd, c, ax1);
+#pragma unroll
+                        for (int i = 0; i < 3; i++) {
+                            f0[(3 + i) * BD] -= fm * ltd[i];
+                            f1[(3 + i) * BD] -= fm * ltd[i];
+                            f1[i * BD] += fm * ax1[i];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 3; i++) f0[i * BD] -= fm * ax1[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        if (has_b1) f1[(3 + i) * BD] += fm * ax1[i];
+                        f0[(3 + i) * BD] -= fm * ax1[i];
+                    }
+                }
+            }
+        }
+    }
+
+    // ---------------- phase 1b: fe -> gmem (needed by the epilogue), tmp1 -> smem --------------
+    for (int b = 0; b < nb; b++) {
+        const DevBody &bc = T->bodies[b];
+        const int f = b * B2P_STATE_FIELDS;
+        float Iw[9], fe[6], t3[3];
+        load_invIw(P, b, w, Iw);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            fe[k] = S.t1[(size_t)(b * 6 + k) * BD + tid];
+            G(P.force, b * 6 + k) = fe[k];
+        }
+        mul_R_v(t3, Iw, fe + 3);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float lv = G(P.state, f + 7 + k), av = G(P.state, f + 10 + k);
+            S.t1[(size_t)(b * 6 + k) * BD + tid] = fe[k] * bc.invMass + lv * hinv;
+            S.t1[(size_t)(b * 6 + 3 + k) * BD + tid] = t3[k] + av * hinv;
+        }
+    }
+
+    // ---------------- phase 2: constraint rows ----------------
+    // ODE orders rows with findex < 0 first (in row order) and friction-dependent rows last.
+    // Head rows are appended as they are emitted; dependent rows are recorded per contact in a bit
+    // mask and appended after all contacts are known.
+    int nhead = 0;
+
+    for (int j = 0; j < nj; j++) {
+        const DevJoint &jc = T->joints[j];
+        int mrows = 0, limot_row = -1;
+        if (jc.b0 >= 0) {
+            const bool has_b1 = jc.b1 >= 0;
+            BodyPose p0, p1;
+            PairCtx pc;
+            pc.b0 = jc.b0;
+            pc.b1 = jc.b1;
+            load_pose(P, jc.b0, w, p0);
+            if (has_b1) load_pose(P, jc.b1, w, p1);
+            pair_ctx(pc, T, S, tid);
+            const float kerp = hinv * P.erp;
+            Row r;
+            if (jc.type == 1) {
+                // ---- hinge: setBall + two angular rows + limot (ODE hinge.cpp getInfo2)
+                float a1[3], a2[3], cb[3];
+                mul_R_v(a1, p0.R, jc.anchor1);
+                if (has_b1) {
+                    mul_R_v(a2, p1.R, jc.anchor2);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) cb[i] = kerp * (a2[i] + p1.pos[i] - a1[i] - p0.pos[i]);
+                } else {
+                    a2[0] = a2[1] = a2[2] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 3; i++) cb[i] = kerp * (jc.anchor2[i] - a1[i] - p0.pos[i]);
+                }
+                // row 0
+                row_init(r, P.cfm);
+                r.J[0] = 1.f; r.J[4] = a1[2]; r.J[5] = -a1[1];
+                if (has_b1) { r.J[6] = -1.f; r.J[10] = -a2[2]; r.J[11] = a2[1]; }
+                r.c = cb[0];
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                row_init(r, P.cfm);
+                r.J[1] = 1.f; r.J[3] = -a1[2]; r.J[5] = a1[0];
+                if (has_b1) { r.J[7] = -1.f; r.J[9] = a2[2]; r.J[11] = -a2[0]; }
+                r.c = cb[1];
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                row_init(r, P.cfm);
+                r.J[2] = 1.f; r.J[3] = a1[1]; r.J[4] = -a1[0];
+                if (has_b1) { r.J[8] = -1.f; r.J[9] = -a2[1]; r.J[10] = a2[0]; }
+                r.c = cb[2];
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                float ax1[3], pv[3], qv[3], ax2[3], bv[3];
+                mul_R_v(ax1, p0.R, jc.axis1);
+                plane_space(ax1, pv, qv);
+                if (has_b1) mul_R_v(ax2, p1.R, jc.axis2);
+                else { ax2[0] = jc.axis2[0]; ax2[1] = jc.axis2[1]; ax2[2] = jc.axis2[2]; }
+                cross3(bv, ax1, ax2);
+                row_init(r, P.cfm);
+                r.J[3] = pv[0]; r.J[4] = pv[1]; r.J[5] = pv[2];
+                if (has_b1) { r.J[9] = -pv[0]; r.J[10] = -pv[1]; r.J[11] = -pv[2]; }
+                r.c = kerp * dot3(bv, pv);
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                row_init(r, P.cfm);
+                r.J[3] = qv[0]; r.J[4] = qv[1]; r.J[5] = qv[2];
+                if (has_b1) { r.J[9] = -qv[0]; r.J[10] = -qv[1]; r.J[11] = -qv[2]; }
+                r.c = kerp * dot3(bv, qv);
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                mrows = 5;
+                LimotState st;
+                joint_limit_state(jc, p0, p1, st);
+                row_init(r, P.cfm);
+                if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 1, p0, p1,
+                                  has_b1)) {
+                    emit_row(P, S, w, tid, nhead++, r, pc);
+                    limot_row = 5;
+                    mrows = 6;
+                }
+            } else if (jc.type == 6) {
+                // ---- fixed (ODE fixed.cpp getInfo2): rows 0-2 position, rows 3-5 orientation
+                float ofs[3], cl[3], ca[3];
+                mul_R_v(ofs, p0.R, jc.offset);
+                const float k = hinv * jc.erp;
+                if (has_b1) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) cl[i] = k * (p1.pos[i] - p0.pos[i] + ofs[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) cl[i] = k * (jc.offset[i] - p0.pos[i]);
+                }
+                fixed_orientation_rhs(jc, p0, p1, has_b1, hinv * P.erp * 2.f, ca);
+                row_init(r, P.cfm);
+                r.J[0] = 1.f;
+                if (has_b1) { r.J[4] = -ofs[2]; r.J[5] = ofs[1]; r.J[6] = -1.f; }
+                r.c = cl[0]; r.cfm = jc.cfm;
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                row_init(r, P.cfm);
+                r.J[1] = 1.f;
+                if (has_b1) { r.J[3] = ofs[2]; r.J[5] = -ofs[0]; r.J[7] = -1.f; }
+                r.c = cl[1]; r.cfm = jc.cfm;
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                row_init(r, P.cfm);
+                r.J[2] = 1.f;
+                if (has_b1) { r.J[3] = -ofs[1]; r.J[4] = ofs[0]; r.J[8] = -1.f; }
+                r.c = cl[2]; r.cfm = jc.cfm;
+                emit_row(P, S, w, tid, nhead++, r, pc);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    row_init(r, P.cfm);
+                    r.J[3 + i] = 1.f;
+                    if (has_b1) r.J[9 + i] = -1.f;
+                    r.c = ca[i];
+                    emit_row(P, S, w, tid, nhead++, r, pc);
+                }
+                mrows = 6;
+            } else if (jc.type == 3) {
+                // ---- slider (ODE slider.cpp getInfo2)
+                float ca[3];
+                fixed_orientation_rhs(jc, p0, p1, has_b1, hinv * P.erp * 2.f, ca);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    row_init(r, P.cfm);
+                    r.J[3 + i] = 1.f;
+                    if (has_b1) r.J[9 + i] = -1.f;
+                    r.c = ca[i];
+                    emit_row(P, S, w, tid, nhead++, r, pc);
+                }
+                float c[3] = {0.f, 0.f, 0.f}, ax1[3], pv[3], qv[3];
+                if (has_b1) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) c[i] = p1.pos[i] - p0.pos[i];
+                }
+                mul_R_v(ax1, p0.R, jc.axis1);
+                plane_space(ax1, pv, qv);
+                float c3, c4, tp[3], tq[3];
+                if (has_b1) {
+                    cross3(tp, c, pv);
+                    cross3(tq, c, qv);
+                    float ofs[3];
+                    mul_R_v(ofs, p1.R, jc.offset);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) c[i] += ofs[i];
+                    c3 = kerp * dot3(pv, c);
+                    c4 = kerp * dot3(qv, c);
+                } else {
+                    float ofs[3];
+#pragma unroll
+                    for (int i = 0; i < 3; i++) ofs[i] = jc.offset[i] - p0.pos[i];
+                    c3 = kerp * dot3(pv, ofs);
+                    c4 = kerp * dot3(qv, ofs);
+                    if (jc.reverse) {
+#pragma unroll
+                        for (int i = 0; i < 3; i++) ax1[i] = -ax1[i];
+                    }
+                }
+                row_init(r, P.cfm);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    r.J[i] = pv[i];
+                    if (has_b1) { r.J[3 + i] = 0.5f * tp[i]; r.J[9 + i] = 0.5f * tp[i]; r.J[6 + i] = -pv[i]; }
+                }
+                r.c = c3;
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                row_init(r, P.cfm);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    r.J[i] = qv[i];
+                    if (has_b1) { r.J[3 + i] = 0.5f * tq[i]; r.J[9 + i] = 0.5f * tq[i]; r.J[6 + i] = -qv[i]; }
+                }
+                r.c = c4;
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                mrows = 5;
+                LimotState st;
+                joint_limit_state(jc, p0, p1, st);
+                row_init(r, P.cfm);
+                if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 0, p0, p1,
+                                  has_b1)) {
+                    emit_row(P, S, w, tid, nhead++, r, pc);
+                    limot_row = 5;
+                    mrows = 6;
+                }
+            } else if (jc.type == 2 && has_b1) {
+                // ---- hinge2 (ODE hinge2.cpp getInfo2): setBall2 along axis1 + one angular row + limots
+                float ax1[3], ax2[3], qv[3];
+                mul_R_v(ax1, p0.R, jc.axis1);
+                mul_R_v(ax2, p1.R, jc.axis2);
+                cross3(qv, ax1, ax2);
+                const float sn = sqrtf(dot3(qv, qv));
+                const float cs = dot3(ax1, ax2);
+                normalize3(qv);
+                float q1[3], q2[3], a1[3], a2[3], d[3];
+                plane_space(ax1, q1, q2);
+                mul_R_v(a1, p0.R, jc.anchor1);
+                mul_R_v(a2, p1.R, jc.anchor2);
+                float a1w[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) a1w[i] = a1[i] + p0.pos[i];
+#pragma unroll
+                for (int i = 0; i < 3; i++) d[i] = a2[i] + p1.pos[i] - a1w[i];
+                const float k1 = hinv * jc.susp_erp;
+                const float *dirs[3] = {ax1, q1, q2};
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    row_init(r, P.cfm);
+                    const float *dv = dirs[i];
+                    r.J[0] = dv[0]; r.J[1] = dv[1]; r.J[2] = dv[2];
+                    cross3(r.J + 3, a1, dv);
+                    r.J[6] = -dv[0]; r.J[7] = -dv[1]; r.J[8] = -dv[2];
+                    cross3(r.J + 9, dv, a2);
+                    r.c = (i == 0 ? k1 : kerp) * dot3(dv, d);
+                    if (i == 0) r.cfm = jc.susp_cfm;
+                    emit_row(P, S, w, tid, nhead++, r, pc);
+                }
+                row_init(r, P.cfm);
+#pragma unroll
+                for (int i = 0; i < 3; i++) { r.J[3 + i] = qv[i]; r.J[9 + i] = -qv[i]; }
+                r.c = kerp * (jc.c0 * sn - jc.s0 * cs);
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                mrows = 4;
+                LimotState st;
+                joint_limit_state(jc, p0, p1, st);
+                row_init(r, P.cfm);
+                if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 1, p0, p1,
+                                  true)) {
+                    emit_row(P, S, w, tid, nhead++, r, pc);
+                    limot_row = mrows;
+                    mrows++;
+                }
+                LimotState st2;
+                st2.limit = 0;
+                st2.limit_err = 0.f;
+                row_init(r, P.cfm);
+                if (add_limot_row(P, jc.limot2, G(P.jcmd, j * 4 + 2), G(P.jcmd, j * 4 + 3), st2, r, ax2, 1, p0, p1,
+                                  true)) {
+                    emit_row(P, S, w, tid, nhead++, r, pc);
+                    if (limot_row < 0) limot_row = mrows;
+                    mrows++;
+                }
+            }
+        }
+        G(P.jrows, j) = (uint8_t)(mrows | ((limot_row + 1) << 4));
+    }
+
+    // ---- contacts (ODE contact.cpp getInfo1/getInfo2 for the mode bits Frame::addContact sets)
+    int nc = G(P.ccount, 0);
+    if (nc > maxc) nc = maxc;
+    // Pre-pass: how many rows of the contacts are independent (findex < 0), so that the dependent ones
+    // can be written straight to their place behind all independent rows.
+    int ntail = nhead;
+    for (int c = 0; c < nc; c++) {
+        const int mode = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_MODE));
+        const float mu = G(P.crec, c * B2P_CONTACT_FIELDS + CR_MU);
+        const float mu2 = G(P.crec, c * B2P_CONTACT_FIELDS + CR_MU2);
+        const bool axisdep = (mode & 0x001) != 0;
+        ntail += 1;
+        if (mu > 0.f && !(mode & 0x1000)) ntail++;
+        if ((axisdep ? (mu2 > 0.f) : (mu > 0.f)) && !(mode & 0x2000)) ntail++;
+        if ((mode & 0x400) && rpc >= 6) {
+            const float rho0 = G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHO);
+            const float rho1 = axisdep ? G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHO2) : rho0;
+            const float rho2 = axisdep ? G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHON) : rho0;
+            if (rho0 > 0.f && !(mode & 0x1000)) ntail++;
+            if (rho1 > 0.f && !(mode & 0x2000)) ntail++;
+            if (rho2 > 0.f && !(mode & 0x4000)) ntail++;
+        }
+    }
+    const int nhead_total = ntail;
+    for (int c = 0; c < nc; c++) {
+        const int ids = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_IDS));
+        const int b0 = ids & 0xff;
+        const int b1 = ((ids >> 8) & 0xff) == 0xff ? -1 : ((ids >> 8) & 0xff);
+        const int mode = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_MODE));
+        float pos[3] = {G(P.crec, c * B2P_CONTACT_FIELDS + CR_PX), G(P.crec, c * B2P_CONTACT_FIELDS + CR_PY),
+                        G(P.crec, c * B2P_CONTACT_FIELDS + CR_PZ)};
+        float n[3] = {G(P.crec, c * B2P_CONTACT_FIELDS + CR_NX), G(P.crec, c * B2P_CONTACT_FIELDS + CR_NY),
+                      G(P.crec, c * B2P_CONTACT_FIELDS + CR_NZ)};
+        float depth = G(P.crec, c * B2P_CONTACT_FIELDS + CR_DEPTH) - P.contact_min_depth;
+        float mu = G(P.crec, c * B2P_CONTACT_FIELDS + CR_MU);
+        float mu2 = G(P.crec, c * B2P_CONTACT_FIELDS + CR_MU2);
+        const float soft_erp = G(P.crec, c * B2P_CONTACT_FIELDS + CR_SOFT_ERP);
+        const float soft_cfm = G(P.crec, c * B2P_CONTACT_FIELDS + CR_SOFT_CFM);
+        if (depth < 0.f) depth = 0.f;
+        if (mu < 0.f) mu = 0.f;
+        if (mu2 < 0.f) mu2 = 0.f;
+        PairCtx pc;
+        pc.b0 = b0;
+        pc.b1 = b1;
+        BodyPose p0, p1;
+        load_pose(P, b0, w, p0);
+        if (b1 >= 0) load_pose(P, b1, w, p1);
+        pair_ctx(pc, T, S, tid);
+        const float erp = (mode & 0x008) ? soft_erp : P.erp;
+        const float pushout = hinv * erp * depth;
+        float c1[3], c2[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 3; i++) c1[i] = pos[i] - p0.pos[i];
+        Row r;
+        row_init(r, P.cfm);
+        r.J[0] = n[0]; r.J[1] = n[1]; r.J[2] = n[2];
+        cross3(r.J + 3, c1, n);
+        if (b1 >= 0) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) { c2[i] = pos[i] - p1.pos[i]; r.J[6 + i] = -n[i]; }
+            cross3(r.J + 9, n, c2);
+        }
+        r.c = pushout > P.contact_max_vel ? P.contact_max_vel : pushout;
+        if (mode & 0x010) r.cfm = soft_cfm;
+        r.lo = 0.f;
+        r.hi = INFINITY;
+        const int nslot = nhead;
+        const int tslot = ntail;
+        const float sn = emit_row(P, S, w, tid, nhead++, r, pc);
+        int row = 1, depmask = 0;
+        float t1[3], t2[3];
+        plane_space(n, t1, t2);
+        const bool axisdep = (mode & 0x001) != 0;
+        const bool fr1 = mu > 0.f;
+        const float mu2e = axisdep ? mu2 : mu;
+        const bool fr2 = axisdep ? (mu2 > 0.f) : (mu > 0.f);
+        // one friction / rolling row: dependent rows (findex = normal row) go behind all independent rows
+        auto emit_fr = [&](bool dependent) {
+            if (dependent) {
+                r.fr = nslot + 1;
+                r.sn = sn;
+                depmask |= 1 << (row - 1);
+                emit_row(P, S, w, tid, ntail++, r, pc);
+            } else {
+                emit_row(P, S, w, tid, nhead++, r, pc);
+            }
+            row++;
+        };
+        if (fr1) {
+            row_init(r, P.cfm);
+            r.J[0] = t1[0]; r.J[1] = t1[1]; r.J[2] = t1[2];
+            cross3(r.J + 3, c1, t1);
+            if (b1 >= 0) { r.J[6] = -t1[0]; r.J[7] = -t1[1]; r.J[8] = -t1[2]; cross3(r.J + 9, t1, c2); }
+            r.lo = -mu;
+            r.hi = mu;
+            emit_fr((mode & 0x1000) != 0);
+        }
+        if (fr2) {
+            row_init(r, P.cfm);
+            r.J[0] = t2[0]; r.J[1] = t2[1]; r.J[2] = t2[2];
+            cross3(r.J + 3, c1, t2);
+            if (b1 >= 0) { r.J[6] = -t2[0]; r.J[7] = -t2[1]; r.J[8] = -t2[2]; cross3(r.J + 9, t2, c2); }
+            r.lo = -mu2e;
+            r.hi = mu2e;
+            emit_fr((mode & 0x2000) != 0);
+        }
+        if ((mode & 0x400) && rpc >= 6) {
+            float rho[3];
+            rho[0] = G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHO);
+            if (axisdep) {
+                rho[1] = G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHO2);
+                rho[2] = G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHON);
+            } else {
+                rho[1] = rho[0];
+                rho[2] = rho[0];
+            }
+            const float *ax[3] = {t1, t2, n};
+            const int bits[3] = {0x1000, 0x2000, 0x4000};
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                if (rho[i] > 0.f) {
+                    row_init(r, P.cfm);
+                    r.J[3] = ax[i][0]; r.J[4] = ax[i][1]; r.J[5] = ax[i][2];
+                    if (b1 >= 0) { r.J[9] = -ax[i][0]; r.J[10] = -ax[i][1]; r.J[11] = -ax[i][2]; }
+                    r.lo = -rho[i];
+                    r.hi = rho[i];
+                    emit_fr((mode & bits[i]) != 0);
+                }
+            }
+        }
+        G(P.cmap, c) = (uint32_t)(row | (depmask << 3)) | ((uint32_t)nslot << 8) | ((uint32_t)tslot << 16);
+    }
+    // rows of the step | independent rows << 16 (ODE sweeps [0,nhead) and [nhead,m) as separate partitions)
+    G(P.nrows, 0) = ntail | (nhead_total << 16);
+}
+
+} // namespace
+
+extern "C" size_t b2p_assemble_smem_bytes(int nb) { return sizeof(float) * (size_t)nb * 12 * BD; }
+
+extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, cudaStream_t stream)
+{
+    static size_t configured = 0;
+    const size_t smem = b2p_assemble_smem_bytes(nb);
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(b2p_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int grid = (P->W + BD - 1) / BD;
+    b2p_assemble_kernel<<<grid, BD, smem, stream>>>(*P);
+    return cudaGetLastError();
+}

@@ -13,9 +13,12 @@
 //   crec    float[maxc*16][Wp] the 16-word contact record         (dContact subset)
 //   cfb     float[maxc*3][Wp]  contact feedback f1
 //   seed    uint32[Wp]         per-world LCG state                (dRandSetSeed)
-//   rows    float4[maxrows*4][Wp]  solver scratch A, slot-major: J1l J1a J2a rhs cfm hi Ad - meta -
-//   rowsB   float4[maxrows*4][Wp]  solver scratch B, position-major (rows in sweep order) + lambda
-//   lambda  float[maxrows][Wp] (by slot), invIw float[nb*9][Wp]
+//   nrows   int[Wp]            rows of the last step | independent ("head") rows << 16
+//   rows    float4[maxrows*4][Wp]  constraint rows in ODE's initial sweep order (slot = position at
+//                              iteration 0): 12 mass- and Ad-scaled Jacobian words, rhs', cfm', bound, meta
+//   lambda  float[maxrows][Wp] scaled multipliers by slot;  rowS float[maxrows][Wp]  sqrt(Ad) by slot
+//   fcacc   float[nb*6][Wp]    M^-1/2 J^T lambda after the last sweep;  invIw float[nb*9][Wp]
+//   cmap    uint32[maxc][Wp]   rows | depmask<<3 | slot of the normal row<<8 | first dependent slot<<16
 #pragma once
 #include <stdint.h>
 
@@ -49,6 +52,9 @@ struct DevBody {
     float invI[9];
     int gyroscopic, nogravity, has_max_ang;
     float max_angular_speed;
+    // symmetric square roots (body frame) used by the mass-scaled row form: J~ = J M^-1/2
+    float sqrtInvMass, sqrtMass;
+    float sqrtInvI[9], sqrtI[9];
 };
 
 struct DevJoint {
@@ -96,16 +102,14 @@ struct StepParams {
     float gravity[3];
     float erp, cfm, contact_max_vel, contact_min_depth, sor_w;
     int iters, reorder;
-    float *state, *force, *jcmd, *jobs, *jfb, *crec, *cfb, *lambda, *rowad, *invIw;
-    float4 *rows;  // scratch A: slot-major [slot][4][Wp]
-    float4 *rowsB; // scratch B: position-major [pos][4][Wp] (rows in sweep order)
-    float *lambdaB; // lambda by sweep position [pos][Wp]
-    uint8_t *ord;   // row order [pos][Wp] -> slot
-    uint8_t *jrows;
+    float *state, *force, *jcmd, *jobs, *jfb, *crec, *cfb, *lambda, *rowS, *invIw, *fcacc;
+    float4 *rows;   // [slot][4][Wp], slot = position in ODE's initial order
+    uint32_t *cmap; // [maxc][Wp]
+    uint8_t *jrows; // [nj][Wp]: rows of joint j | (local limit/motor row + 1) << 4
     int *ccount;
     int *nrows;
     uint32_t *seed;
-    long long *phase_cycles; // optional diagnostics: summed clock64 cycles per phase (6 slots), or null
+    int rows_resident; // rows per world the SOR kernel keeps in shared memory (the rest is read from L2)
 };
 
 struct CollideParams {
