@@ -1749,9 +1749,10 @@ int b2p_collide_get_pairs(b2p_arena *a, int world, int *pairs, int max_pairs)
 namespace {
 constexpr size_t kSmemMax = 227 * 1024;
 
-// Rows per world the SOR kernel keeps in shared memory.  All of them if at least two CTAs (64 worlds) still
-// fit on an SM; otherwise as many as fit next to the per-world lambda / order / fch arrays (the rest is
-// read from L2 in place).  b2p_arena_set_resident_rows overrides the choice.
+// Rows per world the SOR kernel keeps in shared memory (one CTA = 16 worlds).  All of them if at least
+// four CTAs (64 worlds) still fit on an SM; otherwise as many as fit next to the per-world lambda / order /
+// fch arrays at that occupancy, but at least half of what a single CTA could hold (the rest is read from L2
+// in place).  b2p_arena_set_resident_rows overrides the choice.
 int pick_rows_resident(const b2p_arena *a, int nb, int maxrows)
 {
     const size_t fixed = b2p_sor_smem_bytes(nb, maxrows, 0), per_row = b2p_sor_smem_bytes(nb, maxrows, 1) - fixed;
@@ -1761,8 +1762,8 @@ int pick_rows_resident(const b2p_arena *a, int nb, int maxrows)
         return (int)std::min<size_t>((size_t)maxrows, (budget - fixed) / per_row);
     };
     if (a->rows_resident > 0) return std::min(std::min(a->rows_resident, maxrows), fit(1));
-    const int r2 = fit(2);
-    return r2 >= maxrows ? r2 : std::max(r2, std::min(fit(1), maxrows) / 2);
+    const int r4 = fit(4);
+    return r4 >= maxrows ? r4 : std::max(r4, std::min(fit(1), maxrows) / 2);
 }
 } // namespace
 

@@ -114,21 +114,24 @@ __device__ __forceinline__ float emit_row(const StepParams &P, const Smem &S, in
     for (int k = 0; k < 12; k++) sum += o[k] * o[k];
     const float Ad = P.sor_w / (sum + cfm);
     const float sa = sqrtf(Ad), rsa = 1.0f / sa;
-    // bound word: 0xFFFFFFFF = [0,+inf), 0xFFFFFFFE = (-inf,0], otherwise [-b,b] with b = hi/sqrt(Ad)
-    // (b = +inf: unbounded); for a friction-dependent row b = mu*sqrt(Ad_n/Ad_f), multiplied by the normal
-    // row's current lam' in the sweep (ODE: hi = |hicopy * lambda[findex]|).
-    float bound;
+    // bound word b: the row is limited to [-b,b] with b = hi/sqrt(Ad) (+inf: unbounded); kind bit 0 / 1
+    // replaces the lower / upper limit by 0 ([0,+inf) and (-inf,0]); for a friction-dependent row (fr != 0)
+    // b = mu*sqrt(Ad_n/Ad_f) is multiplied by the normal row's current lam' in the sweep
+    // (ODE: hi = |hicopy * lambda[findex]|).
+    float bound = r.hi * rsa;
+    int kind = 0;
     if (r.fr) bound = r.hi * r.sn * rsa;
-    else if (r.lo == 0.f && r.hi == INFINITY) bound = __int_as_float(0xFFFFFFFF);
-    else if (r.lo == -INFINITY && r.hi == 0.f) bound = __int_as_float(0xFFFFFFFE);
-    else bound = r.hi * rsa;
-    // meta: body0 | body1<<8 (0xff = one-body row) | fr<<16
-    const int meta = (pc.b0 & 0xff) | ((pc.b1 < 0 ? 0xff : pc.b1) << 8) | (r.fr << 16);
+    else if (r.lo == 0.f && r.hi == INFINITY) bound = INFINITY, kind = 1;
+    else if (r.lo == -INFINITY && r.hi == 0.f) bound = INFINITY, kind = 2;
+    // meta: body0 | body1<<8 (one-body rows name the dummy body nb) | fr<<16 | kind<<24
+    const int meta = (pc.b0 & 0xff) | ((pc.b1 < 0 ? P.T->nb : pc.b1) << 8) | (r.fr << 16) | (kind << 24);
+    // vectors 0,1 = body-0 side (J0..J5, rhs', cfm'); vectors 2,3 = body-1 side, angular part first
+    // (J9 J10 J11 J6 J7 J8, bound, meta): the SOR kernel gives each side of a world its own lane
     float4 *dst = P.rows + (size_t)(slot * 4) * Wp + w;
     dst[0 * (size_t)Wp] = make_float4(sa * o[0], sa * o[1], sa * o[2], sa * o[3]);
-    dst[1 * (size_t)Wp] = make_float4(sa * o[4], sa * o[5], sa * o[6], sa * o[7]);
-    dst[2 * (size_t)Wp] = make_float4(sa * o[8], sa * o[9], sa * o[10], sa * o[11]);
-    dst[3 * (size_t)Wp] = make_float4(sa * rhs, cfm * Ad, bound, __int_as_float(meta));
+    dst[1 * (size_t)Wp] = make_float4(sa * o[4], sa * o[5], sa * rhs, cfm * Ad);
+    dst[2 * (size_t)Wp] = make_float4(sa * o[9], sa * o[10], sa * o[11], sa * o[6]);
+    dst[3 * (size_t)Wp] = make_float4(sa * o[7], sa * o[8], bound, __int_as_float(meta));
     P.rowS[(size_t)slot * Wp + w] = sa;
     return sa;
 }
