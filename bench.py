@@ -241,6 +241,8 @@ def run_b200(args):
         sc = BUILDERS[args.workload](ar, W, world_offset=rank * W)
     if args.resident_rows:
         ar.set_resident_rows(args.resident_rows)
+    if args.register_rows >= 0:
+        ar.set_register_rows(args.register_rows)
     if args.reorder == "none":
         ar.set_reorder_method(capi.REORDER_NONE)
     nb, nj = len(sc["bodies"]), len(sc["joints"])
@@ -397,6 +399,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident-rows", type=int, default=0,
                     help="tuning: constraint rows per world kept in shared memory by the SOR kernel (0 = auto)")
+    ap.add_argument("--register-rows", type=int, default=-1,
+                    help="tuning: sweep positions per world kept in registers by the SOR kernel (-1 = auto)")
     ap.add_argument("--reorder", default="random", choices=["random", "none"],
                     help="SOR row reordering: ODE 0.16 default (random) or REORDERING_METHOD__DONT_REORDER")
     ap.add_argument("--workload", default="D", choices=["B", "C", "D"],

@@ -127,8 +127,10 @@ int b2p_arena_set_stream(b2p_arena *a, void *cuda_stream);
 /* capacity knobs; must be called before the first step */
 int b2p_arena_set_max_contacts(b2p_arena *a, int max_contacts_per_world);
 int b2p_arena_enable_rolling_friction(b2p_arena *a, int on);
-/* tuning: constraint rows per world the SOR kernel keeps in shared memory (0 = automatic) */
+/* tuning of the SOR kernel's on-chip row storage: sweep positions per world kept in shared memory
+ * (0 = automatic: the longest world seen so far) and in registers (multiple of 4 up to 20; < 0 = automatic) */
 int b2p_arena_set_resident_rows(b2p_arena *a, int n);
+int b2p_arena_set_register_rows(b2p_arena *a, int n);
 
 int b2p_world_set_gravity(b2p_arena *a, double x, double y, double z);      /* dWorldSetGravity :194 */
 int b2p_world_set_cfm(b2p_arena *a, double cfm);                            /* dWorldSetCFM :195 */

@@ -53,6 +53,9 @@ class Arena:
     def set_resident_rows(self, n):
         self._check(self.lib.b2p_arena_set_resident_rows(self.h, int(n)))
 
+    def set_register_rows(self, n):
+        self._check(self.lib.b2p_arena_set_register_rows(self.h, int(n)))
+
     def set_gravity(self, x, y, z):
         self._check(self.lib.b2p_world_set_gravity(self.h, x, y, z))
 

@@ -59,6 +59,7 @@ SIGNATURES = {
     "b2p_arena_set_max_contacts": (_I, [_P, _I]),
     "b2p_arena_enable_rolling_friction": (_I, [_P, _I]),
     "b2p_arena_set_resident_rows": (_I, [_P, _I]),
+    "b2p_arena_set_register_rows": (_I, [_P, _I]),
     "b2p_world_set_gravity": (_I, [_P, _D, _D, _D]),
     "b2p_world_set_cfm": (_I, [_P, _D]),
     "b2p_world_set_erp": (_I, [_P, _D]),

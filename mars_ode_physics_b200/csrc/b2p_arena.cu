@@ -22,6 +22,7 @@
 extern "C" size_t b2p_assemble_smem_bytes(int nb);
 extern "C" size_t b2p_integrate_smem_bytes(int nb);
 extern "C" size_t b2p_sor_smem_bytes(int nb, int maxrows, int rows_resident);
+extern "C" int b2p_sor_register_rows(int maxrows, int wanted);
 extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, cudaStream_t stream);
@@ -219,7 +220,9 @@ struct b2p_arena {
     float *d_lambda = nullptr, *d_rowS = nullptr, *d_invIw = nullptr, *d_fcacc = nullptr;
     uint32_t *d_cmap = nullptr;
     size_t scratch_rows = 0, scratch_nb = 0, scratch_maxc = 0;
-    int rows_resident = 0; // 0 = automatic
+    int rows_resident = 0;   // SOR kernel: sweep positions kept in shared memory; 0 = automatic
+    int rows_registers = -1; // SOR kernel: sweep positions kept in registers; < 0 = automatic
+    int *d_hw_rows = nullptr, *h_hw_rows = nullptr; // largest row count of any world so far (device / pinned copy)
     // optional per-kernel timing (bench / profiling): events around the three launches of a step
     bool timing = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -228,6 +231,7 @@ struct b2p_arena {
     int *d_pairs = nullptr, *d_npairs = nullptr;
     int maxpairs = 0;
     int launches = 0;
+    long long steps_done = 0;
     bool stepped = false;
 };
 
@@ -362,6 +366,8 @@ void free_scratch(b2p_arena *a)
     if (a->d_invIw) cudaFree(a->d_invIw);
     if (a->d_fcacc) cudaFree(a->d_fcacc);
     if (a->d_cmap) cudaFree(a->d_cmap);
+    if (a->d_hw_rows) cudaFree(a->d_hw_rows);
+    a->d_hw_rows = nullptr;
     a->d_rows = nullptr;
     a->d_lambda = a->d_rowS = a->d_invIw = a->d_fcacc = nullptr;
     a->d_cmap = nullptr;
@@ -419,7 +425,7 @@ int finalize(b2p_arena *a)
     if (ng > B2P_MAX_GEOMS) return fail(B2P_ECAPACITY, "too many geoms (%d > %d)", ng, B2P_MAX_GEOMS);
     const int rpc = rpc_of(a);
     const int njslots = nj * B2P_ROWS_PER_JOINT, maxrows = njslots + a->maxc * rpc;
-    if (maxrows > 255) return fail(B2P_ECAPACITY, "too many constraint rows per world (%d > 255)", maxrows);
+    if (maxrows > 253) return fail(B2P_ECAPACITY, "too many constraint rows per world (%d > 253)", maxrows);
     if (a->tmpl_dirty) {
         std::vector<char> buf(sizeof(DevTemplate), 0);
         DevTemplate *T = reinterpret_cast<DevTemplate *>(buf.data());
@@ -563,6 +569,10 @@ int finalize(b2p_arena *a)
         CUDA_TRY(cudaMalloc(&a->d_invIw, sizeof(float) * (size_t)std::max(nb, 1) * 9 * Wp));
         CUDA_TRY(cudaMalloc(&a->d_fcacc, sizeof(float) * (size_t)std::max(nb, 1) * 6 * Wp));
         CUDA_TRY(cudaMalloc(&a->d_cmap, sizeof(uint32_t) * (size_t)std::max(a->maxc, 1) * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_hw_rows, sizeof(int)));
+        CUDA_TRY(cudaMemsetAsync(a->d_hw_rows, 0, sizeof(int), a->stream));
+        if (!a->h_hw_rows) CUDA_TRY(cudaMallocHost(&a->h_hw_rows, sizeof(int)));
+        *a->h_hw_rows = 0;
         // padded worlds (w >= W) and unused slots are read but never used: keep them finite
         CUDA_TRY(cudaMemsetAsync(a->d_rows, 0, sizeof(float4) * mr * 4 * Wp, a->stream));
         CUDA_TRY(cudaMemsetAsync(a->d_lambda, 0, sizeof(float) * mr * Wp, a->stream));
@@ -754,6 +764,7 @@ void b2p_arena_destroy(b2p_arena *a)
     if (a->d_hf) cudaFree(a->d_hf);
     if (a->d_pairs) cudaFree(a->d_pairs);
     if (a->d_npairs) cudaFree(a->d_npairs);
+    if (a->h_hw_rows) cudaFreeHost(a->h_hw_rows);
     delete a;
 }
 
@@ -1749,21 +1760,20 @@ int b2p_collide_get_pairs(b2p_arena *a, int world, int *pairs, int max_pairs)
 namespace {
 constexpr size_t kSmemMax = 227 * 1024;
 
-// Rows per world the SOR kernel keeps in shared memory (one CTA = 16 worlds).  All of them if at least
-// four CTAs (64 worlds) still fit on an SM; otherwise as many as fit next to the per-world lambda / order /
-// fch arrays at that occupancy, but at least half of what a single CTA could hold (the rest is read from L2
-// in place).  b2p_arena_set_resident_rows overrides the choice.
-int pick_rows_resident(const b2p_arena *a, int nb, int maxrows)
+// Sweep positions per world the SOR kernel keeps in shared memory behind the `kr` positions it keeps in
+// registers (one CTA = 16 worlds, 1 KB per position).  Enough for the longest world seen so far (the assemble
+// kernel maintains that high-water mark; before the first step the scene's bound `maxrows` is used), capped by
+// what one CTA can hold; positions beyond are read from L2 in place, so a stale mark costs time, not
+// correctness.  b2p_arena_set_resident_rows overrides the choice.
+int pick_rows_resident(const b2p_arena *a, int nb, int maxrows, int kr)
 {
     const size_t fixed = b2p_sor_smem_bytes(nb, maxrows, 0), per_row = b2p_sor_smem_bytes(nb, maxrows, 1) - fixed;
-    auto fit = [&](int ctas) -> int {
-        const size_t budget = kSmemMax / ctas - 1024;
-        if (budget <= fixed) return 0;
-        return (int)std::min<size_t>((size_t)maxrows, (budget - fixed) / per_row);
-    };
-    if (a->rows_resident > 0) return std::min(std::min(a->rows_resident, maxrows), fit(1));
-    const int r4 = fit(4);
-    return r4 >= maxrows ? r4 : std::max(r4, std::min(fit(1), maxrows) / 2);
+    const int cap = kSmemMax - 1024 > fixed ? (int)((kSmemMax - 1024 - fixed) / per_row) : 0;
+    const int rest = std::max(maxrows - kr, 0);
+    if (a->rows_resident > 0) return std::min(std::min(a->rows_resident, rest), cap);
+    const int seen = a->h_hw_rows ? *(volatile int *)a->h_hw_rows : 0;
+    const int want = seen > 0 ? std::min(std::max(seen - kr, 0), rest) : rest;
+    return std::min(want, cap);
 }
 } // namespace
 
@@ -1807,7 +1817,9 @@ int b2p_step(b2p_arena *a, double step_size)
     P.seed = a->seed.dev;
     const int nb = (int)a->bodies.size();
     const int maxrows = (int)a->joints.size() * B2P_ROWS_PER_JOINT + a->maxc * rpc_of(a);
-    P.rows_resident = pick_rows_resident(a, nb, maxrows);
+    P.rows_registers = b2p_sor_register_rows(maxrows, a->rows_registers);
+    P.rows_resident = pick_rows_resident(a, nb, maxrows, P.rows_registers);
+    P.hw_rows = a->d_hw_rows;
     if (b2p_assemble_smem_bytes(nb) > kSmemMax || b2p_integrate_smem_bytes(nb) > kSmemMax ||
         b2p_sor_smem_bytes(nb, maxrows, P.rows_resident) > kSmemMax)
         return fail(B2P_ECAPACITY, "scene needs more than %zu bytes of shared memory per CTA", kSmemMax);
@@ -1817,6 +1829,10 @@ int b2p_step(b2p_arena *a, double step_size)
     CUDA_TRY(b2p_launch_sor(&P, nb, maxrows, a->stream));
     if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[2], a->stream));
     CUDA_TRY(b2p_launch_integrate(&P, nb, a->stream));
+    // refresh the host copy of the row high-water mark (every step at first, then occasionally)
+    if (a->steps_done < 8 || (a->steps_done & 31) == 0)
+        CUDA_TRY(cudaMemcpyAsync(a->h_hw_rows, a->d_hw_rows, sizeof(int), cudaMemcpyDeviceToHost, a->stream));
+    a->steps_done++;
     a->launches += 3;
     if (a->timing) {
         CUDA_TRY(cudaEventRecord(a->ev[3], a->stream));
@@ -1864,6 +1880,13 @@ int b2p_arena_set_resident_rows(b2p_arena *a, int n)
 {
     if (!a || n < 0) return fail(B2P_EINVAL, "bad resident row count");
     a->rows_resident = n;
+    return 0;
+}
+
+int b2p_arena_set_register_rows(b2p_arena *a, int n)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    a->rows_registers = n;
     return 0;
 }
 

@@ -123,15 +123,18 @@ __device__ __forceinline__ float emit_row(const StepParams &P, const Smem &S, in
     if (r.fr) bound = r.hi * r.sn * rsa;
     else if (r.lo == 0.f && r.hi == INFINITY) bound = INFINITY, kind = 1;
     else if (r.lo == -INFINITY && r.hi == 0.f) bound = INFINITY, kind = 2;
-    // meta: body0 | body1<<8 (one-body rows name the dummy body nb) | fr<<16 | kind<<24
-    const int meta = (pc.b0 & 0xff) | ((pc.b1 < 0 ? P.T->nb : pc.b1) << 8) | (r.fr << 16) | (kind << 24);
-    // vectors 0,1 = body-0 side (J0..J5, rhs', cfm'); vectors 2,3 = body-1 side, angular part first
-    // (J9 J10 J11 J6 J7 J8, bound, meta): the SOR kernel gives each side of a world its own lane
+    // meta: own slot | slot of the multiplier the bound follows << 8 (slot maxrows + 1 holds the constant 1 for
+    // rows with a fixed bound) | body0 << 16 | body1 << 24 (one-body rows name the dummy body nb) | kind << 30
+    const int R = P.T->maxrows;
+    const uint32_t meta = (uint32_t)slot | ((uint32_t)(r.fr ? r.fr - 1 : R + 1) << 8) | ((uint32_t)pc.b0 << 16) |
+                          ((uint32_t)(pc.b1 < 0 ? P.T->nb : pc.b1) << 24) | ((uint32_t)kind << 30);
+    // A = body-0 side (J0..J5), B = body-1 side, angular part first (J9 J10 J11 J6 J7 J8): the SOR kernel gives
+    // each side of a world its own lane.  Vectors: A0..A3 | A4 A5 B0 B1 | B2..B5 | rhs' cfm' bound meta
     float4 *dst = P.rows + (size_t)(slot * 4) * Wp + w;
     dst[0 * (size_t)Wp] = make_float4(sa * o[0], sa * o[1], sa * o[2], sa * o[3]);
-    dst[1 * (size_t)Wp] = make_float4(sa * o[4], sa * o[5], sa * rhs, cfm * Ad);
-    dst[2 * (size_t)Wp] = make_float4(sa * o[9], sa * o[10], sa * o[11], sa * o[6]);
-    dst[3 * (size_t)Wp] = make_float4(sa * o[7], sa * o[8], bound, __int_as_float(meta));
+    dst[1 * (size_t)Wp] = make_float4(sa * o[4], sa * o[5], sa * o[9], sa * o[10]);
+    dst[2 * (size_t)Wp] = make_float4(sa * o[11], sa * o[6], sa * o[7], sa * o[8]);
+    dst[3 * (size_t)Wp] = make_float4(sa * rhs, cfm * Ad, bound, __uint_as_float(meta));
     P.rowS[(size_t)slot * Wp + w] = sa;
     return sa;
 }
@@ -715,6 +718,9 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
     }
     // rows of the step | independent rows << 16 (ODE sweeps [0,nhead) and [nhead,m) as separate partitions)
     G(P.nrows, 0) = ntail | (nhead_total << 16);
+    // high-water mark of rows per world: the host sizes the SOR kernel's on-chip row storage with it
+    const int wmax = __reduce_max_sync(__activemask(), ntail);
+    if ((tid & 31) == 0 && wmax > *(volatile int *)P.hw_rows) atomicMax(P.hw_rows, wmax);
 }
 
 } // namespace

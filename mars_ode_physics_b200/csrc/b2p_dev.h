@@ -15,7 +15,8 @@
 //   seed    uint32[Wp]         per-world LCG state                (dRandSetSeed)
 //   nrows   int[Wp]            rows of the last step | independent ("head") rows << 16
 //   rows    float4[maxrows*4][Wp]  constraint rows in ODE's initial sweep order (slot = position at
-//                              iteration 0): 12 mass- and Ad-scaled Jacobian words, rhs', cfm', bound, meta
+//                              iteration 0): 12 mass- and Ad-scaled Jacobian words (body-0 side J0..J5, then
+//                              body-1 side J9 J10 J11 J6 J7 J8), rhs', cfm', bound, meta
 //   lambda  float[maxrows][Wp] scaled multipliers by slot;  rowS float[maxrows][Wp]  sqrt(Ad) by slot
 //   fcacc   float[nb*6][Wp]    M^-1/2 J^T lambda after the last sweep;  invIw float[nb*9][Wp]
 //   cmap    uint32[maxc][Wp]   rows | depmask<<3 | slot of the normal row<<8 | first dependent slot<<16
@@ -109,7 +110,9 @@ struct StepParams {
     int *ccount;
     int *nrows;
     uint32_t *seed;
-    int rows_resident; // rows per world the SOR kernel keeps in shared memory (the rest is read from L2)
+    int rows_registers; // sweep positions per world the SOR kernel keeps in registers (0, 4, ... 20)
+    int rows_resident;  // further positions it keeps in shared memory (the rest is read from L2 in place)
+    int *hw_rows;       // device counter: largest row count of any world so far
 };
 
 struct CollideParams {

@@ -1,5 +1,5 @@
 // b2p_sor.cu -- kernel 2 of the step: the SOR-LCP sweeps of dWorldQuickStep with every row of a world
-// resident in shared memory (sm_100a).
+// resident on chip, the first KR sweep positions in registers and the rest in shared memory (sm_100a).
 //
 // What it computes: ODE 0.16 quickstep.cpp SOR_LCP as the reference reaches it through
 // dWorldQuickStep (src/WorldPhysics.cpp:365): `iters` projected Gauss-Seidel sweeps over the m rows of
@@ -10,22 +10,33 @@
 //
 // Mapping: two threads per world (lane 2v = body-0 side of world v, lane 2v+1 = body-1 side), one warp
 // (= one CTA) per 16 consecutive worlds.  Gauss-Seidel is sequential inside a world and every world follows
-// its own row order (contact counts and RNG histories differ), so the parallelism is across worlds; the
-// throughput of the kernel is (worlds resident per SM) / (latency of one row-iteration), which is why a
-// world gets two lanes (half the instructions on the dependent chain, twice the warps for the same
-// shared-memory footprint) and why the rows are kept to 64 bytes.
+// its own row order (contact counts and RNG histories differ), so the parallelism is across worlds and the
+// throughput of the kernel is (worlds resident per SM) / (latency of one row-iteration).  Both factors are
+// limited by where the rows live, hence:
+//   * rows are held PHYSICALLY in sweep order.  The order only changes three times per step (identity at
+//     iteration 0, ODE's reshuffles at 8 and 16); at those points every lane re-gathers its half of each
+//     row from the slot-ordered rows in global memory (L2 hits after the first pass).  Inside the sweeps
+//     nothing is indexed by the order any more;
+//   * sweep positions [0,KR) of every world sit in registers (10 per row and lane: six Jacobian words, rhs',
+//     cfm', bound, meta) -- the loop over them is fully unrolled, so the "row fetch" costs no instruction.
+//     The register file (64 K x 32 bit per SM) is larger than shared memory; using both doubles the worlds
+//     an SM can hold compared to rows in shared memory only;
+//   * positions [KR, KR+Rs) sit in shared memory ([position][4][16 worlds] float4, cp.async-gathered);
+//     positions beyond that (worlds with unusually many contacts) are read from global memory in place;
+//   * positions m..mmax-1 of a world with fewer rows than its warp's longest world hold an all-zero row
+//     that points at a dummy multiplier and the dummy body: the sweep is branch- and predicate-free.
 // Shared memory per CTA, every access conflict-free whatever row or body each world is at:
-//     rows  float4[Rs][2][32]   row r: lane L reads vectors (r*2+0)*32+L and (r*2+1)*32+L = its side's six
-//                               Jacobian words + two of the four scalars (cp.async from the assemble
-//                               kernel's [slot][4][Wp] layout, 256 contiguous bytes per side and vector)
-//     lam   float [R][16]       multipliers by slot (also read by friction rows through findex)
-//     fch   float [(nb+1)*6][16] M^-1/2 J^T lambda (+ a dummy body that one-body rows name as body 1);
-//                               side 1 walks the six components angular-first, so the two sides of a warp
-//                               instruction always hit different bank halves
-//     ord   uint8 [R][16]       the world's current row order
-// Rows beyond Rs (worlds with unusually many contacts) are read from global memory (L2) in place.
-// HBM traffic is one read of the rows (64 B each) and one write of lam and fch: the sweeps themselves
-// run out of shared memory.
+//     rows  float4[Rs][4][16]     granule g of position p: A0..A3 | A4 A5 B0 B1 | B2..B5 | rhs' cfm' bound meta
+//                                 (A = body-0 side, B = body-1 side angular part first); a lane reads its six
+//                                 words with three 8-byte loads and the scalars with one 16-byte broadcast load
+//     lam   float [R+2][16]       multipliers by slot; slot R = dummy (zero rows), slot R+1 = constant 1 (the
+//                                 "normal multiplier" of rows whose bound does not follow another row)
+//     fch   float4[(nb+1)*2][16]  M^-1/2 J^T lambda: (lin xyz, -) and (ang xyz, -) per body, + the dummy body
+//                                 one-body rows name as body 1; vector j of world v sits at column v ^ 4j and
+//                                 side 1 reads the angular vector first, so the two lanes of a world never
+//                                 meet in a bank
+//     ord   uint8 [R][16]         the world's current row order (position -> slot)
+// HBM traffic is one read of the rows (64 B each) and one write of lam and fch.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -46,22 +57,24 @@ __device__ __forceinline__ void cp_async_commit_wait_all()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// This lane's view of one row: its side's six Jacobian words (side 1: angular first) and the four scalars
-struct RowRegs {
+// This lane's view of one row: its side's six Jacobian words (side 1: angular first) and the four scalars.
+// meta (written by b2p_assemble.cu emit_row): own slot | slot of the multiplier the bound follows << 8 |
+// body 0 << 16 | body 1 << 24 | "lower bound is 0" << 30 | "upper bound is 0" << 31
+struct Row {
     float j0, j1, j2, j3, j4, j5;
     float rhs, cfm, bound;
-    int meta;
+    uint32_t meta;
 };
 
-template <bool SPILL> __global__ void __launch_bounds__(32) b2p_sor_kernel(const StepParams P)
+template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const StepParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevTemplate *__restrict__ T = P.T;
     const int nb = T->nb, R = T->maxrows, Rs = P.rows_resident;
     float4 *const s_rows = (float4 *)smem_raw;
-    float *const s_lam = (float *)(s_rows + (size_t)Rs * 2 * 32);
-    float *const s_fc = s_lam + (size_t)R * WL;
-    uint8_t *const s_ord = (uint8_t *)(s_fc + (size_t)(nb + 1) * 6 * WL);
+    float4 *const s_fc = s_rows + (size_t)Rs * 4 * WL;
+    float *const s_lam = (float *)(s_fc + (size_t)(nb + 1) * 2 * WL);
+    uint8_t *const s_ord = (uint8_t *)(s_lam + (size_t)(R + 2) * WL);
 
     const int lane = threadIdx.x, v = lane >> 1, side = lane & 1;
     const int w = blockIdx.x * WL + v; // < Wp (padded worlds have no rows)
@@ -69,82 +82,122 @@ template <bool SPILL> __global__ void __launch_bounds__(32) b2p_sor_kernel(const
     const int nr = w < P.W ? P.nrows[w] : 0;
     const int m = nr & 0xffff, nhead = nr >> 16;
     const int mmax = __reduce_max_sync(0xffffffffu, m);
+    const uint32_t zero_meta = (uint32_t)R | ((uint32_t)(R + 1) << 8) | ((uint32_t)nb << 16) | ((uint32_t)nb << 24);
 
-    // rows -> shared memory (asynchronously, while lam / fch / ord are initialised)
-    {
-        const int nload = mmax < Rs ? mmax : Rs;
-        const float4 *src = P.rows + (size_t)(side * 2) * Wp + w;
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rows + lane);
-        for (int r = 0; r < nload; r++) {
-            cp_async16(dst + (uint32_t)((r * 2 + 0) * 32 * 16), src + (size_t)(r * 4 + 0) * Wp);
-            cp_async16(dst + (uint32_t)((r * 2 + 1) * 32 * 16), src + (size_t)(r * 4 + 1) * Wp);
-        }
-    }
-    for (int s = side; s < R; s += 2) {
-        s_lam[s * WL + v] = 0.f;
-        s_ord[s * WL + v] = (uint8_t)s;
-    }
-    for (int k = side; k < (nb + 1) * 6; k += 2) s_fc[k * WL + v] = 0.f;
+    for (int s = side; s < R + 2; s += 2) s_lam[s * WL + v] = s == R + 1 ? 1.f : 0.f;
+    for (int s = side; s < R; s += 2) s_ord[s * WL + v] = (uint8_t)s;
+    for (int k = side; k < (nb + 1) * 2; k += 2) s_fc[k * WL + v] = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t seed = P.seed[w];
-    cp_async_commit_wait_all();
     __syncwarp();
 
-    auto fetch = [&](int r) -> RowRegs {
-        float4 h0, h1;
-        if (!SPILL || r < Rs) {
-            const float4 *p = s_rows + (size_t)(r * 2) * 32 + lane;
-            h0 = p[0];
-            h1 = p[32];
-        } else {
-            const float4 *p = P.rows + (size_t)(r * 4 + side * 2) * Wp + w;
-            h0 = p[0];
-            h1 = p[Wp];
-        }
-        // the four scalars sit two per side: swap them between the lanes of the pair
-        const float oz = __shfl_xor_sync(0xffffffffu, h1.z, 1), ow = __shfl_xor_sync(0xffffffffu, h1.w, 1);
-        RowRegs q;
-        q.j0 = h0.x, q.j1 = h0.y, q.j2 = h0.z, q.j3 = h0.w, q.j4 = h1.x, q.j5 = h1.y;
-        q.rhs = side ? oz : h1.z;
-        q.cfm = side ? ow : h1.w;
-        q.bound = side ? h1.z : oz;
-        q.meta = __float_as_int(side ? h1.w : ow);
+    // ---- this lane's addresses
+    float *const lamL = s_lam + v;
+    // fch vector j of body b, world v: s_fc[(b*2 + j)*16 + (v ^ 4j)]; this lane reads vector `side` first
+    float4 *const fcF = s_fc + side * WL + (v ^ (side << 2));
+    float4 *const fcS = s_fc + (side ^ 1) * WL + (v ^ ((side ^ 1) << 2));
+    const int bshift = 16 + 8 * side;
+    // 8-byte granules of this side inside a shared-memory row block (float2 units): words side*6 + {0,2,4}
+    const int w0 = side * 6;
+    const int o0 = ((w0 >> 2) * WL + v) * 2 + ((w0 >> 1) & 1);
+    const int o1 = (((w0 + 2) >> 2) * WL + v) * 2 + (((w0 + 2) >> 1) & 1);
+    const int o2 = (((w0 + 4) >> 2) * WL + v) * 2 + (((w0 + 4) >> 1) & 1);
+
+    auto zero_row = [&]() -> Row {
+        Row q;
+        q.j0 = q.j1 = q.j2 = q.j3 = q.j4 = q.j5 = 0.f;
+        q.rhs = q.cfm = q.bound = 0.f;
+        q.meta = zero_meta;
         return q;
     };
-    // byte offsets of this lane's six fch components relative to its body's first word: side 0 walks
-    // 0..5, side 1 walks 3,4,5,0,1,2 (other bank half)
-    const int offA = side ? 3 * WL : 0, offB = side ? -3 * WL : 0;
-    const int bshift = side * 8;
+    // this lane's half of the row in slot `slot` of its world, from the slot-ordered rows in global memory
+    auto gload = [&](int slot) -> Row {
+        const float4 *p = P.rows + (size_t)(slot * 4 + side) * Wp + w;
+        const float4 vA = __ldg(p), vB = __ldg(p + Wp);
+        const float4 v3 = __ldg(P.rows + (size_t)(slot * 4 + 3) * Wp + w);
+        Row q;
+        q.j0 = side ? vA.z : vA.x;
+        q.j1 = side ? vA.w : vA.y;
+        q.j2 = side ? vB.x : vA.z;
+        q.j3 = side ? vB.y : vA.w;
+        q.j4 = side ? vB.z : vB.x;
+        q.j5 = side ? vB.w : vB.y;
+        q.rhs = v3.x;
+        q.cfm = v3.y;
+        q.bound = v3.z;
+        q.meta = (uint32_t)__float_as_int(v3.w);
+        return q;
+    };
+    // position p - KR of the shared-memory rows
+    auto sload = [&](int p) -> Row {
+        const float2 *b2 = (const float2 *)(s_rows + (size_t)p * 4 * WL);
+        const float2 a = b2[o0], b = b2[o1], c = b2[o2];
+        const float4 s4 = s_rows[(size_t)(p * 4 + 3) * WL + v];
+        Row q;
+        q.j0 = a.x, q.j1 = a.y, q.j2 = b.x, q.j3 = b.y, q.j4 = c.x, q.j5 = c.y;
+        q.rhs = s4.x, q.cfm = s4.y, q.bound = s4.z;
+        q.meta = (uint32_t)__float_as_int(s4.w);
+        return q;
+    };
+
     // One row-iteration (ODE quickstep.cpp SOR_LCP inner loop, in the scaled coordinates).  Branch-free:
-    // one-body rows name the dummy body nb (its fch stays 0 because their second Jacobian half is 0), and
-    // the bound shapes are selected, not branched on.  Both lanes of a pair compute identical lambdas.
-    auto relax = [&](const RowRegs &q, int r, bool active) {
-        const int b = (q.meta >> bshift) & 0xff, fr = (q.meta >> 16) & 0xff;
-        float *fA = s_fc + (size_t)(b * 6) * WL + v + offA;
-        float *fB = fA + (offB - offA) + 3 * WL;
-        float *lp = s_lam + r * WL + v;
-        const float lam_n = s_lam[(fr ? fr - 1 : r) * WL + v];
-        const float lam_old = *lp;
-        const float x0 = fA[0], x1 = fA[WL], x2 = fA[2 * WL], x3 = fB[0], x4 = fB[WL], x5 = fB[2 * WL];
-        const float d = (q.j0 * x0 + q.j1 * x1 + q.j2 * x2) + (q.j3 * x3 + q.j4 * x4 + q.j5 * x5);
+    // one-body rows name the dummy body nb (its fch stays 0 because their second Jacobian half is 0), rows
+    // whose bound is fixed read the constant-1 multiplier, and the bound shapes are selected, not branched
+    // on.  Both lanes of a pair compute identical lambdas.
+    auto relax = [&](const Row &q) {
+        const uint32_t mt = q.meta;
+        float *lp = lamL + (mt & 0xff) * WL;
+        const float *ln = lamL + ((mt >> 8) & 0xff) * WL;
+        const int b = (mt >> bshift) & 0x3f;
+        float4 *pF = fcF + b * (2 * WL), *pS = fcS + b * (2 * WL);
+        float4 F = *pF, S = *pS;
+        const float lam_old = *lp, lam_n = *ln;
+        const float d = (q.j0 * F.x + q.j1 * F.y + q.j2 * F.z) + (q.j3 * S.x + q.j4 * S.y + q.j5 * S.z);
         const float dot = d + __shfl_xor_sync(0xffffffffu, d, 1);
         float delta = (q.rhs - lam_old * q.cfm) - dot;
-        // meta bits 24/25: lower / upper bound is 0 (ODE lo = 0 / hi = 0); fr: bound follows the normal row
-        const float bnd = fr ? fabsf(q.bound * lam_n) : q.bound;
-        const float hi_act = (q.meta & (2 << 24)) ? 0.f : bnd;
-        const float lo_act = (q.meta & (1 << 24)) ? 0.f : -bnd;
+        const float bnd = fabsf(q.bound * lam_n);
+        const float hi_act = (mt & 0x80000000u) ? 0.f : bnd;
+        const float lo_act = (mt & 0x40000000u) ? 0.f : -bnd;
         const float un = lam_old + delta;
         const float nl = fminf(fmaxf(un, lo_act), hi_act);
         delta = (nl == un) ? delta : nl - lam_old;
-        if (active) {
-            *lp = nl;
-            fA[0] = x0 + delta * q.j0;
-            fA[WL] = x1 + delta * q.j1;
-            fA[2 * WL] = x2 + delta * q.j2;
-            fB[0] = x3 + delta * q.j3;
-            fB[WL] = x4 + delta * q.j4;
-            fB[2 * WL] = x5 + delta * q.j5;
-        }
+        *lp = nl;
+        F.x += delta * q.j0, F.y += delta * q.j1, F.z += delta * q.j2;
+        S.x += delta * q.j3, S.y += delta * q.j4, S.z += delta * q.j5;
+        *pF = F;
+        *pS = S;
     };
+
+    Row rr[KR > 0 ? KR : 1];
+    const int ks = mmax < KR + Rs ? mmax : KR + Rs; // end of the shared-memory positions
+
+    // (re)load every on-chip row in the current order
+    auto load_rows = [&]() {
+#pragma unroll
+        for (int k = 0; k < KR; k++) {
+            if ((k & ~3) < mmax) { // whole groups of four: the sweep skips register positions by group
+                const int slot = s_ord[(k < R ? k : 0) * WL + v];
+                rr[k] = k < m ? gload(slot) : zero_row();
+            }
+        }
+        // lane (v, side) copies granules 2*side and 2*side + 1 of its world's rows
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rows + (side * 2) * WL + v);
+        for (int k = KR; k < ks; k++) {
+            const uint32_t d = dst + (uint32_t)((k - KR) * 4 * WL * 16);
+            if (k < m) {
+                const int slot = s_ord[k * WL + v];
+                const float4 *src = P.rows + (size_t)(slot * 4 + side * 2) * Wp + w;
+                cp_async16(d, src);
+                cp_async16(d + WL * 16, src + Wp);
+            } else {
+                float4 *z = s_rows + (size_t)((k - KR) * 4 + side * 2) * WL + v;
+                z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                z[WL] = make_float4(0.f, 0.f, 0.f, side ? __int_as_float((int)zero_meta) : 0.f);
+            }
+        }
+        cp_async_commit_wait_all();
+        __syncwarp();
+    };
+    if (mmax > 0) load_rows();
 
     for (int it = 0; it < (mmax > 0 ? P.iters : 0); it++) {
         if (P.reorder == 0 && it >= 8 && (it & 7) == 0) {
@@ -161,30 +214,46 @@ template <bool SPILL> __global__ void __launch_bounds__(32) b2p_sor_kernel(const
                 for (int idx = nhead + 1; idx < m; idx++) swap(idx, rand_int(seed, idx - nhead + 1) + nhead);
             }
             __syncwarp();
+            load_rows();
         }
-        // Software pipeline over sweep positions, two per trip so that the row registers ping-pong without
-        // moves: the row of position k+1 and the order byte of position k+2 are fetched before row k is
-        // relaxed (neither depends on the sequential fch / lam state).  Positions >= m of a world read
-        // order byte 0 (harmless) and are computed but not stored.
-        RowRegs qa, qb;
-        int ra = s_ord[v], rb = s_ord[(1 < R ? 1 : 0) * WL + v];
-        qa = fetch(ra);
+        // positions in registers
+#pragma unroll
+        for (int g = 0; g < KR; g += 4) {
+            if (g < mmax) {
+#pragma unroll
+                for (int k = g; k < g + 4 && k < KR; k++) relax(rr[k]);
+            }
+        }
+        // positions in shared memory, software-pipelined two per trip (the fetch of the next row does not
+        // depend on the sequential fch / lam state)
+        if (KR < ks) {
+            Row qa = sload(0), qb;
 #pragma unroll 1
-        for (int k = 0; k < mmax; k += 2) {
-            const int rc = s_ord[(k + 2 < R ? k + 2 : 0) * WL + v];
-            qb = fetch(rb);
-            relax(qa, ra, k < m);
-            const int rd = s_ord[(k + 3 < R ? k + 3 : 0) * WL + v];
-            qa = fetch(rc);
-            if (k + 1 < mmax) relax(qb, rb, k + 1 < m); // (rows >= mmax were never loaded)
-            ra = rc;
-            rb = rd;
+            for (int p = 0; p < ks - KR; p += 2) {
+                qb = sload(p + 1 < Rs ? p + 1 : 0);
+                relax(qa);
+                qa = sload(p + 2 < Rs ? p + 2 : 0);
+                if (p + 1 < ks - KR) relax(qb);
+            }
+        }
+        // positions that did not fit on chip: read in place (L2)
+#pragma unroll 1
+        for (int k = KR + Rs; k < mmax; k++) {
+            const Row q = k < m ? gload(s_ord[k * WL + v]) : zero_row();
+            relax(q);
         }
     }
 
     if (w < P.W) {
         for (int s = side; s < m; s += 2) P.lambda[(size_t)s * Wp + w] = s_lam[s * WL + v];
-        for (int k = side; k < nb * 6; k += 2) P.fcacc[(size_t)k * Wp + w] = s_fc[k * WL + v];
+        for (int k = side; k < nb * 2; k += 2) {
+            const int b = k >> 1, j = k & 1;
+            const float4 f = s_fc[(b * 2 + j) * WL + (v ^ (j << 2))];
+            float *dst = P.fcacc + (size_t)(b * 6 + j * 3) * Wp + w;
+            dst[0] = f.x;
+            dst[Wp] = f.y;
+            dst[2 * Wp] = f.z;
+        }
         if (side == 0) P.seed[w] = seed;
     }
 }
@@ -193,23 +262,41 @@ template <bool SPILL> __global__ void __launch_bounds__(32) b2p_sor_kernel(const
 
 extern "C" size_t b2p_sor_smem_bytes(int nb, int maxrows, int rows_resident)
 {
-    size_t s = sizeof(float4) * (size_t)rows_resident * 2 * 32;
-    s += sizeof(float) * (size_t)maxrows * WL;
-    s += sizeof(float) * (size_t)(nb + 1) * 6 * WL;
+    size_t s = sizeof(float4) * (size_t)rows_resident * 4 * WL;
+    s += sizeof(float4) * (size_t)(nb + 1) * 2 * WL;
+    s += sizeof(float) * (size_t)(maxrows + 2) * WL;
     s += (size_t)maxrows * WL;
     return (s + 15) & ~(size_t)15;
 }
 
+// Sweep positions the kernel keeps in registers for a scene with at most `maxrows` rows per world.
+extern "C" int b2p_sor_register_rows(int maxrows, int wanted)
+{
+    int kr = wanted >= 0 ? wanted : 16;
+    if (kr > maxrows) kr = (maxrows + 3) & ~3;
+    kr &= ~3;
+    return kr > 20 ? 20 : kr;
+}
+
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream)
 {
-    static size_t configured[2] = {0, 0};
+    static size_t configured[6] = {0, 0, 0, 0, 0, 0};
     const size_t smem = b2p_sor_smem_bytes(nb, maxrows, P->rows_resident);
-    const bool spill = P->rows_resident < maxrows;
-    auto kern = spill ? b2p_sor_kernel<true> : b2p_sor_kernel<false>;
-    if (smem > configured[spill]) {
+    void (*kern)(const StepParams) = nullptr;
+    switch (P->rows_registers) {
+    case 0: kern = b2p_sor_kernel<0>; break;
+    case 4: kern = b2p_sor_kernel<4>; break;
+    case 8: kern = b2p_sor_kernel<8>; break;
+    case 12: kern = b2p_sor_kernel<12>; break;
+    case 16: kern = b2p_sor_kernel<16>; break;
+    case 20: kern = b2p_sor_kernel<20>; break;
+    default: return cudaErrorInvalidValue;
+    }
+    const int ci = P->rows_registers / 4;
+    if (smem > configured[ci]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[spill] = smem;
+        configured[ci] = smem;
     }
     const int grid = (P->W + WL - 1) / WL;
     kern<<<grid, 32, smem, stream>>>(*P);
