@@ -563,7 +563,7 @@ int finalize(b2p_arena *a)
     if (a->scratch_rows != (size_t)maxrows || a->scratch_nb != (size_t)nb || a->scratch_maxc != (size_t)a->maxc) {
         free_scratch(a);
         const size_t mr = (size_t)std::max(maxrows, 1), Wp = (size_t)a->Wp;
-        CUDA_TRY(cudaMalloc(&a->d_rows, sizeof(float4) * mr * 4 * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_rows, sizeof(float4) * (mr + 1) * 4 * Wp));
         CUDA_TRY(cudaMalloc(&a->d_lambda, sizeof(float) * mr * Wp));
         CUDA_TRY(cudaMalloc(&a->d_rowS, sizeof(float) * mr * Wp));
         CUDA_TRY(cudaMalloc(&a->d_invIw, sizeof(float) * (size_t)std::max(nb, 1) * 9 * Wp));
@@ -574,7 +574,20 @@ int finalize(b2p_arena *a)
         if (!a->h_hw_rows) CUDA_TRY(cudaMallocHost(&a->h_hw_rows, sizeof(int)));
         *a->h_hw_rows = 0;
         // padded worlds (w >= W) and unused slots are read but never used: keep them finite
-        CUDA_TRY(cudaMemsetAsync(a->d_rows, 0, sizeof(float4) * mr * 4 * Wp, a->stream));
+        CUDA_TRY(cudaMemsetAsync(a->d_rows, 0, sizeof(float4) * (mr + 1) * 4 * Wp, a->stream));
+        {
+            // slot maxrows: the all-zero row the SOR kernel puts behind the last row of a world.  Its meta names
+            // the dummy multiplier (slot maxrows), the constant-1 multiplier (maxrows + 1) and the dummy body nb
+            const uint32_t zm = (uint32_t)maxrows | ((uint32_t)(maxrows + 1) << 8) | ((uint32_t)nb << 16) |
+                                ((uint32_t)nb << 24);
+            std::vector<float4> z(Wp);
+            float mf;
+            memcpy(&mf, &zm, sizeof(mf));
+            for (float4 &q : z) q = make_float4(0.f, 0.f, 0.f, mf);
+            CUDA_TRY(cudaMemcpyAsync(a->d_rows + ((size_t)maxrows * 4 + 3) * Wp, z.data(), sizeof(float4) * Wp,
+                                     cudaMemcpyHostToDevice, a->stream));
+            CUDA_TRY(cudaStreamSynchronize(a->stream));
+        }
         CUDA_TRY(cudaMemsetAsync(a->d_lambda, 0, sizeof(float) * mr * Wp, a->stream));
         a->scratch_rows = (size_t)maxrows;
         a->scratch_nb = (size_t)nb;

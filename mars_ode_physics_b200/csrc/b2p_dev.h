@@ -15,8 +15,8 @@
 //   seed    uint32[Wp]         per-world LCG state                (dRandSetSeed)
 //   nrows   int[Wp]            rows of the last step | independent ("head") rows << 16
 //   rows    float4[maxrows*4][Wp]  constraint rows in ODE's initial sweep order (slot = position at
-//                              iteration 0): 12 mass- and Ad-scaled Jacobian words (body-0 side J0..J5, then
-//                              body-1 side J9 J10 J11 J6 J7 J8), rhs', cfm', bound, meta
+//                              iteration 0): 12 mass- and Ad-scaled Jacobian words, rhs', cfm', bound, meta;
+//                              one more slot (index maxrows) holds an all-zero row for every world
 //   lambda  float[maxrows][Wp] scaled multipliers by slot;  rowS float[maxrows][Wp]  sqrt(Ad) by slot
 //   fcacc   float[nb*6][Wp]    M^-1/2 J^T lambda after the last sweep;  invIw float[nb*9][Wp]
 //   cmap    uint32[maxc][Wp]   rows | depmask<<3 | slot of the normal row<<8 | first dependent slot<<16
@@ -104,7 +104,7 @@ struct StepParams {
     float erp, cfm, contact_max_vel, contact_min_depth, sor_w;
     int iters, reorder;
     float *state, *force, *jcmd, *jobs, *jfb, *crec, *cfb, *lambda, *rowS, *invIw, *fcacc;
-    float4 *rows;   // [slot][4][Wp], slot = position in ODE's initial order
+    float4 *rows;   // [slot][4][Wp], slot = position in ODE's initial order (+ the zero row in slot maxrows)
     uint32_t *cmap; // [maxc][Wp]
     uint8_t *jrows; // [nj][Wp]: rows of joint j | (local limit/motor row + 1) << 4
     int *ccount;

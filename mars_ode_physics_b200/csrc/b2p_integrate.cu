@@ -134,10 +134,10 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
             const float4 *src = P.rows + (size_t)(slot * 4) * Wp + w;
             const float4 j0 = src[0], j1 = src[(size_t)Wp], j2 = src[2 * (size_t)Wp];
             const float lam = G(P.lambda, slot);
-            // row layout (b2p_assemble.cu emit_row): J0..J3 | J4 J5 J9 J10 | J11 J6 J7 J8 | scalars
+            // row layout (b2p_assemble.cu emit_row): J0..J3 | J4..J7 | J8..J11 | scalars
             acc[0] += j0.x * lam; acc[1] += j0.y * lam; acc[2] += j0.z * lam; acc[3] += j0.w * lam;
-            acc[4] += j1.x * lam; acc[5] += j1.y * lam; acc[6] += j2.y * lam; acc[7] += j2.z * lam;
-            acc[8] += j2.w * lam; acc[9] += j1.z * lam; acc[10] += j1.w * lam; acc[11] += j2.x * lam;
+            acc[4] += j1.x * lam; acc[5] += j1.y * lam; acc[6] += j1.z * lam; acc[7] += j1.w * lam;
+            acc[8] += j2.x * lam; acc[9] += j2.y * lam; acc[10] += j2.z * lam; acc[11] += j2.w * lam;
             if (k == lrow) flam = lam * G(P.rowS, slot);
         }
         float data[12];

@@ -8,8 +8,10 @@
 // multiplier.  Rows arrive mass- and Ad-scaled (see b2p_assemble.cu), so one row-iteration is
 //     delta = rhs' - cfm'*lam - Jh.fch ;  lam <- clamp(lam + delta) ;  fch += (lam_new - lam_old) * Jh
 //
-// Mapping: two threads per world (lane 2v = body-0 side of world v, lane 2v+1 = body-1 side), one warp
-// (= one CTA) per 16 consecutive worlds.  Gauss-Seidel is sequential inside a world and every world follows
+// Mapping: two threads per world (one per body side of a row), one warp (= one CTA) per 16 consecutive worlds.
+// Lanes 0-7 / 16-23 are the body-0 sides of worlds 0-7 / 8-15, lanes 24-31 / 8-15 their body-1 sides (partner =
+// lane ^ 24): every half-warp then holds 16 different worlds, which makes all 8- and 16-byte shared-memory
+// accesses conflict-free without padding or swizzles.  Gauss-Seidel is sequential inside a world and every world follows
 // its own row order (contact counts and RNG histories differ), so the parallelism is across worlds and the
 // throughput of the kernel is (worlds resident per SM) / (latency of one row-iteration).  Both factors are
 // limited by where the rows live, hence:
@@ -26,15 +28,13 @@
 //   * positions m..mmax-1 of a world with fewer rows than its warp's longest world hold an all-zero row
 //     that points at a dummy multiplier and the dummy body: the sweep is branch- and predicate-free.
 // Shared memory per CTA, every access conflict-free whatever row or body each world is at:
-//     rows  float4[Rs][4][16]     granule g of position p: A0..A3 | A4 A5 B0 B1 | B2..B5 | rhs' cfm' bound meta
-//                                 (A = body-0 side, B = body-1 side angular part first); a lane reads its six
-//                                 words with three 8-byte loads and the scalars with one 16-byte broadcast load
+//     rows  float4[Rs][4][16]     granule g of position p: J0..J3 | J4..J7 | J8..J11 | rhs' cfm' bound meta
+//                                 (J0..J5 = body-0 side, J6..J11 = body-1 side); a lane reads its six words
+//                                 with three 8-byte loads and the scalars with one 16-byte load
 //     lam   float [R+2][16]       multipliers by slot; slot R = dummy (zero rows), slot R+1 = constant 1 (the
 //                                 "normal multiplier" of rows whose bound does not follow another row)
-//     fch   float4[(nb+1)*2][16]  M^-1/2 J^T lambda: (lin xyz, -) and (ang xyz, -) per body, + the dummy body
-//                                 one-body rows name as body 1; vector j of world v sits at column v ^ 4j and
-//                                 side 1 reads the angular vector first, so the two lanes of a world never
-//                                 meet in a bank
+//     fch   float2[(nb+1)*3][16]  M^-1/2 J^T lambda: (lx ly) (lz ax) (ay az) per body, + the dummy body that
+//                                 one-body rows name as body 1
 //     ord   uint8 [R][16]         the world's current row order (position -> slot)
 // HBM traffic is one read of the rows (64 B each) and one write of lam and fch.
 #include <cuda_runtime.h>
@@ -57,7 +57,7 @@ __device__ __forceinline__ void cp_async_commit_wait_all()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-// This lane's view of one row: its side's six Jacobian words (side 1: angular first) and the four scalars.
+// This lane's view of one row: its side's six Jacobian words and the four scalars.
 // meta (written by b2p_assemble.cu emit_row): own slot | slot of the multiplier the bound follows << 8 |
 // body 0 << 16 | body 1 << 24 | "lower bound is 0" << 30 | "upper bound is 0" << 31
 struct Row {
@@ -72,29 +72,26 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
     const DevTemplate *__restrict__ T = P.T;
     const int nb = T->nb, R = T->maxrows, Rs = P.rows_resident;
     float4 *const s_rows = (float4 *)smem_raw;
-    float4 *const s_fc = s_rows + (size_t)Rs * 4 * WL;
-    float *const s_lam = (float *)(s_fc + (size_t)(nb + 1) * 2 * WL);
+    float2 *const s_fc = (float2 *)(s_rows + (size_t)Rs * 4 * WL);
+    float *const s_lam = (float *)(s_fc + (size_t)(nb + 1) * 3 * WL);
     uint8_t *const s_ord = (uint8_t *)(s_lam + (size_t)(R + 2) * WL);
 
-    const int lane = threadIdx.x, v = lane >> 1, side = lane & 1;
+    const int lane = threadIdx.x, side = (lane >> 3) & 1, v = (lane & 7) + 8 * ((lane >> 4) ^ side);
     const int w = blockIdx.x * WL + v; // < Wp (padded worlds have no rows)
     const size_t Wp = (size_t)P.Wp;
     const int nr = w < P.W ? P.nrows[w] : 0;
     const int m = nr & 0xffff, nhead = nr >> 16;
     const int mmax = __reduce_max_sync(0xffffffffu, m);
-    const uint32_t zero_meta = (uint32_t)R | ((uint32_t)(R + 1) << 8) | ((uint32_t)nb << 16) | ((uint32_t)nb << 24);
 
     for (int s = side; s < R + 2; s += 2) s_lam[s * WL + v] = s == R + 1 ? 1.f : 0.f;
     for (int s = side; s < R; s += 2) s_ord[s * WL + v] = (uint8_t)s;
-    for (int k = side; k < (nb + 1) * 2; k += 2) s_fc[k * WL + v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = side; k < (nb + 1) * 3; k += 2) s_fc[k * WL + v] = make_float2(0.f, 0.f);
     uint32_t seed = P.seed[w];
     __syncwarp();
 
     // ---- this lane's addresses
     float *const lamL = s_lam + v;
-    // fch vector j of body b, world v: s_fc[(b*2 + j)*16 + (v ^ 4j)]; this lane reads vector `side` first
-    float4 *const fcF = s_fc + side * WL + (v ^ (side << 2));
-    float4 *const fcS = s_fc + (side ^ 1) * WL + (v ^ ((side ^ 1) << 2));
+    float2 *const fcL = s_fc + v; // fch of body b, world v: fcL[(b*3 + {0,1,2})*16]
     const int bshift = 16 + 8 * side;
     // 8-byte granules of this side inside a shared-memory row block (float2 units): words side*6 + {0,2,4}
     const int w0 = side * 6;
@@ -102,25 +99,17 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
     const int o1 = (((w0 + 2) >> 2) * WL + v) * 2 + (((w0 + 2) >> 1) & 1);
     const int o2 = (((w0 + 4) >> 2) * WL + v) * 2 + (((w0 + 4) >> 1) & 1);
 
-    auto zero_row = [&]() -> Row {
-        Row q;
-        q.j0 = q.j1 = q.j2 = q.j3 = q.j4 = q.j5 = 0.f;
-        q.rhs = q.cfm = q.bound = 0.f;
-        q.meta = zero_meta;
-        return q;
-    };
     // this lane's half of the row in slot `slot` of its world, from the slot-ordered rows in global memory
+    // (slot R is an all-zero row that names the dummy multiplier and the dummy body)
     auto gload = [&](int slot) -> Row {
-        const float4 *p = P.rows + (size_t)(slot * 4 + side) * Wp + w;
-        const float4 vA = __ldg(p), vB = __ldg(p + Wp);
+        const float2 *p = (const float2 *)(P.rows + (size_t)(slot * 4) * Wp + w);
+        // words side*6 + {0,2,4} of the 16-word row: vector (word >> 2), half ((word >> 1) & 1)
+        const float2 a = __ldg(p + (size_t)(side ? 1 : 0) * Wp * 2 + (side ? 1 : 0));
+        const float2 b = __ldg(p + (size_t)(side ? 2 : 0) * Wp * 2 + (side ? 0 : 1));
+        const float2 c = __ldg(p + (size_t)(side ? 2 : 1) * Wp * 2 + (side ? 1 : 0));
         const float4 v3 = __ldg(P.rows + (size_t)(slot * 4 + 3) * Wp + w);
         Row q;
-        q.j0 = side ? vA.z : vA.x;
-        q.j1 = side ? vA.w : vA.y;
-        q.j2 = side ? vB.x : vA.z;
-        q.j3 = side ? vB.y : vA.w;
-        q.j4 = side ? vB.z : vB.x;
-        q.j5 = side ? vB.w : vB.y;
+        q.j0 = a.x, q.j1 = a.y, q.j2 = b.x, q.j3 = b.y, q.j4 = c.x, q.j5 = c.y;
         q.rhs = v3.x;
         q.cfm = v3.y;
         q.bound = v3.z;
@@ -148,11 +137,11 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
         float *lp = lamL + (mt & 0xff) * WL;
         const float *ln = lamL + ((mt >> 8) & 0xff) * WL;
         const int b = (mt >> bshift) & 0x3f;
-        float4 *pF = fcF + b * (2 * WL), *pS = fcS + b * (2 * WL);
-        float4 F = *pF, S = *pS;
+        float2 *pf = fcL + b * (3 * WL);
+        float2 fa = pf[0], fb = pf[WL], fc = pf[2 * WL];
         const float lam_old = *lp, lam_n = *ln;
-        const float d = (q.j0 * F.x + q.j1 * F.y + q.j2 * F.z) + (q.j3 * S.x + q.j4 * S.y + q.j5 * S.z);
-        const float dot = d + __shfl_xor_sync(0xffffffffu, d, 1);
+        const float d = (q.j0 * fa.x + q.j1 * fa.y + q.j2 * fb.x) + (q.j3 * fb.y + q.j4 * fc.x + q.j5 * fc.y);
+        const float dot = d + __shfl_xor_sync(0xffffffffu, d, 24);
         float delta = (q.rhs - lam_old * q.cfm) - dot;
         const float bnd = fabsf(q.bound * lam_n);
         const float hi_act = (mt & 0x80000000u) ? 0.f : bnd;
@@ -161,38 +150,31 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
         const float nl = fminf(fmaxf(un, lo_act), hi_act);
         delta = (nl == un) ? delta : nl - lam_old;
         *lp = nl;
-        F.x += delta * q.j0, F.y += delta * q.j1, F.z += delta * q.j2;
-        S.x += delta * q.j3, S.y += delta * q.j4, S.z += delta * q.j5;
-        *pF = F;
-        *pS = S;
+        fa.x += delta * q.j0, fa.y += delta * q.j1, fb.x += delta * q.j2;
+        fb.y += delta * q.j3, fc.x += delta * q.j4, fc.y += delta * q.j5;
+        pf[0] = fa;
+        pf[WL] = fb;
+        pf[2 * WL] = fc;
     };
 
     Row rr[KR > 0 ? KR : 1];
     const int ks = mmax < KR + Rs ? mmax : KR + Rs; // end of the shared-memory positions
 
-    // (re)load every on-chip row in the current order
+    // (re)load every on-chip row in the current order; positions >= m of a world get the zero row (slot R)
     auto load_rows = [&]() {
 #pragma unroll
         for (int k = 0; k < KR; k++) {
-            if ((k & ~3) < mmax) { // whole groups of four: the sweep skips register positions by group
-                const int slot = s_ord[(k < R ? k : 0) * WL + v];
-                rr[k] = k < m ? gload(slot) : zero_row();
-            }
+            if ((k & ~3) < mmax) // whole groups of four: the sweep skips register positions by group
+                rr[k] = gload(k < m ? s_ord[k * WL + v] : R);
         }
         // lane (v, side) copies granules 2*side and 2*side + 1 of its world's rows
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rows + (side * 2) * WL + v);
         for (int k = KR; k < ks; k++) {
+            const int slot = k < m ? s_ord[k * WL + v] : R;
+            const float4 *src = P.rows + (size_t)(slot * 4 + side * 2) * Wp + w;
             const uint32_t d = dst + (uint32_t)((k - KR) * 4 * WL * 16);
-            if (k < m) {
-                const int slot = s_ord[k * WL + v];
-                const float4 *src = P.rows + (size_t)(slot * 4 + side * 2) * Wp + w;
-                cp_async16(d, src);
-                cp_async16(d + WL * 16, src + Wp);
-            } else {
-                float4 *z = s_rows + (size_t)((k - KR) * 4 + side * 2) * WL + v;
-                z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                z[WL] = make_float4(0.f, 0.f, 0.f, side ? __int_as_float((int)zero_meta) : 0.f);
-            }
+            cp_async16(d, src);
+            cp_async16(d + WL * 16, src + Wp);
         }
         cp_async_commit_wait_all();
         __syncwarp();
@@ -239,20 +221,17 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
         // positions that did not fit on chip: read in place (L2)
 #pragma unroll 1
         for (int k = KR + Rs; k < mmax; k++) {
-            const Row q = k < m ? gload(s_ord[k * WL + v]) : zero_row();
-            relax(q);
+            relax(gload(k < m ? s_ord[k * WL + v] : R));
         }
     }
 
     if (w < P.W) {
         for (int s = side; s < m; s += 2) P.lambda[(size_t)s * Wp + w] = s_lam[s * WL + v];
-        for (int k = side; k < nb * 2; k += 2) {
-            const int b = k >> 1, j = k & 1;
-            const float4 f = s_fc[(b * 2 + j) * WL + (v ^ (j << 2))];
-            float *dst = P.fcacc + (size_t)(b * 6 + j * 3) * Wp + w;
+        for (int k = side; k < nb * 3; k += 2) {
+            const float2 f = s_fc[k * WL + v];
+            float *dst = P.fcacc + (size_t)(k * 2) * Wp + w;
             dst[0] = f.x;
             dst[Wp] = f.y;
-            dst[2 * Wp] = f.z;
         }
         if (side == 0) P.seed[w] = seed;
     }
@@ -263,7 +242,7 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
 extern "C" size_t b2p_sor_smem_bytes(int nb, int maxrows, int rows_resident)
 {
     size_t s = sizeof(float4) * (size_t)rows_resident * 4 * WL;
-    s += sizeof(float4) * (size_t)(nb + 1) * 2 * WL;
+    s += sizeof(float2) * (size_t)(nb + 1) * 3 * WL;
     s += sizeof(float) * (size_t)(maxrows + 2) * WL;
     s += (size_t)maxrows * WL;
     return (s + 15) & ~(size_t)15;
