@@ -243,6 +243,7 @@ def run_b200(args):
         ar.set_resident_rows(args.resident_rows)
     if args.register_rows >= 0:
         ar.set_register_rows(args.register_rows)
+    ar.set_sor_kernel({"auto": -1, "paired": 0, "tmem": 1}[args.sor_kernel])
     if args.reorder == "none":
         ar.set_reorder_method(capi.REORDER_NONE)
     nb, nj = len(sc["bodies"]), len(sc["joints"])
@@ -401,6 +402,8 @@ def main():
                     help="tuning: constraint rows per world kept in shared memory by the SOR kernel (0 = auto)")
     ap.add_argument("--register-rows", type=int, default=-1,
                     help="tuning: sweep positions per world kept in registers by the SOR kernel (-1 = auto)")
+    ap.add_argument("--sor-kernel", default="auto", choices=["auto", "paired", "tmem"],
+                    help="SOR-LCP kernel: rows in registers + Tensor Memory (tmem) or registers + shared memory (paired)")
     ap.add_argument("--reorder", default="random", choices=["random", "none"],
                     help="SOR row reordering: ODE 0.16 default (random) or REORDERING_METHOD__DONT_REORDER")
     ap.add_argument("--workload", default="D", choices=["B", "C", "D"],

@@ -131,6 +131,14 @@ int b2p_arena_enable_rolling_friction(b2p_arena *a, int on);
  * (0 = automatic: the longest world seen so far) and in registers (multiple of 4 up to 20; < 0 = automatic) */
 int b2p_arena_set_resident_rows(b2p_arena *a, int n);
 int b2p_arena_set_register_rows(b2p_arena *a, int n);
+/* which SOR-LCP kernel a step uses: B2P_SOR_AUTO picks the Tensor-Memory kernel (one thread per world, rows in
+ * registers + TMEM) when the scene fits it and the paired-lane kernel (rows in registers + shared memory)
+ * otherwise; both produce bitwise identical results.  b2p_arena_sor_kernel_used reports the last step's choice. */
+#define B2P_SOR_AUTO (-1)
+#define B2P_SOR_PAIRED 0
+#define B2P_SOR_TMEM 1
+int b2p_arena_set_sor_kernel(b2p_arena *a, int which);
+int b2p_arena_sor_kernel_used(const b2p_arena *a);
 
 int b2p_world_set_gravity(b2p_arena *a, double x, double y, double z);      /* dWorldSetGravity :194 */
 int b2p_world_set_cfm(b2p_arena *a, double cfm);                            /* dWorldSetCFM :195 */

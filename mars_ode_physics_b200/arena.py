@@ -53,6 +53,13 @@ class Arena:
     def set_resident_rows(self, n):
         self._check(self.lib.b2p_arena_set_resident_rows(self.h, int(n)))
 
+    def set_sor_kernel(self, which):
+        """-1 = automatic, 0 = paired-lane kernel (b2p_sor.cu), 1 = Tensor-Memory kernel (b2p_sor_tmem.cu)"""
+        self._check(self.lib.b2p_arena_set_sor_kernel(self.h, int(which)))
+
+    def sor_kernel_used(self):
+        return int(self.lib.b2p_arena_sor_kernel_used(self.h))
+
     def set_register_rows(self, n):
         self._check(self.lib.b2p_arena_set_register_rows(self.h, int(n)))
 

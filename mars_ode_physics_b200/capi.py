@@ -19,6 +19,7 @@ PARAM_GROUP2 = 0x100
 CONTACT_MU2, CONTACT_SOFT_ERP, CONTACT_SOFT_CFM, CONTACT_ROLLING = 0x001, 0x008, 0x010, 0x400
 CONTACT_APPROX1 = 0x7000
 REORDER_RANDOMLY, REORDER_NONE = 0, 1
+SOR_AUTO, SOR_PAIRED, SOR_TMEM = -1, 0, 1
 GEOM_SPHERE, GEOM_BOX, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_PLANE, GEOM_HEIGHTFIELD = range(6)
 E_REJECTED = -6
 
@@ -60,6 +61,8 @@ SIGNATURES = {
     "b2p_arena_enable_rolling_friction": (_I, [_P, _I]),
     "b2p_arena_set_resident_rows": (_I, [_P, _I]),
     "b2p_arena_set_register_rows": (_I, [_P, _I]),
+    "b2p_arena_set_sor_kernel": (_I, [_P, _I]),
+    "b2p_arena_sor_kernel_used": (_I, [_P]),
     "b2p_world_set_gravity": (_I, [_P, _D, _D, _D]),
     "b2p_world_set_cfm": (_I, [_P, _D]),
     "b2p_world_set_erp": (_I, [_P, _D]),

