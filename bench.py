@@ -244,6 +244,7 @@ def run_b200(args):
     if args.register_rows >= 0:
         ar.set_register_rows(args.register_rows)
     ar.set_sor_kernel({"auto": -1, "paired": 0, "tmem": 1}[args.sor_kernel])
+    ar.set_sor_warps(args.sor_warps)
     if args.reorder == "none":
         ar.set_reorder_method(capi.REORDER_NONE)
     nb, nj = len(sc["bodies"]), len(sc["joints"])
@@ -404,6 +405,8 @@ def main():
                     help="tuning: sweep positions per world kept in registers by the SOR kernel (-1 = auto)")
     ap.add_argument("--sor-kernel", default="auto", choices=["auto", "paired", "tmem"],
                     help="SOR-LCP kernel: rows in registers + Tensor Memory (tmem) or registers + shared memory (paired)")
+    ap.add_argument("--sor-warps", type=int, default=0, choices=[0, 4, 8],
+                    help="Tensor-Memory SOR kernel: warps (x32 worlds) per CTA; 0 = auto")
     ap.add_argument("--reorder", default="random", choices=["random", "none"],
                     help="SOR row reordering: ODE 0.16 default (random) or REORDERING_METHOD__DONT_REORDER")
     ap.add_argument("--workload", default="D", choices=["B", "C", "D"],

@@ -139,6 +139,8 @@ int b2p_arena_set_register_rows(b2p_arena *a, int n);
 #define B2P_SOR_TMEM 1
 int b2p_arena_set_sor_kernel(b2p_arena *a, int which);
 int b2p_arena_sor_kernel_used(const b2p_arena *a);
+/* Tensor-Memory kernel: warps (x 32 worlds) per CTA, 4 or 8; 0 = automatic */
+int b2p_arena_set_sor_warps(b2p_arena *a, int warps);
 
 int b2p_world_set_gravity(b2p_arena *a, double x, double y, double z);      /* dWorldSetGravity :194 */
 int b2p_world_set_cfm(b2p_arena *a, double cfm);                            /* dWorldSetCFM :195 */

@@ -57,6 +57,9 @@ class Arena:
         """-1 = automatic, 0 = paired-lane kernel (b2p_sor.cu), 1 = Tensor-Memory kernel (b2p_sor_tmem.cu)"""
         self._check(self.lib.b2p_arena_set_sor_kernel(self.h, int(which)))
 
+    def set_sor_warps(self, warps):
+        self._check(self.lib.b2p_arena_set_sor_warps(self.h, int(warps)))
+
     def sor_kernel_used(self):
         return int(self.lib.b2p_arena_sor_kernel_used(self.h))
 

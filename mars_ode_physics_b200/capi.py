@@ -63,6 +63,7 @@ SIGNATURES = {
     "b2p_arena_set_register_rows": (_I, [_P, _I]),
     "b2p_arena_set_sor_kernel": (_I, [_P, _I]),
     "b2p_arena_sor_kernel_used": (_I, [_P]),
+    "b2p_arena_set_sor_warps": (_I, [_P, _I]),
     "b2p_world_set_gravity": (_I, [_P, _D, _D, _D]),
     "b2p_world_set_cfm": (_I, [_P, _D]),
     "b2p_world_set_erp": (_I, [_P, _D]),

@@ -23,8 +23,8 @@ extern "C" size_t b2p_assemble_smem_bytes(int nb);
 extern "C" size_t b2p_integrate_smem_bytes(int nb);
 extern "C" size_t b2p_sor_smem_bytes(int nb, int maxrows, int rows_resident);
 extern "C" int b2p_sor_register_rows(int maxrows, int wanted);
-extern "C" size_t b2p_sor_tmem_smem_bytes(int nb, int maxrows, int rows_overflow);
-extern "C" int b2p_sor_tmem_rows_on_chip(int kr);
+extern "C" size_t b2p_sor_tmem_smem_bytes(int nb, int maxrows, int pool, int warps);
+extern "C" int b2p_sor_tmem_rows_on_chip(int kr, int warps);
 extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
@@ -226,6 +226,8 @@ struct b2p_arena {
     int rows_resident = 0;   // SOR kernel: sweep positions kept in shared memory; 0 = automatic
     int rows_registers = -1; // SOR kernel: sweep positions kept in registers; < 0 = automatic
     int sor_kernel = -1;     // B2P_SOR_AUTO / B2P_SOR_PAIRED (b2p_sor.cu) / B2P_SOR_TMEM (b2p_sor_tmem.cu)
+    int sor_warps = 0;       // Tensor-Memory kernel: warps per CTA (4 or 8); 0 = automatic
+    int sm_count = 0;
     int sor_kernel_used = 0;
     int *d_hw_rows = nullptr, *h_hw_rows = nullptr; // largest row count of any world so far (device / pinned copy)
     // optional per-kernel timing (bench / profiling): events around the three launches of a step
@@ -752,6 +754,7 @@ int b2p_arena_create(int num_worlds, int device, b2p_arena **out)
     a->W = num_worlds;
     a->Wp = (num_worlds + 31) & ~31;
     a->device = device;
+    cudaDeviceGetAttribute(&a->sm_count, cudaDevAttrMultiProcessorCount, device);
     a->seed.fields = 1;
     a->seed.host.assign((size_t)a->Wp, 0u);
     a->seed.host_newer = true;
@@ -1841,16 +1844,29 @@ int b2p_step(b2p_arena *a, double step_size)
     // world seen so far must fit into registers + TMEM + the shared-memory overflow positions.
     const int seen = a->h_hw_rows && *(volatile int *)a->h_hw_rows > 0 ? *(volatile int *)a->h_hw_rows : maxrows;
     const int kr_t = a->rows_registers < 0 ? 8 : std::min(8, a->rows_registers & ~3);
-    const size_t fixed_t = b2p_sor_tmem_smem_bytes(nb, maxrows, 0);
-    const size_t per_row_t = b2p_sor_tmem_smem_bytes(nb, maxrows, 1) - fixed_t;
-    const int cap_t = fixed_t + 1024 < kSmemMax ? (int)((kSmemMax - 1024 - fixed_t) / per_row_t) : -1;
-    const int want_t = std::max(std::min(seen, maxrows) - b2p_sor_tmem_rows_on_chip(kr_t), 0);
-    bool use_tmem = a->sor_kernel == B2P_SOR_TMEM || (a->sor_kernel == B2P_SOR_AUTO && cap_t >= 0 && want_t <= cap_t);
-    if (use_tmem && cap_t < 0)
-        return fail(B2P_ECAPACITY, "scene too large for the Tensor-Memory SOR kernel (%zu bytes of shared memory)", fixed_t);
+    // warps per CTA: 8 (two per scheduler) unless the per-world arrays of 256 worlds leave no room for a pool
+    int nw_t = a->sor_warps == 4 ? 4 : 8, pool_t = -1, want_t = 0;
+    for (;; nw_t = 4) {
+        const size_t fixed_t = b2p_sor_tmem_smem_bytes(nb, maxrows, 0, nw_t);
+        pool_t = fixed_t + 1024 + 2 * 2048 <= kSmemMax ? (int)((kSmemMax - 1024 - fixed_t) / 2048) : -1;
+        want_t = std::max(std::min(seen, maxrows) - b2p_sor_tmem_rows_on_chip(kr_t, nw_t), 0);
+        if (nw_t == 4 || a->sor_warps == 8 || (pool_t >= 0 && want_t <= pool_t)) break;
+    }
+    bool use_tmem = a->sor_kernel == B2P_SOR_TMEM || (a->sor_kernel == B2P_SOR_AUTO && pool_t >= 0 && want_t <= pool_t);
+    if (use_tmem && pool_t < 0)
+        return fail(B2P_ECAPACITY, "scene too large for the Tensor-Memory SOR kernel");
     if (use_tmem) {
         P.rows_registers = kr_t;
-        P.rows_resident = a->rows_resident > 0 ? std::min(a->rows_resident, cap_t) : std::min(want_t, cap_t);
+        P.sor_warps = nw_t;
+        // one CTA per SM: spread the worlds evenly over whole waves of CTAs instead of leaving the last wave
+        // partly empty (65536 worlds on 148 SMs: 2 waves of 224-world CTAs rather than 1.73 waves of 256)
+        {
+            const int tw = nw_t * 32, sms = std::max(a->sm_count, 1);
+            const int waves = (a->W + tw * sms - 1) / (tw * sms);
+            const int per = (a->W + waves * sms - 1) / (waves * sms);
+            P.worlds_per_cta = std::min(tw, std::max(32, (per + 31) & ~31));
+        }
+        P.rows_resident = a->rows_resident > 0 ? std::max(std::min(a->rows_resident, pool_t), 2) : pool_t;
     } else {
         P.rows_registers = b2p_sor_register_rows(maxrows, a->rows_registers);
         P.rows_resident = pick_rows_resident(a, nb, maxrows, P.rows_registers);
@@ -1928,6 +1944,13 @@ int b2p_arena_set_sor_kernel(b2p_arena *a, int which)
 }
 
 int b2p_arena_sor_kernel_used(const b2p_arena *a) { return a ? a->sor_kernel_used : 0; }
+
+int b2p_arena_set_sor_warps(b2p_arena *a, int warps)
+{
+    if (!a || (warps != 0 && warps != 4 && warps != 8)) return fail(B2P_EINVAL, "warps per CTA must be 0, 4 or 8");
+    a->sor_warps = warps;
+    return 0;
+}
 
 int b2p_arena_set_register_rows(b2p_arena *a, int n)
 {

@@ -113,6 +113,8 @@ struct StepParams {
     int rows_registers; // sweep positions per world the SOR kernel keeps in registers (0, 4, ... 20)
     int rows_resident;  // further positions it keeps in shared memory (the rest is read from L2 in place)
     int *hw_rows;       // device counter: largest row count of any world so far
+    int sor_warps;      // Tensor-Memory SOR kernel: warps per CTA (4 or 8); rows_resident = its overflow pool units
+    int worlds_per_cta; // Tensor-Memory SOR kernel: worlds a CTA takes (multiple of 32, <= 32 * sor_warps)
 };
 
 struct CollideParams {

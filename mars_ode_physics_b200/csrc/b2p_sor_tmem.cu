@@ -2,11 +2,16 @@
 //
 // Same computation as b2p_sor.cu (ODE 0.16 quickstep.cpp SOR_LCP behind dWorldQuickStep,
 // src/WorldPhysics.cpp:365; see there for the scaled row-iteration and the row format), different mapping:
-// ONE thread per world, 128 worlds per CTA, one CTA per SM, and the rows held physically in sweep order in
+// ONE thread per world, 128 or 256 worlds per CTA, one CTA per SM, and the rows held physically in sweep order in
 //   * registers:      sweep positions [0, KR)            (16 words per row)
-//   * Tensor Memory:  positions [KR, KR+32)              (the SM's 256 KB TMEM = 128 lanes x 512 columns; a
-//                                                         thread owns one lane = 32 rows of 16 words)
-//   * shared memory:  positions [KR+32, KR+32+Ro)        ([position][4][128 worlds] float4)
+//   * Tensor Memory:  positions [KR, KR+TROWS)           (the SM's 256 KB TMEM = 128 lanes x 512 columns: with
+//                                                         4 warps a thread owns a whole lane = 32 rows of 16
+//                                                         words; with 8 warps two warps split a lane quadrant's
+//                                                         columns, 16 rows per world)
+//   * shared memory:  the warp's overflow positions      (a pool of [position][4][32 worlds] float4 units handed
+//                                                         out per warp: the worlds of a CTA are sorted by row
+//                                                         count first, so only the warps holding the long worlds
+//                                                         need overflow rows)
 //   * L2 in place:    anything beyond (worlds with unusually many contacts).
 // Blackwell's TMEM is meant for tensor-core accumulators, but tcgen05.st / tcgen05.ld (32x32b shape) give every
 // thread of a warp private access to its own lane at a warp-uniform column.  Because the rows are kept in sweep
@@ -17,9 +22,9 @@
 // cross-lane reduction on the dependent chain, and a warp instruction advances 32 worlds instead of 16.
 // The row of position p+1 is fetched from TMEM while row p is relaxed.
 //
-// Shared memory per CTA (all accesses conflict-free: consecutive lanes = consecutive worlds):
-//     rows  float4[Ro][4][128]   overflow positions
-//     fch   float2[(nb+1)*3][128], lam float[R+2][128], ord uint8[R][128]   as in b2p_sor.cu
+// Shared memory per CTA (all accesses conflict-free: consecutive lanes = consecutive columns):
+//     fch   float2[(nb+1)*3][TW], lam float[R+2][TW], ord uint8[R][TW]   as in b2p_sor.cu, one column per thread
+//     pool  float4[units][4][32]                                          overflow positions
 // The arithmetic of a row-iteration is term-by-term the one of b2p_sor.cu, so both kernels produce bitwise
 // identical multipliers (tests/test_gpu_parity.py::test_sor_kernels_agree).
 #include <cuda_runtime.h>
@@ -31,9 +36,7 @@
 
 namespace {
 
-constexpr int TW = 128;      // worlds (= threads) per CTA
-constexpr int TROWS = 32;    // rows per world in Tensor Memory (512 columns / 16 words)
-constexpr int TCOLS = 512;   // TMEM columns allocated per CTA (all of them: one CTA per SM)
+constexpr int TCOLS = 512; // TMEM columns allocated per CTA (all of them: one CTA per SM)
 
 struct Row {
     float j[12];
@@ -70,36 +73,85 @@ __device__ __forceinline__ void tm_wait_row(Row &q)
                  : "memory");
 }
 
-template <int KR> __global__ void __launch_bounds__(TW, 1) b2p_sor_tmem_kernel(const StepParams P)
+// NW warps per CTA (4 or 8): NW*32 worlds per SM.  With 8 warps two warps share a TMEM lane quadrant and split its
+// columns, so a world has 16 instead of 32 rows in TMEM but every scheduler has two warps to alternate between.
+template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_tmem_kernel(const StepParams P)
 {
+    constexpr int TW = NW * 32;            // worlds (= threads) per CTA
+    constexpr int TROWS = 32 / (NW / 4);   // rows per world in Tensor Memory
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem_base;
+    __shared__ int s_need[NW];
     const DevTemplate *__restrict__ T = P.T;
-    const int nb = T->nb, R = T->maxrows, Ro = P.rows_resident;
-    float4 *const s_rows = (float4 *)smem_raw;
-    float2 *const s_fc = (float2 *)(s_rows + (size_t)Ro * 4 * TW);
+    const int nb = T->nb, R = T->maxrows, pool = P.rows_resident;
+    float2 *const s_fc = (float2 *)smem_raw;
     float *const s_lam = (float *)(s_fc + (size_t)(nb + 1) * 3 * TW);
     uint8_t *const s_ord = (uint8_t *)(s_lam + (size_t)(R + 2) * TW);
+    // overflow rows: `pool` units of one sweep position x 32 worlds, handed to the warps that need them
+    float4 *const s_pool = (float4 *)(smem_raw + (((size_t)(nb + 1) * 3 * TW * 8 + (size_t)(R + 2) * TW * 4 + (size_t)R * TW + 15) & ~(size_t)15));
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    // ---- Tensor Memory: warp 0 allocates all 512 columns; warp i owns lanes 32i .. 32i+31
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- Tensor Memory: warp 0 allocates all 512 columns; warp i owns lanes 32(i&3) .., columns 256(i>>2) ..
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
                          (uint32_t)__cvta_generic_to_shared(&s_tmem_base)),
                      "n"(TCOLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
+
+    // ---- sort the CTA's worlds by row count (descending) so that the 32 worlds of a warp are about equally
+    // long: a warp sweeps as many positions as its longest world has rows.  Counting sort in shared memory
+    // (scratch aliases the overflow pool, which is not in use yet); which of two equally long worlds comes
+    // first is arbitrary and does not influence any result.
+    const size_t Wp = (size_t)P.Wp;
+    int w, nr;
+    {
+        int *const s_cnt = (int *)s_pool;            // [R+2]
+        int *const s_nr = s_cnt + ((R + 2 + 3) & ~3); // [TW] nrows word by sorted position
+        uint16_t *const s_perm = (uint16_t *)(s_nr + TW);
+        // a CTA takes P.worlds_per_cta <= TW consecutive worlds (the host evens out the last wave with it)
+        const int w0 = blockIdx.x * P.worlds_per_cta + tid;
+        const int nr0 = tid < P.worlds_per_cta && w0 < P.W ? P.nrows[w0] : 0;
+        const int m0 = nr0 & 0xffff;
+        for (int i = tid; i < R + 2; i += TW) s_cnt[i] = 0;
+        __syncthreads();
+        atomicAdd(&s_cnt[m0], 1);
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int i = R; i >= 0; i--) {
+                const int c = s_cnt[i];
+                s_cnt[i] = acc;
+                acc += c;
+            }
+        }
+        __syncthreads();
+        const int pos = atomicAdd(&s_cnt[m0], 1);
+        s_perm[pos] = (uint16_t)tid;
+        s_nr[pos] = nr0;
+        __syncthreads();
+        // sorted position of this thread: warps 0..3 take the four longest groups of 32, warps 4..7 the rest in
+        // reverse, so that the two warps sharing a scheduler (i, i + 4) together have about the same work
+        const int grp = NW == 8 && warp >= 4 ? 11 - warp : warp;
+        w = blockIdx.x * P.worlds_per_cta + s_perm[grp * 32 + lane];
+        nr = s_nr[grp * 32 + lane];
+    }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const uint32_t tbase = s_tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tbase = s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * (TROWS * 16));
 
-    const int w = blockIdx.x * TW + tid;
-    const size_t Wp = (size_t)P.Wp;
     const int wl = w < P.Wp ? w : P.Wp - 1; // a CTA may reach past the padded world count: loads are clamped
-    const int nr = w < P.W ? P.nrows[w] : 0;
     const int m = nr & 0xffff, nhead = nr >> 16;
     const int mmax = __reduce_max_sync(0xffffffffu, m);
+
+    // ---- overflow positions of this warp: [KR+TROWS, KR+TROWS+Ro) out of the shared pool, in warp order
+    if (lane == 0) s_need[warp] = mmax - KR - TROWS > 0 ? mmax - KR - TROWS : 0;
+    __syncthreads();
+    int obase = 0;
+    for (int i = 0; i < warp; i++) obase += s_need[i];
+    const int Ro = obase >= pool ? 0 : (s_need[warp] < pool - obase ? s_need[warp] : pool - obase);
+    float4 *const s_rows = s_pool + (size_t)obase * 4 * 32 + lane; // position p, vector g: s_rows[(p*4 + g)*32]
 
     for (int s = 0; s < R + 2; s++) s_lam[s * TW + tid] = s == R + 1 ? 1.f : 0.f;
     for (int s = 0; s < R; s++) s_ord[s * TW + tid] = (uint8_t)s;
@@ -122,8 +174,8 @@ template <int KR> __global__ void __launch_bounds__(TW, 1) b2p_sor_tmem_kernel(c
         return q;
     };
     auto sload = [&](int p) -> Row {
-        const float4 *b = s_rows + (size_t)(p * 4) * TW + tid;
-        const float4 v0 = b[0], v1 = b[TW], v2 = b[2 * TW], v3 = b[3 * TW];
+        const float4 *b = s_rows + (size_t)(p * 4) * 32;
+        const float4 v0 = b[0], v1 = b[32], v2 = b[64], v3 = b[96];
         Row q;
         q.j[0] = v0.x, q.j[1] = v0.y, q.j[2] = v0.z, q.j[3] = v0.w;
         q.j[4] = v1.x, q.j[5] = v1.y, q.j[6] = v1.z, q.j[7] = v1.w;
@@ -166,30 +218,23 @@ template <int KR> __global__ void __launch_bounds__(TW, 1) b2p_sor_tmem_kernel(c
     const int nt = mmax - KR < 0 ? 0 : (mmax - KR < TROWS ? mmax - KR : TROWS); // positions in TMEM
     const int no = mmax - KR - TROWS < 0 ? 0 : (mmax - KR - TROWS < Ro ? mmax - KR - TROWS : Ro); // in smem
 
-    // (re)load every on-chip row in the current order; positions >= m of a world get the zero row (slot R)
-    auto load_rows = [&]() {
-#pragma unroll
-        for (int k = 0; k < KR; k++) {
-            if ((k & ~3) < mmax) rr[k] = gload(k < m ? s_ord[k * TW + tid] : R);
-        }
-#pragma unroll 2
-        for (int p = 0; p < nt; p++) {
-            const int k = KR + p;
-            const Row q = gload(k < m ? s_ord[k * TW + tid] : R);
+    // slot of sweep position k of this world in the current order (positions >= m: the zero row, slot R)
+    auto slot_at = [&](int k) -> int { return k < m ? s_ord[(k < R ? k : 0) * TW + tid] : R; };
+    // put a row at on-chip position p behind the register positions
+    auto deposit = [&](int p, const Row &q) {
+        if (p < TROWS) {
             tm_store_row(tbase + (uint32_t)(p * 16), q);
+        } else {
+            float4 *dst = s_rows + (size_t)((p - TROWS) * 4) * 32;
+            dst[0] = make_float4(q.j[0], q.j[1], q.j[2], q.j[3]);
+            dst[32] = make_float4(q.j[4], q.j[5], q.j[6], q.j[7]);
+            dst[64] = make_float4(q.j[8], q.j[9], q.j[10], q.j[11]);
+            dst[96] = make_float4(q.rhs, q.cfm, q.bound, __int_as_float((int)q.meta));
         }
-        for (int p = 0; p < no; p++) {
-            const int k = KR + TROWS + p;
-            const int slot = k < m ? s_ord[k * TW + tid] : R;
-            const float4 *src = P.rows + (size_t)(slot * 4) * Wp + wl;
-            float4 *dst = s_rows + (size_t)(p * 4) * TW + tid;
-            dst[0] = __ldg(src), dst[TW] = __ldg(src + Wp), dst[2 * TW] = __ldg(src + 2 * Wp), dst[3 * TW] = __ldg(src + 3 * Wp);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
     };
-    if (mmax > 0) load_rows();
 
     for (int it = 0; it < (mmax > 0 ? P.iters : 0); it++) {
+        bool fresh = it == 0; // the rows on chip are not (yet) in the order of this sweep
         if (P.reorder == 0 && it >= 8 && (it & 7) == 0) {
             // ODE ConstraintsReorderingHelper on [0,nhead) and [nhead,m)
             auto swap = [&](int a, int b) {
@@ -202,7 +247,44 @@ template <int KR> __global__ void __launch_bounds__(TW, 1) b2p_sor_tmem_kernel(c
 #pragma unroll 1
             for (int idx = nhead + 1; idx < m; idx++) swap(idx, rand_int(seed, idx - nhead + 1) + nhead);
             __syncwarp(); // the loops above diverge; the TMEM instructions below are warp-collective
-            load_rows();
+            fresh = true;
+        }
+        if (fresh) {
+            // Streaming sweep: the first sweep in a new order takes every row from the slot-ordered rows in global
+            // memory (a per-lane gather; L2 hits after iteration 0), relaxes it, and deposits it at its sweep
+            // position on chip for the sweeps that follow.  The gather of position k+2 is in flight while
+            // position k is relaxed, so the gathers -- which are limited by the L1's rate of one 128-byte line
+            // per clock, 32 lines per warp instruction -- overlap the arithmetic instead of preceding it.
+#pragma unroll
+            for (int k = 0; k < KR; k++) {
+                if ((k & ~3) < mmax) rr[k] = gload(slot_at(k));
+            }
+            const int nchip = nt + no;
+            Row ring[2];
+            ring[0] = gload(slot_at(KR));
+            ring[1] = gload(slot_at(KR + 1));
+#pragma unroll
+            for (int g = 0; g < KR; g += 4) {
+                if (g < mmax) {
+#pragma unroll
+                    for (int k = g; k < g + 4 && k < KR; k++) relax(rr[k]);
+                }
+            }
+#pragma unroll 1
+            for (int p = 0; p < nchip; p += 2) {
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    if (p + i < nchip) {
+                        relax(ring[i]);
+                        deposit(p + i, ring[i]);
+                        ring[i] = gload(p + i + 2 < nchip ? slot_at(KR + p + i + 2) : R);
+                    }
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+#pragma unroll 1
+            for (int k = KR + TROWS + Ro; k < mmax; k++) relax(gload(slot_at(k)));
+            continue;
         }
         // positions in registers
 #pragma unroll
@@ -232,7 +314,7 @@ template <int KR> __global__ void __launch_bounds__(TW, 1) b2p_sor_tmem_kernel(c
 #pragma unroll 1
         for (int p = 0; p < no; p++) relax(sload(p));
 #pragma unroll 1
-        for (int k = KR + TROWS + Ro; k < mmax; k++) relax(gload(k < m ? s_ord[k * TW + tid] : R));
+        for (int k = KR + TROWS + Ro; k < mmax; k++) relax(gload(slot_at(k)));
     }
 
     if (w < P.W) {
@@ -254,39 +336,55 @@ template <int KR> __global__ void __launch_bounds__(TW, 1) b2p_sor_tmem_kernel(c
 
 } // namespace
 
-// dynamic shared memory of the TMEM kernel for `rows_overflow` overflow positions
-extern "C" size_t b2p_sor_tmem_smem_bytes(int nb, int maxrows, int rows_overflow)
+// dynamic shared memory of the TMEM kernel with `warps` warps (4 or 8) per CTA and an overflow pool of `pool`
+// units (one sweep position x 32 worlds = 2 KB each; the counting sort's scratch aliases the first two)
+extern "C" size_t b2p_sor_tmem_smem_bytes(int nb, int maxrows, int pool, int warps)
 {
-    size_t s = sizeof(float4) * (size_t)rows_overflow * 4 * TW;
-    s += sizeof(float2) * (size_t)(nb + 1) * 3 * TW;
+    const size_t TW = (size_t)warps * 32;
+    size_t s = sizeof(float2) * (size_t)(nb + 1) * 3 * TW;
     s += sizeof(float) * (size_t)(maxrows + 2) * TW;
     s += (size_t)maxrows * TW;
-    return (s + 15) & ~(size_t)15;
+    s = (s + 15) & ~(size_t)15;
+    return s + sizeof(float4) * (size_t)pool * 4 * 32;
 }
 
-extern "C" int b2p_sor_tmem_rows_on_chip(int kr) { return kr + TROWS; }
+// sweep positions per world held in registers + Tensor Memory
+extern "C" int b2p_sor_tmem_rows_on_chip(int kr, int warps) { return kr + 32 / (warps / 4); }
 
 extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxrows, cudaStream_t stream)
 {
-    static size_t configured[3] = {0, 0, 0};
+    static size_t configured[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    const int nw = P->sor_warps;
     // at least half of the SM's shared memory, so that two CTAs never share an SM (the second one would
     // only spin in tcgen05.alloc until the first one releases its columns)
-    size_t smem = b2p_sor_tmem_smem_bytes(nb, maxrows, P->rows_resident);
+    size_t smem = b2p_sor_tmem_smem_bytes(nb, maxrows, P->rows_resident, nw);
     if (smem < 116 * 1024) smem = 116 * 1024;
     void (*kern)(const StepParams) = nullptr;
-    switch (P->rows_registers) {
-    case 0: kern = b2p_sor_tmem_kernel<0>; break;
-    case 4: kern = b2p_sor_tmem_kernel<4>; break;
-    case 8: kern = b2p_sor_tmem_kernel<8>; break;
-    default: return cudaErrorInvalidValue;
+    if (nw == 4) {
+        switch (P->rows_registers) {
+        case 0: kern = b2p_sor_tmem_kernel<0, 4>; break;
+        case 4: kern = b2p_sor_tmem_kernel<4, 4>; break;
+        case 8: kern = b2p_sor_tmem_kernel<8, 4>; break;
+        default: return cudaErrorInvalidValue;
+        }
+    } else if (nw == 8) {
+        switch (P->rows_registers) {
+        case 0: kern = b2p_sor_tmem_kernel<0, 8>; break;
+        case 4: kern = b2p_sor_tmem_kernel<4, 8>; break;
+        case 8: kern = b2p_sor_tmem_kernel<8, 8>; break;
+        default: return cudaErrorInvalidValue;
+        }
+    } else {
+        return cudaErrorInvalidValue;
     }
     const int ci = P->rows_registers / 4;
-    if (smem > configured[ci]) {
+    if (smem > configured[nw / 8][ci]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured[ci] = smem;
+        configured[nw / 8][ci] = smem;
     }
-    const int grid = (P->W + TW - 1) / TW;
-    kern<<<grid, TW, smem, stream>>>(*P);
+    const int tw = nw * 32;
+    const int grid = (P->W + P->worlds_per_cta - 1) / P->worlds_per_cta;
+    kern<<<grid, tw, smem, stream>>>(*P);
     return cudaGetLastError();
 }

@@ -143,11 +143,12 @@ def test_determinism_bitwise(cuda_lib):
     assert np.array_equal(outs[0], outs[1])
 
 
-def _rover_arena(W, kernel, register_rows=-1, resident_rows=0):
+def _rover_arena(W, kernel, register_rows=-1, resident_rows=0, warps=0):
     import bench
     ar = Arena(W)
     sc = bench.build_rover_worlds(ar, W)
     ar.set_sor_kernel(kernel)
+    ar.set_sor_warps(warps)
     if register_rows >= 0:
         ar.set_register_rows(register_rows)
     if resident_rows:
@@ -165,17 +166,21 @@ def _run_rover(ar, sc, steps):
     return ar.state_download(nb).copy(), seeds, fb
 
 
-@pytest.mark.parametrize("W", [200, 128 + 32])
+@pytest.mark.parametrize("W", [300, 256 + 32])
 def test_sor_kernels_agree(cuda_lib, W):
     """The two SOR-LCP kernels (rows in registers + shared memory, two lanes per world; rows in registers +
     Tensor Memory, one lane per world) do the same arithmetic in the same order: bitwise identical states,
     RNG states and joint feedback on the rover-on-heightfield scene, through the drop phase and with
-    contacts, for world counts that leave partly filled warps and CTAs."""
+    contacts, for world counts that leave partly filled warps and CTAs.  The Tensor-Memory kernel runs with 4 and
+    8 warps per CTA, with and without register rows, and with an overflow pool too small for its long worlds
+    (rows then come from L2 in place)."""
     runs = {}
-    for name, kernel, kr, rs in (("paired", capi.SOR_PAIRED, -1, 0), ("tmem", capi.SOR_TMEM, -1, 0),
-                                 ("paired_spill", capi.SOR_PAIRED, 8, 6), ("tmem_kr0", capi.SOR_TMEM, 0, 0),
-                                 ("paired_smem_only", capi.SOR_PAIRED, 0, 0)):
-        ar, sc = _rover_arena(W, kernel, kr, rs)
+    for name, kernel, kr, rs, nw in (("paired", capi.SOR_PAIRED, -1, 0, 0), ("tmem8", capi.SOR_TMEM, -1, 0, 8),
+                                     ("tmem4", capi.SOR_TMEM, -1, 0, 4), ("paired_spill", capi.SOR_PAIRED, 8, 6, 0),
+                                     ("tmem8_kr0_small_pool", capi.SOR_TMEM, 0, 3, 8),
+                                     ("tmem4_kr4", capi.SOR_TMEM, 4, 0, 4),
+                                     ("paired_smem_only", capi.SOR_PAIRED, 0, 0, 0)):
+        ar, sc = _rover_arena(W, kernel, kr, rs, nw)
         runs[name] = _run_rover(ar, sc, 260)
         assert ar.sor_kernel_used() == kernel
         ar.close()
@@ -189,14 +194,16 @@ def test_sor_kernels_agree(cuda_lib, W):
 
 
 def test_tmem_kernel_spills_large_scene(cuda_lib):
-    """Forced onto a scene whose rows exceed registers + TMEM + shared-memory overflow (12-hinge quadruped,
-    75+ rows per world), the Tensor-Memory kernel reads the excess rows from global memory in place and still
-    matches the paired-lane kernel bitwise; left alone, the arena picks the paired-lane kernel there."""
+    """Forced onto a scene whose rows exceed registers + TMEM and (with a pool of 8 units for 3 warps) the
+    shared-memory overflow pool (12-hinge quadruped, 75+ rows per world), the Tensor-Memory kernel reads the
+    excess rows from global memory in place and still matches the paired-lane kernel bitwise."""
     outs = {}
-    for kernel in (capi.SOR_AUTO, capi.SOR_TMEM):
+    for name, kernel, pool in (("paired", capi.SOR_PAIRED, 0), ("tmem", capi.SOR_TMEM, 0), ("tmem_spill", capi.SOR_TMEM, 8)):
         ar = Arena(70)
         sc = scenes.quadruped(ar)
         ar.set_sor_kernel(kernel)
+        if pool:
+            ar.set_resident_rows(pool)
         t = 0.0
         for step in range(40):
             ar.contacts_clear()
@@ -205,7 +212,8 @@ def test_tmem_kernel_spills_large_scene(cuda_lib):
                 scenes.sphere_plane_contacts(ar, sc["feet"], sc["foot_radius"], w)
             ar.step(H)
             t += H
-        outs[kernel] = (ar.state_download(len(sc["bodies"])).copy(), ar.sor_kernel_used())
+        assert ar.sor_kernel_used() == kernel
+        outs[name] = ar.state_download(len(sc["bodies"])).copy()
         ar.close()
-    assert outs[capi.SOR_AUTO][1] == capi.SOR_PAIRED and outs[capi.SOR_TMEM][1] == capi.SOR_TMEM
-    assert np.array_equal(outs[capi.SOR_AUTO][0], outs[capi.SOR_TMEM][0])
+    assert np.array_equal(outs["paired"], outs["tmem"])
+    assert np.array_equal(outs["paired"], outs["tmem_spill"])
