@@ -587,11 +587,11 @@ int finalize(b2p_arena *a)
             // the dummy multiplier (slot maxrows), the constant-1 multiplier (maxrows + 1) and the dummy body nb
             const uint32_t zm = (uint32_t)maxrows | ((uint32_t)(maxrows + 1) << 8) | ((uint32_t)nb << 16) |
                                 ((uint32_t)nb << 24);
-            std::vector<float4> z(Wp);
+            std::vector<float4> z(Wp * 2); // unit 1 of slot maxrows: [Wp][2 float4]
             float mf;
             memcpy(&mf, &zm, sizeof(mf));
-            for (float4 &q : z) q = make_float4(0.f, 0.f, 0.f, mf);
-            CUDA_TRY(cudaMemcpyAsync(a->d_rows + ((size_t)maxrows * 4 + 3) * Wp, z.data(), sizeof(float4) * Wp,
+            for (size_t i = 0; i < Wp; i++) z[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f), z[2 * i + 1] = make_float4(0.f, 0.f, 0.f, mf);
+            CUDA_TRY(cudaMemcpyAsync(a->d_rows + ((size_t)maxrows * 2 + 1) * Wp * 2, z.data(), sizeof(float4) * Wp * 2,
                                      cudaMemcpyHostToDevice, a->stream));
             CUDA_TRY(cudaStreamSynchronize(a->stream));
         }

@@ -128,13 +128,12 @@ __device__ __forceinline__ float emit_row(const StepParams &P, const Smem &S, in
     const int R = P.T->maxrows;
     const uint32_t meta = (uint32_t)slot | ((uint32_t)(r.fr ? r.fr - 1 : R + 1) << 8) | ((uint32_t)pc.b0 << 16) |
                           ((uint32_t)(pc.b1 < 0 ? P.T->nb : pc.b1) << 24) | ((uint32_t)kind << 30);
-    // vectors: J0..J3 | J4..J7 | J8..J11 | rhs' cfm' bound meta  (J0..J5 = body-0 side, J6..J11 = body-1 side:
+    // two 32-byte units: J0..J7 | J8..J11 rhs' cfm' bound meta  (J0..J5 = body-0 side, J6..J11 = body-1 side:
     // the SOR kernel gives each side of a world its own lane)
-    float4 *dst = P.rows + (size_t)(slot * 4) * Wp + w;
-    dst[0 * (size_t)Wp] = make_float4(sa * o[0], sa * o[1], sa * o[2], sa * o[3]);
-    dst[1 * (size_t)Wp] = make_float4(sa * o[4], sa * o[5], sa * o[6], sa * o[7]);
-    dst[2 * (size_t)Wp] = make_float4(sa * o[8], sa * o[9], sa * o[10], sa * o[11]);
-    dst[3 * (size_t)Wp] = make_float4(sa * rhs, cfm * Ad, bound, __uint_as_float(meta));
+    stg256(ROW_UNIT(P.rows, slot, 0, Wp, w), make_float4(sa * o[0], sa * o[1], sa * o[2], sa * o[3]),
+           make_float4(sa * o[4], sa * o[5], sa * o[6], sa * o[7]));
+    stg256(ROW_UNIT(P.rows, slot, 1, Wp, w), make_float4(sa * o[8], sa * o[9], sa * o[10], sa * o[11]),
+           make_float4(sa * rhs, cfm * Ad, bound, __uint_as_float(meta)));
     P.rowS[(size_t)slot * Wp + w] = sa;
     return sa;
 }

@@ -14,9 +14,10 @@
 //   cfb     float[maxc*3][Wp]  contact feedback f1
 //   seed    uint32[Wp]         per-world LCG state                (dRandSetSeed)
 //   nrows   int[Wp]            rows of the last step | independent ("head") rows << 16
-//   rows    float4[maxrows*4][Wp]  constraint rows in ODE's initial sweep order (slot = position at
-//                              iteration 0): 12 mass- and Ad-scaled Jacobian words, rhs', cfm', bound, meta;
-//                              one more slot (index maxrows) holds an all-zero row for every world
+//   rows    float[maxrows][2][Wp][8]  constraint rows in ODE's initial sweep order (slot = position at
+//                              iteration 0) as two 32-byte units per world: J0..J7 | J8..J11 rhs' cfm' bound meta
+//                              (12 mass- and Ad-scaled Jacobian words); one more slot (index maxrows) holds an
+//                              all-zero row for every world.  ROW_UNIT(rows, slot, u, Wp, w) addresses a unit
 //   lambda  float[maxrows][Wp] scaled multipliers by slot;  rowS float[maxrows][Wp]  sqrt(Ad) by slot
 //   fcacc   float[nb*6][Wp]    M^-1/2 J^T lambda after the last sweep;  invIw float[nb*9][Wp]
 //   cmap    uint32[maxc][Wp]   rows | depmask<<3 | slot of the normal row<<8 | first dependent slot<<16
@@ -104,7 +105,7 @@ struct StepParams {
     float erp, cfm, contact_max_vel, contact_min_depth, sor_w;
     int iters, reorder;
     float *state, *force, *jcmd, *jobs, *jfb, *crec, *cfb, *lambda, *rowS, *invIw, *fcacc;
-    float4 *rows;   // [slot][4][Wp], slot = position in ODE's initial order (+ the zero row in slot maxrows)
+    float4 *rows;   // [slot][2][Wp] units of two float4; slot = position in ODE's initial order (+ the zero row)
     uint32_t *cmap; // [maxc][Wp]
     uint8_t *jrows; // [nj][Wp]: rows of joint j | (local limit/motor row + 1) << 4
     int *ccount;
@@ -116,6 +117,9 @@ struct StepParams {
     int sor_warps;      // Tensor-Memory SOR kernel: warps per CTA (4 or 8); rows_resident = its overflow pool units
     int worlds_per_cta; // Tensor-Memory SOR kernel: worlds a CTA takes (multiple of 32, <= 32 * sor_warps)
 };
+
+// unit u (0, 1) of the row in `slot` of world w: a pointer to two consecutive float4
+#define ROW_UNIT(rows, slot, u, Wp, w) ((rows) + (((size_t)((slot) * 2 + (u)) * (size_t)(Wp) + (size_t)(w)) * 2))
 
 struct CollideParams {
     const DevTemplate *T;

@@ -131,10 +131,10 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
         for (int q = 0; q < 12; q++) acc[q] = 0.f;
         float flam = 0.f;
         for (int k = 0; k < mrows; k++, slot++) {
-            const float4 *src = P.rows + (size_t)(slot * 4) * Wp + w;
-            const float4 j0 = src[0], j1 = src[(size_t)Wp], j2 = src[2 * (size_t)Wp];
+            const F8 u0 = ldg256(ROW_UNIT(P.rows, slot, 0, Wp, w));
+            const float4 j0 = u0.lo, j1 = u0.hi, j2 = __ldg(ROW_UNIT(P.rows, slot, 1, Wp, w));
             const float lam = G(P.lambda, slot);
-            // row layout (b2p_assemble.cu emit_row): J0..J3 | J4..J7 | J8..J11 | scalars
+            // row layout (b2p_assemble.cu emit_row): J0..J7 | J8..J11 scalars
             acc[0] += j0.x * lam; acc[1] += j0.y * lam; acc[2] += j0.z * lam; acc[3] += j0.w * lam;
             acc[4] += j1.x * lam; acc[5] += j1.y * lam; acc[6] += j1.z * lam; acc[7] += j1.w * lam;
             acc[8] += j2.x * lam; acc[9] += j2.y * lam; acc[10] += j2.z * lam; acc[11] += j2.w * lam;
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
         float f[3] = {0.f, 0.f, 0.f};
         for (int k = 0; k < rows_c; k++) {
             const int s = (k > 0 && (depmask & (1 << (k - 1)))) ? ts++ : hs++;
-            const float4 j0 = P.rows[(size_t)(s * 4) * Wp + w];
+            const float4 j0 = __ldg(ROW_UNIT(P.rows, s, 0, Wp, w));
             const float lam = G(P.lambda, s);
             f[0] += j0.x * lam;
             f[1] += j0.y * lam;

@@ -154,6 +154,28 @@ B2P_HD void normalize4(float *a)
     }
 }
 
+#ifdef __CUDACC__
+// 256-bit global accesses (sm_100: LDG.256 / STG.256).  A constraint row is two 32-byte units; a per-lane
+// gather of a row then costs two 128-byte-line requests per lane instead of four.
+struct F8 {
+    float4 lo, hi;
+};
+__device__ __forceinline__ F8 ldg256(const void *p)
+{
+    F8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg256(void *p, const float4 &lo, const float4 &hi)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w),
+                 "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w)
+                 : "memory");
+}
+#endif
+
 // ODE dPlaneSpace
 B2P_HD void plane_space(const float *n, float *p, float *q)
 {

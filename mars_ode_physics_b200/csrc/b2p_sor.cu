@@ -102,14 +102,14 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
     // this lane's half of the row in slot `slot` of its world, from the slot-ordered rows in global memory
     // (slot R is an all-zero row that names the dummy multiplier and the dummy body)
     auto gload = [&](int slot) -> Row {
-        const float2 *p = (const float2 *)(P.rows + (size_t)(slot * 4) * Wp + w);
-        // words side*6 + {0,2,4} of the 16-word row: vector (word >> 2), half ((word >> 1) & 1)
-        const float2 a = __ldg(p + (size_t)(side ? 1 : 0) * Wp * 2 + (side ? 1 : 0));
-        const float2 b = __ldg(p + (size_t)(side ? 2 : 0) * Wp * 2 + (side ? 0 : 1));
-        const float2 c = __ldg(p + (size_t)(side ? 2 : 1) * Wp * 2 + (side ? 1 : 0));
-        const float4 v3 = __ldg(P.rows + (size_t)(slot * 4 + 3) * Wp + w);
+        // this side's words are side*6 .. side*6 + 5 of the 16-word row = two 32-byte units: side 0 takes unit 0
+        // (J0..J7) and the scalars of unit 1, side 1 takes unit 1 (J8..J11, scalars) and J6 J7 of unit 0
+        const F8 u = ldg256(ROW_UNIT(P.rows, slot, side, Wp, w));
+        const float4 x = __ldg(ROW_UNIT(P.rows, slot, side ^ 1, Wp, w) + 1);
+        const float4 v3 = side ? u.hi : x;
         Row q;
-        q.j0 = a.x, q.j1 = a.y, q.j2 = b.x, q.j3 = b.y, q.j4 = c.x, q.j5 = c.y;
+        q.j0 = side ? x.z : u.lo.x, q.j1 = side ? x.w : u.lo.y, q.j2 = side ? u.lo.x : u.lo.z;
+        q.j3 = side ? u.lo.y : u.lo.w, q.j4 = side ? u.lo.z : u.hi.x, q.j5 = side ? u.lo.w : u.hi.y;
         q.rhs = v3.x;
         q.cfm = v3.y;
         q.bound = v3.z;
@@ -171,10 +171,10 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rows + (side * 2) * WL + v);
         for (int k = KR; k < ks; k++) {
             const int slot = k < m ? s_ord[k * WL + v] : R;
-            const float4 *src = P.rows + (size_t)(slot * 4 + side * 2) * Wp + w;
+            const float4 *src = ROW_UNIT(P.rows, slot, side, Wp, w); // granules 2*side, 2*side + 1
             const uint32_t d = dst + (uint32_t)((k - KR) * 4 * WL * 16);
             cp_async16(d, src);
-            cp_async16(d + WL * 16, src + Wp);
+            cp_async16(d + WL * 16, src + 1);
         }
         cp_async_commit_wait_all();
         __syncwarp();

@@ -163,8 +163,8 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
 
     // the row in slot `slot` of this world, from the slot-ordered rows in global memory (slot R = zero row)
     auto gload = [&](int slot) -> Row {
-        const float4 *p = P.rows + (size_t)(slot * 4) * Wp + wl;
-        const float4 v0 = __ldg(p), v1 = __ldg(p + Wp), v2 = __ldg(p + 2 * Wp), v3 = __ldg(p + 3 * Wp);
+        const F8 u0 = ldg256(ROW_UNIT(P.rows, slot, 0, Wp, wl)), u1 = ldg256(ROW_UNIT(P.rows, slot, 1, Wp, wl));
+        const float4 v0 = u0.lo, v1 = u0.hi, v2 = u1.lo, v3 = u1.hi;
         Row q;
         q.j[0] = v0.x, q.j[1] = v0.y, q.j[2] = v0.z, q.j[3] = v0.w;
         q.j[4] = v1.x, q.j[5] = v1.y, q.j[6] = v1.z, q.j[7] = v1.w;
@@ -252,7 +252,7 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
         if (fresh) {
             // Streaming sweep: the first sweep in a new order takes every row from the slot-ordered rows in global
             // memory (a per-lane gather; L2 hits after iteration 0), relaxes it, and deposits it at its sweep
-            // position on chip for the sweeps that follow.  The gather of position k+2 is in flight while
+            // position on chip for the sweeps that follow.  The gather of position k+3 is in flight while
             // position k is relaxed, so the gathers -- which are limited by the L1's rate of one 128-byte line
             // per clock, 32 lines per warp instruction -- overlap the arithmetic instead of preceding it.
 #pragma unroll
@@ -260,9 +260,10 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
                 if ((k & ~3) < mmax) rr[k] = gload(slot_at(k));
             }
             const int nchip = nt + no;
-            Row ring[2];
-            ring[0] = gload(slot_at(KR));
-            ring[1] = gload(slot_at(KR + 1));
+            constexpr int NPF = 3; // gathers in flight (rows)
+            Row ring[NPF];
+#pragma unroll
+            for (int i = 0; i < NPF; i++) ring[i] = gload(slot_at(KR + i));
 #pragma unroll
             for (int g = 0; g < KR; g += 4) {
                 if (g < mmax) {
@@ -271,13 +272,13 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
                 }
             }
 #pragma unroll 1
-            for (int p = 0; p < nchip; p += 2) {
+            for (int p = 0; p < nchip; p += NPF) {
 #pragma unroll
-                for (int i = 0; i < 2; i++) {
+                for (int i = 0; i < NPF; i++) {
                     if (p + i < nchip) {
                         relax(ring[i]);
                         deposit(p + i, ring[i]);
-                        ring[i] = gload(p + i + 2 < nchip ? slot_at(KR + p + i + 2) : R);
+                        ring[i] = gload(p + i + NPF < nchip ? slot_at(KR + p + i + NPF) : R);
                     }
                 }
             }
