@@ -344,11 +344,17 @@ def run_b200(args):
     mean_rows = float(np.mean([ar.last_num_rows(w) for w in range(0, W, max(1, W // 256))]))
     # compulsory traffic of the SOR kernel per world: rows in (64 B), lambda out (4 B), fch out, counters
     sor_bytes = mean_rows * 68.0 + nb * 24.0 + 12.0
-    traffic = None
+    sor_name = {capi.SOR_TMEM: "b2p_sor_tmem_kernel (rows in registers + Tensor Memory, one thread per world)",
+                capi.SOR_PAIRED: "b2p_sor_kernel (rows in registers + shared memory, two lanes per world)"}[ar.sor_kernel_used()]
+    # measured DRAM traffic per launch (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum) of the same
+    # command, committed under profiles/ by the round's profiling pass
+    traffic, per_kernel_traffic = None, {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.workload == "D" and W == WORLDS_PER_GPU:
         try:
-            traffic = json.load(open(tpath)).get("step_kernel_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("step_kernel_dram_bytes_per_launch")
+            per_kernel_traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in tj.get("kernels", {}).items()}
         except Exception:
             traffic = None
     if rank == 0:
@@ -369,11 +375,21 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "one step = b2p_assemble_kernel + b2p_sor_kernel + b2p_integrate_kernel",
+                         "kernel": "one dWorldQuickStep = b2p_assemble_kernel + SOR-LCP kernel + b2p_integrate_kernel "
+                                   "(three launches; achieved = algorithmic bytes of the step / their summed duration)",
                          "algorithmic_bytes_per_world_step": balg,
-                         "sor_kernel": {"ms": sor_ms, "io_bytes_per_world": sor_bytes,
+                         "sor_kernel": {"name": sor_name, "ms": sor_ms, "share_of_step": sor_ms / step_ms,
+                                        "io_bytes_per_world": sor_bytes,
                                         "io_gbs": sor_bytes * W / (sor_ms * 1e-3) / 1e9 if sor_ms > 0 else None,
-                                        "row_iterations_per_s": mean_rows * 20 * W / (sor_ms * 1e-3) if sor_ms > 0 else None},
+                                        "measured_dram_gbs": (per_kernel_traffic["sor"] / (sor_ms * 1e-3) / 1e9
+                                                              if "sor" in per_kernel_traffic and sor_ms > 0 else None),
+                                        "row_iterations_per_s": mean_rows * 20 * W / (sor_ms * 1e-3) if sor_ms > 0 else None,
+                                        "bound": "on-chip: dependent smem round trip + FP32 issue per row-iteration "
+                                                 "(DESIGN.md section 4); its HBM traffic is one pass over the rows"},
+                         "measured_dram_gbs": {k: (per_kernel_traffic[k] / (ms_k * 1e-3) / 1e9)
+                                               for k, ms_k in (("assemble", asm_ms), ("sor", sor_ms),
+                                                               ("integrate", int_ms), ("collide", collide_ms))
+                                               if k in per_kernel_traffic and ms_k > 0},
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
             "clocks": sampler.summary(),
             "wall_s": t_wall,
