@@ -186,6 +186,11 @@ int b2p_state_download(b2p_arena *a, float *host_state);
 /* one body of every world: float[13][num_worlds] (asynchronous on the arena stream; call
  * b2p_sync before reading the host buffer) */
 int b2p_body_get_state_batch(b2p_arena *a, int body, float *host_out);
+/* pipelined form for control loops: snapshot on the step's stream, D2H on a separate copy stream so that it
+ * overlaps the next step; returns a ticket (0 or 1, two transfers may be in flight), b2p_io_wait(ticket)
+ * blocks until host_out is complete */
+int b2p_body_get_state_batch_begin(b2p_arena *a, int body, float *host_out);
+int b2p_io_wait(b2p_arena *a, int ticket);
 /* device pointers (float, layout [field][padded_worlds]) for zero-copy consumers */
 int b2p_padded_worlds(const b2p_arena *a);
 void *b2p_device_state(b2p_arena *a);       /* [nb*13][Wp] */

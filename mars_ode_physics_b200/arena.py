@@ -189,6 +189,13 @@ class Arena:
         """Asynchronous D2H of float[13][num_worlds] into (pinned) host memory; sync() before reading."""
         self._check(self.lib.b2p_body_get_state_batch(self.h, b, C.c_void_p(host_ptr)))
 
+    def body_get_state_batch_begin(self, b, host_ptr):
+        """Pipelined D2H (copy stream) of float[13][num_worlds]; returns a ticket for io_wait()."""
+        return self._check(self.lib.b2p_body_get_state_batch_begin(self.h, b, C.c_void_p(host_ptr)))
+
+    def io_wait(self, ticket):
+        self._check(self.lib.b2p_io_wait(self.h, int(ticket)))
+
     # -- joints -----------------------------------------------------------------------------
     def joint_create(self, jtype, b1, b2):
         return self._check(self.lib.b2p_joint_create(self.h, jtype, b1, b2))

@@ -238,6 +238,16 @@ struct b2p_arena {
     int *d_pairs = nullptr, *d_npairs = nullptr;
     int maxpairs = 0;
     int launches = 0;
+    // pipelined observation read-back (b2p_body_get_state_batch_begin / b2p_io_wait): a copy stream and two
+    // staging slots, so that the D2H of step k overlaps the kernels of step k+1
+    struct IoSlot {
+        float *dev = nullptr;
+        size_t elems = 0;
+        cudaEvent_t snap = nullptr, done = nullptr;
+        bool pending = false;
+    } io[2];
+    cudaStream_t io_stream = nullptr;
+    int io_next = 0;
     long long steps_done = 0;
     bool stepped = false;
 };
@@ -786,6 +796,12 @@ void b2p_arena_destroy(b2p_arena *a)
     if (a->d_pairs) cudaFree(a->d_pairs);
     if (a->d_npairs) cudaFree(a->d_npairs);
     if (a->h_hw_rows) cudaFreeHost(a->h_hw_rows);
+    for (b2p_arena::IoSlot &sl : a->io) {
+        if (sl.dev) cudaFree(sl.dev);
+        if (sl.snap) cudaEventDestroy(sl.snap);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
+    if (a->io_stream) cudaStreamDestroy(a->io_stream);
     delete a;
 }
 
@@ -1089,6 +1105,53 @@ int b2p_body_get_state_batch(b2p_arena *a, int body, float *host_out)
     CUDA_TRY(cudaMemcpy2DAsync(host_out, sizeof(float) * a->W,
                                a->state.dev + (size_t)body * B2P_STATE_FIELDS * a->Wp, sizeof(float) * a->Wp,
                                sizeof(float) * a->W, B2P_STATE_FIELDS, cudaMemcpyDeviceToHost, a->stream));
+    return 0;
+}
+
+// Pipelined variant: snapshots the body's state on the compute stream (device-to-device, a few microseconds),
+// then copies the snapshot to the host on a separate copy stream, so the transfer overlaps the next step.
+// Returns a ticket (>= 0) for b2p_io_wait, which blocks until the host buffer is complete.
+int b2p_body_get_state_batch_begin(b2p_arena *a, int body, float *host_out)
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    if (!host_out) return fail(B2P_EINVAL, "host_out is null");
+    CUDA_TRY(cudaSetDevice(a->device));
+    if ((rc = mirror_to_device(a, a->state))) return rc;
+    if (!a->io_stream) CUDA_TRY(cudaStreamCreateWithFlags(&a->io_stream, cudaStreamNonBlocking));
+    const int t = a->io_next;
+    a->io_next ^= 1;
+    b2p_arena::IoSlot &sl = a->io[t];
+    const size_t elems = (size_t)B2P_STATE_FIELDS * a->Wp;
+    if (sl.elems != elems) {
+        if (sl.dev) CUDA_TRY(cudaFree(sl.dev));
+        CUDA_TRY(cudaMalloc(&sl.dev, sizeof(float) * elems));
+        sl.elems = elems;
+    }
+    if (!sl.snap) {
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.snap, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    // the slot's previous transfer must have left the staging buffer before it is overwritten
+    if (sl.pending) CUDA_TRY(cudaStreamWaitEvent(a->stream, sl.done, 0));
+    CUDA_TRY(cudaMemcpyAsync(sl.dev, a->state.dev + (size_t)body * B2P_STATE_FIELDS * a->Wp, sizeof(float) * elems,
+                             cudaMemcpyDeviceToDevice, a->stream));
+    CUDA_TRY(cudaEventRecord(sl.snap, a->stream));
+    CUDA_TRY(cudaStreamWaitEvent(a->io_stream, sl.snap, 0));
+    CUDA_TRY(cudaMemcpy2DAsync(host_out, sizeof(float) * a->W, sl.dev, sizeof(float) * a->Wp, sizeof(float) * a->W,
+                               B2P_STATE_FIELDS, cudaMemcpyDeviceToHost, a->io_stream));
+    CUDA_TRY(cudaEventRecord(sl.done, a->io_stream));
+    sl.pending = true;
+    return t;
+}
+
+int b2p_io_wait(b2p_arena *a, int ticket)
+{
+    if (!a || ticket < 0 || ticket > 1) return fail(B2P_EINVAL, "bad ticket");
+    b2p_arena::IoSlot &sl = a->io[ticket];
+    if (!sl.pending) return 0;
+    CUDA_TRY(cudaSetDevice(a->device));
+    CUDA_TRY(cudaEventSynchronize(sl.done));
     return 0;
 }
 

@@ -217,3 +217,26 @@ def test_tmem_kernel_spills_large_scene(cuda_lib):
         ar.close()
     assert np.array_equal(outs["paired"], outs["tmem"])
     assert np.array_equal(outs["paired"], outs["tmem_spill"])
+
+
+def test_pipelined_state_readback(cuda_lib):
+    """b2p_body_get_state_batch_begin / b2p_io_wait (copy-stream D2H that overlaps the next step) return the
+    state of the step they were issued after, also with two transfers in flight."""
+    import torch
+    W = 100
+    ar, sc = _rover_arena(W, capi.SOR_AUTO)
+    bufs = [torch.empty((13, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+    want, tickets = [], []
+    for k in range(6):
+        ar.collide()
+        ar.step(H)
+        tickets.append(ar.body_get_state_batch_begin(sc["chassis"], bufs[k & 1].data_ptr()))
+        if k >= 1:
+            ar.io_wait(tickets[k - 1])
+            got = bufs[(k - 1) & 1].numpy().copy()
+            assert np.array_equal(got, want[k - 1]), k
+        # reference: the synchronous read of the same state (taken after the begin, before the next step)
+        want.append(ar.state_download(len(sc["bodies"]))[sc["chassis"]].copy())
+    ar.io_wait(tickets[-1])
+    assert np.array_equal(bufs[5 & 1].numpy(), want[5])
+    ar.close()
