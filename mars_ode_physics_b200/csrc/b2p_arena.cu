@@ -29,7 +29,7 @@ extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxr
 extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, cudaStream_t stream);
-extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, cudaStream_t stream);
+extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, int sampled, cudaStream_t stream);
 
 namespace {
 
@@ -1815,7 +1815,15 @@ int b2p_collide(b2p_arena *a)
     P.npairs = a->d_npairs;
     P.maxpairs = a->maxpairs;
     if ((size_t)ng * 6 * 128 * sizeof(float) > 200 * 1024) return fail(B2P_ECAPACITY, "too many geoms for the collide kernel");
-    CUDA_TRY(b2p_launch_collide(&P, ng, a->stream));
+    // the sample-point colliders (cylinders; capsule against box / heightfield) live in a separate kernel variant
+    bool has_cyl = false, has_caps = false, has_box = false;
+    for (const HGeom &g : a->geoms) {
+        has_cyl |= g.cls == B2P_GEOM_CYLINDER;
+        has_caps |= g.cls == B2P_GEOM_CAPSULE;
+        has_box |= g.cls == B2P_GEOM_BOX;
+    }
+    const int sampled = has_cyl || (has_caps && (has_box || a->has_hf));
+    CUDA_TRY(b2p_launch_collide(&P, ng, sampled, a->stream));
     a->launches++;
     a->crec.dev_newer = true;
     a->ccount.dev_newer = true;

@@ -287,6 +287,210 @@ __device__ __forceinline__ int collide_sphere_box(const float *c, float r, const
 // ---- box (g1 = A) vs box (g2 = B): separating-axis test over the 15 axes, then either one edge-edge
 // contact or a reference-face / incident-face clip, keeping the <= 4 deepest clipped points in vertex
 // order.  Mirrors collide_box_box of oracle/orc_collide.c step by step (same tie-breaking).
+
+// ---- colliders built from point / sphere samples (semantics: oracle/orc_collide.c, same names).  All return
+// contacts with the normal pointing from the second geom into the first.
+
+// sphere (centre c, radius r; r = 0: a point) vs solid cylinder; normal from the cylinder into the sphere
+__device__ __noinline__ int collide_sphere_cylinder(const float *c, float r, const DevGeom &gc, const GPose &oc, CPoint &out)
+{
+    const float a[3] = {oc.R[2], oc.R[5], oc.R[8]};
+    const float rel[3] = {c[0] - oc.p[0], c[1] - oc.p[1], c[2] - oc.p[2]};
+    const float z = dot3(rel, a), hl = 0.5f * gc.dims[1], R = gc.dims[0];
+    float rv[3] = {rel[0] - z * a[0], rel[1] - z * a[1], rel[2] - z * a[2]}, er[3], tmp[3];
+    const float rho = sqrtf(dot3(rv, rv));
+    if (rho > 1e-9f) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) er[i] = rv[i] / rho;
+    } else {
+        plane_space(a, er, tmp);
+    }
+    if (fabsf(z) > hl || rho > R) {
+        const float zc = z > hl ? hl : (z < -hl ? -hl : z), rc = rho > R ? R : rho;
+        float q[3], dv[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            q[i] = oc.p[i] + zc * a[i] + rc * er[i];
+            dv[i] = c[i] - q[i];
+        }
+        const float dist = sqrtf(dot3(dv, dv));
+        if (r - dist < 0.f || dist <= 0.f) return 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            out.n[i] = dv[i] / dist;
+            out.pos[i] = q[i];
+        }
+        out.depth = r - dist;
+        return 1;
+    }
+    const float dr = R - rho, dz = hl - fabsf(z);
+    if (dr < dz) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            out.n[i] = er[i];
+            out.pos[i] = oc.p[i] + z * a[i] + R * er[i];
+        }
+        out.depth = r + dr;
+    } else {
+        const float sg = z >= 0.f ? 1.f : -1.f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            out.n[i] = sg * a[i];
+            out.pos[i] = oc.p[i] + sg * hl * a[i] + rho * er[i];
+        }
+        out.depth = r + dz;
+    }
+    return 1;
+}
+
+// the eight rim sample points of a cylinder ('+' cap first: towards dir, away, the two sideways)
+__device__ __noinline__ void cylinder_rim(const DevGeom &g, const GPose &o, const float *dir, float (*pts)[3])
+{
+    const float a[3] = {o.R[2], o.R[5], o.R[8]};
+    float u[3], v[3];
+    const float da = dot3(dir, a);
+#pragma unroll
+    for (int i = 0; i < 3; i++) u[i] = dir[i] - da * a[i];
+    const float lu = sqrtf(dot3(u, u));
+    if (lu > 1e-6f) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) u[i] /= lu;
+    } else {
+        float q[3];
+        plane_space(a, u, q);
+    }
+    cross3(v, a, u);
+    for (int s = 0; s < 2; s++)
+        for (int k = 0; k < 4; k++) {
+            const float su = k == 0 ? 1.f : (k == 1 ? -1.f : 0.f), sv = k == 2 ? 1.f : (k == 3 ? -1.f : 0.f);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                pts[s * 4 + k][i] = o.p[i] + (s == 0 ? 0.5f : -0.5f) * g.dims[1] * a[i] + g.dims[0] * (su * u[i] + sv * v[i]);
+        }
+}
+
+// '+' cap centre, '-' cap centre and the axis point closest to `target` (nmid = 0: it is a cap centre)
+__device__ __forceinline__ void capsule_samples(const DevGeom &g, const GPose &o, const float *target, float (*pts)[3],
+                                                int &nmid)
+{
+    const float a[3] = {o.R[2], o.R[5], o.R[8]}, hl = 0.5f * g.dims[1];
+    const float rel[3] = {target[0] - o.p[0], target[1] - o.p[1], target[2] - o.p[2]};
+    float t = dot3(rel, a);
+    nmid = 1;
+    if (t >= hl) t = hl, nmid = 0;
+    if (t <= -hl) t = -hl, nmid = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        pts[0][i] = o.p[i] + hl * a[i];
+        pts[1][i] = o.p[i] - hl * a[i];
+        pts[2][i] = o.p[i] + t * a[i];
+    }
+}
+
+__device__ __noinline__ int collide_capsule_box(const DevGeom &gc, const GPose &oc, const DevGeom &gb, const GPose &ob,
+                                                CPoint *out)
+{
+    float pts[3][3];
+    int nmid;
+    CPoint cand[3];
+    capsule_samples(gc, oc, ob.p, pts, nmid);
+    for (int k = 0; k < 3; k++) {
+        cand[k].depth = -1.f;
+        if (k == 2 && !nmid) continue;
+        if (!collide_sphere_box(pts[k], gc.dims[0], gb, ob, cand[k])) cand[k].depth = -1.f;
+    }
+    return keep_deepest<3>(cand, out);
+}
+
+__device__ __noinline__ int collide_capsule_cylinder(const DevGeom &gc, const GPose &oc, const DevGeom &gy, const GPose &oy,
+                                                     CPoint *out)
+{
+    float pts[3][3];
+    int nmid;
+    CPoint cand[3];
+    capsule_samples(gc, oc, oy.p, pts, nmid);
+    for (int k = 0; k < 3; k++) {
+        cand[k].depth = -1.f;
+        if (k == 2 && !nmid) continue;
+        if (!collide_sphere_cylinder(pts[k], gc.dims[0], gy, oy, cand[k])) cand[k].depth = -1.f;
+    }
+    return keep_deepest<3>(cand, out);
+}
+
+// direction from a point at c straight into a solid cylinder (minus the outward normal of its nearest surface)
+__device__ __forceinline__ void into_cylinder(const float *c, const DevGeom &g, const GPose &o, float *dir)
+{
+    const float a[3] = {o.R[2], o.R[5], o.R[8]};
+    const float rel[3] = {c[0] - o.p[0], c[1] - o.p[1], c[2] - o.p[2]};
+    const float z = dot3(rel, a);
+    const float rv[3] = {rel[0] - z * a[0], rel[1] - z * a[1], rel[2] - z * a[2]};
+    const float rho = sqrtf(dot3(rv, rv));
+    if (fabsf(z) - 0.5f * g.dims[1] > rho - g.dims[0] || rho <= 1e-9f) {
+        const float sg = z >= 0.f ? 1.f : -1.f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) dir[i] = -sg * a[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++) dir[i] = -rv[i] / rho;
+    }
+}
+
+__device__ __noinline__ int collide_cylinder_box(const DevGeom &gy, const GPose &oy, const DevGeom &gb, const GPose &ob,
+                                                 CPoint *out)
+{
+    CPoint cand[16];
+    float rim[8][3], dir[3];
+    {
+        const float rel[3] = {oy.p[0] - ob.p[0], oy.p[1] - ob.p[1], oy.p[2] - ob.p[2]};
+        int ax = 0;
+        float best = -3.0e38f, lax = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const float l = ob.R[i] * rel[0] + ob.R[3 + i] * rel[1] + ob.R[6 + i] * rel[2];
+            const float m = fabsf(l) - 0.5f * gb.dims[i];
+            if (m > best) best = m, ax = i, lax = l;
+        }
+        const float sg = lax >= 0.f ? 1.f : -1.f;
+        for (int i = 0; i < 3; i++) dir[i] = -sg * ob.R[3 * i + ax];
+    }
+    cylinder_rim(gy, oy, dir, rim);
+    for (int k = 0; k < 8; k++)
+        if (!collide_sphere_box(rim[k], 0.f, gb, ob, cand[k])) cand[k].depth = -1.f;
+    for (int k = 0; k < 8; k++) {
+        float v[3];
+        box_vertex(gb, ob, k, v);
+        if (!collide_sphere_cylinder(v, 0.f, gy, oy, cand[8 + k])) {
+            cand[8 + k].depth = -1.f;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; i++) cand[8 + k].n[i] = -cand[8 + k].n[i];
+        }
+    }
+    return keep_deepest<16>(cand, out);
+}
+
+__device__ __noinline__ int collide_cylinder_cylinder(const DevGeom &ga, const GPose &oa, const DevGeom &gb, const GPose &ob,
+                                                      CPoint *out)
+{
+    CPoint cand[16];
+    float rim[8][3], dir[3];
+    into_cylinder(oa.p, gb, ob, dir);
+    cylinder_rim(ga, oa, dir, rim);
+    for (int k = 0; k < 8; k++)
+        if (!collide_sphere_cylinder(rim[k], 0.f, gb, ob, cand[k])) cand[k].depth = -1.f;
+    into_cylinder(ob.p, ga, oa, dir);
+    cylinder_rim(gb, ob, dir, rim);
+    for (int k = 0; k < 8; k++) {
+        if (!collide_sphere_cylinder(rim[k], 0.f, ga, oa, cand[8 + k])) {
+            cand[8 + k].depth = -1.f;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 3; i++) cand[8 + k].n[i] = -cand[8 + k].n[i];
+        }
+    }
+    return keep_deepest<16>(cand, out);
+}
+
 __device__ __forceinline__ int clip_polygon(const float (*in)[3], int n, const float *pn, float pd, float (*out)[3])
 {
     int m = 0;
@@ -660,6 +864,36 @@ __device__ __forceinline__ int collide_box_hf(const DevHeightfield &hf, const De
     return keep_deepest<8>(cand, out);
 }
 
+
+__device__ __noinline__ int collide_capsule_hf(const DevHeightfield &hf, const DevGeom &g, const GPose &o, CPoint *out)
+{
+    float pts[3][3];
+    int nmid;
+    CPoint cand[3];
+    capsule_samples(g, o, o.p, pts, nmid);
+    for (int k = 0; k < 3; k++)
+        if (!collide_sphere_hf(hf, pts[k], g.dims[0], cand[k])) cand[k].depth = -1.f;
+    return keep_deepest<3>(cand, out);
+}
+
+__device__ __noinline__ int collide_cylinder_hf(const DevHeightfield &hf, const DevGeom &g, const GPose &o, CPoint *out)
+{
+    CPoint cand[8];
+    float rim[8][3];
+    const float down[3] = {0.f, 0.f, -1.f};
+    cylinder_rim(g, o, down, rim);
+    for (int k = 0; k < 8; k++) {
+        float h, n[3];
+        cand[k].pos[0] = rim[k][0], cand[k].pos[1] = rim[k][1], cand[k].pos[2] = rim[k][2];
+        cand[k].depth = -1.f;
+        if (hf_sample(hf, rim[k][0], rim[k][1], h, n) && rim[k][2] <= h) {
+            cand[k].depth = (h - rim[k][2]) * n[2];
+            cand[k].n[0] = n[0], cand[k].n[1] = n[1], cand[k].n[2] = n[2];
+        }
+    }
+    return keep_deepest<8>(cand, out);
+}
+
 __device__ __forceinline__ void flip(CPoint *c, int n)
 {
     for (int k = 0; k < n; k++) {
@@ -670,6 +904,7 @@ __device__ __forceinline__ void flip(CPoint *c, int n)
 }
 
 // g1 is dynamic; g2 dynamic or static.  Contacts have the normal pointing from g2 into g1.
+template <bool SAMPLED>
 __device__ __forceinline__ int narrowphase(const CollideParams &P, const DevTemplate *T, const DevGeom &g1,
                                            const DevGeom &g2, int w, CPoint *out)
 {
@@ -680,6 +915,8 @@ __device__ __forceinline__ int narrowphase(const CollideParams &P, const DevTemp
     if (c2 == 5) {
         if (c1 == 0) return collide_sphere_hf(T->hf, o1.p, g1.dims[0], out[0]);
         if (c1 == 1) return collide_box_hf(T->hf, g1, o1, out);
+        if (SAMPLED && c1 == 2) return collide_capsule_hf(T->hf, g1, o1, out);
+        if (SAMPLED && c1 == 3) return collide_cylinder_hf(T->hf, g1, o1, out);
         return 0;
     }
     geom_pose(P, g2, w, o2);
@@ -710,10 +947,39 @@ __device__ __forceinline__ int narrowphase(const CollideParams &P, const DevTemp
         closest_seg_seg(p1, d1, p2, d2, q1, q2);
         return collide_sphere_sphere(q1, g1.dims[0], q2, g2.dims[0], out[0]);
     }
-    return 0;
+    if (!SAMPLED) return 0;
+    int n = 0;
+    if (c1 == 2 && c2 == 1) return collide_capsule_box(g1, o1, g2, o2, out);
+    if (c1 == 1 && c2 == 2) {
+        n = collide_capsule_box(g2, o2, g1, o1, out);
+        flip(out, n);
+        return n;
+    }
+    if (c1 == 0 && c2 == 3) return collide_sphere_cylinder(o1.p, g1.dims[0], g2, o2, out[0]);
+    if (c1 == 3 && c2 == 0) {
+        n = collide_sphere_cylinder(o2.p, g2.dims[0], g1, o1, out[0]);
+        flip(out, n);
+        return n;
+    }
+    if (c1 == 2 && c2 == 3) return collide_capsule_cylinder(g1, o1, g2, o2, out);
+    if (c1 == 3 && c2 == 2) {
+        n = collide_capsule_cylinder(g2, o2, g1, o1, out);
+        flip(out, n);
+        return n;
+    }
+    if (c1 == 3 && c2 == 1) return collide_cylinder_box(g1, o1, g2, o2, out);
+    if (c1 == 1 && c2 == 3) {
+        n = collide_cylinder_box(g2, o2, g1, o1, out);
+        flip(out, n);
+        return n;
+    }
+    if (c1 == 3 && c2 == 3) return collide_cylinder_cylinder(g1, o1, g2, o2, out);
+    return 0; // planes / heightfields against each other
 }
 
-__global__ void __launch_bounds__(CBD) b2p_collide_kernel(const CollideParams P)
+// SAMPLED: the scene has geom pairs handled by the sample-point colliders (cylinders; capsule against box or
+// heightfield).  Scenes without them run the variant that does not carry that code's registers and stack.
+template <bool SAMPLED> __global__ void __launch_bounds__(CBD) b2p_collide_kernel(const CollideParams P)
 {
     extern __shared__ float saabb[]; // [ng*6][CBD]: centre, half extents
     const DevTemplate *__restrict__ T = P.T;
@@ -777,7 +1043,7 @@ __global__ void __launch_bounds__(CBD) b2p_collide_kernel(const CollideParams P)
             CPoint pts[MAXPC];
             const DevGeom &g1 = i_dyn ? gi : gj;
             const DevGeom &g2 = i_dyn ? gj : gi;
-            const int n = narrowphase(P, T, g1, g2, w, pts);
+            const int n = narrowphase<SAMPLED>(P, T, g1, g2, w, pts);
             const float mu = fminf(g1.mu, g2.mu), mu2 = fminf(g1.mu2, g2.mu2);
             const float rho = fminf(g1.rho, g2.rho), rho2 = fminf(g1.rho2, g2.rho2), rhoN = fminf(g1.rhoN, g2.rhoN);
             const float serp = fminf(g1.soft_erp, g2.soft_erp), scfm = fmaxf(g1.soft_cfm, g2.soft_cfm);
@@ -814,17 +1080,17 @@ __global__ void __launch_bounds__(CBD) b2p_collide_kernel(const CollideParams P)
 
 } // namespace
 
-extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, cudaStream_t stream)
+extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, int sampled, cudaStream_t stream)
 {
-    static size_t configured = 0;
+    static size_t configured[2] = {0, 0};
     const size_t smem = sizeof(float) * (size_t)(ng > 0 ? ng : 1) * 6 * CBD;
-    if (smem > configured) {
-        cudaError_t e =
-            cudaFuncSetAttribute(b2p_collide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = sampled ? b2p_collide_kernel<true> : b2p_collide_kernel<false>;
+    if (smem > configured[sampled ? 1 : 0]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[sampled ? 1 : 0] = smem;
     }
     const int grid = (P->W + CBD - 1) / CBD;
-    b2p_collide_kernel<<<grid, CBD, smem, stream>>>(*P);
+    kern<<<grid, CBD, smem, stream>>>(*P);
     return cudaGetLastError();
 }

@@ -254,6 +254,208 @@ static int collide_sphere_box(const double *c, double r, const orc_geom *gb, con
 }
 
 
+
+/* ---- colliders built from point / sphere samples (this repository's own definitions: the reference has no
+ * narrowphase).  All of them return contacts with the normal pointing from the
+ * second geom into the first. ---- */
+
+/* sphere (centre c, radius r) vs solid cylinder: closest point on the cylinder, or -- centre inside --
+ * push-out through the nearer of side and cap (cap on a tie).  r = 0 tests a point.  Normal from the
+ * cylinder into the sphere. */
+static int collide_sphere_cylinder(const double *c, double r, const orc_geom *gc, const gpose *oc, cpoint *out)
+{
+    const double a[3] = {oc->R[2], oc->R[5], oc->R[8]};
+    const double rel[3] = {c[0] - oc->p[0], c[1] - oc->p[1], c[2] - oc->p[2]};
+    const double z = ddot(rel, a), hl = 0.5 * gc->dims[1], R = gc->dims[0];
+    double rv[3] = {rel[0] - z * a[0], rel[1] - z * a[1], rel[2] - z * a[2]}, er[3], tmp[3];
+    const double rho = sqrt(ddot(rv, rv));
+    if (rho > 1e-9) {
+        for (int i = 0; i < 3; i++) er[i] = rv[i] / rho;
+    } else {
+        double aa[3] = {a[0], a[1], a[2]};
+        orc_plane_space(aa, er, tmp);
+    }
+    if (fabs(z) > hl || rho > R) {
+        const double zc = z > hl ? hl : (z < -hl ? -hl : z), rc = rho > R ? R : rho;
+        double q[3], dv[3];
+        for (int i = 0; i < 3; i++) {
+            q[i] = oc->p[i] + zc * a[i] + rc * er[i];
+            dv[i] = c[i] - q[i];
+        }
+        const double dist = sqrt(ddot(dv, dv));
+        if (r - dist < 0 || dist <= 0) return 0;
+        for (int i = 0; i < 3; i++) {
+            out->normal[i] = dv[i] / dist;
+            out->pos[i] = q[i];
+        }
+        out->depth = r - dist;
+        return 1;
+    }
+    const double dr = R - rho, dz = hl - fabs(z);
+    if (dr < dz) {
+        for (int i = 0; i < 3; i++) {
+            out->normal[i] = er[i];
+            out->pos[i] = oc->p[i] + z * a[i] + R * er[i];
+        }
+        out->depth = r + dr;
+    } else {
+        const double sg = z >= 0 ? 1.0 : -1.0;
+        for (int i = 0; i < 3; i++) {
+            out->normal[i] = sg * a[i];
+            out->pos[i] = oc->p[i] + sg * hl * a[i] + rho * er[i];
+        }
+        out->depth = r + dz;
+    }
+    return 1;
+}
+
+/* the eight rim sample points of a cylinder: on each cap ('+' first) the points towards `dir` (projected into
+ * the cap plane), away from it, and the two sideways */
+static void cylinder_rim(const orc_geom *g, const gpose *o, const double *dir, double (*pts)[3])
+{
+    const double a[3] = {o->R[2], o->R[5], o->R[8]};
+    double u[3], v[3];
+    const double da = ddot(dir, a);
+    for (int i = 0; i < 3; i++) u[i] = dir[i] - da * a[i];
+    const double lu = sqrt(ddot(u, u));
+    if (lu > 1e-6) {
+        for (int i = 0; i < 3; i++) u[i] /= lu;
+    } else {
+        double aa[3] = {a[0], a[1], a[2]}, q[3];
+        orc_plane_space(aa, u, q);
+    }
+    dcross(v, a, u);
+    const double sgn[4][2] = {{1, 0}, {-1, 0}, {0, 1}, {0, -1}};
+    for (int s = 0; s < 2; s++)
+        for (int k = 0; k < 4; k++)
+            for (int i = 0; i < 3; i++)
+                pts[s * 4 + k][i] = o->p[i] + (s == 0 ? 0.5 : -0.5) * g->dims[1] * a[i] +
+                                    g->dims[0] * (sgn[k][0] * u[i] + sgn[k][1] * v[i]);
+}
+
+/* the three sample points on a capsule's axis: '+' cap centre, '-' cap centre, and the axis point closest to
+ * `target` (t = 2: it coincides with a cap centre and is skipped) */
+static void capsule_samples(const orc_geom *g, const gpose *o, const double *target, double (*pts)[3], int *nmid)
+{
+    const double a[3] = {o->R[2], o->R[5], o->R[8]}, hl = 0.5 * g->dims[1];
+    const double rel[3] = {target[0] - o->p[0], target[1] - o->p[1], target[2] - o->p[2]};
+    double t = ddot(rel, a);
+    *nmid = 1;
+    if (t >= hl) t = hl, *nmid = 0;
+    if (t <= -hl) t = -hl, *nmid = 0;
+    for (int i = 0; i < 3; i++) {
+        pts[0][i] = o->p[i] + hl * a[i];
+        pts[1][i] = o->p[i] - hl * a[i];
+        pts[2][i] = o->p[i] + t * a[i];
+    }
+}
+
+/* capsule (first) vs box: sphere-box at the capsule's three axis samples */
+static int collide_capsule_box(const orc_geom *gc, const gpose *oc, const orc_geom *gb, const gpose *ob, cpoint *out)
+{
+    double pts[3][3];
+    int nmid, nout = 0;
+    cpoint cand[3];
+    capsule_samples(gc, oc, ob->p, pts, &nmid);
+    for (int k = 0; k < 3; k++) {
+        cand[k].depth = -1;
+        if (k == 2 && !nmid) continue;
+        if (!collide_sphere_box(pts[k], gc->dims[0], gb, ob, &cand[k])) cand[k].depth = -1;
+    }
+    keep_deepest(cand, 3, out, &nout);
+    return nout;
+}
+
+/* capsule (first) vs cylinder: sphere-cylinder at the capsule's three axis samples */
+static int collide_capsule_cylinder(const orc_geom *gc, const gpose *oc, const orc_geom *gy, const gpose *oy, cpoint *out)
+{
+    double pts[3][3];
+    int nmid, nout = 0;
+    cpoint cand[3];
+    capsule_samples(gc, oc, oy->p, pts, &nmid);
+    for (int k = 0; k < 3; k++) {
+        cand[k].depth = -1;
+        if (k == 2 && !nmid) continue;
+        if (!collide_sphere_cylinder(pts[k], gc->dims[0], gy, oy, &cand[k])) cand[k].depth = -1;
+    }
+    keep_deepest(cand, 3, out, &nout);
+    return nout;
+}
+
+/* direction from a point at `c` straight into a solid cylinder: minus the outward normal of the surface (cap or
+ * side) the point is nearest to / would leave through */
+static void into_cylinder(const double *c, const orc_geom *g, const gpose *o, double *dir)
+{
+    const double a[3] = {o->R[2], o->R[5], o->R[8]};
+    const double rel[3] = {c[0] - o->p[0], c[1] - o->p[1], c[2] - o->p[2]};
+    const double z = ddot(rel, a);
+    double rv[3] = {rel[0] - z * a[0], rel[1] - z * a[1], rel[2] - z * a[2]};
+    const double rho = sqrt(ddot(rv, rv));
+    if (fabs(z) - 0.5 * g->dims[1] > rho - g->dims[0] || rho <= 1e-9) {
+        const double sg = z >= 0 ? 1.0 : -1.0;
+        for (int i = 0; i < 3; i++) dir[i] = -sg * a[i];
+    } else {
+        for (int i = 0; i < 3; i++) dir[i] = -rv[i] / rho;
+    }
+}
+
+/* cylinder (first) vs box: the cylinder's rim samples (towards the box face its centre is nearest to) inside
+ * the box, then the box's vertices inside the cylinder; the <= 4 deepest */
+static int collide_cylinder_box(const orc_geom *gy, const gpose *oy, const orc_geom *gb, const gpose *ob, cpoint *out)
+{
+    cpoint cand[16];
+    double rim[8][3], dir[3];
+    int nout = 0;
+    {
+        const double rel[3] = {oy->p[0] - ob->p[0], oy->p[1] - ob->p[1], oy->p[2] - ob->p[2]};
+        int ax = 0;
+        double best = -1e300, lax = 0;
+        for (int i = 0; i < 3; i++) {
+            const double l = ob->R[i] * rel[0] + ob->R[3 + i] * rel[1] + ob->R[6 + i] * rel[2];
+            const double m = fabs(l) - 0.5 * gb->dims[i];
+            if (m > best) best = m, ax = i, lax = l;
+        }
+        const double sg = lax >= 0 ? 1.0 : -1.0;
+        for (int i = 0; i < 3; i++) dir[i] = -sg * ob->R[3 * i + ax];
+    }
+    cylinder_rim(gy, oy, dir, rim);
+    for (int k = 0; k < 8; k++)
+        if (!collide_sphere_box(rim[k], 0.0, gb, ob, &cand[k])) cand[k].depth = -1;
+    for (int k = 0; k < 8; k++) {
+        double v[3];
+        box_vertex(gb, ob, k, v);
+        if (!collide_sphere_cylinder(v, 0.0, gy, oy, &cand[8 + k]))
+            cand[8 + k].depth = -1;
+        else
+            for (int i = 0; i < 3; i++) cand[8 + k].normal[i] = -cand[8 + k].normal[i];
+    }
+    keep_deepest(cand, 16, out, &nout);
+    return nout;
+}
+
+/* cylinder (first) vs cylinder: rim samples of each (towards the other's nearest surface) inside the other;
+ * the <= 4 deepest */
+static int collide_cylinder_cylinder(const orc_geom *ga, const gpose *oa, const orc_geom *gb, const gpose *ob, cpoint *out)
+{
+    cpoint cand[16];
+    double rim[8][3], dir[3];
+    int nout = 0;
+    into_cylinder(oa->p, gb, ob, dir);
+    cylinder_rim(ga, oa, dir, rim);
+    for (int k = 0; k < 8; k++)
+        if (!collide_sphere_cylinder(rim[k], 0.0, gb, ob, &cand[k])) cand[k].depth = -1;
+    into_cylinder(ob->p, ga, oa, dir);
+    cylinder_rim(gb, ob, dir, rim);
+    for (int k = 0; k < 8; k++) {
+        if (!collide_sphere_cylinder(rim[k], 0.0, ga, oa, &cand[8 + k]))
+            cand[8 + k].depth = -1;
+        else
+            for (int i = 0; i < 3; i++) cand[8 + k].normal[i] = -cand[8 + k].normal[i];
+    }
+    keep_deepest(cand, 16, out, &nout);
+    return nout;
+}
+
 /* ---- box (g1 = A) vs box (g2 = B): separating-axis test over the 15 axes, then either one
  * edge-edge contact or a reference-face / incident-face clip (Sutherland-Hodgman), keeping the <= 4
  * deepest clipped points in vertex order.  Same structure as ODE's dBoxBox (box.cpp), own
@@ -633,6 +835,43 @@ static int collide_box_hf(const orc_world *w, const orc_geom *g, const gpose *o,
     return nout;
 }
 
+
+/* capsule vs heightfield: sphere-heightfield at both cap centres and the capsule's centre */
+static int collide_capsule_hf(const orc_world *w, const orc_geom *g, const gpose *o, cpoint *out)
+{
+    if (!w->hf_heights) return 0;
+    double pts[3][3];
+    int nmid, nout = 0;
+    cpoint cand[3];
+    capsule_samples(g, o, o->p, pts, &nmid);
+    for (int k = 0; k < 3; k++)
+        if (!collide_sphere_hf(w, pts[k], g->dims[0], &cand[k])) cand[k].depth = -1;
+    keep_deepest(cand, 3, out, &nout);
+    return nout;
+}
+
+/* cylinder vs heightfield: the rim samples (towards -z) below the surface, as the box's vertices */
+static int collide_cylinder_hf(const orc_world *w, const orc_geom *g, const gpose *o, cpoint *out)
+{
+    if (!w->hf_heights) return 0;
+    cpoint cand[8];
+    double rim[8][3];
+    const double down[3] = {0, 0, -1};
+    int nout = 0;
+    cylinder_rim(g, o, down, rim);
+    for (int k = 0; k < 8; k++) {
+        double h, n[3];
+        memcpy(cand[k].pos, rim[k], sizeof(rim[k]));
+        cand[k].depth = -1;
+        if (hf_sample(w, rim[k][0], rim[k][1], &h, n) && rim[k][2] <= h) {
+            cand[k].depth = (h - rim[k][2]) * n[2];
+            memcpy(cand[k].normal, n, sizeof(n));
+        }
+    }
+    keep_deepest(cand, 8, out, &nout);
+    return nout;
+}
+
 /* ---- dispatch: g1 dynamic-or-static, g2; returns contacts with normal from g2 into g1 ---- */
 static void flip(cpoint *c, int n)
 {
@@ -650,6 +889,8 @@ static int narrowphase(const orc_world *w, const orc_geom *g1, const orc_geom *g
     if (c2 == 5) {
         if (c1 == 0) return collide_sphere_hf(w, o1.p, g1->dims[0], out);
         if (c1 == 1) return collide_box_hf(w, g1, &o1, out);
+        if (c1 == 2) return collide_capsule_hf(w, g1, &o1, out);
+        if (c1 == 3) return collide_cylinder_hf(w, g1, &o1, out);
         return 0;
     }
     if (c1 == 1 && c2 == 1) return collide_box_box(g1, &o1, g2, &o2, out);
@@ -681,7 +922,33 @@ static int narrowphase(const orc_world *w, const orc_geom *g1, const orc_geom *g
         closest_seg_seg(p1, d1, p2, d2, q1, q2);
         return collide_sphere_sphere(q1, g1->dims[0], q2, g2->dims[0], out);
     }
-    return 0; /* pair type without a collider */
+    int n = 0;
+    if (c1 == 2 && c2 == 1) return collide_capsule_box(g1, &o1, g2, &o2, out);
+    if (c1 == 1 && c2 == 2) {
+        n = collide_capsule_box(g2, &o2, g1, &o1, out);
+        flip(out, n);
+        return n;
+    }
+    if (c1 == 0 && c2 == 3) return collide_sphere_cylinder(o1.p, g1->dims[0], g2, &o2, out);
+    if (c1 == 3 && c2 == 0) {
+        n = collide_sphere_cylinder(o2.p, g2->dims[0], g1, &o1, out);
+        flip(out, n);
+        return n;
+    }
+    if (c1 == 2 && c2 == 3) return collide_capsule_cylinder(g1, &o1, g2, &o2, out);
+    if (c1 == 3 && c2 == 2) {
+        n = collide_capsule_cylinder(g2, &o2, g1, &o1, out);
+        flip(out, n);
+        return n;
+    }
+    if (c1 == 3 && c2 == 1) return collide_cylinder_box(g1, &o1, g2, &o2, out);
+    if (c1 == 1 && c2 == 3) {
+        n = collide_cylinder_box(g2, &o2, g1, &o1, out);
+        flip(out, n);
+        return n;
+    }
+    if (c1 == 3 && c2 == 3) return collide_cylinder_cylinder(g1, &o1, g2, &o2, out);
+    return 0; /* planes / heightfields against each other */
 }
 
 /* ------------------------------------------------------------------ */

@@ -97,7 +97,16 @@ def test_primitive_vs_plane(cuda_lib, cls, dims):
     (capi.GEOM_BOX, (0.3, 0.2, 0.25), capi.GEOM_SPHERE, (0.1,)),
     (capi.GEOM_CAPSULE, (0.05, 0.3), capi.GEOM_SPHERE, (0.1,)),
     (capi.GEOM_SPHERE, (0.1,), capi.GEOM_CAPSULE, (0.05, 0.3)),
-    (capi.GEOM_CAPSULE, (0.05, 0.3), capi.GEOM_CAPSULE, (0.07, 0.2))])
+    (capi.GEOM_CAPSULE, (0.05, 0.3), capi.GEOM_CAPSULE, (0.07, 0.2)),
+    (capi.GEOM_CAPSULE, (0.05, 0.3), capi.GEOM_BOX, (0.3, 0.2, 0.25)),
+    (capi.GEOM_BOX, (0.3, 0.2, 0.25), capi.GEOM_CAPSULE, (0.05, 0.3)),
+    (capi.GEOM_SPHERE, (0.1,), capi.GEOM_CYLINDER, (0.1, 0.25)),
+    (capi.GEOM_CYLINDER, (0.1, 0.25), capi.GEOM_SPHERE, (0.1,)),
+    (capi.GEOM_CAPSULE, (0.05, 0.3), capi.GEOM_CYLINDER, (0.1, 0.25)),
+    (capi.GEOM_CYLINDER, (0.1, 0.25), capi.GEOM_CAPSULE, (0.05, 0.3)),
+    (capi.GEOM_CYLINDER, (0.1, 0.25), capi.GEOM_BOX, (0.3, 0.2, 0.25)),
+    (capi.GEOM_BOX, (0.3, 0.2, 0.25), capi.GEOM_CYLINDER, (0.1, 0.25)),
+    (capi.GEOM_CYLINDER, (0.1, 0.25), capi.GEOM_CYLINDER, (0.12, 0.2))])
 def test_primitive_pairs(cuda_lib, ca, da, cb, db):
     W = 128
     rng = np.random.default_rng(77 + 10 * ca + cb)
@@ -183,16 +192,18 @@ def test_rover_on_heightfield_trajectory(cuda_lib):
     assert sum(oc.contact_count(w) for w in range(W)) >= W  # wheels are on the ground
 
 
-def test_box_on_heightfield(cuda_lib):
+@pytest.mark.parametrize("cls,dims", [(capi.GEOM_BOX, (0.4, 0.3, 0.2)), (capi.GEOM_CAPSULE, (0.08, 0.4)),
+                                      (capi.GEOM_CYLINDER, (0.15, 0.2)), (capi.GEOM_SPHERE, (0.12,))])
+def test_primitive_on_heightfield(cuda_lib, cls, dims):
     W = 64
-    rng = np.random.default_rng(5)
+    rng = np.random.default_rng(5 + cls)
     ar, oc = Arena(W), orc.OracleBatch(W)
     heights, x0, y0 = scenes.terrain_heights()
     for be in (ar, oc):
         scenes.setup_world(be)
         be.set_max_contacts(8)
         a = scenes.add_body(be, 1.0, np.eye(3) * 0.01, (0, 0, 0))
-        be.geom_create(capi.GEOM_BOX, a, (0.4, 0.3, 0.2), surface=SURF)
+        be.geom_create(cls, a, dims, surface=SURF)
         be.geom_create_heightfield(heights, 0.1, x0, y0, surface=SURF)
     for w in range(W):
         p = np.array([rng.uniform(-5, 5), rng.uniform(-5, 5), rng.uniform(-0.05, 0.2)])
