@@ -40,6 +40,8 @@ enum {
     B2P_JOINT_HINGE = 1,  /* dJointCreateHinge   -- src/joints/HingeJoint.cpp:33 */
     B2P_JOINT_HINGE2 = 2, /* dJointCreateHinge2  -- src/joints/Hinge2Joint.cpp:37 */
     B2P_JOINT_SLIDER = 3, /* dJointCreateSlider  -- src/joints/SliderJoint.cpp:34 */
+    B2P_JOINT_BALL = 4,      /* dJointCreateBall      -- JOINT_TYPE_BALL arms of src/joints/Joint.cpp:299-301,447-449 */
+    B2P_JOINT_UNIVERSAL = 5, /* dJointCreateUniversal -- what src/joints/UniversalJoint.cpp:50-75 configures */
     B2P_JOINT_FIXED = 6   /* dJointCreateFixed   -- src/joints/FixedJoint.cpp:35 */
 };
 
@@ -186,6 +188,9 @@ int b2p_state_download(b2p_arena *a, float *host_state);
 /* one body of every world: float[13][num_worlds] (asynchronous on the arena stream; call
  * b2p_sync before reading the host buffer) */
 int b2p_body_get_state_batch(b2p_arena *a, int body, float *host_out);
+/* joint observations of the last step for all worlds: float[num_joints][4][num_worlds] = angle1 rate1 angle2 rate2
+ * (dJointGet*Angle / dJointGet*AngleRate / dJointGetSliderPosition(Rate), src/joints/Joint.cpp:395-415,1072-1102) */
+int b2p_joint_obs_download(b2p_arena *a, float *host_obs);
 /* pipelined form for control loops: snapshot on the step's stream, D2H on a separate copy stream so that it
  * overlaps the next step; returns a ticket (0 or 1, two transfers may be in flight), b2p_io_wait(ticket)
  * blocks until host_out is complete */

@@ -12,6 +12,7 @@ ALL_WORLDS = -1
 STATIC_BODY = -1
 
 JOINT_HINGE, JOINT_HINGE2, JOINT_SLIDER, JOINT_FIXED = 1, 2, 3, 6
+JOINT_BALL, JOINT_UNIVERSAL = 4, 5
 (PARAM_LO_STOP, PARAM_HI_STOP, PARAM_VEL, PARAM_LO_VEL, PARAM_HI_VEL, PARAM_FMAX, PARAM_FUDGE_FACTOR,
  PARAM_BOUNCE, PARAM_CFM, PARAM_STOP_ERP, PARAM_STOP_CFM, PARAM_SUSPENSION_ERP, PARAM_SUSPENSION_CFM,
  PARAM_ERP) = range(14)
@@ -100,6 +101,7 @@ SIGNATURES = {
     "b2p_state_upload": (_I, [_P, _P]),
     "b2p_state_download": (_I, [_P, _P]),
     "b2p_body_get_state_batch": (_I, [_P, _I, _P]),
+    "b2p_joint_obs_download": (_I, [_P, _P]),
     "b2p_body_get_state_batch_begin": (_I, [_P, _I, _P]),
     "b2p_io_wait": (_I, [_P, _I]),
     "b2p_padded_worlds": (_I, [_P]),

@@ -18,6 +18,7 @@
 
 #include "../../include/mars_ode_b200.h"
 #include "b2p_dev.h"
+#include "b2p_universal.h"
 
 extern "C" size_t b2p_assemble_smem_bytes(int nb);
 extern "C" size_t b2p_integrate_smem_bytes(int nb);
@@ -173,6 +174,7 @@ struct HJoint {
     int type = 0, b[2] = {-1, -1}, reverse = 0;
     double anchor1[3] = {0, 0, 0}, anchor2[3] = {0, 0, 0}, axis1[3] = {1, 0, 0}, axis2[3] = {1, 0, 0};
     double qrel[4] = {1, 0, 0, 0}, offset[3] = {0, 0, 0};
+    double qrel2[4] = {1, 0, 0, 0}; // universal: body 2 against the cross
     HLimot limot1, limot2;
     double c0 = 0, s0 = 0, v1[3] = {1, 0, 0}, v2[3] = {0, 1, 0}, w1[3] = {1, 0, 0}, w2[3] = {0, 1, 0};
     double susp_erp = 0, susp_cfm = 0, erp = 0, cfm = 0;
@@ -498,7 +500,7 @@ int finalize(b2p_arena *a)
                 d.w1[i] = (float)h.w1[i];
                 d.w2[i] = (float)h.w2[i];
             }
-            for (int i = 0; i < 4; i++) d.qrel[i] = (float)h.qrel[i];
+            for (int i = 0; i < 4; i++) d.qrel[i] = (float)h.qrel[i], d.qrel2[i] = (float)h.qrel2[i];
             fill_limot(d.limot1, h.limot1);
             fill_limot(d.limot2, h.limot2);
             d.c0 = (float)h.c0;
@@ -658,6 +660,28 @@ void initial_relative_rotation(b2p_arena *a, HJoint &j)
         j.qrel[0] = b0.q[0];
         for (int i = 1; i < 4; i++) j.qrel[i] = -b0.q[i];
     }
+}
+// universal joint: world axes at creation poses, and dxJointUniversal::computeInitialRelativeRotations
+void universal_axes_world(const HJoint &j, const double *q0, const double *q1, double *ax1, double *ax2)
+{
+    double R[9];
+    q_to_R(q0, R);
+    Rv(ax1, R, j.axis1);
+    if (j.b[1] >= 0) {
+        q_to_R(q1, R);
+        Rv(ax2, R, j.axis2);
+    } else {
+        ax2[0] = j.axis2[0], ax2[1] = j.axis2[1], ax2[2] = j.axis2[2];
+    }
+}
+void universal_initial_rotations(b2p_arena *a, HJoint &j)
+{
+    if (j.b[0] < 0) return;
+    const double ident[4] = {1, 0, 0, 0};
+    const double *q0 = a->bodies[j.b[0]].q, *q1 = j.b[1] >= 0 ? a->bodies[j.b[1]].q : ident;
+    double ax1[3], ax2[3];
+    universal_axes_world(j, q0, q1, ax1, ax2);
+    b2p_uni::initial_rotations<double>(ax1, ax2, q0, q1, j.b[1] >= 0, j.qrel, j.qrel2);
 }
 void hinge2_axes_world(b2p_arena *a, const HJoint &j, double *ax1, double *ax2)
 {
@@ -1096,6 +1120,19 @@ int b2p_state_download(b2p_arena *a, float *host_state)
     return 0;
 }
 
+// The joint observations the integrate kernel wrote after the last step: float[nj][4][num_worlds] =
+// angle1, rate1, angle2, rate2 per joint (dJointGet*Angle / *Rate for every world at once).
+int b2p_joint_obs_download(b2p_arena *a, float *host_obs)
+{
+    if (!a || !host_obs) return fail(B2P_EINVAL, "null argument");
+    if (!a->stepped || !a->jobs.dev) return fail(B2P_EINVAL, "no step has run yet");
+    CUDA_TRY(cudaSetDevice(a->device));
+    CUDA_TRY(cudaMemcpy2DAsync(host_obs, sizeof(float) * a->W, a->jobs.dev, sizeof(float) * a->Wp, sizeof(float) * a->W,
+                               a->joints.size() * 4, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    return 0;
+}
+
 int b2p_body_get_state_batch(b2p_arena *a, int body, float *host_out)
 {
     int rc = check_body(a, body);
@@ -1163,7 +1200,8 @@ void *b2p_device_joint_obs(b2p_arena *a) { return a ? a->jobs.dev : nullptr; }
 int b2p_joint_create(b2p_arena *a, int type, int body1, int body2)
 {
     if (!a) return fail(B2P_EINVAL, "null arena");
-    if (type != B2P_JOINT_HINGE && type != B2P_JOINT_HINGE2 && type != B2P_JOINT_SLIDER && type != B2P_JOINT_FIXED)
+    if (type != B2P_JOINT_HINGE && type != B2P_JOINT_HINGE2 && type != B2P_JOINT_SLIDER && type != B2P_JOINT_FIXED &&
+        type != B2P_JOINT_BALL && type != B2P_JOINT_UNIVERSAL)
         return fail(B2P_EUNSUPPORTED, "joint type %d is not supported", type);
     if (body1 >= (int)a->bodies.size() || body2 >= (int)a->bodies.size() || body1 < -1 || body2 < -1)
         return fail(B2P_EINVAL, "joint body id out of range");
@@ -1189,7 +1227,7 @@ int b2p_joint_create(b2p_arena *a, int type, int body1, int body2)
     j.cfm = a->cfm;
     j.susp_erp = a->erp;
     j.susp_cfm = a->cfm;
-    if (type == B2P_JOINT_HINGE2) {
+    if (type == B2P_JOINT_HINGE2 || type == B2P_JOINT_UNIVERSAL) {
         j.axis2[0] = 0;
         j.axis2[1] = 1;
     }
@@ -1213,6 +1251,11 @@ int b2p_joint_set_anchor(b2p_arena *a, int ji, double x, double y, double z)
         set_anchors(a, j, x, y, z);
         hinge2_make_v(a, j);
         hinge2_make_w(a, j);
+    } else if (j.type == B2P_JOINT_BALL) {
+        set_anchors(a, j, x, y, z);
+    } else if (j.type == B2P_JOINT_UNIVERSAL) {
+        set_anchors(a, j, x, y, z);
+        universal_initial_rotations(a, j);
     }
     a->tmpl_dirty = true;
     return 0;
@@ -1243,6 +1286,10 @@ int b2p_joint_set_axis1(b2p_arena *a, int ji, double x, double y, double z)
         hinge2_axis_info(a, j);
         hinge2_make_v(a, j);
         hinge2_make_w(a, j);
+    } else if (j.type == B2P_JOINT_UNIVERSAL) { // dJointSetUniversalAxis1
+        if (j.reverse) set_axes(a, j, x, y, z, nullptr, j.axis2);
+        else set_axes(a, j, x, y, z, j.axis1, nullptr);
+        universal_initial_rotations(a, j);
     }
     a->tmpl_dirty = true;
     return 0;
@@ -1253,6 +1300,13 @@ int b2p_joint_set_axis2(b2p_arena *a, int ji, double x, double y, double z)
     int rc = check_joint(a, ji);
     if (rc) return rc;
     HJoint &j = a->joints[ji];
+    if (j.type == B2P_JOINT_UNIVERSAL) { // dJointSetUniversalAxis2
+        if (j.reverse) set_axes(a, j, x, y, z, j.axis1, nullptr);
+        else set_axes(a, j, x, y, z, nullptr, j.axis2);
+        universal_initial_rotations(a, j);
+        a->tmpl_dirty = true;
+        return 0;
+    }
     if (j.type == B2P_JOINT_HINGE2) {
         set_axes(a, j, x, y, z, nullptr, j.axis2);
         hinge2_axis_info(a, j);
@@ -1289,7 +1343,7 @@ int b2p_joint_set_param(b2p_arena *a, int ji, int world, int param, double value
     if (rc) return rc;
     if ((rc = check_world(a, world, true))) return rc;
     HJoint &j = a->joints[ji];
-    if (j.type == B2P_JOINT_FIXED) {
+    if (j.type == B2P_JOINT_FIXED || j.type == B2P_JOINT_BALL) { // dJointSetFixedParam / dJointSetBallParam
         if (param == B2P_PARAM_CFM) j.cfm = value;
         else if (param == B2P_PARAM_ERP) j.erp = value;
         a->tmpl_dirty = true;
@@ -1338,7 +1392,7 @@ int b2p_joint_get_param(b2p_arena *a, int ji, int world, int param, double *valu
     if ((rc = check_world(a, world, false))) return rc;
     HJoint &j = a->joints[ji];
     *value = 0;
-    if (j.type == B2P_JOINT_FIXED) {
+    if (j.type == B2P_JOINT_FIXED || j.type == B2P_JOINT_BALL) {
         if (param == B2P_PARAM_CFM) *value = j.cfm;
         if (param == B2P_PARAM_ERP) *value = j.erp;
         return 0;
@@ -1486,6 +1540,11 @@ int b2p_joint_get_angle1(b2p_arena *a, int ji, int world, double *out)
         Rv(p, R1, j.axis2);
         Rtv(q, R0, p);
         *out = -std::atan2(dot(j.v2, q), dot(j.v1, q));
+    } else if (j.type == B2P_JOINT_UNIVERSAL) { // dJointGetUniversalAngle1
+        double ax1[3], ax2[3], a1, a2;
+        universal_axes_world(j, q0, q1, ax1, ax2);
+        b2p_uni::angles<double>(ax1, ax2, q0, q1, j.b[1] >= 0, j.axis1, j.axis2, j.qrel, j.qrel2, &a1, &a2);
+        *out = j.reverse ? -a2 : a1;
     }
     return 0;
 }
@@ -1497,8 +1556,8 @@ int b2p_joint_get_angle1_rate(b2p_arena *a, int ji, int world, double *out)
     if ((rc = check_world(a, world, false))) return rc;
     const HJoint &j = a->joints[ji];
     *out = 0;
-    if (j.b[0] < 0 || j.type == B2P_JOINT_FIXED) return 0;
-    double p0[3], q0[4], p1[3], q1[4], R0[9], axis[3], lv0[3], av0[3], lv1[3] = {0, 0, 0}, av1[3] = {0, 0, 0};
+    if (j.b[0] < 0 || j.type == B2P_JOINT_FIXED || j.type == B2P_JOINT_BALL) return 0;
+    double p0[3], q0[4], p1[3], q1[4] = {1, 0, 0, 0}, R0[9], axis[3], lv0[3], av0[3], lv1[3] = {0, 0, 0}, av1[3] = {0, 0, 0};
     if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
     q_to_R(q0, R0);
     Rv(axis, R0, j.axis1);
@@ -1508,7 +1567,12 @@ int b2p_joint_get_angle1_rate(b2p_arena *a, int ji, int world, double *out)
         b2p_body_get_linear_vel(a, j.b[1], world, lv1);
         b2p_body_get_angular_vel(a, j.b[1], world, av1);
     }
-    if (j.type == B2P_JOINT_HINGE || j.type == B2P_JOINT_HINGE2) {
+    if (j.type == B2P_JOINT_UNIVERSAL) { // dJointGetUniversalAngle1Rate
+        double ax1[3], ax2[3];
+        universal_axes_world(j, q0, q1, ax1, ax2);
+        const double *ax = j.reverse ? ax2 : ax1;
+        *out = dot(ax, av0) - dot(ax, av1);
+    } else if (j.type == B2P_JOINT_HINGE || j.type == B2P_JOINT_HINGE2) {
         double rate = dot(axis, av0);
         if (j.b[1] >= 0) rate -= dot(axis, av1);
         if (j.type == B2P_JOINT_HINGE && j.reverse) rate = -rate;
@@ -1531,6 +1595,14 @@ int b2p_joint_get_angle2(b2p_arena *a, int ji, int world, double *out)
     if ((rc = check_world(a, world, false))) return rc;
     const HJoint &j = a->joints[ji];
     *out = 0;
+    if (j.type == B2P_JOINT_UNIVERSAL && j.b[0] >= 0) { // dJointGetUniversalAngle2
+        double p0[3], q0[4], p1[3], q1[4] = {1, 0, 0, 0}, ax1[3], ax2[3], a1, a2;
+        if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
+        universal_axes_world(j, q0, q1, ax1, ax2);
+        b2p_uni::angles<double>(ax1, ax2, q0, q1, j.b[1] >= 0, j.axis1, j.axis2, j.qrel, j.qrel2, &a1, &a2);
+        *out = j.reverse ? -a1 : a2;
+        return 0;
+    }
     if (j.type != B2P_JOINT_HINGE2) return 0;
     double p0[3], q0[4], p1[3], q1[4], R0[9], R1[9], p[3], q[3];
     if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
@@ -1549,6 +1621,16 @@ int b2p_joint_get_angle2_rate(b2p_arena *a, int ji, int world, double *out)
     if ((rc = check_world(a, world, false))) return rc;
     const HJoint &j = a->joints[ji];
     *out = 0;
+    if (j.type == B2P_JOINT_UNIVERSAL && j.b[0] >= 0) { // dJointGetUniversalAngle2Rate
+        double p0[3], q0[4], p1[3], q1[4] = {1, 0, 0, 0}, ax1[3], ax2[3], av0[3], av1[3] = {0, 0, 0};
+        if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
+        universal_axes_world(j, q0, q1, ax1, ax2);
+        b2p_body_get_angular_vel(a, j.b[0], world, av0);
+        if (j.b[1] >= 0) b2p_body_get_angular_vel(a, j.b[1], world, av1);
+        const double *ax = j.reverse ? ax1 : ax2;
+        *out = dot(ax, av0) - dot(ax, av1);
+        return 0;
+    }
     if (j.type != B2P_JOINT_HINGE2) return 0;
     double p0[3], q0[4], p1[3], q1[4], R1[9], axis[3], av0[3], av1[3];
     if ((rc = joint_poses(a, j, world, p0, q0, p1, q1))) return rc;
@@ -2062,6 +2144,8 @@ double b2p_algorithmic_bytes_per_world_step(const b2p_arena *ca)
         case B2P_JOINT_FIXED: bytes += 88; break;
         case B2P_JOINT_SLIDER: bytes += 132; break;
         case B2P_JOINT_HINGE2: bytes += 212; break;
+        case B2P_JOINT_BALL: bytes += 88; break;       // ids, anchors 6, erp, cfm in; feedback 12 out (as fixed)
+        case B2P_JOINT_UNIVERSAL: bytes += 228; break; // hinge2's 212 + qrel2
         default: break;
         }
     }

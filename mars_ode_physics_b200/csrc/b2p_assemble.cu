@@ -418,6 +418,70 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
                     limot_row = 5;
                     mrows = 6;
                 }
+            } else if (jc.type == 4 || jc.type == 5) {
+                // ---- ball (ODE ball.cpp getInfo2: setBall with the joint's own erp / cfm) and universal
+                // (universal.cpp getInfo2: setBall + one angular row along ax1 x ax2 + two limot rows)
+                float a1[3], a2[3], cb[3];
+                const float kb = hinv * (jc.type == 4 ? jc.erp : P.erp);
+                mul_R_v(a1, p0.R, jc.anchor1);
+                if (has_b1) {
+                    mul_R_v(a2, p1.R, jc.anchor2);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) cb[i] = kb * (a2[i] + p1.pos[i] - a1[i] - p0.pos[i]);
+                } else {
+                    a2[0] = a2[1] = a2[2] = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 3; i++) cb[i] = kb * (jc.anchor2[i] - a1[i] - p0.pos[i]);
+                }
+                const float bcfm = jc.type == 4 ? jc.cfm : P.cfm;
+                row_init(r, bcfm);
+                r.J[0] = 1.f; r.J[4] = a1[2]; r.J[5] = -a1[1];
+                if (has_b1) { r.J[6] = -1.f; r.J[10] = -a2[2]; r.J[11] = a2[1]; }
+                r.c = cb[0];
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                row_init(r, bcfm);
+                r.J[1] = 1.f; r.J[3] = -a1[2]; r.J[5] = a1[0];
+                if (has_b1) { r.J[7] = -1.f; r.J[9] = a2[2]; r.J[11] = -a2[0]; }
+                r.c = cb[1];
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                row_init(r, bcfm);
+                r.J[2] = 1.f; r.J[3] = a1[1]; r.J[4] = -a1[0];
+                if (has_b1) { r.J[8] = -1.f; r.J[9] = -a2[1]; r.J[10] = a2[0]; }
+                r.c = cb[2];
+                emit_row(P, S, w, tid, nhead++, r, pc);
+                mrows = 3;
+                if (jc.type == 5) {
+                    float ax1[3], ax2[3], ax2t[3], pv[3];
+                    universal_axes(jc, p0, p1, has_b1, ax1, ax2);
+                    const float k = dot3(ax1, ax2);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) ax2t[i] = ax2[i] - k * ax1[i];
+                    cross3(pv, ax1, ax2t);
+                    normalize3(pv);
+                    row_init(r, P.cfm);
+                    r.J[3] = pv[0]; r.J[4] = pv[1]; r.J[5] = pv[2];
+                    if (has_b1) { r.J[9] = -pv[0]; r.J[10] = -pv[1]; r.J[11] = -pv[2]; }
+                    r.c = kerp * -k;
+                    emit_row(P, S, w, tid, nhead++, r, pc);
+                    mrows = 4;
+                    LimotState st, st2;
+                    joint_limit_state(jc, p0, p1, st);
+                    joint_limit_state2(jc, p0, p1, st2);
+                    row_init(r, P.cfm);
+                    if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 1, p0, p1,
+                                      has_b1)) {
+                        emit_row(P, S, w, tid, nhead++, r, pc);
+                        limot_row = mrows;
+                        mrows++;
+                    }
+                    row_init(r, P.cfm);
+                    if (add_limot_row(P, jc.limot2, G(P.jcmd, j * 4 + 2), G(P.jcmd, j * 4 + 3), st2, r, ax2, 1, p0, p1,
+                                      has_b1)) {
+                        emit_row(P, S, w, tid, nhead++, r, pc);
+                        if (limot_row < 0) limot_row = mrows;
+                        mrows++;
+                    }
+                }
             } else if (jc.type == 6) {
                 // ---- fixed (ODE fixed.cpp getInfo2): rows 0-2 position, rows 3-5 orientation
                 float ofs[3], cl[3], ca[3];

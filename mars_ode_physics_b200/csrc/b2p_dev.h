@@ -66,7 +66,8 @@ struct DevJoint {
     float anchor1[3], anchor2[3], axis1[3], axis2[3], qrel[4], offset[3];
     DevLimot limot1, limot2;
     float c0, s0, v1[3], v2[3], w1[3], w2[3], susp_erp, susp_cfm;
-    float erp, cfm; // fixed joint
+    float erp, cfm; // fixed / ball joint
+    float qrel2[4]; // universal: body 2 against the cross (qrel = body 1 against the cross)
 };
 
 struct DevGeom {

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
     for (int j = 0; j < nj; j++) {
         const DevJoint &jc = T->joints[j];
         float a1 = 0.f, r1 = 0.f, a2 = 0.f, r2 = 0.f;
-        if (jc.b0 >= 0 && jc.type != 6) {
+        if (jc.b0 >= 0 && jc.type != 6 && jc.type != 4) {
             const bool has_b1 = jc.b1 >= 0;
             BodyPose p0, p1;
             load_pose(P, jc.b0, w, p0);
@@ -225,6 +225,15 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
                 float axis2[3];
                 mul_R_v(axis2, p1.R, jc.axis2);
                 r2 = dot3(axis2, av0) - dot3(axis2, av1);
+            } else if (jc.type == 5) { // universal: dJointGetUniversalAngle1/2 and their rates
+                float ax1[3], ax2[3], ang1, ang2;
+                universal_axes(jc, p0, p1, has_b1, ax1, ax2);
+                universal_angles(jc, p0, p1, has_b1, ang1, ang2);
+                const float ra = dot3(ax1, av0) - dot3(ax1, av1), rb = dot3(ax2, av0) - dot3(ax2, av1);
+                a1 = jc.reverse ? -ang2 : ang1;
+                a2 = jc.reverse ? -ang1 : ang2;
+                r1 = jc.reverse ? rb : ra;
+                r2 = jc.reverse ? ra : rb;
             }
         }
         G(P.jobs, j * 4 + 0) = a1;

@@ -8,6 +8,7 @@
 
 #include "b2p_dev.h"
 #include "b2p_math.cuh"
+#include "b2p_universal.h"
 
 #define G(arr, field) (arr)[(size_t)(field) * Wp + w]
 
@@ -116,6 +117,25 @@ __device__ __forceinline__ float hinge2_angle2(const DevJoint &jc, const BodyPos
     return -atan2f(y, x);
 }
 
+// universal joint: world axes and the two angles (ODE universal.cpp getAxes / getAngles)
+__device__ __forceinline__ void universal_axes(const DevJoint &jc, const BodyPose &p0, const BodyPose &p1, bool has_b1,
+                                               float *ax1, float *ax2)
+{
+    mul_R_v(ax1, p0.R, jc.axis1);
+    if (has_b1) {
+        mul_R_v(ax2, p1.R, jc.axis2);
+    } else {
+        ax2[0] = jc.axis2[0], ax2[1] = jc.axis2[1], ax2[2] = jc.axis2[2];
+    }
+}
+__device__ __forceinline__ void universal_angles(const DevJoint &jc, const BodyPose &p0, const BodyPose &p1, bool has_b1,
+                                                 float &a1, float &a2)
+{
+    float ax1[3], ax2[3];
+    universal_axes(jc, p0, p1, has_b1, ax1, ax2);
+    b2p_uni::angles<float>(ax1, ax2, p0.q, p1.q, has_b1 ? 1 : 0, jc.axis1, jc.axis2, jc.qrel, jc.qrel2, &a1, &a2);
+}
+
 // Limit state of limot 1 of joint jc in this world (getInfo1 part that looks at the pose).
 __device__ __forceinline__ void joint_limit_state(const DevJoint &jc, const BodyPose &p0, const BodyPose &p1,
                                                   LimotState &st)
@@ -133,6 +153,27 @@ __device__ __forceinline__ void joint_limit_state(const DevJoint &jc, const Body
     } else if (jc.type == 2) { // hinge2
         if ((l.lostop >= -PI || l.histop <= PI) && l.lostop <= l.histop)
             limot_test(l, hinge2_angle1(jc, p0, p1), st);
+    } else if (jc.type == 5) { // universal, first angle
+        if ((l.lostop >= -PI || l.histop <= PI) && l.lostop <= l.histop) {
+            float a1, a2;
+            universal_angles(jc, p0, p1, jc.b1 >= 0, a1, a2);
+            limot_test(l, a1, st);
+        }
+    }
+}
+
+// Limit state of limot 2 (universal joints only: ODE's hinge2 has no stop on its second axis)
+__device__ __forceinline__ void joint_limit_state2(const DevJoint &jc, const BodyPose &p0, const BodyPose &p1,
+                                                   LimotState &st)
+{
+    st.limit = 0;
+    st.limit_err = 0.f;
+    const DevLimot &l = jc.limot2;
+    const float PI = 3.14159265358979323846f;
+    if (jc.type == 5 && (l.lostop >= -PI || l.histop <= PI) && l.lostop <= l.histop) {
+        float a1, a2;
+        universal_angles(jc, p0, p1, jc.b1 >= 0, a1, a2);
+        limot_test(l, a2, st);
     }
 }
 

@@ -250,3 +250,23 @@ def pendulum_chain(be, n=3, joint_type=capi.JOINT_HINGE):
         sc["joints"].append(j)
         prev = b
     return sc
+
+
+def ball_universal_arm(be):
+    """A two-link arm hanging from the world: link 0 on a ball joint (dJointCreateBall), link 1 on a universal
+    joint (dJointCreateUniversal) whose first axis is motor-driven and whose second axis has stops."""
+    setup_world(be)
+    be.set_max_contacts(0)
+    a = add_body(be, 0.8, inertia_box(0.8, 0.3, 0.06, 0.06), (0.15, 0.0, 1.0))
+    b = add_body(be, 0.5, inertia_box(0.5, 0.3, 0.05, 0.05), (0.45, 0.0, 1.0))
+    jb = be.joint_create(capi.JOINT_BALL, a, -1)
+    be.joint_set_anchor(jb, (0.0, 0.0, 1.0))
+    ju = be.joint_create(capi.JOINT_UNIVERSAL, a, b)
+    be.joint_set_anchor(ju, (0.3, 0.0, 1.0))
+    be.joint_set_axis1(ju, (0, 1, 0))
+    be.joint_set_axis2(ju, (0, 0, 1))
+    be.joint_set_param(ju, capi.PARAM_FMAX, 0.4)
+    be.joint_set_param(ju, capi.PARAM_VEL, 0.8)
+    be.joint_set_param(ju, capi.PARAM_LO_STOP | capi.PARAM_GROUP2, -0.2)
+    be.joint_set_param(ju, capi.PARAM_HI_STOP | capi.PARAM_GROUP2, 0.25)
+    return {"bodies": [a, b], "joints": [jb, ju], "ball": jb, "universal": ju, "name": "ball_universal_arm"}

@@ -55,6 +55,7 @@ typedef struct {
     int reverse;
     unsigned creation_serial; /* attach order, for the island DFS */
     real anchor1[3], anchor2[3], axis1[3], axis2[3], qrel[4], offset[3];
+    real qrel2[4]; /* universal: qrel = qrel1 (body 1 vs the cross), qrel2 (body 2 vs the cross) */
     limot_t limot1, limot2;
     /* hinge2 */
     real c0, s0, v1[3], v2[3], w1[3], w2[3], susp_erp, susp_cfm;

@@ -541,6 +541,11 @@ int orc_joint_create(orc_world *w, int type, int b1, int b2)
     limot_init(&j->limot2, w);
     j->erp = w->erp;
     j->cfm = w->cfm;
+    j->qrel2[0] = 1;
+    if (type == ORC_JOINT_UNIVERSAL) {
+        j->axis2[0] = 0;
+        j->axis2[1] = 1;
+    }
     if (type == ORC_JOINT_HINGE2) {
         j->axis2[0] = 0;
         j->axis2[1] = 1;
@@ -650,6 +655,8 @@ static void hinge2_make_w1_w2(orc_world *w, joint_t *j)
     mul_Rt_v(j->w2, w->bodies[j->b[1]].R, v);
 }
 
+static void universal_initial_rotations(orc_world *w, joint_t *j);
+
 void orc_joint_set_anchor(orc_world *w, int ji, double x, double y, double z)
 {
     joint_t *j = &w->joints[ji];
@@ -662,6 +669,11 @@ void orc_joint_set_anchor(orc_world *w, int ji, double x, double y, double z)
         set_anchors(w, j, (real)x, (real)y, (real)z);
         hinge2_make_v1_v2(w, j);
         hinge2_make_w1_w2(w, j);
+        break;
+    case ORC_JOINT_BALL: set_anchors(w, j, (real)x, (real)y, (real)z); break;
+    case ORC_JOINT_UNIVERSAL:
+        set_anchors(w, j, (real)x, (real)y, (real)z);
+        universal_initial_rotations(w, j);
         break;
     default: break; /* slider/fixed have no anchor (Joint.cpp:436-438) */
     }
@@ -703,6 +715,13 @@ void orc_joint_set_axis1(orc_world *w, int ji, double x, double y, double z)
         hinge2_make_v1_v2(w, j);
         hinge2_make_w1_w2(w, j);
         break;
+    case ORC_JOINT_UNIVERSAL: /* dJointSetUniversalAxis1 */
+        if (j->reverse)
+            set_axes(w, j, (real)x, (real)y, (real)z, 0, j->axis2);
+        else
+            set_axes(w, j, (real)x, (real)y, (real)z, j->axis1, 0);
+        universal_initial_rotations(w, j);
+        break;
     default: break;
     }
 }
@@ -710,6 +729,14 @@ void orc_joint_set_axis1(orc_world *w, int ji, double x, double y, double z)
 void orc_joint_set_axis2(orc_world *w, int ji, double x, double y, double z)
 {
     joint_t *j = &w->joints[ji];
+    if (j->type == ORC_JOINT_UNIVERSAL) { /* dJointSetUniversalAxis2 */
+        if (j->reverse)
+            set_axes(w, j, (real)x, (real)y, (real)z, j->axis1, 0);
+        else
+            set_axes(w, j, (real)x, (real)y, (real)z, 0, j->axis2);
+        universal_initial_rotations(w, j);
+        return;
+    }
     if (j->type != ORC_JOINT_HINGE2) return;
     if (j->b[0] >= 0 && j->b[1] >= 0) {
         real ax1[3], ax2[3], ax[3];
@@ -740,7 +767,7 @@ void orc_joint_set_fixed(orc_world *w, int ji)
 void orc_joint_set_param(orc_world *w, int ji, int param, double value)
 {
     joint_t *j = &w->joints[ji];
-    if (j->type == ORC_JOINT_FIXED) {
+    if (j->type == ORC_JOINT_FIXED || j->type == ORC_JOINT_BALL) { /* dJointSetFixedParam / dJointSetBallParam */
         if (param == ORC_PARAM_CFM) j->cfm = (real)value;
         if (param == ORC_PARAM_ERP) j->erp = (real)value;
         return;
@@ -759,7 +786,7 @@ void orc_joint_set_param(orc_world *w, int ji, int param, double value)
 double orc_joint_get_param(const orc_world *w, int ji, int param)
 {
     const joint_t *j = &w->joints[ji];
-    if (j->type == ORC_JOINT_FIXED) {
+    if (j->type == ORC_JOINT_FIXED || j->type == ORC_JOINT_BALL) {
         if (param == ORC_PARAM_CFM) return j->cfm;
         if (param == ORC_PARAM_ERP) return j->erp;
         return 0;
@@ -839,6 +866,130 @@ static real hinge_angle(const orc_world *w, const joint_t *j)
     return hinge_angle_from_qrel(qrel, j->axis1);
 }
 
+/* ---- universal joint (ODE 0.16 universal.cpp) ---- */
+static void qmul0(real *r, const real *b, const real *c) /* b * c */
+{
+    r[0] = b[0] * c[0] - b[1] * c[1] - b[2] * c[2] - b[3] * c[3];
+    r[1] = b[0] * c[1] + b[1] * c[0] + b[2] * c[3] - b[3] * c[2];
+    r[2] = b[0] * c[2] + b[2] * c[0] + b[3] * c[1] - b[1] * c[3];
+    r[3] = b[0] * c[3] + b[3] * c[0] + b[1] * c[2] - b[2] * c[1];
+}
+
+/* ODE rotation.cpp dRFrom2Axes: columns a^, (b orthogonalised against a)^, a^ x b^ */
+static void r_from_2_axes(real *R, const real *a, const real *b)
+{
+    real ax = a[0], ay = a[1], az = a[2], bx = b[0], by = b[1], bz = b[2];
+    real l = R_SQRT(ax * ax + ay * ay + az * az);
+    if (l <= 0) return;
+    l = 1 / l;
+    ax *= l, ay *= l, az *= l;
+    const real k = ax * bx + ay * by + az * bz;
+    bx -= k * ax, by -= k * ay, bz -= k * az;
+    l = R_SQRT(bx * bx + by * by + bz * bz);
+    if (l <= 0) return;
+    l = 1 / l;
+    bx *= l, by *= l, bz *= l;
+    R[0] = ax, R[3] = ay, R[6] = az;
+    R[1] = bx, R[4] = by, R[7] = bz;
+    R[2] = ay * bz - by * az, R[5] = az * bx - bz * ax, R[8] = ax * by - bx * ay;
+}
+
+/* ODE rotation.cpp dRtoQ */
+static void r_to_q(const real *R, real *q)
+{
+    const real tr = R[0] + R[4] + R[8];
+    real s;
+    if (tr >= 0) {
+        s = R_SQRT(tr + 1);
+        q[0] = (real)0.5 * s;
+        s = (real)0.5 / s;
+        q[1] = (R[7] - R[5]) * s;
+        q[2] = (R[2] - R[6]) * s;
+        q[3] = (R[3] - R[1]) * s;
+        return;
+    }
+    int c = 0;
+    if (R[4] > R[0]) c = R[8] > R[4] ? 2 : 1;
+    else c = R[8] > R[0] ? 2 : 0;
+    if (c == 0) {
+        s = R_SQRT((R[0] - (R[4] + R[8])) + 1);
+        q[1] = (real)0.5 * s;
+        s = (real)0.5 / s;
+        q[2] = (R[1] + R[3]) * s;
+        q[3] = (R[6] + R[2]) * s;
+        q[0] = (R[7] - R[5]) * s;
+    } else if (c == 1) {
+        s = R_SQRT((R[4] - (R[8] + R[0])) + 1);
+        q[2] = (real)0.5 * s;
+        s = (real)0.5 / s;
+        q[3] = (R[5] + R[7]) * s;
+        q[1] = (R[1] + R[3]) * s;
+        q[0] = (R[2] - R[6]) * s;
+    } else {
+        s = R_SQRT((R[8] - (R[0] + R[4])) + 1);
+        q[3] = (real)0.5 * s;
+        s = (real)0.5 / s;
+        q[1] = (R[6] + R[2]) * s;
+        q[2] = (R[5] + R[7]) * s;
+        q[0] = (R[3] - R[1]) * s;
+    }
+}
+
+static void universal_axes(const orc_world *w, const joint_t *j, real *ax1, real *ax2)
+{
+    mul_R_v(ax1, w->bodies[j->b[0]].R, j->axis1);
+    if (j->b[1] >= 0)
+        mul_R_v(ax2, w->bodies[j->b[1]].R, j->axis2);
+    else
+        memcpy(ax2, j->axis2, 3 * sizeof(real));
+}
+
+/* dxJointUniversal::computeInitialRelativeRotations */
+static void universal_initial_rotations(orc_world *w, joint_t *j)
+{
+    if (j->b[0] < 0) return;
+    real ax1[3], ax2[3], R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, qcross[4];
+    universal_axes(w, j, ax1, ax2);
+    r_from_2_axes(R, ax1, ax2);
+    r_to_q(R, qcross);
+    qmul1(j->qrel, w->bodies[j->b[0]].q, qcross);
+    r_from_2_axes(R, ax2, ax1);
+    r_to_q(R, qcross);
+    if (j->b[1] >= 0)
+        qmul1(j->qrel2, w->bodies[j->b[1]].q, qcross);
+    else
+        memcpy(j->qrel2, qcross, sizeof(qcross));
+}
+
+/* dxJointUniversal::getAngles */
+static void universal_angles(const orc_world *w, const joint_t *j, real *angle1, real *angle2)
+{
+    *angle1 = *angle2 = 0;
+    if (j->b[0] < 0) return;
+    real ax1[3], ax2[3], R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, qcross[4], qq[4], qrel[4], qcross2[4];
+    universal_axes(w, j, ax1, ax2);
+    r_from_2_axes(R, ax1, ax2);
+    r_to_q(R, qcross);
+    qmul1(qq, w->bodies[j->b[0]].q, qcross);
+    qmul2(qrel, qq, j->qrel);
+    *angle1 = hinge_angle_from_qrel(qrel, j->axis1);
+    /* the cross seen from body 2: the first frame turned by 180 degrees about the bisector of the two axes */
+    qrel[0] = 0;
+    qrel[1] = ax1[0] + ax2[0];
+    qrel[2] = ax1[1] + ax2[1];
+    qrel[3] = ax1[2] + ax2[2];
+    const real l = 1 / R_SQRT(qrel[1] * qrel[1] + qrel[2] * qrel[2] + qrel[3] * qrel[3]);
+    qrel[1] *= l, qrel[2] *= l, qrel[3] *= l;
+    qmul0(qcross2, qrel, qcross);
+    if (j->b[1] >= 0) {
+        qmul1(qq, w->bodies[j->b[1]].q, qcross2);
+        qmul2(qrel, qq, j->qrel2);
+    } else {
+        qmul2(qrel, qcross2, j->qrel2);
+    }
+    *angle2 = -hinge_angle_from_qrel(qrel, j->axis2);
+}
+
 static real slider_position(const orc_world *w, const joint_t *j)
 {
     const body_t *b0 = &w->bodies[j->b[0]];
@@ -899,6 +1050,11 @@ double orc_joint_get_angle1(const orc_world *w, int ji)
     }
     case ORC_JOINT_SLIDER: return slider_position(w, j);
     case ORC_JOINT_HINGE2: return hinge2_angle1(w, j);
+    case ORC_JOINT_UNIVERSAL: { /* dJointGetUniversalAngle1 */
+        real a1, a2;
+        universal_angles(w, j, &a1, &a2);
+        return j->reverse ? -a2 : a1;
+    }
     default: return 0;
     }
 }
@@ -911,6 +1067,14 @@ double orc_joint_get_angle1_rate(const orc_world *w, int ji)
     real axis[3];
     mul_R_v(axis, b0->R, j->axis1);
     switch (j->type) {
+    case ORC_JOINT_UNIVERSAL: { /* dJointGetUniversalAngle1Rate */
+        real ax1[3], ax2[3];
+        universal_axes(w, j, ax1, ax2);
+        const real *ax = j->reverse ? ax2 : ax1;
+        real rate = dot3(ax, b0->avel);
+        if (j->b[1] >= 0) rate -= dot3(ax, w->bodies[j->b[1]].avel);
+        return rate;
+    }
     case ORC_JOINT_HINGE:
     case ORC_JOINT_HINGE2: {
         real rate = dot3(axis, b0->avel);
@@ -930,6 +1094,11 @@ double orc_joint_get_angle1_rate(const orc_world *w, int ji)
 double orc_joint_get_angle2(const orc_world *w, int ji)
 {
     const joint_t *j = &w->joints[ji];
+    if (j->type == ORC_JOINT_UNIVERSAL && j->b[0] >= 0) { /* dJointGetUniversalAngle2 */
+        real a1, a2;
+        universal_angles(w, j, &a1, &a2);
+        return j->reverse ? -a1 : a2;
+    }
     if (j->type != ORC_JOINT_HINGE2 || j->b[0] < 0) return 0;
     return hinge2_angle2(w, j);
 }
@@ -937,6 +1106,14 @@ double orc_joint_get_angle2(const orc_world *w, int ji)
 double orc_joint_get_angle2_rate(const orc_world *w, int ji)
 {
     const joint_t *j = &w->joints[ji];
+    if (j->type == ORC_JOINT_UNIVERSAL && j->b[0] >= 0) { /* dJointGetUniversalAngle2Rate */
+        real ax1[3], ax2[3];
+        universal_axes(w, j, ax1, ax2);
+        const real *ax = j->reverse ? ax1 : ax2;
+        real rate = dot3(ax, w->bodies[j->b[0]].avel);
+        if (j->b[1] >= 0) rate -= dot3(ax, w->bodies[j->b[1]].avel);
+        return rate;
+    }
     if (j->type != ORC_JOINT_HINGE2 || j->b[0] < 0 || j->b[1] < 0) return 0;
     real axis[3];
     mul_R_v(axis, w->bodies[j->b[1]].R, j->axis2);
@@ -1116,6 +1293,22 @@ static int joint_info1(orc_world *w, joint_t *j)
         if (j->limot1.limit || j->limot1.fmax > 0) m++;
         j->limot2.limit = 0;
         if (j->limot2.fmax > 0) m++;
+        return m;
+    }
+    case ORC_JOINT_BALL: return 3;
+    case ORC_JOINT_UNIVERSAL: { /* dxJointUniversal::getInfo1 */
+        int m = 4;
+        const int lim1 = (j->limot1.lostop >= -R_PI || j->limot1.histop <= R_PI) && j->limot1.lostop <= j->limot1.histop;
+        const int lim2 = (j->limot2.lostop >= -R_PI || j->limot2.histop <= R_PI) && j->limot2.lostop <= j->limot2.histop;
+        j->limot1.limit = j->limot2.limit = 0;
+        if (lim1 || lim2) {
+            real a1, a2;
+            universal_angles(w, j, &a1, &a2);
+            if (lim1) limot_test_rotational_limit(&j->limot1, a1);
+            if (lim2) limot_test_rotational_limit(&j->limot2, a2);
+        }
+        if (j->limot1.limit || j->limot1.fmax > 0) m++;
+        if (j->limot2.limit || j->limot2.fmax > 0) m++;
         return m;
     }
     default: return 0;
@@ -1536,6 +1729,33 @@ static void joint_info2(orc_world *w, joint_t *j, real fps, row_t *r, int m)
         for (int i = 0; i < 3; i++) r[3].J[9 + i] = -q[i];
         real k = fps * world_erp;
         r[3].c = k * (j->c0 * s - j->s0 * c);
+        int row = 4;
+        if (row < m && add_limot(w, j, &j->limot1, fps, &r[row], ax1, 1)) {
+            j->limot_row = row;
+            row++;
+        }
+        if (row < m && add_limot(w, j, &j->limot2, fps, &r[row], ax2, 1)) {
+            if (j->limot_row < 0) j->limot_row = row;
+        }
+        break;
+    }
+    case ORC_JOINT_BALL: { /* dxJointBall::getInfo2: the joint's own erp / cfm */
+        set_ball(w, j, fps, j->erp, r);
+        r[0].cfm = r[1].cfm = r[2].cfm = j->cfm;
+        break;
+    }
+    case ORC_JOINT_UNIVERSAL: { /* dxJointUniversal::getInfo2 */
+        real ax1[3], ax2[3], ax2t[3], p[3];
+        set_ball(w, j, fps, world_erp, r);
+        universal_axes(w, j, ax1, ax2);
+        const real k = dot3(ax1, ax2);
+        for (int i = 0; i < 3; i++) ax2t[i] = ax2[i] - k * ax1[i];
+        cross3(p, ax1, ax2t);
+        normalize3(p);
+        memcpy(r[3].J + 3, p, 3 * sizeof(real));
+        if (j->b[1] >= 0)
+            for (int i = 0; i < 3; i++) r[3].J[9 + i] = -p[i];
+        r[3].c = fps * world_erp * -k;
         int row = 4;
         if (row < m && add_limot(w, j, &j->limot1, fps, &r[row], ax1, 1)) {
             j->limot_row = row;

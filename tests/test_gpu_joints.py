@@ -147,3 +147,43 @@ def test_external_forces_and_add_torque(cuda_lib):
         oc.step(H)
     _compare(ar, oc, 2)
     assert np.allclose(ar.body_get_force(1, 2), 0.0)  # accumulators are zeroed by the step
+
+
+def test_ball_and_universal_parity(cuda_lib):
+    """Ball (3 rows) and universal (4 rows + motor on axis 1 + stops on axis 2) joints: row counts and RNG state
+    exact, poses and the universal's two angles / rates against the fp64 oracle over 300 steps, per-world
+    initial spin so that worlds reach the stops at different times."""
+    W = 40
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    scs = [scenes.ball_universal_arm(be) for be in (ar, oc)]
+    sc = scs[0]
+    for w in range(W):
+        for be in (ar, oc):
+            be.body_set_angular_vel(sc["bodies"][1], (0.0, 0.2 * (w % 5), 3.0 - 0.15 * w), w)
+    ju = sc["universal"]
+    hit_stop = 0
+    for step in range(300):
+        ar.step(H)
+        oc.step(H)
+        if step % 50 == 49:
+            for w in range(0, W, 3):
+                assert ar.last_num_rows(w) == oc.last_num_rows(w), (step, w)
+                assert ar.joint_get_num_rows(ju, w) == oc.joint_get_num_rows(ju, w), (step, w)
+                assert ar.rand_get_seed(w) == oc.rand_get_seed(w)
+                hit_stop += oc.joint_get_num_rows(ju, w) == 6
+                assert abs(ar.joint_get_angle1(ju, w) - oc.joint_get_angle1(ju, w)) < 2e-4
+                assert abs(ar.joint_get_angle2(ju, w) - oc.joint_get_angle2(ju, w)) < 2e-4
+                assert abs(ar.joint_get_angle1_rate(ju, w) - oc.joint_get_angle1_rate(ju, w)) < 5e-3
+                assert abs(ar.joint_get_angle2_rate(ju, w) - oc.joint_get_angle2_rate(ju, w)) < 5e-3
+    assert hit_stop > 0  # some worlds ran into the second axis' stops (motor row + limit row)
+    sa = ar.state_download(2).astype(np.float64)
+    so = oc.state_download(2)
+    d = np.abs(sa - so)
+    assert d[:, 0:3].max() < 2e-4 and d[:, 3:7].max() < 5e-4, (d[:, 0:3].max(), d[:, 3:7].max())
+    assert oc.joint_get_num_rows(sc["ball"], 0) == 3 and ar.joint_get_num_rows(sc["ball"], 0) == 3
+    # the motor drives the first angle at its commanded rate in most worlds
+    rates = [oc.joint_get_angle1_rate(ju, w) for w in range(W)]
+    assert np.median(np.abs(np.array(rates) - 0.8)) < 0.1, rates
+    # device-side observation array agrees with the host-side getter
+    obs = ar.joint_obs_download(2)
+    assert abs(obs[ju, 0, 3] - ar.joint_get_angle1(ju, 3)) < 1e-5 and abs(obs[ju, 2, 3] - ar.joint_get_angle2(ju, 3)) < 1e-5
