@@ -9,6 +9,13 @@
 namespace mars {
 namespace ode_physics {
 
+// hinge2 and universal share every two-axis arm of the reference's Joint.cpp (e.g. :302,330,349,370,389,410)
+static inline bool twoAxes(int t)
+{
+    return t == interfaces::JOINT_TYPE_HINGE2 || t == interfaces::JOINT_TYPE_UNIVERSAL;
+}
+
+
 using namespace utils;
 using namespace interfaces;
 
@@ -138,7 +145,7 @@ void Joint::getAnchor(Vector *anchor) const
 {
     MutexLocker locker(&(theWorld->iMutex));
     double p[3] = {0, 0, 0};
-    if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_HINGE2)
+    if (joint_type == JOINT_TYPE_HINGE || twoAxes(joint_type) || joint_type == JOINT_TYPE_BALL)
         b2p_joint_get_anchor(theWorld->getWorld(), jointId, world_index, p);
     *anchor = Vector(p[0], p[1], p[2]);
 }
@@ -146,27 +153,27 @@ void Joint::getAnchor(Vector *anchor) const
 void Joint::setAnchor(const Vector &a)
 {
     MutexLocker locker(&(theWorld->iMutex));
-    if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_HINGE2)
+    if (joint_type == JOINT_TYPE_HINGE || twoAxes(joint_type) || joint_type == JOINT_TYPE_BALL)
         b2p_joint_set_anchor(theWorld->getWorld(), jointId, a.x(), a.y(), a.z());
 }
 
 void Joint::setAxis(const Vector &a)
 {
     MutexLocker locker(&(theWorld->iMutex));
-    if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_HINGE2 || joint_type == JOINT_TYPE_SLIDER)
+    if (joint_type == JOINT_TYPE_HINGE || twoAxes(joint_type) || joint_type == JOINT_TYPE_SLIDER)
         b2p_joint_set_axis1(theWorld->getWorld(), jointId, a.x(), a.y(), a.z());
 }
 
 void Joint::setAxis2(const Vector &a)
 {
     MutexLocker locker(&(theWorld->iMutex));
-    if (joint_type == JOINT_TYPE_HINGE2) b2p_joint_set_axis2(theWorld->getWorld(), jointId, a.x(), a.y(), a.z());
+    if (twoAxes(joint_type)) b2p_joint_set_axis2(theWorld->getWorld(), jointId, a.x(), a.y(), a.z());
 }
 
 void Joint::getAxisI(Vector *axis) const
 {
     double p[3] = {0, 0, 0};
-    if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_HINGE2 || joint_type == JOINT_TYPE_SLIDER)
+    if (joint_type == JOINT_TYPE_HINGE || twoAxes(joint_type) || joint_type == JOINT_TYPE_SLIDER)
         b2p_joint_get_axis1(theWorld->getWorld(), jointId, world_index, p);
     *axis = Vector(p[0], p[1], p[2]);
 }
@@ -179,7 +186,7 @@ void Joint::getAxis2(Vector *axis) const
 {
     MutexLocker locker(&(theWorld->iMutex));
     double p[3] = {0, 0, 0};
-    if (joint_type == JOINT_TYPE_HINGE2) b2p_joint_get_axis2(theWorld->getWorld(), jointId, world_index, p);
+    if (twoAxes(joint_type)) b2p_joint_get_axis2(theWorld->getWorld(), jointId, world_index, p);
     *axis = Vector(p[0], p[1], p[2]);
 }
 
@@ -189,25 +196,25 @@ void Joint::setWorldObject(std::shared_ptr<PhysicsInterface>) {}
 void Joint::setForceLimit(sReal max_force)
 {
     MutexLocker locker(&(theWorld->iMutex));
-    if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_HINGE2 || joint_type == JOINT_TYPE_SLIDER)
+    if (joint_type == JOINT_TYPE_HINGE || twoAxes(joint_type) || joint_type == JOINT_TYPE_SLIDER)
         setParam(B2P_PARAM_FMAX, max_force);
 }
 void Joint::setForceLimit2(sReal max_force)
 {
     MutexLocker locker(&(theWorld->iMutex));
-    if (joint_type == JOINT_TYPE_HINGE2) setParam(B2P_PARAM_FMAX | B2P_PARAM_GROUP2, max_force);
+    if (twoAxes(joint_type)) setParam(B2P_PARAM_FMAX | B2P_PARAM_GROUP2, max_force);
 }
 // Joint.cpp:355-393: hinge and slider negate, hinge2 does not
 void Joint::setVelocity(sReal velocity)
 {
     MutexLocker locker(&(theWorld->iMutex));
     if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_SLIDER) setParam(B2P_PARAM_VEL, -velocity);
-    else if (joint_type == JOINT_TYPE_HINGE2) setParam(B2P_PARAM_VEL, velocity);
+    else if (twoAxes(joint_type)) setParam(B2P_PARAM_VEL, velocity);
 }
 void Joint::setVelocity2(sReal velocity)
 {
     MutexLocker locker(&(theWorld->iMutex));
-    if (joint_type == JOINT_TYPE_HINGE2) setParam(B2P_PARAM_VEL | B2P_PARAM_GROUP2, velocity);
+    if (twoAxes(joint_type)) setParam(B2P_PARAM_VEL | B2P_PARAM_GROUP2, velocity);
 }
 void Joint::setVelocityBatch(const float *v)
 {
@@ -229,7 +236,7 @@ sReal Joint::getPosition(void) const
     double a = 0;
     b2p_joint_get_angle1(theWorld->getWorld(), jointId, world_index, &a);
     if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_SLIDER) return -a;
-    if (joint_type == JOINT_TYPE_HINGE2) return a;
+    if (twoAxes(joint_type)) return a;
     return 0;
 }
 sReal Joint::getPosition2(void) const { return 0; } // only universal in the reference (Joint.cpp:417-429)
@@ -244,6 +251,7 @@ void Joint::setJointAsMotor(int axis)
         setParam(B2P_PARAM_HI_STOP, kInf);
         break;
     case JOINT_TYPE_HINGE2:
+    case JOINT_TYPE_UNIVERSAL:
         if (!lo1 && !hi1 && axis == 1) {
             setParam(B2P_PARAM_LO_STOP, -kInf);
             setParam(B2P_PARAM_HI_STOP, kInf);
@@ -272,6 +280,7 @@ void Joint::unsetJointAsMotor(int axis)
         setParam(B2P_PARAM_HI_STOP, hi1);
         break;
     case JOINT_TYPE_HINGE2:
+    case JOINT_TYPE_UNIVERSAL:
         if (axis == 1) {
             setParam(B2P_PARAM_LO_STOP, lo1);
             setParam(B2P_PARAM_HI_STOP, hi1);
@@ -303,7 +312,7 @@ void Joint::reattacheJoint(void)
 {
     MutexLocker locker(&(theWorld->iMutex));
     b2p_arena *a = theWorld->getWorld();
-    if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_HINGE2) {
+    if (joint_type == JOINT_TYPE_HINGE || twoAxes(joint_type)) {
         double p[3];
         b2p_joint_get_anchor(a, jointId, 0, p);
         b2p_joint_set_anchor(a, jointId, p[0], p[1], p[2]);
@@ -335,7 +344,7 @@ void Joint::update(void)
     axis1_torque.setZero();
     axis2_torque.setZero();
     joint_load.setZero();
-    if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_HINGE2) {
+    if (joint_type == JOINT_TYPE_HINGE || twoAxes(joint_type)) {
         double p[3], ax[3], bp[3];
         b2p_joint_get_anchor(a, jointId, world_index, p);
         b2p_joint_get_axis1(a, jointId, world_index, ax);
@@ -410,14 +419,14 @@ sReal Joint::getVelocityI(void) const
     double r = 0;
     b2p_joint_get_angle1_rate(theWorld->getWorld(), jointId, world_index, &r);
     if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_SLIDER) return -1 * r;
-    if (joint_type == JOINT_TYPE_HINGE2) return r;
+    if (twoAxes(joint_type)) return r;
     return 0;
 }
 sReal Joint::getVelocity2(void) const
 {
     MutexLocker locker(&(theWorld->iMutex));
     double r = 0;
-    if (joint_type == JOINT_TYPE_HINGE2) b2p_joint_get_angle2_rate(theWorld->getWorld(), jointId, world_index, &r);
+    if (twoAxes(joint_type)) b2p_joint_get_angle2_rate(theWorld->getWorld(), jointId, world_index, &r);
     return r;
 }
 
@@ -428,46 +437,46 @@ void Joint::changeStepSize(const JointData &jointS)
     if (!(theWorld && theWorld->existsWorld())) return;
     calculateCfmErp();
     if (jointS.type == JOINT_TYPE_HINGE || jointS.type == JOINT_TYPE_SLIDER) applyLimotConfig(false);
-    else if (jointS.type == JOINT_TYPE_HINGE2) applyLimotConfig(true);
+    else if (twoAxes(jointS.type)) applyLimotConfig(true);
 }
 
 // Joint.cpp:1301-1464 (including the reference's sign / slot conventions)
 sReal Joint::getLowStop() const
 {
     if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_SLIDER) return -1 * getParam(B2P_PARAM_HI_STOP);
-    if (joint_type == JOINT_TYPE_HINGE2) return getParam(B2P_PARAM_LO_STOP);
+    if (twoAxes(joint_type)) return getParam(B2P_PARAM_LO_STOP);
     fprintf(stderr, "mars::ode_physics::Joint: getLowStop for type %d not implemented yet\n", joint_type);
     return 0.;
 }
 sReal Joint::getHighStop() const
 {
     if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_SLIDER) return -1 * getParam(B2P_PARAM_LO_STOP);
-    if (joint_type == JOINT_TYPE_HINGE2) return getParam(B2P_PARAM_HI_STOP);
+    if (twoAxes(joint_type)) return getParam(B2P_PARAM_HI_STOP);
     fprintf(stderr, "mars::ode_physics::Joint: getHighStop for type %d not implemented yet\n", joint_type);
     return 0.;
 }
 sReal Joint::getLowStop2() const
 {
-    if (joint_type == JOINT_TYPE_HINGE2) return getParam(B2P_PARAM_LO_STOP | B2P_PARAM_GROUP2);
+    if (twoAxes(joint_type)) return getParam(B2P_PARAM_LO_STOP | B2P_PARAM_GROUP2);
     fprintf(stderr, "mars::ode_physics::Joint: getLowStop2 for type %d not implemented yet\n", joint_type);
     return 0.;
 }
 sReal Joint::getHighStop2() const
 {
-    if (joint_type == JOINT_TYPE_HINGE2) return getParam(B2P_PARAM_HI_STOP | B2P_PARAM_GROUP2);
+    if (twoAxes(joint_type)) return getParam(B2P_PARAM_HI_STOP | B2P_PARAM_GROUP2);
     fprintf(stderr, "mars::ode_physics::Joint: getHighStop2 for type %d not implemented yet\n", joint_type);
     return 0.;
 }
 sReal Joint::getCFM() const
 {
-    if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_HINGE2 || joint_type == JOINT_TYPE_SLIDER)
+    if (joint_type == JOINT_TYPE_HINGE || twoAxes(joint_type) || joint_type == JOINT_TYPE_SLIDER)
         return getParam(B2P_PARAM_CFM);
     fprintf(stderr, "mars::ode_physics::Joint: cfm for type %d not implemented yet\n", joint_type);
     return 0.;
 }
 void Joint::setLowStop(sReal lowStop)
 {
-    if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_HINGE2 || joint_type == JOINT_TYPE_SLIDER)
+    if (joint_type == JOINT_TYPE_HINGE || twoAxes(joint_type) || joint_type == JOINT_TYPE_SLIDER)
         setParam(B2P_PARAM_LO_STOP, lowStop);
     else fprintf(stderr, "mars::ode_physics::Joint: setLowStop for type %d not implemented yet\n", joint_type);
 }
@@ -475,22 +484,22 @@ void Joint::setHighStop(sReal highStop)
 {
     // the reference writes dParamLoStop with the negated value for hinge and slider (Joint.cpp:1403,1409)
     if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_SLIDER) setParam(B2P_PARAM_LO_STOP, -1 * highStop);
-    else if (joint_type == JOINT_TYPE_HINGE2) setParam(B2P_PARAM_HI_STOP, highStop);
+    else if (twoAxes(joint_type)) setParam(B2P_PARAM_HI_STOP, highStop);
     else fprintf(stderr, "mars::ode_physics::Joint: setHighStop for type %d not implemented yet\n", joint_type);
 }
 void Joint::setLowStop2(sReal lowStop)
 {
-    if (joint_type == JOINT_TYPE_HINGE2) setParam(B2P_PARAM_HI_STOP, -1 * lowStop); // sic (Joint.cpp:1423)
+    if (twoAxes(joint_type)) setParam(B2P_PARAM_HI_STOP, -1 * lowStop); // sic (Joint.cpp:1423)
     else fprintf(stderr, "mars::ode_physics::Joint: setLowStop2 for type %d not implemented yet\n", joint_type);
 }
 void Joint::setHighStop2(sReal highStop)
 {
-    if (joint_type == JOINT_TYPE_HINGE2) setParam(B2P_PARAM_LO_STOP | B2P_PARAM_GROUP2, -1 * highStop);
+    if (twoAxes(joint_type)) setParam(B2P_PARAM_LO_STOP | B2P_PARAM_GROUP2, -1 * highStop);
     else fprintf(stderr, "mars::ode_physics::Joint: setHighStop2 for type %d not implemented yet\n", joint_type);
 }
 void Joint::setCFM(sReal v)
 {
-    if (joint_type == JOINT_TYPE_HINGE || joint_type == JOINT_TYPE_HINGE2 || joint_type == JOINT_TYPE_SLIDER)
+    if (joint_type == JOINT_TYPE_HINGE || twoAxes(joint_type) || joint_type == JOINT_TYPE_SLIDER)
         setParam(B2P_PARAM_CFM, v);
     else fprintf(stderr, "mars::ode_physics::Joint: cfm for type %d not implemented yet\n", joint_type);
 }
@@ -515,6 +524,8 @@ B2P_JOINT_BOILERPLATE(HingeJoint)
 B2P_JOINT_BOILERPLATE(FixedJoint)
 B2P_JOINT_BOILERPLATE(SliderJoint)
 B2P_JOINT_BOILERPLATE(Hinge2Joint)
+B2P_JOINT_BOILERPLATE(UniversalJoint)
+B2P_JOINT_BOILERPLATE(BallJoint)
 #undef B2P_JOINT_BOILERPLATE
 
 // HingeJoint.cpp:31-66
@@ -565,6 +576,37 @@ bool Hinge2Joint::createJoint(int b1, int b2)
     b2p_joint_set_axis1(a, jointId, config["axis1"]["x"], config["axis1"]["y"], config["axis1"]["z"]);
     b2p_joint_set_axis2(a, jointId, config["axis2"]["x"], config["axis2"]["y"], config["axis2"]["z"]);
     applyLimotConfig(true);
+    return true;
+}
+
+// UniversalJoint.cpp:33-80.  The reference creates a *hinge2* there and then sets *universal* parameters on it
+// (self-inconsistent, and the type is not registered in its loader); this creates the universal joint those
+// parameter calls address: same config keys (anchor, axis1, axis2, damping / spring / stops for both axes).
+bool UniversalJoint::createJoint(int b1, int b2)
+{
+    if (b1 < 0 && b2 < 0) return false;
+    b2p_arena *a = theWorld->getWorld();
+    jointId = b2p_joint_create(a, B2P_JOINT_UNIVERSAL, b1, b2);
+    if (jointId < 0) {
+        fprintf(stderr, "UniversalJoint: %s\n", b2p_last_error());
+        return false;
+    }
+    b2p_joint_set_anchor(a, jointId, config["anchor"]["x"], config["anchor"]["y"], config["anchor"]["z"]);
+    b2p_joint_set_axis1(a, jointId, config["axis1"]["x"], config["axis1"]["y"], config["axis1"]["z"]);
+    b2p_joint_set_axis2(a, jointId, config["axis2"]["x"], config["axis2"]["y"], config["axis2"]["z"]);
+    applyLimotConfig(true);
+    return true;
+}
+
+// The reference has no BallJoint class, only the JOINT_TYPE_BALL arms of Joint.cpp (:299-301, :447-449,
+// dJointSetBallAnchor / dJointGetBallAnchor); this is the class those arms presuppose.
+bool BallJoint::createJoint(int b1, int b2)
+{
+    if (b1 < 0 && b2 < 0) return false;
+    b2p_arena *a = theWorld->getWorld();
+    jointId = b2p_joint_create(a, B2P_JOINT_BALL, b1, b2);
+    if (jointId < 0) return false;
+    b2p_joint_set_anchor(a, jointId, config["anchor"]["x"], config["anchor"]["y"], config["anchor"]["z"]);
     return true;
 }
 

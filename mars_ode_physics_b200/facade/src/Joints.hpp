@@ -111,6 +111,8 @@ B2P_DECLARE_JOINT(HingeJoint)
 B2P_DECLARE_JOINT(FixedJoint)
 B2P_DECLARE_JOINT(SliderJoint)
 B2P_DECLARE_JOINT(Hinge2Joint)
+B2P_DECLARE_JOINT(UniversalJoint)
+B2P_DECLARE_JOINT(BallJoint)
 #undef B2P_DECLARE_JOINT
 
 typedef Joint *(*instantiateJointfPtr)(WorldPhysics *world, data_broker::DataBrokerInterface *dataBroker,

@@ -23,6 +23,8 @@ WorldPhysicsLoader::WorldPhysicsLoader(lib_manager::LibManager *theManager) : li
     JointFactory::Instance().addJointType("slider", &SliderJoint::instantiate);
     JointFactory::Instance().addJointType("prismatic", &SliderJoint::instantiate);
     JointFactory::Instance().addJointType("hinge2", &Hinge2Joint::instantiate);
+    JointFactory::Instance().addJointType("universal", &UniversalJoint::instantiate);
+    JointFactory::Instance().addJointType("ball", &BallJoint::instantiate);
 }
 
 WorldPhysicsLoader::~WorldPhysicsLoader(void) {}
