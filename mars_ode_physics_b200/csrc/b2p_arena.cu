@@ -1992,9 +1992,10 @@ int b2p_step(b2p_arena *a, double step_size)
     const int nb = (int)a->bodies.size();
     const int maxrows = (int)a->joints.size() * B2P_ROWS_PER_JOINT + a->maxc * rpc_of(a);
     P.hw_rows = a->d_hw_rows;
-    // SOR kernel choice.  The Tensor-Memory kernel (one thread per world, 128 worlds per SM) wins whenever a
-    // world's rows fit on chip there: its per-world arrays must leave room in shared memory, and the longest
-    // world seen so far must fit into registers + TMEM + the shared-memory overflow positions.
+    // SOR kernel choice.  The Tensor-Memory kernel (one thread per world) wins on every workload measured
+    // (configs B, C, D), also when part of a world's rows must be read from L2 in place, so it is used whenever
+    // its per-world arrays leave room for an overflow pool in shared memory: with 8 warps (256 worlds) per SM if
+    // the longest world seen so far then fits on chip, else with 4 warps (32 instead of 16 TMEM rows per world).
     const int seen = a->h_hw_rows && *(volatile int *)a->h_hw_rows > 0 ? *(volatile int *)a->h_hw_rows : maxrows;
     const int kr_t = a->rows_registers < 0 ? 8 : std::min(8, a->rows_registers & ~3);
     // warps per CTA: 8 (two per scheduler) unless the per-world arrays of 256 worlds leave no room for a pool
@@ -2005,7 +2006,7 @@ int b2p_step(b2p_arena *a, double step_size)
         want_t = std::max(std::min(seen, maxrows) - b2p_sor_tmem_rows_on_chip(kr_t, nw_t), 0);
         if (nw_t == 4 || a->sor_warps == 8 || (pool_t >= 0 && want_t <= pool_t)) break;
     }
-    bool use_tmem = a->sor_kernel == B2P_SOR_TMEM || (a->sor_kernel == B2P_SOR_AUTO && pool_t >= 0 && want_t <= pool_t);
+    bool use_tmem = a->sor_kernel == B2P_SOR_TMEM || (a->sor_kernel == B2P_SOR_AUTO && pool_t >= 0);
     if (use_tmem && pool_t < 0)
         return fail(B2P_ECAPACITY, "scene too large for the Tensor-Memory SOR kernel");
     if (use_tmem) {

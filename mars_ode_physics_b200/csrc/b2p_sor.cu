@@ -219,9 +219,15 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
             }
         }
         // positions that did not fit on chip: read in place (L2)
+        if (KR + Rs < mmax) {
+            Row qa = gload(KR + Rs < m ? s_ord[(KR + Rs) * WL + v] : R), qb;
 #pragma unroll 1
-        for (int k = KR + Rs; k < mmax; k++) {
-            relax(gload(k < m ? s_ord[k * WL + v] : R));
+            for (int k = KR + Rs; k < mmax; k += 2) {
+                qb = gload(k + 1 < m ? s_ord[(k + 1) * WL + v] : R);
+                relax(qa);
+                qa = gload(k + 2 < m ? s_ord[(k + 2) * WL + v] : R);
+                if (k + 1 < mmax) relax(qb);
+            }
         }
     }
 

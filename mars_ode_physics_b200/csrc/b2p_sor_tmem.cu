@@ -233,6 +233,26 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
         }
     };
 
+    // positions that did not fit on chip: read in place from global memory (L2), three gathers in flight
+    auto sweep_spilled = [&]() {
+        const int k0 = KR + TROWS + Ro;
+        if (k0 >= mmax) return;
+        constexpr int NSP = 3;
+        Row ring[NSP];
+#pragma unroll
+        for (int i = 0; i < NSP; i++) ring[i] = gload(k0 + i < mmax ? slot_at(k0 + i) : R);
+#pragma unroll 1
+        for (int k = k0; k < mmax; k += NSP) {
+#pragma unroll
+            for (int i = 0; i < NSP; i++) {
+                if (k + i < mmax) {
+                    relax(ring[i]);
+                    ring[i] = gload(k + i + NSP < mmax ? slot_at(k + i + NSP) : R);
+                }
+            }
+        }
+    };
+
     for (int it = 0; it < (mmax > 0 ? P.iters : 0); it++) {
         bool fresh = it == 0; // the rows on chip are not (yet) in the order of this sweep
         if (P.reorder == 0 && it >= 8 && (it & 7) == 0) {
@@ -283,8 +303,7 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
                 }
             }
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-#pragma unroll 1
-            for (int k = KR + TROWS + Ro; k < mmax; k++) relax(gload(slot_at(k)));
+            sweep_spilled();
             continue;
         }
         // positions in registers
@@ -314,8 +333,7 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
         // overflow positions in shared memory, then the ones that did not fit on chip (read in place from L2)
 #pragma unroll 1
         for (int p = 0; p < no; p++) relax(sload(p));
-#pragma unroll 1
-        for (int k = KR + TROWS + Ro; k < mmax; k++) relax(gload(slot_at(k)));
+        sweep_spilled();
     }
 
     if (w < P.W) {
