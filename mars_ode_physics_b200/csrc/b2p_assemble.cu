@@ -792,7 +792,10 @@ extern "C" size_t b2p_assemble_smem_bytes(int nb) { return sizeof(float) * (size
 
 extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, cudaStream_t stream)
 {
-    static size_t configured = 0;
+    static size_t configured_dev[B2P_MAX_DEVICES] = {0}; // cudaFuncSetAttribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t &configured = configured_dev[dev % B2P_MAX_DEVICES];
     const size_t smem = b2p_assemble_smem_bytes(nb);
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(b2p_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1082,7 +1082,10 @@ template <bool SAMPLED> __global__ void __launch_bounds__(CBD) b2p_collide_kerne
 
 extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, int sampled, cudaStream_t stream)
 {
-    static size_t configured[2] = {0, 0};
+    static size_t configured_dev[B2P_MAX_DEVICES][2] = {{0, 0}}; // cudaFuncSetAttribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t *configured = configured_dev[dev % B2P_MAX_DEVICES];
     const size_t smem = sizeof(float) * (size_t)(ng > 0 ? ng : 1) * 6 * CBD;
     auto kern = sampled ? b2p_collide_kernel<true> : b2p_collide_kernel<false>;
     if (smem > configured[sampled ? 1 : 0]) {

@@ -24,6 +24,7 @@
 #pragma once
 #include <stdint.h>
 
+#define B2P_MAX_DEVICES 16
 #define B2P_MAX_BODIES 32
 #define B2P_MAX_JOINTS 48
 #define B2P_MAX_GEOMS 48

@@ -249,7 +249,10 @@ extern "C" size_t b2p_integrate_smem_bytes(int nb) { return sizeof(float) * (siz
 
 extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, cudaStream_t stream)
 {
-    static size_t configured = 0;
+    static size_t configured_dev[B2P_MAX_DEVICES] = {0}; // cudaFuncSetAttribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t &configured = configured_dev[dev % B2P_MAX_DEVICES];
     const size_t smem = b2p_integrate_smem_bytes(nb);
     if (smem > configured) {
         cudaError_t e =

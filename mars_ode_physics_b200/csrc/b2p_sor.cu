@@ -265,7 +265,10 @@ extern "C" int b2p_sor_register_rows(int maxrows, int wanted)
 
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream)
 {
-    static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+    static size_t configured_dev[B2P_MAX_DEVICES][6] = {{0}}; // cudaFuncSetAttribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t *configured = configured_dev[dev % B2P_MAX_DEVICES];
     const size_t smem = b2p_sor_smem_bytes(nb, maxrows, P->rows_resident);
     void (*kern)(const StepParams) = nullptr;
     switch (P->rows_registers) {

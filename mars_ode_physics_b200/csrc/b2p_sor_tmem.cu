@@ -372,7 +372,10 @@ extern "C" int b2p_sor_tmem_rows_on_chip(int kr, int warps) { return kr + 32 / (
 
 extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxrows, cudaStream_t stream)
 {
-    static size_t configured[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    static size_t configured_dev[B2P_MAX_DEVICES][2][3] = {{{0}}}; // cudaFuncSetAttribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t (*configured)[3] = configured_dev[dev % B2P_MAX_DEVICES];
     const int nw = P->sor_warps;
     // at least half of the SM's shared memory, so that two CTAs never share an SM (the second one would
     // only spin in tcgen05.alloc until the first one releases its columns)
