@@ -310,8 +310,11 @@ def run_b200(args):
 
     def e2e_step(k, pending):
         cmd = cmds[k % NB]
-        for ji, j in enumerate(cmd_joints):
-            ar.joint_set_param_batch_ptr(j, param, cmd[ji].data_ptr())
+        if cmd_joints == list(range(len(cmd_joints))):
+            ar.joints_set_param_batch_ptr(param, cmd.data_ptr(), len(cmd_joints))  # one transfer
+        else:
+            for ji, j in enumerate(cmd_joints):
+                ar.joint_set_param_batch_ptr(j, param, cmd[ji].data_ptr())
         ar.collide()
         ar.step(H)
         t = ar.body_get_state_batch_begin(sc["chassis"], obs[k & 1].data_ptr())

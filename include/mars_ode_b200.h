@@ -213,6 +213,8 @@ int b2p_joint_set_param(b2p_arena *a, int joint, int world, int param, double va
 int b2p_joint_get_param(b2p_arena *a, int joint, int world, int param, double *value);
 /* batched motor commands: float[num_worlds] per call */
 int b2p_joint_set_param_batch(b2p_arena *a, int joint, int param, const float *values);
+/* the same for joints 0 .. num_joints-1 in one transfer: values[num_joints][num_worlds] */
+int b2p_joints_set_param_batch(b2p_arena *a, int param, const float *values, int num_joints);
 int b2p_joint_get_anchor(b2p_arena *a, int joint, int world, double out[3]);
 int b2p_joint_get_anchor2(b2p_arena *a, int joint, int world, double out[3]);
 int b2p_joint_get_axis1(b2p_arena *a, int joint, int world, double out[3]);

@@ -231,6 +231,10 @@ class Arena:
         assert a.shape == (self.num_worlds,)
         self._check(self.lib.b2p_joint_set_param_batch(self.h, j, param, a.ctypes.data_as(C.c_void_p)))
 
+    def joints_set_param_batch_ptr(self, param, host_ptr, num_joints):
+        """One H2D for values[num_joints][num_worlds] (pinned host memory) of joints 0 .. num_joints-1."""
+        self._check(self.lib.b2p_joints_set_param_batch(self.h, param, C.c_void_p(host_ptr), int(num_joints)))
+
     def joint_set_param_batch_ptr(self, j, param, host_ptr):
         self._check(self.lib.b2p_joint_set_param_batch(self.h, j, param, C.c_void_p(host_ptr)))
 

@@ -116,6 +116,7 @@ SIGNATURES = {
     "b2p_joint_set_param": (_I, [_P, _I, _I, _I, _D]),
     "b2p_joint_get_param": (_I, [_P, _I, _I, _I, _DP]),
     "b2p_joint_set_param_batch": (_I, [_P, _I, _I, _P]),
+    "b2p_joints_set_param_batch": (_I, [_P, _I, _P, _I]),
     "b2p_joint_get_anchor": (_I, [_P, _I, _I, _DP]),
     "b2p_joint_get_anchor2": (_I, [_P, _I, _I, _DP]),
     "b2p_joint_get_axis1": (_I, [_P, _I, _I, _DP]),

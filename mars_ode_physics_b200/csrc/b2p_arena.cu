@@ -1436,6 +1436,25 @@ int b2p_joint_set_param_batch(b2p_arena *a, int ji, int param, const float *valu
     return 0;
 }
 
+// One transfer for a whole command vector: values[num_joints][num_worlds] -> the same per-world parameter
+// (VEL or FMAX, optionally | GROUP2) of joints 0 .. num_joints-1.
+int b2p_joints_set_param_batch(b2p_arena *a, int param, const float *values, int num_joints)
+{
+    if (!a || !values) return fail(B2P_EINVAL, "null argument");
+    if (num_joints <= 0 || num_joints > (int)a->joints.size()) return fail(B2P_EINVAL, "bad joint count");
+    const int num = param & 0xff, axis = ((param & 0xff00) == B2P_PARAM_GROUP2) ? 1 : 0;
+    if (num != B2P_PARAM_VEL && num != B2P_PARAM_FMAX)
+        return fail(B2P_EUNSUPPORTED, "only VEL and FMAX can be set per world");
+    CUDA_TRY(cudaSetDevice(a->device));
+    int rc = mirror_to_device(a, a->jcmd);
+    if (rc) return rc;
+    const size_t field = (size_t)axis * 2 + (num == B2P_PARAM_FMAX ? 1 : 0);
+    CUDA_TRY(cudaMemcpy2DAsync(a->jcmd.dev + field * a->Wp, sizeof(float) * 4 * a->Wp, values, sizeof(float) * a->W,
+                               sizeof(float) * a->W, (size_t)num_joints, cudaMemcpyHostToDevice, a->stream));
+    a->jcmd.dev_newer = true;
+    return 0;
+}
+
 static int joint_poses(b2p_arena *a, const HJoint &j, int world, double *p0, double *q0, double *p1, double *q1)
 {
     int rc;
