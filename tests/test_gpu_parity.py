@@ -276,3 +276,23 @@ def test_full_size_kernels_agree_and_repeat(cuda_lib):
     tail = ar.state_download(len(sc["bodies"]))
     assert np.array_equal(tail, outs[0][0][:, :, W - 96:])
     ar.close()
+
+
+def test_large_scene_falls_back_to_paired_kernel(cuda_lib):
+    """A 30-link hinge chain (180 rows, 30 bodies per world) does not fit the Tensor-Memory kernel's per-world
+    shared-memory arrays: the arena picks the paired-lane kernel by itself, and the result matches the oracle."""
+    W = 20
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    for be in (ar, oc):
+        sc = scenes.pendulum_chain(be, 30)
+        for w in range(W):
+            be.body_set_angular_vel(sc["bodies"][29], (0, 0.02 * w, 0.0), w)
+    for _ in range(40):
+        ar.step(H)
+        oc.step(H)
+    assert ar.sor_kernel_used() == capi.SOR_PAIRED
+    for w in (0, W - 1):
+        assert ar.last_num_rows(w) == oc.last_num_rows(w) == 150
+        assert ar.rand_get_seed(w) == oc.rand_get_seed(w)
+    e = _max_state_err(ar, oc, 30)
+    assert e["pos"] < 2e-4 and e["quat"] < 5e-4, e
