@@ -279,12 +279,14 @@ def test_full_size_kernels_agree_and_repeat(cuda_lib):
 
 
 def test_large_scene_falls_back_to_paired_kernel(cuda_lib):
-    """A 30-link hinge chain (180 rows, 30 bodies per world) does not fit the Tensor-Memory kernel's per-world
-    shared-memory arrays: the arena picks the paired-lane kernel by itself, and the result matches the oracle."""
+    """A 30-link hinge chain with room for 20 contacts (240 row slots, 30 bodies per world) does not fit the
+    Tensor-Memory kernel's per-world shared-memory arrays: the arena picks the paired-lane kernel by itself, and
+    the result matches the oracle."""
     W = 20
     ar, oc = Arena(W), orc.OracleBatch(W)
     for be in (ar, oc):
         sc = scenes.pendulum_chain(be, 30)
+        be.set_max_contacts(20)
         for w in range(W):
             be.body_set_angular_vel(sc["bodies"][29], (0, 0.02 * w, 0.0), w)
     for _ in range(40):
