@@ -201,6 +201,11 @@ int b2p_padded_worlds(const b2p_arena *a);
 void *b2p_device_state(b2p_arena *a);       /* [nb*13][Wp] */
 void *b2p_device_joint_cmd(b2p_arena *a);   /* [nj*4][Wp]: vel1,fmax1,vel2,fmax2 */
 void *b2p_device_joint_obs(b2p_arena *a);   /* [nj*4][Wp]: angle1,rate1,angle2,rate2 */
+void *b2p_device_joint_feedback(b2p_arena *a);  /* [nj*13][Wp]: f1 t1 f2 t2 lambda (dJointFeedback, Joint.cpp:268) */
+void *b2p_device_contact_records(b2p_arena *a); /* [maxc*16][Wp]: the contact stream (b2p_contact_desc order) */
+void *b2p_device_contact_count(b2p_arena *a);   /* int[Wp] */
+/* dJointFeedback of all joints and worlds: float[num_joints][13][num_worlds] (Joint::update, Joint.cpp:859-1019) */
+int b2p_joint_feedback_download(b2p_arena *a, float *host_fb);
 
 /* ---- joints (dJoint*: reference src/joints/) ---- */
 int b2p_joint_create(b2p_arena *a, int type, int body1, int body2);         /* dJointCreate* + dJointAttach */

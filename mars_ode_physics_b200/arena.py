@@ -191,6 +191,12 @@ class Arena:
         self._check(self.lib.b2p_joint_obs_download(self.h, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def joint_feedback_download(self, num_joints):
+        """float[num_joints][13][num_worlds]: f1 t1 f2 t2 lambda of every joint after the last step."""
+        out = np.empty((num_joints, 13, self.num_worlds), dtype=np.float32)
+        self._check(self.lib.b2p_joint_feedback_download(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def body_get_state_batch_ptr(self, b, host_ptr):
         """Asynchronous D2H of float[13][num_worlds] into (pinned) host memory; sync() before reading."""
         self._check(self.lib.b2p_body_get_state_batch(self.h, b, C.c_void_p(host_ptr)))

@@ -102,6 +102,10 @@ SIGNATURES = {
     "b2p_state_download": (_I, [_P, _P]),
     "b2p_body_get_state_batch": (_I, [_P, _I, _P]),
     "b2p_joint_obs_download": (_I, [_P, _P]),
+    "b2p_joint_feedback_download": (_I, [_P, _P]),
+    "b2p_device_joint_feedback": (_P, [_P]),
+    "b2p_device_contact_records": (_P, [_P]),
+    "b2p_device_contact_count": (_P, [_P]),
     "b2p_body_get_state_batch_begin": (_I, [_P, _I, _P]),
     "b2p_io_wait": (_I, [_P, _I]),
     "b2p_padded_worlds": (_I, [_P]),

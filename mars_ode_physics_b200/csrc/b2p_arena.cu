@@ -1195,6 +1195,21 @@ int b2p_io_wait(b2p_arena *a, int ticket)
 void *b2p_device_state(b2p_arena *a) { return a ? a->state.dev : nullptr; }
 void *b2p_device_joint_cmd(b2p_arena *a) { return a ? a->jcmd.dev : nullptr; }
 void *b2p_device_joint_obs(b2p_arena *a) { return a ? a->jobs.dev : nullptr; }
+void *b2p_device_joint_feedback(b2p_arena *a) { return a ? a->jfb.dev : nullptr; }
+void *b2p_device_contact_records(b2p_arena *a) { return a ? a->crec.dev : nullptr; }
+void *b2p_device_contact_count(b2p_arena *a) { return a ? a->ccount.dev : nullptr; }
+
+// dJointFeedback of every joint and world after the last step: float[nj][13][num_worlds] = f1 t1 f2 t2 lambda
+int b2p_joint_feedback_download(b2p_arena *a, float *host_fb)
+{
+    if (!a || !host_fb) return fail(B2P_EINVAL, "null argument");
+    if (!a->stepped || !a->jfb.dev) return fail(B2P_EINVAL, "no step has run yet");
+    CUDA_TRY(cudaSetDevice(a->device));
+    CUDA_TRY(cudaMemcpy2DAsync(host_fb, sizeof(float) * a->W, a->jfb.dev, sizeof(float) * a->Wp, sizeof(float) * a->W,
+                               a->joints.size() * 13, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    return 0;
+}
 
 // ---------------- joints ----------------
 int b2p_joint_create(b2p_arena *a, int type, int body1, int body2)

@@ -185,5 +185,8 @@ def test_ball_and_universal_parity(cuda_lib):
     rates = [oc.joint_get_angle1_rate(ju, w) for w in range(W)]
     assert np.median(np.abs(np.array(rates) - 0.8)) < 0.1, rates
     # device-side observation array agrees with the host-side getter
+    fb = ar.joint_feedback_download(2)
+    assert np.allclose(fb[ju, :, 5], ar.joint_get_feedback(ju, 5), rtol=0, atol=0)
+    assert np.allclose(fb[ju, :, 5], oc.joint_get_feedback(ju, 5), rtol=5e-3, atol=5e-3)
     obs = ar.joint_obs_download(2)
     assert abs(obs[ju, 0, 3] - ar.joint_get_angle1(ju, 3)) < 1e-5 and abs(obs[ju, 2, 3] - ar.joint_get_angle2(ju, 3)) < 1e-5
