@@ -392,8 +392,8 @@ def run_b200(args):
                                      "integrate": int_ms}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(len(cmd_joints) * W * 4),
                     "d2h_bytes_per_step": int(13 * W * 4), "ms_per_step": ms_e2e / K,
-                    "mode": "pipelined control loop, depth 2: D2H of step k on a copy stream overlaps step k+1; "
-                            "H2D of the commands on the step's stream"},
+                    "mode": "pipelined control loop, depth 2: on a copy stream the D2H of step k overlaps step k+1 and "
+                            "the H2D of step k+1's commands follows step k's assemble kernel"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,

@@ -250,6 +250,10 @@ struct b2p_arena {
     } io[2];
     cudaStream_t io_stream = nullptr;
     int io_next = 0;
+    // command uploads on the copy stream: ordered after the assemble kernel of the last step (the only reader of
+    // jcmd) and before the next one
+    cudaEvent_t ev_asm_done = nullptr, ev_h2d_done = nullptr;
+    bool asm_recorded = false, h2d_pending = false;
     long long steps_done = 0;
     bool stepped = false;
 };
@@ -293,8 +297,20 @@ template <typename T> int mirror_to_device(b2p_arena *a, Mirror<T> &m)
     return 0;
 }
 
+// a command upload may still be in flight on the copy stream: everything on the main stream that follows is
+// ordered behind it
+int join_pending_upload(b2p_arena *a)
+{
+    if (a->h2d_pending) {
+        CUDA_TRY(cudaStreamWaitEvent(a->stream, a->ev_h2d_done, 0));
+        a->h2d_pending = false;
+    }
+    return 0;
+}
+
 template <typename T> int mirror_to_host(b2p_arena *a, Mirror<T> &m)
 {
+    if (int rc = join_pending_upload(a)) return rc;
     if (m.dev_newer && m.dev && m.dev_elems) {
         CUDA_TRY(cudaMemcpyAsync(m.host.data(), m.dev, sizeof(T) * m.dev_elems, cudaMemcpyDeviceToHost, a->stream));
         CUDA_TRY(cudaStreamSynchronize(a->stream));
@@ -438,6 +454,8 @@ void sym_sqrt33(const double *A, double *out)
 // (re)build the device template and size every buffer
 int finalize(b2p_arena *a)
 {
+    if (a->jcmd.host_newer)
+        if (int rc = join_pending_upload(a)) return rc; // a host-side edit is about to overwrite the device copy
     const int nb = (int)a->bodies.size(), nj = (int)a->joints.size(), ng = (int)a->geoms.size();
     if (nb > B2P_MAX_BODIES) return fail(B2P_ECAPACITY, "too many bodies (%d > %d)", nb, B2P_MAX_BODIES);
     if (nj > B2P_MAX_JOINTS) return fail(B2P_ECAPACITY, "too many joints (%d > %d)", nj, B2P_MAX_JOINTS);
@@ -826,6 +844,8 @@ void b2p_arena_destroy(b2p_arena *a)
         if (sl.done) cudaEventDestroy(sl.done);
     }
     if (a->io_stream) cudaStreamDestroy(a->io_stream);
+    if (a->ev_asm_done) cudaEventDestroy(a->ev_asm_done);
+    if (a->ev_h2d_done) cudaEventDestroy(a->ev_h2d_done);
     delete a;
 }
 
@@ -1443,6 +1463,7 @@ int b2p_joint_set_param_batch(b2p_arena *a, int ji, int param, const float *valu
     const int num = param & 0xff, axis = ((param & 0xff00) == B2P_PARAM_GROUP2) ? 1 : 0;
     if (num != B2P_PARAM_VEL && num != B2P_PARAM_FMAX)
         return fail(B2P_EUNSUPPORTED, "only VEL and FMAX can be set per world");
+    if ((rc = join_pending_upload(a))) return rc;
     if ((rc = mirror_to_device(a, a->jcmd))) return rc; // device copy current
     const size_t field = (size_t)ji * 4 + axis * 2 + (num == B2P_PARAM_FMAX ? 1 : 0);
     CUDA_TRY(cudaMemcpyAsync(a->jcmd.dev + field * a->Wp, values, sizeof(float) * a->W, cudaMemcpyHostToDevice,
@@ -1461,11 +1482,25 @@ int b2p_joints_set_param_batch(b2p_arena *a, int param, const float *values, int
     if (num != B2P_PARAM_VEL && num != B2P_PARAM_FMAX)
         return fail(B2P_EUNSUPPORTED, "only VEL and FMAX can be set per world");
     CUDA_TRY(cudaSetDevice(a->device));
+    // If the device copy is current and a step has been enqueued, the transfer goes over the copy stream behind
+    // that step's assemble kernel (the only reader of jcmd), i.e. it overlaps the step's SOR-LCP kernel.
+    const bool overlap = !a->jcmd.host_newer && a->jcmd.dev && a->asm_recorded && a->io_stream;
     int rc = mirror_to_device(a, a->jcmd);
     if (rc) return rc;
     const size_t field = (size_t)axis * 2 + (num == B2P_PARAM_FMAX ? 1 : 0);
+    cudaStream_t st = a->stream;
+    if (overlap) {
+        if ((rc = join_pending_upload(a))) return rc; // uploads stay in order among themselves
+        if (!a->ev_h2d_done) CUDA_TRY(cudaEventCreateWithFlags(&a->ev_h2d_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaStreamWaitEvent(a->io_stream, a->ev_asm_done, 0));
+        st = a->io_stream;
+    }
     CUDA_TRY(cudaMemcpy2DAsync(a->jcmd.dev + field * a->Wp, sizeof(float) * 4 * a->Wp, values, sizeof(float) * a->W,
-                               sizeof(float) * a->W, (size_t)num_joints, cudaMemcpyHostToDevice, a->stream));
+                               sizeof(float) * a->W, (size_t)num_joints, cudaMemcpyHostToDevice, st));
+    if (overlap) {
+        CUDA_TRY(cudaEventRecord(a->ev_h2d_done, a->io_stream));
+        a->h2d_pending = true;
+    }
     a->jcmd.dev_newer = true;
     return 0;
 }
@@ -2063,8 +2098,14 @@ int b2p_step(b2p_arena *a, double step_size)
     if (b2p_assemble_smem_bytes(nb) > kSmemMax || b2p_integrate_smem_bytes(nb) > kSmemMax ||
         (!use_tmem && b2p_sor_smem_bytes(nb, maxrows, P.rows_resident) > kSmemMax))
         return fail(B2P_ECAPACITY, "scene needs more than %zu bytes of shared memory per CTA", kSmemMax);
+    if ((rc = join_pending_upload(a))) return rc;
     if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[0], a->stream));
     CUDA_TRY(b2p_launch_assemble(&P, nb, a->stream));
+    if (a->io_stream) { // lets the next command upload start as soon as this kernel has read jcmd
+        if (!a->ev_asm_done) CUDA_TRY(cudaEventCreateWithFlags(&a->ev_asm_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(a->ev_asm_done, a->stream));
+        a->asm_recorded = true;
+    }
     if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[1], a->stream));
     if (use_tmem) CUDA_TRY(b2p_launch_sor_tmem(&P, nb, maxrows, a->stream));
     else CUDA_TRY(b2p_launch_sor(&P, nb, maxrows, a->stream));

@@ -298,3 +298,43 @@ def test_large_scene_falls_back_to_paired_kernel(cuda_lib):
         assert ar.rand_get_seed(w) == oc.rand_get_seed(w)
     e = _max_state_err(ar, oc, 30)
     assert e["pos"] < 2e-4 and e["quat"] < 5e-4, e
+
+
+def test_overlapped_command_upload_is_ordered(cuda_lib):
+    """b2p_joints_set_param_batch sends the commands over the copy stream behind the previous step's assemble
+    kernel once the pipelined read-back is in use; every step must still see exactly the commands issued before
+    it.  Reference: the same command sequence through the synchronous per-joint setter."""
+    import torch
+    W, steps = 96, 40
+    param = capi.PARAM_VEL | capi.PARAM_GROUP2
+    rng = np.random.default_rng(3)
+    seq = rng.uniform(1.0, 6.0, size=(steps, 4, W)).astype(np.float32)
+
+    ar, sc = _rover_arena(W, capi.SOR_AUTO)
+    assert sc["joints"] == [0, 1, 2, 3]
+    for k in range(steps):
+        for j in sc["joints"]:
+            ar.joint_set_param_batch(j, param, seq[k, j])
+        ar.collide()
+        ar.step(H)
+    want = ar.state_download(len(sc["bodies"])).copy()
+    ar.close()
+
+    ar, sc = _rover_arena(W, capi.SOR_AUTO)
+    cmds = [torch.empty((4, W), dtype=torch.float32).pin_memory() for _ in range(3)]
+    obs = [torch.empty((13, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+    pending = None
+    for k in range(steps):
+        cmds[k % 3].copy_(torch.from_numpy(seq[k]))
+        ar.joints_set_param_batch_ptr(param, cmds[k % 3].data_ptr(), 4)
+        ar.collide()
+        ar.step(H)
+        t = ar.body_get_state_batch_begin(sc["chassis"], obs[k & 1].data_ptr())
+        if pending is not None:
+            ar.io_wait(pending)
+        pending = t
+    ar.io_wait(pending)
+    got = ar.state_download(len(sc["bodies"]))
+    assert np.array_equal(got, want)
+    assert np.array_equal(obs[(steps - 1) & 1].numpy(), want[sc["chassis"]])
+    ar.close()
