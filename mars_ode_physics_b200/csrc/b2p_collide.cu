@@ -822,12 +822,31 @@ __device__ __forceinline__ int collide_sphere_hf(const DevHeightfield &hf, const
             out.pos[0] = c[0], out.pos[1] = c[1], out.pos[2] = h;
         }
     }
+    const float r2cull = r * r * 1.0001f + 1e-12f;
     for (int iy = iy0; iy <= iy1; iy++)
-        for (int ix = ix0; ix <= ix1; ix++)
+        for (int ix = ix0; ix <= ix1; ix++) {
+            // the cell's four corners once for both triangles, and a conservative cull: every point of the two
+            // triangles lies in the box [x0,x1] x [y0,y1] x [hmin,hmax]; if that box is farther from the centre
+            // than r (with a margin far above fp32 rounding) neither triangle can touch the sphere.  The cull
+            // never changes the result, it only skips triangles whose test below would fail.
+            const float x0 = hf.x0 + ix * hf.dx, y0 = hf.y0 + iy * hf.dx, x1 = x0 + hf.dx, y1 = y0 + hf.dx;
+            const float h00 = hf_h(hf, ix, iy), h10 = hf_h(hf, ix + 1, iy), h11 = hf_h(hf, ix + 1, iy + 1),
+                        h01 = hf_h(hf, ix, iy + 1);
+            const float hmn = fminf(fminf(h00, h10), fminf(h11, h01)), hmx = fmaxf(fmaxf(h00, h10), fmaxf(h11, h01));
+            const float ex = fmaxf(fmaxf(x0 - c[0], c[0] - x1), 0.f), ey = fmaxf(fmaxf(y0 - c[1], c[1] - y1), 0.f);
+            const float ez = fmaxf(fmaxf(hmn - c[2], c[2] - hmx), 0.f);
+            if (ex * ex + ey * ey + ez * ez > r2cull) continue;
 #pragma unroll
             for (int t = 0; t < 2; t++) {
                 float a[3], b[3], cc[3], q[3], n[3];
-                hf_triangle(hf, ix, iy, t, a, b, cc);
+                a[0] = x0, a[1] = y0, a[2] = h00;
+                if (t == 0) {
+                    b[0] = x1, b[1] = y0, b[2] = h10;
+                    cc[0] = x1, cc[1] = y1, cc[2] = h11;
+                } else {
+                    b[0] = x1, b[1] = y1, b[2] = h11;
+                    cc[0] = x0, cc[1] = y1, cc[2] = h01;
+                }
                 closest_pt_triangle(c, a, b, cc, q);
                 const float dv[3] = {c[0] - q[0], c[1] - q[1], c[2] - q[2]};
                 const float dist = sqrtf(dot3(dv, dv));
@@ -845,6 +864,7 @@ __device__ __forceinline__ int collide_sphere_hf(const DevHeightfield &hf, const
                     }
                 }
             }
+        }
     return best >= 0.f ? 1 : 0;
 }
 
