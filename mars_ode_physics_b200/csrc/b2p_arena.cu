@@ -20,14 +20,14 @@
 #include "b2p_dev.h"
 #include "b2p_universal.h"
 
-extern "C" size_t b2p_assemble_smem_bytes(int nb);
+extern "C" size_t b2p_assemble_smem_bytes(int nb, int nj);
 extern "C" size_t b2p_integrate_smem_bytes(int nb);
 extern "C" size_t b2p_sor_smem_bytes(int nb, int maxrows, int rows_resident);
 extern "C" int b2p_sor_register_rows(int maxrows, int wanted);
 extern "C" size_t b2p_sor_tmem_smem_bytes(int nb, int maxrows, int pool, int warps);
 extern "C" int b2p_sor_tmem_rows_on_chip(int kr, int warps);
 extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
-extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, cudaStream_t stream);
+extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, int nj, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, int sampled, cudaStream_t stream);
@@ -2095,12 +2095,12 @@ int b2p_step(b2p_arena *a, double step_size)
         P.rows_resident = pick_rows_resident(a, nb, maxrows, P.rows_registers);
     }
     a->sor_kernel_used = use_tmem ? B2P_SOR_TMEM : B2P_SOR_PAIRED;
-    if (b2p_assemble_smem_bytes(nb) > kSmemMax || b2p_integrate_smem_bytes(nb) > kSmemMax ||
+    if (b2p_assemble_smem_bytes(nb, (int)a->joints.size()) > kSmemMax || b2p_integrate_smem_bytes(nb) > kSmemMax ||
         (!use_tmem && b2p_sor_smem_bytes(nb, maxrows, P.rows_resident) > kSmemMax))
         return fail(B2P_ECAPACITY, "scene needs more than %zu bytes of shared memory per CTA", kSmemMax);
     if ((rc = join_pending_upload(a))) return rc;
     if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[0], a->stream));
-    CUDA_TRY(b2p_launch_assemble(&P, nb, a->stream));
+    CUDA_TRY(b2p_launch_assemble(&P, nb, (int)a->joints.size(), a->stream));
     if (a->io_stream) { // lets the next command upload start as soon as this kernel has read jcmd
         if (!a->ev_asm_done) CUDA_TRY(cudaEventCreateWithFlags(&a->ev_asm_done, cudaEventDisableTiming));
         CUDA_TRY(cudaEventRecord(a->ev_asm_done, a->stream));

@@ -26,9 +26,23 @@ namespace {
 constexpr int BD = 64; // threads (= worlds) per CTA
 
 struct Smem {
+    const DevBody *bodies;   // the scene template's bodies and joints, copied into shared memory by the CTA: the
+    const DevJoint *joints;  // kernel reads them all the time, always warp-uniformly (one broadcast LDS instead
+                             // of a global load on the thread's dependent chain)
     float *t1; // [nb*6][BD]  fe -> tmp1 = v/h + invM fe
     float *sw; // [nb*6][BD]  symmetric sqrt(invI_world): xx xy xz yy yz zz
+    float *pq; // [nb*7][BD]  position and quaternion of every body: the joints and contacts re-read the poses
+               //             of their bodies, and a shared-memory read costs a tenth of a global one
 };
+
+// pose of body b from the copy phase 1 left in shared memory
+__device__ __forceinline__ void load_pose_s(const Smem &S, int b, int tid, BodyPose &bp)
+{
+    const float *p = S.pq + (size_t)(b * 7) * BD + tid;
+    bp.pos[0] = p[0], bp.pos[1] = p[BD], bp.pos[2] = p[2 * BD];
+    bp.q[0] = p[3 * BD], bp.q[1] = p[4 * BD], bp.q[2] = p[5 * BD], bp.q[3] = p[6 * BD];
+    q_to_R(bp.q, bp.R);
+}
 
 // One constraint row under construction (ODE Info2 view).
 struct Row {
@@ -56,14 +70,14 @@ struct PairCtx {
     float S0[6], S1[6];
 };
 
-__device__ __forceinline__ void pair_ctx(PairCtx &pc, const DevTemplate *T, const Smem &S, int tid)
+__device__ __forceinline__ void pair_ctx(PairCtx &pc, const Smem &S, int tid)
 {
-    pc.sm0 = T->bodies[pc.b0].sqrtInvMass;
+    pc.sm0 = S.bodies[pc.b0].sqrtInvMass;
 #pragma unroll
     for (int k = 0; k < 6; k++) pc.S0[k] = S.sw[(size_t)(pc.b0 * 6 + k) * BD + tid];
     pc.sm1 = 0.f;
     if (pc.b1 >= 0) {
-        pc.sm1 = T->bodies[pc.b1].sqrtInvMass;
+        pc.sm1 = S.bodies[pc.b1].sqrtInvMass;
 #pragma unroll
         for (int k = 0; k < 6; k++) pc.S1[k] = S.sw[(size_t)(pc.b1 * 6 + k) * BD + tid];
     } else {
@@ -201,17 +215,33 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
     Smem S;
     S.t1 = (float *)smem_raw;
     S.sw = S.t1 + (size_t)nb * 6 * BD;
+    S.pq = S.sw + (size_t)nb * 6 * BD;
     const int tid = threadIdx.x;
     const int w = blockIdx.x * BD + tid;
+    {
+        uint32_t *sb = (uint32_t *)(S.pq + (size_t)nb * 7 * BD);
+        uint32_t *sj = sb + (size_t)nb * (sizeof(DevBody) / 4);
+        const uint32_t *gb = (const uint32_t *)T->bodies, *gj = (const uint32_t *)T->joints;
+        for (int i = tid; i < nb * (int)(sizeof(DevBody) / 4); i += BD) sb[i] = __ldg(gb + i);
+        for (int i = tid; i < nj * (int)(sizeof(DevJoint) / 4); i += BD) sj[i] = __ldg(gj + i);
+        S.bodies = (const DevBody *)sb;
+        S.joints = (const DevJoint *)sj;
+        __syncthreads();
+    }
     if (w >= P.W) return;
     const int Wp = P.Wp;
     const float h = P.h, hinv = 1.0f / P.h;
 
     // ---------------- phase 1: bodies ----------------
     for (int b = 0; b < nb; b++) {
-        const DevBody &bc = T->bodies[b];
+        const DevBody &bc = S.bodies[b];
         BodyPose bp;
         load_pose(P, b, w, bp);
+        {
+            float *p = S.pq + (size_t)(b * 7) * BD + tid;
+            p[0] = bp.pos[0], p[BD] = bp.pos[1], p[2 * BD] = bp.pos[2];
+            p[3 * BD] = bp.q[0], p[4 * BD] = bp.q[1], p[5 * BD] = bp.q[2], p[6 * BD] = bp.q[3];
+        }
         const int f = b * B2P_STATE_FIELDS;
         float avel[3] = {G(P.state, f + 10), G(P.state, f + 11), G(P.state, f + 12)};
         float facc[3] = {G(P.force, b * 6 + 0), G(P.force, b * 6 + 1), G(P.force, b * 6 + 2)};
@@ -275,12 +305,12 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
     // ---------------- phase 1a: limit motors powered into a stop add forces (rare) -------------
     if (T->has_limit_motors) {
         for (int j = 0; j < nj; j++) {
-            const DevJoint &jc = T->joints[j];
+            const DevJoint &jc = S.joints[j];
             if (jc.type == 6 || jc.b0 < 0) continue;
             BodyPose p0, p1;
-            load_pose(P, jc.b0, w, p0);
+            load_pose_s(S, jc.b0, tid, p0);
             const bool has_b1 = jc.b1 >= 0;
-            if (has_b1) load_pose(P, jc.b1, w, p1);
+            if (has_b1) load_pose_s(S, jc.b1, tid, p1);
             LimotState st;
             joint_limit_state(jc, p0, p1, st);
             const float vel = G(P.jcmd, j * 4 + 0), fmax = G(P.jcmd, j * 4 + 1);
@@ -325,7 +355,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
 
     // ---------------- phase 1b: fe -> gmem (needed by the epilogue), tmp1 -> smem --------------
     for (int b = 0; b < nb; b++) {
-        const DevBody &bc = T->bodies[b];
+        const DevBody &bc = S.bodies[b];
         const int f = b * B2P_STATE_FIELDS;
         float Iw[9], fe[6], t3[3];
         load_invIw(P, b, w, Iw);
@@ -350,7 +380,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
     int nhead = 0;
 
     for (int j = 0; j < nj; j++) {
-        const DevJoint &jc = T->joints[j];
+        const DevJoint &jc = S.joints[j];
         int mrows = 0, limot_row = -1;
         if (jc.b0 >= 0) {
             const bool has_b1 = jc.b1 >= 0;
@@ -358,9 +388,9 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
             PairCtx pc;
             pc.b0 = jc.b0;
             pc.b1 = jc.b1;
-            load_pose(P, jc.b0, w, p0);
-            if (has_b1) load_pose(P, jc.b1, w, p1);
-            pair_ctx(pc, T, S, tid);
+            load_pose_s(S, jc.b0, tid, p0);
+            if (has_b1) load_pose_s(S, jc.b1, tid, p1);
+            pair_ctx(pc, S, tid);
             const float kerp = hinv * P.erp;
             Row r;
             if (jc.type == 1) {
@@ -692,9 +722,9 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
         pc.b0 = b0;
         pc.b1 = b1;
         BodyPose p0, p1;
-        load_pose(P, b0, w, p0);
-        if (b1 >= 0) load_pose(P, b1, w, p1);
-        pair_ctx(pc, T, S, tid);
+        load_pose_s(S, b0, tid, p0);
+        if (b1 >= 0) load_pose_s(S, b1, tid, p1);
+        pair_ctx(pc, S, tid);
         const float erp = (mode & 0x008) ? soft_erp : P.erp;
         const float pushout = hinv * erp * depth;
         float c1[3], c2[3] = {0.f, 0.f, 0.f};
@@ -788,15 +818,18 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
 
 } // namespace
 
-extern "C" size_t b2p_assemble_smem_bytes(int nb) { return sizeof(float) * (size_t)nb * 12 * BD; }
+extern "C" size_t b2p_assemble_smem_bytes(int nb, int nj)
+{
+    return sizeof(float) * (size_t)nb * 19 * BD + (size_t)nb * sizeof(DevBody) + (size_t)nj * sizeof(DevJoint);
+}
 
-extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, cudaStream_t stream)
+extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, int nj, cudaStream_t stream)
 {
     static size_t configured_dev[B2P_MAX_DEVICES] = {0}; // cudaFuncSetAttribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
     size_t &configured = configured_dev[dev % B2P_MAX_DEVICES];
-    const size_t smem = b2p_assemble_smem_bytes(nb);
+    const size_t smem = b2p_assemble_smem_bytes(nb, nj);
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(b2p_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
