@@ -925,7 +925,7 @@ __device__ __forceinline__ void flip(CPoint *c, int n)
 
 // g1 is dynamic; g2 dynamic or static.  Contacts have the normal pointing from g2 into g1.
 template <bool SAMPLED>
-__device__ __forceinline__ int narrowphase(const CollideParams &P, const DevTemplate *T, const DevGeom &g1,
+__device__ __forceinline__ int narrowphase(const CollideParams &P, const DevHeightfield &hfield, const DevGeom &g1,
                                            const DevGeom &g2, int w, CPoint *out)
 {
     GPose o1, o2;
@@ -933,10 +933,10 @@ __device__ __forceinline__ int narrowphase(const CollideParams &P, const DevTemp
     const int c1 = g1.cls, c2 = g2.cls;
     if (c2 == 4) return collide_plane(g1, o1, g2.dims, out);
     if (c2 == 5) {
-        if (c1 == 0) return collide_sphere_hf(T->hf, o1.p, g1.dims[0], out[0]);
-        if (c1 == 1) return collide_box_hf(T->hf, g1, o1, out);
-        if (SAMPLED && c1 == 2) return collide_capsule_hf(T->hf, g1, o1, out);
-        if (SAMPLED && c1 == 3) return collide_cylinder_hf(T->hf, g1, o1, out);
+        if (c1 == 0) return collide_sphere_hf(hfield, o1.p, g1.dims[0], out[0]);
+        if (c1 == 1) return collide_box_hf(hfield, g1, o1, out);
+        if (SAMPLED && c1 == 2) return collide_capsule_hf(hfield, g1, o1, out);
+        if (SAMPLED && c1 == 3) return collide_cylinder_hf(hfield, g1, o1, out);
         return 0;
     }
     geom_pose(P, g2, w, o2);
@@ -1005,11 +1005,30 @@ template <bool SAMPLED> __global__ void __launch_bounds__(CBD) b2p_collide_kerne
     const DevTemplate *__restrict__ T = P.T;
     const int tid = threadIdx.x;
     const int w = blockIdx.x * CBD + tid;
-    if (w >= P.W) return;
     const int Wp = P.Wp;
     const int ng = T->ng, maxc = T->maxc;
+    // the scene template's geoms, body adjacency and heightfield header in shared memory (read warp-uniformly
+    // in every pair test)
+    const DevGeom *s_geoms;
+    const uint32_t *s_connected;
+    const DevHeightfield *s_hf;
+    {
+        uint32_t *sg = (uint32_t *)(saabb + (size_t)ng * 6 * CBD);
+        uint32_t *sc = sg + (size_t)ng * (sizeof(DevGeom) / 4);
+        uint32_t *sh = sc + B2P_MAX_BODIES;
+        sh += ((uintptr_t)sh & 7) ? 1 : 0; // the header holds a pointer
+        const uint32_t *gg = (const uint32_t *)T->geoms, *gc = (const uint32_t *)T->connected, *gh = (const uint32_t *)&T->hf;
+        for (int i = tid; i < ng * (int)(sizeof(DevGeom) / 4); i += CBD) sg[i] = __ldg(gg + i);
+        for (int i = tid; i < B2P_MAX_BODIES; i += CBD) sc[i] = __ldg(gc + i);
+        for (int i = tid; i < (int)(sizeof(DevHeightfield) / 4); i += CBD) sh[i] = __ldg(gh + i);
+        s_geoms = (const DevGeom *)sg;
+        s_connected = sc;
+        s_hf = (const DevHeightfield *)sh;
+        __syncthreads();
+    }
+    if (w >= P.W) return;
     for (int g = 0; g < ng; g++) {
-        const DevGeom &gg = T->geoms[g];
+        const DevGeom &gg = s_geoms[g];
         if (gg.body < 0) continue;
         GPose o;
         geom_pose(P, gg, w, o);
@@ -1023,12 +1042,12 @@ template <bool SAMPLED> __global__ void __launch_bounds__(CBD) b2p_collide_kerne
     }
     int total = 0, npairs = 0;
     for (int i = 0; i < ng; i++) {
-        const DevGeom &gi = T->geoms[i];
+        const DevGeom &gi = s_geoms[i];
         for (int j = i + 1; j < ng; j++) {
-            const DevGeom &gj = T->geoms[j];
+            const DevGeom &gj = s_geoms[j];
             if (gi.body < 0 && gj.body < 0) continue;
             if (gi.body == gj.body) continue;
-            if (gi.body >= 0 && gj.body >= 0 && (T->connected[gi.body] >> gj.body & 1u)) continue;
+            if (gi.body >= 0 && gj.body >= 0 && (s_connected[gi.body] >> gj.body & 1u)) continue;
             bool overlap;
             const bool i_dyn = gi.body >= 0;
             const int d_idx = i_dyn ? i : j;
@@ -1050,7 +1069,7 @@ template <bool SAMPLED> __global__ void __launch_bounds__(CBD) b2p_collide_kerne
                 const float *n = gs.dims;
                 overlap = (dot3(n, c) - (fabsf(n[0]) * e[0] + fabsf(n[1]) * e[1] + fabsf(n[2]) * e[2])) <= n[3];
             } else if (gs.cls == 5) {
-                const DevHeightfield &hf = T->hf;
+                const DevHeightfield &hf = *s_hf;
                 const float xe = hf.x0 + (hf.nx - 1) * hf.dx, ye = hf.y0 + (hf.ny - 1) * hf.dx;
                 overlap = (c[2] - e[2] <= hf.hmax) && c[0] + e[0] >= hf.x0 && c[0] - e[0] <= xe &&
                           c[1] + e[1] >= hf.y0 && c[1] - e[1] <= ye;
@@ -1063,7 +1082,7 @@ template <bool SAMPLED> __global__ void __launch_bounds__(CBD) b2p_collide_kerne
             CPoint pts[MAXPC];
             const DevGeom &g1 = i_dyn ? gi : gj;
             const DevGeom &g2 = i_dyn ? gj : gi;
-            const int n = narrowphase<SAMPLED>(P, T, g1, g2, w, pts);
+            const int n = narrowphase<SAMPLED>(P, *s_hf, g1, g2, w, pts);
             const float mu = fminf(g1.mu, g2.mu), mu2 = fminf(g1.mu2, g2.mu2);
             const float rho = fminf(g1.rho, g2.rho), rho2 = fminf(g1.rho2, g2.rho2), rhoN = fminf(g1.rhoN, g2.rhoN);
             const float serp = fminf(g1.soft_erp, g2.soft_erp), scfm = fmaxf(g1.soft_cfm, g2.soft_cfm);
@@ -1106,7 +1125,8 @@ extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, int sa
     int dev = 0;
     cudaGetDevice(&dev);
     size_t *configured = configured_dev[dev % B2P_MAX_DEVICES];
-    const size_t smem = sizeof(float) * (size_t)(ng > 0 ? ng : 1) * 6 * CBD;
+    const size_t smem = sizeof(float) * (size_t)(ng > 0 ? ng : 1) * 6 * CBD + (size_t)ng * sizeof(DevGeom) +
+                        sizeof(uint32_t) * B2P_MAX_BODIES + sizeof(DevHeightfield) + 16;
     auto kern = sampled ? b2p_collide_kernel<true> : b2p_collide_kernel<false>;
     if (smem > configured[sampled ? 1 : 0]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
