@@ -6,6 +6,7 @@ The reference's criterion is determinism of the "%g" CSV (scripts/reproducable_t
 of that the CSV is compared with the oracle's over a short horizon (fp32 device vs fp64 oracle:
 the gait is chaotic, so the comparison horizon is bounded and the tolerance grows with it).
 """
+import math
 import os
 import subprocess
 
@@ -52,3 +53,15 @@ def test_facade_replicas_agree(cuda_lib, tmp_path):
     one = _run(str(tmp_path / "one.csv"), 0.2, 1)
     many = _run(str(tmp_path / "many.csv"), 0.2, 33)
     assert np.array_equal(one, many)
+
+
+def test_universal_and_ball_joints_through_the_loader(cuda_lib):
+    """The joint types beyond the reference's registered set, created like a MARS host would (plugin loader ->
+    createWorldInstance -> createFrame / createObject / createJoint with ConfigMaps): a two-link arm on a ball and
+    a universal joint swings under gravity, the anchors hold, and the universal's first angle is observable."""
+    exe = os.path.join(ROOT, "mars_ode_physics_b200", "lib", "joint_types_test")
+    assert os.path.exists(exe), "facade test binary missing: run __graft_entry__.build()"
+    out = subprocess.run([exe, "400"], check=True, capture_output=True, text=True).stdout.split()
+    ball_err, len_a_err, len_b_err, angle1, moved = map(float, out)
+    assert ball_err < 5e-3 and len_a_err < 5e-3 and len_b_err < 5e-3
+    assert moved > 0.05 and math.isfinite(angle1)
