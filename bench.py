@@ -229,6 +229,11 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # stdout carries exactly one line (the JSON result of rank 0): anything a library prints there meanwhile
+    # (e.g. NCCL's version banner) goes to stderr instead
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W = args.worlds
@@ -424,7 +429,10 @@ def run_b200(args):
                                     "sample": f"{sample} settled worlds x {nsteps} steps of the same workload, "
                                               f"oracle f64 (CPU restatement of ODE-0.16 quickstep, not libode), "
                                               f"{cores} threads, {dt:.1f} s"}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world_size > 1:
         dist.destroy_process_group()
 
