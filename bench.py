@@ -315,7 +315,7 @@ def run_b200(args):
 
     def e2e_step(k, pending):
         cmd = cmds[k % NB]
-        if cmd_joints == list(range(len(cmd_joints))):
+        if cmd_joints and cmd_joints == list(range(len(cmd_joints))):
             ar.joints_set_param_batch_ptr(param, cmd.data_ptr(), len(cmd_joints))  # one transfer
         else:
             for ji, j in enumerate(cmd_joints):
