@@ -323,3 +323,43 @@ def test_box_stack_config_b(cuda_lib):
     assert err[:, :3].max() < 2e-3 and err[:, 3:7].max() < 5e-3
     z = oc.state_download(nb)[:, 2, :]
     assert np.all(np.diff(z, axis=0) > 0.15)  # still a stack
+
+
+def test_sampled_colliders_against_committed_golden(cuda_lib):
+    """Device contact records of the sample-point colliders vs the committed oracle fixture
+    (tests/golden/sampled_colliders_oracle_f64.npz: 5 pair types x 24 seeded poses)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sampled_colliders_oracle_f64.npz"))
+    pairs = [(capi.GEOM_CAPSULE, (0.05, 0.3), capi.GEOM_BOX, (0.3, 0.2, 0.25)),
+             (capi.GEOM_SPHERE, (0.1,), capi.GEOM_CYLINDER, (0.1, 0.25)),
+             (capi.GEOM_CAPSULE, (0.05, 0.3), capi.GEOM_CYLINDER, (0.1, 0.25)),
+             (capi.GEOM_CYLINDER, (0.1, 0.25), capi.GEOM_BOX, (0.3, 0.2, 0.25)),
+             (capi.GEOM_CYLINDER, (0.1, 0.25), capi.GEOM_CYLINDER, (0.12, 0.2))]
+    total = 0
+    for pi, (ca, da, cb, db) in enumerate(pairs):
+        W = 24
+        ar = Arena(W)
+        _build_pair_scene(ar, ca, da, cb, db)
+        for w in range(W):
+            for body in (0, 1):
+                ar.body_set_position(body, g["poses"][pi, w, body, :3], w)
+                ar.body_set_quaternion(body, g["poses"][pi, w, body, 3:], w)
+        ar.collide()
+        for w in range(W):
+            want = g["records"][pi, w]
+            n_want = int(np.isfinite(want[:, 7]).sum())
+            n_got = ar.contact_count(w)
+            depths = list(want[:n_want, 7])
+            if n_got != n_want:
+                assert min(depths + [ar.contact_get(w, c)[2].depth for c in range(n_got)]) < 2e-5, (pi, w, n_got, n_want)
+                continue
+            for c in range(n_got):
+                b1, b2, d = ar.contact_get(w, c)
+                assert b1 == int(want[c, 0])
+                if abs(d.depth - want[c, 7]) > 2e-5:
+                    assert min(depths) < 2e-5, (pi, w, c, d.depth, want[c, 7])  # borderline candidate set
+                    break
+                assert np.allclose(d.pos[:], want[c, 1:4], atol=5e-5) and np.allclose(d.normal[:], want[c, 4:7], atol=2e-4)
+                total += 1
+        ar.close()
+    assert total > 100

@@ -190,3 +190,27 @@ def test_ball_and_universal_parity(cuda_lib):
     assert np.allclose(fb[ju, :, 5], oc.joint_get_feedback(ju, 5), rtol=5e-3, atol=5e-3)
     obs = ar.joint_obs_download(2)
     assert abs(obs[ju, 0, 3] - ar.joint_get_angle1(ju, 3)) < 1e-5 and abs(obs[ju, 2, 3] - ar.joint_get_angle2(ju, 3)) < 1e-5
+
+
+def test_arm_against_committed_golden(cuda_lib):
+    """Device vs the committed oracle fixture (tests/golden/arm_ball_universal_oracle_f64.npz): row counts per
+    step and RNG state exact, state and universal angles within fp32 tolerance."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "arm_ball_universal_oracle_f64.npz"))
+    W = 6
+    ar = Arena(W)
+    sc = scenes.ball_universal_arm(ar)
+    for w in range(W):
+        ar.body_set_angular_vel(sc["bodies"][1], (0.0, 0.3 * w, 3.0 - 0.5 * w), w)
+    for k in range(300):
+        ar.step(H)
+        if k % 25 == 0 or k == 299:
+            assert [ar.last_num_rows(w) for w in range(W)] == list(g["rows"][k]), k
+    assert [ar.rand_get_seed(w) for w in range(W)] == list(g["seeds"])
+    d = np.abs(ar.state_download(2).astype(np.float64) - g["state"])
+    assert d[:, 0:3].max() < 2e-4 and d[:, 3:7].max() < 5e-4, (d[:, 0:3].max(), d[:, 3:7].max())
+    ju = sc["universal"]
+    ang = np.array([[ar.joint_get_angle1(ju, w), ar.joint_get_angle1_rate(ju, w), ar.joint_get_angle2(ju, w),
+                     ar.joint_get_angle2_rate(ju, w)] for w in range(W)])
+    assert np.abs(ang[:, [0, 2]] - g["angles"][:, [0, 2]]).max() < 5e-4
+    assert np.abs(ang[:, [1, 3]] - g["angles"][:, [1, 3]]).max() < 2e-2
