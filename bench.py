@@ -37,10 +37,11 @@ UNIT = "world-steps/s"
 WORKLOAD = "D: hinge2 rover (5 bodies, 4 hinge2, sphere wheels) on shared 256x256 heightfield, dt=1ms, 20 SOR iters"
 
 
-def build_rover_worlds(be, num_worlds, world_offset=0, torch_free=True):
+def build_rover_worlds(be, num_worlds, world_offset=0, torch_free=True, wheel_shape="sphere"):
     """Config D scene on any backend; per-world placement / wheel speed from splitmix64(0xD ^ id)."""
     from mars_ode_physics_b200 import capi, scenes
-    sc = scenes.rover(be, with_geoms=True)
+    sc = scenes.rover(be, with_geoms=True, wheel_shape=wheel_shape,
+                      max_contacts=8 if wheel_shape == "sphere" else 20)
     heights, x0, y0 = scenes.terrain_heights()
     be.geom_create_heightfield(heights, 0.1, x0, y0,
                                surface={"mu": 1.0, "mu2": 1.0, "soft_erp": 0.2, "soft_cfm": 1e-5})
@@ -111,8 +112,13 @@ def build_quadruped_worlds(be, num_worlds, world_offset=0):
     return sc
 
 
-BUILDERS = {"D": None, "B": build_box_stack_worlds, "C": build_quadruped_worlds}
+def build_rover_cylinder_worlds(be, num_worlds, world_offset=0):
+    return build_rover_worlds(be, num_worlds, world_offset, wheel_shape="cylinder")
+
+
+BUILDERS = {"D": None, "B": build_box_stack_worlds, "C": build_quadruped_worlds, "Dcyl": build_rover_cylinder_worlds}
 WORKLOADS = {
+    "Dcyl": "D with cylinder wheels (r 0.1, width 0.05; up to 4 contacts per wheel) on the shared heightfield",
     "B": "B: 10-box stack on a plane (box-box + box-plane contacts), dt=1ms, 20 SOR iters",
     "C": "C: 12-hinge legged robot (13 bodies), foot spheres on a plane, dt=1ms, 20 SOR iters",
 }
@@ -311,7 +317,7 @@ def run_b200(args):
         c[:] = (torch.from_numpy(sc["vel"])[None, :] + 0.001 * i) if sc["vel"] is not None else 0.0
         cmds.append(c)
     obs = [torch.empty((13, W), dtype=torch.float32).pin_memory() for _ in range(2)]
-    param = (capi.PARAM_VEL | capi.PARAM_GROUP2) if args.workload == "D" else capi.PARAM_VEL
+    param = (capi.PARAM_VEL | capi.PARAM_GROUP2) if args.workload in ("D", "Dcyl") else capi.PARAM_VEL
 
     def e2e_step(k, pending):
         cmd = cmds[k % NB]
@@ -455,7 +461,7 @@ def main():
                     help="Tensor-Memory SOR kernel: warps (x32 worlds) per CTA; 0 = auto")
     ap.add_argument("--reorder", default="random", choices=["random", "none"],
                     help="SOR row reordering: ODE 0.16 default (random) or REORDERING_METHOD__DONT_REORDER")
-    ap.add_argument("--workload", default="D", choices=["B", "C", "D"],
+    ap.add_argument("--workload", default="D", choices=["B", "C", "D", "Dcyl"],
                     help="D (default) is the headline configuration; B and C are extra data points")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -156,7 +156,9 @@ def sphere_plane_contacts(be, bodies, radius, world, mu=0.8, soft_erp=0.2, soft_
 
 # ---------------------------------------------------------------------------------------------
 # config D: wheeled rover, chassis box + 4 wheels on hinge2 joints (axis1 = z steer, axis2 = y drive)
-def rover(be, max_contacts=8, wheel_fmax=5.0, steer_lock=True, with_geoms=False, surface=None):
+def rover(be, max_contacts=8, wheel_fmax=5.0, steer_lock=True, with_geoms=False, surface=None, wheel_shape="sphere"):
+    """Config D rover: chassis box + 4 wheels on hinge2 joints (axis1 = z steer, locked by stops; axis2 = y drive).
+    wheel_shape "sphere" (r 0.1, the bring-up variant SURVEY 8(d) allows) or "cylinder" (r 0.1, width 0.05, axis y)."""
     be.set_max_contacts(max_contacts)
     setup_world(be)
     sc = {"bodies": [], "joints": [], "wheels": [], "wheel_radius": 0.1, "name": "rover"}
@@ -167,7 +169,8 @@ def rover(be, max_contacts=8, wheel_fmax=5.0, steer_lock=True, with_geoms=False,
     for sx in (1.0, -1.0):
         for sy in (1.0, -1.0):
             x, y, z = sx * 0.25, sy * 0.25, z0 - 0.1
-            wheel = add_body(be, 1.0, inertia_sphere(1.0, 0.1), (x, y, z))
+            wheel = add_body(be, 1.0, inertia_sphere(1.0, 0.1) if wheel_shape == "sphere"
+                             else inertia_cylinder(1.0, 0.1, 0.05, axis=1), (x, y, z))
             sc["bodies"].append(wheel)
             sc["wheels"].append(wheel)
             j = be.joint_create(capi.JOINT_HINGE2, chassis, wheel)
@@ -186,7 +189,11 @@ def rover(be, max_contacts=8, wheel_fmax=5.0, steer_lock=True, with_geoms=False,
         s = surface or {"mu": 1.0, "mu2": 1.0, "soft_erp": 0.2, "soft_cfm": 1e-5}
         sc["geoms"] = [be.geom_create(capi.GEOM_BOX, chassis, (0.6, 0.4, 0.15), surface=s)]
         for wbody in sc["wheels"]:
-            sc["geoms"].append(be.geom_create(capi.GEOM_SPHERE, wbody, (0.1,), surface=s))
+            if wheel_shape == "sphere":
+                sc["geoms"].append(be.geom_create(capi.GEOM_SPHERE, wbody, (0.1,), surface=s))
+            else:  # the cylinder's axis (local z) turned onto the wheel axle (y)
+                sc["geoms"].append(be.geom_create(capi.GEOM_CYLINDER, wbody, (0.1, 0.05),
+                                                  lquat=quat_axis_angle((1, 0, 0), math.pi / 2), surface=s))
     return sc
 
 

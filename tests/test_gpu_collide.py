@@ -23,8 +23,9 @@ def _rand_quat(rng):
     return q / np.linalg.norm(q)
 
 
-def _compare_contacts(ar, oc, W, borderline=2e-5):
-    """Returns (#worlds compared exactly, #borderline worlds)."""
+def _compare_contacts(ar, oc, W, borderline=2e-5, depth_atol=2e-5, pos_atol=5e-5, normal_atol=2e-4):
+    """Returns (#worlds compared exactly, #borderline worlds).  The default tolerances are for identical poses;
+    trajectory tests (device and oracle states drift apart by fp32 rounding) pass wider ones."""
     exact = border = 0
     for w in range(W):
         na, no = ar.contact_count(w), oc.contact_count(w)
@@ -41,9 +42,9 @@ def _compare_contacts(ar, oc, W, borderline=2e-5):
             if abs(da.depth - do.depth) > 1e-4 and min(da.depth, do.depth) < borderline:
                 border += 1
                 break
-            assert abs(da.depth - do.depth) < 2e-5, (w, da.depth, do.depth)
-            assert np.allclose(da.pos[:], do.pos[:], atol=5e-5), (w, da.pos[:], do.pos[:])
-            assert np.allclose(da.normal[:], do.normal[:], atol=2e-4), (w, da.normal[:], do.normal[:])
+            assert abs(da.depth - do.depth) < depth_atol, (w, da.depth, do.depth)
+            assert np.allclose(da.pos[:], do.pos[:], atol=pos_atol), (w, da.pos[:], do.pos[:])
+            assert np.allclose(da.normal[:], do.normal[:], atol=normal_atol), (w, da.normal[:], do.normal[:])
             assert da.mode == do.mode
             assert abs(da.mu - do.mu) < 1e-6 and abs(da.soft_cfm - do.soft_cfm) < 1e-9
         else:
@@ -150,13 +151,15 @@ def test_joint_connected_pairs_are_excluded(cuda_lib):
         assert ar.contact_count(w) == oc.contact_count(w) == 2
 
 
-def test_rover_on_heightfield_trajectory(cuda_lib):
-    """Config D scene (hinge2 rover, shared heightfield), device collide + step vs oracle."""
+@pytest.mark.parametrize("wheel_shape", ["sphere", "cylinder"])
+def test_rover_on_heightfield_trajectory(cuda_lib, wheel_shape):
+    """Config D scene (hinge2 rover, shared heightfield), device collide + step vs oracle; with the sphere
+    wheels of the benchmark and with cylinder wheels (sample-point cylinder-heightfield collider)."""
     W = 16
     ar, oc = Arena(W), orc.OracleBatch(W)
     heights, x0, y0 = scenes.terrain_heights()
     for be in (ar, oc):
-        sc = scenes.rover(be, with_geoms=True)
+        sc = scenes.rover(be, with_geoms=True, wheel_shape=wheel_shape, max_contacts=8 if wheel_shape == "sphere" else 20)
         be.geom_create_heightfield(heights, 0.1, x0, y0, surface={"mu": 1.0, "mu2": 1.0, "soft_erp": 0.2, "soft_cfm": 1e-5})
         for w in range(W):
             dx, dy = 3.0 * scenes.uniform01(0xD, w, 1) - 1.5, 3.0 * scenes.uniform01(0xD, w, 2) - 1.5
@@ -178,7 +181,8 @@ def test_rover_on_heightfield_trajectory(cuda_lib):
         if step % 20 == 0:
             for w in range(W):
                 assert ar.collide_get_pairs(w) == oc.collide_get_pairs(w), (step, w)
-            exact, border = _compare_contacts(ar, oc, W, borderline=1e-4)
+            # states have drifted by fp32 rounding (checked at the end): contact geometry within that drift
+            exact, border = _compare_contacts(ar, oc, W, borderline=1e-4, depth_atol=2e-4, pos_atol=5e-4, normal_atol=2e-3)
             mismatch_steps += border
         ar.step(0.001)
         oc.step(0.001)
@@ -187,7 +191,7 @@ def test_rover_on_heightfield_trajectory(cuda_lib):
     err = np.abs(sa - so)
     print("rover/heightfield 400 steps: max pos err", err[:, :3].max(), "quat", err[:, 3:7].max(),
           "lvel", err[:, 7:10].max(), "borderline worlds", mismatch_steps)
-    assert mismatch_steps <= 2
+    assert mismatch_steps <= (2 if wheel_shape == "sphere" else 6)
     assert err[:, :3].max() < 2e-3 and err[:, 3:7].max() < 5e-3
     assert sum(oc.contact_count(w) for w in range(W)) >= W  # wheels are on the ground
 
