@@ -20,7 +20,8 @@
 // This frees shared memory -- and its single 128 B/clk pipe -- for what really needs per-lane dynamic
 // addressing: fch (indexed by body) and lambda (indexed by slot).  With one thread per world there is no
 // cross-lane reduction on the dependent chain, and a warp instruction advances 32 worlds instead of 16.
-// The row of position p+1 is fetched from TMEM while row p is relaxed.
+// Two rows are fetched per tcgen05.ld (x32) right before they are relaxed; the second warp of the scheduler
+// covers the load's latency.
 //
 // Shared memory per CTA (all accesses conflict-free: consecutive lanes = consecutive columns):
 //     fch   float2[(nb+1)*3][TW], lam float[R+2][TW], ord uint8[R][TW]   as in b2p_sor.cu, one column per thread
@@ -52,27 +53,23 @@ __device__ __forceinline__ void tm_store_row(uint32_t taddr, const Row &q)
         "f"(q.j[9]), "f"(q.j[10]), "f"(q.j[11]), "f"(q.rhs), "f"(q.cfm), "f"(q.bound), "r"(q.meta)
         : "memory");
 }
-__device__ __forceinline__ void tm_load_row(uint32_t taddr, Row &q)
+// Two consecutive rows (32 columns) with one instruction and one wait.  tcgen05.ld is asynchronous: the registers
+// are valid only after tcgen05.wait::ld, which is part of the same asm statement so that the compiler cannot move
+// a use in between.  A ld / wait pair costs about 85 cycles of issue time whatever its width (scratch
+// microbenchmark), which is why rows travel in pairs.
+__device__ __forceinline__ void tm_load_2rows(uint32_t taddr, Row &a, Row &b)
 {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-        : "=f"(q.j[0]), "=f"(q.j[1]), "=f"(q.j[2]), "=f"(q.j[3]), "=f"(q.j[4]), "=f"(q.j[5]), "=f"(q.j[6]), "=f"(q.j[7]),
-          "=f"(q.j[8]), "=f"(q.j[9]), "=f"(q.j[10]), "=f"(q.j[11]), "=f"(q.rhs), "=f"(q.cfm), "=f"(q.bound), "=r"(q.meta)
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;\n"
+        : "=f"(a.j[0]), "=f"(a.j[1]), "=f"(a.j[2]), "=f"(a.j[3]), "=f"(a.j[4]), "=f"(a.j[5]), "=f"(a.j[6]), "=f"(a.j[7]),
+          "=f"(a.j[8]), "=f"(a.j[9]), "=f"(a.j[10]), "=f"(a.j[11]), "=f"(a.rhs), "=f"(a.cfm), "=f"(a.bound), "=r"(a.meta),
+          "=f"(b.j[0]), "=f"(b.j[1]), "=f"(b.j[2]), "=f"(b.j[3]), "=f"(b.j[4]), "=f"(b.j[5]), "=f"(b.j[6]), "=f"(b.j[7]),
+          "=f"(b.j[8]), "=f"(b.j[9]), "=f"(b.j[10]), "=f"(b.j[11]), "=f"(b.rhs), "=f"(b.cfm), "=f"(b.bound), "=r"(b.meta)
         : "r"(taddr)
         : "memory");
 }
-// tcgen05.ld is asynchronous: the registers of `q` are valid only after this wait.  They are passed through
-// the asm statement so that the compiler cannot move a use above it.
-__device__ __forceinline__ void tm_wait_row(Row &q)
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-                 : "+f"(q.j[0]), "+f"(q.j[1]), "+f"(q.j[2]), "+f"(q.j[3]), "+f"(q.j[4]), "+f"(q.j[5]), "+f"(q.j[6]),
-                   "+f"(q.j[7]), "+f"(q.j[8]), "+f"(q.j[9]), "+f"(q.j[10]), "+f"(q.j[11]), "+f"(q.rhs), "+f"(q.cfm),
-                   "+f"(q.bound), "+r"(q.meta)
-                 :
-                 : "memory");
-}
-
 // NW warps per CTA (4 or 8): NW*32 worlds per SM.  With 8 warps two warps share a TMEM lane quadrant and split its
 // columns, so a world has 16 instead of 32 rows in TMEM but every scheduler has two warps to alternate between.
 template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_tmem_kernel(const StepParams P)
@@ -314,20 +311,14 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
                 for (int k = g; k < g + 4 && k < KR; k++) relax(rr[k]);
             }
         }
-        // positions in Tensor Memory: row p+1 is in flight while row p is relaxed
+        // positions in Tensor Memory, two per load
         if (nt > 0) {
             Row qa, qb;
-            tm_load_row(tbase, qa);
 #pragma unroll 1
             for (int p = 0; p < nt; p += 2) {
-                tm_wait_row(qa);
-                if (p + 1 < nt) tm_load_row(tbase + (uint32_t)((p + 1) * 16), qb);
+                tm_load_2rows(tbase + (uint32_t)(p * 16), qa, qb);
                 relax(qa);
-                if (p + 1 < nt) {
-                    tm_wait_row(qb);
-                    if (p + 2 < nt) tm_load_row(tbase + (uint32_t)((p + 2) * 16), qa);
-                    relax(qb);
-                }
+                if (p + 1 < nt) relax(qb);
             }
         }
         // overflow positions in shared memory, then the ones that did not fit on chip (read in place from L2)
