@@ -40,7 +40,7 @@ def build(strict=True, force=False, verbose=False):
     deps = srcs + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
     targets = [("libmars_ode_b200.so", [])]
     if strict:
-        targets.append(("libmars_ode_b200_strict.so", ["-fmad=false"]))
+        targets.append(("libmars_ode_b200_strict.so", ["-fmad=false", "-DB2P_STRICT"]))
     built = []
     for name, extra in targets:
         out = os.path.join(LIBDIR, name)

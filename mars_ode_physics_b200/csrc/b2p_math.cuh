@@ -176,6 +176,43 @@ __device__ __forceinline__ void stg256(void *p, const float4 &lo, const float4 &
 }
 #endif
 
+#ifdef __CUDACC__
+// Pinned fused multiply-add for the SOR row-iteration: both SOR kernels must round identically (they are
+// compared bitwise), and the B2P_STRICT build (-fmad=false, compared with the float oracle) must not fuse.
+#ifdef B2P_STRICT
+__device__ __forceinline__ float sor_fma(float a, float b, float c) { return __fadd_rn(__fmul_rn(a, b), c); }
+#else
+__device__ __forceinline__ float sor_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#endif
+// packed pairs (sm_100 FFMA2 / FMUL2): (a.x*b.x + c.x, a.y*b.y + c.y) in one instruction
+__device__ __forceinline__ float2 sor_fma2(float2 a, float2 b, float2 c)
+{
+#ifdef B2P_STRICT
+    return make_float2(sor_fma(a.x, b.x, c.x), sor_fma(a.y, b.y, c.y));
+#else
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mov.b64 rc, {%6,%7};\n"
+        " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0,%1}, rd; }"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+#endif
+}
+__device__ __forceinline__ float2 sor_mul2(float2 a, float2 b)
+{
+#ifdef B2P_STRICT
+    return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+#else
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mul.rn.f32x2 rd, ra, rb;\n"
+        " mov.b64 {%0,%1}, rd; }"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+#endif
+}
+#endif
+
 // ODE dPlaneSpace
 B2P_HD void plane_space(const float *n, float *p, float *q)
 {

@@ -140,7 +140,11 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
         float2 *pf = fcL + b * (3 * WL);
         float2 fa = pf[0], fb = pf[WL], fc = pf[2 * WL];
         const float lam_old = *lp, lam_n = *ln;
-        const float d = (q.j0 * fa.x + q.j1 * fa.y + q.j2 * fb.x) + (q.j3 * fb.y + q.j4 * fc.x + q.j5 * fc.y);
+        // (even terms) + (odd terms), each a chain of fused multiply-adds: the association b2p_sor_tmem.cu gets
+        // from its packed FFMA2 chains
+        const float de = sor_fma(q.j4, fc.x, sor_fma(q.j2, fb.x, __fmul_rn(q.j0, fa.x)));
+        const float dod = sor_fma(q.j5, fc.y, sor_fma(q.j3, fb.y, __fmul_rn(q.j1, fa.y)));
+        const float d = de + dod;
         const float dot = d + __shfl_xor_sync(0xffffffffu, d, 24);
         float delta = (q.rhs - lam_old * q.cfm) - dot;
         const float bnd = fabsf(q.bound * lam_n);
@@ -150,8 +154,8 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
         const float nl = fminf(fmaxf(un, lo_act), hi_act);
         delta = (nl == un) ? delta : nl - lam_old;
         *lp = nl;
-        fa.x += delta * q.j0, fa.y += delta * q.j1, fb.x += delta * q.j2;
-        fb.y += delta * q.j3, fc.x += delta * q.j4, fc.y += delta * q.j5;
+        fa.x = sor_fma(delta, q.j0, fa.x), fa.y = sor_fma(delta, q.j1, fa.y), fb.x = sor_fma(delta, q.j2, fb.x);
+        fb.y = sor_fma(delta, q.j3, fb.y), fc.x = sor_fma(delta, q.j4, fc.x), fc.y = sor_fma(delta, q.j5, fc.y);
         pf[0] = fa;
         pf[WL] = fb;
         pf[2 * WL] = fc;

@@ -192,9 +192,12 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
         float2 a0 = pa[0], a1 = pa[TW], a2 = pa[2 * TW];
         float2 b0 = pb[0], b1 = pb[TW], b2 = pb[2 * TW];
         const float lam_old = *lp, lam_n = *ln;
-        const float dA = (q.j[0] * a0.x + q.j[1] * a0.y + q.j[2] * a1.x) + (q.j[3] * a1.y + q.j[4] * a2.x + q.j[5] * a2.y);
-        const float dB = (q.j[6] * b0.x + q.j[7] * b0.y + q.j[8] * b1.x) + (q.j[9] * b1.y + q.j[10] * b2.x + q.j[11] * b2.y);
-        const float dot = dA + dB;
+        // J.fch per side as (even terms) + (odd terms), each a chain of fused multiply-adds: two packed chains here,
+        // the same scalar chains in b2p_sor.cu
+        float2 pA = sor_mul2(make_float2(q.j[0], q.j[1]), a0), pB = sor_mul2(make_float2(q.j[6], q.j[7]), b0);
+        pA = sor_fma2(make_float2(q.j[2], q.j[3]), a1, pA), pB = sor_fma2(make_float2(q.j[8], q.j[9]), b1, pB);
+        pA = sor_fma2(make_float2(q.j[4], q.j[5]), a2, pA), pB = sor_fma2(make_float2(q.j[10], q.j[11]), b2, pB);
+        const float dot = (pA.x + pA.y) + (pB.x + pB.y);
         float delta = (q.rhs - lam_old * q.cfm) - dot;
         const float bnd = fabsf(q.bound * lam_n);
         const float hi_act = (mt & 0x80000000u) ? 0.f : bnd;
@@ -203,10 +206,10 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
         const float nl = fminf(fmaxf(un, lo_act), hi_act);
         delta = (nl == un) ? delta : nl - lam_old;
         *lp = nl;
-        a0.x += delta * q.j[0], a0.y += delta * q.j[1], a1.x += delta * q.j[2];
-        a1.y += delta * q.j[3], a2.x += delta * q.j[4], a2.y += delta * q.j[5];
-        b0.x += delta * q.j[6], b0.y += delta * q.j[7], b1.x += delta * q.j[8];
-        b1.y += delta * q.j[9], b2.x += delta * q.j[10], b2.y += delta * q.j[11];
+        const float2 dd = make_float2(delta, delta);
+        a0 = sor_fma2(dd, make_float2(q.j[0], q.j[1]), a0), a1 = sor_fma2(dd, make_float2(q.j[2], q.j[3]), a1);
+        a2 = sor_fma2(dd, make_float2(q.j[4], q.j[5]), a2), b0 = sor_fma2(dd, make_float2(q.j[6], q.j[7]), b0);
+        b1 = sor_fma2(dd, make_float2(q.j[8], q.j[9]), b1), b2 = sor_fma2(dd, make_float2(q.j[10], q.j[11]), b2);
         pa[0] = a0, pa[TW] = a1, pa[2 * TW] = a2;
         pb[0] = b0, pb[TW] = b1, pb[2 * TW] = b2;
     };
