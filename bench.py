@@ -127,9 +127,9 @@ WORKLOADS = {
 class ClockSampler(threading.Thread):
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_indices):
         super().__init__(daemon=True)
-        self.gpu = gpu_index
+        self.gpus = ",".join(str(g) for g in gpu_indices)  # one nvidia-smi call covers all GPUs of the job
         self.samples = []
         self.stop_flag = threading.Event()
 
@@ -139,11 +139,12 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_power_cap")
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                out = subprocess.run(["nvidia-smi", "-i", self.gpus, f"--query-gpu={q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                parts = [p.strip() for p in out.stdout.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                for line in out.stdout.strip().splitlines():
+                    parts = [p.strip() for p in line.split(",")]
+                    if len(parts) >= 7:
+                        self.samples.append(parts)
             except Exception:
                 pass
             self.stop_flag.wait(0.15)
@@ -275,27 +276,36 @@ def run_b200(args):
         ar.collide()
         ar.step(H)
     K = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     launches0 = ar.kernel_launch_count()
-    sampler = ClockSampler(local_rank)
+    # rank 0 samples the clocks of every GPU of the job (the other ranks spawn nothing: eight nvidia-smi loops
+    # next to eight launch threads cost host time the launches need)
+    sampler = ClockSampler(range(world_size) if world_size > 1 else [local_rank])
     barrier()
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     t_wall0 = time.perf_counter()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record(stream)
-    for k in range(K):
-        ev[k][0].record(stream)
+    for k in range(K):  # the timed region: nothing but the product calls
         ar.collide()
-        ev[k][1].record(stream)
         ar.step(H)
-        ev[k][2].record(stream)
     end.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     ms = start.elapsed_time(end)
     launches = ar.kernel_launch_count() - launches0
-    collide_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
-    step_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    # collide / step split: a separate pass with events around the two calls
+    KE = min(K, 50)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(KE)]
+    for k in range(KE):
+        ev[k][0].record(stream)
+        ar.collide()
+        ev[k][1].record(stream)
+        ar.step(H)
+        ev[k][2].record(stream)
+    torch.cuda.synchronize()
+    collide_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / KE
+    step_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / KE
     # per-kernel durations of the step (CUDA events on the arena's stream between its three launches;
     # a separate pass because every step then synchronises)
     ar.debug_kernel_times(True)
@@ -350,7 +360,8 @@ def run_b200(args):
     barrier()
     t_e2e = time.perf_counter() - t_e2e0
     sampler.stop_flag.set()
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
     # the last D2H ends on the copy stream: take the larger of the stream time and the host wall clock
     ms_e2e = max(e0.elapsed_time(e1), t_e2e * 1e3)
     assert np.isfinite(obs[0].numpy()).all() and np.isfinite(obs[1].numpy()).all(), "non-finite chassis state"
