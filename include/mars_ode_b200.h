@@ -129,8 +129,10 @@ int b2p_arena_set_stream(b2p_arena *a, void *cuda_stream);
 /* capacity knobs; must be called before the first step */
 int b2p_arena_set_max_contacts(b2p_arena *a, int max_contacts_per_world);
 int b2p_arena_enable_rolling_friction(b2p_arena *a, int on);
-/* tuning of the SOR kernel's on-chip row storage: sweep positions per world kept in shared memory
- * (0 = automatic: the longest world seen so far) and in registers (multiple of 4 up to 20; < 0 = automatic) */
+/* tuning of the SOR kernels' on-chip row storage (0 / < 0 = automatic).  resident rows: paired-lane kernel = sweep
+ * positions per world kept in shared memory (automatic: the longest world seen so far); Tensor-Memory kernel =
+ * units of its shared-memory overflow pool (one unit = one sweep position of one warp's 32 worlds, 2 KB).
+ * register rows: sweep positions per world kept in registers (multiple of 4; up to 20 paired-lane, up to 8 TMEM) */
 int b2p_arena_set_resident_rows(b2p_arena *a, int n);
 int b2p_arena_set_register_rows(b2p_arena *a, int n);
 /* which SOR-LCP kernel a step uses: B2P_SOR_AUTO picks the Tensor-Memory kernel (one thread per world, rows in
