@@ -124,39 +124,105 @@ WORKLOADS = {
 }
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region.  ONE long-running `nvidia-smi -lms 100`
+    process started well before the timed region (no fork, no Python thread and no GIL traffic while the launch
+    loop is being timed); its time-stamped lines are parsed afterwards and cut to the timed windows."""
+
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_indices):
-        super().__init__(daemon=True)
-        self.gpus = ",".join(str(g) for g in gpu_indices)  # one nvidia-smi call covers all GPUs of the job
+        self.gpus = ",".join(str(g) for g in gpu_indices)  # one nvidia-smi process covers all GPUs of the job
+        self.proc, self.out = None, None
+        self.window = None  # (t0, t1) time.time() bounds; samples outside are dropped when any lie inside
         self.samples = []
-        self.stop_flag = threading.Event()
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", self.gpus, f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                for line in out.stdout.strip().splitlines():
-                    parts = [p.strip() for p in line.split(",")]
-                    if len(parts) >= 7:
-                        self.samples.append(parts)
-            except Exception:
-                pass
-            self.stop_flag.wait(0.15)
+    def start(self):
+        import tempfile
+        try:
+            self.out = tempfile.TemporaryFile(mode="w+")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.gpus, f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.out,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            import datetime
+            self.out.seek(0)
+            for line in self.out.read().strip().splitlines():
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 8:
+                    continue
+                try:
+                    ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    float(parts[1])
+                except Exception:
+                    continue
+                self.samples.append(parts[1:] + [ts])
+        except Exception:
+            pass
+        self.proc = None
 
     def summary(self):
-        if not self.samples:
+        samples = self.samples
+        if self.window is not None:
+            inside = [x for x in samples if self.window[0] - 0.05 <= x[-1] <= self.window[1] + 0.05]
+            samples = inside or samples
+        if not samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(s[0]) for s in self.samples)
+        sm = sorted(float(x[0]) for x in samples)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples), "power_w_max": max(float(s[2]) for s in self.samples)}
+        reasons = [n for i, n in enumerate(names) if any(x[3 + i].lower().startswith("active") for x in samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(samples[0][1]), "reasons": reasons,
+                "samples": len(samples), "power_w_max": max(float(x[2]) for x in samples)}
+
+
+def pin_to_gpu_numa_node(local_rank, world_size):
+    """Keep this rank's launch thread on the cores next to its GPU (NUMA node of the GPU's PCI device, shared
+    evenly between the ranks on that node); falls back to an even split of the allowed cores."""
+    try:
+        import torch
+        allowed = sorted(os.sched_getaffinity(0))
+        cores = None
+        try:
+            bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+            dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+            dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+            path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+            node = int(open(path).read().strip())
+            if node >= 0:
+                txt = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+                node_cores = []
+                for part in txt.split(","):
+                    lo, _, hi = part.partition("-")
+                    node_cores += list(range(int(lo), int(hi or lo) + 1))
+                node_cores = [c for c in node_cores if c in allowed]
+                # ranks sharing the node: assume GPUs are spread evenly over the nodes in index order
+                nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+                per_node = max(1, (world_size + nodes - 1) // nodes)
+                k = local_rank % per_node
+                chunk = max(1, len(node_cores) // per_node)
+                cores = node_cores[k * chunk:(k + 1) * chunk] or node_cores
+        except Exception:
+            cores = None
+        if not cores:
+            chunk = max(1, len(allowed) // max(1, world_size))
+            cores = allowed[local_rank * chunk:(local_rank + 1) * chunk] or allowed
+        os.sched_setaffinity(0, cores)
+        return len(cores)
+    except Exception:
+        return 0
 
 
 class CpuBaseline:
@@ -236,6 +302,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    pinned_cores = pin_to_gpu_numa_node(local_rank, world_size) if world_size > 1 else 0
     # stdout carries exactly one line (the JSON result of rank 0): anything a library prints there meanwhile
     # (e.g. NCCL's version banner) goes to stderr instead
     sys.stdout.flush()
@@ -268,27 +335,27 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident loop ----------------
-    for _ in range(SETTLE_STEPS):
-        ar.collide()
-        ar.step(H)
-    ar.sync()
-    for _ in range(max(args.warmup, 3)):
-        ar.collide()
-        ar.step(H)
-    K = args.steps
-    launches0 = ar.kernel_launch_count()
     # rank 0 samples the clocks of every GPU of the job (the other ranks spawn nothing: eight nvidia-smi loops
-    # next to eight launch threads cost host time the launches need)
+    # next to eight launch threads cost host time the launches need).  The sampler runs from before the settle
+    # phase, so that no process is forked at the start of the timed window; only samples inside the timed windows
+    # are reported.
     sampler = ClockSampler(range(world_size) if world_size > 1 else [local_rank])
-    barrier()
     if rank == 0:
         sampler.start()
+    for _ in range(SETTLE_STEPS):
+        ar.collide_step(H)
+    ar.sync()
+    for _ in range(max(args.warmup, 3)):
+        ar.collide_step(H)
+    K = args.steps
+    launches0 = ar.kernel_launch_count()
+    barrier()
     t_wall0 = time.perf_counter()
+    t_epoch0 = time.time()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record(stream)
-    for k in range(K):  # the timed region: nothing but the product calls
-        ar.collide()
-        ar.step(H)
+    for k in range(K):  # the timed region: nothing but the product call (one CUDA graph launch: 4 kernels)
+        ar.collide_step(H)
     end.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -327,6 +394,7 @@ def run_b200(args):
         c[:] = (torch.from_numpy(sc["vel"])[None, :] + 0.001 * i) if sc["vel"] is not None else 0.0
         cmds.append(c)
     obs = [torch.empty((13, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+    jobs = [torch.empty((max(nj, 1), 4, W), dtype=torch.float32).pin_memory() for _ in range(2)]
     param = (capi.PARAM_VEL | capi.PARAM_GROUP2) if args.workload in ("D", "Dcyl") else capi.PARAM_VEL
 
     def e2e_step(k, pending):
@@ -336,9 +404,9 @@ def run_b200(args):
         else:
             for ji, j in enumerate(cmd_joints):
                 ar.joint_set_param_batch_ptr(j, param, cmd[ji].data_ptr())
-        ar.collide()
-        ar.step(H)
-        t = ar.body_get_state_batch_begin(sc["chassis"], obs[k & 1].data_ptr())
+        ar.collide_step(H)
+        # observation: chassis state + angle / rate of every joint (what a controller reads each tick)
+        t = ar.observe_begin(sc["chassis"], obs[k & 1].data_ptr(), jobs[k & 1].data_ptr() if nj else None)
         if pending is not None:
             ar.io_wait(pending)  # the observation of the previous step is complete: the caller may read it
         return t
@@ -359,12 +427,13 @@ def run_b200(args):
     e1.record(stream)
     barrier()
     t_e2e = time.perf_counter() - t_e2e0
-    sampler.stop_flag.set()
+    sampler.window = (t_epoch0, time.time())  # device-resident loop .. end of the end-to-end loop
     if rank == 0:
-        sampler.join(timeout=2)
+        sampler.stop()
     # the last D2H ends on the copy stream: take the larger of the stream time and the host wall clock
     ms_e2e = max(e0.elapsed_time(e1), t_e2e * 1e3)
     assert np.isfinite(obs[0].numpy()).all() and np.isfinite(obs[1].numpy()).all(), "non-finite chassis state"
+    assert np.isfinite(jobs[0].numpy()).all() and np.isfinite(jobs[1].numpy()).all(), "non-finite joint observation"
 
     # ---------------- reduce over ranks (max time) ----------------
     t = torch.tensor([ms, ms_e2e, step_ms, collide_ms, asm_ms, sor_ms, int_ms], dtype=torch.float64, device="cuda")
@@ -399,6 +468,12 @@ def run_b200(args):
             per_kernel_traffic = {k: v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in tj.get("kernels", {}).items()}
         except Exception:
             traffic = None
+    clocks = sampler.summary() if rank == 0 else {}
+    # FP32 side of the roofline (SURVEY 8d asks for it beside the HBM figure): 27 FMA per row-iteration against
+    # 148 SMs x 128 FP32 lanes at the SM clock the run held
+    sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    fma_peak = 148 * 128 * sm_mhz * 1e6
+    row_it_s = mean_rows * 20 * W / (sor_ms * 1e-3) if sor_ms > 0 else 0.0
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": K,
@@ -409,11 +484,16 @@ def run_b200(args):
                        "sharding": f"worlds/{world_size} GPUs, no collective on the step path",
                        "l2": "per-step working set (row scratch) > L2; no flush needed",
                        "settle_steps": SETTLE_STEPS, "row_reordering": args.reorder,
+                       "launch": "one CUDA graph (collide + assemble + SOR + integrate) per step",
+                       "host_cores_pinned": pinned_cores,
+                       "collision_semantics": "repo-defined (oracle/orc_collide.c), not ODE's dCollide: one contact "
+                                              "per sphere-heightfield pair, <= 4 deepest vertices per box-plane pair",
                        "mean_rows_per_world": mean_rows,
                        "kernel_ms": {"collide": collide_ms, "step": step_ms, "assemble": asm_ms, "sor": sor_ms,
                                      "integrate": int_ms}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(len(cmd_joints) * W * 4),
-                    "d2h_bytes_per_step": int(13 * W * 4), "ms_per_step": ms_e2e / K,
+                    "d2h_bytes_per_step": int((13 + 4 * nj) * W * 4), "ms_per_step": ms_e2e / K,
+                    "observation": "chassis state (13 floats) + angle1 rate1 angle2 rate2 of every joint, per world",
                     "mode": "pipelined control loop, depth 2: on a copy stream the D2H of step k overlaps step k+1 and "
                             "the H2D of step k+1's commands follows step k's assemble kernel"},
             "gpu_launches": launches,
@@ -427,7 +507,9 @@ def run_b200(args):
                                         "io_gbs": sor_bytes * W / (sor_ms * 1e-3) / 1e9 if sor_ms > 0 else None,
                                         "measured_dram_gbs": (per_kernel_traffic["sor"] / (sor_ms * 1e-3) / 1e9
                                                               if "sor" in per_kernel_traffic and sor_ms > 0 else None),
-                                        "row_iterations_per_s": mean_rows * 20 * W / (sor_ms * 1e-3) if sor_ms > 0 else None,
+                                        "row_iterations_per_s": row_it_s or None,
+                                        "fp32_fma_frac": 27.0 * row_it_s / fma_peak if row_it_s else None,
+                                        "fp32_fma_peak": f"148 SMs x 128 lanes x {sm_mhz:.0f} MHz",
                                         "bound": "on-chip: dependent smem round trip + FP32 issue per row-iteration "
                                                  "(DESIGN.md section 4); its HBM traffic is one pass over the rows"},
                          "measured_dram_gbs": {k: (per_kernel_traffic[k] / (ms_k * 1e-3) / 1e9)
@@ -435,7 +517,7 @@ def run_b200(args):
                                                                ("integrate", int_ms), ("collide", collide_ms))
                                                if k in per_kernel_traffic and ms_k > 0},
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
-            "clocks": sampler.summary(),
+            "clocks": clocks,
             "wall_s": t_wall,
         }
         if not args.no_cpu_baseline and world_size == 1 and args.workload == "D":

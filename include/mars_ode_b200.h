@@ -146,6 +146,16 @@ int b2p_arena_sor_kernel_used(const b2p_arena *a);
 /* Tensor-Memory kernel: warps (x 32 worlds) per CTA, 4 or 8; 0 = automatic */
 int b2p_arena_set_sor_warps(b2p_arena *a, int warps);
 
+/* replay collide + step from a CUDA graph when their parameters did not change since the previous call
+ * (default on; one host call per tick instead of four launches) */
+int b2p_arena_set_graph_launch(b2p_arena *a, int on);
+/* What WorldPhysics::stepTheWorld does after the ODE call (src/WorldPhysics.cpp:372-397) is computed on the device
+ * for every world.  Flags select the telemetry arrays; damping (b2p_body_set_damping) and joint friction
+ * (b2p_joint_set_friction_coefficient) act on the state and are always applied.  Default: both. */
+#define B2P_POST_JOINT_UPDATE 1 /* Joint::update: motor torque, axis torque, joint load (Joint.cpp:859-1019) */
+#define B2P_POST_FRAME_UPDATE 2 /* Frame::update accelerations + computeContactForce (Frame.cpp:899-921,159-171) */
+int b2p_arena_set_post_step_outputs(b2p_arena *a, int flags);
+
 int b2p_world_set_gravity(b2p_arena *a, double x, double y, double z);      /* dWorldSetGravity :194 */
 int b2p_world_set_cfm(b2p_arena *a, double cfm);                            /* dWorldSetCFM :195 */
 int b2p_world_set_erp(b2p_arena *a, double erp);                            /* dWorldSetERP :196 */
@@ -180,6 +190,16 @@ int b2p_body_get_linear_vel(b2p_arena *a, int body, int world, double out[3]);
 int b2p_body_get_angular_vel(b2p_arena *a, int body, int world, double out[3]);
 int b2p_body_get_force(b2p_arena *a, int body, int world, double out[3]);
 int b2p_body_get_torque(b2p_arena *a, int body, int world, double out[3]);
+/* Frame's linearDamping / angularDamping (src/objects/Frame.cpp:55-58): after every step the body's velocity is
+ * multiplied by the factor if it is < 1 (Frame::update :922-941).  Per template, all worlds. */
+int b2p_body_set_damping(b2p_arena *a, int body, double linear, double angular);
+int b2p_body_get_damping(b2p_arena *a, int body, double *linear, double *angular);
+/* Frame::update / computeContactForce results of the last step (Frame.cpp:899-921,159-171) */
+int b2p_body_get_acceleration(b2p_arena *a, int body, int world, double lin[3], double ang[3]);
+int b2p_body_get_contact_force(b2p_arena *a, int body, int world, double out[3]);
+/* all bodies and worlds: float[num_bodies][15][num_worlds] = last_l_vel3 last_a_vel3 l_acc3 a_acc3 contact_force3 */
+int b2p_body_post_download(b2p_arena *a, float *host);
+void *b2p_device_body_post(b2p_arena *a);   /* [nb*15][Wp] */
 /* 13 values: pos3, quat4 (w,x,y,z), lvel3, avel3 */
 int b2p_body_get_state(b2p_arena *a, int body, int world, double out[13]);
 int b2p_body_set_state(b2p_arena *a, int body, int world, const double in[13]);
@@ -197,6 +217,9 @@ int b2p_joint_obs_download(b2p_arena *a, float *host_obs);
  * overlaps the next step; returns a ticket (0 or 1, two transfers may be in flight), b2p_io_wait(ticket)
  * blocks until host_out is complete */
 int b2p_body_get_state_batch_begin(b2p_arena *a, int body, float *host_out);
+/* the same with the joint observations of all joints in the same transfer: host_joint_obs = float[num_joints][4]
+ * [num_worlds] (angle1 rate1 angle2 rate2) or NULL */
+int b2p_observe_begin(b2p_arena *a, int body, float *host_out, float *host_joint_obs);
 int b2p_io_wait(b2p_arena *a, int ticket);
 /* device pointers (float, layout [field][padded_worlds]) for zero-copy consumers */
 int b2p_padded_worlds(const b2p_arena *a);
@@ -234,6 +257,14 @@ int b2p_joint_add_torque(b2p_arena *a, int joint, int world, double t);         
 /* dJointFeedback incl. the patched `lambda`: f1 t1 f2 t2 lambda = 13 doubles (Joint.cpp:268,900) */
 int b2p_joint_get_feedback(b2p_arena *a, int joint, int world, double out[13]);
 int b2p_joint_get_num_rows(b2p_arena *a, int joint, int world, int *rows);
+/* Joint's frictionCoefficient (src/joints/Joint.cpp:43,47-52): when > 0, Joint::applyJointFriction (:1031-1063) adds
+ * its force / torque to both bodies after every step, for the next one.  Per template, all worlds. */
+int b2p_joint_set_friction_coefficient(b2p_arena *a, int joint, double k);
+int b2p_joint_get_friction_coefficient(b2p_arena *a, int joint, double *k);
+/* Joint::update results of the last step (Joint.cpp:859-1019): motor_torque, axis1_torque[3], joint_load[3] */
+int b2p_joint_get_update(b2p_arena *a, int joint, int world, double out[7]);
+int b2p_joint_update_download(b2p_arena *a, float *host); /* float[num_joints][7][num_worlds] */
+void *b2p_device_joint_update(b2p_arena *a);              /* [nj*7][Wp] */
 int b2p_are_connected_excluding_contacts(b2p_arena *a, int body1, int body2);    /* dAreConnectedExcluding :461 */
 
 /* ---- host-injected contacts (dJointCreateContact: src/WorldPhysics.cpp:458-468) ---- */
@@ -252,6 +283,13 @@ int b2p_geom_create_heightfield(b2p_arena *a, const float *heights, int nx, int 
                                 double x0, double y0, const b2p_surface *s);
 /* run broadphase + narrowphase on the device, replacing the contact stream of every world */
 int b2p_collide(b2p_arena *a);
+/* b2p_collide + b2p_step in one call (one CUDA graph launch once the parameters are stable) */
+int b2p_collide_step(b2p_arena *a, double step_size);
+/* contacts the narrowphase found beyond max_contacts_per_world (dropped in pair order), summed over all worlds and
+ * all b2p_collide calls so far: 0 means no stream was ever truncated */
+int b2p_contacts_dropped(b2p_arena *a, long long *count);
+/* debug output: record the broadphase pair list during b2p_collide (off by default) */
+int b2p_collide_record_pairs(b2p_arena *a, int on);
 /* broadphase pair list of one world, sorted by (min geom, max geom); returns pair count */
 int b2p_collide_get_pairs(b2p_arena *a, int world, int *pairs, int max_pairs);
 
@@ -264,6 +302,9 @@ int b2p_kernel_launch_count(const b2p_arena *a); /* kernels launched by this are
 /* diagnostics: per-kernel CUDA-event timing of b2p_step (enable resets; every step then synchronises);
  * out[0..2] = mean milliseconds of the assemble / SOR / integrate kernels, out[3] = steps accumulated. */
 int b2p_debug_kernel_times(b2p_arena *a, int enable, double out[4]);
+/* LCP residual of the last step's solve, one value per world: max over rows of the projected
+ * |J invM J^T lambda + cfm lambda - rhs| (the oracle's orc_world_last_residual) */
+int b2p_debug_lcp_residual(b2p_arena *a, float *host_out);
 /* algorithmic bytes one step of one world moves */
 double b2p_algorithmic_bytes_per_world_step(const b2p_arena *a);
 

@@ -373,3 +373,72 @@ class Arena:
 
     def padded_worlds(self):
         return self.lib.b2p_padded_worlds(self.h)
+
+    # -- round 2: graph launch, post-step outputs, diagnostics ------------------------------------
+    def set_graph_launch(self, on=True):
+        self._check(self.lib.b2p_arena_set_graph_launch(self.h, int(on)))
+
+    def set_post_step_outputs(self, flags):
+        self._check(self.lib.b2p_arena_set_post_step_outputs(self.h, int(flags)))
+
+    def collide_step(self, h):
+        """collide() + step(h) as one call (one CUDA graph launch once the parameters are stable)"""
+        self._check(self.lib.b2p_collide_step(self.h, float(h)))
+
+    def collide_record_pairs(self, on=True):
+        self._check(self.lib.b2p_collide_record_pairs(self.h, int(on)))
+
+    def contacts_dropped(self):
+        v = C.c_longlong()
+        self._check(self.lib.b2p_contacts_dropped(self.h, C.byref(v)))
+        return v.value
+
+    def body_set_damping(self, b, linear, angular):
+        self._check(self.lib.b2p_body_set_damping(self.h, b, float(linear), float(angular)))
+
+    def body_get_damping(self, b):
+        l, a = C.c_double(), C.c_double()
+        self._check(self.lib.b2p_body_get_damping(self.h, b, C.byref(l), C.byref(a)))
+        return l.value, a.value
+
+    def body_get_acceleration(self, b, world=0):
+        l, a = self._out(3), self._out(3)
+        self._check(self.lib.b2p_body_get_acceleration(self.h, b, world, l, a))
+        return np.array(l[:], dtype=float), np.array(a[:], dtype=float)
+
+    def body_get_contact_force(self, b, world=0):
+        return self._get(self.lib.b2p_body_get_contact_force, 3, b, world)
+
+    def body_post_download(self, num_bodies):
+        """float[num_bodies][15][num_worlds]: last_l_vel3 last_a_vel3 l_acc3 a_acc3 contact_force3"""
+        out = np.empty((num_bodies, 15, self.num_worlds), dtype=np.float32)
+        self._check(self.lib.b2p_body_post_download(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def joint_set_friction_coefficient(self, j, k):
+        self._check(self.lib.b2p_joint_set_friction_coefficient(self.h, j, float(k)))
+
+    def joint_get_friction_coefficient(self, j):
+        v = C.c_double()
+        self._check(self.lib.b2p_joint_get_friction_coefficient(self.h, j, C.byref(v)))
+        return v.value
+
+    def joint_get_update(self, j, world=0):
+        """motor_torque, axis1_torque[3], joint_load[3] of the last step (Joint::update)"""
+        return self._get(self.lib.b2p_joint_get_update, 7, j, world)
+
+    def joint_update_download(self, num_joints):
+        out = np.empty((num_joints, 7, self.num_worlds), dtype=np.float32)
+        self._check(self.lib.b2p_joint_update_download(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def observe_begin(self, b, host_body_ptr, host_jobs_ptr=None):
+        """Pipelined D2H of body b's state [13][W] and (optionally) all joint observations [nj][4][W]."""
+        return self._check(self.lib.b2p_observe_begin(self.h, b, C.c_void_p(host_body_ptr),
+                                                      C.c_void_p(host_jobs_ptr) if host_jobs_ptr else None))
+
+    def lcp_residual(self):
+        """per-world LCP residual of the last step (projected |J invM J^T lambda + cfm lambda - rhs|)"""
+        out = np.empty((self.num_worlds,), dtype=np.float32)
+        self._check(self.lib.b2p_debug_lcp_residual(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out

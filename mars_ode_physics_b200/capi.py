@@ -148,6 +148,24 @@ SIGNATURES = {
     "b2p_kernel_launch_count": (_I, [_P]),
     "b2p_debug_kernel_times": (_I, [_P, _I, _DP]),
     "b2p_algorithmic_bytes_per_world_step": (_D, [_P]),
+    "b2p_arena_set_graph_launch": (_I, [_P, _I]),
+    "b2p_arena_set_post_step_outputs": (_I, [_P, _I]),
+    "b2p_body_set_damping": (_I, [_P, _I, _D, _D]),
+    "b2p_body_get_damping": (_I, [_P, _I, _DP, _DP]),
+    "b2p_body_get_acceleration": (_I, [_P, _I, _I, _DP, _DP]),
+    "b2p_body_get_contact_force": (_I, [_P, _I, _I, _DP]),
+    "b2p_body_post_download": (_I, [_P, _P]),
+    "b2p_device_body_post": (_P, [_P]),
+    "b2p_observe_begin": (_I, [_P, _I, _P, _P]),
+    "b2p_joint_set_friction_coefficient": (_I, [_P, _I, _D]),
+    "b2p_joint_get_friction_coefficient": (_I, [_P, _I, _DP]),
+    "b2p_joint_get_update": (_I, [_P, _I, _I, _DP]),
+    "b2p_joint_update_download": (_I, [_P, _P]),
+    "b2p_device_joint_update": (_P, [_P]),
+    "b2p_collide_step": (_I, [_P, _D]),
+    "b2p_contacts_dropped": (_I, [_P, C.POINTER(C.c_longlong)]),
+    "b2p_collide_record_pairs": (_I, [_P, _I]),
+    "b2p_debug_lcp_residual": (_I, [_P, _P]),
 }
 
 _libs = {}

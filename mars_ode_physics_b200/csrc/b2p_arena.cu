@@ -21,7 +21,6 @@
 #include "b2p_universal.h"
 
 extern "C" size_t b2p_assemble_smem_bytes(int nb, int nj);
-extern "C" size_t b2p_integrate_smem_bytes(int nb);
 extern "C" size_t b2p_sor_smem_bytes(int nb, int maxrows, int rows_resident);
 extern "C" int b2p_sor_register_rows(int maxrows, int wanted);
 extern "C" size_t b2p_sor_tmem_smem_bytes(int nb, int maxrows, int pool, int warps);
@@ -30,6 +29,7 @@ extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxr
 extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, int nj, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, cudaStream_t stream);
+extern "C" cudaError_t b2p_launch_residual(const StepParams *P, float *out, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, int sampled, cudaStream_t stream);
 
 namespace {
@@ -168,6 +168,7 @@ struct HBody {
     int gyroscopic = 1, nogravity = 0, has_max_ang = 0;
     double max_angular_speed = kInf;
     double pos[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0}; // template pose (world 0 / broadcast)
+    double lin_damp = 1.0, ang_damp = 1.0;          // Frame::update damping factors; >= 1: off
 };
 
 struct HJoint {
@@ -178,6 +179,7 @@ struct HJoint {
     HLimot limot1, limot2;
     double c0 = 0, s0 = 0, v1[3] = {1, 0, 0}, v2[3] = {0, 1, 0}, w1[3] = {1, 0, 0}, w2[3] = {0, 1, 0};
     double susp_erp = 0, susp_cfm = 0, erp = 0, cfm = 0;
+    double friction = -0.1; // Joint::applyJointFriction coefficient (Joint.cpp:43: off by default)
 };
 
 struct HGeom {
@@ -217,6 +219,8 @@ struct b2p_arena {
     b2p_surface hf_surface{};
 
     Mirror<float> state, force, jcmd, jobs, jfb, crec, cfb;
+    Mirror<float> bodyx, jupd; // post-step outputs (b2p_dev.h); sized when post_flags selects them
+    int post_flags = B2P_POST_JOINT_UPDATE | B2P_POST_FRAME_UPDATE;
     Mirror<int> ccount, nrows;
     Mirror<uint32_t> seed;
     Mirror<uint8_t> jrows;
@@ -240,11 +244,27 @@ struct b2p_arena {
     int *d_pairs = nullptr, *d_npairs = nullptr;
     int maxpairs = 0;
     int launches = 0;
+    bool want_pairs = false; // the broadphase pair list is a debug output: written only after it was asked for
+    int *d_dropped = nullptr; // contacts the narrowphase found beyond max_contacts, summed over worlds and steps
+    float *d_residual = nullptr;
+    StepParams lastP{};      // parameters of the last step (b2p_debug_lcp_residual)
+    // one CUDA graph per launch shape: [0] = step, [1] = collide + step.  Re-captured when any kernel parameter
+    // changes (step size, gravity, on-chip row split ...), launched with one call otherwise.
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        StepParams P{};
+        CollideParams C{};
+        int use_tmem = -1, sampled = -1;
+    } graphs[2];
+    bool use_graph = true;
+    cudaStream_t cap_stream = nullptr; // capture happens here (the arena's own stream may be the legacy default stream)
     // pipelined observation read-back (b2p_body_get_state_batch_begin / b2p_io_wait): a copy stream and two
     // staging slots, so that the D2H of step k overlaps the kernels of step k+1
     struct IoSlot {
         float *dev = nullptr;
         size_t elems = 0;
+        float *dev_jobs = nullptr; // joint observations snapshot (b2p_observe_begin)
+        size_t jobs_elems = 0;
         cudaEvent_t snap = nullptr, done = nullptr;
         bool pending = false;
     } io[2];
@@ -319,6 +339,31 @@ template <typename T> int mirror_to_host(b2p_arena *a, Mirror<T> &m)
     return 0;
 }
 
+// One world's column of `n` consecutive fields: device -> host mirror.  The one-world accessors of the reference
+// API (Frame::getPosition, Joint::getVelocity ...) read a handful of values; they must not cost a transfer of the
+// whole batch.  The mirror stays "device newer": only this column of the host copy is refreshed.
+template <typename T> int mirror_fetch_column(b2p_arena *a, Mirror<T> &m, size_t field0, size_t n, int world)
+{
+    if (!(m.dev_newer && m.dev && m.dev_elems)) return 0;
+    if (int rc = join_pending_upload(a)) return rc;
+    const size_t pitch = sizeof(T) * (size_t)a->Wp, off = field0 * (size_t)a->Wp + (size_t)world;
+    CUDA_TRY(cudaMemcpy2DAsync(m.host.data() + off, pitch, m.dev + off, pitch, sizeof(T), n, cudaMemcpyDeviceToHost,
+                               a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    return 0;
+}
+
+// ... and host mirror -> device, for a one-world setter while the device copy is the newer one
+template <typename T> int mirror_push_column(b2p_arena *a, Mirror<T> &m, size_t field0, size_t n, int world)
+{
+    if (!(m.dev && m.dev_elems)) return 0;
+    const size_t pitch = sizeof(T) * (size_t)a->Wp, off = field0 * (size_t)a->Wp + (size_t)world;
+    CUDA_TRY(cudaMemcpy2DAsync(m.dev + off, pitch, m.host.data() + off, pitch, sizeof(T), n, cudaMemcpyHostToDevice,
+                               a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream)); // the source is pageable host memory that may change right away
+    return 0;
+}
+
 template <typename T> void mirror_free(Mirror<T> &m)
 {
     if (m.dev) cudaFree(m.dev);
@@ -340,6 +385,7 @@ template <typename T> void mset(b2p_arena *a, Mirror<T> &m, size_t field, int wo
 int check_world(const b2p_arena *a, int world, bool allow_all)
 {
     if (!a) return fail(B2P_EINVAL, "null arena");
+    cudaSetDevice(a->device); // every entry point works on the arena's device, whatever the caller's current one is
     if (world == B2P_ALL_WORLDS && allow_all) return 0;
     if (world < 0 || world >= a->W) return fail(B2P_EINVAL, "world index %d out of range [0,%d)", world, a->W);
     return 0;
@@ -347,12 +393,14 @@ int check_world(const b2p_arena *a, int world, bool allow_all)
 int check_body(const b2p_arena *a, int body)
 {
     if (!a) return fail(B2P_EINVAL, "null arena");
+    cudaSetDevice(a->device);
     if (body < 0 || body >= (int)a->bodies.size()) return fail(B2P_EINVAL, "body id %d out of range", body);
     return 0;
 }
 int check_joint(const b2p_arena *a, int j)
 {
     if (!a) return fail(B2P_EINVAL, "null arena");
+    cudaSetDevice(a->device);
     if (j < 0 || j >= (int)a->joints.size()) return fail(B2P_EINVAL, "joint id %d out of range", j);
     return 0;
 }
@@ -362,7 +410,7 @@ int rpc_of(const b2p_arena *a) { return a->rolling ? 6 : 3; }
 // host view of a body's pose in one world (double from the float mirror)
 int body_pose(b2p_arena *a, int body, int world, double *pos, double *q)
 {
-    int rc = mirror_to_host(a, a->state);
+    int rc = mirror_fetch_column(a, a->state, (size_t)body * B2P_STATE_FIELDS, 7, world);
     if (rc) return rc;
     const float *s = a->state.host.data();
     const size_t f = (size_t)body * B2P_STATE_FIELDS;
@@ -373,7 +421,7 @@ int body_pose(b2p_arena *a, int body, int world, double *pos, double *q)
 
 int body_vec(b2p_arena *a, Mirror<float> &m, size_t field0, int world, int n, double *out)
 {
-    int rc = mirror_to_host(a, m);
+    int rc = mirror_fetch_column(a, m, field0, (size_t)n, world);
     if (rc) return rc;
     for (int i = 0; i < n; i++) out[i] = m.host[(field0 + i) * a->Wp + world];
     return 0;
@@ -498,6 +546,8 @@ int finalize(b2p_arena *a)
             d.nogravity = h.nogravity;
             d.has_max_ang = h.has_max_ang;
             d.max_angular_speed = (float)h.max_angular_speed;
+            d.lin_damp = (float)h.lin_damp;
+            d.ang_damp = (float)h.ang_damp;
         }
         for (int j = 0; j < nj; j++) {
             const HJoint &h = a->joints[j];
@@ -527,6 +577,7 @@ int finalize(b2p_arena *a)
             d.susp_cfm = (float)h.susp_cfm;
             d.erp = (float)h.erp;
             d.cfm = (float)h.cfm;
+            d.friction = (float)h.friction;
             if (h.type != B2P_JOINT_FIXED && limot_has_stops(h.limot1)) T->has_limit_motors = 1;
             if (h.b[0] >= 0 && h.b[1] >= 0) {
                 T->connected[h.b[0]] |= 1u << h.b[1];
@@ -585,6 +636,10 @@ int finalize(b2p_arena *a)
     if ((rc = mirror_resize(a, a->jobs, (size_t)nj * 4, 0.f))) return rc;
     if ((rc = mirror_resize(a, a->jfb, (size_t)nj * 13, 0.f))) return rc;
     if ((rc = mirror_resize(a, a->jrows, (size_t)nj, (uint8_t)0))) return rc;
+    if ((rc = mirror_resize(a, a->bodyx, (a->post_flags & B2P_POST_FRAME_UPDATE) ? (size_t)nb * 15 : 0, 0.f))) return rc;
+    if ((rc = mirror_resize(a, a->jupd, (a->post_flags & B2P_POST_JOINT_UPDATE) ? (size_t)nj * 7 : 0, 0.f))) return rc;
+    if ((rc = mirror_to_device(a, a->bodyx))) return rc;
+    if ((rc = mirror_to_device(a, a->jupd))) return rc;
     if ((rc = mirror_to_device(a, a->state))) return rc;
     if ((rc = mirror_to_device(a, a->force))) return rc;
     if ((rc = mirror_to_device(a, a->jcmd))) return rc;
@@ -629,6 +684,25 @@ int finalize(b2p_arena *a)
         a->scratch_rows = (size_t)maxrows;
         a->scratch_nb = (size_t)nb;
         a->scratch_maxc = (size_t)a->maxc;
+    }
+    return 0;
+}
+
+// The joint geometry setters below read the poses of the joint's bodies, as ODE's dJointSet*Anchor / *Axis /
+// dJointSetFixed read the live dBody.  The template pose (HBody.pos / q) is what they use; once the worlds have
+// moved (a step, a state upload, a per-world setter) it is refreshed from world 0 first.  Joint geometry is per
+// template: it is shared by all worlds.
+int refresh_template_poses(b2p_arena *a, const HJoint &j)
+{
+    for (int k = 0; k < 2; k++) {
+        const int b = j.b[k];
+        if (b < 0 || !(a->state.dev_newer && a->state.dev)) continue;
+        int rc = mirror_fetch_column(a, a->state, (size_t)b * B2P_STATE_FIELDS, 7, 0);
+        if (rc) return rc;
+        const float *st = a->state.host.data() + (size_t)b * B2P_STATE_FIELDS * a->Wp;
+        HBody &hb = a->bodies[b];
+        for (int i = 0; i < 3; i++) hb.pos[i] = st[(size_t)i * a->Wp];
+        for (int i = 0; i < 4; i++) hb.q[i] = st[(size_t)(3 + i) * a->Wp];
     }
     return 0;
 }
@@ -830,7 +904,13 @@ void b2p_arena_destroy(b2p_arena *a)
     mirror_free(a->nrows);
     mirror_free(a->seed);
     mirror_free(a->jrows);
+    mirror_free(a->bodyx);
+    mirror_free(a->jupd);
     free_scratch(a);
+    for (b2p_arena::StepGraph &g : a->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (a->d_dropped) cudaFree(a->d_dropped);
+    if (a->d_residual) cudaFree(a->d_residual);
     for (cudaEvent_t e : a->ev)
         if (e) cudaEventDestroy(e);
     if (a->dT) cudaFree(a->dT);
@@ -840,10 +920,12 @@ void b2p_arena_destroy(b2p_arena *a)
     if (a->h_hw_rows) cudaFreeHost(a->h_hw_rows);
     for (b2p_arena::IoSlot &sl : a->io) {
         if (sl.dev) cudaFree(sl.dev);
+        if (sl.dev_jobs) cudaFree(sl.dev_jobs);
         if (sl.snap) cudaEventDestroy(sl.snap);
         if (sl.done) cudaEventDestroy(sl.done);
     }
     if (a->io_stream) cudaStreamDestroy(a->io_stream);
+    if (a->cap_stream) cudaStreamDestroy(a->cap_stream);
     if (a->ev_asm_done) cudaEventDestroy(a->ev_asm_done);
     if (a->ev_h2d_done) cudaEventDestroy(a->ev_h2d_done);
     delete a;
@@ -922,7 +1004,7 @@ int b2p_world_rand_get_seed(b2p_arena *a, int world, uint32_t *seed)
 {
     int rc = check_world(a, world, false);
     if (rc) return rc;
-    if ((rc = mirror_to_host(a, a->seed))) return rc;
+    if ((rc = mirror_fetch_column(a, a->seed, 0, 1, world))) return rc;
     *seed = a->seed.host[(size_t)world];
     return 0;
 }
@@ -966,8 +1048,17 @@ static int set3(b2p_arena *a, Mirror<float> &m, size_t field0, int body, int wor
     int rc = check_body(a, body);
     if (rc) return rc;
     if ((rc = check_world(a, world, true))) return rc;
-    if ((rc = mirror_to_host(a, m))) return rc;
     const double v[3] = {x, y, z};
+    if (world != B2P_ALL_WORLDS && m.dev_newer) {
+        // the device copy is the current one: update this world's column in place (read-modify-write for `add`)
+        if (add && (rc = mirror_fetch_column(a, m, field0, 3, world))) return rc;
+        for (int i = 0; i < 3; i++) {
+            float &x0 = m.host[(field0 + i) * (size_t)a->Wp + world];
+            x0 = add ? x0 + (float)v[i] : (float)v[i];
+        }
+        return mirror_push_column(a, m, field0, 3, world);
+    }
+    if ((rc = mirror_to_host(a, m))) return rc;
     for (int i = 0; i < 3; i++) {
         float *row = m.host.data() + (field0 + i) * (size_t)a->Wp;
         if (world == B2P_ALL_WORLDS) {
@@ -996,11 +1087,16 @@ int b2p_body_set_quaternion(b2p_arena *a, int body, int world, double qw, double
     int rc = check_body(a, body);
     if (rc) return rc;
     if ((rc = check_world(a, world, true))) return rc;
-    if ((rc = mirror_to_host(a, a->state))) return rc;
     double q[4] = {qw, qx, qy, qz};
     norm4(q); // dBodySetQuaternion normalises
-    for (int i = 0; i < 4; i++) mset(a, a->state, (size_t)body * B2P_STATE_FIELDS + 3 + i, world, (float)q[i]);
     if (world == B2P_ALL_WORLDS || world == 0) memcpy(a->bodies[body].q, q, sizeof(q));
+    const size_t f0 = (size_t)body * B2P_STATE_FIELDS + 3;
+    if (world != B2P_ALL_WORLDS && a->state.dev_newer) {
+        for (int i = 0; i < 4; i++) a->state.host[(f0 + i) * (size_t)a->Wp + world] = (float)q[i];
+        return mirror_push_column(a, a->state, f0, 4, world);
+    }
+    if ((rc = mirror_to_host(a, a->state))) return rc;
+    for (int i = 0; i < 4; i++) mset(a, a->state, f0 + i, world, (float)q[i]);
     return 0;
 }
 
@@ -1168,22 +1264,29 @@ int b2p_body_get_state_batch(b2p_arena *a, int body, float *host_out)
 // Pipelined variant: snapshots the body's state on the compute stream (device-to-device, a few microseconds),
 // then copies the snapshot to the host on a separate copy stream, so the transfer overlaps the next step.
 // Returns a ticket (>= 0) for b2p_io_wait, which blocks until the host buffer is complete.
-int b2p_body_get_state_batch_begin(b2p_arena *a, int body, float *host_out)
+int b2p_observe_begin(b2p_arena *a, int body, float *host_out, float *host_joint_obs)
 {
     int rc = check_body(a, body);
     if (rc) return rc;
     if (!host_out) return fail(B2P_EINVAL, "host_out is null");
     CUDA_TRY(cudaSetDevice(a->device));
     if ((rc = mirror_to_device(a, a->state))) return rc;
+    const size_t nj = a->joints.size();
+    if (host_joint_obs && (!a->stepped || !a->jobs.dev || nj == 0)) return fail(B2P_EINVAL, "no joint observations yet");
     if (!a->io_stream) CUDA_TRY(cudaStreamCreateWithFlags(&a->io_stream, cudaStreamNonBlocking));
     const int t = a->io_next;
     a->io_next ^= 1;
     b2p_arena::IoSlot &sl = a->io[t];
-    const size_t elems = (size_t)B2P_STATE_FIELDS * a->Wp;
+    const size_t elems = (size_t)B2P_STATE_FIELDS * a->Wp, jelems = host_joint_obs ? nj * 4 * a->Wp : 0;
     if (sl.elems != elems) {
         if (sl.dev) CUDA_TRY(cudaFree(sl.dev));
         CUDA_TRY(cudaMalloc(&sl.dev, sizeof(float) * elems));
         sl.elems = elems;
+    }
+    if (jelems && sl.jobs_elems != jelems) {
+        if (sl.dev_jobs) CUDA_TRY(cudaFree(sl.dev_jobs));
+        CUDA_TRY(cudaMalloc(&sl.dev_jobs, sizeof(float) * jelems));
+        sl.jobs_elems = jelems;
     }
     if (!sl.snap) {
         CUDA_TRY(cudaEventCreateWithFlags(&sl.snap, cudaEventDisableTiming));
@@ -1193,13 +1296,23 @@ int b2p_body_get_state_batch_begin(b2p_arena *a, int body, float *host_out)
     if (sl.pending) CUDA_TRY(cudaStreamWaitEvent(a->stream, sl.done, 0));
     CUDA_TRY(cudaMemcpyAsync(sl.dev, a->state.dev + (size_t)body * B2P_STATE_FIELDS * a->Wp, sizeof(float) * elems,
                              cudaMemcpyDeviceToDevice, a->stream));
+    if (jelems)
+        CUDA_TRY(cudaMemcpyAsync(sl.dev_jobs, a->jobs.dev, sizeof(float) * jelems, cudaMemcpyDeviceToDevice, a->stream));
     CUDA_TRY(cudaEventRecord(sl.snap, a->stream));
     CUDA_TRY(cudaStreamWaitEvent(a->io_stream, sl.snap, 0));
     CUDA_TRY(cudaMemcpy2DAsync(host_out, sizeof(float) * a->W, sl.dev, sizeof(float) * a->Wp, sizeof(float) * a->W,
                                B2P_STATE_FIELDS, cudaMemcpyDeviceToHost, a->io_stream));
+    if (jelems)
+        CUDA_TRY(cudaMemcpy2DAsync(host_joint_obs, sizeof(float) * a->W, sl.dev_jobs, sizeof(float) * a->Wp,
+                                   sizeof(float) * a->W, nj * 4, cudaMemcpyDeviceToHost, a->io_stream));
     CUDA_TRY(cudaEventRecord(sl.done, a->io_stream));
     sl.pending = true;
     return t;
+}
+
+int b2p_body_get_state_batch_begin(b2p_arena *a, int body, float *host_out)
+{
+    return b2p_observe_begin(a, body, host_out, nullptr);
 }
 
 int b2p_io_wait(b2p_arena *a, int ticket)
@@ -1279,6 +1392,7 @@ int b2p_joint_set_anchor(b2p_arena *a, int ji, double x, double y, double z)
     int rc = check_joint(a, ji);
     if (rc) return rc;
     HJoint &j = a->joints[ji];
+    if ((rc = refresh_template_poses(a, j))) return rc;
     if (j.type == B2P_JOINT_HINGE) {
         set_anchors(a, j, x, y, z);
         initial_relative_rotation(a, j);
@@ -1301,6 +1415,7 @@ int b2p_joint_set_axis1(b2p_arena *a, int ji, double x, double y, double z)
     int rc = check_joint(a, ji);
     if (rc) return rc;
     HJoint &j = a->joints[ji];
+    if ((rc = refresh_template_poses(a, j))) return rc;
     if (j.type == B2P_JOINT_HINGE) {
         set_axes(a, j, x, y, z, j.axis1, j.axis2);
         initial_relative_rotation(a, j);
@@ -1335,6 +1450,7 @@ int b2p_joint_set_axis2(b2p_arena *a, int ji, double x, double y, double z)
     int rc = check_joint(a, ji);
     if (rc) return rc;
     HJoint &j = a->joints[ji];
+    if ((rc = refresh_template_poses(a, j))) return rc;
     if (j.type == B2P_JOINT_UNIVERSAL) { // dJointSetUniversalAxis2
         if (j.reverse) set_axes(a, j, x, y, z, j.axis1, nullptr);
         else set_axes(a, j, x, y, z, nullptr, j.axis2);
@@ -1358,6 +1474,7 @@ int b2p_joint_set_fixed(b2p_arena *a, int ji)
     if (rc) return rc;
     HJoint &j = a->joints[ji];
     if (j.b[0] < 0) return 0;
+    if ((rc = refresh_template_poses(a, j))) return rc;
     const HBody &b0 = a->bodies[j.b[0]];
     if (j.b[1] >= 0) {
         const HBody &b1 = a->bodies[j.b[1]];
@@ -1394,9 +1511,15 @@ int b2p_joint_set_param(b2p_arena *a, int ji, int world, int param, double value
     const int axis = (l == &j.limot2) ? 1 : 0;
     if (num == B2P_PARAM_VEL || num == B2P_PARAM_FMAX) {
         if (num == B2P_PARAM_FMAX && value < 0) return 0; // ODE ignores negative fmax
-        if ((rc = mirror_to_host(a, a->jcmd))) return rc;
-        mset(a, a->jcmd, (size_t)ji * 4 + axis * 2 + (num == B2P_PARAM_FMAX ? 1 : 0), world, (float)value);
         if (world == B2P_ALL_WORLDS || world == 0) (num == B2P_PARAM_VEL ? l->vel : l->fmax) = value;
+        const size_t field = (size_t)ji * 4 + axis * 2 + (num == B2P_PARAM_FMAX ? 1 : 0);
+        if (world != B2P_ALL_WORLDS && a->jcmd.dev_newer) { // device copy current: update this world's value in place
+            if ((rc = join_pending_upload(a))) return rc;
+            a->jcmd.host[field * (size_t)a->Wp + world] = (float)value;
+            return mirror_push_column(a, a->jcmd, field, 1, world);
+        }
+        if ((rc = mirror_to_host(a, a->jcmd))) return rc;
+        mset(a, a->jcmd, field, world, (float)value);
         return 0;
     }
     if (world != B2P_ALL_WORLDS && a->W > 1)
@@ -1407,9 +1530,7 @@ int b2p_joint_set_param(b2p_arena *a, int ji, int world, int param, double value
     case B2P_PARAM_FUDGE_FACTOR:
         if (value >= 0 && value <= 1) l->fudge = value;
         break;
-    case B2P_PARAM_BOUNCE:
-        if (value != 0) return fail(B2P_EUNSUPPORTED, "dParamBounce is not supported by the device path");
-        break;
+    case B2P_PARAM_BOUNCE: l->bounce = value; break;
     case B2P_PARAM_CFM: l->normal_cfm = value; break;
     case B2P_PARAM_STOP_ERP: l->stop_erp = value; break;
     case B2P_PARAM_STOP_CFM: l->stop_cfm = value; break;
@@ -1440,9 +1561,12 @@ int b2p_joint_get_param(b2p_arena *a, int ji, int world, int param, double *valu
     switch (num) {
     case B2P_PARAM_VEL:
     case B2P_PARAM_FMAX:
-        if ((rc = mirror_to_host(a, a->jcmd))) return rc;
-        *value = a->jcmd.host[((size_t)ji * 4 + axis * 2 + (num == B2P_PARAM_FMAX ? 1 : 0)) * a->Wp + world];
+    {
+        const size_t field = (size_t)ji * 4 + axis * 2 + (num == B2P_PARAM_FMAX ? 1 : 0);
+        if ((rc = mirror_fetch_column(a, a->jcmd, field, 1, world))) return rc;
+        *value = a->jcmd.host[field * a->Wp + world];
         break;
+    }
     case B2P_PARAM_LO_STOP: *value = l->lostop; break;
     case B2P_PARAM_HI_STOP: *value = l->histop; break;
     case B2P_PARAM_FUDGE_FACTOR: *value = l->fudge; break;
@@ -1763,8 +1887,8 @@ int b2p_joint_get_num_rows(b2p_arena *a, int ji, int world, int *rows)
     if ((rc = check_world(a, world, false))) return rc;
     *rows = 0;
     if (a->jrows.fields <= (size_t)ji) return 0;
-    if ((rc = mirror_to_host(a, a->jrows))) return rc;
-    *rows = a->jrows.host[(size_t)ji * a->Wp + world] & 7; // high nibble: limit/motor row (device use)
+    if ((rc = mirror_fetch_column(a, a->jrows, (size_t)ji, 1, world))) return rc;
+    *rows = a->jrows.host[(size_t)ji * a->Wp + world] & 7; // bits 3, 4: which limit / motor rows exist (device use)
     return 0;
 }
 
@@ -1791,6 +1915,21 @@ int b2p_contacts_clear(b2p_arena *a, int world)
 {
     int rc = check_world(a, world, true);
     if (rc) return rc;
+    if (world == B2P_ALL_WORLDS) {
+        // "reset the contact counter": no record stays valid, so a device-side stream is simply dropped, and when
+        // the counters live on the device they are zeroed there (O(1) on the host)
+        if ((rc = mirror_resize(a, a->crec, (size_t)a->maxc * B2P_CONTACT_FIELDS, 0.f))) return rc;
+        if ((rc = mirror_resize(a, a->ccount, 1, 0))) return rc;
+        a->crec.dev_newer = false;
+        if (a->ccount.dev && a->ccount.dev_elems == a->ccount.host.size() && !a->ccount.host_newer) {
+            CUDA_TRY(cudaMemsetAsync(a->ccount.dev, 0, sizeof(int) * a->ccount.dev_elems, a->stream));
+            a->ccount.dev_newer = true;
+            return 0;
+        }
+        a->ccount.dev_newer = false;
+        mset(a, a->ccount, 0, world, 0);
+        return 0;
+    }
     if ((rc = ensure_contact_mirrors(a))) return rc;
     mset(a, a->ccount, 0, world, 0);
     return 0;
@@ -1846,7 +1985,7 @@ int b2p_contact_count(b2p_arena *a, int world, int *count)
     if (rc) return rc;
     *count = 0;
     if (a->ccount.fields == 0) return 0;
-    if ((rc = mirror_to_host(a, a->ccount))) return rc;
+    if ((rc = mirror_fetch_column(a, a->ccount, 0, 1, world))) return rc;
     *count = a->ccount.host[(size_t)world];
     return 0;
 }
@@ -1866,7 +2005,7 @@ int b2p_contact_get(b2p_arena *a, int world, int contact, int *body1, int *body2
     int rc = check_world(a, world, false);
     if (rc) return rc;
     if (contact < 0 || contact >= a->maxc || a->crec.fields == 0) return fail(B2P_EINVAL, "contact id out of range");
-    if ((rc = mirror_to_host(a, a->crec))) return rc;
+    if ((rc = mirror_fetch_column(a, a->crec, (size_t)contact * B2P_CONTACT_FIELDS, B2P_CONTACT_FIELDS, world))) return rc;
     float rec[B2P_CONTACT_FIELDS];
     for (int f = 0; f < B2P_CONTACT_FIELDS; f++)
         rec[f] = a->crec.host[((size_t)contact * B2P_CONTACT_FIELDS + f) * a->Wp + world];
@@ -1901,6 +2040,8 @@ int b2p_geom_create(b2p_arena *a, int cls, int body, const double dims[4], const
     if (cls < B2P_GEOM_SPHERE || cls > B2P_GEOM_PLANE) return fail(B2P_EINVAL, "bad geom class %d", cls);
     if (body >= (int)a->bodies.size() || body < -1) return fail(B2P_EINVAL, "bad geom body");
     if (cls == B2P_GEOM_PLANE && body >= 0) return fail(B2P_EINVAL, "planes are static");
+    if (cls != B2P_GEOM_PLANE && body < 0)
+        return fail(B2P_EUNSUPPORTED, "static geoms are planes and the heightfield; attach other shapes to a body");
     if ((int)a->geoms.size() >= B2P_MAX_GEOMS) return fail(B2P_ECAPACITY, "too many geoms");
     HGeom g;
     g.cls = cls;
@@ -1939,67 +2080,7 @@ int b2p_geom_create_heightfield(b2p_arena *a, const float *heights, int nx, int 
     return (int)a->geoms.size() - 1;
 }
 
-int b2p_collide(b2p_arena *a)
-{
-    if (!a) return fail(B2P_EINVAL, "null arena");
-    CUDA_TRY(cudaSetDevice(a->device));
-    int rc = finalize(a);
-    if (rc) return rc;
-    const int ng = (int)a->geoms.size();
-    const int maxpairs = ng * (ng - 1) / 2;
-    if (maxpairs > a->maxpairs || !a->d_npairs) {
-        if (a->d_pairs) cudaFree(a->d_pairs);
-        if (a->d_npairs) cudaFree(a->d_npairs);
-        a->d_pairs = a->d_npairs = nullptr;
-        CUDA_TRY(cudaMalloc(&a->d_pairs, sizeof(int) * (size_t)std::max(maxpairs, 1) * a->Wp));
-        CUDA_TRY(cudaMalloc(&a->d_npairs, sizeof(int) * (size_t)a->Wp));
-        a->maxpairs = maxpairs;
-    }
-    CollideParams P;
-    P.T = a->dT;
-    P.W = a->W;
-    P.Wp = a->Wp;
-    P.state = a->state.dev;
-    P.crec = a->crec.dev;
-    P.ccount = a->ccount.dev;
-    P.pairs = a->d_pairs;
-    P.npairs = a->d_npairs;
-    P.maxpairs = a->maxpairs;
-    if ((size_t)ng * 6 * 128 * sizeof(float) > 200 * 1024) return fail(B2P_ECAPACITY, "too many geoms for the collide kernel");
-    // the sample-point colliders (cylinders; capsule against box / heightfield) live in a separate kernel variant
-    bool has_cyl = false, has_caps = false, has_box = false;
-    for (const HGeom &g : a->geoms) {
-        has_cyl |= g.cls == B2P_GEOM_CYLINDER;
-        has_caps |= g.cls == B2P_GEOM_CAPSULE;
-        has_box |= g.cls == B2P_GEOM_BOX;
-    }
-    const int sampled = has_cyl || (has_caps && (has_box || a->has_hf));
-    CUDA_TRY(b2p_launch_collide(&P, ng, sampled, a->stream));
-    a->launches++;
-    a->crec.dev_newer = true;
-    a->ccount.dev_newer = true;
-    a->crec.host_newer = false;
-    a->ccount.host_newer = false;
-    return 0;
-}
-
-int b2p_collide_get_pairs(b2p_arena *a, int world, int *pairs, int max_pairs)
-{
-    int rc = check_world(a, world, false);
-    if (rc) return rc;
-    if (!a->d_pairs) return 0;
-    std::vector<int> col((size_t)a->maxpairs);
-    int n = 0;
-    CUDA_TRY(cudaMemcpyAsync(&n, a->d_npairs + world, sizeof(int), cudaMemcpyDeviceToHost, a->stream));
-    CUDA_TRY(cudaMemcpy2DAsync(col.data(), sizeof(int), a->d_pairs + world, sizeof(int) * a->Wp, sizeof(int),
-                               (size_t)a->maxpairs, cudaMemcpyDeviceToHost, a->stream));
-    CUDA_TRY(cudaStreamSynchronize(a->stream));
-    if (n > a->maxpairs) n = a->maxpairs;
-    for (int i = 0; i < n && i < max_pairs; i++) pairs[i] = col[(size_t)i];
-    return n;
-}
-
-// ---------------- the step ----------------
+// ---------------- collision + step: parameter blocks, launches, CUDA graph ----------------
 namespace {
 constexpr size_t kSmemMax = 227 * 1024;
 
@@ -2018,16 +2099,63 @@ int pick_rows_resident(const b2p_arena *a, int nb, int maxrows, int kr)
     const int want = seen > 0 ? std::min(std::max(seen - kr, 0), rest) : rest;
     return std::min(want, cap);
 }
-} // namespace
 
-int b2p_step(b2p_arena *a, double step_size)
+// broadphase + narrowphase launch parameters (buffers are created on first use)
+int prepare_collide(b2p_arena *a, CollideParams &P, int &sampled)
 {
-    if (!a) return fail(B2P_EINVAL, "null arena");
-    if (!(step_size > 0)) return fail(B2P_EINVAL, "step size must be positive");
-    CUDA_TRY(cudaSetDevice(a->device));
     int rc = finalize(a);
     if (rc) return rc;
-    StepParams P;
+    const int ng = (int)a->geoms.size();
+    const int maxpairs = ng * (ng - 1) / 2;
+    if (a->want_pairs && (maxpairs > a->maxpairs || !a->d_npairs)) {
+        if (a->d_pairs) cudaFree(a->d_pairs);
+        if (a->d_npairs) cudaFree(a->d_npairs);
+        a->d_pairs = a->d_npairs = nullptr;
+        CUDA_TRY(cudaMalloc(&a->d_pairs, sizeof(int) * (size_t)std::max(maxpairs, 1) * a->Wp));
+        CUDA_TRY(cudaMalloc(&a->d_npairs, sizeof(int) * (size_t)a->Wp));
+        a->maxpairs = maxpairs;
+    }
+    if (!a->d_dropped) {
+        CUDA_TRY(cudaMalloc(&a->d_dropped, sizeof(int)));
+        CUDA_TRY(cudaMemsetAsync(a->d_dropped, 0, sizeof(int), a->stream));
+    }
+    memset(&P, 0, sizeof(P));
+    P.T = a->dT;
+    P.W = a->W;
+    P.Wp = a->Wp;
+    P.state = a->state.dev;
+    P.crec = a->crec.dev;
+    P.ccount = a->ccount.dev;
+    P.pairs = a->want_pairs ? a->d_pairs : nullptr;
+    P.npairs = a->want_pairs ? a->d_npairs : nullptr;
+    P.maxpairs = a->want_pairs ? a->maxpairs : 0;
+    P.dropped = a->d_dropped;
+    if ((size_t)ng * 6 * 128 * sizeof(float) > 200 * 1024) return fail(B2P_ECAPACITY, "too many geoms for the collide kernel");
+    // the sample-point colliders (cylinders; capsule against box / heightfield) live in a separate kernel variant
+    bool has_cyl = false, has_caps = false, has_box = false;
+    for (const HGeom &g : a->geoms) {
+        has_cyl |= g.cls == B2P_GEOM_CYLINDER;
+        has_caps |= g.cls == B2P_GEOM_CAPSULE;
+        has_box |= g.cls == B2P_GEOM_BOX;
+    }
+    sampled = has_cyl || (has_caps && (has_box || a->has_hf));
+    return 0;
+}
+
+void after_collide(b2p_arena *a)
+{
+    a->launches++;
+    a->crec.dev_newer = true;
+    a->ccount.dev_newer = true;
+    a->crec.host_newer = false;
+    a->ccount.host_newer = false;
+}
+
+// the step's launch parameters and its choice of SOR-LCP kernel
+int prepare_step(b2p_arena *a, double step_size, StepParams &P, bool &use_tmem)
+{
+    int rc = finalize(a);
+    if (rc) return rc;
     memset(&P, 0, sizeof(P));
     P.T = a->dT;
     P.W = a->W;
@@ -2058,6 +2186,8 @@ int b2p_step(b2p_arena *a, double step_size)
     P.ccount = a->ccount.dev;
     P.nrows = a->nrows.dev;
     P.seed = a->seed.dev;
+    P.bodyx = (a->post_flags & B2P_POST_FRAME_UPDATE) ? a->bodyx.dev : nullptr;
+    P.jupd = (a->post_flags & B2P_POST_JOINT_UPDATE) ? a->jupd.dev : nullptr;
     const int nb = (int)a->bodies.size();
     const int maxrows = (int)a->joints.size() * B2P_ROWS_PER_JOINT + a->maxc * rpc_of(a);
     P.hw_rows = a->d_hw_rows;
@@ -2075,7 +2205,7 @@ int b2p_step(b2p_arena *a, double step_size)
         want_t = std::max(std::min(seen, maxrows) - b2p_sor_tmem_rows_on_chip(kr_t, nw_t), 0);
         if (nw_t == 4 || a->sor_warps == 8 || (pool_t >= 0 && want_t <= pool_t)) break;
     }
-    bool use_tmem = a->sor_kernel == B2P_SOR_TMEM || (a->sor_kernel == B2P_SOR_AUTO && pool_t >= 0);
+    use_tmem = a->sor_kernel == B2P_SOR_TMEM || (a->sor_kernel == B2P_SOR_AUTO && pool_t >= 0);
     if (use_tmem && pool_t < 0)
         return fail(B2P_ECAPACITY, "scene too large for the Tensor-Memory SOR kernel");
     if (use_tmem) {
@@ -2094,30 +2224,122 @@ int b2p_step(b2p_arena *a, double step_size)
         P.rows_registers = b2p_sor_register_rows(maxrows, a->rows_registers);
         P.rows_resident = pick_rows_resident(a, nb, maxrows, P.rows_registers);
     }
-    a->sor_kernel_used = use_tmem ? B2P_SOR_TMEM : B2P_SOR_PAIRED;
-    if (b2p_assemble_smem_bytes(nb, (int)a->joints.size()) > kSmemMax || b2p_integrate_smem_bytes(nb) > kSmemMax ||
+    if (b2p_assemble_smem_bytes(nb, (int)a->joints.size()) > kSmemMax ||
         (!use_tmem && b2p_sor_smem_bytes(nb, maxrows, P.rows_resident) > kSmemMax))
         return fail(B2P_ECAPACITY, "scene needs more than %zu bytes of shared memory per CTA", kSmemMax);
-    if ((rc = join_pending_upload(a))) return rc;
-    if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[0], a->stream));
-    CUDA_TRY(b2p_launch_assemble(&P, nb, (int)a->joints.size(), a->stream));
+    return 0;
+}
+
+// the three launches of a step on stream `st` (a real stream, or the capture stream of a graph)
+int enqueue_step(b2p_arena *a, const StepParams &P, bool use_tmem, cudaStream_t st, bool capturing)
+{
+    const int nb = (int)a->bodies.size();
+    const int maxrows = (int)a->joints.size() * B2P_ROWS_PER_JOINT + a->maxc * rpc_of(a);
+    const bool timing = a->timing && !capturing;
+    if (timing) CUDA_TRY(cudaEventRecord(a->ev[0], st));
+    CUDA_TRY(b2p_launch_assemble(&P, nb, (int)a->joints.size(), st));
     if (a->io_stream) { // lets the next command upload start as soon as this kernel has read jcmd
         if (!a->ev_asm_done) CUDA_TRY(cudaEventCreateWithFlags(&a->ev_asm_done, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventRecord(a->ev_asm_done, a->stream));
+        if (capturing) CUDA_TRY(cudaEventRecordWithFlags(a->ev_asm_done, st, cudaEventRecordExternal));
+        else CUDA_TRY(cudaEventRecord(a->ev_asm_done, st));
         a->asm_recorded = true;
     }
-    if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[1], a->stream));
-    if (use_tmem) CUDA_TRY(b2p_launch_sor_tmem(&P, nb, maxrows, a->stream));
-    else CUDA_TRY(b2p_launch_sor(&P, nb, maxrows, a->stream));
-    if (a->timing) CUDA_TRY(cudaEventRecord(a->ev[2], a->stream));
-    CUDA_TRY(b2p_launch_integrate(&P, nb, a->stream));
+    if (timing) CUDA_TRY(cudaEventRecord(a->ev[1], st));
+    if (use_tmem) CUDA_TRY(b2p_launch_sor_tmem(&P, nb, maxrows, st));
+    else CUDA_TRY(b2p_launch_sor(&P, nb, maxrows, st));
+    if (timing) CUDA_TRY(cudaEventRecord(a->ev[2], st));
+    CUDA_TRY(b2p_launch_integrate(&P, nb, st));
+    if (timing) CUDA_TRY(cudaEventRecord(a->ev[3], st));
+    return 0;
+}
+
+void after_step(b2p_arena *a, const StepParams &P, bool use_tmem)
+{
+    a->sor_kernel_used = use_tmem ? B2P_SOR_TMEM : B2P_SOR_PAIRED;
+    a->lastP = P;
+    a->steps_done++;
+    a->launches += 3;
+    a->stepped = true;
+    a->state.dev_newer = true;
+    a->jobs.dev_newer = a->jfb.dev_newer = a->cfb.dev_newer = true;
+    a->bodyx.dev_newer = a->bodyx.dev != nullptr;
+    a->jupd.dev_newer = a->jupd.dev != nullptr;
+    a->nrows.dev_newer = a->seed.dev_newer = a->jrows.dev_newer = true;
+    // The step leaves the force accumulators on the device: zero (ODE: "zero all force accumulators") plus what
+    // Joint::applyJointFriction added for the next step.  The host mirror is NOT touched (no O(worlds) host work
+    // per step): the device copy is the current one, one-world accessors fetch / update their column.
+    a->force.host_newer = false;
+    a->force.dev_newer = true;
+}
+
+// Collide (optional) + step.  Launch shape `which` (0 = step, 1 = collide + step) is replayed from a CUDA graph
+// when its parameter blocks equal the previous call's; the call in which they change launches directly (that is
+// also where a kernel's shared-memory attribute gets configured) and the next identical one re-captures.
+int run_step(b2p_arena *a, double step_size, bool with_collide)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    if (!(step_size > 0)) return fail(B2P_EINVAL, "step size must be positive");
+    CUDA_TRY(cudaSetDevice(a->device));
+    CollideParams C;
+    memset(&C, 0, sizeof(C));
+    int sampled = 0, rc;
+    if (with_collide && (rc = prepare_collide(a, C, sampled))) return rc;
+    StepParams P;
+    bool use_tmem = false;
+    if ((rc = prepare_step(a, step_size, P, use_tmem))) return rc;
+    if (with_collide) { // finalize() inside prepare_step may have (re)allocated nothing new, but keep both views equal
+        C.state = a->state.dev;
+        C.crec = a->crec.dev;
+        C.ccount = a->ccount.dev;
+    }
+    if ((rc = join_pending_upload(a))) return rc;
+    const int ng = (int)a->geoms.size();
+    b2p_arena::StepGraph &g = a->graphs[with_collide ? 1 : 0];
+    const bool same = memcmp(&g.P, &P, sizeof(P)) == 0 && g.use_tmem == (int)use_tmem &&
+                      (!with_collide || (memcmp(&g.C, &C, sizeof(C)) == 0 && g.sampled == sampled));
+    const bool graph_ok = a->use_graph && !a->timing;
+    if (graph_ok && same) {
+        if (!g.exec) {
+            if (!a->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&a->cap_stream, cudaStreamNonBlocking));
+            cudaGraph_t graph = nullptr;
+            CUDA_TRY(cudaStreamBeginCapture(a->cap_stream, cudaStreamCaptureModeThreadLocal));
+            int erc = 0;
+            if (with_collide) {
+                cudaError_t e = b2p_launch_collide(&C, ng, sampled, a->cap_stream);
+                if (e != cudaSuccess) erc = fail(B2P_ECUDA, "collide launch (capture): %s", cudaGetErrorString(e));
+            }
+            if (!erc) erc = enqueue_step(a, P, use_tmem, a->cap_stream, true);
+            cudaError_t ee = cudaStreamEndCapture(a->cap_stream, &graph);
+            if (erc) {
+                if (graph) cudaGraphDestroy(graph);
+                return erc;
+            }
+            if (ee != cudaSuccess) return fail(B2P_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ee));
+            ee = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ee != cudaSuccess) {
+                g.exec = nullptr;
+                return fail(B2P_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ee));
+            }
+        }
+        CUDA_TRY(cudaGraphLaunch(g.exec, a->stream));
+    } else {
+        if (g.exec) {
+            cudaGraphExecDestroy(g.exec);
+            g.exec = nullptr;
+        }
+        g.P = P;
+        g.C = C;
+        g.use_tmem = use_tmem;
+        g.sampled = sampled;
+        if (with_collide) CUDA_TRY(b2p_launch_collide(&C, ng, sampled, a->stream));
+        if ((rc = enqueue_step(a, P, use_tmem, a->stream, false))) return rc;
+    }
+    if (with_collide) after_collide(a);
     // refresh the host copy of the row high-water mark (every step at first, then occasionally)
     if (a->steps_done < 8 || (a->steps_done & 31) == 0)
         CUDA_TRY(cudaMemcpyAsync(a->h_hw_rows, a->d_hw_rows, sizeof(int), cudaMemcpyDeviceToHost, a->stream));
-    a->steps_done++;
-    a->launches += 3;
     if (a->timing) {
-        CUDA_TRY(cudaEventRecord(a->ev[3], a->stream));
         CUDA_TRY(cudaEventSynchronize(a->ev[3]));
         for (int i = 0; i < 3; i++) {
             float ms = 0;
@@ -2126,14 +2348,76 @@ int b2p_step(b2p_arena *a, double step_size)
         }
         a->timed_steps++;
     }
-    a->stepped = true;
-    a->state.dev_newer = true;
-    a->jobs.dev_newer = a->jfb.dev_newer = a->cfb.dev_newer = true;
-    a->nrows.dev_newer = a->seed.dev_newer = a->jrows.dev_newer = true;
-    // the step zeroes the force accumulators on the device (ODE: "zero all force accumulators")
-    std::fill(a->force.host.begin(), a->force.host.end(), 0.f);
-    a->force.host_newer = false;
-    a->force.dev_newer = false;
+    after_step(a, P, use_tmem);
+    return 0;
+}
+} // namespace
+
+int b2p_collide(b2p_arena *a)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    CUDA_TRY(cudaSetDevice(a->device));
+    CollideParams P;
+    int sampled = 0;
+    int rc = prepare_collide(a, P, sampled);
+    if (rc) return rc;
+    CUDA_TRY(b2p_launch_collide(&P, (int)a->geoms.size(), sampled, a->stream));
+    after_collide(a);
+    return 0;
+}
+
+int b2p_collide_record_pairs(b2p_arena *a, int on)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    a->want_pairs = on != 0;
+    return 0;
+}
+
+int b2p_contacts_dropped(b2p_arena *a, long long *count)
+{
+    if (!a || !count) return fail(B2P_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(a->device));
+    *count = 0;
+    if (!a->d_dropped) return 0;
+    int n = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n, a->d_dropped, sizeof(int), cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    *count = n;
+    return 0;
+}
+
+int b2p_collide_get_pairs(b2p_arena *a, int world, int *pairs, int max_pairs)
+{
+    int rc = check_world(a, world, false);
+    if (rc) return rc;
+    if (!a->want_pairs) return fail(B2P_EINVAL, "call b2p_collide_record_pairs(a, 1) before b2p_collide");
+    if (!a->d_pairs) return 0;
+    std::vector<int> col((size_t)a->maxpairs);
+    int n = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n, a->d_npairs + world, sizeof(int), cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaMemcpy2DAsync(col.data(), sizeof(int), a->d_pairs + world, sizeof(int) * a->Wp, sizeof(int),
+                               (size_t)a->maxpairs, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    if (n > a->maxpairs) n = a->maxpairs;
+    for (int i = 0; i < n && i < max_pairs; i++) pairs[i] = col[(size_t)i];
+    return n;
+}
+
+// ---------------- the step ----------------
+int b2p_step(b2p_arena *a, double step_size) { return run_step(a, step_size, false); }
+
+// b2p_collide + b2p_step as one call (and, from the second identical call on, one CUDA graph launch of the four
+// kernels): the per-tick sequence of a device-collision scene
+int b2p_collide_step(b2p_arena *a, double step_size)
+{
+    if (a && a->geoms.empty()) return run_step(a, step_size, false);
+    return run_step(a, step_size, true);
+}
+
+int b2p_arena_set_graph_launch(b2p_arena *a, int on)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    a->use_graph = on != 0;
     return 0;
 }
 
@@ -2151,7 +2435,7 @@ int b2p_world_last_num_rows(b2p_arena *a, int world, int *rows)
     if (rc) return rc;
     *rows = 0;
     if (a->nrows.fields == 0) return 0;
-    if ((rc = mirror_to_host(a, a->nrows))) return rc;
+    if ((rc = mirror_fetch_column(a, a->nrows, 0, 1, world))) return rc;
     *rows = a->nrows.host[(size_t)world] & 0xffff; // high half: independent rows (device use)
     return 0;
 }
@@ -2204,6 +2488,120 @@ int b2p_debug_kernel_times(b2p_arena *a, int enable, double out[4])
     if (enable)
         for (cudaEvent_t &e : a->ev)
             if (!e) CUDA_TRY(cudaEventCreate(&e));
+    return 0;
+}
+
+// ---------------- post-step bookkeeping of WorldPhysics::stepTheWorld, for every world ----------------
+int b2p_arena_set_post_step_outputs(b2p_arena *a, int flags)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    a->post_flags = flags & (B2P_POST_JOINT_UPDATE | B2P_POST_FRAME_UPDATE);
+    return 0;
+}
+
+int b2p_body_set_damping(b2p_arena *a, int body, double linear, double angular)
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    a->bodies[body].lin_damp = linear;
+    a->bodies[body].ang_damp = angular;
+    a->tmpl_dirty = true;
+    return 0;
+}
+
+int b2p_body_get_damping(b2p_arena *a, int body, double *linear, double *angular)
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    if (linear) *linear = a->bodies[body].lin_damp;
+    if (angular) *angular = a->bodies[body].ang_damp;
+    return 0;
+}
+
+int b2p_joint_set_friction_coefficient(b2p_arena *a, int ji, double k)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    a->joints[ji].friction = k;
+    a->tmpl_dirty = true;
+    return 0;
+}
+
+int b2p_joint_get_friction_coefficient(b2p_arena *a, int ji, double *k)
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if (k) *k = a->joints[ji].friction;
+    return 0;
+}
+
+int b2p_joint_get_update(b2p_arena *a, int ji, int world, double out[7])
+{
+    int rc = check_joint(a, ji);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    for (int i = 0; i < 7; i++) out[i] = 0;
+    if (a->jupd.fields < (size_t)(ji + 1) * 7) return 0; // never stepped, or the output is switched off
+    return body_vec(a, a->jupd, (size_t)ji * 7, world, 7, out);
+}
+
+int b2p_body_get_acceleration(b2p_arena *a, int body, int world, double lin[3], double ang[3])
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    if (a->bodyx.fields >= (size_t)(body + 1) * 15 && (rc = body_vec(a, a->bodyx, (size_t)body * 15 + 6, world, 6, v)))
+        return rc;
+    for (int i = 0; i < 3; i++) {
+        if (lin) lin[i] = v[i];
+        if (ang) ang[i] = v[3 + i];
+    }
+    return 0;
+}
+
+int b2p_body_get_contact_force(b2p_arena *a, int body, int world, double out[3])
+{
+    int rc = check_body(a, body);
+    if (rc) return rc;
+    if ((rc = check_world(a, world, false))) return rc;
+    out[0] = out[1] = out[2] = 0;
+    if (a->bodyx.fields < (size_t)(body + 1) * 15) return 0;
+    return body_vec(a, a->bodyx, (size_t)body * 15 + 12, world, 3, out);
+}
+
+static int download_fields(b2p_arena *a, const float *dev, size_t fields, float *host)
+{
+    if (!a || !host) return fail(B2P_EINVAL, "null argument");
+    if (!a->stepped || !dev) return fail(B2P_EINVAL, "no step has run yet (or the output is switched off)");
+    CUDA_TRY(cudaSetDevice(a->device));
+    CUDA_TRY(cudaMemcpy2DAsync(host, sizeof(float) * a->W, dev, sizeof(float) * a->Wp, sizeof(float) * a->W, fields,
+                               cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    return 0;
+}
+int b2p_joint_update_download(b2p_arena *a, float *host)
+{
+    return download_fields(a, a ? a->jupd.dev : nullptr, a ? a->joints.size() * 7 : 0, host);
+}
+int b2p_body_post_download(b2p_arena *a, float *host)
+{
+    return download_fields(a, a ? a->bodyx.dev : nullptr, a ? a->bodies.size() * 15 : 0, host);
+}
+void *b2p_device_joint_update(b2p_arena *a) { return a ? a->jupd.dev : nullptr; }
+void *b2p_device_body_post(b2p_arena *a) { return a ? a->bodyx.dev : nullptr; }
+
+// LCP residual of the last step's solve, one value per world (see b2p_residual_kernel)
+int b2p_debug_lcp_residual(b2p_arena *a, float *host_out)
+{
+    if (!a || !host_out) return fail(B2P_EINVAL, "null argument");
+    if (!a->stepped) return fail(B2P_EINVAL, "no step has run yet");
+    CUDA_TRY(cudaSetDevice(a->device));
+    if (!a->d_residual) CUDA_TRY(cudaMalloc(&a->d_residual, sizeof(float) * (size_t)a->Wp));
+    CUDA_TRY(b2p_launch_residual(&a->lastP, a->d_residual, a->stream));
+    a->launches++;
+    CUDA_TRY(cudaMemcpyAsync(host_out, a->d_residual, sizeof(float) * (size_t)a->W, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
     return 0;
 }
 

@@ -19,7 +19,7 @@
 //
 // Rows are stored in ODE's initial sweep order (rows with findex < 0 first, in creation order, then the
 // friction-dependent rows), so that the order array of iteration 0 is the identity.
-#include "b2p_kern.cuh"
+#include "b2p_rows.cuh"
 
 namespace {
 
@@ -42,26 +42,6 @@ __device__ __forceinline__ void load_pose_s(const Smem &S, int b, int tid, BodyP
     bp.pos[0] = p[0], bp.pos[1] = p[BD], bp.pos[2] = p[2 * BD];
     bp.q[0] = p[3 * BD], bp.q[1] = p[4 * BD], bp.q[2] = p[5 * BD], bp.q[3] = p[6 * BD];
     q_to_R(bp.q, bp.R);
-}
-
-// One constraint row under construction (ODE Info2 view).
-struct Row {
-    float J[12];
-    float c, cfm, lo, hi;
-    int fr;     // slot of the contact's normal row + 1 if this row's bounds follow it (findex), else 0
-    float sn;   // sqrt(Ad) of that normal row
-};
-
-__device__ __forceinline__ void row_init(Row &r, float world_cfm)
-{
-#pragma unroll
-    for (int k = 0; k < 12; k++) r.J[k] = 0.f;
-    r.c = 0.f;
-    r.cfm = world_cfm;
-    r.lo = -INFINITY;
-    r.hi = INFINITY;
-    r.fr = 0;
-    r.sn = 1.f;
 }
 
 struct PairCtx {
@@ -150,61 +130,6 @@ __device__ __forceinline__ float emit_row(const StepParams &P, const Smem &S, in
            make_float4(sa * rhs, cfm * Ad, bound, __uint_as_float(meta)));
     P.rowS[(size_t)slot * Wp + w] = sa;
     return sa;
-}
-
-// dxJointLimitMotor::addLimot, row part.  Returns 1 if the row is used.
-// The "powered while at a limit" force injection is done by limot_prepass() before tmp1 exists.
-__device__ __forceinline__ int add_limot_row(const StepParams &P, const DevLimot &l, float vel, float fmax,
-                                             const LimotState &st, Row &r, const float *ax1, int rotational,
-                                             const BodyPose &p0, const BodyPose &p1, bool has_b1)
-{
-    int powered = fmax > 0.f;
-    if (!(powered || st.limit)) return 0;
-    float *J1 = rotational ? r.J + 3 : r.J;
-    float *J2 = rotational ? r.J + 9 : r.J + 6;
-#pragma unroll
-    for (int i = 0; i < 3; i++) J1[i] = ax1[i];
-    if (has_b1) {
-#pragma unroll
-        for (int i = 0; i < 3; i++) J2[i] = -ax1[i];
-    }
-    if (!rotational && has_b1) {
-        float c[3], ltd[3];
-#pragma unroll
-        for (int i = 0; i < 3; i++) c[i] = 0.5f * (p1.pos[i] - p0.pos[i]);
-        cross3(ltd, c, ax1);
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            r.J[3 + i] = ltd[i];
-            r.J[9 + i] = ltd[i];
-        }
-    }
-    if (st.limit && (l.lostop == l.histop)) powered = 0;
-    if (powered) {
-        r.cfm = l.normal_cfm;
-        if (!st.limit) {
-            r.c = vel;
-            r.lo = -fmax;
-            r.hi = fmax;
-        }
-    }
-    if (st.limit) {
-        const float k = (1.0f / P.h) * l.stop_erp;
-        r.c = -k * st.limit_err;
-        r.cfm = l.stop_cfm;
-        if (l.lostop == l.histop) {
-            r.lo = -INFINITY;
-            r.hi = INFINITY;
-        } else if (st.limit == 1) {
-            r.lo = 0.f;
-            r.hi = INFINITY;
-        } else {
-            r.lo = -INFINITY;
-            r.hi = 0.f;
-        }
-        // dParamBounce is never set by the reference; not supported on the device path.
-    }
-    return 1;
 }
 
 __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
@@ -381,300 +306,29 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
 
     for (int j = 0; j < nj; j++) {
         const DevJoint &jc = S.joints[j];
-        int mrows = 0, limot_row = -1;
+        int jr = 0;
         if (jc.b0 >= 0) {
-            const bool has_b1 = jc.b1 >= 0;
             BodyPose p0, p1;
             PairCtx pc;
             pc.b0 = jc.b0;
             pc.b1 = jc.b1;
             load_pose_s(S, jc.b0, tid, p0);
-            if (has_b1) load_pose_s(S, jc.b1, tid, p1);
+            if (jc.b1 >= 0) load_pose_s(S, jc.b1, tid, p1);
             pair_ctx(pc, S, tid);
-            const float kerp = hinv * P.erp;
-            Row r;
-            if (jc.type == 1) {
-                // ---- hinge: setBall + two angular rows + limot (ODE hinge.cpp getInfo2)
-                float a1[3], a2[3], cb[3];
-                mul_R_v(a1, p0.R, jc.anchor1);
-                if (has_b1) {
-                    mul_R_v(a2, p1.R, jc.anchor2);
-#pragma unroll
-                    for (int i = 0; i < 3; i++) cb[i] = kerp * (a2[i] + p1.pos[i] - a1[i] - p0.pos[i]);
-                } else {
-                    a2[0] = a2[1] = a2[2] = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 3; i++) cb[i] = kerp * (jc.anchor2[i] - a1[i] - p0.pos[i]);
-                }
-                // row 0
-                row_init(r, P.cfm);
-                r.J[0] = 1.f; r.J[4] = a1[2]; r.J[5] = -a1[1];
-                if (has_b1) { r.J[6] = -1.f; r.J[10] = -a2[2]; r.J[11] = a2[1]; }
-                r.c = cb[0];
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                row_init(r, P.cfm);
-                r.J[1] = 1.f; r.J[3] = -a1[2]; r.J[5] = a1[0];
-                if (has_b1) { r.J[7] = -1.f; r.J[9] = a2[2]; r.J[11] = -a2[0]; }
-                r.c = cb[1];
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                row_init(r, P.cfm);
-                r.J[2] = 1.f; r.J[3] = a1[1]; r.J[4] = -a1[0];
-                if (has_b1) { r.J[8] = -1.f; r.J[9] = -a2[1]; r.J[10] = a2[0]; }
-                r.c = cb[2];
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                float ax1[3], pv[3], qv[3], ax2[3], bv[3];
-                mul_R_v(ax1, p0.R, jc.axis1);
-                plane_space(ax1, pv, qv);
-                if (has_b1) mul_R_v(ax2, p1.R, jc.axis2);
-                else { ax2[0] = jc.axis2[0]; ax2[1] = jc.axis2[1]; ax2[2] = jc.axis2[2]; }
-                cross3(bv, ax1, ax2);
-                row_init(r, P.cfm);
-                r.J[3] = pv[0]; r.J[4] = pv[1]; r.J[5] = pv[2];
-                if (has_b1) { r.J[9] = -pv[0]; r.J[10] = -pv[1]; r.J[11] = -pv[2]; }
-                r.c = kerp * dot3(bv, pv);
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                row_init(r, P.cfm);
-                r.J[3] = qv[0]; r.J[4] = qv[1]; r.J[5] = qv[2];
-                if (has_b1) { r.J[9] = -qv[0]; r.J[10] = -qv[1]; r.J[11] = -qv[2]; }
-                r.c = kerp * dot3(bv, qv);
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                mrows = 5;
-                LimotState st;
-                joint_limit_state(jc, p0, p1, st);
-                row_init(r, P.cfm);
-                if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 1, p0, p1,
-                                  has_b1)) {
-                    emit_row(P, S, w, tid, nhead++, r, pc);
-                    limot_row = 5;
-                    mrows = 6;
-                }
-            } else if (jc.type == 4 || jc.type == 5) {
-                // ---- ball (ODE ball.cpp getInfo2: setBall with the joint's own erp / cfm) and universal
-                // (universal.cpp getInfo2: setBall + one angular row along ax1 x ax2 + two limot rows)
-                float a1[3], a2[3], cb[3];
-                const float kb = hinv * (jc.type == 4 ? jc.erp : P.erp);
-                mul_R_v(a1, p0.R, jc.anchor1);
-                if (has_b1) {
-                    mul_R_v(a2, p1.R, jc.anchor2);
-#pragma unroll
-                    for (int i = 0; i < 3; i++) cb[i] = kb * (a2[i] + p1.pos[i] - a1[i] - p0.pos[i]);
-                } else {
-                    a2[0] = a2[1] = a2[2] = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 3; i++) cb[i] = kb * (jc.anchor2[i] - a1[i] - p0.pos[i]);
-                }
-                const float bcfm = jc.type == 4 ? jc.cfm : P.cfm;
-                row_init(r, bcfm);
-                r.J[0] = 1.f; r.J[4] = a1[2]; r.J[5] = -a1[1];
-                if (has_b1) { r.J[6] = -1.f; r.J[10] = -a2[2]; r.J[11] = a2[1]; }
-                r.c = cb[0];
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                row_init(r, bcfm);
-                r.J[1] = 1.f; r.J[3] = -a1[2]; r.J[5] = a1[0];
-                if (has_b1) { r.J[7] = -1.f; r.J[9] = a2[2]; r.J[11] = -a2[0]; }
-                r.c = cb[1];
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                row_init(r, bcfm);
-                r.J[2] = 1.f; r.J[3] = a1[1]; r.J[4] = -a1[0];
-                if (has_b1) { r.J[8] = -1.f; r.J[9] = -a2[1]; r.J[10] = a2[0]; }
-                r.c = cb[2];
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                mrows = 3;
-                if (jc.type == 5) {
-                    float ax1[3], ax2[3], ax2t[3], pv[3];
-                    universal_axes(jc, p0, p1, has_b1, ax1, ax2);
-                    const float k = dot3(ax1, ax2);
-#pragma unroll
-                    for (int i = 0; i < 3; i++) ax2t[i] = ax2[i] - k * ax1[i];
-                    cross3(pv, ax1, ax2t);
-                    normalize3(pv);
-                    row_init(r, P.cfm);
-                    r.J[3] = pv[0]; r.J[4] = pv[1]; r.J[5] = pv[2];
-                    if (has_b1) { r.J[9] = -pv[0]; r.J[10] = -pv[1]; r.J[11] = -pv[2]; }
-                    r.c = kerp * -k;
-                    emit_row(P, S, w, tid, nhead++, r, pc);
-                    mrows = 4;
-                    LimotState st, st2;
-                    joint_limit_state(jc, p0, p1, st);
-                    joint_limit_state2(jc, p0, p1, st2);
-                    row_init(r, P.cfm);
-                    if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 1, p0, p1,
-                                      has_b1)) {
-                        emit_row(P, S, w, tid, nhead++, r, pc);
-                        limot_row = mrows;
-                        mrows++;
-                    }
-                    row_init(r, P.cfm);
-                    if (add_limot_row(P, jc.limot2, G(P.jcmd, j * 4 + 2), G(P.jcmd, j * 4 + 3), st2, r, ax2, 1, p0, p1,
-                                      has_b1)) {
-                        emit_row(P, S, w, tid, nhead++, r, pc);
-                        if (limot_row < 0) limot_row = mrows;
-                        mrows++;
-                    }
-                }
-            } else if (jc.type == 6) {
-                // ---- fixed (ODE fixed.cpp getInfo2): rows 0-2 position, rows 3-5 orientation
-                float ofs[3], cl[3], ca[3];
-                mul_R_v(ofs, p0.R, jc.offset);
-                const float k = hinv * jc.erp;
-                if (has_b1) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) cl[i] = k * (p1.pos[i] - p0.pos[i] + ofs[i]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) cl[i] = k * (jc.offset[i] - p0.pos[i]);
-                }
-                fixed_orientation_rhs(jc, p0, p1, has_b1, hinv * P.erp * 2.f, ca);
-                row_init(r, P.cfm);
-                r.J[0] = 1.f;
-                if (has_b1) { r.J[4] = -ofs[2]; r.J[5] = ofs[1]; r.J[6] = -1.f; }
-                r.c = cl[0]; r.cfm = jc.cfm;
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                row_init(r, P.cfm);
-                r.J[1] = 1.f;
-                if (has_b1) { r.J[3] = ofs[2]; r.J[5] = -ofs[0]; r.J[7] = -1.f; }
-                r.c = cl[1]; r.cfm = jc.cfm;
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                row_init(r, P.cfm);
-                r.J[2] = 1.f;
-                if (has_b1) { r.J[3] = -ofs[1]; r.J[4] = ofs[0]; r.J[8] = -1.f; }
-                r.c = cl[2]; r.cfm = jc.cfm;
-                emit_row(P, S, w, tid, nhead++, r, pc);
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    row_init(r, P.cfm);
-                    r.J[3 + i] = 1.f;
-                    if (has_b1) r.J[9 + i] = -1.f;
-                    r.c = ca[i];
-                    emit_row(P, S, w, tid, nhead++, r, pc);
-                }
-                mrows = 6;
-            } else if (jc.type == 3) {
-                // ---- slider (ODE slider.cpp getInfo2)
-                float ca[3];
-                fixed_orientation_rhs(jc, p0, p1, has_b1, hinv * P.erp * 2.f, ca);
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    row_init(r, P.cfm);
-                    r.J[3 + i] = 1.f;
-                    if (has_b1) r.J[9 + i] = -1.f;
-                    r.c = ca[i];
-                    emit_row(P, S, w, tid, nhead++, r, pc);
-                }
-                float c[3] = {0.f, 0.f, 0.f}, ax1[3], pv[3], qv[3];
-                if (has_b1) {
-#pragma unroll
-                    for (int i = 0; i < 3; i++) c[i] = p1.pos[i] - p0.pos[i];
-                }
-                mul_R_v(ax1, p0.R, jc.axis1);
-                plane_space(ax1, pv, qv);
-                float c3, c4, tp[3], tq[3];
-                if (has_b1) {
-                    cross3(tp, c, pv);
-                    cross3(tq, c, qv);
-                    float ofs[3];
-                    mul_R_v(ofs, p1.R, jc.offset);
-#pragma unroll
-                    for (int i = 0; i < 3; i++) c[i] += ofs[i];
-                    c3 = kerp * dot3(pv, c);
-                    c4 = kerp * dot3(qv, c);
-                } else {
-                    float ofs[3];
-#pragma unroll
-                    for (int i = 0; i < 3; i++) ofs[i] = jc.offset[i] - p0.pos[i];
-                    c3 = kerp * dot3(pv, ofs);
-                    c4 = kerp * dot3(qv, ofs);
-                    if (jc.reverse) {
-#pragma unroll
-                        for (int i = 0; i < 3; i++) ax1[i] = -ax1[i];
-                    }
-                }
-                row_init(r, P.cfm);
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    r.J[i] = pv[i];
-                    if (has_b1) { r.J[3 + i] = 0.5f * tp[i]; r.J[9 + i] = 0.5f * tp[i]; r.J[6 + i] = -pv[i]; }
-                }
-                r.c = c3;
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                row_init(r, P.cfm);
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    r.J[i] = qv[i];
-                    if (has_b1) { r.J[3 + i] = 0.5f * tq[i]; r.J[9 + i] = 0.5f * tq[i]; r.J[6 + i] = -qv[i]; }
-                }
-                r.c = c4;
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                mrows = 5;
-                LimotState st;
-                joint_limit_state(jc, p0, p1, st);
-                row_init(r, P.cfm);
-                if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 0, p0, p1,
-                                  has_b1)) {
-                    emit_row(P, S, w, tid, nhead++, r, pc);
-                    limot_row = 5;
-                    mrows = 6;
-                }
-            } else if (jc.type == 2 && has_b1) {
-                // ---- hinge2 (ODE hinge2.cpp getInfo2): setBall2 along axis1 + one angular row + limots
-                float ax1[3], ax2[3], qv[3];
-                mul_R_v(ax1, p0.R, jc.axis1);
-                mul_R_v(ax2, p1.R, jc.axis2);
-                cross3(qv, ax1, ax2);
-                const float sn = sqrtf(dot3(qv, qv));
-                const float cs = dot3(ax1, ax2);
-                normalize3(qv);
-                float q1[3], q2[3], a1[3], a2[3], d[3];
-                plane_space(ax1, q1, q2);
-                mul_R_v(a1, p0.R, jc.anchor1);
-                mul_R_v(a2, p1.R, jc.anchor2);
-                float a1w[3];
-#pragma unroll
-                for (int i = 0; i < 3; i++) a1w[i] = a1[i] + p0.pos[i];
-#pragma unroll
-                for (int i = 0; i < 3; i++) d[i] = a2[i] + p1.pos[i] - a1w[i];
-                const float k1 = hinv * jc.susp_erp;
-                const float *dirs[3] = {ax1, q1, q2};
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    row_init(r, P.cfm);
-                    const float *dv = dirs[i];
-                    r.J[0] = dv[0]; r.J[1] = dv[1]; r.J[2] = dv[2];
-                    cross3(r.J + 3, a1, dv);
-                    r.J[6] = -dv[0]; r.J[7] = -dv[1]; r.J[8] = -dv[2];
-                    cross3(r.J + 9, dv, a2);
-                    r.c = (i == 0 ? k1 : kerp) * dot3(dv, d);
-                    if (i == 0) r.cfm = jc.susp_cfm;
-                    emit_row(P, S, w, tid, nhead++, r, pc);
-                }
-                row_init(r, P.cfm);
-#pragma unroll
-                for (int i = 0; i < 3; i++) { r.J[3 + i] = qv[i]; r.J[9 + i] = -qv[i]; }
-                r.c = kerp * (jc.c0 * sn - jc.s0 * cs);
-                emit_row(P, S, w, tid, nhead++, r, pc);
-                mrows = 4;
-                LimotState st;
-                joint_limit_state(jc, p0, p1, st);
-                row_init(r, P.cfm);
-                if (add_limot_row(P, jc.limot1, G(P.jcmd, j * 4 + 0), G(P.jcmd, j * 4 + 1), st, r, ax1, 1, p0, p1,
-                                  true)) {
-                    emit_row(P, S, w, tid, nhead++, r, pc);
-                    limot_row = mrows;
-                    mrows++;
-                }
-                LimotState st2;
-                st2.limit = 0;
-                st2.limit_err = 0.f;
-                row_init(r, P.cfm);
-                if (add_limot_row(P, jc.limot2, G(P.jcmd, j * 4 + 2), G(P.jcmd, j * 4 + 3), st2, r, ax2, 1, p0, p1,
-                                  true)) {
-                    emit_row(P, S, w, tid, nhead++, r, pc);
-                    if (limot_row < 0) limot_row = mrows;
-                    mrows++;
+            LimotCmd cmd = {0.f, 0.f, 0.f, 0.f};
+            if (jc.type != 6 && jc.type != 4) {
+                cmd.vel1 = G(P.jcmd, j * 4 + 0);
+                cmd.fmax1 = G(P.jcmd, j * 4 + 1);
+                if (jc.type == 2 || jc.type == 5) {
+                    cmd.vel2 = G(P.jcmd, j * 4 + 2);
+                    cmd.fmax2 = G(P.jcmd, j * 4 + 3);
                 }
             }
+            auto emit = [&](const Row &r) { emit_row(P, S, w, tid, nhead++, r, pc); };
+            jr = joint_rows<true>(P, jc, p0, p1, cmd, 0, w, emit);
         }
-        G(P.jrows, j) = (uint8_t)(mrows | ((limot_row + 1) << 4));
+        // rows of the joint | which limit / motor rows exist (b2p_rows.cuh); the integrate kernel follows it
+        G(P.jrows, j) = (uint8_t)jr;
     }
 
     // ---- contacts (ODE contact.cpp getInfo1/getInfo2 for the mode bits Frame::addContact sets)
@@ -807,7 +461,10 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
                 }
             }
         }
-        G(P.cmap, c) = (uint32_t)(row | (depmask << 3)) | ((uint32_t)nslot << 8) | ((uint32_t)tslot << 16);
+        // rows | dependent-row mask << 3 | slot of the normal row << 8 | first dependent slot << 16 | friction row 1 / 2
+        // present << 24 / 25 (the integrate kernel rebuilds the contact's feedback from it)
+        G(P.cmap, c) = (uint32_t)(row | (depmask << 3)) | ((uint32_t)nslot << 8) | ((uint32_t)tslot << 16) |
+                       ((uint32_t)(fr1 ? 1 : 0) << 24) | ((uint32_t)(fr2 ? 1 : 0) << 25);
     }
     // rows of the step | independent rows << 16 (ODE sweeps [0,nhead) and [nhead,m) as separate partitions)
     G(P.nrows, 0) = ntail | (nhead_total << 16);

@@ -1040,7 +1040,7 @@ template <bool SAMPLED> __global__ void __launch_bounds__(CBD) b2p_collide_kerne
             saabb[(size_t)(g * 6 + 3 + k) * CBD + tid] = e[k];
         }
     }
-    int total = 0, npairs = 0;
+    int total = 0, npairs = 0, dropped = 0;
     for (int i = 0; i < ng; i++) {
         const DevGeom &gi = s_geoms[i];
         for (int j = i + 1; j < ng; j++) {
@@ -1091,7 +1091,10 @@ template <bool SAMPLED> __global__ void __launch_bounds__(CBD) b2p_collide_kerne
             if (mu != mu2) mode |= 0x001;
             const int ids = (g1.body & 0xff) | ((g2.body < 0 ? 0xff : g2.body) << 8);
             for (int k = 0; k < n; k++) {
-                if (total >= maxc) break;
+                if (total >= maxc) {
+                    dropped += n - k;
+                    break;
+                }
                 const int f = total * B2P_CONTACT_FIELDS;
                 G(P.crec, f + CR_IDS) = __int_as_float(ids);
                 G(P.crec, f + CR_PX) = pts[k].pos[0];
@@ -1115,6 +1118,9 @@ template <bool SAMPLED> __global__ void __launch_bounds__(CBD) b2p_collide_kerne
     }
     G(P.ccount, 0) = total;
     if (P.npairs) G(P.npairs, 0) = npairs;
+    // the stream holds at most maxc contacts per world; what did not fit is counted so that the host can tell
+    // (b2p_contacts_dropped) instead of seeing a full but plausible stream
+    if (dropped && P.dropped) atomicAdd(P.dropped, dropped);
 }
 
 } // namespace

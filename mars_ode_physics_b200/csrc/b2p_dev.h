@@ -8,7 +8,7 @@
 //   jcmd    float[nj*4][Wp]    vel1 fmax1 vel2 fmax2              (dParamVel / dParamFMax)
 //   jobs    float[nj*4][Wp]    angle1 rate1 angle2 rate2          (dJointGet*Angle / *Rate)
 //   jfb     float[nj*13][Wp]   f1 t1 f2 t2 lambda                 (dJointFeedback)
-//   jrows   uint8[nj][Wp]      rows used by each joint in the last step
+//   jrows   uint8[nj][Wp]      rows used by each joint in the last step | limit/motor row 1 present<<3 | row 2<<4
 //   ccount  int[Wp]            contacts in the stream of each world
 //   crec    float[maxc*16][Wp] the 16-word contact record         (dContact subset)
 //   cfb     float[maxc*3][Wp]  contact feedback f1
@@ -20,7 +20,9 @@
 //                              all-zero row for every world.  ROW_UNIT(rows, slot, u, Wp, w) addresses a unit
 //   lambda  float[maxrows][Wp] scaled multipliers by slot;  rowS float[maxrows][Wp]  sqrt(Ad) by slot
 //   fcacc   float[nb*6][Wp]    M^-1/2 J^T lambda after the last sweep;  invIw float[nb*9][Wp]
-//   cmap    uint32[maxc][Wp]   rows | depmask<<3 | slot of the normal row<<8 | first dependent slot<<16
+//   cmap    uint32[maxc][Wp]   rows | depmask<<3 | slot of the normal row<<8 | first dependent slot<<16 | fr1<<24 | fr2<<25
+//   bodyx   float[nb*15][Wp]   last_l_vel3 last_a_vel3 l_acc3 a_acc3 contact_force3   (Frame::update)
+//   jupd    float[nj*7][Wp]    motor_torque axis1_torque3 joint_load3                 (Joint::update)
 #pragma once
 #include <stdint.h>
 
@@ -58,6 +60,8 @@ struct DevBody {
     // symmetric square roots (body frame) used by the mass-scaled row form: J~ = J M^-1/2
     float sqrtInvMass, sqrtMass;
     float sqrtInvI[9], sqrtI[9];
+    // Frame::update (src/objects/Frame.cpp:899-943): multiplicative velocity damping applied after the step when < 1
+    float lin_damp, ang_damp;
 };
 
 struct DevJoint {
@@ -69,6 +73,8 @@ struct DevJoint {
     float c0, s0, v1[3], v2[3], w1[3], w2[3], susp_erp, susp_cfm;
     float erp, cfm; // fixed / ball joint
     float qrel2[4]; // universal: body 2 against the cross (qrel = body 1 against the cross)
+    float friction; // Joint::applyJointFriction coefficient (src/joints/Joint.cpp:1031-1063); <= 0: off
+    float pad3[3];
 };
 
 struct DevGeom {
@@ -109,7 +115,7 @@ struct StepParams {
     float *state, *force, *jcmd, *jobs, *jfb, *crec, *cfb, *lambda, *rowS, *invIw, *fcacc;
     float4 *rows;   // [slot][2][Wp] units of two float4; slot = position in ODE's initial order (+ the zero row)
     uint32_t *cmap; // [maxc][Wp]
-    uint8_t *jrows; // [nj][Wp]: rows of joint j | (local limit/motor row + 1) << 4
+    uint8_t *jrows; // [nj][Wp]: rows of joint j | limit/motor row of axis 1 present << 3 | of axis 2 << 4
     int *ccount;
     int *nrows;
     uint32_t *seed;
@@ -118,6 +124,9 @@ struct StepParams {
     int *hw_rows;       // device counter: largest row count of any world so far
     int sor_warps;      // Tensor-Memory SOR kernel: warps per CTA (4 or 8); rows_resident = its overflow pool units
     int worlds_per_cta; // Tensor-Memory SOR kernel: worlds a CTA takes (multiple of 32, <= 32 * sor_warps)
+    // post-step outputs of the reference's stepTheWorld for every world (null: not wanted)
+    float *bodyx; // [nb*15][Wp] last_l_vel3 last_a_vel3 l_acc3 a_acc3 contact_force3  (Frame::update, computeContactForce)
+    float *jupd;  // [nj*7][Wp]  motor_torque axis1_torque3 joint_load3              (Joint::update)
 };
 
 // unit u (0, 1) of the row in `slot` of world w: a pointer to two consecutive float4
@@ -131,4 +140,5 @@ struct CollideParams {
     int *pairs; // optional debug: int[maxpairs][Wp] packed g1 | g2<<16, or null
     int *npairs;
     int maxpairs;
+    int *dropped; // one counter per arena: contacts found beyond maxc (they are dropped in pair order), or null
 };

@@ -1,17 +1,23 @@
-// b2p_integrate.cu -- kernel 3 of the step: velocity update, dxStepBody, joint / contact feedback and
-// joint observations (sm_100a).
+// b2p_integrate.cu -- kernel 3 of the step: joint / contact feedback, velocity update, dxStepBody, joint
+// observations and the reference's post-step bookkeeping for every world (sm_100a).
 //
 // One thread per world, world-fastest SoA accesses.  It finishes dWorldQuickStep as the reference calls
 // it at src/WorldPhysics.cpp:365 (ODE 0.16 quickstep.cpp stage 6: v += h*(invM*fe + invM J^T lambda);
-// util.cpp dxStepBody with the angular-speed cap and the finite-rotation quaternion update) and produces
-// what the reference reads right after the step:
-//   dJointFeedback f1 t1 f2 t2 and the patched `lambda`  (src/joints/Joint.cpp:859-1019, :900)
-//   the contact joint's feedback f1                       (src/objects/Frame.cpp:159-171)
-//   dJointGet*Angle / *Rate / SliderPosition              (src/joints/Joint.cpp:355-415,1072-1102)
+// util.cpp dxStepBody with the angular-speed cap and the finite-rotation quaternion update) and then does what
+// WorldPhysics::stepTheWorld does after the ODE call (src/WorldPhysics.cpp:372-397), for ALL worlds:
+//   dJointFeedback f1 t1 f2 t2 and the patched `lambda`      (src/joints/Joint.cpp:268,900)
+//   the contact joints' feedback f1 and its sum per frame     (src/objects/Frame.cpp:159-171)
+//   dJointGet*Angle / *Rate / SliderPosition                  (src/joints/Joint.cpp:355-415,1072-1102)
+//   Joint::update: motor torque, axis torque, joint load      (src/joints/Joint.cpp:859-1019)
+//   Joint::applyJointFriction: force / torque for the NEXT step (src/joints/Joint.cpp:1031-1063)
+//   Frame::update: finite-difference accelerations, damping   (src/objects/Frame.cpp:899-943)
 //
-// The SOR kernel leaves fch = M^-1/2 J^T lambda and lam' = lambda/sqrt(Ad) (see b2p_assemble.cu), so
-//   invM J^T lambda = M^-1/2 fch,   lambda * J = lam' * Jh * M^1/2   (the sqrt(Ad) factors cancel).
-#include "b2p_kern.cuh"
+// Feedback without a second pass over the rows: lambda * J is accumulated while the joint's Jacobian is rebuilt
+// from the pre-step poses by the same code that assembled it (b2p_rows.cuh, FULL = false); a contact's f1 is
+// lambda_n n + lambda_1 t1 + lambda_2 t2 with the tangents of dPlaneSpace(n).  The SOR kernel leaves
+// fch = M^-1/2 J^T lambda and lam' = lambda / sqrt(Ad) (see b2p_assemble.cu), so invM J^T lambda = M^-1/2 fch and
+// lambda = lam' * sqrt(Ad) (rowS).
+#include "b2p_rows.cuh"
 
 namespace {
 
@@ -42,15 +48,100 @@ __device__ __forceinline__ void sym_mul(float *o, const float *S, const float *v
 
 __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevTemplate *__restrict__ T = P.T;
     const int nb = T->nb, nj = T->nj, maxc = T->maxc;
-    float *const s_si = (float *)smem_raw; // [nb*6][BD] symmetric sqrt(I_world) of the pre-step pose
     const int tid = threadIdx.x;
     const int w = blockIdx.x * BD + tid;
     if (w >= P.W) return;
     const int Wp = P.Wp;
     const float h = P.h;
+
+    // ---------------- joint feedback from the pre-step poses: sum of lambda * J over the joint's rows --------
+    {
+        int slot = 0;
+        for (int j = 0; j < nj; j++) {
+            const DevJoint &jc = T->joints[j];
+            const int jr = G(P.jrows, j);
+            const int mrows = B2P_JR_ROWS(jr);
+            float acc[12];
+#pragma unroll
+            for (int q = 0; q < 12; q++) acc[q] = 0.f;
+            float flam = 0.f;
+            if (jc.b0 >= 0 && mrows > 0) {
+                BodyPose p0, p1;
+                load_pose(P, jc.b0, w, p0);
+                if (jc.b1 >= 0) load_pose(P, jc.b1, w, p1);
+                // `lambda` of the patched dJointFeedback: the multiplier of the joint's first limit / motor row
+                const int nl = ((jr & B2P_JR_L1) ? 1 : 0) + ((jr & B2P_JR_L2) ? 1 : 0);
+                const int first_limot = nl ? mrows - nl : -1;
+                int k = 0;
+                auto emit = [&](const Row &r) {
+                    const float lam = G(P.lambda, slot + k) * G(P.rowS, slot + k);
+#pragma unroll
+                    for (int q = 0; q < 12; q++) acc[q] += r.J[q] * lam;
+                    if (k == first_limot) flam = lam;
+                    k++;
+                };
+                const LimotCmd cmd = {0.f, 0.f, 0.f, 0.f};
+                joint_rows<false>(P, jc, p0, p1, cmd, jr, w, emit);
+            }
+            slot += mrows;
+#pragma unroll
+            for (int q = 0; q < 12; q++) G(P.jfb, j * 13 + q) = acc[q];
+            G(P.jfb, j * 13 + 12) = flam;
+        }
+    }
+
+    // ---------------- contact feedback f1, and its sum per body (Frame::computeContactForce) ----------------
+    const bool frame_out = P.bodyx != nullptr;
+    if (frame_out) {
+        for (int b = 0; b < nb; b++) {
+            G(P.bodyx, b * 15 + 12) = 0.f;
+            G(P.bodyx, b * 15 + 13) = 0.f;
+            G(P.bodyx, b * 15 + 14) = 0.f;
+        }
+    }
+    {
+        int nc = G(P.ccount, 0);
+        if (nc > maxc) nc = maxc;
+        for (int c = 0; c < nc; c++) {
+            const uint32_t cm = G(P.cmap, c);
+            const int depmask = (cm >> 3) & 31;
+            int hs = (cm >> 8) & 0xff, ts = (cm >> 16) & 0xff;
+            const bool fr1 = (cm >> 24) & 1, fr2 = (cm >> 25) & 1;
+            const int b0 = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_IDS)) & 0xff;
+            const float n[3] = {G(P.crec, c * B2P_CONTACT_FIELDS + CR_NX), G(P.crec, c * B2P_CONTACT_FIELDS + CR_NY),
+                                G(P.crec, c * B2P_CONTACT_FIELDS + CR_NZ)};
+            float t1[3], t2[3];
+            plane_space(n, t1, t2);
+            const float ln = G(P.lambda, hs) * G(P.rowS, hs);
+            hs++;
+            float f[3] = {n[0] * ln, n[1] * ln, n[2] * ln};
+            int k = 1;
+            if (fr1) {
+                const int s = (depmask & (1 << (k - 1))) ? ts++ : hs++;
+                const float l1 = G(P.lambda, s) * G(P.rowS, s);
+#pragma unroll
+                for (int i = 0; i < 3; i++) f[i] += t1[i] * l1;
+                k++;
+            }
+            if (fr2) {
+                const int s = (depmask & (1 << (k - 1))) ? ts++ : hs++;
+                const float l2 = G(P.lambda, s) * G(P.rowS, s);
+#pragma unroll
+                for (int i = 0; i < 3; i++) f[i] += t2[i] * l2;
+            }
+            // (rolling rows have no linear part)
+            G(P.cfb, c * 3 + 0) = f[0];
+            G(P.cfb, c * 3 + 1) = f[1];
+            G(P.cfb, c * 3 + 2) = f[2];
+            if (frame_out) {
+                G(P.bodyx, b0 * 15 + 12) += f[0];
+                G(P.bodyx, b0 * 15 + 13) += f[1];
+                G(P.bodyx, b0 * 15 + 14) += f[2];
+            }
+        }
+    }
 
     // ---------------- velocity update + dxStepBody ----------------
     for (int b = 0; b < nb; b++) {
@@ -70,9 +161,6 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
             fch[k] = G(P.fcacc, b * 6 + k);
         }
         q_to_R(q, R);
-        sym6_from(S6, R, bc.sqrtI, tmp);
-#pragma unroll
-        for (int k = 0; k < 6; k++) s_si[(size_t)(b * 6 + k) * BD + tid] = S6[k];
         // v += h * M^-1/2 fch
         sym6_from(S6, R, bc.sqrtInvI, tmp);
         sym_mul(t3, S6, fch + 3);
@@ -120,79 +208,18 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
         for (int k = 0; k < 6; k++) G(P.force, b * 6 + k) = 0.f;
     }
 
-    // ---------------- joint feedback: lambda * J = lam' * Jh * M^1/2 ----------------
-    int slot = 0;
-    for (int j = 0; j < nj; j++) {
-        const DevJoint &jc = T->joints[j];
-        const int jr = G(P.jrows, j);
-        const int mrows = jr & 7, lrow = (jr >> 4) - 1;
-        float acc[12];
-#pragma unroll
-        for (int q = 0; q < 12; q++) acc[q] = 0.f;
-        float flam = 0.f;
-        for (int k = 0; k < mrows; k++, slot++) {
-            const F8 u0 = ldg256(ROW_UNIT(P.rows, slot, 0, Wp, w));
-            const float4 j0 = u0.lo, j1 = u0.hi, j2 = __ldg(ROW_UNIT(P.rows, slot, 1, Wp, w));
-            const float lam = G(P.lambda, slot);
-            // row layout (b2p_assemble.cu emit_row): J0..J7 | J8..J11 scalars
-            acc[0] += j0.x * lam; acc[1] += j0.y * lam; acc[2] += j0.z * lam; acc[3] += j0.w * lam;
-            acc[4] += j1.x * lam; acc[5] += j1.y * lam; acc[6] += j1.z * lam; acc[7] += j1.w * lam;
-            acc[8] += j2.x * lam; acc[9] += j2.y * lam; acc[10] += j2.z * lam; acc[11] += j2.w * lam;
-            if (k == lrow) flam = lam * G(P.rowS, slot);
-        }
-        float data[12];
-#pragma unroll
-        for (int q = 0; q < 12; q++) data[q] = 0.f;
-        if (jc.b0 >= 0 && mrows > 0) {
-            float S6[6];
-            const float sm0 = T->bodies[jc.b0].sqrtMass;
-#pragma unroll
-            for (int k = 0; k < 6; k++) S6[k] = s_si[(size_t)(jc.b0 * 6 + k) * BD + tid];
-            data[0] = sm0 * acc[0]; data[1] = sm0 * acc[1]; data[2] = sm0 * acc[2];
-            sym_mul(data + 3, S6, acc + 3);
-            if (jc.b1 >= 0) {
-                const float sm1 = T->bodies[jc.b1].sqrtMass;
-#pragma unroll
-                for (int k = 0; k < 6; k++) S6[k] = s_si[(size_t)(jc.b1 * 6 + k) * BD + tid];
-                data[6] = sm1 * acc[6]; data[7] = sm1 * acc[7]; data[8] = sm1 * acc[8];
-                sym_mul(data + 9, S6, acc + 9);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 12; q++) G(P.jfb, j * 13 + q) = data[q];
-        G(P.jfb, j * 13 + 12) = flam;
-    }
-    // ---------------- contact feedback f1 ----------------
-    int nc = G(P.ccount, 0);
-    if (nc > maxc) nc = maxc;
-    for (int c = 0; c < nc; c++) {
-        const uint32_t cm = G(P.cmap, c);
-        const int rows_c = cm & 7, depmask = (cm >> 3) & 31;
-        int hs = (cm >> 8) & 0xff, ts = (cm >> 16) & 0xff;
-        const int b0 = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_IDS)) & 0xff;
-        float f[3] = {0.f, 0.f, 0.f};
-        for (int k = 0; k < rows_c; k++) {
-            const int s = (k > 0 && (depmask & (1 << (k - 1)))) ? ts++ : hs++;
-            const float4 j0 = __ldg(ROW_UNIT(P.rows, s, 0, Wp, w));
-            const float lam = G(P.lambda, s);
-            f[0] += j0.x * lam;
-            f[1] += j0.y * lam;
-            f[2] += j0.z * lam;
-        }
-        const float sm0 = T->bodies[b0].sqrtMass;
-        G(P.cfb, c * 3 + 0) = sm0 * f[0];
-        G(P.cfb, c * 3 + 1) = sm0 * f[1];
-        G(P.cfb, c * 3 + 2) = sm0 * f[2];
-    }
-
-    // ---------------- joint observations from the new state ----------------
+    // ---------------- joint observations, Joint::update and applyJointFriction from the new state -----------
     for (int j = 0; j < nj; j++) {
         const DevJoint &jc = T->joints[j];
         float a1 = 0.f, r1 = 0.f, a2 = 0.f, r2 = 0.f;
-        if (jc.b0 >= 0 && jc.type != 6 && jc.type != 4) {
-            const bool has_b1 = jc.b1 >= 0;
-            BodyPose p0, p1;
+        float axis[3] = {0.f, 0.f, 0.f};
+        BodyPose p0, p1;
+        const bool has_b1 = jc.b1 >= 0;
+        if (jc.b0 >= 0) {
             load_pose(P, jc.b0, w, p0);
+            if (has_b1) load_pose(P, jc.b1, w, p1);
+        }
+        if (jc.b0 >= 0 && jc.type != 6 && jc.type != 4) {
             float lv0[3], av0[3], lv1[3] = {0.f, 0.f, 0.f}, av1[3] = {0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 3; k++) {
@@ -200,14 +227,12 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
                 av0[k] = G(P.state, jc.b0 * B2P_STATE_FIELDS + 10 + k);
             }
             if (has_b1) {
-                load_pose(P, jc.b1, w, p1);
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
                     lv1[k] = G(P.state, jc.b1 * B2P_STATE_FIELDS + 7 + k);
                     av1[k] = G(P.state, jc.b1 * B2P_STATE_FIELDS + 10 + k);
                 }
             }
-            float axis[3];
             mul_R_v(axis, p0.R, jc.axis1);
             if (jc.type == 1) {
                 a1 = hinge_angle(jc, p0.q, p1.q, has_b1);
@@ -240,27 +265,192 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
         G(P.jobs, j * 4 + 1) = r1;
         G(P.jobs, j * 4 + 2) = a2;
         G(P.jobs, j * 4 + 3) = r2;
+
+        // Joint::update (Joint.cpp:859-1019): motor torque = -feedback.lambda; axis torque and joint load of
+        // hinge / hinge2 / universal joints from the feedback forces and the anchor geometry of the new poses.
+        // The reference's "body1" is the first body handed to dJointAttach: b0 unless the joint is reversed.
+        if (P.jupd) {
+            float at[3] = {0.f, 0.f, 0.f}, jl[3] = {0.f, 0.f, 0.f};
+            if (jc.b0 >= 0 && (jc.type == 1 || jc.type == 2 || jc.type == 5)) {
+                float anchor[3], v1[3], normal[3], load[3], tmp1[3];
+                mul_R_v(anchor, p0.R, jc.anchor1);
+#pragma unroll
+                for (int i = 0; i < 3; i++) v1[i] = -anchor[i]; // body position - (body position + R anchor1)
+                if (!jc.reverse) {
+                    const float f1[3] = {G(P.jfb, j * 13 + 0), G(P.jfb, j * 13 + 1), G(P.jfb, j * 13 + 2)};
+                    const float t1[3] = {G(P.jfb, j * 13 + 3), G(P.jfb, j * 13 + 4), G(P.jfb, j * 13 + 5)};
+                    cross3(normal, axis, v1);
+                    float d = dot3(normal, f1);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        normal[i] *= d;
+                        load[i] = f1[i] - normal[i];
+                    }
+                    cross3(at, v1, normal);
+                    cross3(jl, v1, load);
+                    d = dot3(axis, t1);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        tmp1[i] = axis[i] * d;
+                        at[i] += tmp1[i];
+                        jl[i] += t1[i] - tmp1[i];
+                    }
+                } else {
+                    const float f2[3] = {G(P.jfb, j * 13 + 6), G(P.jfb, j * 13 + 7), G(P.jfb, j * 13 + 8)};
+                    const float t2[3] = {G(P.jfb, j * 13 + 9), G(P.jfb, j * 13 + 10), G(P.jfb, j * 13 + 11)};
+                    float d = dot3(f2, v1) / dot3(v1, v1);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) tmp1[i] = f2[i] - v1[i] * d;
+                    const float torque = sqrtf(dot3(tmp1, tmp1)) / sqrtf(dot3(v1, v1));
+                    cross3(normal, v1, tmp1);
+                    const float sc = torque / sqrtf(dot3(normal, normal));
+#pragma unroll
+                    for (int i = 0; i < 3; i++) normal[i] *= sc;
+                    d = dot3(normal, axis);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) {
+                        at[i] = axis[i] * d;
+                        jl[i] = normal[i] - at[i];
+                    }
+                    d = dot3(t2, axis);
+#pragma unroll
+                    for (int i = 0; i < 3; i++) jl[i] += t2[i] - axis[i] * d;
+                }
+            }
+            G(P.jupd, j * 7 + 0) = -G(P.jfb, j * 13 + 12);
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                G(P.jupd, j * 7 + 1 + i) = at[i];
+                G(P.jupd, j * 7 + 4 + i) = jl[i];
+            }
+        }
+
+        // Joint::applyJointFriction (Joint.cpp:1031-1063): an external force / torque on both bodies for the NEXT
+        // step; dampingTorque = getVelocityI() * -frictionCoefficient with the reference's sign rules
+        if (jc.friction > 0.f && jc.b0 >= 0) {
+            float fax[3] = {axis[0], axis[1], axis[2]}; // getAxisI: world axis 1; none for ball / fixed
+            if (jc.type == 3 && jc.reverse && !has_b1) {
+                fax[0] = -fax[0], fax[1] = -fax[1], fax[2] = -fax[2];
+            }
+            const float vel = (jc.type == 1 || jc.type == 3) ? -r1 : ((jc.type == 2 || jc.type == 5) ? r1 : 0.f);
+            const float dt_ = vel * -jc.friction;
+            const float nrm = sqrtf(dot3(fax, fax));
+            float u[3] = {0.f, 0.f, 0.f};
+            if (nrm > 0.f) {
+#pragma unroll
+                for (int i = 0; i < 3; i++) u[i] = fax[i] / nrm;
+            }
+            float sn, cs;
+            sincosf(dt_, &sn, &cs);
+#pragma unroll
+            for (int side = 0; side < 2; side++) {
+                const int body = side == 0 ? jc.b0 : jc.b1;
+                if (body < 0) continue;
+                const BodyPose &bp = side == 0 ? p0 : p1;
+                float pos[3], ux[3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) pos[i] = bp.pos[i] - fax[i];
+                cross3(ux, u, pos);
+                const float ud = dot3(u, pos);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const float rot = pos[i] * cs + ux[i] * sn + u[i] * ud * (1.f - cs);
+                    G(P.force, body * 6 + i) += rot - pos[i];
+                    G(P.force, body * 6 + 3 + i) += u[i] * dt_;
+                }
+            }
+        }
     }
+
+    // ---------------- Frame::update (Frame.cpp:899-943): accelerations by finite differences, damping -------
+    for (int b = 0; b < nb; b++) {
+        const DevBody &bc = T->bodies[b];
+        const bool damp_l = bc.lin_damp < 1.f, damp_a = bc.ang_damp < 1.f;
+        if (!frame_out && !damp_l && !damp_a) continue;
+        const int f = b * B2P_STATE_FIELDS;
+        float lv[3], av[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lv[k] = G(P.state, f + 7 + k);
+            av[k] = G(P.state, f + 10 + k);
+        }
+        if (frame_out) {
+            const float hinv = 1.0f / h;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float ll = G(P.bodyx, b * 15 + k), la = G(P.bodyx, b * 15 + 3 + k);
+                G(P.bodyx, b * 15 + 6 + k) = (lv[k] - ll) * hinv;
+                G(P.bodyx, b * 15 + 9 + k) = (av[k] - la) * hinv;
+                G(P.bodyx, b * 15 + k) = lv[k];
+                G(P.bodyx, b * 15 + 3 + k) = av[k];
+            }
+        }
+        if (damp_l) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) G(P.state, f + 7 + k) = lv[k] * bc.lin_damp;
+        }
+        if (damp_a) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) G(P.state, f + 10 + k) = av[k] * bc.ang_damp;
+        }
+    }
+}
+
+// Diagnostic: the LCP residual of the last solve, per world (north-star correctness bar "constraint residual after
+// N iterations").  w = J invM J^T lambda + cfm lambda - rhs on the unscaled system, projected on the active
+// bounds exactly as the oracle does (oracle/orc_quickstep.c, "residual diagnostic").  In the scaled
+// coordinates of b2p_assemble.cu:  w_i = -(rhs' - cfm' lam' - Jh.fch) / sqrt(Ad_i).
+__global__ void __launch_bounds__(BD, 8) b2p_residual_kernel(const StepParams P, float *__restrict__ out)
+{
+    const DevTemplate *__restrict__ T = P.T;
+    const int w = blockIdx.x * BD + threadIdx.x;
+    if (w >= P.W) return;
+    const int Wp = P.Wp, R = T->maxrows, nb = T->nb;
+    const int m = G(P.nrows, 0) & 0xffff;
+    float maxres = 0.f;
+    for (int s = 0; s < m; s++) {
+        const F8 u0 = ldg256(ROW_UNIT(P.rows, s, 0, Wp, w)), u1 = ldg256(ROW_UNIT(P.rows, s, 1, Wp, w));
+        const float jv[12] = {u0.lo.x, u0.lo.y, u0.lo.z, u0.lo.w, u0.hi.x, u0.hi.y,
+                              u0.hi.z, u0.hi.w, u1.lo.x, u1.lo.y, u1.lo.z, u1.lo.w};
+        const float rhs = u1.hi.x, cfm = u1.hi.y, bound = u1.hi.z;
+        const uint32_t mt = (uint32_t)__float_as_int(u1.hi.w);
+        const int fi = (mt >> 8) & 0xff, b0 = (mt >> 16) & 0x3f, b1 = (mt >> 24) & 0x3f;
+        const float lam = G(P.lambda, s);
+        const float lam_n = fi < R ? G(P.lambda, fi) : 1.f;
+        float dotv = 0.f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) dotv += jv[k] * G(P.fcacc, b0 * 6 + k);
+        if (b1 < nb) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) dotv += jv[6 + k] * G(P.fcacc, b1 * 6 + k);
+        }
+        const float sa = G(P.rowS, s);
+        const float wi = -((rhs - lam * cfm) - dotv) / sa; // unscaled residual of row s
+        const float bnd = fabsf(bound * lam_n);
+        const float hi_act = (mt & 0x80000000u) ? 0.f : bnd;
+        const float lo_act = (mt & 0x40000000u) ? 0.f : -bnd;
+        float res;
+        if (lam <= lo_act && lo_act > -INFINITY) res = wi < 0.f ? -wi : 0.f;
+        else if (lam >= hi_act && hi_act < INFINITY) res = wi > 0.f ? wi : 0.f;
+        else res = fabsf(wi);
+        if (lo_act == hi_act) res = 0.f;
+        maxres = fmaxf(maxres, res);
+    }
+    out[w] = maxres;
 }
 
 } // namespace
 
-extern "C" size_t b2p_integrate_smem_bytes(int nb) { return sizeof(float) * (size_t)nb * 6 * BD; }
-
 extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, cudaStream_t stream)
 {
-    static size_t configured_dev[B2P_MAX_DEVICES] = {0}; // cudaFuncSetAttribute is per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    size_t &configured = configured_dev[dev % B2P_MAX_DEVICES];
-    const size_t smem = b2p_integrate_smem_bytes(nb);
-    if (smem > configured) {
-        cudaError_t e =
-            cudaFuncSetAttribute(b2p_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
     const int grid = (P->W + BD - 1) / BD;
-    b2p_integrate_kernel<<<grid, BD, smem, stream>>>(*P);
+    b2p_integrate_kernel<<<grid, BD, 0, stream>>>(*P);
+    return cudaGetLastError();
+}
+
+extern "C" cudaError_t b2p_launch_residual(const StepParams *P, float *out, cudaStream_t stream)
+{
+    const int grid = (P->W + BD - 1) / BD;
+    b2p_residual_kernel<<<grid, BD, 0, stream>>>(*P, out);
     return cudaGetLastError();
 }

@@ -102,6 +102,7 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
     // first is arbitrary and does not influence any result.
     const size_t Wp = (size_t)P.Wp;
     int w, nr;
+    bool valid; // false: a phantom thread (the CTA takes fewer than TW worlds, or reaches past the last world)
     {
         int *const s_cnt = (int *)s_pool;            // [R+2]
         int *const s_nr = s_cnt + ((R + 2 + 3) & ~3); // [TW] nrows word by sorted position
@@ -130,15 +131,19 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
         // sorted position of this thread: warps 0..3 take the four longest groups of 32, warps 4..7 the rest in
         // reverse, so that the two warps sharing a scheduler (i, i + 4) together have about the same work
         const int grp = NW == 8 && warp >= 4 ? 11 - warp : warp;
-        w = blockIdx.x * P.worlds_per_cta + s_perm[grp * 32 + lane];
+        const int src = s_perm[grp * 32 + lane];
+        w = blockIdx.x * P.worlds_per_cta + src;
         nr = s_nr[grp * 32 + lane];
+        // A phantom's index would name a world of the NEXT CTA: it must neither read that world's seed nor write
+        // its results (it sweeps zero rows only, like every position behind a world's last row)
+        valid = src < P.worlds_per_cta && w < P.W;
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tbase = s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * (TROWS * 16));
 
-    const int wl = w < P.Wp ? w : P.Wp - 1; // a CTA may reach past the padded world count: loads are clamped
+    const int wl = valid ? w : blockIdx.x * P.worlds_per_cta; // phantoms read (only zero rows of) the CTA's first world
     const int m = nr & 0xffff, nhead = nr >> 16;
     const int mmax = __reduce_max_sync(0xffffffffu, m);
 
@@ -330,7 +335,7 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
         sweep_spilled();
     }
 
-    if (w < P.W) {
+    if (valid) {
         for (int s = 0; s < m; s++) P.lambda[(size_t)s * Wp + w] = s_lam[s * TW + tid];
         for (int k = 0; k < nb * 3; k++) {
             const float2 f = s_fc[k * TW + tid];

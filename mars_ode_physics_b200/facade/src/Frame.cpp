@@ -29,6 +29,7 @@ Frame::Frame(PhysicsInterface *world, data_broker::DataBrokerInterface *, config
         angularDamping = config["angularDamping"];
     }
     world_index = 0;
+    post_step = -1;
 }
 
 Frame::~Frame(void) { clearContactData(); } // bodies live as long as the arena
@@ -51,20 +52,33 @@ void Frame::rotated_offset(const double quat[4], double out[3]) const
     for (int i = 0; i < 3; i++) out[i] = R[3 * i] * o[0] + R[3 * i + 1] * o[1] + R[3 * i + 2] * o[2];
 }
 
-// reference :159-171
-void Frame::computeContactForce()
+// reference :159-171.  The sum over the contact joints created through this frame (the ones whose first body
+// is this frame's body) is formed on the device for every world by the step's epilogue; the host only fetches
+// the active world's three numbers, and only when somebody asks for them.
+void Frame::computeContactForce() { post_step = -1; }
+void Frame::fetchPostStep() const
 {
-    Vector sum(0, 0, 0);
-    for (int c : contactIds) {
-        double f1[3];
-        b2p_contact_get_feedback(theWorld->getWorld(), world_index, c, f1);
-        sum += Vector(f1[0], f1[1], f1[2]);
-    }
-    contactForceVector = sum;
+    if (nBody < 0 || post_step == theWorld->getStepCount()) return;
+    double f[3], la[3], aa[3];
+    b2p_arena *a = theWorld->getWorld();
+    b2p_body_get_contact_force(a, nBody, world_index, f);
+    b2p_body_get_acceleration(a, nBody, world_index, la, aa);
+    contactForceVector = Vector(f[0], f[1], f[2]);
     contactForce = contactForceVector.norm();
+    l_acc = Vector(la[0], la[1], la[2]);
+    a_acc = Vector(aa[0], aa[1], aa[2]);
+    post_step = theWorld->getStepCount();
 }
-const Vector &Frame::getContactForceVector() const { return contactForceVector; }
-const sReal &Frame::getContactForce() const { return contactForce; }
+const Vector &Frame::getContactForceVector() const
+{
+    fetchPostStep();
+    return contactForceVector;
+}
+const sReal &Frame::getContactForce() const
+{
+    fetchPostStep();
+    return contactForce;
+}
 
 // reference :183-207
 void Frame::addObject(Object *object)
@@ -77,6 +91,7 @@ void Frame::addObject(Object *object)
         checkB2P(nBody, "Frame::addObject");
         b2p_body_set_position(a, nBody, B2P_ALL_WORLDS, position.x(), position.y(), position.z());
         b2p_body_set_quaternion(a, nBody, B2P_ALL_WORLDS, q.w(), q.x(), q.y(), q.z());
+        b2p_body_set_damping(a, nBody, linearDamping, angularDamping); // applied by the step's epilogue (:922-941)
     }
     addObjectMass(object);
 }
@@ -185,7 +200,14 @@ void Frame::getTorque(Vector *v) const
 void Frame::getLinearAcceleration(Vector *v) const
 {
     MutexLocker locker(&(theWorld->iMutex));
+    fetchPostStep();
     *v = l_acc;
+}
+void Frame::getAngularAcceleration(Vector *v) const
+{
+    MutexLocker locker(&(theWorld->iMutex));
+    fetchPostStep();
+    *v = a_acc;
 }
 
 int Frame::getBody() const { return nBody; }
@@ -201,6 +223,7 @@ int Frame::acquireBody()
         checkB2P(nBody, "Frame::acquireBody");
         b2p_body_set_position(a, nBody, B2P_ALL_WORLDS, position.x(), position.y(), position.z());
         b2p_body_set_quaternion(a, nBody, B2P_ALL_WORLDS, q.w(), q.x(), q.y(), q.z());
+        b2p_body_set_damping(a, nBody, linearDamping, angularDamping);
         nMass.setSphereTotal(0.01, 0.01);
         b2p_body_set_mass(a, nBody, nMass.mass, nMass.I);
     }
@@ -301,31 +324,10 @@ void Frame::getMass(sReal *mass, sReal *inertia) const
         for (int i = 0; i < 9; i++) inertia[i] = nMass.I[i];
 }
 
-// reference :899-943: finite-difference accelerations and multiplicative damping
-void Frame::update()
-{
-    if (nBody < 0) return;
-    const sReal dt = theWorld->step_size;
-    b2p_arena *a = theWorld->getWorld();
-    double lv[3], av[3];
-    b2p_body_get_linear_vel(a, nBody, world_index, lv);
-    b2p_body_get_angular_vel(a, nBody, world_index, av);
-    if (dt > 0) {
-        const Vector v(lv[0], lv[1], lv[2]), wv(av[0], av[1], av[2]);
-        l_acc = (v - last_l_vel) / dt;
-        last_l_vel = v;
-        a_acc = (wv - last_a_vel) / dt;
-        last_a_vel = wv;
-    } else {
-        l_acc = last_l_vel = Vector(0, 0, 0);
-        a_acc = last_a_vel = Vector(0, 0, 0);
-    }
-    if (linearDamping < 1.0)
-        b2p_body_set_linear_vel(a, nBody, world_index, lv[0] * linearDamping, lv[1] * linearDamping, lv[2] * linearDamping);
-    if (angularDamping < 1.0)
-        b2p_body_set_angular_vel(a, nBody, world_index, av[0] * angularDamping, av[1] * angularDamping,
-                                 av[2] * angularDamping);
-}
+// reference :899-943: finite-difference accelerations and multiplicative damping.  Both are done by the step's
+// device epilogue for every world (b2p_integrate.cu, with this frame's linearDamping / angularDamping); nothing is
+// left to do on the host but to drop the cached values of the previous step.
+void Frame::update() { post_step = -1; }
 
 void Frame::clearContactData()
 {
@@ -374,6 +376,7 @@ void Frame::addContact(const ContactData &contact)
     // bounce / motion / slip values are copied by the reference but their mode bits are never set
     if (c.mu != c.mu2) c.mode |= B2P_CONTACT_MU2;
     const int id = theWorld->createContact(c, nBody, nBody2, world_index);
+    if (id == -2) return; // capacity: already reported
     if (id < 0) {
         fprintf(stderr, "Failed to create contact for (%s) because there was already a joint between the two bodies\n",
                 getName().c_str());

@@ -33,6 +33,7 @@ public:
     virtual std::vector<std::shared_ptr<DynamicObject>> getLinkedFrames(void) override;
     void getLinearVelocity(utils::Vector *vel) const;
     void getLinearAcceleration(utils::Vector *vel) const;
+    void getAngularAcceleration(utils::Vector *vel) const;
     void getAngularVelocity(utils::Vector *vel) const;
     void getForce(utils::Vector *f) const;
     void getTorque(utils::Vector *t) const;
@@ -73,8 +74,11 @@ private:
     utils::Vector offsetPos;
     bool ground_contact;
     std::vector<int> contactIds;
-    utils::Vector contactForceVector, l_acc, a_acc, last_l_vel, last_a_vel;
-    interfaces::sReal contactForce;
+    // post-step values of the active world, fetched from the device on demand (once per step)
+    void fetchPostStep() const;
+    mutable utils::Vector contactForceVector, l_acc, a_acc;
+    mutable interfaces::sReal contactForce;
+    mutable long long post_step;
     interfaces::sReal linearDamping, angularDamping;
     int world_index;
 };

@@ -35,6 +35,7 @@ Joint::Joint(WorldPhysics *world, data_broker::DataBrokerInterface *, configmaps
     joint_created = false;
     motor_torque = 0;
     world_index = 0;
+    fetched_step = -1;
     for (double &v : feedback) v = 0;
     name << config["name"];
     if (config.hasKey("frictionCoefficient")) frictionCoefficient = config["frictionCoefficient"];
@@ -96,6 +97,8 @@ bool Joint::createJoint()
     body1 = n1 ? n1->acquireBody() : -1;
     body2 = n2 ? n2->acquireBody() : -1;
     if (!createJoint(body1, body2)) return false;
+    // Joint::applyJointFriction runs in the step's device epilogue with this coefficient (off unless > 0)
+    b2p_joint_set_friction_coefficient(theWorld->getWorld(), jointId, frictionCoefficient);
     if (n1 && n2) {
         n1->addLinkedFrame(n2);
         n2->addLinkedFrame(n1);
@@ -293,10 +296,26 @@ void Joint::unsetJointAsMotor(int axis)
     }
 }
 
-void Joint::getForce1(Vector *f) const { *f = Vector(feedback[0], feedback[1], feedback[2]); }
-void Joint::getTorque1(Vector *t) const { *t = Vector(feedback[3], feedback[4], feedback[5]); }
-void Joint::getForce2(Vector *f) const { *f = Vector(feedback[6], feedback[7], feedback[8]); }
-void Joint::getTorque2(Vector *t) const { *t = Vector(feedback[9], feedback[10], feedback[11]); }
+void Joint::getForce1(Vector *f) const
+{
+    fetchPostStep();
+    *f = Vector(feedback[0], feedback[1], feedback[2]);
+}
+void Joint::getTorque1(Vector *t) const
+{
+    fetchPostStep();
+    *t = Vector(feedback[3], feedback[4], feedback[5]);
+}
+void Joint::getForce2(Vector *f) const
+{
+    fetchPostStep();
+    *f = Vector(feedback[6], feedback[7], feedback[8]);
+}
+void Joint::getTorque2(Vector *t) const
+{
+    fetchPostStep();
+    *t = Vector(feedback[9], feedback[10], feedback[11]);
+}
 
 // Joint.cpp:1121-1146: hinge torque / slider force, sign flipped
 void Joint::setTorque(sReal torque)
@@ -321,92 +340,53 @@ void Joint::reattacheJoint(void)
     }
 }
 
-void Joint::getAxisTorque(Vector *t) const { *t = axis1_torque; }
-void Joint::getAxis2Torque(Vector *t) const { *t = axis2_torque; }
-void Joint::getJointLoad(Vector *t) const { *t = joint_load; }
-sReal Joint::getMotorTorque(void) const { return motor_torque; }
+// Joint.cpp:859-1019 (motor torque = -feedback.lambda; axis torque and joint load from the feedback forces and the
+// anchor geometry) and :1031-1063 (joint friction for the next tick) run in the step's device epilogue for every
+// world (b2p_integrate.cu, restated in oracle/orc_post.c).  update() only invalidates the values cached for the
+// active world; the getters fetch them -- two small columns -- when they are asked for.
+void Joint::update(void) { fetched_step = -1; }
 
-static Vector cross(const Vector &a, const Vector &b)
+void Joint::fetchPostStep() const
 {
-    return Vector(a.y() * b.z() - a.z() * b.y(), a.z() * b.x() - a.x() * b.z(), a.x() * b.y() - a.y() * b.x());
-}
-static double dot(const Vector &a, const Vector &b) { return a.x() * b.x() + a.y() * b.y() + a.z() * b.z(); }
-
-// Joint.cpp:859-1019: motor torque = -feedback.lambda; axis torque and joint load from the feedback
-// forces and the anchor geometry; then the (optional) joint friction for the next tick
-void Joint::update(void)
-{
+    if (jointId < 0 || fetched_step == theWorld->getStepCount()) return;
     b2p_arena *a = theWorld->getWorld();
+    double u[7];
     b2p_joint_get_feedback(a, jointId, world_index, feedback);
-    const Vector f1(feedback[0], feedback[1], feedback[2]), t1(feedback[3], feedback[4], feedback[5]);
-    const Vector f2(feedback[6], feedback[7], feedback[8]), t2(feedback[9], feedback[10], feedback[11]);
-    motor_torque = -feedback[12];
-    axis1_torque.setZero();
-    axis2_torque.setZero();
-    joint_load.setZero();
-    if (joint_type == JOINT_TYPE_HINGE || twoAxes(joint_type)) {
-        double p[3], ax[3], bp[3];
-        b2p_joint_get_anchor(a, jointId, world_index, p);
-        b2p_joint_get_axis1(a, jointId, world_index, ax);
-        const Vector anchor(p[0], p[1], p[2]), axis(ax[0], ax[1], ax[2]);
-        if (body1 >= 0) {
-            b2p_body_get_position(a, body1, world_index, bp);
-            const Vector v1 = Vector(bp[0], bp[1], bp[2]) - anchor;
-            Vector normal = cross(axis, v1);
-            normal *= dot(normal, f1);
-            Vector load = f1 - normal;
-            axis1_torque = cross(v1, normal);
-            joint_load = cross(v1, load);
-            const Vector along = axis * dot(axis, t1);
-            axis1_torque += along;
-            joint_load += t1 - along;
-        } else if (body2 >= 0) {
-            b2p_body_get_position(a, body2, world_index, bp);
-            const Vector v1 = Vector(bp[0], bp[1], bp[2]) - anchor;
-            const Vector axis_force = v1 * (dot(f2, v1) / dot(v1, v1));
-            const Vector tang = f2 - axis_force;
-            const double torque = tang.norm() / v1.norm();
-            Vector normal = cross(v1, tang);
-            normal *= torque / normal.norm();
-            const Vector along = axis * dot(normal, axis);
-            axis1_torque = along;
-            joint_load = normal - along;
-            joint_load += t2 - axis * dot(t2, axis);
-        }
-    }
-    applyJointFriction();
+    b2p_joint_get_update(a, jointId, world_index, u);
+    motor_torque = u[0];
+    axis1_torque = Vector(u[1], u[2], u[3]);
+    axis2_torque.setZero(); // calc2 is always 0 in the reference (:880,893)
+    joint_load = Vector(u[4], u[5], u[6]);
+    fetched_step = theWorld->getStepCount();
 }
 
-void Joint::setJointFrictionCoefficient(sReal friction) { frictionCoefficient = friction; }
+void Joint::getAxisTorque(Vector *t) const
+{
+    fetchPostStep();
+    *t = axis1_torque;
+}
+void Joint::getAxis2Torque(Vector *t) const
+{
+    fetchPostStep();
+    *t = axis2_torque;
+}
+void Joint::getJointLoad(Vector *t) const
+{
+    fetchPostStep();
+    *t = joint_load;
+}
+sReal Joint::getMotorTorque(void) const
+{
+    fetchPostStep();
+    return motor_torque;
+}
+
+void Joint::setJointFrictionCoefficient(sReal friction)
+{
+    frictionCoefficient = friction;
+    if (jointId >= 0) b2p_joint_set_friction_coefficient(theWorld->getWorld(), jointId, friction);
+}
 sReal Joint::getJointFrictionCoefficient() { return frictionCoefficient; }
-
-// Joint.cpp:1031-1063 (external force/torque for the NEXT step; off unless the coefficient is > 0)
-void Joint::applyJointFriction()
-{
-    if (frictionCoefficient > 0.0) {
-        Vector axis;
-        getAxisI(&axis);
-        const sReal dampingTorque = getVelocityI() * -frictionCoefficient;
-        std::shared_ptr<Frame> n1 = parentFrame.lock(), n2 = childFrame.lock();
-        if (n1) applyJointFriction(n1, axis, dampingTorque);
-        if (n2) applyJointFriction(n2, axis, dampingTorque);
-    }
-}
-void Joint::applyJointFriction(std::shared_ptr<Frame> frame, Vector axis, sReal dampingTorque)
-{
-    const int body = frame->getBody();
-    if (body < 0) return;
-    b2p_arena *a = theWorld->getWorld();
-    double bp[3];
-    b2p_body_get_position(a, body, world_index, bp);
-    Vector pos(bp[0], bp[1], bp[2]);
-    pos -= axis;
-    const Quaternion rot = angleAxisToQuaternion(dampingTorque, axis);
-    const Vector force = rot * pos - pos;
-    const Vector torque = axis.normalized() * dampingTorque;
-    b2p_body_add_force(a, body, world_index, force.x(), force.y(), force.z());
-    b2p_body_add_torque(a, body, world_index, torque.x(), torque.y(), torque.z());
-}
 
 sReal Joint::getVelocity(void) const
 {

@@ -76,14 +76,17 @@ protected:
     WorldPhysics *theWorld;
     configmaps::ConfigMap config;
     int jointId;
-    double feedback[13];
+    mutable double feedback[13];
     int body1, body2;
     int joint_type;
     double cfm, cfm1, cfm2, erp1, erp2;
     double lo1, lo2, hi1, hi2;
     double damping, spring, jointCFM;
-    utils::Vector axis1_torque, axis2_torque, joint_load;
-    double motor_torque;
+    // Joint::update results of the active world, fetched from the device on demand (once per step)
+    void fetchPostStep() const;
+    mutable utils::Vector axis1_torque, axis2_torque, joint_load;
+    mutable double motor_torque;
+    mutable long long fetched_step;
     double frictionCoefficient;
     std::string name;
     std::weak_ptr<Frame> parentFrame, childFrame;
@@ -92,8 +95,6 @@ protected:
     void calculateCfmErp();
     void getAxisI(utils::Vector *axis) const;
     interfaces::sReal getVelocityI(void) const;
-    void applyJointFriction();
-    void applyJointFriction(std::shared_ptr<Frame> frame, utils::Vector axis, interfaces::sReal dampingTorque);
 
 private:
     bool joint_created;

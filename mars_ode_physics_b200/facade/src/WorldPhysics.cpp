@@ -43,7 +43,9 @@ WorldPhysics::WorldPhysics() : interfaces::PhysicsInterface()
     num_worlds = 1;
     device = 0;
     max_contacts = 8;
-    warned_dense_step = false;
+    rolling_friction = true;
+    step_failed = warned_capacity = false;
+    step_count = 0;
 }
 
 WorldPhysics::~WorldPhysics(void) { freeTheWorld(); }
@@ -63,6 +65,7 @@ void WorldPhysics::initTheWorld(void)
     if (world_init) return;
     checkB2P(b2p_arena_create(num_worlds, device, &arena), "WorldPhysics::initTheWorld");
     b2p_arena_set_max_contacts(arena, max_contacts);
+    b2p_arena_enable_rolling_friction(arena, rolling_friction ? 1 : 0);
     b2p_world_rand_set_seed(arena, 11211u);
     old_gravity = world_gravity;
     old_cfm = world_cfm;
@@ -118,39 +121,47 @@ void WorldPhysics::computeContactForces()
         if (auto f = pair.second.lock()) f->computeContactForce();
 }
 
-// reference :349-421.  Only the quickstep path exists on the device; fast_step == false (dWorldStep,
-// a dense LCP) is out of scope and is served by the same quickstep kernel
-// after a one-time warning.
+// reference :349-421.  Only the quickstep path exists on the device.  fast_step == false asks for dWorldStep (the
+// dense LCP), which is not implemented: the call then steps NOTHING, raises
+// WorldPhysics::error / lastStepFailed() and says so on stderr -- it never silently substitutes quickstep.
+// Everything the reference does after the ODE call (Joint::update, Frame::update, computeContactForces) is part
+// of b2p_step's device epilogue for all worlds; the loops below only drop per-object caches.
 void WorldPhysics::stepTheWorld(void)
 {
     const MutexLocker locker{&iMutex};
     if (!(world_init && step_size > 0)) return;
     preStepChecks();
-    if (!fast_step && !warned_dense_step) {
-        fprintf(stderr, "mars_ode_physics_b200: fast_step == false (dWorldStep) is not implemented; using quickstep\n");
-        warned_dense_step = true;
-    }
-    try {
-        checkB2P(b2p_step(arena, step_size), "WorldPhysics::stepTheWorld");
-        for (auto it = jointMap.begin(); it != jointMap.end();) {
-            if (auto joint = it->second.lock()) {
-                joint->update();
-                ++it;
-            } else {
-                it = jointMap.erase(it);
+    step_failed = false;
+    if (!fast_step) {
+        fprintf(stderr, "mars_ode_physics_b200: ERROR fast_step == false selects dWorldStep, which the device path does "
+                        "not implement; the world was NOT stepped (set fast_step = true for dWorldQuickStep)\n");
+        WorldPhysics::error = PHYSICS_ERROR;
+        step_failed = true;
+    } else {
+        try {
+            checkB2P(b2p_step(arena, step_size), "WorldPhysics::stepTheWorld");
+            step_count++;
+            for (auto it = jointMap.begin(); it != jointMap.end();) {
+                if (auto joint = it->second.lock()) {
+                    joint->update();
+                    ++it;
+                } else {
+                    it = jointMap.erase(it);
+                }
             }
-        }
-        for (auto it = frameMap.begin(); it != frameMap.end();) {
-            if (auto frame = it->second.lock()) {
-                frame->update();
-                ++it;
-            } else {
-                it = frameMap.erase(it);
+            for (auto it = frameMap.begin(); it != frameMap.end();) {
+                if (auto frame = it->second.lock()) {
+                    frame->update();
+                    ++it;
+                } else {
+                    it = frameMap.erase(it);
+                }
             }
+            computeContactForces();
+        } catch (const std::exception &e) {
+            fprintf(stderr, "WorldPhysics::stepTheWorld: %s\n", e.what());
+            step_failed = true;
         }
-        computeContactForces();
-    } catch (const std::exception &e) {
-        fprintf(stderr, "WorldPhysics::stepTheWorld: %s\n", e.what());
     }
     if (WorldPhysics::error) WorldPhysics::error = PHYSICS_NO_ERROR;
 }
@@ -164,6 +175,14 @@ int WorldPhysics::createContact(const b2p_contact_desc &c, int body1, int body2,
 {
     const int rc = b2p_contact_add(arena, world, body1, body2, &c);
     if (rc == B2P_EREJECTED) return -1; // joint-connected bodies (reference :461)
+    if (rc == B2P_ECAPACITY) {
+        // the reference has no contact cap: never throw out of addContact; drop the contact and say so once
+        if (!warned_capacity)
+            fprintf(stderr, "mars_ode_physics_b200: more than %d contacts in one world; extra contacts are dropped "
+                            "(WorldPhysics::setMaxContacts before initTheWorld raises the capacity)\n", max_contacts);
+        warned_capacity = true;
+        return -2;
+    }
     checkB2P(rc, "WorldPhysics::createContact");
     return rc;
 }

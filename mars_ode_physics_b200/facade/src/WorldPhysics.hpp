@@ -54,6 +54,12 @@ public:
     int getNumWorlds() const { return num_worlds; }
     void setDevice(int d) { device = d; }
     void setMaxContacts(int n) { max_contacts = n; }
+    // rolling / spinning friction rows (ContactData::rolling_friction ...) double the row capacity reserved per
+    // contact; on by default as the reference always honours them (Frame.cpp:1049-1054)
+    void setRollingFriction(bool on) { rolling_friction = on; }
+    long long getStepCount() const { return step_count; }
+    // true if the last stepTheWorld() could not step (fast_step == false: dWorldStep is not implemented)
+    bool lastStepFailed() const { return step_failed; }
 
     mutable utils::Mutex iMutex;
     interfaces::sReal max_angular_speed;
@@ -64,7 +70,8 @@ private:
     b2p_arena *arena;
     bool world_init;
     int num_worlds, device, max_contacts;
-    bool warned_dense_step;
+    bool rolling_friction, step_failed, warned_capacity;
+    long long step_count;
     utils::Vector old_gravity;
     interfaces::sReal old_cfm, old_erp;
     std::map<std::string, std::weak_ptr<Frame>> frameMap;

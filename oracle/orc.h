@@ -233,6 +233,16 @@ int orc_collide(orc_world *w); /* replaces the contact group; returns the number
 int orc_collide_get_pairs(const orc_world *w, int *pairs, int max_pairs); /* g1 | g2<<16, sorted */
 int orc_contact_get(const orc_world *w, int c, int *b1, int *b2, orc_contact_desc *out);
 
+/* ---- orc_post.c: what WorldPhysics::stepTheWorld does after the ODE call (src/WorldPhysics.cpp:372-397), on body
+ * and joint ids, one world at a time (the device does it for the whole batch) ---- */
+void orc_post_joint_update(const orc_world *w, int j, double out[7]); /* motor_torque axis1_torque3 joint_load3 */
+void orc_post_joint_friction(orc_world *w, int j, double coeff);
+void orc_post_frame_update(orc_world *w, int b, double dt, double lin_damp, double ang_damp, double last6[6],
+                           double acc6[6]);
+void orc_post_body_contact_force(const orc_world *w, int b, double out[3]);
+void orc_post_step_world(orc_world *w, double dt, const double *lin_damp, const double *ang_damp,
+                         const double *friction, double *last, double *acc, double *cforce, double *jupd);
+
 /* timing helper for bench.py's cpu_baseline: collide (optional) + quickstep, `steps` times over n worlds */
 void orc_bench_run(orc_world **worlds, int n, int steps, double h, int do_collide);
 

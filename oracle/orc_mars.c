@@ -490,144 +490,31 @@ void orc_mars_joint_get_joint_load(const orc_mars *m, int j, double out[3])
     memcpy(out, m->joints[j].joint_load, 3 * sizeof(double));
 }
 
-static void v_cross(double *r, const double *a, const double *b)
-{
-    double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
-    r[0] = x;
-    r[1] = y;
-    r[2] = z;
-}
-static double v_dot(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-static double v_len(const double *a) { return sqrt(v_dot(a, a)); }
-
-/* Joint::applyJointFriction :1031-1063 (off unless frictionCoefficient > 0) */
-static void apply_joint_friction(orc_mars *m, mjoint_t *j)
-{
-    if (!(j->friction > 0.0)) return;
-    double axis[3];
-    orc_joint_get_axis1(m->w, j->ode, axis);
-    double vel = (j->type == ORC_JOINT_HINGE2) ? orc_joint_get_angle1_rate(m->w, j->ode)
-                                                : -orc_joint_get_angle1_rate(m->w, j->ode);
-    double damping_torque = vel * -j->friction;
-    int fr[2] = {j->parent, j->child};
-    for (int k = 0; k < 2; k++) {
-        if (fr[k] < 0) continue;
-        int body = m->frames[fr[k]].body;
-        if (body < 0) continue;
-        double pos[3];
-        orc_body_get_position(m->w, body, pos);
-        for (int i = 0; i < 3; i++) pos[i] -= axis[i];
-        /* angleAxisToQuaternion(dampingTorque, axis) applied to pos (Rodrigues) */
-        double n = v_len(axis), u[3] = {0, 0, 0};
-        if (n > 0)
-            for (int i = 0; i < 3; i++) u[i] = axis[i] / n;
-        double c = cos(damping_torque), s = sin(damping_torque), ux[3];
-        v_cross(ux, u, pos);
-        double ud = v_dot(u, pos), force[3], torque[3];
-        for (int i = 0; i < 3; i++) {
-            double rot = pos[i] * c + ux[i] * s + u[i] * ud * (1 - c);
-            force[i] = rot - pos[i];
-            torque[i] = u[i] * damping_torque;
-        }
-        orc_body_add_force(m->w, body, force[0], force[1], force[2]);
-        orc_body_add_torque(m->w, body, torque[0], torque[1], torque[2]);
-    }
-}
-
-/* Joint::update :859-1019 */
+/* Joint::applyJointFriction :1031-1063 and Joint::update :859-1019 -> orc_post.c (shared with the batch form) */
 static void joint_update(orc_mars *m, mjoint_t *j)
 {
-    double fb[13], anchor[3] = {0, 0, 0}, axis[3] = {0, 0, 0};
-    orc_joint_get_feedback(m->w, j->ode, fb);
-    const double *f1 = fb, *t1 = fb + 3, *f2 = fb + 6, *t2 = fb + 9;
-    int calc1 = 0;
-    if (j->type == ORC_JOINT_HINGE || j->type == ORC_JOINT_HINGE2) {
-        orc_joint_get_anchor(m->w, j->ode, anchor);
-        orc_joint_get_axis1(m->w, j->ode, axis);
-        calc1 = 1;
-    }
-    j->motor_torque = -fb[12];
-    memset(j->axis1_torque, 0, sizeof(j->axis1_torque));
-    memset(j->joint_load, 0, sizeof(j->joint_load));
-    if (calc1 == 1) {
-        double v1[3], normal[3], load[3], tmp1[3];
-        if (j->body1 >= 0) {
-            double b1p[3];
-            orc_body_get_position(m->w, j->body1, b1p);
-            for (int i = 0; i < 3; i++) v1[i] = b1p[i] - anchor[i];
-            v_cross(normal, axis, v1);
-            double dot = v_dot(normal, f1);
-            for (int i = 0; i < 3; i++) normal[i] *= dot;
-            for (int i = 0; i < 3; i++) load[i] = f1[i] - normal[i];
-            v_cross(tmp1, v1, normal);
-            memcpy(j->axis1_torque, tmp1, sizeof(tmp1));
-            v_cross(tmp1, v1, load);
-            memcpy(j->joint_load, tmp1, sizeof(tmp1));
-            dot = v_dot(axis, t1);
-            for (int i = 0; i < 3; i++) {
-                tmp1[i] = axis[i] * dot;
-                load[i] = t1[i] - tmp1[i];
-                j->axis1_torque[i] += tmp1[i];
-                j->joint_load[i] += load[i];
-            }
-        } else if (j->body2 >= 0) {
-            double b2p[3], axis_force[3];
-            orc_body_get_position(m->w, j->body2, b2p);
-            for (int i = 0; i < 3; i++) v1[i] = b2p[i] - anchor[i];
-            double dot = v_dot(f2, v1) / v_dot(v1, v1);
-            for (int i = 0; i < 3; i++) {
-                axis_force[i] = v1[i] * dot;
-                tmp1[i] = f2[i] - axis_force[i];
-            }
-            double torque = v_len(tmp1) / v_len(v1);
-            v_cross(normal, v1, tmp1);
-            double nl = v_len(normal);
-            for (int i = 0; i < 3; i++) normal[i] *= torque / nl;
-            dot = v_dot(normal, axis);
-            for (int i = 0; i < 3; i++) {
-                tmp1[i] = axis[i] * dot;
-                load[i] = normal[i] - tmp1[i];
-            }
-            memcpy(j->axis1_torque, tmp1, sizeof(tmp1));
-            memcpy(j->joint_load, load, sizeof(load));
-            dot = v_dot(t2, axis);
-            for (int i = 0; i < 3; i++) {
-                tmp1[i] = axis[i] * dot;
-                load[i] = t2[i] - tmp1[i];
-                j->joint_load[i] += load[i];
-            }
-        }
-    }
-    apply_joint_friction(m, j);
+    double out[7];
+    orc_post_joint_update(m->w, j->ode, out);
+    j->motor_torque = out[0];
+    memcpy(j->axis1_torque, out + 1, 3 * sizeof(double));
+    memcpy(j->joint_load, out + 4, 3 * sizeof(double));
+    orc_post_joint_friction(m->w, j->ode, j->friction);
 }
 
-/* Frame::update :899-943 */
+/* Frame::update :899-943 -> orc_post.c */
 static void frame_update(orc_mars *m, mframe_t *f)
 {
     if (f->body < 0) return;
-    double dt = m->step_size, v[3];
-    if (dt > 0) {
-        orc_body_get_linear_vel(m->w, f->body, v);
-        for (int i = 0; i < 3; i++) {
-            f->l_acc[i] = (v[i] - f->last_l_vel[i]) / dt;
-            f->last_l_vel[i] = v[i];
-        }
-        orc_body_get_angular_vel(m->w, f->body, v);
-        for (int i = 0; i < 3; i++) {
-            f->a_acc[i] = (v[i] - f->last_a_vel[i]) / dt;
-            f->last_a_vel[i] = v[i];
-        }
-    }
-    if (f->linear_damping < 1.0) {
-        orc_body_get_linear_vel(m->w, f->body, v);
-        orc_body_set_linear_vel(m->w, f->body, v[0] * f->linear_damping, v[1] * f->linear_damping,
-                                v[2] * f->linear_damping);
-    }
-    if (f->angular_damping < 1.0) {
-        orc_body_get_angular_vel(m->w, f->body, v);
-        orc_body_set_angular_vel(m->w, f->body, v[0] * f->angular_damping, v[1] * f->angular_damping,
-                                 v[2] * f->angular_damping);
-    }
+    double last[6], acc[6];
+    memcpy(last, f->last_l_vel, sizeof(f->last_l_vel));
+    memcpy(last + 3, f->last_a_vel, sizeof(f->last_a_vel));
+    memcpy(acc, f->l_acc, sizeof(f->l_acc));
+    memcpy(acc + 3, f->a_acc, sizeof(f->a_acc));
+    orc_post_frame_update(m->w, f->body, m->step_size, f->linear_damping, f->angular_damping, last, acc);
+    memcpy(f->last_l_vel, last, sizeof(f->last_l_vel));
+    memcpy(f->last_a_vel, last + 3, sizeof(f->last_a_vel));
+    memcpy(f->l_acc, acc, sizeof(f->l_acc));
+    memcpy(f->a_acc, acc + 3, sizeof(f->a_acc));
 }
 
 /* WorldPhysics::clearPreviousStep :314-325 + Frame::clearContactData :945-955 */

@@ -117,6 +117,11 @@ def load(single=False):
         "orc_geom_create": (I, [P, I, I, DP, DP, DP, C.POINTER(Surface)]),
         "orc_geom_create_heightfield": (I, [P, P, I, I, D, D, D, C.POINTER(Surface)]),
         "orc_world_set_max_contacts": (None, [P, I]),
+        "orc_post_joint_update": (None, [P, I, DP]),
+        "orc_post_joint_friction": (None, [P, I, D]),
+        "orc_post_frame_update": (None, [P, I, D, D, D, DP, DP]),
+        "orc_post_body_contact_force": (None, [P, I, DP]),
+        "orc_post_step_world": (None, [P, D, P, P, P, P, P, P, P]),
         "orc_collide": (I, [P]),
         "orc_collide_get_pairs": (I, [P, C.POINTER(C.c_int), I]),
         "orc_contact_get": (I, [P, I, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(ContactDesc)]),
@@ -465,9 +470,72 @@ class OracleBatch:
         return [(v & 0xffff, v >> 16) for v in buf[:n]]
 
     # step
+    def _post_arrays(self):
+        """per-world arrays of the post-step bookkeeping (sized on first use / when the scene grew)"""
+        nb = self.lib.orc_world_num_bodies(self.worlds[0])
+        nj = self.lib.orc_world_num_joints(self.worlds[0])
+        W = self.num_worlds
+        if getattr(self, "_post_shape", None) != (nb, nj):
+            old_last = getattr(self, "_last", None)
+            self._last = np.zeros((W, max(nb, 1) * 6))
+            if old_last is not None:
+                n = min(old_last.shape[1], self._last.shape[1])
+                self._last[:, :n] = old_last[:, :n]
+            self._acc = np.zeros((W, max(nb, 1) * 6))
+            self._cforce = np.zeros((W, max(nb, 1) * 3))
+            self._jupd = np.zeros((W, max(nj, 1) * 7))
+            self._post_shape = (nb, nj)
+        lin = np.ones(max(nb, 1))
+        ang = np.ones(max(nb, 1))
+        for b, (l, a) in getattr(self, "_damping", {}).items():
+            lin[b], ang[b] = l, a
+        fr = -0.1 * np.ones(max(nj, 1))
+        for j, k in getattr(self, "_friction", {}).items():
+            fr[j] = k
+        return lin, ang, fr
+
     def step(self, h):
-        for w in self.worlds:
+        """dWorldQuickStep, then what WorldPhysics::stepTheWorld does after it (joint update + friction, frame
+        update, contact force) -- as b2p_step does for the batch"""
+        lin, ang, fr = self._post_arrays()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        for i, w in enumerate(self.worlds):
             self.lib.orc_world_quickstep(w, float(h))
+            self.lib.orc_post_step_world(w, float(h), vp(lin), vp(ang), vp(fr), vp(self._last[i]), vp(self._acc[i]),
+                                         vp(self._cforce[i]), vp(self._jupd[i]))
+
+    def collide_step(self, h):
+        self.collide()
+        self.step(h)
+
+    def body_set_damping(self, b, linear, angular):
+        self.__dict__.setdefault("_damping", {})[b] = (float(linear), float(angular))
+
+    def joint_set_friction_coefficient(self, j, k):
+        self.__dict__.setdefault("_friction", {})[j] = float(k)
+
+    def body_get_acceleration(self, b, world=0):
+        a = self._acc[world, 6 * b:6 * b + 6]
+        return a[:3].copy(), a[3:].copy()
+
+    def body_get_contact_force(self, b, world=0):
+        return self._cforce[world, 3 * b:3 * b + 3].copy()
+
+    def joint_get_update(self, j, world=0):
+        return self._jupd[world, 7 * j:7 * j + 7].copy()
+
+    def body_post_download(self, num_bodies):
+        """[num_bodies][15][W] like Arena.body_post_download"""
+        W = self.num_worlds
+        out = np.zeros((num_bodies, 15, W))
+        for b in range(num_bodies):
+            out[b, 0:6, :] = self._last[:, 6 * b:6 * b + 6].T
+            out[b, 6:12, :] = self._acc[:, 6 * b:6 * b + 6].T
+            out[b, 12:15, :] = self._cforce[:, 3 * b:3 * b + 3].T
+        return out
+
+    def joint_update_download(self, num_joints):
+        return np.ascontiguousarray(self._jupd[:, :7 * num_joints].reshape(self.num_worlds, num_joints, 7).transpose(1, 2, 0))
 
     def sync(self):
         pass

@@ -15,6 +15,15 @@ from mars_ode_physics_b200 import Arena, capi, scenes
 
 pytestmark = pytest.mark.gpu
 
+_Arena = Arena
+
+
+def Arena(W, **kw):  # the broadphase pair list is a debug output of b2p_collide: these tests read it
+    ar = _Arena(W, **kw)
+    ar.collide_record_pairs(True)
+    return ar
+
+
 SURF = {"mu": 0.8, "mu2": 0.8, "soft_erp": 0.2, "soft_cfm": 1e-5}
 
 
@@ -327,6 +336,63 @@ def test_box_stack_config_b(cuda_lib):
     assert err[:, :3].max() < 2e-3 and err[:, 3:7].max() < 5e-3
     z = oc.state_download(nb)[:, 2, :]
     assert np.all(np.diff(z, axis=0) > 0.15)  # still a stack
+
+
+def test_box_stack_config_b_free_running(cuda_lib):
+    """Config B with NO re-synchronisation: 130 steps of device collide + step against the oracle from the same
+    jittered start.  The stack lands (5 mm gaps close within ~35 steps) and rests on face contacts whose
+    candidate sets flip with fp32 / fp64 rounding, so the bar is a bounded drift of a stack that stays a stack,
+    plus exact agreement of the contact counts while the boxes are still in free fall."""
+    W = 32
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    for be in (ar, oc):
+        sc = scenes.box_stack(be, n=10)
+        scenes.jitter_box_stack(be, sc, W)
+    nb = 10
+    hist = []
+    for step in range(130):
+        ar.collide_step(0.001)
+        oc.collide_step(0.001)
+        if step == 10:
+            for w in range(W):
+                assert ar.contact_count(w) == oc.contact_count(w)
+        if step % 10 == 9:
+            d = np.abs(ar.state_download(nb).astype(np.float64) - oc.state_download(nb))
+            hist.append((step + 1, d[:, :3].max(), d[:, 3:7].max(), d[:, 7:].max()))
+    print("box stack free-running drift (step, pos, quat, vel):", hist)
+    assert hist[2][1] < 1e-5                      # 30 steps: still falling, pure integration
+    assert hist[-1][1] < 5e-3 and hist[-1][2] < 1e-2, hist[-1]
+    z = ar.state_download(nb)[:, 2, :]
+    assert np.all(np.diff(z, axis=0) > 0.15) and np.isfinite(z).all()  # still a stack on the device too
+    assert ar.contacts_dropped() == 0
+
+
+def test_config_c_device_collision_sampled_worlds(cuda_lib):
+    """BASELINE config C at its size (16384 worlds of the 12-hinge robot, foot spheres on a plane, DEVICE
+    collision as bench.py --workload C runs it): the last 6 worlds of the batch against the same 6 worlds built
+    alone on the oracle (per-world commands depend on the world id only), 100 steps, free-running."""
+    import bench
+    W, S = 16384, 6
+    ar = _Arena(W)
+    sa = bench.build_quadruped_worlds(ar, W)
+    oc = orc.OracleBatch(S)
+    so = bench.build_quadruped_worlds(oc, S, world_offset=W - S)
+    nb = len(sa["bodies"])
+    for step in range(100):
+        ar.collide_step(0.001)
+        oc.collide_step(0.001)
+    got = ar.state_download(nb)[:, :, W - S:].astype(np.float64)
+    want = oc.state_download(nb)
+    d = np.abs(got - want)
+    print("config C device collision, 100 steps: pos", d[:, :3].max(), "quat", d[:, 3:7].max(), "lvel",
+          d[:, 7:10].max(), "avel", d[:, 10:].max())
+    for k in range(S):
+        assert ar.contact_count(W - S + k) == oc.contact_count(k)
+        assert ar.last_num_rows(W - S + k) == oc.last_num_rows(k)
+        assert ar.rand_get_seed(W - S + k) == oc.rand_get_seed(k)
+    assert d[:, :3].max() < 2e-4 and d[:, 3:7].max() < 1e-3 and d[:, 7:10].max() < 2e-2, d.max()
+    assert sum(oc.contact_count(k) for k in range(S)) >= S  # the feet are on the ground
+    ar.close()
 
 
 def test_sampled_colliders_against_committed_golden(cuda_lib):
