@@ -340,30 +340,46 @@ def test_box_stack_config_b(cuda_lib):
 
 def test_box_stack_config_b_free_running(cuda_lib):
     """Config B with NO re-synchronisation: 130 steps of device collide + step against the oracle from the same
-    jittered start.  The stack lands (5 mm gaps close within ~35 steps) and rests on face contacts whose
-    candidate sets flip with fp32 / fp64 rounding, so the bar is a bounded drift of a stack that stays a stack,
-    plus exact agreement of the contact counts while the boxes are still in free fall."""
+    jittered start.  The boxes fall 5 mm onto each other (all ten gaps close in the same step, ~32) and then rest
+    on face contacts.  A box-box face contact keeps the <= 4 deepest of up to 8 clipped candidate points whose
+    depths differ by less than fp32 resolution, so device (fp32) and oracle (fp64) choose different -- equally
+    valid -- manifolds in some steps of EVERY world (measured: the first differing contact count appears between
+    step 33 and 126), and the trajectories then separate at the millimetre level.  Bars: free fall agrees to
+    rounding in every world; the drift after 130 steps is bounded and the per-box mean heights over the worlds
+    agree; both stacks still stand and are nearly at rest."""
     W = 32
     ar, oc = Arena(W), orc.OracleBatch(W)
     for be in (ar, oc):
         sc = scenes.box_stack(be, n=10)
         scenes.jitter_box_stack(be, sc, W)
     nb = 10
-    hist = []
+    agree = total = 0
     for step in range(130):
-        ar.collide_step(0.001)
-        oc.collide_step(0.001)
-        if step == 10:
-            for w in range(W):
-                assert ar.contact_count(w) == oc.contact_count(w)
-        if step % 10 == 9:
+        ar.collide()
+        oc.collide()
+        for w in range(W):
+            agree += ar.contact_count(w) == oc.contact_count(w)
+            total += 1
+        ar.step(0.001)
+        oc.step(0.001)
+        if step == 29:
             d = np.abs(ar.state_download(nb).astype(np.float64) - oc.state_download(nb))
-            hist.append((step + 1, d[:, :3].max(), d[:, 3:7].max(), d[:, 7:].max()))
-    print("box stack free-running drift (step, pos, quat, vel):", hist)
-    assert hist[2][1] < 1e-5                      # 30 steps: still falling, pure integration
-    assert hist[-1][1] < 5e-3 and hist[-1][2] < 1e-2, hist[-1]
-    z = ar.state_download(nb)[:, 2, :]
-    assert np.all(np.diff(z, axis=0) > 0.15) and np.isfinite(z).all()  # still a stack on the device too
+            assert d[:, :7].max() < 1e-6 and d[:, 7:].max() < 1e-5, d.max()   # free fall: pure integration
+    sa, so = ar.state_download(nb).astype(np.float64), oc.state_download(nb)
+    d = np.abs(sa - so)
+    print("box stack free-running 130 steps: contact counts agree in", agree, "of", total, "(world, step) pairs; pos",
+          d[:, :3].max(), "quat", d[:, 3:7].max(), "| speed device", np.abs(sa[:, 7:10]).max(), "oracle",
+          np.abs(so[:, 7:10]).max())
+    # (count agreement is reported, not asserted: once two trajectories are a millimetre apart their contact sets
+    # legitimately differ; on IDENTICAL states the device and the oracle agree, see test_box_stack_config_b)
+    assert d[:, :3].max() < 1e-2 and d[:, 3:7].max() < 3e-2, (d[:, :3].max(), d[:, 3:7].max())
+    # statistics over the 32 worlds are stable where single trajectories are not: mean height of every box
+    mz = np.abs(sa[:, 2, :].mean(axis=1) - so[:, 2, :].mean(axis=1))
+    print("mean box heights differ by", mz.max())
+    assert mz.max() < 5e-4, mz
+    for z in (sa[:, 2, :], so[:, 2, :]):
+        assert np.all(np.diff(z, axis=0) > 0.15) and np.isfinite(z).all()  # still a stack, on both sides
+    assert np.abs(sa[:, 7:10]).max() < 0.2 and np.abs(so[:, 7:10]).max() < 0.2   # and (nearly) at rest
     assert ar.contacts_dropped() == 0
 
 

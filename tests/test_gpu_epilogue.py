@@ -34,7 +34,8 @@ def _ball_on_plane(be, W, rolling):
     be.set_max_contacts(2)
     if rolling:
         be.enable_rolling_friction(True)
-    b = scenes.add_body(be, 1.0, scenes.inertia_sphere(1.0, 0.1), (0.0, 0.0, 0.1))
+    # 0.1 mm into the plane: a start exactly on it (depth 0) would be decided by fp32 rounding of z
+    b = scenes.add_body(be, 1.0, scenes.inertia_sphere(1.0, 0.1), (0.0, 0.0, 0.0999))
     for w in range(W):
         be.body_set_linear_vel(b, (0.5 + 0.01 * w, -0.2, 0.0), w)
         be.body_set_angular_vel(b, (1.0, 0.5 * (w % 5), 2.0), w)
@@ -270,7 +271,8 @@ def test_rover_residual_bound_at_full_size(cuda_lib):
     r = ar.lcp_residual()
     print("rover residual: max", r.max(), "median", np.median(r), "99.9%", np.quantile(r, 0.999))
     assert np.isfinite(r).all()
-    assert np.median(r) < 50.0 and r.max() < 5e3
+    # observed on B200: median 1.4e-6, 99.9 % quantile 62, max 181 (worlds in hard contact transitions)
+    assert np.median(r) < 1e-3 and np.quantile(r, 0.999) < 600.0 and r.max() < 2e3
     assert ar.contacts_dropped() == 0
 
 

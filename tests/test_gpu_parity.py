@@ -107,14 +107,15 @@ def test_quadruped_parity_f64_oracle(cuda_lib):
     ar, oc = Arena(W), orc.OracleBatch(W)
     worst, sa, so = _run_quadruped(ar, oc, W, 150, check_every=10)
     print("quadruped fp32-vs-fp64 worst errors:", worst)
-    assert worst["pos"] < 5e-4 and worst["quat"] < 2e-3 and worst["lvel"] < 5e-2 and worst["avel"] < 0.5, worst
+    # observed on B200: pos 3.1e-6, quat 2.8e-5, lvel 1.5e-4, avel 2.8e-3; the bars are ~10x that
+    assert worst["pos"] < 4e-5 and worst["quat"] < 3e-4 and worst["lvel"] < 2e-3 and worst["avel"] < 3e-2, worst
     # the LCP residual bound itself is a CPU test (tests/test_oracle.py::test_residual_*): GPU and
     # oracle run the same 20 sweeps, so matching lambdas (feedback below) means matching residuals
     # feedback / contact force parity on the last step
     for w in (0, W - 1):
         for c in range(ar.contact_count(w)):
             fa, fo = ar.contact_get_feedback(w, c), oc.contact_get_feedback(w, c)
-            assert np.allclose(fa, fo, rtol=5e-2, atol=5e-2), (fa, fo)
+            assert np.allclose(fa, fo, rtol=5e-3, atol=5e-3), (fa, fo)
 
 
 def test_quadruped_parity_strict_f32_oracle(cuda_lib):
