@@ -324,6 +324,8 @@ def run_b200(args):
         ar.set_register_rows(args.register_rows)
     ar.set_sor_kernel({"auto": -1, "paired": 0, "tmem": 1}[args.sor_kernel])
     ar.set_sor_warps(args.sor_warps)
+    if args.no_graph:
+        ar.set_graph_launch(False)
     if args.reorder == "none":
         ar.set_reorder_method(capi.REORDER_NONE)
     nb, nj = len(sc["bodies"]), len(sc["joints"])
@@ -342,7 +344,7 @@ def run_b200(args):
     sampler = ClockSampler(range(world_size) if world_size > 1 else [local_rank])
     if rank == 0:
         sampler.start()
-    for _ in range(SETTLE_STEPS):
+    for _ in range(args.settle):
         ar.collide_step(H)
     ar.sync()
     for _ in range(max(args.warmup, 3)):
@@ -483,7 +485,7 @@ def run_b200(args):
                        "worlds_per_gpu": W, "total_worlds": total_worlds,
                        "sharding": f"worlds/{world_size} GPUs, no collective on the step path",
                        "l2": "per-step working set (row scratch) > L2; no flush needed",
-                       "settle_steps": SETTLE_STEPS, "row_reordering": args.reorder,
+                       "settle_steps": args.settle, "row_reordering": args.reorder,
                        "launch": "one CUDA graph (collide + assemble + SOR + integrate) per step",
                        "host_cores_pinned": pinned_cores,
                        "collision_semantics": "repo-defined (oracle/orc_collide.c), not ODE's dCollide: one contact "
@@ -520,6 +522,24 @@ def run_b200(args):
             "clocks": clocks,
             "wall_s": t_wall,
         }
+        if world_size == 1 and args.workload == "D" and not args.no_facade:
+            # the same workload built and stepped through the reference-facing plugin API (C++ facade:
+            # WorldPhysicsLoader / createFrame / createObject / createJoint / stepTheWorld, batched I/O), its own
+            # process and arena; commands and observations travel through pinned host buffers every step
+            exe = os.path.join(ROOT, "mars_ode_physics_b200", "lib", "facade_bench")
+            try:
+                ar.close()
+                out = subprocess.run([exe, str(W), str(max(K, 20)), "5", str(SETTLE_STEPS)], capture_output=True,
+                                     text=True, timeout=600,
+                                     env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank))))
+                fl = json.loads(out.stdout.strip().splitlines()[-1])
+                line["e2e_facade"] = {"value": fl["e2e_facade"], "unit": UNIT, "ms_per_step": fl["ms_per_step"],
+                                      "h2d_bytes_per_step": fl["h2d_bytes_per_step"],
+                                      "d2h_bytes_per_step": fl["d2h_bytes_per_step"], "ok": fl["ok"],
+                                      "path": "facade_bench: plugin loader -> PhysicsInterface::stepTheWorld "
+                                              "(device collision + step + post-step bookkeeping), wall clock"}
+            except Exception as e:  # the number is additional evidence, never a reason to lose the bench line
+                line["e2e_facade"] = {"value": None, "error": str(e)[:200]}
         if not args.no_cpu_baseline and world_size == 1 and args.workload == "D":
             cores = os.cpu_count() or 1
             sample = 128 * cores  # enough worlds that ~12 s of CPU work stays within a few thousand steps
@@ -544,6 +564,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--worlds", type=int, default=WORLDS_PER_GPU, help="worlds per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-facade", action="store_true", help="skip the C++ plugin-API leg (e2e_facade)")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="profiling aid: launch the four kernels directly instead of replaying the CUDA graph")
+    ap.add_argument("--settle", type=int, default=SETTLE_STEPS, help="profiling aid: untimed settle steps")
     ap.add_argument("--resident-rows", type=int, default=0,
                     help="tuning: constraint rows per world kept in shared memory by the SOR kernel (0 = auto)")
     ap.add_argument("--register-rows", type=int, default=-1,

@@ -16,6 +16,7 @@
 #ifndef MARS_ODE_B200_H
 #define MARS_ODE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -221,6 +222,9 @@ int b2p_body_get_state_batch_begin(b2p_arena *a, int body, float *host_out);
  * [num_worlds] (angle1 rate1 angle2 rate2) or NULL */
 int b2p_observe_begin(b2p_arena *a, int body, float *host_out, float *host_joint_obs);
 int b2p_io_wait(b2p_arena *a, int ticket);
+/* page-locked host memory for the batched transfers above (asynchronous copies need it to overlap the step) */
+void *b2p_host_alloc(size_t bytes);
+void b2p_host_free(void *p);
 /* device pointers (float, layout [field][padded_worlds]) for zero-copy consumers */
 int b2p_padded_worlds(const b2p_arena *a);
 void *b2p_device_state(b2p_arena *a);       /* [nb*13][Wp] */

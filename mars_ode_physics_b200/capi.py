@@ -166,6 +166,8 @@ SIGNATURES = {
     "b2p_contacts_dropped": (_I, [_P, C.POINTER(C.c_longlong)]),
     "b2p_collide_record_pairs": (_I, [_P, _I]),
     "b2p_debug_lcp_residual": (_I, [_P, _P]),
+    "b2p_host_alloc": (_P, [C.c_size_t]),
+    "b2p_host_free": (None, [_P]),
 }
 
 _libs = {}

@@ -2491,6 +2491,23 @@ int b2p_debug_kernel_times(b2p_arena *a, int enable, double out[4])
     return 0;
 }
 
+// page-locked host memory for the batched transfers (b2p_joints_set_param_batch, b2p_observe_begin ...): a host
+// written in C++ / C has no CUDA runtime of its own to get it from
+void *b2p_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        fail(B2P_ECUDA, "cudaMallocHost(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+void b2p_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 // ---------------- post-step bookkeeping of WorldPhysics::stepTheWorld, for every world ----------------
 int b2p_arena_set_post_step_outputs(b2p_arena *a, int flags)
 {

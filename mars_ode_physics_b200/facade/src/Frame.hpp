@@ -50,6 +50,8 @@ public:
     virtual void getMass(interfaces::sReal *mass, interfaces::sReal *inertia = 0) const;
 
     int getBody() const;   // b2p body id, -1 if none (reference: dBodyID getBody())
+    WorldPhysics *getWorldPhysics() const { return theWorld; }
+    const utils::Vector &getComOffset() const { return offsetPos; } // accumulated COM shift in the body frame
     int acquireBody();
     MassProps getMass(void) const;
     void addObjectMass(Object *object);

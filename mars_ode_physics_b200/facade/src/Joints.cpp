@@ -99,6 +99,7 @@ bool Joint::createJoint()
     if (!createJoint(body1, body2)) return false;
     // Joint::applyJointFriction runs in the step's device epilogue with this coefficient (off unless > 0)
     b2p_joint_set_friction_coefficient(theWorld->getWorld(), jointId, frictionCoefficient);
+    theWorld->noteJoint(jointId, joint_type);
     if (n1 && n2) {
         n1->addLinkedFrame(n2);
         n2->addLinkedFrame(n1);

@@ -44,6 +44,27 @@ void Object::registerOnFrame()
     objectCreated = true;
 }
 
+void Object::requestGeom(ConfigMap &config, int cls, double d0, double d1, double d2)
+{
+    auto f = frame.lock();
+    if (!f) return;
+    WorldPhysics *world = f->getWorldPhysics();
+    if (!world || !world->getDeviceCollision()) return;
+    b2p_surface s = world->defaultSurface();
+    if (config.hasKey("c_params")) {
+        ConfigMap &c = config["c_params"];
+        if (c.hasKey("friction1")) s.mu = s.mu2 = (double)c["friction1"];
+        if (c.hasKey("friction2")) s.mu2 = (double)c["friction2"];
+        if (c.hasKey("rolling_friction")) s.rho = s.rho2 = (double)c["rolling_friction"];
+        if (c.hasKey("rolling_friction2")) s.rho2 = (double)c["rolling_friction2"];
+        if (c.hasKey("spinning_friction")) s.rhoN = (double)c["spinning_friction"];
+        if (c.hasKey("cfm")) s.soft_cfm = (double)c["cfm"];
+        if (c.hasKey("erp")) s.soft_erp = (double)c["erp"];
+    }
+    const double dims[4] = {d0, d1, d2, 0.0};
+    world->requestGeom(f.get(), cls, dims, pos, q, s);
+}
+
 #define B2P_OBJECT_BOILERPLATE(Name)                                                                      \
     Name::Name(std::shared_ptr<Frame> frame, ConfigMap &config) : Object(frame), config(config)           \
     {                                                                                                     \
@@ -64,6 +85,8 @@ bool Box::createMass()
     nMass.setBoxTotal((double)config["mass"], (double)config["extend"]["x"], (double)config["extend"]["y"],
                       (double)config["extend"]["z"]);
     registerOnFrame();
+    requestGeom(config, B2P_GEOM_BOX, (double)config["extend"]["x"], (double)config["extend"]["y"],
+                (double)config["extend"]["z"]);
     return true;
 }
 
@@ -71,6 +94,7 @@ bool Sphere::createMass() // Sphere.cpp:36-39: radius = extend.x
 {
     nMass.setSphereTotal((double)config["mass"], (double)config["extend"]["x"]);
     registerOnFrame();
+    requestGeom(config, B2P_GEOM_SPHERE, (double)config["extend"]["x"], 0.0, 0.0);
     return true;
 }
 
@@ -78,6 +102,7 @@ bool Capsule::createMass() // Capsule.cpp:37-41: radius = extend.x, length = ext
 {
     nMass.setCapsuleTotal((double)config["mass"], 3, (double)config["extend"]["x"], (double)config["extend"]["y"]);
     registerOnFrame();
+    requestGeom(config, B2P_GEOM_CAPSULE, (double)config["extend"]["x"], (double)config["extend"]["y"], 0.0);
     return true;
 }
 
@@ -85,6 +110,7 @@ bool Cylinder::createMass() // Cylinder.cpp:37-41
 {
     nMass.setCylinderTotal((double)config["mass"], 3, (double)config["extend"]["x"], (double)config["extend"]["y"]);
     registerOnFrame();
+    requestGeom(config, B2P_GEOM_CYLINDER, (double)config["extend"]["x"], (double)config["extend"]["y"], 0.0);
     return true;
 }
 

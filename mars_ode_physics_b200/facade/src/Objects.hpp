@@ -1,6 +1,7 @@
 // Objects.hpp -- mass-only scene objects and their factory (reference src/objects/Object.hpp,
 // Box/Sphere/Capsule/Cylinder/Inertial.{hpp,cpp}, ObjectFactory.{hpp,cpp}).  As in the reference
-// an object contributes a mass to its Frame and creates no geom.
+// an object contributes a mass to its Frame; with WorldPhysics::setDeviceCollision(true) its shape additionally
+// becomes a geom of the device collision path (the reference keeps collision in a separate plugin).
 #pragma once
 #include <map>
 
@@ -25,6 +26,8 @@ public:
 protected:
     void readPose(configmaps::ConfigMap &config);
     void registerOnFrame();
+    // device collision (WorldPhysics::setDeviceCollision): this object's shape as a geom on the frame's body
+    void requestGeom(configmaps::ConfigMap &config, int geom_class, double d0, double d1, double d2);
     std::weak_ptr<Frame> frame;
     utils::Vector pos;
     utils::Quaternion q;

@@ -45,6 +45,7 @@ WorldPhysics::WorldPhysics() : interfaces::PhysicsInterface()
     max_contacts = 8;
     rolling_friction = true;
     step_failed = warned_capacity = false;
+    device_collision = geoms_dirty = false;
     step_count = 0;
 }
 
@@ -139,7 +140,12 @@ void WorldPhysics::stepTheWorld(void)
         step_failed = true;
     } else {
         try {
-            checkB2P(b2p_step(arena, step_size), "WorldPhysics::stepTheWorld");
+            if (device_collision) {
+                flushGeoms();
+                checkB2P(b2p_collide_step(arena, step_size), "WorldPhysics::stepTheWorld");
+            } else {
+                checkB2P(b2p_step(arena, step_size), "WorldPhysics::stepTheWorld");
+            }
             step_count++;
             for (auto it = jointMap.begin(); it != jointMap.end();) {
                 if (auto joint = it->second.lock()) {
@@ -186,6 +192,153 @@ int WorldPhysics::createContact(const b2p_contact_desc &c, int body1, int body2,
     checkB2P(rc, "WorldPhysics::createContact");
     return rc;
 }
+
+// ---------------- device collision through the plugin API ----------------
+void WorldPhysics::setDeviceCollision(bool on)
+{
+    if (!geom_requests.empty() && !on) throw std::runtime_error("WorldPhysics::setDeviceCollision: geoms exist already");
+    device_collision = on;
+}
+
+b2p_surface WorldPhysics::defaultSurface() const
+{
+    b2p_surface s{};
+    s.mu = s.mu2 = ground_friction;
+    s.soft_cfm = ground_cfm;
+    s.soft_erp = ground_erp;
+    return s;
+}
+
+void WorldPhysics::createGroundPlane(double a, double b, double c, double d)
+{
+    const MutexLocker locker{&iMutex};
+    if (!world_init) throw std::runtime_error("WorldPhysics::createGroundPlane: world not initialised");
+    flushGeoms(); // geoms keep their creation order (it fixes the order of the contact stream)
+    const double dims[4] = {a, b, c, d};
+    const b2p_surface s = defaultSurface();
+    checkB2P(b2p_geom_create(arena, B2P_GEOM_PLANE, B2P_STATIC_BODY, dims, nullptr, nullptr, &s), "createGroundPlane");
+    device_collision = true;
+}
+
+void WorldPhysics::createHeightfield(const float *heights, int nx, int ny, double dx, double x0, double y0)
+{
+    const MutexLocker locker{&iMutex};
+    if (!world_init) throw std::runtime_error("WorldPhysics::createHeightfield: world not initialised");
+    flushGeoms();
+    const b2p_surface s = defaultSurface();
+    checkB2P(b2p_geom_create_heightfield(arena, heights, nx, ny, dx, x0, y0, &s), "createHeightfield");
+    device_collision = true;
+}
+
+void WorldPhysics::requestGeom(Frame *frame, int cls, const double dims[4], const Vector &pos, const Quaternion &q,
+                               const b2p_surface &s)
+{
+    GeomRequest r;
+    r.frame = frame;
+    r.cls = cls;
+    for (int i = 0; i < 4; i++) r.dims[i] = dims[i];
+    r.pos = pos;
+    r.q = q;
+    r.s = s;
+    geom_requests.push_back(r);
+    geoms_dirty = true;
+}
+
+// Geoms are created when the first step needs them: only then is every frame's centre of mass final
+// (Frame::addObjectMass re-centres the body each time an object is added), and a geom's local pose is the
+// object's pose in the frame minus that accumulated offset.
+void WorldPhysics::flushGeoms()
+{
+    if (!geoms_dirty) return;
+    for (const GeomRequest &r : geom_requests) {
+        const int body = r.frame->getBody();
+        if (body < 0) continue;
+        const Vector off = r.frame->getComOffset();
+        const double lpos[3] = {r.pos.x() - off.x(), r.pos.y() - off.y(), r.pos.z() - off.z()};
+        const double lq[4] = {r.q.w(), r.q.x(), r.q.y(), r.q.z()};
+        checkB2P(b2p_geom_create(arena, r.cls, body, r.dims, lpos, lq, &r.s), "WorldPhysics::flushGeoms");
+    }
+    geom_requests.clear();
+    geoms_dirty = false;
+}
+
+std::vector<ContactData> WorldPhysics::getContacts(int world)
+{
+    const MutexLocker locker{&iMutex};
+    std::vector<ContactData> out;
+    if (!world_init) return out;
+    int n = 0;
+    b2p_contact_count(arena, world, &n);
+    std::map<int, std::shared_ptr<Frame>> by_body;
+    for (auto &pair : frameMap)
+        if (auto f = pair.second.lock())
+            if (f->getBody() >= 0) by_body[f->getBody()] = f;
+    for (int c = 0; c < n; c++) {
+        int b1 = -1, b2 = -1;
+        b2p_contact_desc d{};
+        if (b2p_contact_get(arena, world, c, &b1, &b2, &d) < 0) break;
+        ContactData cd;
+        if (by_body.count(b1)) {
+            cd.body1 = by_body[b1];
+            cd.nameObject1 = by_body[b1]->getName();
+        }
+        if (b2 >= 0 && by_body.count(b2)) {
+            cd.body2 = by_body[b2];
+            cd.nameObject2 = by_body[b2]->getName();
+        }
+        cd.pos = Vector(d.pos[0], d.pos[1], d.pos[2]);
+        cd.normal = Vector(d.normal[0], d.normal[1], d.normal[2]);
+        cd.depth = d.depth;
+        cd.c_params.friction1 = d.mu;
+        cd.c_params.friction2 = d.mu2;
+        cd.c_params.rolling_friction = d.rho;
+        cd.c_params.rolling_friction2 = d.rho2;
+        cd.c_params.spinning_friction = d.rhoN;
+        cd.c_params.cfm = d.soft_cfm;
+        cd.c_params.erp = d.soft_erp;
+        out.push_back(cd);
+    }
+    return out;
+}
+
+// ---------------- batched I/O ----------------
+void WorldPhysics::noteJoint(int joint_id, int joint_type)
+{
+    if (joint_id < 0) return;
+    if ((int)joint_types_by_id.size() <= joint_id) joint_types_by_id.resize(joint_id + 1, JOINT_TYPE_UNDEFINED);
+    joint_types_by_id[joint_id] = joint_type;
+}
+
+void WorldPhysics::setJointVelocitiesBatch(const float *values, int num_joints, int axis)
+{
+    const MutexLocker locker{&iMutex};
+    bool negate = false;
+    for (int j = 0; j < num_joints && j < (int)joint_types_by_id.size(); j++)
+        negate |= axis == 1 && (joint_types_by_id[j] == JOINT_TYPE_HINGE || joint_types_by_id[j] == JOINT_TYPE_SLIDER);
+    const int param = B2P_PARAM_VEL | (axis == 2 ? B2P_PARAM_GROUP2 : 0);
+    if (!negate) { // no sign change on the way: one transfer straight from the caller's (pinned) buffer
+        checkB2P(b2p_joints_set_param_batch(arena, param, values, num_joints), "WorldPhysics::setJointVelocitiesBatch");
+        return;
+    }
+    batch_tmp.assign(values, values + (size_t)num_joints * num_worlds);
+    for (int j = 0; j < num_joints; j++)
+        if (joint_types_by_id[j] == JOINT_TYPE_HINGE || joint_types_by_id[j] == JOINT_TYPE_SLIDER)
+            for (int w = 0; w < num_worlds; w++) batch_tmp[(size_t)j * num_worlds + w] = -batch_tmp[(size_t)j * num_worlds + w];
+    checkB2P(b2p_joints_set_param_batch(arena, param, batch_tmp.data(), num_joints), "WorldPhysics::setJointVelocitiesBatch");
+    b2p_sync(arena); // batch_tmp must outlive the asynchronous copy
+}
+
+int WorldPhysics::observeBatchBegin(const std::shared_ptr<DynamicObject> &frame, float *body13, float *joint_obs)
+{
+    const MutexLocker locker{&iMutex};
+    const Frame *f = dynamic_cast<const Frame *>(frame.get());
+    if (!f || f->getBody() < 0) throw std::runtime_error("WorldPhysics::observeBatchBegin: frame has no body");
+    const int t = b2p_observe_begin(arena, f->getBody(), body13, joint_obs);
+    checkB2P(t, "WorldPhysics::observeBatchBegin");
+    return t;
+}
+
+void WorldPhysics::observeBatchWait(int ticket) { checkB2P(b2p_io_wait(arena, ticket), "WorldPhysics::observeBatchWait"); }
 
 const Vector WorldPhysics::getCenterOfMass(const std::vector<std::shared_ptr<NodeInterface>> &) const { return Vector(); }
 

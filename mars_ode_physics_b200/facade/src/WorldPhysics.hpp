@@ -47,6 +47,7 @@ public:
     std::shared_ptr<Frame> getFrameIntern(const std::string &name);
     // returns the contact id or -1 when the bodies are joint-connected (WorldPhysics.cpp:458-468)
     int createContact(const b2p_contact_desc &c, int body1, int body2, int world = 0);
+    void noteJoint(int joint_id, int joint_type);
     void computeContactForces();
 
     // ---- batch extension (not in the reference): call before initTheWorld ----
@@ -57,6 +58,29 @@ public:
     // rolling / spinning friction rows (ContactData::rolling_friction ...) double the row capacity reserved per
     // contact; on by default as the reference always honours them (Frame.cpp:1049-1054)
     void setRollingFriction(bool on) { rolling_friction = on; }
+    // ---- device collision: broadphase + narrowphase on the device as the contact source.  With it
+    // switched on (before the objects are created) every box / sphere / capsule / cylinder object also becomes a
+    // geom on its frame's body, stepTheWorld() runs collide + step, and the generated contacts can be read back
+    // in the reference's ContactData form.  Surface parameters: an object's config["c_params"] (friction1,
+    // friction2, rolling_friction, rolling_friction2, spinning_friction, cfm, erp) or, where absent, the world's
+    // ground_friction / ground_cfm / ground_erp (reference src/WorldPhysics.cpp:86-88, unused there).
+    void setDeviceCollision(bool on);
+    bool getDeviceCollision() const { return device_collision; }
+    void createGroundPlane(double a, double b, double c, double d);            // a x + b y + c z = d, static
+    void createHeightfield(const float *heights, int nx, int ny, double dx, double x0, double y0); // shared by all worlds
+    b2p_surface defaultSurface() const;
+    // the contact stream of one world as the records Frame::addContact consumes (Frame.cpp:996-1092)
+    std::vector<interfaces::ContactData> getContacts(int world = 0);
+    void requestGeom(Frame *frame, int geom_class, const double dims[4], const utils::Vector &pos,
+                     const utils::Quaternion &q, const b2p_surface &s);
+    // ---- batched I/O for all worlds (batch extension; the one-world accessors keep working next to it) ----
+    // per-world motor commands of joints 0 .. n-1 in creation order: values[n][num_worlds], axis 1 or 2, with the
+    // sign rule of Joint::setVelocity (hinge / slider negate; Joint.cpp:355-393) applied on the way
+    void setJointVelocitiesBatch(const float *values, int num_joints, int axis);
+    // state of one frame's body (13 floats per world) + angle / rate of every joint of every world, copied to
+    // host buffers over a copy stream while the next step runs; returns a ticket for observeBatchWait
+    int observeBatchBegin(const std::shared_ptr<interfaces::DynamicObject> &frame, float *body13, float *joint_obs);
+    void observeBatchWait(int ticket);
     long long getStepCount() const { return step_count; }
     // true if the last stepTheWorld() could not step (fast_step == false: dWorldStep is not implemented)
     bool lastStepFailed() const { return step_failed; }
@@ -71,6 +95,19 @@ private:
     bool world_init;
     int num_worlds, device, max_contacts;
     bool rolling_friction, step_failed, warned_capacity;
+    bool device_collision, geoms_dirty;
+    struct GeomRequest {
+        Frame *frame;
+        int cls;
+        double dims[4];
+        utils::Vector pos;
+        utils::Quaternion q;
+        b2p_surface s;
+    };
+    std::vector<GeomRequest> geom_requests;
+    std::vector<float> batch_tmp;
+    std::vector<int> joint_types_by_id; // interfaces::JointType per arena joint id (sign rule of the batch setter)
+    void flushGeoms();
     long long step_count;
     utils::Vector old_gravity;
     interfaces::sReal old_cfm, old_erp;

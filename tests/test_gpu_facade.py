@@ -65,3 +65,42 @@ def test_universal_and_ball_joints_through_the_loader(cuda_lib):
     ball_err, len_a_err, len_b_err, angle1, moved = map(float, out)
     assert ball_err < 5e-3 and len_a_err < 5e-3 and len_b_err < 5e-3
     assert moved > 0.05 and math.isfinite(angle1)
+
+
+def test_config_d_entirely_through_the_loader(cuda_lib, tmp_path):
+    """BASELINE config D built and stepped through the plugin API only (facade_bench: WorldPhysicsLoader ->
+    createFrame / createObject / createJoint with ConfigMaps, device collision from the objects' shapes, the
+    heightfield entry point, ground_* surface defaults, stepTheWorld, batched commands and observations,
+    ContactData read-back) gives the SAME worlds as the scene built through the C ABI by bench.build_rover_worlds:
+    same bodies, geoms, joints and per-world randomisation, so the final states must agree bitwise."""
+    import json
+    import bench
+    from mars_ode_physics_b200 import Arena
+    exe = os.path.join(ROOT, "mars_ode_physics_b200", "lib", "facade_bench")
+    assert os.path.exists(exe), "facade_bench missing: run __graft_entry__.build()"
+    W, steps, warm, settle = 300, 40, 5, 200
+    dump = str(tmp_path / "facade_state.bin")
+    res = subprocess.run([exe, str(W), str(steps), str(warm), str(settle), dump], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:] + res.stdout[-500:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    print("facade_bench:", line)
+    assert line["ok"] and line["worlds"] == W and line["e2e_facade"] > 0 and line["contacts_first_worlds"] >= 1
+    assert line["launches"] == 4 * (settle + warm + steps)
+    got = np.fromfile(dump, dtype=np.float32).reshape(5, 13, W)
+    ar = Arena(W)
+    sc = bench.build_rover_worlds(ar, W)
+    from mars_ode_physics_b200 import capi
+    param = capi.PARAM_VEL | capi.PARAM_GROUP2
+    k_total = 0
+    for _ in range(settle):
+        ar.collide_step(0.001)
+    for phase in (warm, steps):  # the bench rotates four command buffers (vel + 0.001 * (k % 4)) in both phases
+        for k in range(phase):
+            for j in sc["joints"]:
+                ar.joint_set_param_batch(j, param, (sc["vel"] + np.float32(0.001) * np.float32(k % 4)).astype(np.float32))
+            ar.collide_step(0.001)
+            k_total += 1
+    want = ar.state_download(5)
+    d = np.abs(got.astype(np.float64) - want)
+    print("facade vs C ABI rover worlds: max |diff|", d.max())
+    assert np.array_equal(got, want)
