@@ -291,6 +291,50 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def measure_workload(Arena, torch, stream, name, builder, W, world_offset, settle, steps, peak):
+    """A secondary configuration (BASELINE configs 2, 3, 5): device-resident collide + step over `steps` steps,
+    CUDA events on the launch stream, plus the per-kernel split.  Returns (dict for the JSON line, ms)."""
+    ar = Arena(W, device=torch.cuda.current_device())
+    ar.set_stream(stream.cuda_stream)
+    builder(ar, W, world_offset=world_offset)
+    for _ in range(settle):
+        ar.collide_step(H)
+    ar.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        ar.collide_step(H)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(min(steps, 20))]
+    for e in ev:
+        e[0].record(stream)
+        ar.collide()
+        e[1].record(stream)
+        ar.step(H)
+        e[2].record(stream)
+    torch.cuda.synchronize()
+    collide_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / len(ev)
+    step_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / len(ev)
+    ar.debug_kernel_times(True)
+    for _ in range(min(steps, 20)):
+        ar.collide()
+        ar.step(H)
+    kt = ar.debug_kernel_times(False)
+    balg = ar.algorithmic_bytes_per_world_step()
+    rows = float(np.mean([ar.last_num_rows(w) for w in range(0, W, max(1, W // 128))]))
+    achieved = balg * W / (step_ms * 1e-3) / 1e9
+    out = {"workload": name, "worlds_per_gpu": W, "settle_steps": settle, "steps": steps, "ms_per_step": ms / steps,
+           "mean_rows_per_world": rows, "contacts_dropped": ar.contacts_dropped(),
+           "kernel_ms": {"collide": collide_ms, "step": step_ms, "assemble": float(kt[0]), "sor": float(kt[1]),
+                         "integrate": float(kt[2])},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "algorithmic_bytes_per_world_step": balg}}
+    ar.close()
+    return out, ms
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -453,6 +497,34 @@ def run_b200(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    # ---------------- BASELINE config 5 (strong scaling): 524288 rover worlds split over the GPUs of the job ---------
+    extra = {}
+    if args.workload == "D" and not args.no_extra:
+        total_strong = 524288
+        Ws = total_strong // world_size
+        barrier()
+        res, ms_s = measure_workload(Arena, torch, stream, WORKLOAD, build_rover_worlds, Ws, rank * Ws,
+                                     args.settle, max(10, min(K, 20)), peak)
+        t2 = torch.tensor([ms_s], dtype=torch.float64, device="cuda")
+        if world_size > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        ms_s = float(t2.cpu()[0])
+        res["total_worlds"] = total_strong
+        res["ms_per_step"] = ms_s / res["steps"]
+        res["value"] = total_strong * res["steps"] / (ms_s * 1e-3)
+        res["unit"] = UNIT
+        res["scaling"] = "strong (total worlds fixed at 524288; same per-world seeds for every GPU count)"
+        extra["strong_scaling_524288"] = res
+        # ---------------- BASELINE configs 2 and 3 at their sizes (one GPU each; rank 0 reports) ----------------
+        if rank == 0:
+            for key, name, builder, Wx, settle_x in (("config_B_4096", WORKLOADS["B"], build_box_stack_worlds, 4096, 150),
+                                                     ("config_C_16384", WORKLOADS["C"], build_quadruped_worlds, 16384, 300)):
+                r, ms_x = measure_workload(Arena, torch, stream, name, builder, Wx, 0, settle_x, 100, peak)
+                r["value"] = Wx * r["steps"] / (ms_x * 1e-3)
+                r["unit"] = UNIT
+                extra[key] = r
+        barrier()
     achieved = balg * W / (step_ms * 1e-3) / 1e9
     mean_rows = float(np.mean([ar.last_num_rows(w) for w in range(0, W, max(1, W // 256))]))
     # compulsory traffic of the SOR kernel per world: rows in (64 B), lambda out (4 B), fch out, counters
@@ -520,6 +592,7 @@ def run_b200(args):
                                                if k in per_kernel_traffic and ms_k > 0},
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
             "clocks": clocks,
+            "extra_configs": extra,
             "wall_s": t_wall,
         }
         if world_size == 1 and args.workload == "D" and not args.no_facade:
@@ -565,6 +638,8 @@ def main():
     ap.add_argument("--worlds", type=int, default=WORLDS_PER_GPU, help="worlds per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-facade", action="store_true", help="skip the C++ plugin-API leg (e2e_facade)")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the secondary configurations (strong scaling at 524288 worlds, configs B and C)")
     ap.add_argument("--no-graph", action="store_true",
                     help="profiling aid: launch the four kernels directly instead of replaying the CUDA graph")
     ap.add_argument("--settle", type=int, default=SETTLE_STEPS, help="profiling aid: untimed settle steps")

@@ -104,3 +104,124 @@ def test_config_d_entirely_through_the_loader(cuda_lib, tmp_path):
     d = np.abs(got.astype(np.float64) - want)
     print("facade vs C ABI rover worlds: max |diff|", d.max())
     assert np.array_equal(got, want)
+
+
+def test_scene_construction_matches_the_reference_restatement(cuda_lib, orc_lib):
+    """SURVEY 8 rows a11 / a12 through the plugin API (setup_test): every object type's mass pipeline -- sphere,
+    capsule and cylinder with a rotated object pose, the three Inertial variants, and a composite frame whose
+    centre of mass is re-centred twice (reference src/objects/*.cpp createMass, Frame.cpp:794-851) -- and the joint
+    set-up: spring / damper constants mapped to stop ERP / CFM and motor fmax, jointCFM, the forced lo = hi = 0,
+    hinge2's axis-2 values written over the axis-1 slots, a child-only (reversed) hinge, the friction coefficient
+    (Joint.cpp:147-273 and the per-type createJoint).  Compared with oracle/orc_mars.c, which restates the same
+    reference lines on the CPU."""
+    import ctypes as C
+    import json
+    exe = os.path.join(ROOT, "mars_ode_physics_b200", "lib", "setup_test")
+    assert os.path.exists(exe), "setup_test missing: run __graft_entry__.build()"
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    got = json.loads(res.stdout)
+
+    L = orc_lib
+    L.orc_mars_create.restype = C.c_void_p
+    m = C.c_void_p(L.orc_mars_create())
+    L.orc_mars_init_the_world(m)
+    L.orc_mars_set_step_size(m, C.c_double(0.002))
+    vec = lambda *v: (C.c_double * len(v))(*v)
+    s30, c30 = math.sin(0.5 * 0.5235987755982988), math.cos(0.5 * 0.5235987755982988)
+
+    def mass(kind, *a):
+        mm = orc.Mass()
+        {"sphere": lambda: L.orc_mass_set_sphere_total(C.byref(mm), C.c_double(a[0]), C.c_double(a[1])),
+         "capsule": lambda: L.orc_mass_set_capsule_total(C.byref(mm), C.c_double(a[0]), 3, C.c_double(a[1]), C.c_double(a[2])),
+         "cylinder": lambda: L.orc_mass_set_cylinder_total(C.byref(mm), C.c_double(a[0]), 3, C.c_double(a[1]), C.c_double(a[2])),
+         "box": lambda: L.orc_mass_set_box_total(C.byref(mm), C.c_double(a[0]), C.c_double(a[1]), C.c_double(a[2]), C.c_double(a[3])),
+         "box_density": lambda: L.orc_mass_set_box(C.byref(mm), C.c_double(a[0]), C.c_double(a[1]), C.c_double(a[2]), C.c_double(a[3])),
+         }[kind]()
+        return mm
+
+    frames = {}
+
+    def add(name, mm, pos, q=(1, 0, 0, 0)):
+        if name not in frames:
+            frames[name] = L.orc_mars_create_frame(m, C.c_double(1.1), C.c_double(1.1))
+        L.orc_mars_frame_add_object(m, frames[name], C.byref(mm), vec(*pos), vec(*q))
+
+    add("fs", mass("sphere", 2.0, 0.15), (0.1, 0.2, 0.3))
+    add("fc", mass("capsule", 1.5, 0.05, 0.4), (0.0, 0.0, 1.0), (c30, s30, 0, 0))
+    add("fy", mass("cylinder", 0.8, 0.1, 0.3), (0.5, 0.0, 0.5), (c30, 0, s30, 0))
+    mi = orc.Mass()
+    mi.mass = 1.2
+    mi.I[:] = [0.02, 0.001, 0.0, 0.001, 0.03, 0.002, 0.0, 0.002, 0.025]
+    add("fi", mi, (-0.3, 0.0, 0.2))
+    add("fb", mass("box_density", 500.0, 0.2, 0.1, 0.05), (0.0, 0.4, 0.2))
+    add("fsph", mass("sphere", 0.6, 0.07), (0.2, -0.4, 0.3))   # density 0 -> the mass branch
+    add("comp", mass("box", 1.0, 0.4, 0.2, 0.1), (0.0, 0.0, 0.5))
+    add("comp", mass("sphere", 0.3, 0.05), (0.2, 0.0, 0.6))
+    add("comp", mass("cylinder", 0.5, 0.04, 0.2), (-0.1, 0.1, 0.45), (c30, s30, 0, 0))
+
+    for name, fid in frames.items():
+        mo, Io, po = C.c_double(), (C.c_double * 9)(), (C.c_double * 3)()
+        L.orc_mars_frame_get_mass(m, fid, C.byref(mo), Io)
+        L.orc_mars_frame_get_position(m, fid, po)
+        g = got["frames"][name]
+        assert abs(g["mass"] - mo.value) < 1e-12 * max(1.0, mo.value), (name, g["mass"], mo.value)
+        assert np.allclose(g["I"], Io[:], rtol=1e-10, atol=1e-14), (name, g["I"], Io[:])
+        assert np.allclose(g["frame_pos"], po[:], atol=1e-7), (name, g["frame_pos"], po[:])   # fp32 body position
+        bo = (C.c_double * 3)()
+        L.orc_body_get_position(C.c_void_p(L.orc_mars_world(m)), L.orc_mars_frame_body(m, fid), bo)
+        assert np.allclose(g["body_pos"], bo[:], atol=1e-6), (name, g["body_pos"], bo[:])
+    # composite: the frame still reports its origin although the body sits at the common centre of mass
+    assert np.allclose(got["frames"]["comp"]["frame_pos"], 0.0, atol=1e-7)
+    assert abs(got["frames"]["comp"]["mass"] - 1.8) < 1e-12
+
+    L.orc_mars_world.restype = C.c_void_p
+    L.orc_joint_get_param.restype = C.c_double
+    w = C.c_void_p(L.orc_mars_world(m))
+
+    def joint(jtype, parent, child, anchor, damping=None, stiffness=None, jcfm=None, friction=None):
+        cfg = orc.MarsJointCfg()
+        cfg.type = jtype
+        cfg.parent = frames.get(parent, -1)
+        cfg.child = frames.get(child, -1)
+        cfg.anchor[:] = anchor
+        cfg.axis1[:] = (0, 1, 0)
+        cfg.axis2[:] = (0, 0, 1)
+        for key, val in (("spring_damping", damping), ("spring_stiffness", stiffness), ("joint_cfm", jcfm)):
+            setattr(cfg, "has_" + key, int(val is not None))
+            setattr(cfg, key, float(val or 0.0))
+        cfg.has_friction = int(friction is not None)
+        cfg.friction_coefficient = float(friction or 0.0)
+        j = L.orc_mars_create_joint(m, C.byref(cfg))
+        assert j >= 0
+        return L.orc_mars_joint_ode_id(m, j)
+
+    P = orc
+    want = {"hinge_spring_damper": joint(1, "fs", "fc", (0.05, 0.1, 0.6), 0.5, 20.0, 1e-4, 0.02),
+            "slider_spring": joint(3, "fc", "fy", (0, 0, 0), None, 15.0),
+            "hinge2_damper": joint(2, "comp", "fsph", (0.1, -0.2, 0.4), 0.3),
+            "fixed": joint(6, "fi", "fb", (0, 0, 0)),
+            "hinge_child_only": joint(1, "nonexistent", "fy", (0.5, 0.0, 0.7))}
+    params = {"fmax": 5, "vel": 2, "lo": 0, "hi": 1, "stop_cfm": 10, "stop_erp": 9, "cfm": 8, "fmax2": 5 | 0x100,
+              "lo2": 0 | 0x100}
+    for name, jid in want.items():
+        g = got["joints"][name]
+        for key, pid in params.items():
+            if name == "fixed" and key not in ("cfm",):
+                continue
+            wv = L.orc_joint_get_param(w, jid, pid)
+            assert (g[key] == wv) or abs(g[key] - wv) <= 1e-12 * max(1.0, abs(wv)), (name, key, g[key], wv)
+        if name != "fixed" and name != "slider_spring":
+            a = (C.c_double * 3)()
+            L.orc_joint_get_anchor(w, jid, a)
+            assert np.allclose(g["anchor"], a[:], atol=1e-6), (name, g["anchor"], a[:])
+        if name != "fixed":
+            ax = (C.c_double * 3)()
+            L.orc_joint_get_axis1(w, jid, ax)
+            assert np.allclose(g["axis1"], ax[:], atol=1e-6), (name, g["axis1"], ax[:])
+    assert got["joints"]["hinge_spring_damper"]["friction"] == 0.02 and got["joints"]["fixed"]["friction"] == -0.1
+    # the documented quirks made it through: damping as motor (fmax = damping, vel = 0), spring as stop with the
+    # forced lo = hi = 0, hinge2 zeroing the axis-1 stop parameters
+    assert got["joints"]["hinge_spring_damper"]["fmax"] == 0.5 and got["joints"]["hinge_spring_damper"]["lo"] == 0.0
+    assert got["joints"]["hinge2_damper"]["fmax2"] == 0.3
+    L.orc_mars_destroy(m)
