@@ -210,9 +210,9 @@ def test_scene_construction_matches_the_reference_restatement(cuda_lib, orc_lib)
             if name == "fixed" and key not in ("cfm",):
                 continue
             wv = L.orc_joint_get_param(w, jid, pid)
-                # (VEL / FMAX are per-world commands: the arena keeps them as fp32)
-                tol = 1e-6 if key in ("fmax", "vel", "fmax2") else 1e-12
-                assert (g[key] == wv) or abs(g[key] - wv) <= tol * max(1.0, abs(wv)), (name, key, g[key], wv)
+            # (VEL / FMAX are per-world commands: the arena keeps them as fp32)
+            tol = 1e-6 if key in ("fmax", "vel", "fmax2") else 1e-12
+            assert (g[key] == wv) or abs(g[key] - wv) <= tol * max(1.0, abs(wv)), (name, key, g[key], wv)
         if name != "fixed" and name != "slider_spring":
             a = (C.c_double * 3)()
             L.orc_joint_get_anchor(w, jid, a)
