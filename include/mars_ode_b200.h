@@ -84,6 +84,15 @@ enum {
     B2P_REORDER_NONE = 1
 };
 
+/* Order of the constraint rows inside a world's solve.  ODE (util.cpp dxProcessIslands) solves one island of
+ * joint-connected bodies at a time, visiting bodies, joints and the step's contacts depth-first from the most
+ * recently created body; the default here is one block per world (joints in creation order, then the contact
+ * stream).  Both solve the same LCP; after the fixed number of sweeps they differ by the unconverged part. */
+enum {
+    B2P_ORDER_WORLD_BLOCK = 0,
+    B2P_ORDER_ODE_ISLANDS = 1
+};
+
 /* geom classes for the device collision path (dCreate* -- absent from the reference tree,
  * SURVEY.md section 8 a13) */
 enum {
@@ -166,6 +175,7 @@ int b2p_world_set_contact_surface_layer(b2p_arena *a, double d);
 int b2p_world_set_quickstep_num_iterations(b2p_arena *a, int n);
 int b2p_world_set_quickstep_w(b2p_arena *a, double w);
 int b2p_world_set_reorder_method(b2p_arena *a, int method);
+int b2p_world_set_row_order(b2p_arena *a, int order);
 int b2p_world_rand_set_seed(b2p_arena *a, uint32_t seed);                   /* dRandSetSeed :169 (per world) */
 int b2p_world_rand_get_seed(b2p_arena *a, int world, uint32_t *seed);
 

@@ -93,6 +93,10 @@ class Arena:
     def set_reorder_method(self, m):
         self._check(self.lib.b2p_world_set_reorder_method(self.h, m))
 
+    def set_order_mode(self, mode):
+        """0: one block per world (default); 1: ODE's island order (capi.ORDER_ODE_ISLANDS)"""
+        self._check(self.lib.b2p_world_set_row_order(self.h, int(mode)))
+
     def rand_set_seed(self, seed):
         self._check(self.lib.b2p_world_rand_set_seed(self.h, seed))
 

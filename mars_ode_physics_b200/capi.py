@@ -20,6 +20,7 @@ PARAM_GROUP2 = 0x100
 CONTACT_MU2, CONTACT_SOFT_ERP, CONTACT_SOFT_CFM, CONTACT_ROLLING = 0x001, 0x008, 0x010, 0x400
 CONTACT_APPROX1 = 0x7000
 REORDER_RANDOMLY, REORDER_NONE = 0, 1
+ORDER_WORLD_BLOCK, ORDER_ODE_ISLANDS = 0, 1
 SOR_AUTO, SOR_PAIRED, SOR_TMEM = -1, 0, 1
 GEOM_SPHERE, GEOM_BOX, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_PLANE, GEOM_HEIGHTFIELD = range(6)
 E_REJECTED = -6
@@ -166,6 +167,7 @@ SIGNATURES = {
     "b2p_contacts_dropped": (_I, [_P, C.POINTER(C.c_longlong)]),
     "b2p_collide_record_pairs": (_I, [_P, _I]),
     "b2p_debug_lcp_residual": (_I, [_P, _P]),
+    "b2p_world_set_row_order": (_I, [_P, _I]),
     "b2p_host_alloc": (_P, [C.c_size_t]),
     "b2p_host_free": (None, [_P]),
 }

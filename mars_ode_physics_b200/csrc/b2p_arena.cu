@@ -20,13 +20,13 @@
 #include "b2p_dev.h"
 #include "b2p_universal.h"
 
-extern "C" size_t b2p_assemble_smem_bytes(int nb, int nj);
+extern "C" size_t b2p_assemble_smem_bytes(int nb, int nj, int maxc, int islands);
 extern "C" size_t b2p_sor_smem_bytes(int nb, int maxrows, int rows_resident);
 extern "C" int b2p_sor_register_rows(int maxrows, int wanted);
 extern "C" size_t b2p_sor_tmem_smem_bytes(int nb, int maxrows, int pool, int warps);
 extern "C" int b2p_sor_tmem_rows_on_chip(int kr, int warps);
 extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
-extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, int nj, cudaStream_t stream);
+extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, int nj, int maxc, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_residual(const StepParams *P, float *out, cudaStream_t stream);
@@ -227,7 +227,9 @@ struct b2p_arena {
     // solver scratch (device only)
     float4 *d_rows = nullptr;
     float *d_lambda = nullptr, *d_rowS = nullptr, *d_invIw = nullptr, *d_fcacc = nullptr;
-    uint32_t *d_cmap = nullptr;
+    uint32_t *d_cmap = nullptr, *d_isl = nullptr;
+    uint8_t *d_jslot = nullptr;
+    int order_mode = B2P_ORDER_WORLD_BLOCK;
     size_t scratch_rows = 0, scratch_nb = 0, scratch_maxc = 0;
     int rows_resident = 0;   // SOR kernel: sweep positions kept in shared memory; 0 = automatic
     int rows_registers = -1; // SOR kernel: sweep positions kept in registers; < 0 = automatic
@@ -449,6 +451,10 @@ void free_scratch(b2p_arena *a)
     if (a->d_invIw) cudaFree(a->d_invIw);
     if (a->d_fcacc) cudaFree(a->d_fcacc);
     if (a->d_cmap) cudaFree(a->d_cmap);
+    if (a->d_isl) cudaFree(a->d_isl);
+    if (a->d_jslot) cudaFree(a->d_jslot);
+    a->d_isl = nullptr;
+    a->d_jslot = nullptr;
     if (a->d_hw_rows) cudaFree(a->d_hw_rows);
     a->d_hw_rows = nullptr;
     a->d_rows = nullptr;
@@ -652,7 +658,8 @@ int finalize(b2p_arena *a)
     if ((rc = mirror_to_device(a, a->cfb))) return rc;
     if ((rc = mirror_to_device(a, a->nrows))) return rc;
     if ((rc = mirror_to_device(a, a->jrows))) return rc;
-    if (a->scratch_rows != (size_t)maxrows || a->scratch_nb != (size_t)nb || a->scratch_maxc != (size_t)a->maxc) {
+    if (a->scratch_rows != (size_t)maxrows || a->scratch_nb != (size_t)nb || a->scratch_maxc != (size_t)a->maxc ||
+        !a->d_jslot) {
         free_scratch(a);
         const size_t mr = (size_t)std::max(maxrows, 1), Wp = (size_t)a->Wp;
         CUDA_TRY(cudaMalloc(&a->d_rows, sizeof(float4) * (mr + 1) * 4 * Wp));
@@ -661,6 +668,10 @@ int finalize(b2p_arena *a)
         CUDA_TRY(cudaMalloc(&a->d_invIw, sizeof(float) * (size_t)std::max(nb, 1) * 9 * Wp));
         CUDA_TRY(cudaMalloc(&a->d_fcacc, sizeof(float) * (size_t)std::max(nb, 1) * 6 * Wp));
         CUDA_TRY(cudaMalloc(&a->d_cmap, sizeof(uint32_t) * (size_t)std::max(a->maxc, 1) * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_isl, sizeof(uint32_t) * (size_t)std::max(nb, 1) * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_jslot, (size_t)std::max(nj, 1) * Wp));
+        CUDA_TRY(cudaMemsetAsync(a->d_isl, 0, sizeof(uint32_t) * (size_t)std::max(nb, 1) * Wp, a->stream));
+        CUDA_TRY(cudaMemsetAsync(a->d_jslot, 0, (size_t)std::max(nj, 1) * Wp, a->stream));
         CUDA_TRY(cudaMalloc(&a->d_hw_rows, sizeof(int)));
         CUDA_TRY(cudaMemsetAsync(a->d_hw_rows, 0, sizeof(int), a->stream));
         if (!a->h_hw_rows) CUDA_TRY(cudaMallocHost(&a->h_hw_rows, sizeof(int)));
@@ -991,6 +1002,12 @@ int b2p_world_set_reorder_method(b2p_arena *a, int m)
 {
     if (!a || (m != B2P_REORDER_RANDOMLY && m != B2P_REORDER_NONE)) return fail(B2P_EINVAL, "bad reorder method");
     a->reorder = m;
+    return 0;
+}
+int b2p_world_set_row_order(b2p_arena *a, int order)
+{
+    if (!a || (order != B2P_ORDER_WORLD_BLOCK && order != B2P_ORDER_ODE_ISLANDS)) return fail(B2P_EINVAL, "bad row order");
+    a->order_mode = order;
     return 0;
 }
 int b2p_world_rand_set_seed(b2p_arena *a, uint32_t seed)
@@ -2182,6 +2199,9 @@ int prepare_step(b2p_arena *a, double step_size, StepParams &P, bool &use_tmem)
     P.fcacc = a->d_fcacc;
     P.rows = a->d_rows;
     P.cmap = a->d_cmap;
+    P.isl = a->d_isl;
+    P.jslot = a->d_jslot;
+    P.order_mode = a->order_mode;
     P.jrows = a->jrows.dev;
     P.ccount = a->ccount.dev;
     P.nrows = a->nrows.dev;
@@ -2224,7 +2244,9 @@ int prepare_step(b2p_arena *a, double step_size, StepParams &P, bool &use_tmem)
         P.rows_registers = b2p_sor_register_rows(maxrows, a->rows_registers);
         P.rows_resident = pick_rows_resident(a, nb, maxrows, P.rows_registers);
     }
-    if (b2p_assemble_smem_bytes(nb, (int)a->joints.size()) > kSmemMax ||
+    if (a->order_mode == B2P_ORDER_ODE_ISLANDS && a->maxc > 64)
+        return fail(B2P_ECAPACITY, "the island row order supports at most 64 contacts per world");
+    if (b2p_assemble_smem_bytes(nb, (int)a->joints.size(), a->maxc, a->order_mode) > kSmemMax ||
         (!use_tmem && b2p_sor_smem_bytes(nb, maxrows, P.rows_resident) > kSmemMax))
         return fail(B2P_ECAPACITY, "scene needs more than %zu bytes of shared memory per CTA", kSmemMax);
     return 0;
@@ -2237,7 +2259,7 @@ int enqueue_step(b2p_arena *a, const StepParams &P, bool use_tmem, cudaStream_t 
     const int maxrows = (int)a->joints.size() * B2P_ROWS_PER_JOINT + a->maxc * rpc_of(a);
     const bool timing = a->timing && !capturing;
     if (timing) CUDA_TRY(cudaEventRecord(a->ev[0], st));
-    CUDA_TRY(b2p_launch_assemble(&P, nb, (int)a->joints.size(), st));
+    CUDA_TRY(b2p_launch_assemble(&P, nb, (int)a->joints.size(), a->maxc, st));
     if (a->io_stream) { // lets the next command upload start as soon as this kernel has read jcmd
         if (!a->ev_asm_done) CUDA_TRY(cudaEventCreateWithFlags(&a->ev_asm_done, cudaEventDisableTiming));
         if (capturing) CUDA_TRY(cudaEventRecordWithFlags(a->ev_asm_done, st, cudaEventRecordExternal));

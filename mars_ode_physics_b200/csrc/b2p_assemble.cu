@@ -33,6 +33,7 @@ struct Smem {
     float *sw; // [nb*6][BD]  symmetric sqrt(invI_world): xx xy xz yy yz zz
     float *pq; // [nb*7][BD]  position and quaternion of every body: the joints and contacts re-read the poses
                //             of their bodies, and a shared-memory read costs a tenth of a global one
+    uint8_t *scratch; // island order only: [(nj + maxc) + nb][BD] bytes (item list, depth-first stack)
 };
 
 // pose of body b from the copy phase 1 left in shared memory
@@ -132,7 +133,7 @@ __device__ __forceinline__ float emit_row(const StepParams &P, const Smem &S, in
     return sa;
 }
 
-__global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
+template <bool ISLANDS> __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DevTemplate *__restrict__ T = P.T;
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
         for (int i = tid; i < nj * (int)(sizeof(DevJoint) / 4); i += BD) sj[i] = __ldg(gj + i);
         S.bodies = (const DevBody *)sb;
         S.joints = (const DevJoint *)sj;
+        S.scratch = (uint8_t *)(sj + (size_t)nj * (sizeof(DevJoint) / 4));
         __syncthreads();
     }
     if (w >= P.W) return;
@@ -299,14 +301,56 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
     }
 
     // ---------------- phase 2: constraint rows ----------------
-    // ODE orders rows with findex < 0 first (in row order) and friction-dependent rows last.
-    // Head rows are appended as they are emitted; dependent rows are recorded per contact in a bit
-    // mask and appended after all contacts are known.
-    int nhead = 0;
+    // ODE solves one island at a time; inside an island the rows with findex < 0 come first (in joint order) and
+    // the friction-dependent rows last.  Every island therefore is a block [start, start + nh) (+) [.., start + m)
+    // of slots; the SOR kernels get the block table (isl) for ODE's per-island reshuffles.
+    //   ISLANDS == false: the whole world is one block, joints in creation order, then the contact stream.
+    //   ISLANDS == true:  ODE's dxProcessIslands order (util.cpp): bodies from the most recently created one,
+    //                     depth-first through each body's joint list (most recently attached first: the step's
+    //                     contacts in reverse stream order, then the joints in reverse creation order).
+    int nc = G(P.ccount, 0);
+    if (nc > maxc) nc = maxc;
 
-    for (int j = 0; j < nj; j++) {
+    // independent (head) rows of contact c; `tails` gets its friction-dependent rows
+    auto contact_counts = [&](int c, int &tails) -> int {
+        const int mode = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_MODE));
+        const float mu = G(P.crec, c * B2P_CONTACT_FIELDS + CR_MU);
+        const float mu2 = G(P.crec, c * B2P_CONTACT_FIELDS + CR_MU2);
+        const bool axisdep = (mode & 0x001) != 0;
+        int heads = 1;
+        tails = 0;
+        if (mu > 0.f) ((mode & 0x1000) ? tails : heads)++;
+        if (axisdep ? (mu2 > 0.f) : (mu > 0.f)) ((mode & 0x2000) ? tails : heads)++;
+        if ((mode & 0x400) && rpc >= 6) {
+            const float rho0 = G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHO);
+            const float rho1 = axisdep ? G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHO2) : rho0;
+            const float rho2 = axisdep ? G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHON) : rho0;
+            if (rho0 > 0.f) ((mode & 0x1000) ? tails : heads)++;
+            if (rho1 > 0.f) ((mode & 0x2000) ? tails : heads)++;
+            if (rho2 > 0.f) ((mode & 0x4000) ? tails : heads)++;
+        }
+        return heads;
+    };
+
+    // per-world commands of joint j
+    auto joint_cmd = [&](int j, const DevJoint &jc) -> LimotCmd {
+        LimotCmd cmd = {0.f, 0.f, 0.f, 0.f};
+        if (jc.type != 6 && jc.type != 4) {
+            cmd.vel1 = G(P.jcmd, j * 4 + 0);
+            cmd.fmax1 = G(P.jcmd, j * 4 + 1);
+            if (jc.type == 2 || jc.type == 5) {
+                cmd.vel2 = G(P.jcmd, j * 4 + 2);
+                cmd.fmax2 = G(P.jcmd, j * 4 + 3);
+            }
+        }
+        return cmd;
+    };
+
+    // rows of joint j at slots head, head + 1, ... (all of a joint's rows are independent rows)
+    auto emit_joint = [&](int j, int &head) {
         const DevJoint &jc = S.joints[j];
         int jr = 0;
+        G(P.jslot, j) = (uint8_t)head;
         if (jc.b0 >= 0) {
             BodyPose p0, p1;
             PairCtx pc;
@@ -315,47 +359,17 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
             load_pose_s(S, jc.b0, tid, p0);
             if (jc.b1 >= 0) load_pose_s(S, jc.b1, tid, p1);
             pair_ctx(pc, S, tid);
-            LimotCmd cmd = {0.f, 0.f, 0.f, 0.f};
-            if (jc.type != 6 && jc.type != 4) {
-                cmd.vel1 = G(P.jcmd, j * 4 + 0);
-                cmd.fmax1 = G(P.jcmd, j * 4 + 1);
-                if (jc.type == 2 || jc.type == 5) {
-                    cmd.vel2 = G(P.jcmd, j * 4 + 2);
-                    cmd.fmax2 = G(P.jcmd, j * 4 + 3);
-                }
-            }
-            auto emit = [&](const Row &r) { emit_row(P, S, w, tid, nhead++, r, pc); };
+            const LimotCmd cmd = joint_cmd(j, jc);
+            auto emit = [&](const Row &r) { emit_row(P, S, w, tid, head++, r, pc); };
             jr = joint_rows<true>(P, jc, p0, p1, cmd, 0, w, emit);
         }
         // rows of the joint | which limit / motor rows exist (b2p_rows.cuh); the integrate kernel follows it
         G(P.jrows, j) = (uint8_t)jr;
-    }
+    };
 
-    // ---- contacts (ODE contact.cpp getInfo1/getInfo2 for the mode bits Frame::addContact sets)
-    int nc = G(P.ccount, 0);
-    if (nc > maxc) nc = maxc;
-    // Pre-pass: how many rows of the contacts are independent (findex < 0), so that the dependent ones
-    // can be written straight to their place behind all independent rows.
-    int ntail = nhead;
-    for (int c = 0; c < nc; c++) {
-        const int mode = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_MODE));
-        const float mu = G(P.crec, c * B2P_CONTACT_FIELDS + CR_MU);
-        const float mu2 = G(P.crec, c * B2P_CONTACT_FIELDS + CR_MU2);
-        const bool axisdep = (mode & 0x001) != 0;
-        ntail += 1;
-        if (mu > 0.f && !(mode & 0x1000)) ntail++;
-        if ((axisdep ? (mu2 > 0.f) : (mu > 0.f)) && !(mode & 0x2000)) ntail++;
-        if ((mode & 0x400) && rpc >= 6) {
-            const float rho0 = G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHO);
-            const float rho1 = axisdep ? G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHO2) : rho0;
-            const float rho2 = axisdep ? G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHON) : rho0;
-            if (rho0 > 0.f && !(mode & 0x1000)) ntail++;
-            if (rho1 > 0.f && !(mode & 0x2000)) ntail++;
-            if (rho2 > 0.f && !(mode & 0x4000)) ntail++;
-        }
-    }
-    const int nhead_total = ntail;
-    for (int c = 0; c < nc; c++) {
+    // ---- one contact (ODE contact.cpp getInfo1/getInfo2 for the mode bits Frame::addContact sets): independent
+    // rows at head++, friction-dependent rows (findex = its normal row) at tail++
+    auto emit_contact = [&](int c, int &head, int &tail) {
         const int ids = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_IDS));
         const int b0 = ids & 0xff;
         const int b1 = ((ids >> 8) & 0xff) == 0xff ? -1 : ((ids >> 8) & 0xff);
@@ -397,9 +411,9 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
         if (mode & 0x010) r.cfm = soft_cfm;
         r.lo = 0.f;
         r.hi = INFINITY;
-        const int nslot = nhead;
-        const int tslot = ntail;
-        const float sn = emit_row(P, S, w, tid, nhead++, r, pc);
+        const int nslot = head;
+        const int tslot = tail;
+        const float sn = emit_row(P, S, w, tid, head++, r, pc);
         int row = 1, depmask = 0;
         float t1[3], t2[3];
         plane_space(n, t1, t2);
@@ -413,9 +427,9 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
                 r.fr = nslot + 1;
                 r.sn = sn;
                 depmask |= 1 << (row - 1);
-                emit_row(P, S, w, tid, ntail++, r, pc);
+                emit_row(P, S, w, tid, tail++, r, pc);
             } else {
-                emit_row(P, S, w, tid, nhead++, r, pc);
+                emit_row(P, S, w, tid, head++, r, pc);
             }
             row++;
         };
@@ -465,9 +479,98 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
         // present << 24 / 25 (the integrate kernel rebuilds the contact's feedback from it)
         G(P.cmap, c) = (uint32_t)(row | (depmask << 3)) | ((uint32_t)nslot << 8) | ((uint32_t)tslot << 16) |
                        ((uint32_t)(fr1 ? 1 : 0) << 24) | ((uint32_t)(fr2 ? 1 : 0) << 25);
+    };
+
+    int ntail = 0, nisl = 0; // rows of the world so far; islands (blocks) so far
+    if (!ISLANDS) {
+        int head = 0;
+        for (int j = 0; j < nj; j++) emit_joint(j, head);
+        // how many rows of the contacts are independent, so that the dependent ones can be written straight to
+        // their place behind all independent rows
+        int tail = head;
+        for (int c = 0; c < nc; c++) {
+            int t;
+            tail += contact_counts(c, t);
+        }
+        const int nh = tail;
+        for (int c = 0; c < nc; c++) emit_contact(c, head, tail);
+        ntail = tail;
+        G(P.isl, 0) = (uint32_t)nh << 8 | (uint32_t)ntail << 16; // start 0 | independent rows << 8 | rows << 16
+        nisl = 1;
+    } else {
+        // scratch of this thread behind the template copy: the island's items in discovery order and the
+        // depth-first stack (bytes; item = joint index, or 0x80 | contact index)
+        uint8_t *const seq = S.scratch + tid, *const stack = S.scratch + (size_t)(nj + maxc) * BD + tid;
+        uint32_t visited = 0;
+        uint64_t jtag = 0, ctag = 0;
+        for (int bb = nb - 1; bb >= 0; bb--) {
+            if (visited >> bb & 1u) continue;
+            visited |= 1u << bb;
+            int nseq = 0, sp = 0, b = bb;
+            for (;;) {
+                for (int c = nc - 1; c >= 0; c--) { // this step's contacts: attached last, listed first
+                    if (ctag >> c & 1ull) continue;
+                    const int ids = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_IDS));
+                    const int c0 = ids & 0xff, c1 = (ids >> 8) & 0xff;
+                    if (c0 != b && c1 != b) continue;
+                    ctag |= 1ull << c;
+                    seq[(size_t)nseq++ * BD] = (uint8_t)(0x80 | c);
+                    const int other = c0 == b ? c1 : c0;
+                    if (other != 0xff && !(visited >> other & 1u)) {
+                        visited |= 1u << other;
+                        stack[(size_t)sp++ * BD] = (uint8_t)other;
+                    }
+                }
+                for (int j = nj - 1; j >= 0; j--) {
+                    const DevJoint &jc = S.joints[j];
+                    if ((jtag >> j & 1ull) || (jc.b0 != b && jc.b1 != b)) continue;
+                    jtag |= 1ull << j;
+                    seq[(size_t)nseq++ * BD] = (uint8_t)j;
+                    const int other = jc.b0 == b ? jc.b1 : jc.b0;
+                    if (other >= 0 && !(visited >> other & 1u)) {
+                        visited |= 1u << other;
+                        stack[(size_t)sp++ * BD] = (uint8_t)other;
+                    }
+                }
+                if (sp == 0) break;
+                b = stack[(size_t)--sp * BD];
+            }
+            if (nseq == 0) continue; // a free body: an island without rows
+            // independent rows of the island: joints contribute all of theirs, contacts per their mode bits
+            int nh = 0, nt = 0;
+            for (int i = 0; i < nseq; i++) {
+                const int it = seq[(size_t)i * BD];
+                if (it & 0x80) {
+                    int t;
+                    nh += contact_counts(it & 0x7f, t);
+                    nt += t;
+                } else {
+                    const DevJoint &jc = S.joints[it];
+                    BodyPose p0, p1;
+                    load_pose_s(S, jc.b0, tid, p0);
+                    if (jc.b1 >= 0) load_pose_s(S, jc.b1, tid, p1);
+                    nh += joint_row_count(jc, p0, p1, joint_cmd(it, jc));
+                }
+            }
+            const int start = ntail;
+            int head = start, tail = start + nh;
+            for (int i = 0; i < nseq; i++) {
+                const int it = seq[(size_t)i * BD];
+                if (it & 0x80) emit_contact(it & 0x7f, head, tail);
+                else emit_joint(it, head);
+            }
+            ntail = start + nh + nt;
+            if (nh + nt > 0) G(P.isl, nisl++) = (uint32_t)start | (uint32_t)nh << 8 | (uint32_t)(nh + nt) << 16;
+        }
+        for (int j = 0; j < nj; j++) { // joints without a body produce no rows
+            if (!(jtag >> j & 1ull)) {
+                G(P.jrows, j) = 0;
+                G(P.jslot, j) = 0;
+            }
+        }
     }
-    // rows of the step | independent rows << 16 (ODE sweeps [0,nhead) and [nhead,m) as separate partitions)
-    G(P.nrows, 0) = ntail | (nhead_total << 16);
+    // rows of the step | islands << 16
+    G(P.nrows, 0) = ntail | (nisl << 16);
     // high-water mark of rows per world: the host sizes the SOR kernel's on-chip row storage with it
     const int wmax = __reduce_max_sync(__activemask(), ntail);
     if ((tid & 31) == 0 && wmax > *(volatile int *)P.hw_rows) atomicMax(P.hw_rows, wmax);
@@ -475,24 +578,27 @@ __global__ void __launch_bounds__(BD, 8) b2p_assemble_kernel(const StepParams P)
 
 } // namespace
 
-extern "C" size_t b2p_assemble_smem_bytes(int nb, int nj)
+extern "C" size_t b2p_assemble_smem_bytes(int nb, int nj, int maxc, int islands)
 {
-    return sizeof(float) * (size_t)nb * 19 * BD + (size_t)nb * sizeof(DevBody) + (size_t)nj * sizeof(DevJoint);
+    return sizeof(float) * (size_t)nb * 19 * BD + (size_t)nb * sizeof(DevBody) + (size_t)nj * sizeof(DevJoint) +
+           (islands ? (size_t)(nj + maxc + nb) * BD : 0);
 }
 
-extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, int nj, cudaStream_t stream)
+extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, int nj, int maxc, cudaStream_t stream)
 {
-    static size_t configured_dev[B2P_MAX_DEVICES] = {0}; // cudaFuncSetAttribute is per device
+    static size_t configured_dev[B2P_MAX_DEVICES][2] = {{0, 0}}; // cudaFuncSetAttribute is per device
     int dev = 0;
     cudaGetDevice(&dev);
-    size_t &configured = configured_dev[dev % B2P_MAX_DEVICES];
-    const size_t smem = b2p_assemble_smem_bytes(nb, nj);
+    const int isl = P->order_mode != 0;
+    size_t &configured = configured_dev[dev % B2P_MAX_DEVICES][isl];
+    const size_t smem = b2p_assemble_smem_bytes(nb, nj, maxc, isl);
+    auto kern = isl ? b2p_assemble_kernel<true> : b2p_assemble_kernel<false>;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(b2p_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     const int grid = (P->W + BD - 1) / BD;
-    b2p_assemble_kernel<<<grid, BD, smem, stream>>>(*P);
+    kern<<<grid, BD, smem, stream>>>(*P);
     return cudaGetLastError();
 }

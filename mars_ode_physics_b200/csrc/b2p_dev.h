@@ -13,7 +13,9 @@
 //   crec    float[maxc*16][Wp] the 16-word contact record         (dContact subset)
 //   cfb     float[maxc*3][Wp]  contact feedback f1
 //   seed    uint32[Wp]         per-world LCG state                (dRandSetSeed)
-//   nrows   int[Wp]            rows of the last step | independent ("head") rows << 16
+//   nrows   int[Wp]            rows of the last step | row blocks (islands) << 16
+//   isl     uint32[nb][Wp]     block k: first slot | independent ("head") rows << 8 | rows << 16
+//   jslot   uint8[nj][Wp]      first slot of each joint's rows
 //   rows    float[maxrows][2][Wp][8]  constraint rows in ODE's initial sweep order (slot = position at
 //                              iteration 0) as two 32-byte units per world: J0..J7 | J8..J11 rhs' cfm' bound meta
 //                              (12 mass- and Ad-scaled Jacobian words); one more slot (index maxrows) holds an
@@ -125,6 +127,10 @@ struct StepParams {
     int sor_warps;      // Tensor-Memory SOR kernel: warps per CTA (4 or 8); rows_resident = its overflow pool units
     int worlds_per_cta; // Tensor-Memory SOR kernel: worlds a CTA takes (multiple of 32, <= 32 * sor_warps)
     // post-step outputs of the reference's stepTheWorld for every world (null: not wanted)
+    // ODE solves island by island: block k of a world's rows = start | independent rows << 8 | rows << 16
+    uint32_t *isl;  // [max(nb,1)][Wp]; nrows = rows of the world | blocks << 16
+    uint8_t *jslot; // [nj][Wp]: first slot of joint j's rows
+    int order_mode; // 0: one block per world (joints in creation order, then contacts); 1: ODE's island order
     float *bodyx; // [nb*15][Wp] last_l_vel3 last_a_vel3 l_acc3 a_acc3 contact_force3  (Frame::update, computeContactForce)
     float *jupd;  // [nj*7][Wp]  motor_torque axis1_torque3 joint_load3              (Joint::update)
 };

@@ -58,10 +58,10 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
 
     // ---------------- joint feedback from the pre-step poses: sum of lambda * J over the joint's rows --------
     {
-        int slot = 0;
         for (int j = 0; j < nj; j++) {
             const DevJoint &jc = T->joints[j];
             const int jr = G(P.jrows, j);
+            const int slot = G(P.jslot, j); // first slot of the joint's rows (the row order may be ODE's island order)
             const int mrows = B2P_JR_ROWS(jr);
             float acc[12];
 #pragma unroll
@@ -85,7 +85,6 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
                 const LimotCmd cmd = {0.f, 0.f, 0.f, 0.f};
                 joint_rows<false>(P, jc, p0, p1, cmd, jr, w, emit);
             }
-            slot += mrows;
 #pragma unroll
             for (int q = 0; q < 12; q++) G(P.jfb, j * 13 + q) = acc[q];
             G(P.jfb, j * 13 + 12) = flam;

@@ -282,3 +282,34 @@ B2P_HD int rand_int(uint32_t &seed, int n)
     }
     return (int)(r % un);
 }
+
+#ifdef __CUDACC__
+// ODE's constraint reshuffle (quickstep.cpp ConstraintsReorderingHelper, REORDERING_METHOD__RANDOMLY) for one
+// world whose rows are cut into island blocks (b2p_dev.h: block = first slot | independent rows << 8 | rows << 16).
+// ODE solves the islands one after the other, each with all its iterations, so the draws of the world's LCG are
+// consumed island by island: block k uses, for its reshuffle event `ev` (0-based; `nev` events per solve, at
+// iterations 8, 16, ...), the draws [sum_{i<k} nev d_i + ev d_k, ... + d_k) with d = (nh - 1)+ + (m - nh - 1)+.
+// The kernels sweep all blocks of a world together (they share no row and no body, so the result is the same) and
+// jump through the sequence accordingly.  Returns the seed after ALL events of the step.
+template <class Swap>
+__device__ __forceinline__ uint32_t island_reshuffle(const uint32_t *isl, size_t Wp, int w, int nisl, uint32_t seed0,
+                                                     int ev, int nev, Swap &&swap)
+{
+    uint32_t s = seed0;
+#pragma unroll 1
+    for (int k = 0; k < nisl; k++) {
+        const uint32_t e = isl[(size_t)k * Wp + w];
+        const int start = e & 0xff, nh = (e >> 8) & 0xff, mk = e >> 16;
+        const int d = (nh > 1 ? nh - 1 : 0) + (mk - nh > 1 ? mk - nh - 1 : 0);
+#pragma unroll 1
+        for (int i = 0; i < ev * d; i++) s = 1664525u * s + 1013904223u;
+#pragma unroll 1
+        for (int idx = 1; idx < nh; idx++) swap(start + idx, start + rand_int(s, idx + 1));
+#pragma unroll 1
+        for (int idx = nh + 1; idx < mk; idx++) swap(start + idx, start + nh + rand_int(s, idx - nh + 1));
+#pragma unroll 1
+        for (int i = 0; i < (nev - 1 - ev) * d; i++) s = 1664525u * s + 1013904223u;
+    }
+    return s;
+}
+#endif

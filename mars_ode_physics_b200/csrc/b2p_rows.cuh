@@ -163,6 +163,34 @@ __device__ __forceinline__ void ball_rows(const float *a1, const float *a2, cons
     emit(r);
 }
 
+// getInfo1: the number of rows joint `jc` will produce (what joint_rows<true> then emits, decided by the same tests)
+__device__ __forceinline__ int joint_row_count(const DevJoint &jc, const BodyPose &p0, const BodyPose &p1,
+                                               const LimotCmd &cmd)
+{
+    if (jc.b0 < 0) return 0;
+    int base;
+    switch (jc.type) {
+    case 1: base = 5; break;
+    case 2: if (jc.b1 < 0) return 0; base = 4; break;
+    case 3: base = 5; break;
+    case 4: return 3;
+    case 5: base = 4; break;
+    case 6: return 6;
+    default: return 0;
+    }
+    LimotState st;
+    joint_limit_state(jc, p0, p1, st);
+    int rows = base + ((cmd.fmax1 > 0.f || st.limit) ? 1 : 0);
+    if (jc.type == 2) {
+        rows += cmd.fmax2 > 0.f ? 1 : 0; // ODE's hinge2 has no stop on its second axis
+    } else if (jc.type == 5) {
+        LimotState st2;
+        joint_limit_state2(jc, p0, p1, st2);
+        rows += (cmd.fmax2 > 0.f || st2.limit) ? 1 : 0;
+    }
+    return rows;
+}
+
 // All rows of joint `jc` in getInfo2 order, each handed to emit(const Row &).  Returns the joint's jrows byte.
 // `p0`, `p1`: pre-step poses of its bodies (p1 unused without a second body); `flags_in`: the jrows byte of the
 // FULL pass (only read when FULL is false).

@@ -80,13 +80,15 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
     const int w = blockIdx.x * WL + v; // < Wp (padded worlds have no rows)
     const size_t Wp = (size_t)P.Wp;
     const int nr = w < P.W ? P.nrows[w] : 0;
-    const int m = nr & 0xffff, nhead = nr >> 16;
+    const int m = nr & 0xffff, nisl = nr >> 16; // rows, island blocks (b2p_dev.h)
     const int mmax = __reduce_max_sync(0xffffffffu, m);
+    const int nev = P.reorder == 0 && P.iters > 8 ? (P.iters - 1) >> 3 : 0; // reshuffles per solve (iterations 8, 16, ..)
 
     for (int s = side; s < R + 2; s += 2) s_lam[s * WL + v] = s == R + 1 ? 1.f : 0.f;
     for (int s = side; s < R; s += 2) s_ord[s * WL + v] = (uint8_t)s;
     for (int k = side; k < (nb + 1) * 3; k += 2) s_fc[k * WL + v] = make_float2(0.f, 0.f);
-    uint32_t seed = P.seed[w];
+    const uint32_t seed = P.seed[w]; // the world's LCG state at the start of the step
+    uint32_t seed_out = seed;        // ... and after the step's reshuffles
     __syncwarp();
 
     // ---- this lane's addresses
@@ -187,17 +189,14 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
 
     for (int it = 0; it < (mmax > 0 ? P.iters : 0); it++) {
         if (P.reorder == 0 && it >= 8 && (it & 7) == 0) {
-            // ODE ConstraintsReorderingHelper on [0,nhead) and [nhead,m); one lane of the pair shuffles
+            // ODE ConstraintsReorderingHelper on both partitions of every island block; one lane of the pair shuffles
             if (side == 0) {
                 auto swap = [&](int a, int b) {
                     const uint8_t x = s_ord[a * WL + v], y = s_ord[b * WL + v];
                     s_ord[a * WL + v] = y;
                     s_ord[b * WL + v] = x;
                 };
-#pragma unroll 1
-                for (int idx = 1; idx < nhead; idx++) swap(idx, rand_int(seed, idx + 1));
-#pragma unroll 1
-                for (int idx = nhead + 1; idx < m; idx++) swap(idx, rand_int(seed, idx - nhead + 1) + nhead);
+                seed_out = island_reshuffle(P.isl, Wp, w < P.W ? w : 0, nisl, seed, (it >> 3) - 1, nev, swap);
             }
             __syncwarp();
             load_rows();
@@ -243,7 +242,7 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
             dst[0] = f.x;
             dst[Wp] = f.y;
         }
-        if (side == 0) P.seed[w] = seed;
+        if (side == 0) P.seed[w] = seed_out;
     }
 }
 

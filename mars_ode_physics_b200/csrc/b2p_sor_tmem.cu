@@ -144,8 +144,9 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
     const uint32_t tbase = s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * (TROWS * 16));
 
     const int wl = valid ? w : blockIdx.x * P.worlds_per_cta; // phantoms read (only zero rows of) the CTA's first world
-    const int m = nr & 0xffff, nhead = nr >> 16;
+    const int m = nr & 0xffff, nisl = nr >> 16; // rows, island blocks (b2p_dev.h)
     const int mmax = __reduce_max_sync(0xffffffffu, m);
+    const int nev = P.reorder == 0 && P.iters > 8 ? (P.iters - 1) >> 3 : 0; // reshuffles per solve (iterations 8, 16, ..)
 
     // ---- overflow positions of this warp: [KR+TROWS, KR+TROWS+Ro) out of the shared pool, in warp order
     if (lane == 0) s_need[warp] = mmax - KR - TROWS > 0 ? mmax - KR - TROWS : 0;
@@ -158,7 +159,8 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
     for (int s = 0; s < R + 2; s++) s_lam[s * TW + tid] = s == R + 1 ? 1.f : 0.f;
     for (int s = 0; s < R; s++) s_ord[s * TW + tid] = (uint8_t)s;
     for (int k = 0; k < (nb + 1) * 3; k++) s_fc[k * TW + tid] = make_float2(0.f, 0.f);
-    uint32_t seed = P.seed[wl];
+    const uint32_t seed = P.seed[wl]; // the world's LCG state at the start of the step
+    uint32_t seed_out = seed;         // ... and after the step's reshuffles
 
     float *const lamL = s_lam + tid;
     float2 *const fcL = s_fc + tid;
@@ -261,16 +263,13 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
     for (int it = 0; it < (mmax > 0 ? P.iters : 0); it++) {
         bool fresh = it == 0; // the rows on chip are not (yet) in the order of this sweep
         if (P.reorder == 0 && it >= 8 && (it & 7) == 0) {
-            // ODE ConstraintsReorderingHelper on [0,nhead) and [nhead,m)
+            // ODE ConstraintsReorderingHelper on both partitions of every island block
             auto swap = [&](int a, int b) {
                 const uint8_t x = s_ord[a * TW + tid], y = s_ord[b * TW + tid];
                 s_ord[a * TW + tid] = y;
                 s_ord[b * TW + tid] = x;
             };
-#pragma unroll 1
-            for (int idx = 1; idx < nhead; idx++) swap(idx, rand_int(seed, idx + 1));
-#pragma unroll 1
-            for (int idx = nhead + 1; idx < m; idx++) swap(idx, rand_int(seed, idx - nhead + 1) + nhead);
+            seed_out = island_reshuffle(P.isl, Wp, wl, nisl, seed, (it >> 3) - 1, nev, swap);
             __syncwarp(); // the loops above diverge; the TMEM instructions below are warp-collective
             fresh = true;
         }
@@ -343,7 +342,7 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
             dst[0] = f.x;
             dst[Wp] = f.y;
         }
-        P.seed[w] = seed;
+        P.seed[w] = seed_out;
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");

@@ -402,3 +402,136 @@ def test_tmem_kernel_phantom_threads_leave_other_ctas_alone(cuda_lib):
         ar.close()
     assert outs[0][1] == outs[1][1]
     assert np.array_equal(outs[0][0], outs[1][0])
+
+
+def _multi_island_scene(be, W):
+    """Three separate pendulum chains (three islands with rows), two free bodies (islands without rows) and a ball
+    on the plane with a host-injected contact: the row blocks and the order in which the world's LCG is consumed
+    differ between ODE's island order and the one-block-per-world order."""
+    scenes.setup_world(be)
+    be.set_max_contacts(4)
+    bodies, joints = [], []
+    for k, n in enumerate((2, 3, 1)):
+        prev = -1
+        for i in range(n):
+            b = scenes.add_body(be, 0.5, scenes.inertia_box(0.5, 0.3, 0.05, 0.05), (0.15 + 0.3 * i, 1.0 * k, 1.0))
+            j = scenes.add_hinge(be, prev, b, (0.3 * i, 1.0 * k, 1.0), (0, 1, 0), 0.2 if i == 0 else None)
+            bodies.append(b)
+            joints.append(j)
+            prev = b
+        if k == 0:  # a free body created between the chains
+            bodies.append(scenes.add_body(be, 1.0, scenes.inertia_sphere(1.0, 0.1), (5.0, 5.0, 5.0)))
+    ball = scenes.add_body(be, 1.0, scenes.inertia_sphere(1.0, 0.1), (0.0, -2.0, 0.0999))
+    bodies.append(ball)
+    bodies.append(scenes.add_body(be, 1.0, scenes.inertia_sphere(1.0, 0.1), (-5.0, 5.0, 5.0)))
+    for w in range(W):
+        be.body_set_angular_vel(bodies[1], (0, 0.05 * w, 0.0), w)
+        be.body_set_linear_vel(ball, (0.3, 0.01 * w, 0.0), w)
+    return bodies, joints, ball
+
+
+@pytest.mark.parametrize("kernel", [capi.SOR_TMEM, capi.SOR_PAIRED])
+def test_ode_island_order_matches_oracle(cuda_lib, kernel):
+    """B2P_ORDER_ODE_ISLANDS: rows in ODE's dxProcessIslands order (bodies from the most recently created one,
+    depth-first through the joint lists, the step's contacts first), one row block per island, per-island
+    reshuffles that consume the world's LCG island by island -- against the oracle's ORDER_ODE_ISLANDS.  The RNG
+    state after every step is an exact check of the block sizes and of the draw order."""
+    W = 37
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    for be in (ar, oc):
+        bodies, joints, ball = _multi_island_scene(be, W)
+        be.set_order_mode(capi.ORDER_ODE_ISLANDS)
+    ar.set_sor_kernel(kernel)
+    nb = len(bodies)
+    for step in range(60):
+        for be in (ar, oc):
+            be.contacts_clear()
+            for w in range(W):
+                p = be.body_get_position(ball, w)
+                if w % 3 != 2 and 0.1 - p[2] >= 0:  # every third world has no contact: one island less
+                    be.contact_add(w, ball, -1, pos=(p[0], p[1], p[2] - 0.1), normal=(0, 0, 1), depth=0.1 - p[2],
+                                   mode=MODE, mu=0.5, mu2=0.5, soft_erp=0.2, soft_cfm=1e-5)
+        ar.step(H)
+        oc.step(H)
+        for w in (0, 1, 2, 17, W - 1):
+            assert ar.last_num_rows(w) == oc.last_num_rows(w), (step, w)
+            assert ar.rand_get_seed(w) == oc.rand_get_seed(w), (step, w)
+    assert ar.sor_kernel_used() == kernel
+    e = _state_err(ar, oc, nb)
+    print("island order, multi-island scene:", e)
+    assert e["pos"] < 2e-5 and e["quat"] < 5e-5 and e["lvel"] < 1e-3 and e["avel"] < 5e-3, e
+    fa, fo = ar.joint_get_feedback(joints[3], 5), oc.joint_get_feedback(joints[3], 5)
+    assert np.allclose(fa, fo, rtol=2e-3, atol=2e-3), (fa, fo)
+    # and the island order does differ from the world-block order (different sweep order, different RNG use)
+    ref = orc.OracleBatch(1)
+    _multi_island_scene(ref, 1)
+    ref.step(H)
+    isl = orc.OracleBatch(1)
+    _multi_island_scene(isl, 1)
+    isl.set_order_mode(capi.ORDER_ODE_ISLANDS)
+    isl.step(H)
+    assert np.abs(ref.state_download(nb) - isl.state_download(nb)).max() > 0
+
+
+def test_ode_island_order_with_device_collision(cuda_lib):
+    """The island order on scenes whose islands are made by the device contact stream: config D rovers (one
+    island; ODE lists the step's contacts before the joints) and the config B box stack (ten islands in free fall
+    that merge into one when the stack lands), against the oracle's ORDER_ODE_ISLANDS; and the two SOR kernels
+    agree bitwise in this mode too."""
+    import bench
+    W = 40
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    for be in (ar, oc):
+        sc = bench.build_rover_worlds(be, W)
+        be.set_order_mode(capi.ORDER_ODE_ISLANDS)
+    nb = len(sc["bodies"])
+    for step in range(220):
+        ar.collide_step(H)
+        oc.collide_step(H)
+        if step % 20 == 19:
+            for w in (0, 13, W - 1):
+                if ar.contact_count(w) == oc.contact_count(w):
+                    assert ar.last_num_rows(w) == oc.last_num_rows(w), (step, w)
+    e = _state_err(ar, oc, nb)
+    print("island order, rovers on the heightfield, 220 steps:", e)
+    assert e["pos"] < 5e-4 and e["quat"] < 1e-3, e
+    outs = []
+    for kernel in (capi.SOR_TMEM, capi.SOR_PAIRED):
+        a2 = Arena(64)
+        s2 = scenes.box_stack(a2, n=10)
+        scenes.jitter_box_stack(a2, s2, 64)
+        a2.set_order_mode(capi.ORDER_ODE_ISLANDS)
+        a2.set_sor_kernel(kernel)
+        for step in range(60):
+            a2.collide_step(H)
+        outs.append((a2.state_download(10).copy(), [a2.rand_get_seed(w) for w in range(64)]))
+        a2.close()
+    assert outs[0][1] == outs[1][1] and np.array_equal(outs[0][0], outs[1][0])
+    # box stack against the oracle through the landing: identical inputs (state and RNG) re-imposed before every
+    # compared step, row counts and RNG states exact whenever the contact counts agree
+    Wb = 16
+    ab, ob = Arena(Wb), orc.OracleBatch(Wb)
+    for be in (ab, ob):
+        sb = scenes.box_stack(be, n=10)
+        scenes.jitter_box_stack(be, sb, Wb)
+        be.set_order_mode(capi.ORDER_ODE_ISLANDS)
+    checked = 0
+    for step in range(60):
+        st32 = ob.state_download(10).astype(np.float32)
+        ab.state_upload(st32)
+        for w in range(Wb):
+            for b in range(10):
+                ob.body_set_state(b, st32[b, :, w].astype(np.float64), w)
+        ab.rand_set_seed(1000 + step)
+        ob.rand_set_seed(1000 + step)
+        ab.collide()
+        ob.collide()
+        same = [ab.contact_count(w) == ob.contact_count(w) for w in range(Wb)]
+        ab.step(H)
+        ob.step(H)
+        for w in range(Wb):
+            if same[w]:
+                assert ab.last_num_rows(w) == ob.last_num_rows(w), (step, w)
+                assert ab.rand_get_seed(w) == ob.rand_get_seed(w), (step, w)
+                checked += 1
+    assert checked > 50 * Wb
