@@ -370,6 +370,7 @@ def run_b200(args):
     ar.set_sor_warps(args.sor_warps)
     if args.no_graph:
         ar.set_graph_launch(False)
+    ar.set_order_mode(capi.ORDER_ODE_ISLANDS if args.row_order == "islands" else capi.ORDER_WORLD_BLOCK)
     if args.reorder == "none":
         ar.set_reorder_method(capi.REORDER_NONE)
     nb, nj = len(sc["bodies"]), len(sc["joints"])
@@ -557,7 +558,7 @@ def run_b200(args):
                        "worlds_per_gpu": W, "total_worlds": total_worlds,
                        "sharding": f"worlds/{world_size} GPUs, no collective on the step path",
                        "l2": "per-step working set (row scratch) > L2; no flush needed",
-                       "settle_steps": args.settle, "row_reordering": args.reorder,
+                       "settle_steps": args.settle, "row_reordering": args.reorder, "row_order": args.row_order,
                        "launch": "one CUDA graph (collide + assemble + SOR + integrate) per step",
                        "host_cores_pinned": pinned_cores,
                        "collision_semantics": "repo-defined (oracle/orc_collide.c), not ODE's dCollide: one contact "
@@ -653,6 +654,8 @@ def main():
                     help="Tensor-Memory SOR kernel: warps (x32 worlds) per CTA; 0 = auto")
     ap.add_argument("--reorder", default="random", choices=["random", "none"],
                     help="SOR row reordering: ODE 0.16 default (random) or REORDERING_METHOD__DONT_REORDER")
+    ap.add_argument("--row-order", default="islands", choices=["islands", "block"],
+                    help="constraint row order: ODE's island order (dxProcessIslands; default) or one block per world")
     ap.add_argument("--workload", default="D", choices=["B", "C", "D", "Dcyl"],
                     help="D (default) is the headline configuration; B and C are extra data points")
     args = ap.parse_args()
