@@ -236,6 +236,7 @@ class CpuBaseline:
         self.n, self.threads = sample_worlds, threads
         self.oc = orc.OracleBatch(sample_worlds)
         build_rover_worlds(self.oc, sample_worlds)
+        self.oc.set_order_mode(orc.ORDER_ODE_ISLANDS)  # ODE's island order, as the device arm runs
         per = (sample_worlds + threads - 1) // threads
         self.chunks = [(i, min(i + per, sample_worlds)) for i in range(0, sample_worlds, per)]
         self.ex = ThreadPoolExecutor(max_workers=threads)
@@ -291,12 +292,13 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def measure_workload(Arena, torch, stream, name, builder, W, world_offset, settle, steps, peak):
+def measure_workload(Arena, torch, stream, name, builder, W, world_offset, settle, steps, peak, order_mode=1):
     """A secondary configuration (BASELINE configs 2, 3, 5): device-resident collide + step over `steps` steps,
     CUDA events on the launch stream, plus the per-kernel split.  Returns (dict for the JSON line, ms)."""
     ar = Arena(W, device=torch.cuda.current_device())
     ar.set_stream(stream.cuda_stream)
     builder(ar, W, world_offset=world_offset)
+    ar.set_order_mode(order_mode)
     for _ in range(settle):
         ar.collide_step(H)
     ar.sync()
@@ -506,7 +508,8 @@ def run_b200(args):
         Ws = total_strong // world_size
         barrier()
         res, ms_s = measure_workload(Arena, torch, stream, WORKLOAD, build_rover_worlds, Ws, rank * Ws,
-                                     args.settle, max(10, min(K, 20)), peak)
+                                     args.settle, max(10, min(K, 20)), peak,
+                                     capi.ORDER_ODE_ISLANDS if args.row_order == "islands" else capi.ORDER_WORLD_BLOCK)
         t2 = torch.tensor([ms_s], dtype=torch.float64, device="cuda")
         if world_size > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
@@ -521,7 +524,8 @@ def run_b200(args):
         if rank == 0:
             for key, name, builder, Wx, settle_x in (("config_B_4096", WORKLOADS["B"], build_box_stack_worlds, 4096, 150),
                                                      ("config_C_16384", WORKLOADS["C"], build_quadruped_worlds, 16384, 300)):
-                r, ms_x = measure_workload(Arena, torch, stream, name, builder, Wx, 0, settle_x, 100, peak)
+                r, ms_x = measure_workload(Arena, torch, stream, name, builder, Wx, 0, settle_x, 100, peak,
+                                           capi.ORDER_ODE_ISLANDS if args.row_order == "islands" else capi.ORDER_WORLD_BLOCK)
                 r["value"] = Wx * r["steps"] / (ms_x * 1e-3)
                 r["unit"] = UNIT
                 extra[key] = r

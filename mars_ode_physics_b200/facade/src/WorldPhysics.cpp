@@ -67,6 +67,8 @@ void WorldPhysics::initTheWorld(void)
     checkB2P(b2p_arena_create(num_worlds, device, &arena), "WorldPhysics::initTheWorld");
     b2p_arena_set_max_contacts(arena, max_contacts);
     b2p_arena_enable_rolling_friction(arena, rolling_friction ? 1 : 0);
+    // rows in ODE's own order: island by island, bodies / joints / contacts as dxProcessIslands visits them
+    b2p_world_set_row_order(arena, B2P_ORDER_ODE_ISLANDS);
     b2p_world_rand_set_seed(arena, 11211u);
     old_gravity = world_gravity;
     old_cfm = world_cfm;

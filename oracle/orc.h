@@ -93,6 +93,19 @@ enum {
     ORC_REORDER_NONE = 1      /* REORDERING_METHOD__DONT_REORDER */
 };
 
+/* Restatement choices: details of ODE 0.16 that this oracle restates from memory and that only a run of the real
+ * libode can settle.  Value 0 is what the oracle (and the device path) does; the other
+ * values are the plausible alternatives, so that the day a libode is available the pin is one run per switch.
+ * tests/test_oracle.py::test_restatement_variants quantifies what each one changes. */
+enum {
+    ORC_VARIANT_GYRO = 0,         /* 0: implicit (Lacoursiere) gyroscopic torque; 1: explicit -w x (I w); 2: none */
+    ORC_VARIANT_SHUFFLE_AT_0 = 1, /* 0: reshuffles at iterations 8, 16, ...; 1: also at iteration 0 (ODE <= 0.13) */
+    ORC_VARIANT_LAMBDA_ROW = 2,   /* feedback.lambda (patched dJointFeedback): 0: first limit/motor row; 1: last */
+    ORC_NUM_VARIANTS = 3
+};
+struct orc_world;
+void orc_world_set_variant(struct orc_world *w, int which, int value);
+
 /* the dContact record as filled by Frame::addContact (Frame.cpp:1023-1079) */
 typedef struct orc_contact_desc {
     double pos[3];

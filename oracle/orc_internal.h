@@ -73,6 +73,7 @@ typedef struct {
 struct orc_world {
     real gravity[3], erp, cfm, max_angular_speed, contact_max_vel, contact_min_depth, sor_w;
     int iters, order_mode, reorder_method;
+    int variant[ORC_NUM_VARIANTS]; /* restatement choices that only a real libode can settle (orc.h) */
     uint32_t seed;
     body_t *bodies;
     int nb, capb;

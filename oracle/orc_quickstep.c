@@ -357,6 +357,10 @@ uint32_t orc_world_rand_get_seed(const orc_world *w) { return w->seed; }
 int orc_world_last_num_rows(const orc_world *w) { return w->last_m; }
 int orc_world_last_num_islands(const orc_world *w) { return w->last_islands; }
 double orc_world_last_residual(const orc_world *w) { return (double)w->last_residual; }
+void orc_world_set_variant(orc_world *w, int which, int value)
+{
+    if (which >= 0 && which < ORC_NUM_VARIANTS) w->variant[which] = value;
+}
 int orc_world_num_bodies(const orc_world *w) { return w->nb; }
 int orc_world_num_joints(const orc_world *w) { return w->nj; }
 int orc_world_num_contacts(const orc_world *w) { return w->nc; }
@@ -1813,7 +1817,16 @@ static void quickstep_island(orc_world *w, int *bodies, int nb, jref_t *jl, int 
         real tmp[9];
         mul33_bt(tmp, b->invI, b->R);
         mul33(b->invI_w, b->R, tmp);
-        if (b->gyroscopic) {
+        if (b->gyroscopic && w->variant[ORC_VARIANT_GYRO] == 1) {
+            /* ORC_VARIANT_GYRO 1: the explicit form tau = -w x (I w) (ODE before the implicit term) */
+            real I[9], L[3];
+            mul33_bt(tmp, b->I, b->R);
+            mul33(I, b->R, tmp);
+            mul_R_v(L, I, b->avel);
+            b->tacc[0] -= b->avel[1] * L[2] - b->avel[2] * L[1];
+            b->tacc[1] -= b->avel[2] * L[0] - b->avel[0] * L[2];
+            b->tacc[2] -= b->avel[0] * L[1] - b->avel[1] * L[0];
+        } else if (b->gyroscopic && w->variant[ORC_VARIANT_GYRO] == 0) {
             /* implicit gyroscopic torque (Lacoursiere 2006) as in ODE 0.13+ quickstep */
             real I[9], L[3], It[9], itInv[9];
             mul33_bt(tmp, b->I, b->R);
@@ -1956,7 +1969,8 @@ static void quickstep_island(orc_world *w, int *bodies, int nb, jref_t *jl, int 
         }
 
         for (int it = 0; it < w->iters; it++) {
-            if (w->reorder_method == ORC_REORDER_RANDOMLY && it >= 8 && (it % 8) == 0) {
+            if (w->reorder_method == ORC_REORDER_RANDOMLY && (it % 8) == 0 &&
+                (it >= 8 || w->variant[ORC_VARIANT_SHUFFLE_AT_0])) {
                 /* ODE ConstraintsReorderingHelper on both partitions */
                 for (int idx = 1; idx < nhead; idx++) {
                     int sw = orc_rand_int(&w->seed, idx + 1);
@@ -2058,6 +2072,7 @@ static void quickstep_island(orc_world *w, int *bodies, int nb, jref_t *jl, int 
             /* `lambda` of the DFKI-patched dJointFeedback (read at src/joints/Joint.cpp:900):
              * multiplier of the joint's limit/motor row (assumption) */
             j->fb_lambda = j->limot_row >= 0 ? lambda[jl[i].ofs + j->limot_row] : 0;
+            if (j->limot_row >= 0 && w->variant[ORC_VARIANT_LAMBDA_ROW] == 1) j->fb_lambda = lambda[jl[i].ofs + jl[i].m - 1];
         }
 
         /* v += h * cforce */

@@ -37,7 +37,7 @@ def test_reproducable_scene_deterministic(cuda_lib, tmp_path):
 def test_reproducable_scene_matches_oracle(cuda_lib, orc_lib, tmp_path):
     gpu = _run(str(tmp_path / "gpu.csv"), 0.5)
     ocsv = str(tmp_path / "orc.csv")
-    rows = orc_lib.orc_mars_run_reproducable_test(ocsv.encode(), 0.5, orc.ORDER_WORLD_BLOCK, None)
+    rows = orc_lib.orc_mars_run_reproducable_test(ocsv.encode(), 0.5, orc.ORDER_ODE_ISLANDS, None)  # the facade's order
     ora = np.loadtxt(ocsv, delimiter=",", skiprows=1)
     assert rows == len(ora) == len(gpu)
     assert np.array_equal(gpu[:, 0], ora[:, 0])  # identical time column (same double accumulation)
@@ -90,6 +90,7 @@ def test_config_d_entirely_through_the_loader(cuda_lib, tmp_path):
     ar = Arena(W)
     sc = bench.build_rover_worlds(ar, W)
     from mars_ode_physics_b200 import capi
+    ar.set_order_mode(capi.ORDER_ODE_ISLANDS)  # what the facade selects in initTheWorld
     param = capi.PARAM_VEL | capi.PARAM_GROUP2
     k_total = 0
     for _ in range(settle):
