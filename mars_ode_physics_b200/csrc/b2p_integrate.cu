@@ -23,30 +23,7 @@ namespace {
 
 constexpr int BD = 64;
 
-__device__ __forceinline__ void sym6_from(float *s6, const float *R, const float *Bsym, float *tmp)
-{
-    float M[9];
-    mul33_bt(tmp, Bsym, R);
-    mul33(M, R, tmp);
-    s6[0] = M[0];
-    s6[1] = M[1];
-    s6[2] = M[2];
-    s6[3] = M[4];
-    s6[4] = M[5];
-    s6[5] = M[8];
-}
-
-__device__ __forceinline__ void sym_mul(float *o, const float *S, const float *v)
-{
-    const float x = S[0] * v[0] + S[1] * v[1] + S[2] * v[2];
-    const float y = S[1] * v[0] + S[3] * v[1] + S[4] * v[2];
-    const float z = S[2] * v[0] + S[4] * v[1] + S[5] * v[2];
-    o[0] = x;
-    o[1] = y;
-    o[2] = z;
-}
-
-__global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P)
+__global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P)
 {
     const DevTemplate *__restrict__ T = P.T;
     const int nb = T->nb, nj = T->nj, maxc = T->maxc;
@@ -57,32 +34,64 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
     const float h = P.h;
 
     // ---------------- joint feedback from the pre-step poses: sum of lambda * J over the joint's rows --------
+    // (software-pipelined like the body loop below: the poses, row counts and multipliers of joint j + 1 are
+    // requested before joint j's Jacobian is rebuilt)
     {
+        struct JointIn {
+            float pq0[7], pq1[7]; // raw position + quaternion: nothing here may wait for the loads
+            int jr, slot;
+            float lam[B2P_ROWS_PER_JOINT];
+        };
+        auto load_joint = [&](int j, JointIn &x) {
+            const DevJoint &jc = T->joints[j];
+            x.jr = G(P.jrows, j);
+            x.slot = G(P.jslot, j);
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                x.pq0[k] = jc.b0 >= 0 ? G(P.state, jc.b0 * B2P_STATE_FIELDS + k) : 0.f;
+                x.pq1[k] = jc.b1 >= 0 ? G(P.state, jc.b1 * B2P_STATE_FIELDS + k) : 0.f;
+            }
+            const int mrows = B2P_JR_ROWS(x.jr);
+#pragma unroll
+            for (int k = 0; k < B2P_ROWS_PER_JOINT; k++)
+                x.lam[k] = k < mrows ? G(P.lambda, x.slot + k) * G(P.rowS, x.slot + k) : 0.f; // lambda = lam' sqrt(Ad)
+        };
+        JointIn nxt;
+        if (nj > 0) load_joint(0, nxt);
         for (int j = 0; j < nj; j++) {
             const DevJoint &jc = T->joints[j];
-            const int jr = G(P.jrows, j);
-            const int slot = G(P.jslot, j); // first slot of the joint's rows (the row order may be ODE's island order)
+            const JointIn cur = nxt;
+            if (j + 1 < nj) load_joint(j + 1, nxt);
+            const int jr = cur.jr;
             const int mrows = B2P_JR_ROWS(jr);
             float acc[12];
 #pragma unroll
             for (int q = 0; q < 12; q++) acc[q] = 0.f;
             float flam = 0.f;
             if (jc.b0 >= 0 && mrows > 0) {
-                BodyPose p0, p1;
-                load_pose(P, jc.b0, w, p0);
-                if (jc.b1 >= 0) load_pose(P, jc.b1, w, p1);
                 // `lambda` of the patched dJointFeedback: the multiplier of the joint's first limit / motor row
                 const int nl = ((jr & B2P_JR_L1) ? 1 : 0) + ((jr & B2P_JR_L2) ? 1 : 0);
                 const int first_limot = nl ? mrows - nl : -1;
                 int k = 0;
                 auto emit = [&](const Row &r) {
-                    const float lam = G(P.lambda, slot + k) * G(P.rowS, slot + k);
+                    // (k is a compile-time constant on every path through joint_rows once it is inlined)
+                    float lam = 0.f;
+#pragma unroll
+                    for (int i = 0; i < B2P_ROWS_PER_JOINT; i++)
+                        if (i == k) lam = cur.lam[i];
 #pragma unroll
                     for (int q = 0; q < 12; q++) acc[q] += r.J[q] * lam;
                     if (k == first_limot) flam = lam;
                     k++;
                 };
                 const LimotCmd cmd = {0.f, 0.f, 0.f, 0.f};
+                BodyPose p0, p1;
+#pragma unroll
+                for (int i = 0; i < 3; i++) p0.pos[i] = cur.pq0[i], p1.pos[i] = cur.pq1[i];
+#pragma unroll
+                for (int i = 0; i < 4; i++) p0.q[i] = cur.pq0[3 + i], p1.q[i] = cur.pq1[3 + i];
+                q_to_R(p0.q, p0.R);
+                if (jc.b1 >= 0) q_to_R(p1.q, p1.R);
                 joint_rows<false>(P, jc, p0, p1, cmd, jr, w, emit);
             }
 #pragma unroll
@@ -143,39 +152,62 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
     }
 
     // ---------------- velocity update + dxStepBody ----------------
-    for (int b = 0; b < nb; b++) {
-        const DevBody &bc = T->bodies[b];
+    // Software-pipelined over the bodies: the 25 input words of body b + 1 are requested before body b is worked
+    // on, so that their DRAM latency (the kernel has one thread per world, i.e. few warps per SM to hide it
+    // otherwise) runs under ~300 instructions of arithmetic.
+    struct BodyIn {
+        float pos[3], q[4], lv[3], av[3], fe[6], fch[6], last[6];
+    };
+    auto load_body = [&](int b, BodyIn &x) {
         const int f = b * B2P_STATE_FIELDS;
-        float pos[3], q[4], lv[3], av[3], fe[6], R[9], tmp[9], S6[6], fch[6], t3[3];
-        pos[0] = G(P.state, f + 0); pos[1] = G(P.state, f + 1); pos[2] = G(P.state, f + 2);
-        q[0] = G(P.state, f + 3); q[1] = G(P.state, f + 4); q[2] = G(P.state, f + 5); q[3] = G(P.state, f + 6);
+        x.pos[0] = G(P.state, f + 0); x.pos[1] = G(P.state, f + 1); x.pos[2] = G(P.state, f + 2);
+        x.q[0] = G(P.state, f + 3); x.q[1] = G(P.state, f + 4); x.q[2] = G(P.state, f + 5); x.q[3] = G(P.state, f + 6);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            lv[k] = G(P.state, f + 7 + k);
-            av[k] = G(P.state, f + 10 + k);
+            x.lv[k] = G(P.state, f + 7 + k);
+            x.av[k] = G(P.state, f + 10 + k);
         }
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            fe[k] = G(P.force, b * 6 + k);
-            fch[k] = G(P.fcacc, b * 6 + k);
+            x.fe[k] = G(P.force, b * 6 + k);
+            x.fch[k] = G(P.fcacc, b * 6 + k);
+            x.last[k] = frame_out ? G(P.bodyx, b * 15 + k) : 0.f; // Frame::update's last_l_vel / last_a_vel
         }
+    };
+    BodyIn nxt;
+    if (nb > 0) load_body(0, nxt);
+    for (int b = 0; b < nb; b++) {
+        const DevBody &bc = T->bodies[b];
+        const int f = b * B2P_STATE_FIELDS;
+        const BodyIn cur = nxt;
+        if (b + 1 < nb) load_body(b + 1, nxt);
+        float pos[3], q[4], lv[3], av[3], fe[6], R[9], t3[3], u3[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) pos[k] = cur.pos[k], lv[k] = cur.lv[k], av[k] = cur.av[k];
+#pragma unroll
+        for (int k = 0; k < 4; k++) q[k] = cur.q[k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) fe[k] = cur.fe[k];
+        const float *fch = cur.fch;
         q_to_R(q, R);
-        // v += h * M^-1/2 fch
-        sym6_from(S6, R, bc.sqrtInvI, tmp);
-        sym_mul(t3, S6, fch + 3);
+        // v += h * M^-1/2 fch, with the angular block R sqrt(invI_body) R^T applied as three matrix-vector products
+        mul_Rt_v(t3, R, fch + 3);
+        mul_R_v(u3, bc.sqrtInvI, t3);
+        mul_R_v(t3, R, u3);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             lv[k] += h * (bc.sqrtInvMass * fch[k]);
             av[k] += h * t3[k];
         }
         // v += h * invM fe
-        sym6_from(S6, R, bc.invI, tmp);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             lv[k] += h * bc.invMass * fe[k];
             fe[3 + k] *= h;
         }
-        sym_mul(t3, S6, fe + 3);
+        mul_Rt_v(t3, R, fe + 3);
+        mul_R_v(u3, bc.invI, t3);
+        mul_R_v(t3, R, u3);
 #pragma unroll
         for (int k = 0; k < 3; k++) av[k] += t3[k];
         if (bc.has_max_ang) {
@@ -205,6 +237,18 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
         }
 #pragma unroll
         for (int k = 0; k < 6; k++) G(P.force, b * 6 + k) = 0.f;
+        if (frame_out) {
+            // Frame::update (Frame.cpp:899-921): accelerations by finite differences of the step's (not yet damped)
+            // velocities; the damping itself follows the joints' post-step work below, as in stepTheWorld
+            const float hinv = 1.0f / h;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                G(P.bodyx, b * 15 + 6 + k) = (lv[k] - cur.last[k]) * hinv;
+                G(P.bodyx, b * 15 + 9 + k) = (av[k] - cur.last[3 + k]) * hinv;
+                G(P.bodyx, b * 15 + k) = lv[k];
+                G(P.bodyx, b * 15 + 3 + k) = av[k];
+            }
+        }
     }
 
     // ---------------- joint observations, Joint::update and applyJointFriction from the new state -----------
@@ -361,36 +405,19 @@ __global__ void __launch_bounds__(BD, 8) b2p_integrate_kernel(const StepParams P
         }
     }
 
-    // ---------------- Frame::update (Frame.cpp:899-943): accelerations by finite differences, damping -------
+    // ---------------- Frame::update, second half (Frame.cpp:922-941): multiplicative damping ---------------
     for (int b = 0; b < nb; b++) {
         const DevBody &bc = T->bodies[b];
         const bool damp_l = bc.lin_damp < 1.f, damp_a = bc.ang_damp < 1.f;
-        if (!frame_out && !damp_l && !damp_a) continue;
+        if (!damp_l && !damp_a) continue;
         const int f = b * B2P_STATE_FIELDS;
-        float lv[3], av[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            lv[k] = G(P.state, f + 7 + k);
-            av[k] = G(P.state, f + 10 + k);
-        }
-        if (frame_out) {
-            const float hinv = 1.0f / h;
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const float ll = G(P.bodyx, b * 15 + k), la = G(P.bodyx, b * 15 + 3 + k);
-                G(P.bodyx, b * 15 + 6 + k) = (lv[k] - ll) * hinv;
-                G(P.bodyx, b * 15 + 9 + k) = (av[k] - la) * hinv;
-                G(P.bodyx, b * 15 + k) = lv[k];
-                G(P.bodyx, b * 15 + 3 + k) = av[k];
-            }
-        }
         if (damp_l) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) G(P.state, f + 7 + k) = lv[k] * bc.lin_damp;
+            for (int k = 0; k < 3; k++) G(P.state, f + 7 + k) = G(P.state, f + 7 + k) * bc.lin_damp;
         }
         if (damp_a) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) G(P.state, f + 10 + k) = av[k] * bc.ang_damp;
+            for (int k = 0; k < 3; k++) G(P.state, f + 10 + k) = G(P.state, f + 10 + k) * bc.ang_damp;
         }
     }
 }
