@@ -271,6 +271,7 @@ struct b2p_arena {
         bool pending = false;
     } io[2];
     cudaStream_t io_stream = nullptr;
+    cudaStream_t up_stream = nullptr; // command uploads: their own stream, so that they never queue behind a read-back
     int io_next = 0;
     // command uploads on the copy stream: ordered after the assemble kernel of the last step (the only reader of
     // jcmd) and before the next one
@@ -936,6 +937,7 @@ void b2p_arena_destroy(b2p_arena *a)
         if (sl.done) cudaEventDestroy(sl.done);
     }
     if (a->io_stream) cudaStreamDestroy(a->io_stream);
+    if (a->up_stream) cudaStreamDestroy(a->up_stream);
     if (a->cap_stream) cudaStreamDestroy(a->cap_stream);
     if (a->ev_asm_done) cudaEventDestroy(a->ev_asm_done);
     if (a->ev_h2d_done) cudaEventDestroy(a->ev_h2d_done);
@@ -1317,11 +1319,17 @@ int b2p_observe_begin(b2p_arena *a, int body, float *host_out, float *host_joint
         CUDA_TRY(cudaMemcpyAsync(sl.dev_jobs, a->jobs.dev, sizeof(float) * jelems, cudaMemcpyDeviceToDevice, a->stream));
     CUDA_TRY(cudaEventRecord(sl.snap, a->stream));
     CUDA_TRY(cudaStreamWaitEvent(a->io_stream, sl.snap, 0));
-    CUDA_TRY(cudaMemcpy2DAsync(host_out, sizeof(float) * a->W, sl.dev, sizeof(float) * a->Wp, sizeof(float) * a->W,
-                               B2P_STATE_FIELDS, cudaMemcpyDeviceToHost, a->io_stream));
-    if (jelems)
-        CUDA_TRY(cudaMemcpy2DAsync(host_joint_obs, sizeof(float) * a->W, sl.dev_jobs, sizeof(float) * a->Wp,
-                                   sizeof(float) * a->W, nj * 4, cudaMemcpyDeviceToHost, a->io_stream));
+    if (a->W == a->Wp) { // no padding between the fields: one contiguous transfer each
+        CUDA_TRY(cudaMemcpyAsync(host_out, sl.dev, sizeof(float) * elems, cudaMemcpyDeviceToHost, a->io_stream));
+        if (jelems)
+            CUDA_TRY(cudaMemcpyAsync(host_joint_obs, sl.dev_jobs, sizeof(float) * jelems, cudaMemcpyDeviceToHost, a->io_stream));
+    } else {
+        CUDA_TRY(cudaMemcpy2DAsync(host_out, sizeof(float) * a->W, sl.dev, sizeof(float) * a->Wp, sizeof(float) * a->W,
+                                   B2P_STATE_FIELDS, cudaMemcpyDeviceToHost, a->io_stream));
+        if (jelems)
+            CUDA_TRY(cudaMemcpy2DAsync(host_joint_obs, sizeof(float) * a->W, sl.dev_jobs, sizeof(float) * a->Wp,
+                                       sizeof(float) * a->W, nj * 4, cudaMemcpyDeviceToHost, a->io_stream));
+    }
     CUDA_TRY(cudaEventRecord(sl.done, a->io_stream));
     sl.pending = true;
     return t;
@@ -1633,13 +1641,16 @@ int b2p_joints_set_param_batch(b2p_arena *a, int param, const float *values, int
     if (overlap) {
         if ((rc = join_pending_upload(a))) return rc; // uploads stay in order among themselves
         if (!a->ev_h2d_done) CUDA_TRY(cudaEventCreateWithFlags(&a->ev_h2d_done, cudaEventDisableTiming));
-        CUDA_TRY(cudaStreamWaitEvent(a->io_stream, a->ev_asm_done, 0));
-        st = a->io_stream;
+        // (host -> device and device -> host transfers run concurrently on the link: the upload gets its own
+        // stream instead of waiting behind the observation of the previous step on the read-back stream)
+        if (!a->up_stream) CUDA_TRY(cudaStreamCreateWithFlags(&a->up_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamWaitEvent(a->up_stream, a->ev_asm_done, 0));
+        st = a->up_stream;
     }
     CUDA_TRY(cudaMemcpy2DAsync(a->jcmd.dev + field * a->Wp, sizeof(float) * 4 * a->Wp, values, sizeof(float) * a->W,
                                sizeof(float) * a->W, (size_t)num_joints, cudaMemcpyHostToDevice, st));
     if (overlap) {
-        CUDA_TRY(cudaEventRecord(a->ev_h2d_done, a->io_stream));
+        CUDA_TRY(cudaEventRecord(a->ev_h2d_done, a->up_stream));
         a->h2d_pending = true;
     }
     a->jcmd.dev_newer = true;
