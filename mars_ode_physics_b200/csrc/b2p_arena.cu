@@ -228,7 +228,7 @@ struct b2p_arena {
     float4 *d_rows = nullptr;
     float *d_lambda = nullptr, *d_rowS = nullptr, *d_invIw = nullptr, *d_fcacc = nullptr;
     uint32_t *d_cmap = nullptr, *d_isl = nullptr;
-    uint8_t *d_jslot = nullptr;
+    uint8_t *d_ord0 = nullptr;
     int order_mode = B2P_ORDER_WORLD_BLOCK;
     size_t scratch_rows = 0, scratch_nb = 0, scratch_maxc = 0;
     int rows_resident = 0;   // SOR kernel: sweep positions kept in shared memory; 0 = automatic
@@ -453,9 +453,9 @@ void free_scratch(b2p_arena *a)
     if (a->d_fcacc) cudaFree(a->d_fcacc);
     if (a->d_cmap) cudaFree(a->d_cmap);
     if (a->d_isl) cudaFree(a->d_isl);
-    if (a->d_jslot) cudaFree(a->d_jslot);
+    if (a->d_ord0) cudaFree(a->d_ord0);
     a->d_isl = nullptr;
-    a->d_jslot = nullptr;
+    a->d_ord0 = nullptr;
     if (a->d_hw_rows) cudaFree(a->d_hw_rows);
     a->d_hw_rows = nullptr;
     a->d_rows = nullptr;
@@ -660,7 +660,7 @@ int finalize(b2p_arena *a)
     if ((rc = mirror_to_device(a, a->nrows))) return rc;
     if ((rc = mirror_to_device(a, a->jrows))) return rc;
     if (a->scratch_rows != (size_t)maxrows || a->scratch_nb != (size_t)nb || a->scratch_maxc != (size_t)a->maxc ||
-        !a->d_jslot) {
+        !a->d_ord0) {
         free_scratch(a);
         const size_t mr = (size_t)std::max(maxrows, 1), Wp = (size_t)a->Wp;
         CUDA_TRY(cudaMalloc(&a->d_rows, sizeof(float4) * (mr + 1) * 4 * Wp));
@@ -670,9 +670,9 @@ int finalize(b2p_arena *a)
         CUDA_TRY(cudaMalloc(&a->d_fcacc, sizeof(float) * (size_t)std::max(nb, 1) * 6 * Wp));
         CUDA_TRY(cudaMalloc(&a->d_cmap, sizeof(uint32_t) * (size_t)std::max(a->maxc, 1) * Wp));
         CUDA_TRY(cudaMalloc(&a->d_isl, sizeof(uint32_t) * (size_t)std::max(nb, 1) * Wp));
-        CUDA_TRY(cudaMalloc(&a->d_jslot, (size_t)std::max(nj, 1) * Wp));
+        CUDA_TRY(cudaMalloc(&a->d_ord0, mr * Wp));
         CUDA_TRY(cudaMemsetAsync(a->d_isl, 0, sizeof(uint32_t) * (size_t)std::max(nb, 1) * Wp, a->stream));
-        CUDA_TRY(cudaMemsetAsync(a->d_jslot, 0, (size_t)std::max(nj, 1) * Wp, a->stream));
+        CUDA_TRY(cudaMemsetAsync(a->d_ord0, 0, mr * Wp, a->stream));
         CUDA_TRY(cudaMalloc(&a->d_hw_rows, sizeof(int)));
         CUDA_TRY(cudaMemsetAsync(a->d_hw_rows, 0, sizeof(int), a->stream));
         if (!a->h_hw_rows) CUDA_TRY(cudaMallocHost(&a->h_hw_rows, sizeof(int)));
@@ -2211,8 +2211,12 @@ int prepare_step(b2p_arena *a, double step_size, StepParams &P, bool &use_tmem)
     P.rows = a->d_rows;
     P.cmap = a->d_cmap;
     P.isl = a->d_isl;
-    P.jslot = a->d_jslot;
+    P.ord0 = a->d_ord0;
     P.order_mode = a->order_mode;
+    {
+        static const int tune = getenv("B2P_TUNE") ? atoi(getenv("B2P_TUNE")) : 0;
+        P.tune = tune;
+    }
     P.jrows = a->jrows.dev;
     P.ccount = a->ccount.dev;
     P.nrows = a->nrows.dev;
@@ -2236,8 +2240,10 @@ int prepare_step(b2p_arena *a, double step_size, StepParams &P, bool &use_tmem)
         want_t = std::max(std::min(seen, maxrows) - b2p_sor_tmem_rows_on_chip(kr_t, nw_t), 0);
         if (nw_t == 4 || a->sor_warps == 8 || (pool_t >= 0 && want_t <= pool_t)) break;
     }
-    use_tmem = a->sor_kernel == B2P_SOR_TMEM || (a->sor_kernel == B2P_SOR_AUTO && pool_t >= 0);
-    if (use_tmem && pool_t < 0)
+    // (the Tensor-Memory kernel addresses a world's row units with 32-bit byte offsets: row buffer < 4 GB)
+    const bool rows_fit32 = (double)(maxrows + 1) * 64.0 * (double)a->Wp < 4294967296.0;
+    use_tmem = a->sor_kernel == B2P_SOR_TMEM || (a->sor_kernel == B2P_SOR_AUTO && pool_t >= 0 && rows_fit32);
+    if (use_tmem && (pool_t < 0 || !rows_fit32))
         return fail(B2P_ECAPACITY, "scene too large for the Tensor-Memory SOR kernel");
     if (use_tmem) {
         P.rows_registers = kr_t;

@@ -17,8 +17,9 @@
 // which is the same Gauss-Seidel iteration in different coordinates (Ad = w / (|J M^-1/2|^2 + cfm)).
 // A friction row's bound mu*lambda_n becomes (mu*sqrt(Ad_n/Ad_f)) * lam'_n.
 //
-// Rows are stored in ODE's initial sweep order (rows with findex < 0 first, in creation order, then the
-// friction-dependent rows), so that the order array of iteration 0 is the identity.
+// Rows are stored by constraint (static slots: joint j owns slots j*B2P_ROWS_PER_JOINT .., contact c owns
+// njslots + c*rpc ..); `ord0` lists the used slots in ODE's initial sweep order (per island: rows with findex < 0
+// first, in ODE's joint order, then the friction-dependent rows) and seeds the SOR kernels' order array.
 #include "b2p_rows.cuh"
 
 namespace {
@@ -33,7 +34,8 @@ struct Smem {
     float *sw; // [nb*6][BD]  symmetric sqrt(invI_world): xx xy xz yy yz zz
     float *pq; // [nb*7][BD]  position and quaternion of every body: the joints and contacts re-read the poses
                //             of their bodies, and a shared-memory read costs a tenth of a global one
-    uint8_t *scratch; // island order only: [(nj + maxc) + nb + 2 maxc][BD] bytes (items, stack, contact body ids)
+    int nb, maxrows;
+    uint8_t *scratch; // [nj + 3 maxc (+ nj + maxc + nb)][BD] bytes: per-item row bytes, contact body ids (+ island search)
 };
 
 // pose of body b from the copy phase 1 left in shared memory
@@ -79,6 +81,7 @@ __device__ __forceinline__ void sym_mul(float *o, const float *Ssym, const float
 __device__ __forceinline__ float emit_row(const StepParams &P, const Smem &S, int w, int tid, int slot, const Row &r,
                                           const PairCtx &pc)
 {
+    const int R = S.maxrows, nbodies = S.nb; // (copies of the template's: no global load on the row's path)
     const int Wp = P.Wp;
     const float hinv = 1.0f / P.h;
     float rhs = r.c * hinv;
@@ -120,9 +123,8 @@ __device__ __forceinline__ float emit_row(const StepParams &P, const Smem &S, in
     else if (r.lo == -INFINITY && r.hi == 0.f) bound = INFINITY, kind = 2;
     // meta: own slot | slot of the multiplier the bound follows << 8 (slot maxrows + 1 holds the constant 1 for
     // rows with a fixed bound) | body0 << 16 | body1 << 24 (one-body rows name the dummy body nb) | kind << 30
-    const int R = P.T->maxrows;
     const uint32_t meta = (uint32_t)slot | ((uint32_t)(r.fr ? r.fr - 1 : R + 1) << 8) | ((uint32_t)pc.b0 << 16) |
-                          ((uint32_t)(pc.b1 < 0 ? P.T->nb : pc.b1) << 24) | ((uint32_t)kind << 30);
+                          ((uint32_t)(pc.b1 < 0 ? nbodies : pc.b1) << 24) | ((uint32_t)kind << 30);
     // two 32-byte units: J0..J7 | J8..J11 rhs' cfm' bound meta  (J0..J5 = body-0 side, J6..J11 = body-1 side:
     // the SOR kernel gives each side of a world its own lane)
     stg256(ROW_UNIT(P.rows, slot, 0, Wp, w), make_float4(sa * o[0], sa * o[1], sa * o[2], sa * o[3]),
@@ -139,6 +141,8 @@ template <bool ISLANDS> __global__ void __launch_bounds__(BD, 8) b2p_assemble_ke
     const DevTemplate *__restrict__ T = P.T;
     const int nb = T->nb, nj = T->nj, maxc = T->maxc, rpc = T->rpc;
     Smem S;
+    S.nb = nb;
+    S.maxrows = T->maxrows;
     S.t1 = (float *)smem_raw;
     S.sw = S.t1 + (size_t)nb * 6 * BD;
     S.pq = S.sw + (size_t)nb * 6 * BD;
@@ -301,36 +305,14 @@ template <bool ISLANDS> __global__ void __launch_bounds__(BD, 8) b2p_assemble_ke
     }
 
     // ---------------- phase 2: constraint rows ----------------
-    // ODE solves one island at a time; inside an island the rows with findex < 0 come first (in joint order) and
-    // the friction-dependent rows last.  Every island therefore is a block [start, start + nh) (+) [.., start + m)
-    // of slots; the SOR kernels get the block table (isl) for ODE's per-island reshuffles.
-    //   ISLANDS == false: the whole world is one block, joints in creation order, then the contact stream.
-    //   ISLANDS == true:  ODE's dxProcessIslands order (util.cpp): bodies from the most recently created one,
-    //                     depth-first through each body's joint list (most recently attached first: the step's
-    //                     contacts in reverse stream order, then the joints in reverse creation order).
+    // Every constraint owns fixed slots (joint j: j*B2P_ROWS_PER_JOINT .., contact c: njslots + c*rpc ..), so the
+    // rows can be produced in any order; phase 3 then lists the used slots in the order ODE sweeps them first.
     int nc = G(P.ccount, 0);
     if (nc > maxc) nc = maxc;
-
-    // independent (head) rows of contact c; `tails` gets its friction-dependent rows
-    auto contact_counts = [&](int c, int &tails) -> int {
-        const int mode = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_MODE));
-        const float mu = G(P.crec, c * B2P_CONTACT_FIELDS + CR_MU);
-        const float mu2 = G(P.crec, c * B2P_CONTACT_FIELDS + CR_MU2);
-        const bool axisdep = (mode & 0x001) != 0;
-        int heads = 1;
-        tails = 0;
-        if (mu > 0.f) ((mode & 0x1000) ? tails : heads)++;
-        if (axisdep ? (mu2 > 0.f) : (mu > 0.f)) ((mode & 0x2000) ? tails : heads)++;
-        if ((mode & 0x400) && rpc >= 6) {
-            const float rho0 = G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHO);
-            const float rho1 = axisdep ? G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHO2) : rho0;
-            const float rho2 = axisdep ? G(P.crec, c * B2P_CONTACT_FIELDS + CR_RHON) : rho0;
-            if (rho0 > 0.f) ((mode & 0x1000) ? tails : heads)++;
-            if (rho1 > 0.f) ((mode & 0x2000) ? tails : heads)++;
-            if (rho2 > 0.f) ((mode & 0x4000) ? tails : heads)++;
-        }
-        return heads;
-    };
+    const int njslots = T->njslots;
+    // phase 3 reads back what phase 2 found out: the jrows byte of every joint and rows | dependent-row mask << 3
+    // of every contact (bytes, this thread's column of the scratch area)
+    uint8_t *const s_jr = S.scratch + tid, *const s_cr = S.scratch + (size_t)nj * BD + tid;
 
     // per-world commands of joint j
     auto joint_cmd = [&](int j, const DevJoint &jc) -> LimotCmd {
@@ -346,11 +328,10 @@ template <bool ISLANDS> __global__ void __launch_bounds__(BD, 8) b2p_assemble_ke
         return cmd;
     };
 
-    // rows of joint j at slots head, head + 1, ... (all of a joint's rows are independent rows)
-    auto emit_joint = [&](int j, int &head) {
+    // rows of joint j (all of a joint's rows are independent rows)
+    auto emit_joint = [&](int j) {
         const DevJoint &jc = S.joints[j];
         int jr = 0;
-        G(P.jslot, j) = (uint8_t)head;
         if (jc.b0 >= 0) {
             BodyPose p0, p1;
             PairCtx pc;
@@ -360,18 +341,19 @@ template <bool ISLANDS> __global__ void __launch_bounds__(BD, 8) b2p_assemble_ke
             if (jc.b1 >= 0) load_pose_s(S, jc.b1, tid, p1);
             pair_ctx(pc, S, tid);
             const LimotCmd cmd = joint_cmd(j, jc);
-            auto emit = [&](const Row &r) { emit_row(P, S, w, tid, head++, r, pc); };
+            int slot = j * B2P_ROWS_PER_JOINT;
+            auto emit = [&](const Row &r) { emit_row(P, S, w, tid, slot++, r, pc); };
             jr = joint_rows<true>(P, jc, p0, p1, cmd, 0, w, emit);
         }
         // rows of the joint | which limit / motor rows exist (b2p_rows.cuh); the integrate kernel follows it
         G(P.jrows, j) = (uint8_t)jr;
+        s_jr[(size_t)j * BD] = (uint8_t)jr;
     };
 
-    // ---- one contact (ODE contact.cpp getInfo1/getInfo2 for the mode bits Frame::addContact sets): independent
-    // rows at head++, friction-dependent rows (findex = its normal row) at tail++
-    // `pass`: 0 = all rows; 1 = the independent rows only (cmap gets the normal row's slot); 2 = the dependent rows
-    // only (the normal row's slot and sqrt(Ad) come from pass 1).  Returns true if the contact has dependent rows.
-    auto emit_contact = [&](int c, int &head, int &tail, const int pass) {
+    // ---- one contact (ODE contact.cpp getInfo1/getInfo2 for the mode bits Frame::addContact sets): the normal row,
+    // then the friction (and rolling) rows in consecutive slots; a row whose bound follows the normal force
+    // (findex = the normal row) is "dependent" and sweeps behind all independent rows of its island
+    auto emit_contact = [&](int c) {
         const int ids = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_IDS));
         const int b0 = ids & 0xff;
         const int b1 = ((ids >> 8) & 0xff) == 0xff ? -1 : ((ids >> 8) & 0xff);
@@ -413,15 +395,8 @@ template <bool ISLANDS> __global__ void __launch_bounds__(BD, 8) b2p_assemble_ke
         if (mode & 0x010) r.cfm = soft_cfm;
         r.lo = 0.f;
         r.hi = INFINITY;
-        int nslot = head;
-        const int tslot = tail;
-        float sn;
-        if (pass != 2) {
-            sn = emit_row(P, S, w, tid, head++, r, pc);
-        } else {
-            nslot = (G(P.cmap, c) >> 8) & 0xff;
-            sn = G(P.rowS, nslot);
-        }
+        const int nslot = njslots + c * rpc;
+        const float sn = emit_row(P, S, w, tid, nslot, r, pc);
         int row = 1, depmask = 0;
         float t1[3], t2[3];
         plane_space(n, t1, t2);
@@ -429,16 +404,13 @@ template <bool ISLANDS> __global__ void __launch_bounds__(BD, 8) b2p_assemble_ke
         const bool fr1 = mu > 0.f;
         const float mu2e = axisdep ? mu2 : mu;
         const bool fr2 = axisdep ? (mu2 > 0.f) : (mu > 0.f);
-        // one friction / rolling row: dependent rows (findex = normal row) go behind all independent rows
         auto emit_fr = [&](bool dependent) {
             if (dependent) {
                 r.fr = nslot + 1;
                 r.sn = sn;
                 depmask |= 1 << (row - 1);
-                if (pass != 1) emit_row(P, S, w, tid, tail++, r, pc);
-            } else {
-                if (pass != 2) emit_row(P, S, w, tid, head++, r, pc);
             }
+            emit_row(P, S, w, tid, nslot + row, r, pc);
             row++;
         };
         if (fr1) {
@@ -483,39 +455,66 @@ template <bool ISLANDS> __global__ void __launch_bounds__(BD, 8) b2p_assemble_ke
                 }
             }
         }
-        // rows | dependent-row mask << 3 | slot of the normal row << 8 | first dependent slot << 16 | friction row 1 / 2
-        // present << 24 / 25 (the integrate kernel rebuilds the contact's feedback from it)
-        G(P.cmap, c) = (uint32_t)(row | (depmask << 3)) | ((uint32_t)nslot << 8) | ((uint32_t)tslot << 16) |
-                       ((uint32_t)(fr1 ? 1 : 0) << 24) | ((uint32_t)(fr2 ? 1 : 0) << 25);
-        return depmask != 0;
+        // rows | dependent-row mask << 3 | slot of the normal row << 8 | friction row 1 / 2 present << 24 / 25
+        // (the integrate kernel rebuilds the contact's feedback from it)
+        G(P.cmap, c) = (uint32_t)(row | (depmask << 3)) | ((uint32_t)nslot << 8) | ((uint32_t)(fr1 ? 1 : 0) << 24) |
+                       ((uint32_t)(fr2 ? 1 : 0) << 25);
+        s_cr[(size_t)c * BD] = (uint8_t)(row | (depmask << 3));
+        if (ISLANDS) { // body ids for the island search of phase 3
+            s_cr[(size_t)(maxc + c) * BD] = (uint8_t)b0;
+            s_cr[(size_t)(2 * maxc + c) * BD] = (uint8_t)(b1 < 0 ? 0xff : b1);
+        }
     };
 
+    for (int j = 0; j < nj; j++) emit_joint(j);
+    for (int c = 0; c < nc; c++) emit_contact(c);
+
+    // ---------------- phase 3: the initial sweep order ----------------
+    // ODE solves one island at a time; inside an island the rows with findex < 0 come first (in joint order) and
+    // the friction-dependent rows last.  Every island therefore is a block [start, start + nh) (+) [.., start + m)
+    // of sweep positions; the SOR kernels get the block table (isl) for ODE's per-island reshuffles and ord0, the
+    // slot at every position.
+    //   ISLANDS == false: the whole world is one block, joints in creation order, then the contact stream.
+    //   ISLANDS == true:  ODE's dxProcessIslands order (util.cpp): bodies from the most recently created one,
+    //                     depth-first through each body's joint list (most recently attached first: the step's
+    //                     contacts in reverse stream order, then the joints in reverse creation order).
     int ntail = 0, nisl = 0; // rows of the world so far; islands (blocks) so far
-    if (!ISLANDS) {
-        int head = 0;
-        for (int j = 0; j < nj; j++) emit_joint(j, head);
-        // how many rows of the contacts are independent, so that the dependent ones can be written straight to
-        // their place behind all independent rows
-        int tail = head;
-        for (int c = 0; c < nc; c++) {
-            int t;
-            tail += contact_counts(c, t);
+    // the independent rows of one item at positions head.., counting its dependent rows
+    auto place_heads = [&](int it, int &head, int &ndep) {
+        if (it & 0x80) {
+            const int c = it & 0x7f, cr = s_cr[(size_t)c * BD], rows = cr & 7, dep = cr >> 3;
+            const int base = njslots + c * rpc;
+            for (int k = 0; k < rows; k++) {
+                if (k > 0 && (dep >> (k - 1) & 1)) ndep++;
+                else G(P.ord0, head++) = (uint8_t)(base + k);
+            }
+        } else {
+            const int rows = B2P_JR_ROWS(s_jr[(size_t)it * BD]);
+            for (int k = 0; k < rows; k++) G(P.ord0, head++) = (uint8_t)(it * B2P_ROWS_PER_JOINT + k);
         }
-        const int nh = tail;
-        for (int c = 0; c < nc; c++) emit_contact(c, head, tail, 0);
+    };
+    auto place_tails = [&](int c, int &tail) {
+        const int cr = s_cr[(size_t)c * BD], rows = cr & 7, dep = cr >> 3;
+        const int base = njslots + c * rpc;
+        for (int k = 1; k < rows; k++)
+            if (dep >> (k - 1) & 1) G(P.ord0, tail++) = (uint8_t)(base + k);
+    };
+    if (!ISLANDS) {
+        int head = 0, ndep = 0;
+        for (int j = 0; j < nj; j++) place_heads(j, head, ndep);
+        for (int c = 0; c < nc; c++) place_heads(0x80 | c, head, ndep);
+        int tail = head;
+        if (ndep) {
+            for (int c = 0; c < nc; c++) place_tails(c, tail);
+        }
         ntail = tail;
-        G(P.isl, 0) = (uint32_t)nh << 8 | (uint32_t)ntail << 16; // start 0 | independent rows << 8 | rows << 16
+        G(P.isl, 0) = (uint32_t)head << 8 | (uint32_t)ntail << 16; // start 0 | independent rows << 8 | rows << 16
         nisl = 1;
     } else {
-        // scratch of this thread behind the template copy (bytes): the island's items in discovery order (item =
-        // joint index, or 0x80 | contact index), the depth-first stack, and the two body ids of every contact
-        uint8_t *const seq = S.scratch + tid, *const stack = S.scratch + (size_t)(nj + maxc) * BD + tid;
-        uint8_t *const cb0 = S.scratch + (size_t)(nj + maxc + nb) * BD + tid, *const cb1 = cb0 + (size_t)maxc * BD;
-        for (int c = 0; c < nc; c++) {
-            const int ids = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_IDS));
-            cb0[(size_t)c * BD] = (uint8_t)(ids & 0xff);
-            cb1[(size_t)c * BD] = (uint8_t)((ids >> 8) & 0xff);
-        }
+        // scratch of this thread (bytes): the island's items in discovery order (item = joint index, or 0x80 |
+        // contact index) and the depth-first stack, behind the per-item bytes of phase 2
+        uint8_t *const seq = S.scratch + (size_t)(nj + 3 * maxc) * BD + tid, *const stack = seq + (size_t)(nj + maxc) * BD;
+        const uint8_t *const cb0 = s_cr + (size_t)maxc * BD, *const cb1 = cb0 + (size_t)maxc * BD;
         uint32_t visited = 0;
         uint64_t jtag = 0, ctag = 0;
         for (int bb = nb - 1; bb >= 0; bb--) {
@@ -551,33 +550,19 @@ template <bool ISLANDS> __global__ void __launch_bounds__(BD, 8) b2p_assemble_ke
             }
             if (nseq == 0) continue; // a free body: an island without rows
             // the island's independent rows in item order, then the friction-dependent rows of its contacts
-            // (measured alternatives: a counting pre-pass over the items, 98 us per 65536 rover worlds; producing
-            // joints and contacts in separate lane-uniform loops, 147 us -- the extra inlined copies of the row
-            // code spill; this form: 87 us, against 65 us for the one-block order)
             const int start = ntail;
-            int head = start, tail = 0;
-            bool any_tail = false;
-            for (int i = 0; i < nseq; i++) {
-                const int it = seq[(size_t)i * BD];
-                if (it & 0x80) any_tail |= emit_contact(it & 0x7f, head, tail, 1);
-                else emit_joint(it, head);
-            }
+            int head = start, ndep = 0;
+            for (int i = 0; i < nseq; i++) place_heads(seq[(size_t)i * BD], head, ndep);
             const int nh = head - start;
-            tail = head;
-            if (any_tail) {
+            int tail = head;
+            if (ndep) {
                 for (int i = 0; i < nseq; i++) {
                     const int it = seq[(size_t)i * BD];
-                    if (it & 0x80) emit_contact(it & 0x7f, head, tail, 2);
+                    if (it & 0x80) place_tails(it & 0x7f, tail);
                 }
             }
             ntail = tail;
             if (tail > start) G(P.isl, nisl++) = (uint32_t)start | (uint32_t)nh << 8 | (uint32_t)(tail - start) << 16;
-        }
-        for (int j = 0; j < nj; j++) { // joints without a body produce no rows
-            if (!(jtag >> j & 1ull)) {
-                G(P.jrows, j) = 0;
-                G(P.jslot, j) = 0;
-            }
         }
     }
     // rows of the step | islands << 16
@@ -592,7 +577,7 @@ template <bool ISLANDS> __global__ void __launch_bounds__(BD, 8) b2p_assemble_ke
 extern "C" size_t b2p_assemble_smem_bytes(int nb, int nj, int maxc, int islands)
 {
     return sizeof(float) * (size_t)nb * 19 * BD + (size_t)nb * sizeof(DevBody) + (size_t)nj * sizeof(DevJoint) +
-           (islands ? (size_t)(nj + 3 * maxc + nb) * BD : 0);
+           (size_t)(nj + 3 * maxc + (islands ? nj + maxc + nb : 0)) * BD;
 }
 
 extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, int nj, int maxc, cudaStream_t stream)

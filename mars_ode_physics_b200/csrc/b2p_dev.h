@@ -15,9 +15,11 @@
 //   seed    uint32[Wp]         per-world LCG state                (dRandSetSeed)
 //   nrows   int[Wp]            rows of the last step | row blocks (islands) << 16
 //   isl     uint32[nb][Wp]     block k: first slot | independent ("head") rows << 8 | rows << 16
-//   jslot   uint8[nj][Wp]      first slot of each joint's rows
-//   rows    float[maxrows][2][Wp][8]  constraint rows in ODE's initial sweep order (slot = position at
-//                              iteration 0) as two 32-byte units per world: J0..J7 | J8..J11 rhs' cfm' bound meta
+//   ord0    uint8[maxrows][Wp] slot of the row at sweep position p of ODE's initial order (iteration 0)
+//   rows    float[maxrows][2][Wp][8]  constraint rows by slot as two 32-byte units per world: J0..J7 | J8..J11 rhs'
+//                              cfm' bound meta.  Slots are static: joint j owns slots j*B2P_ROWS_PER_JOINT .., contact
+//                              c owns njslots + c*rpc .. (unused slots are never read); ord0 lists the used slots in
+//                              ODE's initial sweep order
 //                              (12 mass- and Ad-scaled Jacobian words); one more slot (index maxrows) holds an
 //                              all-zero row for every world.  ROW_UNIT(rows, slot, u, Wp, w) addresses a unit
 //   lambda  float[maxrows][Wp] scaled multipliers by slot;  rowS float[maxrows][Wp]  sqrt(Ad) by slot
@@ -129,10 +131,11 @@ struct StepParams {
     // post-step outputs of the reference's stepTheWorld for every world (null: not wanted)
     // ODE solves island by island: block k of a world's rows = start | independent rows << 8 | rows << 16
     uint32_t *isl;  // [max(nb,1)][Wp]; nrows = rows of the world | blocks << 16
-    uint8_t *jslot; // [nj][Wp]: first slot of joint j's rows
+    uint8_t *ord0;  // [maxrows][Wp]: slot of the row at position p of the initial sweep order (p < rows of the world)
     int order_mode; // 0: one block per world (joints in creation order, then contacts); 1: ODE's island order
     float *bodyx; // [nb*15][Wp] last_l_vel3 last_a_vel3 l_acc3 a_acc3 contact_force3  (Frame::update, computeContactForce)
     float *jupd;  // [nj*7][Wp]  motor_torque axis1_torque3 joint_load3              (Joint::update)
+    int tune;     // experiment switches from the environment variable B2P_TUNE (bit mask; 0 in production)
 };
 
 // unit u (0, 1) of the row in `slot` of world w: a pointer to two consecutive float4

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
         auto load_joint = [&](int j, JointIn &x) {
             const DevJoint &jc = T->joints[j];
             x.jr = G(P.jrows, j);
-            x.slot = G(P.jslot, j);
+            x.slot = jc.slot_base; // joint j owns slots j * B2P_ROWS_PER_JOINT ..
 #pragma unroll
             for (int k = 0; k < 7; k++) {
                 x.pq0[k] = jc.b0 >= 0 ? G(P.state, jc.b0 * B2P_STATE_FIELDS + k) : 0.f;
@@ -113,28 +113,25 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
         int nc = G(P.ccount, 0);
         if (nc > maxc) nc = maxc;
         for (int c = 0; c < nc; c++) {
+            // the contact's rows sit in consecutive slots in emission order: normal, friction 1, friction 2, (rolling)
             const uint32_t cm = G(P.cmap, c);
-            const int depmask = (cm >> 3) & 31;
-            int hs = (cm >> 8) & 0xff, ts = (cm >> 16) & 0xff;
+            int s = (cm >> 8) & 0xff;
             const bool fr1 = (cm >> 24) & 1, fr2 = (cm >> 25) & 1;
             const int b0 = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_IDS)) & 0xff;
             const float n[3] = {G(P.crec, c * B2P_CONTACT_FIELDS + CR_NX), G(P.crec, c * B2P_CONTACT_FIELDS + CR_NY),
                                 G(P.crec, c * B2P_CONTACT_FIELDS + CR_NZ)};
             float t1[3], t2[3];
             plane_space(n, t1, t2);
-            const float ln = G(P.lambda, hs) * G(P.rowS, hs);
-            hs++;
+            const float ln = G(P.lambda, s) * G(P.rowS, s);
+            s++;
             float f[3] = {n[0] * ln, n[1] * ln, n[2] * ln};
-            int k = 1;
             if (fr1) {
-                const int s = (depmask & (1 << (k - 1))) ? ts++ : hs++;
                 const float l1 = G(P.lambda, s) * G(P.rowS, s);
+                s++;
 #pragma unroll
                 for (int i = 0; i < 3; i++) f[i] += t1[i] * l1;
-                k++;
             }
             if (fr2) {
-                const int s = (depmask & (1 << (k - 1))) ? ts++ : hs++;
                 const float l2 = G(P.lambda, s) * G(P.rowS, s);
 #pragma unroll
                 for (int i = 0; i < 3; i++) f[i] += t2[i] * l2;
@@ -434,7 +431,8 @@ __global__ void __launch_bounds__(BD, 8) b2p_residual_kernel(const StepParams P,
     const int Wp = P.Wp, R = T->maxrows, nb = T->nb;
     const int m = G(P.nrows, 0) & 0xffff;
     float maxres = 0.f;
-    for (int s = 0; s < m; s++) {
+    for (int p = 0; p < m; p++) {
+        const int s = G(P.ord0, p); // the used slots, in the initial sweep order
         const F8 u0 = ldg256(ROW_UNIT(P.rows, s, 0, Wp, w)), u1 = ldg256(ROW_UNIT(P.rows, s, 1, Wp, w));
         const float jv[12] = {u0.lo.x, u0.lo.y, u0.lo.z, u0.lo.w, u0.hi.x, u0.hi.y,
                               u0.hi.z, u0.hi.w, u1.lo.x, u1.lo.y, u1.lo.z, u1.lo.w};

@@ -85,7 +85,8 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
     const int nev = P.reorder == 0 && P.iters > 8 ? (P.iters - 1) >> 3 : 0; // reshuffles per solve (iterations 8, 16, ..)
 
     for (int s = side; s < R + 2; s += 2) s_lam[s * WL + v] = s == R + 1 ? 1.f : 0.f;
-    for (int s = side; s < R; s += 2) s_ord[s * WL + v] = (uint8_t)s;
+    // the used slots in ODE's initial sweep order (b2p_assemble.cu); positions behind the world's rows are not read
+    for (int p = side; p < m; p += 2) s_ord[p * WL + v] = P.ord0[(size_t)p * Wp + w];
     for (int k = side; k < (nb + 1) * 3; k += 2) s_fc[k * WL + v] = make_float2(0.f, 0.f);
     const uint32_t seed = P.seed[w]; // the world's LCG state at the start of the step
     uint32_t seed_out = seed;        // ... and after the step's reshuffles
@@ -235,7 +236,10 @@ template <int KR> __global__ void __launch_bounds__(32) b2p_sor_kernel(const Ste
     }
 
     if (w < P.W) {
-        for (int s = side; s < m; s += 2) P.lambda[(size_t)s * Wp + w] = s_lam[s * WL + v];
+        for (int p = side; p < m; p += 2) {
+            const int s = s_ord[p * WL + v];
+            P.lambda[(size_t)s * Wp + w] = s_lam[s * WL + v];
+        }
         for (int k = side; k < nb * 3; k += 2) {
             const float2 f = s_fc[k * WL + v];
             float *dst = P.fcacc + (size_t)(k * 2) * Wp + w;

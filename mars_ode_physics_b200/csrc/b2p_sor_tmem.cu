@@ -70,6 +70,10 @@ __device__ __forceinline__ void tm_load_2rows(uint32_t taddr, Row &a, Row &b)
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void *g)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
 // NW warps per CTA (4 or 8): NW*32 worlds per SM.  With 8 warps two warps share a TMEM lane quadrant and split its
 // columns, so a world has 16 instead of 32 rows in TMEM but every scheduler has two warps to alternate between.
 template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_tmem_kernel(const StepParams P)
@@ -101,6 +105,9 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
     // (scratch aliases the overflow pool, which is not in use yet); which of two equally long worlds comes
     // first is arbitrary and does not influence any result.
     const size_t Wp = (size_t)P.Wp;
+    // CTAs take the worlds from the end: the assemble kernel wrote the rows of the last worlds last, so the first
+    // wave finds them in L2
+    const int cta = (P.tune & 1) ? (int)blockIdx.x : (int)(gridDim.x - 1 - blockIdx.x);
     int w, nr;
     bool valid; // false: a phantom thread (the CTA takes fewer than TW worlds, or reaches past the last world)
     {
@@ -108,7 +115,7 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
         int *const s_nr = s_cnt + ((R + 2 + 3) & ~3); // [TW] nrows word by sorted position
         uint16_t *const s_perm = (uint16_t *)(s_nr + TW);
         // a CTA takes P.worlds_per_cta <= TW consecutive worlds (the host evens out the last wave with it)
-        const int w0 = blockIdx.x * P.worlds_per_cta + tid;
+        const int w0 = cta * P.worlds_per_cta + tid;
         const int nr0 = tid < P.worlds_per_cta && w0 < P.W ? P.nrows[w0] : 0;
         const int m0 = nr0 & 0xffff;
         for (int i = tid; i < R + 2; i += TW) s_cnt[i] = 0;
@@ -132,7 +139,7 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
         // reverse, so that the two warps sharing a scheduler (i, i + 4) together have about the same work
         const int grp = NW == 8 && warp >= 4 ? 11 - warp : warp;
         const int src = s_perm[grp * 32 + lane];
-        w = blockIdx.x * P.worlds_per_cta + src;
+        w = cta * P.worlds_per_cta + src;
         nr = s_nr[grp * 32 + lane];
         // A phantom's index would name a world of the NEXT CTA: it must neither read that world's seed nor write
         // its results (it sweeps zero rows only, like every position behind a world's last row)
@@ -143,7 +150,7 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tbase = s_tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * (TROWS * 16));
 
-    const int wl = valid ? w : blockIdx.x * P.worlds_per_cta; // phantoms read (only zero rows of) the CTA's first world
+    const int wl = valid ? w : cta * P.worlds_per_cta; // phantoms read (only zero rows of) the CTA's first world
     const int m = nr & 0xffff, nisl = nr >> 16; // rows, island blocks (b2p_dev.h)
     const int mmax = __reduce_max_sync(0xffffffffu, m);
     const int nev = P.reorder == 0 && P.iters > 8 ? (P.iters - 1) >> 3 : 0; // reshuffles per solve (iterations 8, 16, ..)
@@ -157,7 +164,8 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
     float4 *const s_rows = s_pool + (size_t)obase * 4 * 32 + lane; // position p, vector g: s_rows[(p*4 + g)*32]
 
     for (int s = 0; s < R + 2; s++) s_lam[s * TW + tid] = s == R + 1 ? 1.f : 0.f;
-    for (int s = 0; s < R; s++) s_ord[s * TW + tid] = (uint8_t)s;
+    // the used slots in ODE's initial sweep order (b2p_assemble.cu); positions behind the world's rows are not read
+    for (int p = 0; p < m; p++) s_ord[p * TW + tid] = P.ord0[(size_t)p * Wp + wl];
     for (int k = 0; k < (nb + 1) * 3; k++) s_fc[k * TW + tid] = make_float2(0.f, 0.f);
     const uint32_t seed = P.seed[wl]; // the world's LCG state at the start of the step
     uint32_t seed_out = seed;         // ... and after the step's reshuffles
@@ -166,8 +174,13 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
     float2 *const fcL = s_fc + tid;
 
     // the row in slot `slot` of this world, from the slot-ordered rows in global memory (slot R = zero row)
+    // (unit (slot, u) of world wl lies (slot * 2 + u) * Wp * 32 bytes behind the world's unit (0, 0): a 32-bit offset
+    // -- the host checks that the row buffer is smaller than 4 GB -- instead of 64-bit index arithmetic per gather)
+    const char *const rows_w = (const char *)ROW_UNIT(P.rows, 0, 0, Wp, wl);
+    const uint32_t slot_stride = (uint32_t)P.Wp * 64u;
     auto gload = [&](int slot) -> Row {
-        const F8 u0 = ldg256(ROW_UNIT(P.rows, slot, 0, Wp, wl)), u1 = ldg256(ROW_UNIT(P.rows, slot, 1, Wp, wl));
+        const char *const pu = rows_w + (uint32_t)slot * slot_stride;
+        const F8 u0 = ldg256(pu), u1 = ldg256(pu + (slot_stride >> 1));
         const float4 v0 = u0.lo, v1 = u0.hi, v2 = u1.lo, v3 = u1.hi;
         Row q;
         q.j[0] = v0.x, q.j[1] = v0.y, q.j[2] = v0.z, q.j[3] = v0.w;
@@ -283,11 +296,44 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
             for (int k = 0; k < KR; k++) {
                 if ((k & ~3) < mmax) rr[k] = gload(slot_at(k));
             }
-            const int nchip = nt + no;
+            // overflow positions: straight from global to their place in the shared-memory pool (cp.async, no
+            // registers), all in flight while the register and Tensor Memory positions are worked on
+            if (no > 0) {
+                const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(s_rows);
+#pragma unroll 1
+                for (int p = 0; p < no; p++) {
+                    const char *const pu = rows_w + (uint32_t)slot_at(KR + TROWS + p) * slot_stride;
+                    const uint32_t d = dst0 + (uint32_t)(p * 4 * 32 * 16);
+                    cp_async16(d, pu);
+                    cp_async16(d + 32 * 16, pu + 16);
+                    cp_async16(d + 64 * 16, pu + (slot_stride >> 1));
+                    cp_async16(d + 96 * 16, pu + (slot_stride >> 1) + 16);
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
             constexpr int NPF = 3; // gathers in flight (rows)
             Row ring[NPF];
 #pragma unroll
-            for (int i = 0; i < NPF; i++) ring[i] = gload(slot_at(KR + i));
+            for (int i = 0; i < NPF; i++) ring[i] = gload(i < nt ? slot_at(KR + i) : R);
+            if (P.tune & 2) {
+                // experiment switch (B2P_TUNE=2): gather everything first, no arithmetic between the loads, and let
+                // the sweep below run from the chip
+#pragma unroll 1
+                for (int p = 0; p < nt; p += NPF) {
+#pragma unroll
+                    for (int i = 0; i < NPF; i++) {
+                        if (p + i < nt) {
+                            tm_store_row(tbase + (uint32_t)((p + i) * 16), ring[i]);
+                            ring[i] = gload(p + i + NPF < nt ? slot_at(KR + p + i + NPF) : R);
+                        }
+                    }
+                }
+                if (no > 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+                asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+                __syncwarp();
+                fresh = false;
+            }
+            if (fresh) {
 #pragma unroll
             for (int g = 0; g < KR; g += 4) {
                 if (g < mmax) {
@@ -296,19 +342,26 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
                 }
             }
 #pragma unroll 1
-            for (int p = 0; p < nchip; p += NPF) {
+            for (int p = 0; p < nt; p += NPF) {
 #pragma unroll
                 for (int i = 0; i < NPF; i++) {
-                    if (p + i < nchip) {
+                    if (p + i < nt) {
                         relax(ring[i]);
-                        deposit(p + i, ring[i]);
-                        ring[i] = gload(p + i + NPF < nchip ? slot_at(KR + p + i + NPF) : R);
+                        tm_store_row(tbase + (uint32_t)((p + i) * 16), ring[i]);
+                        ring[i] = gload(p + i + NPF < nt ? slot_at(KR + p + i + NPF) : R);
                     }
                 }
+            }
+            if (no > 0) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncwarp();
+#pragma unroll 1
+                for (int p = 0; p < no; p++) relax(sload(p));
             }
             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
             sweep_spilled();
             continue;
+            }
         }
         // positions in registers
 #pragma unroll
@@ -335,7 +388,10 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
     }
 
     if (valid) {
-        for (int s = 0; s < m; s++) P.lambda[(size_t)s * Wp + w] = s_lam[s * TW + tid];
+        for (int p = 0; p < m; p++) {
+            const int s = s_ord[p * TW + tid];
+            P.lambda[(size_t)s * Wp + w] = s_lam[s * TW + tid];
+        }
         for (int k = 0; k < nb * 3; k++) {
             const float2 f = s_fc[k * TW + tid];
             float *dst = P.fcacc + (size_t)(k * 2) * Wp + w;
