@@ -28,7 +28,7 @@ extern "C" int b2p_sor_tmem_rows_on_chip(int kr, int warps);
 extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, int nj, int maxc, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
-extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, cudaStream_t stream);
+extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, int nj, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_residual(const StepParams *P, float *out, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, int sampled, cudaStream_t stream);
 
@@ -693,6 +693,7 @@ int finalize(b2p_arena *a)
             CUDA_TRY(cudaStreamSynchronize(a->stream));
         }
         CUDA_TRY(cudaMemsetAsync(a->d_lambda, 0, sizeof(float) * mr * Wp, a->stream));
+        CUDA_TRY(cudaMemsetAsync(a->d_rowS, 0, sizeof(float) * mr * Wp, a->stream)); // (unused slots are read, then masked)
         a->scratch_rows = (size_t)maxrows;
         a->scratch_nb = (size_t)nb;
         a->scratch_maxc = (size_t)a->maxc;
@@ -2298,7 +2299,7 @@ int enqueue_step(b2p_arena *a, const StepParams &P, bool use_tmem, cudaStream_t 
     if (use_tmem) CUDA_TRY(b2p_launch_sor_tmem(&P, nb, maxrows, st));
     else CUDA_TRY(b2p_launch_sor(&P, nb, maxrows, st));
     if (timing) CUDA_TRY(cudaEventRecord(a->ev[2], st));
-    CUDA_TRY(b2p_launch_integrate(&P, nb, st));
+    CUDA_TRY(b2p_launch_integrate(&P, nb, (int)a->joints.size(), st));
     if (timing) CUDA_TRY(cudaEventRecord(a->ev[3], st));
     return 0;
 }

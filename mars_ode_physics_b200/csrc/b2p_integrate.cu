@@ -23,11 +23,16 @@ namespace {
 
 constexpr int BD = 64;
 
-__global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P)
+// `stash`: the CTA has shared memory for [nb*3 + nj*7][BD] floats -- the contact-force sum per body and the part of
+// the joint feedback Joint::update reads back -- so that neither goes through global memory and back
+__global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P, const int stash)
 {
+    extern __shared__ float s_stash[];
     const DevTemplate *__restrict__ T = P.T;
     const int nb = T->nb, nj = T->nj, maxc = T->maxc;
     const int tid = threadIdx.x;
+    float *const s_cf = s_stash + tid;                        // [nb*3][BD] contact force on body b
+    float *const s_jf = s_stash + (size_t)nb * 3 * BD + tid;  // [nj*7][BD] f t (of the reference's body1), lambda
     const int w = blockIdx.x * BD + tid;
     if (w >= P.W) return;
     const int Wp = P.Wp;
@@ -51,10 +56,11 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
                 x.pq0[k] = jc.b0 >= 0 ? G(P.state, jc.b0 * B2P_STATE_FIELDS + k) : 0.f;
                 x.pq1[k] = jc.b1 >= 0 ? G(P.state, jc.b1 * B2P_STATE_FIELDS + k) : 0.f;
             }
-            const int mrows = B2P_JR_ROWS(x.jr);
+            // all of the joint's slots, whether used this step or not (the row count is still on its way: no load
+            // here may depend on another one); the unused ones are masked when the count is there
 #pragma unroll
             for (int k = 0; k < B2P_ROWS_PER_JOINT; k++)
-                x.lam[k] = k < mrows ? G(P.lambda, x.slot + k) * G(P.rowS, x.slot + k) : 0.f; // lambda = lam' sqrt(Ad)
+                x.lam[k] = G(P.lambda, x.slot + k) * G(P.rowS, x.slot + k); // lambda = lam' sqrt(Ad)
         };
         JointIn nxt;
         if (nj > 0) load_joint(0, nxt);
@@ -78,7 +84,7 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
                     float lam = 0.f;
 #pragma unroll
                     for (int i = 0; i < B2P_ROWS_PER_JOINT; i++)
-                        if (i == k) lam = cur.lam[i];
+                        if (i == k && i < mrows) lam = cur.lam[i];
 #pragma unroll
                     for (int q = 0; q < 12; q++) acc[q] += r.J[q] * lam;
                     if (k == first_limot) flam = lam;
@@ -97,42 +103,48 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
 #pragma unroll
             for (int q = 0; q < 12; q++) G(P.jfb, j * 13 + q) = acc[q];
             G(P.jfb, j * 13 + 12) = flam;
+            if (stash && P.jupd) {
+                const int o = jc.reverse ? 6 : 0;
+#pragma unroll
+                for (int q = 0; q < 6; q++) s_jf[(size_t)(j * 7 + q) * BD] = o ? acc[6 + q] : acc[q];
+                s_jf[(size_t)(j * 7 + 6) * BD] = flam;
+            }
         }
     }
 
     // ---------------- contact feedback f1, and its sum per body (Frame::computeContactForce) ----------------
     const bool frame_out = P.bodyx != nullptr;
     if (frame_out) {
-        for (int b = 0; b < nb; b++) {
-            G(P.bodyx, b * 15 + 12) = 0.f;
-            G(P.bodyx, b * 15 + 13) = 0.f;
-            G(P.bodyx, b * 15 + 14) = 0.f;
+        for (int k = 0; k < nb * 3; k++) {
+            if (stash) s_cf[(size_t)k * BD] = 0.f;
+            else G(P.bodyx, (k / 3) * 15 + 12 + k % 3) = 0.f;
         }
     }
     {
         int nc = G(P.ccount, 0);
         if (nc > maxc) nc = maxc;
+        const int njslots = T->njslots, rpc = T->rpc;
         for (int c = 0; c < nc; c++) {
-            // the contact's rows sit in consecutive slots in emission order: normal, friction 1, friction 2, (rolling)
+            // the contact's rows sit in consecutive slots in emission order: normal, friction 1, friction 2,
+            // (rolling).  Everything is requested at once -- the two slots behind the normal row whether they hold
+            // friction rows or not -- and sorted out when the contact's row map is there.
+            const int s0 = njslots + c * rpc;
             const uint32_t cm = G(P.cmap, c);
-            int s = (cm >> 8) & 0xff;
-            const bool fr1 = (cm >> 24) & 1, fr2 = (cm >> 25) & 1;
             const int b0 = __float_as_int(G(P.crec, c * B2P_CONTACT_FIELDS + CR_IDS)) & 0xff;
             const float n[3] = {G(P.crec, c * B2P_CONTACT_FIELDS + CR_NX), G(P.crec, c * B2P_CONTACT_FIELDS + CR_NY),
                                 G(P.crec, c * B2P_CONTACT_FIELDS + CR_NZ)};
+            const float ln = G(P.lambda, s0) * G(P.rowS, s0);
+            const float la = G(P.lambda, s0 + 1) * G(P.rowS, s0 + 1), lb = G(P.lambda, s0 + 2) * G(P.rowS, s0 + 2);
+            const bool fr1 = (cm >> 24) & 1, fr2 = (cm >> 25) & 1;
             float t1[3], t2[3];
             plane_space(n, t1, t2);
-            const float ln = G(P.lambda, s) * G(P.rowS, s);
-            s++;
             float f[3] = {n[0] * ln, n[1] * ln, n[2] * ln};
             if (fr1) {
-                const float l1 = G(P.lambda, s) * G(P.rowS, s);
-                s++;
 #pragma unroll
-                for (int i = 0; i < 3; i++) f[i] += t1[i] * l1;
+                for (int i = 0; i < 3; i++) f[i] += t1[i] * la;
             }
             if (fr2) {
-                const float l2 = G(P.lambda, s) * G(P.rowS, s);
+                const float l2 = fr1 ? lb : la;
 #pragma unroll
                 for (int i = 0; i < 3; i++) f[i] += t2[i] * l2;
             }
@@ -141,9 +153,14 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
             G(P.cfb, c * 3 + 1) = f[1];
             G(P.cfb, c * 3 + 2) = f[2];
             if (frame_out) {
-                G(P.bodyx, b0 * 15 + 12) += f[0];
-                G(P.bodyx, b0 * 15 + 13) += f[1];
-                G(P.bodyx, b0 * 15 + 14) += f[2];
+                if (stash) {
+#pragma unroll
+                    for (int i = 0; i < 3; i++) s_cf[(size_t)(b0 * 3 + i) * BD] += f[i];
+                } else {
+                    G(P.bodyx, b0 * 15 + 12) += f[0];
+                    G(P.bodyx, b0 * 15 + 13) += f[1];
+                    G(P.bodyx, b0 * 15 + 14) += f[2];
+                }
             }
         }
     }
@@ -244,6 +261,7 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
                 G(P.bodyx, b * 15 + 9 + k) = (av[k] - cur.last[3 + k]) * hinv;
                 G(P.bodyx, b * 15 + k) = lv[k];
                 G(P.bodyx, b * 15 + 3 + k) = av[k];
+                if (stash) G(P.bodyx, b * 15 + 12 + k) = s_cf[(size_t)(b * 3 + k) * BD];
             }
         }
     }
@@ -316,9 +334,14 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
                 mul_R_v(anchor, p0.R, jc.anchor1);
 #pragma unroll
                 for (int i = 0; i < 3; i++) v1[i] = -anchor[i]; // body position - (body position + R anchor1)
+                float fa[3], ta[3]; // feedback force / torque on the reference's body1 (f1 t1, reversed: f2 t2)
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    fa[i] = stash ? s_jf[(size_t)(j * 7 + i) * BD] : G(P.jfb, j * 13 + (jc.reverse ? 6 : 0) + i);
+                    ta[i] = stash ? s_jf[(size_t)(j * 7 + 3 + i) * BD] : G(P.jfb, j * 13 + (jc.reverse ? 9 : 3) + i);
+                }
                 if (!jc.reverse) {
-                    const float f1[3] = {G(P.jfb, j * 13 + 0), G(P.jfb, j * 13 + 1), G(P.jfb, j * 13 + 2)};
-                    const float t1[3] = {G(P.jfb, j * 13 + 3), G(P.jfb, j * 13 + 4), G(P.jfb, j * 13 + 5)};
+                    const float *f1 = fa, *t1 = ta;
                     cross3(normal, axis, v1);
                     float d = dot3(normal, f1);
 #pragma unroll
@@ -336,8 +359,7 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
                         jl[i] += t1[i] - tmp1[i];
                     }
                 } else {
-                    const float f2[3] = {G(P.jfb, j * 13 + 6), G(P.jfb, j * 13 + 7), G(P.jfb, j * 13 + 8)};
-                    const float t2[3] = {G(P.jfb, j * 13 + 9), G(P.jfb, j * 13 + 10), G(P.jfb, j * 13 + 11)};
+                    const float *f2 = fa, *t2 = ta;
                     float d = dot3(f2, v1) / dot3(v1, v1);
 #pragma unroll
                     for (int i = 0; i < 3; i++) tmp1[i] = f2[i] - v1[i] * d;
@@ -357,7 +379,7 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
                     for (int i = 0; i < 3; i++) jl[i] += t2[i] - axis[i] * d;
                 }
             }
-            G(P.jupd, j * 7 + 0) = -G(P.jfb, j * 13 + 12);
+            G(P.jupd, j * 7 + 0) = -(stash ? s_jf[(size_t)(j * 7 + 6) * BD] : G(P.jfb, j * 13 + 12));
 #pragma unroll
             for (int i = 0; i < 3; i++) {
                 G(P.jupd, j * 7 + 1 + i) = at[i];
@@ -465,10 +487,13 @@ __global__ void __launch_bounds__(BD, 8) b2p_residual_kernel(const StepParams P,
 
 } // namespace
 
-extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, cudaStream_t stream)
+extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, int nj, cudaStream_t stream)
 {
     const int grid = (P->W + BD - 1) / BD;
-    b2p_integrate_kernel<<<grid, BD, 0, stream>>>(*P);
+    // the stash rides in the default 48 KB of dynamic shared memory; larger scenes go through global memory
+    const size_t smem = sizeof(float) * (size_t)(nb * 3 + nj * 7) * BD;
+    const int stash = smem <= 32 * 1024;
+    b2p_integrate_kernel<<<grid, BD, stash ? smem : 0, stream>>>(*P, stash);
     return cudaGetLastError();
 }
 
