@@ -159,6 +159,11 @@ int b2p_arena_set_sor_warps(b2p_arena *a, int warps);
 /* replay collide + step from a CUDA graph when their parameters did not change since the previous call
  * (default on; one host call per tick instead of four launches) */
 int b2p_arena_set_graph_launch(b2p_arena *a, int on);
+/* experiment switches of the kernels (bit mask; default: the environment variable B2P_TUNE, else 0 = production):
+ * 1 SOR CTAs take the worlds in ascending instead of descending order; 2 SOR streaming sweeps gather all rows
+ * first and sweep afterwards; 4 the integrate kernel keeps nothing in shared memory (the path scenes too large for
+ * the stash take).  Results do not depend on them. */
+int b2p_arena_set_tune(b2p_arena *a, int bits);
 /* What WorldPhysics::stepTheWorld does after the ODE call (src/WorldPhysics.cpp:372-397) is computed on the device
  * for every world.  Flags select the telemetry arrays; damping (b2p_body_set_damping) and joint friction
  * (b2p_joint_set_friction_coefficient) act on the state and are always applied.  Default: both. */

@@ -379,6 +379,9 @@ class Arena:
         return self.lib.b2p_padded_worlds(self.h)
 
     # -- round 2: graph launch, post-step outputs, diagnostics ------------------------------------
+    def set_tune(self, bits):
+        self._check(self.lib.b2p_arena_set_tune(self.h, int(bits)))
+
     def set_graph_launch(self, on=True):
         self._check(self.lib.b2p_arena_set_graph_launch(self.h, int(on)))
 

@@ -150,6 +150,7 @@ SIGNATURES = {
     "b2p_debug_kernel_times": (_I, [_P, _I, _DP]),
     "b2p_algorithmic_bytes_per_world_step": (_D, [_P]),
     "b2p_arena_set_graph_launch": (_I, [_P, _I]),
+    "b2p_arena_set_tune": (_I, [_P, _I]),
     "b2p_arena_set_post_step_outputs": (_I, [_P, _I]),
     "b2p_body_set_damping": (_I, [_P, _I, _D, _D]),
     "b2p_body_get_damping": (_I, [_P, _I, _DP, _DP]),

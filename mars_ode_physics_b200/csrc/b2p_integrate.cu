@@ -492,7 +492,7 @@ extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, int nj,
     const int grid = (P->W + BD - 1) / BD;
     // the stash rides in the default 48 KB of dynamic shared memory; larger scenes go through global memory
     const size_t smem = sizeof(float) * (size_t)(nb * 3 + nj * 7) * BD;
-    const int stash = smem <= 32 * 1024;
+    const int stash = smem <= 32 * 1024 && !(P->tune & 4);
     b2p_integrate_kernel<<<grid, BD, stash ? smem : 0, stream>>>(*P, stash);
     return cudaGetLastError();
 }

@@ -19,13 +19,15 @@ __device__ __forceinline__ F8 ldg256(const void *p) {
     return r;
 }
 __device__ __forceinline__ uint32_t lcg(uint32_t &s) { s = s * 1664525u + 1013904223u; return s >> 8; }
-template <int MODE> __global__ void __launch_bounds__(TW, 1) k(const float4 *__restrict__ rows, float *out, int passes)
+template <int MODE> __global__ void __launch_bounds__(TW, 1) k(const float4 *__restrict__ rows, float *out, int passes, int global_scatter)
 {
     extern __shared__ __align__(16) unsigned char sm[];
     const int tid = threadIdx.x, lane = tid & 31;
     // worlds of this thread: a scattered one inside the CTA's window (like the sorted worlds of the SOR kernel)
     const int base = blockIdx.x * 224;
-    const int w = base + (tid * 37) % 224;
+    // global_scatter: the CTA's worlds come from all over the batch (a globally rank-sorted assignment) instead of
+    // one 224-world window
+    const int w = global_scatter ? (int)(((unsigned)(base + tid) * 40503u + 12345u) % (unsigned)W) : base + (tid * 37) % 224;
     uint32_t s = 12345u + w;
     float acc = 0.f;
     for (int pass = 0; pass < passes; pass++) {
@@ -95,7 +97,7 @@ template <int MODE> __global__ void __launch_bounds__(TW, 1) k(const float4 *__r
     }
     out[blockIdx.x * TW + tid] = acc;
 }
-template <int MODE> void run(const char *name, const float4 *rows, float *out)
+template <int MODE> void run(const char *name, const float4 *rows, float *out, int gs = 0)
 {
     const int grid = (W + 223) / 224, passes = 3;
     size_t smem = MODE == 4 ? (size_t)6 * 4 * TW * 16 : 0;
@@ -103,10 +105,10 @@ template <int MODE> void run(const char *name, const float4 *rows, float *out)
     smem = smem < 120 * 1024 ? 120 * 1024 : smem; // one CTA per SM, as the SOR kernel
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k<MODE><<<grid, TW, smem>>>(rows, out, passes);
+    k<MODE><<<grid, TW, smem>>>(rows, out, passes, gs);
     cudaDeviceSynchronize();
     cudaEventRecord(e0);
-    for (int i = 0; i < 10; i++) k<MODE><<<grid, TW, smem>>>(rows, out, passes);
+    for (int i = 0; i < 10; i++) k<MODE><<<grid, TW, smem>>>(rows, out, passes, gs);
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -123,5 +125,6 @@ int main()
     run<2>("C pair exchange (16 lines/request), layout B", rows, out);
     run<3>("D LDG.128 x4, layout A", rows, out);
     run<4>("E cp.async 16B x4 -> smem, layout A", rows, out);
+    run<0>("A with the CTA's worlds scattered over the whole batch", rows, out, 1);
     return 0;
 }

@@ -535,3 +535,33 @@ def test_ode_island_order_with_device_collision(cuda_lib):
                 assert ab.rand_get_seed(w) == ob.rand_get_seed(w), (step, w)
                 checked += 1
     assert checked > 50 * Wb
+
+
+@pytest.mark.gpu
+def test_integrate_shared_memory_stash_changes_nothing(cuda_lib):
+    """The integrate kernel keeps the contact-force sums and Joint::update's inputs in shared memory when they fit
+    (nb*3 + nj*7 <= 128 columns); larger scenes read them back from global memory.  Both paths on the same scene
+    (tune bit 4 forces the second one), the SOR experiment switches along the way: bitwise equal."""
+    W = 96
+    outs = []
+    for tune in (0, 4, 1 | 2 | 4):
+        ar = Arena(W)
+        ar.set_tune(tune)
+        sc = scenes.quadruped(ar)
+        for b in sc["bodies"]:
+            ar.body_set_damping(b, 0.995, 0.99)
+        for j in sc["hip"]:
+            ar.joint_set_friction_coefficient(j, 0.05)
+        nb, nj = len(sc["bodies"]), len(sc["joints"])
+        t = 0.0
+        for step in range(40):
+            ar.contacts_clear()
+            for w in range(W):
+                scenes.quadruped_control(ar, sc, t, w, 0.4 * w)
+                scenes.sphere_plane_contacts(ar, sc["feet"], sc["foot_radius"], w)
+            ar.step(H)
+            t += H
+        outs.append((ar.state_download(nb), ar.body_post_download(nb), ar.joint_update_download(nj)))
+    for o in outs[1:]:
+        for x, y in zip(outs[0], o):
+            assert np.array_equal(x, y)
