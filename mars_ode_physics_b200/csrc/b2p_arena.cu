@@ -237,6 +237,7 @@ struct b2p_arena {
     int sor_warps = 0;       // Tensor-Memory kernel: warps per CTA (4 or 8); 0 = automatic
     int sm_count = 0;
     int sor_kernel_used = 0;
+    int tune = -1; // experiment switches (b2p_arena_set_tune); < 0: from the environment variable B2P_TUNE
     int *d_hw_rows = nullptr, *h_hw_rows = nullptr; // largest row count of any world so far (device / pinned copy)
     // optional per-kernel timing (bench / profiling): events around the three launches of a step
     bool timing = false;
@@ -2215,8 +2216,8 @@ int prepare_step(b2p_arena *a, double step_size, StepParams &P, bool &use_tmem)
     P.ord0 = a->d_ord0;
     P.order_mode = a->order_mode;
     {
-        static const int tune = getenv("B2P_TUNE") ? atoi(getenv("B2P_TUNE")) : 0;
-        P.tune = tune;
+        static const int env_tune = getenv("B2P_TUNE") ? atoi(getenv("B2P_TUNE")) : 0;
+        P.tune = a->tune >= 0 ? a->tune : env_tune;
     }
     P.jrows = a->jrows.dev;
     P.ccount = a->ccount.dev;
@@ -2463,6 +2464,13 @@ int b2p_collide_step(b2p_arena *a, double step_size)
 {
     if (a && a->geoms.empty()) return run_step(a, step_size, false);
     return run_step(a, step_size, true);
+}
+
+int b2p_arena_set_tune(b2p_arena *a, int bits)
+{
+    if (!a) return fail(B2P_EINVAL, "null arena");
+    a->tune = bits;
+    return 0;
 }
 
 int b2p_arena_set_graph_launch(b2p_arena *a, int on)
