@@ -2258,17 +2258,10 @@ int prepare_step(b2p_arena *a, double step_size, StepParams &P, bool &use_tmem)
             const int per = (a->W + waves * sms - 1) / (waves * sms);
             P.worlds_per_cta = std::min(tw, std::max(32, (per + 31) & ~31));
         }
-        // Pool size.  Shared memory comes in carve-out steps (.. 164, 196, 228 KB per SM) and what is left of the
-        // 256 KB is L1, which the per-lane gathers of the streaming sweeps live on: staying at the 196 KB step (60 KB
-        // of L1 instead of 28 KB) is worth more than the last pool units (65536 rover worlds: 48 units 0.302 ms,
-        // 59 units 0.326 ms; rows without a unit are read from L2 in place).  So the pool stops at the 196 KB step
-        // unless that would leave fewer than 24 units.
-        int pool_auto = pool_t;
-        {
-            const size_t fixed_t = b2p_sor_tmem_smem_bytes(nb, maxrows, 0, nw_t);
-            const size_t step = 196 * 1024;
-            if (fixed_t + 1024 + 24 * 2048 <= step) pool_auto = std::min(pool_t, (int)((step - 1024 - fixed_t) / 2048));
-        }
+        // Pool size: all the shared memory there is.  The kernel's row gathers do not allocate in L1 (LDG.NA), so
+        // nothing is gained by leaving shared memory to the L1 carve-out (65536 rover worlds: 59 units 0.266 ms,
+        // 48 units 0.292 ms; with L1-allocating gathers it was the other way round, 0.307 against 0.279 ms).
+        const int pool_auto = pool_t;
         P.rows_resident = a->rows_resident > 0 ? std::max(std::min(a->rows_resident, pool_t), 2) : pool_auto;
     } else {
         P.rows_registers = b2p_sor_register_rows(maxrows, a->rows_registers);

@@ -168,6 +168,17 @@ __device__ __forceinline__ F8 ldg256(const void *p)
                  : "l"(p));
     return r;
 }
+// The same load without keeping the line in L1 (LDG.NA): for data that is used once -- the per-lane row gathers of
+// the Tensor-Memory SOR kernel, whose 32 lines per request would otherwise churn through whatever L1 the kernel's
+// shared-memory carve-out leaves.
+__device__ __forceinline__ F8 ldg256_stream(const void *p)
+{
+    F8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+                 : "l"(p));
+    return r;
+}
 __device__ __forceinline__ void stg256(void *p, const float4 &lo, const float4 &hi)
 {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w),

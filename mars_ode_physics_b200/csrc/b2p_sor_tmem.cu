@@ -180,7 +180,7 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
     const uint32_t slot_stride = (uint32_t)P.Wp * 64u;
     auto gload = [&](int slot) -> Row {
         const char *const pu = rows_w + (uint32_t)slot * slot_stride;
-        const F8 u0 = ldg256(pu), u1 = ldg256(pu + (slot_stride >> 1));
+        const F8 u0 = ldg256_stream(pu), u1 = ldg256_stream(pu + (slot_stride >> 1));
         const float4 v0 = u0.lo, v1 = u0.hi, v2 = u1.lo, v3 = u1.hi;
         Row q;
         q.j[0] = v0.x, q.j[1] = v0.y, q.j[2] = v0.z, q.j[3] = v0.w;
