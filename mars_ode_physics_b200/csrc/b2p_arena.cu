@@ -254,12 +254,16 @@ struct b2p_arena {
     // one CUDA graph per launch shape: [0] = step, [1] = collide + step.  Re-captured when any kernel parameter
     // changes (step size, gravity, on-chip row split ...), launched with one call otherwise.
     struct StepGraph {
-        cudaGraphExec_t exec = nullptr;
+        // [0] (collide +) assemble, [1] SOR + integrate: the event the command uploads wait for is recorded on the
+        // stream between the two (recorded from inside one graph it only becomes visible when that graph ends)
+        // [2] all of it in one graph, used as long as nobody uploads per-tick commands
+        cudaGraphExec_t exec[3] = {nullptr, nullptr, nullptr};
         StepParams P{};
         CollideParams C{};
         int use_tmem = -1, sampled = -1;
     } graphs[2];
     bool use_graph = true;
+    bool upload_mode = false; // per-tick command uploads are in use (b2p_joints_set_param_batch): split step graph
     cudaStream_t cap_stream = nullptr; // capture happens here (the arena's own stream may be the legacy default stream)
     // pipelined observation read-back (b2p_body_get_state_batch_begin / b2p_io_wait): a copy stream and two
     // staging slots, so that the D2H of step k overlaps the kernels of step k+1
@@ -922,7 +926,8 @@ void b2p_arena_destroy(b2p_arena *a)
     mirror_free(a->jupd);
     free_scratch(a);
     for (b2p_arena::StepGraph &g : a->graphs)
-        if (g.exec) cudaGraphExecDestroy(g.exec);
+        for (int i = 0; i < 3; i++)
+            if (g.exec[i]) cudaGraphExecDestroy(g.exec[i]);
     if (a->d_dropped) cudaFree(a->d_dropped);
     if (a->d_residual) cudaFree(a->d_residual);
     for (cudaEvent_t e : a->ev)
@@ -1633,9 +1638,10 @@ int b2p_joints_set_param_batch(b2p_arena *a, int param, const float *values, int
     if (num != B2P_PARAM_VEL && num != B2P_PARAM_FMAX)
         return fail(B2P_EUNSUPPORTED, "only VEL and FMAX can be set per world");
     CUDA_TRY(cudaSetDevice(a->device));
-    // If the device copy is current and a step has been enqueued, the transfer goes over the copy stream behind
+    // If the device copy is current and a step has been enqueued, the transfer goes over the upload stream behind
     // that step's assemble kernel (the only reader of jcmd), i.e. it overlaps the step's SOR-LCP kernel.
-    const bool overlap = !a->jcmd.host_newer && a->jcmd.dev && a->asm_recorded && a->io_stream;
+    a->upload_mode = true;
+    const bool overlap = !a->jcmd.host_newer && a->jcmd.dev && a->asm_recorded;
     int rc = mirror_to_device(a, a->jcmd);
     if (rc) return rc;
     const size_t field = (size_t)axis * 2 + (num == B2P_PARAM_FMAX ? 1 : 0);
@@ -2275,26 +2281,38 @@ int prepare_step(b2p_arena *a, double step_size, StepParams &P, bool &use_tmem)
     return 0;
 }
 
-// the three launches of a step on stream `st` (a real stream, or the capture stream of a graph)
-int enqueue_step(b2p_arena *a, const StepParams &P, bool use_tmem, cudaStream_t st, bool capturing)
+// The assemble kernel is the only reader of the joint commands: an event behind it lets the next command upload
+// start while the step's SOR-LCP kernel is still running (b2p_joints_set_param_batch).
+cudaError_t mark_assemble_done(b2p_arena *a, cudaStream_t st)
+{
+    if (!a->ev_asm_done) {
+        cudaError_t e = cudaEventCreateWithFlags(&a->ev_asm_done, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    a->asm_recorded = true;
+    return cudaEventRecord(a->ev_asm_done, st);
+}
+
+// the three launches of a step on stream `st` (a real stream, or the capture stream of a graph); `part`: 0 the
+// assemble kernel, 1 the SOR-LCP and integrate kernels, -1 all three
+int enqueue_step(b2p_arena *a, const StepParams &P, bool use_tmem, cudaStream_t st, bool capturing, int part)
 {
     const int nb = (int)a->bodies.size();
     const int maxrows = (int)a->joints.size() * B2P_ROWS_PER_JOINT + a->maxc * rpc_of(a);
     const bool timing = a->timing && !capturing;
-    if (timing) CUDA_TRY(cudaEventRecord(a->ev[0], st));
-    CUDA_TRY(b2p_launch_assemble(&P, nb, (int)a->joints.size(), a->maxc, st));
-    if (a->io_stream) { // lets the next command upload start as soon as this kernel has read jcmd
-        if (!a->ev_asm_done) CUDA_TRY(cudaEventCreateWithFlags(&a->ev_asm_done, cudaEventDisableTiming));
-        if (capturing) CUDA_TRY(cudaEventRecordWithFlags(a->ev_asm_done, st, cudaEventRecordExternal));
-        else CUDA_TRY(cudaEventRecord(a->ev_asm_done, st));
-        a->asm_recorded = true;
+    if (part != 1) {
+        if (timing) CUDA_TRY(cudaEventRecord(a->ev[0], st));
+        CUDA_TRY(b2p_launch_assemble(&P, nb, (int)a->joints.size(), a->maxc, st));
+        if (!capturing) CUDA_TRY(mark_assemble_done(a, st));
+        if (timing) CUDA_TRY(cudaEventRecord(a->ev[1], st));
     }
-    if (timing) CUDA_TRY(cudaEventRecord(a->ev[1], st));
-    if (use_tmem) CUDA_TRY(b2p_launch_sor_tmem(&P, nb, maxrows, st));
-    else CUDA_TRY(b2p_launch_sor(&P, nb, maxrows, st));
-    if (timing) CUDA_TRY(cudaEventRecord(a->ev[2], st));
-    CUDA_TRY(b2p_launch_integrate(&P, nb, (int)a->joints.size(), st));
-    if (timing) CUDA_TRY(cudaEventRecord(a->ev[3], st));
+    if (part != 0) {
+        if (use_tmem) CUDA_TRY(b2p_launch_sor_tmem(&P, nb, maxrows, st));
+        else CUDA_TRY(b2p_launch_sor(&P, nb, maxrows, st));
+        if (timing) CUDA_TRY(cudaEventRecord(a->ev[2], st));
+        CUDA_TRY(b2p_launch_integrate(&P, nb, (int)a->joints.size(), st));
+        if (timing) CUDA_TRY(cudaEventRecord(a->ev[3], st));
+    }
     return 0;
 }
 
@@ -2344,41 +2362,56 @@ int run_step(b2p_arena *a, double step_size, bool with_collide)
                       (!with_collide || (memcmp(&g.C, &C, sizeof(C)) == 0 && g.sampled == sampled));
     const bool graph_ok = a->use_graph && !a->timing;
     if (graph_ok && same) {
-        if (!g.exec) {
+        const int first = a->upload_mode ? 0 : 2, last = a->upload_mode ? 1 : 2;
+        if (!g.exec[first]) {
             if (!a->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&a->cap_stream, cudaStreamNonBlocking));
-            cudaGraph_t graph = nullptr;
-            CUDA_TRY(cudaStreamBeginCapture(a->cap_stream, cudaStreamCaptureModeThreadLocal));
-            int erc = 0;
-            if (with_collide) {
-                cudaError_t e = b2p_launch_collide(&C, ng, sampled, a->cap_stream);
-                if (e != cudaSuccess) erc = fail(B2P_ECUDA, "collide launch (capture): %s", cudaGetErrorString(e));
-            }
-            if (!erc) erc = enqueue_step(a, P, use_tmem, a->cap_stream, true);
-            cudaError_t ee = cudaStreamEndCapture(a->cap_stream, &graph);
-            if (erc) {
+            for (int gi = first; gi <= last; gi++) {
+                const int part = gi == 2 ? -1 : gi;
+                cudaGraph_t graph = nullptr;
+                CUDA_TRY(cudaStreamBeginCapture(a->cap_stream, cudaStreamCaptureModeThreadLocal));
+                int erc = 0;
+                if (part != 1 && with_collide) {
+                    cudaError_t e = b2p_launch_collide(&C, ng, sampled, a->cap_stream);
+                    if (e != cudaSuccess) erc = fail(B2P_ECUDA, "collide launch (capture): %s", cudaGetErrorString(e));
+                }
+                if (!erc) erc = enqueue_step(a, P, use_tmem, a->cap_stream, true, part);
+                cudaError_t ee = cudaStreamEndCapture(a->cap_stream, &graph);
+                if (!erc && ee != cudaSuccess) erc = fail(B2P_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ee));
+                if (!erc) {
+                    ee = cudaGraphInstantiate(&g.exec[gi], graph, 0);
+                    if (ee != cudaSuccess) {
+                        g.exec[gi] = nullptr;
+                        erc = fail(B2P_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ee));
+                    }
+                }
                 if (graph) cudaGraphDestroy(graph);
-                return erc;
-            }
-            if (ee != cudaSuccess) return fail(B2P_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(ee));
-            ee = cudaGraphInstantiate(&g.exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (ee != cudaSuccess) {
-                g.exec = nullptr;
-                return fail(B2P_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ee));
+                if (erc) {
+                    for (int i = first; i <= last; i++) {
+                        if (g.exec[i]) cudaGraphExecDestroy(g.exec[i]);
+                        g.exec[i] = nullptr;
+                    }
+                    return erc;
+                }
             }
         }
-        CUDA_TRY(cudaGraphLaunch(g.exec, a->stream));
+        if (a->upload_mode) {
+            CUDA_TRY(cudaGraphLaunch(g.exec[0], a->stream));
+            CUDA_TRY(mark_assemble_done(a, a->stream));
+            CUDA_TRY(cudaGraphLaunch(g.exec[1], a->stream));
+        } else {
+            CUDA_TRY(cudaGraphLaunch(g.exec[2], a->stream));
+        }
     } else {
-        if (g.exec) {
-            cudaGraphExecDestroy(g.exec);
-            g.exec = nullptr;
+        for (int i = 0; i < 3; i++) {
+            if (g.exec[i]) cudaGraphExecDestroy(g.exec[i]);
+            g.exec[i] = nullptr;
         }
         g.P = P;
         g.C = C;
         g.use_tmem = use_tmem;
         g.sampled = sampled;
         if (with_collide) CUDA_TRY(b2p_launch_collide(&C, ng, sampled, a->stream));
-        if ((rc = enqueue_step(a, P, use_tmem, a->stream, false))) return rc;
+        if ((rc = enqueue_step(a, P, use_tmem, a->stream, false, -1))) return rc;
     }
     if (with_collide) after_collide(a);
     // refresh the host copy of the row high-water mark (every step at first, then occasionally)
