@@ -20,6 +20,8 @@
 // Rows are stored by constraint (static slots: joint j owns slots j*B2P_ROWS_PER_JOINT .., contact c owns
 // njslots + c*rpc ..); `ord0` lists the used slots in ODE's initial sweep order (per island: rows with findex < 0
 // first, in ODE's joint order, then the friction-dependent rows) and seeds the SOR kernels' order array.
+#include <mutex>
+
 #include "b2p_rows.cuh"
 
 namespace {
@@ -583,6 +585,8 @@ extern "C" size_t b2p_assemble_smem_bytes(int nb, int nj, int maxc, int islands)
 extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, int nj, int maxc, cudaStream_t stream)
 {
     static size_t configured_dev[B2P_MAX_DEVICES][2] = {{0, 0}}; // cudaFuncSetAttribute is per device
+    static std::mutex configured_mutex; // arenas of several threads / devices may launch at the same time
+    std::lock_guard<std::mutex> configured_lock(configured_mutex);
     int dev = 0;
     cudaGetDevice(&dev);
     const int isl = P->order_mode != 0;

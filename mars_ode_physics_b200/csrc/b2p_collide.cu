@@ -13,6 +13,7 @@
 // order canonical (the SOR row order depends on it).  No atomics, no cross-thread compaction:
 // each world appends to its own column of the stream.
 #include <cuda_runtime.h>
+#include <mutex>
 #include <math.h>
 #include <stdint.h>
 
@@ -1128,6 +1129,8 @@ template <bool SAMPLED> __global__ void __launch_bounds__(CBD) b2p_collide_kerne
 extern "C" cudaError_t b2p_launch_collide(const CollideParams *P, int ng, int sampled, cudaStream_t stream)
 {
     static size_t configured_dev[B2P_MAX_DEVICES][2] = {{0, 0}}; // cudaFuncSetAttribute is per device
+    static std::mutex configured_mutex; // arenas of several threads / devices may launch at the same time
+    std::lock_guard<std::mutex> configured_lock(configured_mutex);
     int dev = 0;
     cudaGetDevice(&dev);
     size_t *configured = configured_dev[dev % B2P_MAX_DEVICES];

@@ -38,6 +38,7 @@
 //     ord   uint8 [R][16]         the world's current row order (position -> slot)
 // HBM traffic is one read of the rows (64 B each) and one write of lam and fch.
 #include <cuda_runtime.h>
+#include <mutex>
 #include <math.h>
 #include <stdint.h>
 
@@ -273,6 +274,8 @@ extern "C" int b2p_sor_register_rows(int maxrows, int wanted)
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream)
 {
     static size_t configured_dev[B2P_MAX_DEVICES][6] = {{0}}; // cudaFuncSetAttribute is per device
+    static std::mutex configured_mutex; // arenas of several threads / devices may launch at the same time
+    std::lock_guard<std::mutex> configured_lock(configured_mutex);
     int dev = 0;
     cudaGetDevice(&dev);
     size_t *configured = configured_dev[dev % B2P_MAX_DEVICES];

@@ -29,6 +29,7 @@
 // The arithmetic of a row-iteration is term-by-term the one of b2p_sor.cu, so both kernels produce bitwise
 // identical multipliers (tests/test_gpu_parity.py::test_sor_kernels_agree).
 #include <cuda_runtime.h>
+#include <mutex>
 #include <math.h>
 #include <stdint.h>
 
@@ -427,6 +428,8 @@ extern "C" int b2p_sor_tmem_rows_on_chip(int kr, int warps) { return kr + 32 / (
 extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxrows, cudaStream_t stream)
 {
     static size_t configured_dev[B2P_MAX_DEVICES][2][3] = {{{0}}}; // cudaFuncSetAttribute is per device
+    static std::mutex configured_mutex; // arenas of several threads / devices may launch at the same time
+    std::lock_guard<std::mutex> configured_lock(configured_mutex);
     int dev = 0;
     cudaGetDevice(&dev);
     size_t (*configured)[3] = configured_dev[dev % B2P_MAX_DEVICES];
