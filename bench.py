@@ -563,7 +563,9 @@ def run_b200(args):
                        "sharding": f"worlds/{world_size} GPUs, no collective on the step path",
                        "l2": "per-step working set (row scratch) > L2; no flush needed",
                        "settle_steps": args.settle, "row_reordering": args.reorder, "row_order": args.row_order,
-                       "launch": "one CUDA graph (collide + assemble + SOR + integrate) per step",
+                       "launch": "one CUDA graph (collide + assemble + SOR + integrate) per step; in the end-to-end loop two, split "
+                                 "behind the assemble kernel, so that the next command upload can wait for an event "
+                                 "recorded between them",
                        "host_cores_pinned": pinned_cores,
                        "collision_semantics": "repo-defined (oracle/orc_collide.c), not ODE's dCollide: one contact "
                                               "per sphere-heightfield pair, <= 4 deepest vertices per box-plane pair",
@@ -578,6 +580,9 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
+                         # the same with the collide kernel's time in the denominator (the algorithmic bytes count
+                         # the geoms and the device-produced contact stream)
+                         "frac_incl_collide": balg * W / ((step_ms + collide_ms) * 1e-3) / 1e9 / peak,
                          "kernel": "one dWorldQuickStep = b2p_assemble_kernel + SOR-LCP kernel + b2p_integrate_kernel "
                                    "(three launches; achieved = algorithmic bytes of the step / their summed duration)",
                          "algorithmic_bytes_per_world_step": balg,
