@@ -18,6 +18,7 @@ class Arena:
         self.h = C.c_void_p()
         self._check(self.lib.b2p_arena_create(int(num_worlds), int(device), C.byref(self.h)))
         self.num_worlds = int(num_worlds)
+        self.device = int(device)
 
     # -- plumbing ---------------------------------------------------------------------------
     def _check(self, rc):
@@ -378,6 +379,35 @@ class Arena:
     def padded_worlds(self):
         return self.lib.b2p_padded_worlds(self.h)
 
+    # -- zero-copy views of the batched device arrays (CUDA array interface / DLPack) ---------------
+    _DEVICE_ARRAYS = {  # name -> (C ABI accessor, fields per item, which count, dtype)
+        "state": ("b2p_device_state", 13, "bodies", "<f4"),                   # pos3 quat4 lvel3 avel3
+        "joint_cmd": ("b2p_device_joint_cmd", 4, "joints", "<f4"),            # vel1 fmax1 vel2 fmax2
+        "joint_obs": ("b2p_device_joint_obs", 4, "joints", "<f4"),            # angle1 rate1 angle2 rate2
+        "joint_feedback": ("b2p_device_joint_feedback", 13, "joints", "<f4"), # f1 t1 f2 t2 lambda
+        "joint_update": ("b2p_device_joint_update", 7, "joints", "<f4"),      # motor torque, axis torque3, load3
+        "body_post": ("b2p_device_body_post", 15, "bodies", "<f4"),           # last vel6, acc6, contact force3
+        "contact_records": ("b2p_device_contact_records", 16, "contacts", "<f4"),
+        "contact_count": ("b2p_device_contact_count", 0, None, "<i4"),
+    }
+
+    def device_array(self, name, count=None):
+        """The device array ``name`` of the last step as an object with ``__cuda_array_interface__`` (version 3) and
+        ``__dlpack__``: shape ``[count, fields, padded_worlds]`` (world index fastest, worlds padded to a multiple of
+        32), float32, no copy.  ``count`` = number of bodies / joints / contact slots (the arrays hold all of the
+        scene's; pass fewer to view a prefix).  ``torch.as_tensor(arena.device_array("joint_obs", nj), device="cuda")``
+        or ``torch.from_dlpack(...)`` give a tensor on the arena's GPU; the arena keeps ownership, and the content is
+        defined once the arena's stream has reached the end of the step (``sync()`` or stream ordering)."""
+        fn, fields, _, typestr = self._DEVICE_ARRAYS[name]
+        ptr = getattr(self.lib, fn)(self.h)
+        if not ptr:
+            raise B2PError(-1, f"device array {name!r} does not exist (yet)")
+        if fields and count is None:
+            raise ValueError("count (bodies / joints / contact slots) is required")
+        Wp = self.padded_worlds()
+        shape = (Wp,) if fields == 0 else (int(count), fields, Wp)
+        return _DeviceArray(ptr, shape, typestr, self.device)
+
     # -- round 2: graph launch, post-step outputs, diagnostics ------------------------------------
     def set_tune(self, bits):
         self._check(self.lib.b2p_arena_set_tune(self.h, int(bits)))
@@ -449,3 +479,22 @@ class Arena:
         out = np.empty((self.num_worlds,), dtype=np.float32)
         self._check(self.lib.b2p_debug_lcp_residual(self.h, out.ctypes.data_as(C.c_void_p)))
         return out
+
+
+class _DeviceArray:
+    """A borrowed view of device memory: CUDA array interface v3, DLPack through torch when it is importable."""
+
+    def __init__(self, ptr, shape, typestr, device):
+        self.device = device
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None, "stream": None}
+
+    def _torch(self):
+        import torch
+        return torch.as_tensor(self, device=f"cuda:{self.device}")
+
+    def __dlpack__(self, stream=None):
+        return self._torch().__dlpack__(stream=stream)
+
+    def __dlpack_device__(self):
+        return (2, self.device)  # kDLCUDA

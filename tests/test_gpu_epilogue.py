@@ -565,3 +565,32 @@ def test_integrate_shared_memory_stash_changes_nothing(cuda_lib):
     for o in outs[1:]:
         for x, y in zip(outs[0], o):
             assert np.array_equal(x, y)
+
+
+@pytest.mark.gpu
+def test_device_arrays_as_cuda_array_interface_and_dlpack(cuda_lib):
+    """The batched observation / telemetry arrays are visible to other GPU code without a copy (CUDA array interface,
+    DLPack): what torch sees through them equals the C ABI's batched downloads."""
+    torch = pytest.importorskip("torch")
+    W = 40
+    ar = Arena(W)
+    sc = scenes.quadruped(ar)
+    nb, nj = len(sc["bodies"]), len(sc["joints"])
+    t = 0.0
+    for step in range(10):
+        ar.contacts_clear()
+        for w in range(W):
+            scenes.quadruped_control(ar, sc, t, w, 0.3 * w)
+            scenes.sphere_plane_contacts(ar, sc["feet"], sc["foot_radius"], w)
+        ar.step(H)
+        t += H
+    ar.sync()
+    obs = torch.as_tensor(ar.device_array("joint_obs", nj), device="cuda")
+    assert obs.shape == (nj, 4, ar.padded_worlds()) and obs.dtype == torch.float32
+    assert np.array_equal(obs[:, :, :W].cpu().numpy(), ar.joint_obs_download(nj))
+    st = torch.from_dlpack(ar.device_array("state", nb))
+    assert np.array_equal(st[:, :, :W].cpu().numpy(), ar.state_download(nb))
+    post = torch.from_dlpack(ar.device_array("body_post", nb))
+    assert np.array_equal(post[:, :, :W].cpu().numpy(), ar.body_post_download(nb))
+    cnt = torch.as_tensor(ar.device_array("contact_count"), device="cuda")
+    assert cnt.dtype == torch.int32 and [int(c) for c in cnt[:W].cpu()] == [ar.contact_count(w) for w in range(W)]
