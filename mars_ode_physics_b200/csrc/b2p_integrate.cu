@@ -17,6 +17,8 @@
 // lambda_n n + lambda_1 t1 + lambda_2 t2 with the tangents of dPlaneSpace(n).  The SOR kernel leaves
 // fch = M^-1/2 J^T lambda and lam' = lambda / sqrt(Ad) (see b2p_assemble.cu), so invM J^T lambda = M^-1/2 fch and
 // lambda = lam' * sqrt(Ad) (rowS).
+#include <mutex>
+
 #include "b2p_rows.cuh"
 
 namespace {
@@ -31,8 +33,21 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
     const DevTemplate *__restrict__ T = P.T;
     const int nb = T->nb, nj = T->nj, maxc = T->maxc;
     const int tid = threadIdx.x;
-    float *const s_cf = s_stash + tid;                        // [nb*3][BD] contact force on body b
-    float *const s_jf = s_stash + (size_t)nb * 3 * BD + tid;  // [nj*7][BD] f t (of the reference's body1), lambda
+    // the scene template's bodies and joints in shared memory (read warp-uniformly all over the kernel: a broadcast
+    // LDS instead of a global load on the thread's dependent chain), then the stash
+    uint32_t *const sb = (uint32_t *)s_stash;
+    uint32_t *const sj = sb + (size_t)nb * (sizeof(DevBody) / 4);
+    {
+        const uint32_t *gb = (const uint32_t *)T->bodies, *gj = (const uint32_t *)T->joints;
+        for (int i = tid; i < nb * (int)(sizeof(DevBody) / 4); i += BD) sb[i] = __ldg(gb + i);
+        for (int i = tid; i < nj * (int)(sizeof(DevJoint) / 4); i += BD) sj[i] = __ldg(gj + i);
+        __syncthreads();
+    }
+    const DevBody *const s_bodies = (const DevBody *)sb;
+    const DevJoint *const s_joints = (const DevJoint *)sj;
+    float *const s_st = (float *)(sj + (size_t)nj * (sizeof(DevJoint) / 4));
+    float *const s_cf = s_st + tid;                        // [nb*3][BD] contact force on body b
+    float *const s_jf = s_st + (size_t)nb * 3 * BD + tid;  // [nj*7][BD] f t (of the reference's body1), lambda
     const int w = blockIdx.x * BD + tid;
     if (w >= P.W) return;
     const int Wp = P.Wp;
@@ -48,7 +63,7 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
             float lam[B2P_ROWS_PER_JOINT];
         };
         auto load_joint = [&](int j, JointIn &x) {
-            const DevJoint &jc = T->joints[j];
+            const DevJoint &jc = s_joints[j];
             x.jr = G(P.jrows, j);
             x.slot = jc.slot_base; // joint j owns slots j * B2P_ROWS_PER_JOINT ..
 #pragma unroll
@@ -65,7 +80,7 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
         JointIn nxt;
         if (nj > 0) load_joint(0, nxt);
         for (int j = 0; j < nj; j++) {
-            const DevJoint &jc = T->joints[j];
+            const DevJoint &jc = s_joints[j];
             const JointIn cur = nxt;
             if (j + 1 < nj) load_joint(j + 1, nxt);
             const int jr = cur.jr;
@@ -191,7 +206,7 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
     BodyIn nxt;
     if (nb > 0) load_body(0, nxt);
     for (int b = 0; b < nb; b++) {
-        const DevBody &bc = T->bodies[b];
+        const DevBody &bc = s_bodies[b];
         const int f = b * B2P_STATE_FIELDS;
         const BodyIn cur = nxt;
         if (b + 1 < nb) load_body(b + 1, nxt);
@@ -268,7 +283,7 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
 
     // ---------------- joint observations, Joint::update and applyJointFriction from the new state -----------
     for (int j = 0; j < nj; j++) {
-        const DevJoint &jc = T->joints[j];
+        const DevJoint &jc = s_joints[j];
         float a1 = 0.f, r1 = 0.f, a2 = 0.f, r2 = 0.f;
         float axis[3] = {0.f, 0.f, 0.f};
         BodyPose p0, p1;
@@ -426,7 +441,7 @@ __global__ void __launch_bounds__(BD, 7) b2p_integrate_kernel(const StepParams P
 
     // ---------------- Frame::update, second half (Frame.cpp:922-941): multiplicative damping ---------------
     for (int b = 0; b < nb; b++) {
-        const DevBody &bc = T->bodies[b];
+        const DevBody &bc = s_bodies[b];
         const bool damp_l = bc.lin_damp < 1.f, damp_a = bc.ang_damp < 1.f;
         if (!damp_l && !damp_a) continue;
         const int f = b * B2P_STATE_FIELDS;
@@ -491,9 +506,22 @@ extern "C" cudaError_t b2p_launch_integrate(const StepParams *P, int nb, int nj,
 {
     const int grid = (P->W + BD - 1) / BD;
     // the stash rides in the default 48 KB of dynamic shared memory; larger scenes go through global memory
+    const size_t tmpl = (size_t)nb * sizeof(DevBody) + (size_t)nj * sizeof(DevJoint); // (<= 32 x 192 + 48 x 432 bytes)
     const size_t smem = sizeof(float) * (size_t)(nb * 3 + nj * 7) * BD;
-    const int stash = smem <= 32 * 1024 && !(P->tune & 4);
-    b2p_integrate_kernel<<<grid, BD, stash ? smem : 0, stream>>>(*P, stash);
+    const int stash = smem <= 24 * 1024 && !(P->tune & 4);
+    static bool configured_dev[B2P_MAX_DEVICES] = {false};
+    static std::mutex configured_mutex;
+    {
+        std::lock_guard<std::mutex> lock(configured_mutex);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!configured_dev[dev % B2P_MAX_DEVICES]) { // template copy of the largest scene + stash: above the default 48 KB
+            cudaError_t e = cudaFuncSetAttribute(b2p_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            if (e != cudaSuccess) return e;
+            configured_dev[dev % B2P_MAX_DEVICES] = true;
+        }
+    }
+    b2p_integrate_kernel<<<grid, BD, tmpl + (stash ? smem : 0), stream>>>(*P, stash);
     return cudaGetLastError();
 }
 
