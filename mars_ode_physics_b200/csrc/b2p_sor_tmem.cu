@@ -24,7 +24,8 @@
 // covers the load's latency.
 //
 // Shared memory per CTA (all accesses conflict-free: consecutive lanes = consecutive columns):
-//     fch   float2[(nb+1)*3][TW], lam float[R+2][TW], ord uint8[R][TW]   as in b2p_sor.cu, one column per thread
+//     fch   float4[nb+1][TW] + float2[nb+1][TW] (words 0..3 | 4, 5 of a body), lam float[R+2][TW], ord uint8[R][TW]:
+//           one column per thread
 //     pool  float4[units][4][32]                                          overflow positions
 // The arithmetic of a row-iteration is term-by-term the one of b2p_sor.cu, so both kernels produce bitwise
 // identical multipliers (tests/test_gpu_parity.py::test_sor_kernels_agree).
@@ -86,8 +87,10 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
     __shared__ int s_need[NW];
     const DevTemplate *__restrict__ T = P.T;
     const int nb = T->nb, R = T->maxrows, pool = P.rows_resident;
-    float2 *const s_fc = (float2 *)smem_raw;
-    float *const s_lam = (float *)(s_fc + (size_t)(nb + 1) * 3 * TW);
+    // fch of body b: words 0..3 in a float4 plane, words 4, 5 in a float2 plane (one LDS.128 + one LDS.64 per body)
+    float4 *const s_fc4 = (float4 *)smem_raw;
+    float2 *const s_fc2 = (float2 *)(s_fc4 + (size_t)(nb + 1) * TW);
+    float *const s_lam = (float *)(s_fc2 + (size_t)(nb + 1) * TW);
     uint8_t *const s_ord = (uint8_t *)(s_lam + (size_t)(R + 2) * TW);
     // overflow rows: `pool` units of one sweep position x 32 worlds, handed to the warps that need them
     float4 *const s_pool = (float4 *)(smem_raw + (((size_t)(nb + 1) * 3 * TW * 8 + (size_t)(R + 2) * TW * 4 + (size_t)R * TW + 15) & ~(size_t)15));
@@ -167,12 +170,16 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
     for (int s = 0; s < R + 2; s++) s_lam[s * TW + tid] = s == R + 1 ? 1.f : 0.f;
     // the used slots in ODE's initial sweep order (b2p_assemble.cu); positions behind the world's rows are not read
     for (int p = 0; p < m; p++) s_ord[p * TW + tid] = P.ord0[(size_t)p * Wp + wl];
-    for (int k = 0; k < (nb + 1) * 3; k++) s_fc[k * TW + tid] = make_float2(0.f, 0.f);
+    for (int k = 0; k < nb + 1; k++) {
+        s_fc4[k * TW + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+        s_fc2[k * TW + tid] = make_float2(0.f, 0.f);
+    }
     const uint32_t seed = P.seed[wl]; // the world's LCG state at the start of the step
     uint32_t seed_out = seed;         // ... and after the step's reshuffles
 
     float *const lamL = s_lam + tid;
-    float2 *const fcL = s_fc + tid;
+    float4 *const fc4L = s_fc4 + tid;
+    float2 *const fc2L = s_fc2 + tid;
 
     // the row in slot `slot` of this world, from the slot-ordered rows in global memory (slot R = zero row)
     // (unit (slot, u) of world wl lies (slot * 2 + u) * Wp * 32 bytes behind the world's unit (0, 0): a 32-bit offset
@@ -208,10 +215,11 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
         const uint32_t mt = q.meta;
         float *lp = lamL + (mt & 0xff) * TW;
         const float *ln = lamL + ((mt >> 8) & 0xff) * TW;
-        float2 *pa = fcL + ((mt >> 16) & 0x3f) * (3 * TW);
-        float2 *pb = fcL + ((mt >> 24) & 0x3f) * (3 * TW);
-        float2 a0 = pa[0], a1 = pa[TW], a2 = pa[2 * TW];
-        float2 b0 = pb[0], b1 = pb[TW], b2 = pb[2 * TW];
+        const int ba = ((mt >> 16) & 0x3f) * TW, bb = ((mt >> 24) & 0x3f) * TW;
+        const float4 a01 = fc4L[ba], b01 = fc4L[bb];
+        float2 a2 = fc2L[ba], b2 = fc2L[bb];
+        float2 a0 = make_float2(a01.x, a01.y), a1 = make_float2(a01.z, a01.w);
+        float2 b0 = make_float2(b01.x, b01.y), b1 = make_float2(b01.z, b01.w);
         const float lam_old = *lp, lam_n = *ln;
         // J.fch per side as (even terms) + (odd terms), each a chain of fused multiply-adds: two packed chains here,
         // the same scalar chains in b2p_sor.cu
@@ -231,8 +239,8 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
         a0 = sor_fma2(dd, make_float2(q.j[0], q.j[1]), a0), a1 = sor_fma2(dd, make_float2(q.j[2], q.j[3]), a1);
         a2 = sor_fma2(dd, make_float2(q.j[4], q.j[5]), a2), b0 = sor_fma2(dd, make_float2(q.j[6], q.j[7]), b0);
         b1 = sor_fma2(dd, make_float2(q.j[8], q.j[9]), b1), b2 = sor_fma2(dd, make_float2(q.j[10], q.j[11]), b2);
-        pa[0] = a0, pa[TW] = a1, pa[2 * TW] = a2;
-        pb[0] = b0, pb[TW] = b1, pb[2 * TW] = b2;
+        fc4L[ba] = make_float4(a0.x, a0.y, a1.x, a1.y), fc2L[ba] = a2;
+        fc4L[bb] = make_float4(b0.x, b0.y, b1.x, b1.y), fc2L[bb] = b2;
     };
 
     Row rr[KR > 0 ? KR : 1];
@@ -393,11 +401,11 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
             const int s = s_ord[p * TW + tid];
             P.lambda[(size_t)s * Wp + w] = s_lam[s * TW + tid];
         }
-        for (int k = 0; k < nb * 3; k++) {
-            const float2 f = s_fc[k * TW + tid];
-            float *dst = P.fcacc + (size_t)(k * 2) * Wp + w;
-            dst[0] = f.x;
-            dst[Wp] = f.y;
+        for (int b = 0; b < nb; b++) {
+            const float4 f = s_fc4[b * TW + tid];
+            const float2 g = s_fc2[b * TW + tid];
+            float *dst = P.fcacc + (size_t)(b * 6) * Wp + w;
+            dst[0] = f.x, dst[Wp] = f.y, dst[2 * Wp] = f.z, dst[3 * Wp] = f.w, dst[4 * Wp] = g.x, dst[5 * Wp] = g.y;
         }
         P.seed[w] = seed_out;
     }
