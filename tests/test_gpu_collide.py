@@ -411,6 +411,38 @@ def test_config_c_device_collision_sampled_worlds(cuda_lib):
     ar.close()
 
 
+def test_config_d_full_size_sampled_worlds(cuda_lib):
+    """BASELINE config D at its full size as bench.py runs it (65536 rovers on the shared heightfield, device
+    collision, ODE island row order, random row reordering): the last 6 worlds of the batch against the same 6
+    worlds built alone on the oracle (placement and wheel speed depend on the world id only), 400 steps from the
+    drop to driving on the terrain, free-running."""
+    import bench
+    W, S = 65536, 6
+    ar = _Arena(W)
+    sa = bench.build_rover_worlds(ar, W)
+    ar.set_order_mode(capi.ORDER_ODE_ISLANDS)
+    oc = orc.OracleBatch(S)
+    so = bench.build_rover_worlds(oc, S, world_offset=W - S)
+    oc.set_order_mode(capi.ORDER_ODE_ISLANDS)
+    nb = len(sa["bodies"])
+    for step in range(400):
+        ar.collide_step(0.001)
+        oc.collide_step(0.001)
+    got = ar.state_download(nb)[:, :, W - S:].astype(np.float64)
+    want = oc.state_download(nb)
+    d = np.abs(got - want)
+    print("config D full size, 400 steps: pos", d[:, :3].max(), "quat", d[:, 3:7].max(), "lvel", d[:, 7:10].max(),
+          "avel", d[:, 10:].max())
+    for k in range(S):
+        assert ar.contact_count(W - S + k) == oc.contact_count(k)
+        assert ar.last_num_rows(W - S + k) == oc.last_num_rows(k)
+        assert ar.rand_get_seed(W - S + k) == oc.rand_get_seed(k)
+    # (observed on B200: pos 1.1e-5, quat 1.5e-5, lvel 4.3e-4, avel 7.8e-4; bars at about ten times that)
+    assert d[:, :3].max() < 1e-4 and d[:, 3:7].max() < 2e-4 and d[:, 7:10].max() < 5e-3 and d[:, 10:].max() < 1e-2, d.max()
+    assert sum(oc.contact_count(k) for k in range(S)) >= S  # the rovers are on the ground
+    ar.close()
+
+
 def test_sampled_colliders_against_committed_golden(cuda_lib):
     """Device contact records of the sample-point colliders vs the committed oracle fixture
     (tests/golden/sampled_colliders_oracle_f64.npz: 5 pair types x 24 seeded poses)."""
