@@ -93,6 +93,14 @@ enum {
     ORC_REORDER_NONE = 1      /* REORDERING_METHOD__DONT_REORDER */
 };
 
+/* which ODE stepper orc_world_quickstep runs: dWorldQuickStep (SOR-LCP, fast_step == true,
+ * src/WorldPhysics.cpp:365) or dWorldStep (dense LCP solved by Dantzig's method, fast_step == false,
+ * src/WorldPhysics.cpp:369; oracle/orc_lcp.c) */
+enum {
+    ORC_STEPPER_QUICK = 0,
+    ORC_STEPPER_DENSE = 1
+};
+
 /* Restatement choices: details of ODE 0.16 that this oracle restates from memory and that only a run of the real
  * libode can settle.  Value 0 is what the oracle (and the device path) does; the other
  * values are the plausible alternatives, so that the day a libode is available the pin is one run per switch.
@@ -105,6 +113,8 @@ enum {
 };
 struct orc_world;
 void orc_world_set_variant(struct orc_world *w, int which, int value);
+void orc_world_set_stepper(struct orc_world *w, int stepper);
+int orc_world_last_lcp_error(const struct orc_world *w);
 
 /* the dContact record as filled by Frame::addContact (Frame.cpp:1023-1079) */
 typedef struct orc_contact_desc {

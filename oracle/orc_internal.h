@@ -19,6 +19,10 @@ typedef double real;
 #define R_FABS fabs
 #define R_ATAN2 atan2
 #define ORC_DEFAULT_CFM 1e-10
+/* orc_lcp.c: Dantzig box-LCP solver of dWorldStep */
+int orc_solve_lcp(int n, const double *A, double *x, const double *b, double *w, double *lo, double *hi,
+                  const int *findex);
+
 #endif
 
 
@@ -73,6 +77,8 @@ typedef struct {
 struct orc_world {
     real gravity[3], erp, cfm, max_angular_speed, contact_max_vel, contact_min_depth, sor_w;
     int iters, order_mode, reorder_method;
+    int stepper;        /* ORC_STEPPER_QUICK / ORC_STEPPER_DENSE (orc.h) */
+    int last_lcp_error; /* dense stepper: the LCP solver gave up in some island of the last step */
     int variant[ORC_NUM_VARIANTS]; /* restatement choices that only a real libode can settle (orc.h) */
     uint32_t seed;
     body_t *bodies;
@@ -96,5 +102,9 @@ struct orc_world {
     int npairs, cappairs;
 };
 
+
+/* orc_lcp.c: Dantzig box-LCP solver of dWorldStep */
+int orc_solve_lcp(int n, const double *A, double *x, const double *b, double *w, double *lo, double *hi,
+                  const int *findex);
 
 #endif

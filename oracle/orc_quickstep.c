@@ -352,6 +352,8 @@ void orc_world_set_quickstep_num_iterations(orc_world *w, int n) { w->iters = n;
 void orc_world_set_quickstep_w(orc_world *w, double sor_w) { w->sor_w = (real)sor_w; }
 void orc_world_set_order_mode(orc_world *w, int m) { w->order_mode = m; }
 void orc_world_set_reorder_method(orc_world *w, int m) { w->reorder_method = m; }
+void orc_world_set_stepper(orc_world *w, int s) { w->stepper = s; }
+int orc_world_last_lcp_error(const orc_world *w) { return w->last_lcp_error; }
 void orc_world_rand_set_seed(orc_world *w, uint32_t seed) { w->seed = seed; }
 uint32_t orc_world_rand_get_seed(const orc_world *w) { return w->seed; }
 int orc_world_last_num_rows(const orc_world *w) { return w->last_m; }
@@ -1947,11 +1949,66 @@ static void quickstep_island(orc_world *w, int *bodies, int nb, jref_t *jl, int 
             } else {
                 for (int k = 6; k < 12; k++) o[k] = 0;
             }
+            if (w->stepper == ORC_STEPPER_DENSE) {
+                Ad[i] = 1; /* dWorldStep solves the unscaled system */
+                Adcfm[i] = cfm[i];
+                continue;
+            }
             Ad[i] = w->sor_w / (sum + cfm[i]);
             int nk = jb[2 * i + 1] >= 0 ? 12 : 6;
             for (int k = 0; k < nk; k++) J[k] *= Ad[i];
             rhs[i] *= Ad[i];
             Adcfm[i] = Ad[i] * cfm[i];
+        }
+
+        if (w->stepper == ORC_STEPPER_DENSE) {
+            /* dWorldStep (ODE step.cpp): A = J invM J^T + diag(cfm / h), then dSolveLCP (orc_lcp.c); the constraint
+             * force invM J^T lambda goes where the SOR sweep accumulates it */
+            double *A = (double *)calloc((size_t)m * m, sizeof(double));
+            double *xs = (double *)malloc(sizeof(double) * (size_t)m), *bs = (double *)malloc(sizeof(double) * (size_t)m);
+            double *ws = (double *)malloc(sizeof(double) * (size_t)m), *los = (double *)malloc(sizeof(double) * (size_t)m);
+            double *his = (double *)malloc(sizeof(double) * (size_t)m);
+            for (int i = 0; i < m; i++) {
+                for (int k = 0; k < m; k++) {
+                    double s = 0;
+                    for (int si = 0; si < 2; si++) {
+                        const int bi = jb[2 * i + si];
+                        if (bi < 0) continue;
+                        for (int sk = 0; sk < 2; sk++) {
+                            if (jb[2 * k + sk] != bi) continue;
+                            for (int q = 0; q < 6; q++) s += (double)rows[i].J[6 * si + q] * (double)iMJ[12 * k + 6 * sk + q];
+                        }
+                    }
+                    A[(size_t)i * m + k] = s;
+                }
+                A[(size_t)i * m + i] += (double)cfm[i];
+                bs[i] = (double)rhs[i];
+                los[i] = (double)rows[i].lo;
+                his[i] = (double)rows[i].hi;
+            }
+            /* symmetrise (the two triangles differ by rounding only) */
+            for (int i = 0; i < m; i++)
+                for (int k = i + 1; k < m; k++) {
+                    const double a = 0.5 * (A[(size_t)i * m + k] + A[(size_t)k * m + i]);
+                    A[(size_t)i * m + k] = a, A[(size_t)k * m + i] = a;
+                }
+            if (orc_solve_lcp(m, A, xs, bs, ws, los, his, findex)) w->last_lcp_error = 1;
+            for (int i = 0; i < m; i++) {
+                lambda[i] = (real)xs[i];
+                /* the friction rows' bounds were fixed from the friction-less solution: hand them to the
+                 * residual diagnostic below as plain bounds */
+                rows[i].lo = (real)los[i];
+                rows[i].hi = (real)his[i];
+                findex[i] = -1;
+                const real *im = iMJ + 12 * i;
+                real *f1 = fc + 6 * jb[2 * i];
+                for (int q = 0; q < 6; q++) f1[q] += lambda[i] * im[q];
+                if (jb[2 * i + 1] >= 0) {
+                    real *f2 = fc + 6 * jb[2 * i + 1];
+                    for (int q = 0; q < 6; q++) f2[q] += lambda[i] * im[6 + q];
+                }
+            }
+            free(A), free(xs), free(bs), free(ws), free(los), free(his);
         }
 
         /* order: rows with findex < 0 first, dependent rows last */
@@ -1968,7 +2025,7 @@ static void quickstep_island(orc_world *w, int *bodies, int nb, jref_t *jl, int 
             }
         }
 
-        for (int it = 0; it < w->iters; it++) {
+        for (int it = 0; it < (w->stepper == ORC_STEPPER_DENSE ? 0 : w->iters); it++) {
             if (w->reorder_method == ORC_REORDER_RANDOMLY && (it % 8) == 0 &&
                 (it >= 8 || w->variant[ORC_VARIANT_SHUFFLE_AT_0])) {
                 /* ODE ConstraintsReorderingHelper on both partitions */
@@ -2147,6 +2204,7 @@ void orc_world_quickstep(orc_world *w, double hd)
     w->last_m = 0;
     w->last_islands = 0;
     w->last_residual = 0;
+    w->last_lcp_error = 0;
     int total_j = w->nj + w->nc;
     int *bodies = (int *)malloc(sizeof(int) * (size_t)(w->nb > 0 ? w->nb : 1));
     jref_t *jl = (jref_t *)malloc(sizeof(jref_t) * (size_t)(total_j > 0 ? total_j : 1));

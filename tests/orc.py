@@ -82,6 +82,7 @@ def load(single=False):
         "orc_world_set_reorder_method": (None, [P, I]),
         "orc_world_rand_set_seed": (None, [P, C.c_uint32]), "orc_world_rand_get_seed": (C.c_uint32, [P]),
         "orc_world_set_variant": (None, [P, I, I]),
+        "orc_world_set_stepper": (None, [P, I]), "orc_world_last_lcp_error": (I, [P]),
         "orc_world_quickstep": (None, [P, D]), "orc_world_last_num_rows": (I, [P]),
         "orc_world_last_num_islands": (I, [P]), "orc_world_last_residual": (D, [P]),
         "orc_world_num_bodies": (I, [P]), "orc_world_num_joints": (I, [P]),
@@ -250,6 +251,13 @@ class OracleBatch:
 
     def set_order_mode(self, m):
         self._all(self.lib.orc_world_set_order_mode, m)
+
+    def set_stepper(self, stepper):
+        """0: dWorldQuickStep (SOR-LCP); 1: dWorldStep (dense LCP, Dantzig)"""
+        self._all(self.lib.orc_world_set_stepper, stepper)
+
+    def last_lcp_error(self, world):
+        return self.lib.orc_world_last_lcp_error(self.worlds[world])
 
     def set_variant(self, which, value):
         """restatement choices (orc.h ORC_VARIANT_*)"""
