@@ -156,6 +156,20 @@ int b2p_arena_sor_kernel_used(const b2p_arena *a);
 /* Tensor-Memory kernel: warps (x 32 worlds) per CTA, 4 or 8; 0 = automatic */
 int b2p_arena_set_sor_warps(b2p_arena *a, int warps);
 
+/* Which ODE stepper b2p_step runs.  B2P_STEPPER_QUICK: dWorldQuickStep (SOR-LCP, the reference's fast_step == true,
+ * src/WorldPhysics.cpp:365).  B2P_STEPPER_DENSE: dWorldStep (fast_step == false, src/WorldPhysics.cpp:369, the
+ * WorldPhysics constructor's default :82): the same rows, the box-LCP solved exactly by Dantzig's method (ODE
+ * lcp.cpp dSolveLCP) in FP64, one world per thread; O(rows^3) per world and step. */
+#define B2P_STEPPER_QUICK 0
+#define B2P_STEPPER_DENSE 1
+int b2p_arena_set_stepper(b2p_arena *a, int stepper);
+int b2p_arena_stepper(const b2p_arena *a);
+/* dense stepper: worlds (accumulated over all steps) in which the solver gave up -- ODE prints "LCP internal error"
+ * and carries on with the multipliers found so far, so does this */
+int b2p_dense_failures(b2p_arena *a, long long *count);
+/* dense stepper, debug: complementarity residual of the last step's solved problem per world (W floats) */
+int b2p_dense_residual(b2p_arena *a, float *host_out);
+
 /* replay collide + step from a CUDA graph when their parameters did not change since the previous call
  * (default on; one host call per tick instead of four launches) */
 int b2p_arena_set_graph_launch(b2p_arena *a, int on);

@@ -474,6 +474,24 @@ class Arena:
         return self._check(self.lib.b2p_observe_begin(self.h, b, C.c_void_p(host_body_ptr),
                                                       C.c_void_p(host_jobs_ptr) if host_jobs_ptr else None))
 
+    def set_stepper(self, stepper):
+        """capi.STEPPER_QUICK (dWorldQuickStep) or capi.STEPPER_DENSE (dWorldStep: exact dense LCP)"""
+        self._check(self.lib.b2p_arena_set_stepper(self.h, int(stepper)))
+
+    def stepper(self):
+        return self.lib.b2p_arena_stepper(self.h)
+
+    def dense_failures(self):
+        v = C.c_longlong()
+        self._check(self.lib.b2p_dense_failures(self.h, C.byref(v)))
+        return v.value
+
+    def dense_residual(self):
+        """dense stepper: per-world complementarity residual of the last step's solved (scaled) problem"""
+        out = np.empty((self.num_worlds,), dtype=np.float32)
+        self._check(self.lib.b2p_dense_residual(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def lcp_residual(self):
         """per-world LCP residual of the last step (projected |J invM J^T lambda + cfm lambda - rhs|)"""
         out = np.empty((self.num_worlds,), dtype=np.float32)

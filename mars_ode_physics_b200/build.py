@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-SOURCES = ["b2p_assemble.cu", "b2p_sor.cu", "b2p_sor_tmem.cu", "b2p_integrate.cu", "b2p_arena.cu", "b2p_collide.cu"]
+SOURCES = ["b2p_assemble.cu", "b2p_sor.cu", "b2p_sor_tmem.cu", "b2p_dense.cu", "b2p_integrate.cu", "b2p_arena.cu", "b2p_collide.cu"]
 HEADERS = ["b2p_dev.h", "b2p_math.cuh", "b2p_kern.cuh", "b2p_rows.cuh", "b2p_universal.h",
            os.path.join("..", "..", "include", "mars_ode_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

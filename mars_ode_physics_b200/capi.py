@@ -22,6 +22,7 @@ CONTACT_APPROX1 = 0x7000
 REORDER_RANDOMLY, REORDER_NONE = 0, 1
 ORDER_WORLD_BLOCK, ORDER_ODE_ISLANDS = 0, 1
 SOR_AUTO, SOR_PAIRED, SOR_TMEM = -1, 0, 1
+STEPPER_QUICK, STEPPER_DENSE = 0, 1  # dWorldQuickStep | dWorldStep (fast_step == false)
 GEOM_SPHERE, GEOM_BOX, GEOM_CAPSULE, GEOM_CYLINDER, GEOM_PLANE, GEOM_HEIGHTFIELD = range(6)
 E_REJECTED = -6
 
@@ -66,6 +67,10 @@ SIGNATURES = {
     "b2p_arena_set_sor_kernel": (_I, [_P, _I]),
     "b2p_arena_sor_kernel_used": (_I, [_P]),
     "b2p_arena_set_sor_warps": (_I, [_P, _I]),
+    "b2p_arena_set_stepper": (_I, [_P, _I]),
+    "b2p_arena_stepper": (_I, [_P]),
+    "b2p_dense_failures": (_I, [_P, C.POINTER(C.c_longlong)]),
+    "b2p_dense_residual": (_I, [_P, _P]),
     "b2p_world_set_gravity": (_I, [_P, _D, _D, _D]),
     "b2p_world_set_cfm": (_I, [_P, _D]),
     "b2p_world_set_erp": (_I, [_P, _D]),

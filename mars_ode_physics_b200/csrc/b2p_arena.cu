@@ -25,6 +25,8 @@ extern "C" size_t b2p_sor_smem_bytes(int nb, int maxrows, int rows_resident);
 extern "C" int b2p_sor_register_rows(int maxrows, int wanted);
 extern "C" size_t b2p_sor_tmem_smem_bytes(int nb, int maxrows, int pool, int warps);
 extern "C" int b2p_sor_tmem_rows_on_chip(int kr, int warps);
+extern "C" void b2p_dense_scratch_sizes(int nb, int maxrows, size_t *mat_doubles, size_t *vec_doubles, size_t *set_bytes);
+extern "C" cudaError_t b2p_launch_dense(const StepParams *P, const DenseScratch *D, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, int nj, int maxc, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
@@ -237,6 +239,9 @@ struct b2p_arena {
     int sor_warps = 0;       // Tensor-Memory kernel: warps per CTA (4 or 8); 0 = automatic
     int sm_count = 0;
     int sor_kernel_used = 0;
+    int stepper = 0;      // B2P_STEPPER_QUICK / B2P_STEPPER_DENSE
+    DenseScratch dense{}; // scratch of the dense stepper (allocated on first use)
+    int dense_rows = 0, dense_nb = 0;
     int tune = -1; // experiment switches (b2p_arena_set_tune); < 0: from the environment variable B2P_TUNE
     int *d_hw_rows = nullptr, *h_hw_rows = nullptr; // largest row count of any world so far (device / pinned copy)
     // optional per-kernel timing (bench / profiling): events around the three launches of a step
@@ -467,6 +472,14 @@ void free_scratch(b2p_arena *a)
     a->d_lambda = a->d_rowS = a->d_invIw = a->d_fcacc = nullptr;
     a->d_cmap = nullptr;
     a->scratch_rows = a->scratch_nb = a->scratch_maxc = 0;
+    if (a->dense.A) cudaFree(a->dense.A);
+    if (a->dense.L) cudaFree(a->dense.L);
+    if (a->dense.vec) cudaFree(a->dense.vec);
+    if (a->dense.sets) cudaFree(a->dense.sets);
+    if (a->dense.failures) cudaFree(a->dense.failures);
+    if (a->dense.residual) cudaFree(a->dense.residual);
+    a->dense = DenseScratch{};
+    a->dense_rows = a->dense_nb = 0;
 }
 
 // Square root of a symmetric positive (semi)definite 3x3 matrix (row-major) by cyclic Jacobi rotations:
@@ -2273,6 +2286,31 @@ int prepare_step(b2p_arena *a, double step_size, StepParams &P, bool &use_tmem)
         P.rows_registers = b2p_sor_register_rows(maxrows, a->rows_registers);
         P.rows_resident = pick_rows_resident(a, nb, maxrows, P.rows_registers);
     }
+    P.stepper = a->stepper;
+    if (a->stepper == B2P_STEPPER_DENSE) {
+        if (maxrows > 254) return fail(B2P_ECAPACITY, "the dense stepper supports at most 254 rows per world");
+        if (a->dense_rows != maxrows || a->dense_nb != nb || !a->dense.A) {
+            if (a->dense.A) cudaFree(a->dense.A);
+            if (a->dense.L) cudaFree(a->dense.L);
+            if (a->dense.vec) cudaFree(a->dense.vec);
+            if (a->dense.sets) cudaFree(a->dense.sets);
+            a->dense.A = a->dense.L = a->dense.vec = nullptr;
+            a->dense.sets = nullptr;
+            size_t md = 0, vd = 0, sb = 0;
+            b2p_dense_scratch_sizes(nb, std::max(maxrows, 1), &md, &vd, &sb);
+            CUDA_TRY(cudaMalloc(&a->dense.A, sizeof(double) * md * (size_t)a->Wp));
+            CUDA_TRY(cudaMalloc(&a->dense.L, sizeof(double) * md * (size_t)a->Wp));
+            CUDA_TRY(cudaMalloc(&a->dense.vec, sizeof(double) * vd * (size_t)a->Wp));
+            CUDA_TRY(cudaMalloc(&a->dense.sets, sb * (size_t)a->Wp));
+            if (!a->dense.failures) {
+                CUDA_TRY(cudaMalloc(&a->dense.failures, sizeof(int)));
+                CUDA_TRY(cudaMemsetAsync(a->dense.failures, 0, sizeof(int), a->stream));
+            }
+            if (!a->dense.residual) CUDA_TRY(cudaMalloc(&a->dense.residual, sizeof(float) * (size_t)a->Wp));
+            a->dense_rows = maxrows;
+            a->dense_nb = nb;
+        }
+    }
     if (a->order_mode == B2P_ORDER_ODE_ISLANDS && a->maxc > 64)
         return fail(B2P_ECAPACITY, "the island row order supports at most 64 contacts per world");
     if (b2p_assemble_smem_bytes(nb, (int)a->joints.size(), a->maxc, a->order_mode) > kSmemMax ||
@@ -2307,7 +2345,8 @@ int enqueue_step(b2p_arena *a, const StepParams &P, bool use_tmem, cudaStream_t 
         if (timing) CUDA_TRY(cudaEventRecord(a->ev[1], st));
     }
     if (part != 0) {
-        if (use_tmem) CUDA_TRY(b2p_launch_sor_tmem(&P, nb, maxrows, st));
+        if (P.stepper == B2P_STEPPER_DENSE) CUDA_TRY(b2p_launch_dense(&P, &a->dense, st));
+        else if (use_tmem) CUDA_TRY(b2p_launch_sor_tmem(&P, nb, maxrows, st));
         else CUDA_TRY(b2p_launch_sor(&P, nb, maxrows, st));
         if (timing) CUDA_TRY(cudaEventRecord(a->ev[2], st));
         CUDA_TRY(b2p_launch_integrate(&P, nb, (int)a->joints.size(), st));
@@ -2547,6 +2586,38 @@ int b2p_arena_set_sor_warps(b2p_arena *a, int warps)
 {
     if (!a || (warps != 0 && warps != 4 && warps != 8)) return fail(B2P_EINVAL, "warps per CTA must be 0, 4 or 8");
     a->sor_warps = warps;
+    return 0;
+}
+
+int b2p_arena_set_stepper(b2p_arena *a, int stepper)
+{
+    if (!a || (stepper != B2P_STEPPER_QUICK && stepper != B2P_STEPPER_DENSE)) return fail(B2P_EINVAL, "bad stepper selector");
+    a->stepper = stepper;
+    return 0;
+}
+
+int b2p_arena_stepper(const b2p_arena *a) { return a ? a->stepper : 0; }
+
+int b2p_dense_failures(b2p_arena *a, long long *count)
+{
+    if (!a || !count) return fail(B2P_EINVAL, "null argument");
+    *count = 0;
+    if (!a->dense.failures) return 0;
+    CUDA_TRY(cudaSetDevice(a->device));
+    int v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, a->dense.failures, sizeof(int), cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
+    *count = v;
+    return 0;
+}
+
+int b2p_dense_residual(b2p_arena *a, float *host_out)
+{
+    if (!a || !host_out) return fail(B2P_EINVAL, "null argument");
+    if (!a->stepped || !a->dense.residual || a->stepper != B2P_STEPPER_DENSE) return fail(B2P_EINVAL, "no dense step has run yet");
+    CUDA_TRY(cudaSetDevice(a->device));
+    CUDA_TRY(cudaMemcpyAsync(host_out, a->dense.residual, sizeof(float) * (size_t)a->W, cudaMemcpyDeviceToHost, a->stream));
+    CUDA_TRY(cudaStreamSynchronize(a->stream));
     return 0;
 }
 

@@ -136,6 +136,16 @@ struct StepParams {
     float *bodyx; // [nb*15][Wp] last_l_vel3 last_a_vel3 l_acc3 a_acc3 contact_force3  (Frame::update, computeContactForce)
     float *jupd;  // [nj*7][Wp]  motor_torque axis1_torque3 joint_load3              (Joint::update)
     int tune;     // experiment switches from the environment variable B2P_TUNE (bit mask; 0 in production)
+    int stepper;  // 0: dWorldQuickStep (SOR-LCP kernels); 1: dWorldStep (dense LCP, b2p_dense.cu)
+};
+
+// per-world scratch of the dense stepper (b2p_dense.cu), every array world index fastest
+struct DenseScratch {
+    double *A, *L;  // [maxrows * maxrows][Wp]: the LCP matrix; the Cholesky factor of its clamped block
+    double *vec;    // [9 * maxrows + 6 * (nb + 1)][Wp]: x w lo hi dx dw b + two solve vectors; fch in double
+    uint8_t *sets;  // [5 * maxrows][Wp]: clamped list, set of every row, scratch list, normal-row position, order
+    int *failures;  // worlds in which the solver gave up (ODE: "LCP internal error"), accumulated
+    float *residual; // [Wp] complementarity residual of the solved problem, or null
 };
 
 // unit u (0, 1) of the row in `slot` of world w: a pointer to two consecutive float4
