@@ -292,15 +292,20 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def measure_workload(Arena, torch, stream, name, builder, W, world_offset, settle, steps, peak, order_mode=1):
+def measure_workload(Arena, torch, stream, name, builder, W, world_offset, settle, steps, peak, order_mode=1, dense=False):
     """A secondary configuration (BASELINE configs 2, 3, 5): device-resident collide + step over `steps` steps,
-    CUDA events on the launch stream, plus the per-kernel split.  Returns (dict for the JSON line, ms)."""
+    CUDA events on the launch stream, plus the per-kernel split.  Returns (dict for the JSON line, ms).
+    dense: the worlds settle under dWorldQuickStep, the timed steps run dWorldStep (fast_step == false)."""
     ar = Arena(W, device=torch.cuda.current_device())
     ar.set_stream(stream.cuda_stream)
     builder(ar, W, world_offset=world_offset)
     ar.set_order_mode(order_mode)
     for _ in range(settle):
         ar.collide_step(H)
+    if dense:
+        ar.set_stepper(1)
+        for _ in range(3):
+            ar.collide_step(H)
     ar.sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -333,6 +338,10 @@ def measure_workload(Arena, torch, stream, name, builder, W, world_offset, settl
                          "integrate": float(kt[2])},
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "algorithmic_bytes_per_world_step": balg}}
+    if dense:
+        out["stepper"] = "dWorldStep (fast_step == false): dense LCP, Dantzig's method, FP64, one world per thread; kernel_ms.sor is b2p_dense_lcp_kernel"
+        out["lcp_failures"] = ar.dense_failures()
+        out["max_lcp_residual"] = float(ar.dense_residual().max())
     ar.close()
     return out, ms
 
@@ -529,6 +538,14 @@ def run_b200(args):
                 r["value"] = Wx * r["steps"] / (ms_x * 1e-3)
                 r["unit"] = UNIT
                 extra[key] = r
+            # the exact stepper (dWorldStep, the reference's fast_step == false) on config D
+            Wd = min(W, 16384)
+            r, ms_x = measure_workload(Arena, torch, stream, WORKLOAD, build_rover_worlds, Wd, 0, args.settle, 10, peak,
+                                       capi.ORDER_ODE_ISLANDS if args.row_order == "islands" else capi.ORDER_WORLD_BLOCK,
+                                       dense=True)
+            r["value"] = Wd * r["steps"] / (ms_x * 1e-3)
+            r["unit"] = UNIT
+            extra["dense_stepper_D_%d" % Wd] = r
         barrier()
     achieved = balg * W / (step_ms * 1e-3) / 1e9
     mean_rows = float(np.mean([ar.last_num_rows(w) for w in range(0, W, max(1, W // 256))]))

@@ -124,24 +124,20 @@ void WorldPhysics::computeContactForces()
         if (auto f = pair.second.lock()) f->computeContactForce();
 }
 
-// reference :349-421.  Only the quickstep path exists on the device.  fast_step == false asks for dWorldStep (the
-// dense LCP), which is not implemented: the call then steps NOTHING, raises
-// WorldPhysics::error / lastStepFailed() and says so on stderr -- it never silently substitutes quickstep.
-// Everything the reference does after the ODE call (Joint::update, Frame::update, computeContactForces) is part
-// of b2p_step's device epilogue for all worlds; the loops below only drop per-object caches.
+// reference :349-421.  fast_step selects the stepper exactly as the reference does (:365-370): true runs
+// dWorldQuickStep (the SOR-LCP kernels), false -- the constructor's default -- dWorldStep (the dense LCP solved by
+// Dantzig's method, b2p_dense.cu; exact and O(rows^3) per world).  Everything the reference does after the ODE call
+// (Joint::update, Frame::update, computeContactForces) is part of b2p_step's device epilogue for all worlds; the
+// loops below only drop per-object caches.
 void WorldPhysics::stepTheWorld(void)
 {
     const MutexLocker locker{&iMutex};
     if (!(world_init && step_size > 0)) return;
     preStepChecks();
     step_failed = false;
-    if (!fast_step) {
-        fprintf(stderr, "mars_ode_physics_b200: ERROR fast_step == false selects dWorldStep, which the device path does "
-                        "not implement; the world was NOT stepped (set fast_step = true for dWorldQuickStep)\n");
-        WorldPhysics::error = PHYSICS_ERROR;
-        step_failed = true;
-    } else {
+    {
         try {
+            checkB2P(b2p_arena_set_stepper(arena, fast_step ? B2P_STEPPER_QUICK : B2P_STEPPER_DENSE), "WorldPhysics::stepTheWorld");
             if (device_collision) {
                 flushGeoms();
                 checkB2P(b2p_collide_step(arena, step_size), "WorldPhysics::stepTheWorld");

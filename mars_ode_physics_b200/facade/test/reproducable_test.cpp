@@ -58,6 +58,7 @@ int main(int argc, char **argv)
     const std::string csv = argc > 1 ? argv[1] : "reproducable_test_log.csv";
     const double t_end = argc > 2 ? atof(argv[2]) : 4.0;
     const int num_worlds = argc > 3 ? atoi(argv[3]) : 1;
+    const bool fast_step = argc > 4 ? atoi(argv[4]) != 0 : true; // 0: dWorldStep (the reference's default), 1: dWorldQuickStep
 
     // the test registers "sphere" as Box, like the reference test does
     ObjectFactory::Instance().addObjectType("box", &Box::instantiate);
@@ -77,7 +78,7 @@ int main(int argc, char **argv)
         return 2;
     }
     wp.step_size = 0.001;
-    wp.fast_step = true;
+    wp.fast_step = fast_step;
 
     ConfigMap map;
     const LinkSpec links[9] = {{"body", 0.4, 1.0},      {"fl_upper", 0.03, 0.2}, {"fl_lower", 0.03, 0.2},

@@ -664,10 +664,18 @@ int orc_mars_reproducable_tick(orc_mars *m, const int frames[13], const int join
 
 int orc_mars_run_reproducable_test(const char *csv_path, double t_end, int order_mode, double *last_pos)
 {
+    return orc_mars_run_reproducable_test_stepper(csv_path, t_end, order_mode, ORC_STEPPER_QUICK, last_pos);
+}
+
+/* the same run with the stepper the reference's fast_step selects (src/WorldPhysics.cpp:365-370) */
+int orc_mars_run_reproducable_test_stepper(const char *csv_path, double t_end, int order_mode, int stepper,
+                                           double *last_pos)
+{
     orc_mars *m = orc_mars_create();
     int frames[13], joints[12];
     orc_mars_build_reproducable_scene(m, frames, joints);
     orc_world_set_order_mode(m->w, order_mode);
+    orc_world_set_stepper(m->w, stepper);
     FILE *file = csv_path ? fopen(csv_path, "w") : 0;
     if (file) fprintf(file, "time_sec,body_x,body_y,body_z\n");
     double time = 0.0, pos[3] = {0, 0, 0};

@@ -85,6 +85,8 @@ void orc_mars_build_reproducable_scene(orc_mars *m, int frames[13], int joints[1
 int orc_mars_reproducable_tick(orc_mars *m, const int frames[13], const int joints[12], double time);
 /* whole run; writes the "%g,%g,%g,%g" CSV if path != NULL; returns number of rows written */
 int orc_mars_run_reproducable_test(const char *csv_path, double t_end, int order_mode, double *last_pos);
+int orc_mars_run_reproducable_test_stepper(const char *csv_path, double t_end, int order_mode, int stepper,
+                                           double *last_pos);
 
 #ifdef __cplusplus
 }

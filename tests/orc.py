@@ -172,6 +172,7 @@ def load(single=False):
         "orc_mars_build_reproducable_scene": (None, [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "orc_mars_reproducable_tick": (I, [P, C.POINTER(C.c_int), C.POINTER(C.c_int), D]),
         "orc_mars_run_reproducable_test": (I, [C.c_char_p, D, I, DP]),
+        "orc_mars_run_reproducable_test_stepper": (I, [C.c_char_p, D, I, I, DP]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

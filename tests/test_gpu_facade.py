@@ -20,9 +20,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "mars_ode_physics_b200", "lib", "reproducable_test")
 
 
-def _run(path, t_end, worlds=1):
+def _run(path, t_end, worlds=1, fast_step=1):
     assert os.path.exists(BIN), "facade test binary missing: run __graft_entry__.build()"
-    subprocess.run([BIN, path, str(t_end), str(worlds)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    subprocess.run([BIN, path, str(t_end), str(worlds), str(fast_step)], check=True, stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
     return np.loadtxt(path, delimiter=",", skiprows=1)
 
 
@@ -46,6 +47,28 @@ def test_reproducable_scene_matches_oracle(cuda_lib, orc_lib, tmp_path):
     assert err[:100].max() < 2e-4
     assert err.max() < 5e-3
     assert np.abs(ora[-1, 1:]).max() > 1e-3  # the robot actually moved
+
+
+def test_reproducable_scene_with_fast_step_false(cuda_lib, orc_lib, tmp_path):
+    """fast_step == false (the WorldPhysics constructor's default, reference src/WorldPhysics.cpp:82) selects
+    dWorldStep (:367-370): through the facade that is the dense stepper (b2p_dense.cu), here on the reference's own
+    test scene against the oracle's restatement of it (orc_lcp.c).  Deterministic like the quickstep run; the
+    scene is over-constrained (84 rows, fixed joints, world cfm 1e-10), so the fp32 rows limit the agreement
+    (tests/test_gpu_dense.py::test_dense_quadruped_with_friction states that sensitivity)."""
+    a = _run(str(tmp_path / "d1.csv"), 0.2, 1, 0)
+    b = _run(str(tmp_path / "d2.csv"), 0.2, 1, 0)
+    assert np.array_equal(a, b)
+    ocsv = str(tmp_path / "orc_dense.csv")
+    rows = orc_lib.orc_mars_run_reproducable_test_stepper(ocsv.encode(), 0.2, orc.ORDER_ODE_ISLANDS, 1, None)
+    ora = np.loadtxt(ocsv, delimiter=",", skiprows=1)
+    quick = _run(str(tmp_path / "q.csv"), 0.2, 1, 1)
+    assert rows == len(ora) == len(a)
+    err = np.abs(a[:, 1:] - ora[:, 1:])
+    print("facade fast_step=false vs oracle dWorldStep: max |dx| over 0.05 s", err[:50].max(), "over 0.2 s", err.max(),
+          "| dense vs quickstep on the device", np.abs(a[:, 1:] - quick[:, 1:]).max())
+    assert np.isfinite(a).all()
+    assert err[:50].max() < 5e-4 and err.max() < 1e-2
+    assert np.abs(a[:, 1:] - quick[:, 1:]).max() > 0.0  # it really is another stepper
 
 
 def test_facade_replicas_agree(cuda_lib, tmp_path):
