@@ -339,7 +339,7 @@ def measure_workload(Arena, torch, stream, name, builder, W, world_offset, settl
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "algorithmic_bytes_per_world_step": balg}}
     if dense:
-        out["stepper"] = "dWorldStep (fast_step == false): dense LCP, Dantzig's method, FP64, one world per thread; kernel_ms.sor is b2p_dense_lcp_kernel"
+        out["stepper"] = "dWorldStep (fast_step == false): dense LCP, Dantzig's method, FP64, one warp per world in shared memory; kernel_ms.sor is b2p_dense_warp_kernel"
         out["lcp_failures"] = ar.dense_failures()
         out["max_lcp_residual"] = float(ar.dense_residual().max())
     ar.close()
@@ -539,7 +539,7 @@ def run_b200(args):
                 r["unit"] = UNIT
                 extra[key] = r
             # the exact stepper (dWorldStep, the reference's fast_step == false) on config D
-            Wd = min(W, 16384)
+            Wd = W
             r, ms_x = measure_workload(Arena, torch, stream, WORKLOAD, build_rover_worlds, Wd, 0, args.settle, 10, peak,
                                        capi.ORDER_ODE_ISLANDS if args.row_order == "islands" else capi.ORDER_WORLD_BLOCK,
                                        dense=True)

@@ -26,7 +26,8 @@ extern "C" int b2p_sor_register_rows(int maxrows, int wanted);
 extern "C" size_t b2p_sor_tmem_smem_bytes(int nb, int maxrows, int pool, int warps);
 extern "C" int b2p_sor_tmem_rows_on_chip(int kr, int warps);
 extern "C" void b2p_dense_scratch_sizes(int nb, int maxrows, size_t *mat_doubles, size_t *vec_doubles, size_t *set_bytes);
-extern "C" cudaError_t b2p_launch_dense(const StepParams *P, const DenseScratch *D, cudaStream_t stream);
+extern "C" cudaError_t b2p_launch_dense(const StepParams *P, const DenseScratch *D, int nb, int maxrows, int sm_count,
+                                        int force_thread_kernel, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_sor_tmem(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_assemble(const StepParams *P, int nb, int nj, int maxc, cudaStream_t stream);
 extern "C" cudaError_t b2p_launch_sor(const StepParams *P, int nb, int maxrows, cudaStream_t stream);
@@ -2345,7 +2346,7 @@ int enqueue_step(b2p_arena *a, const StepParams &P, bool use_tmem, cudaStream_t 
         if (timing) CUDA_TRY(cudaEventRecord(a->ev[1], st));
     }
     if (part != 0) {
-        if (P.stepper == B2P_STEPPER_DENSE) CUDA_TRY(b2p_launch_dense(&P, &a->dense, st));
+        if (P.stepper == B2P_STEPPER_DENSE) CUDA_TRY(b2p_launch_dense(&P, &a->dense, nb, maxrows, a->sm_count, (P.tune & 8) != 0, st));
         else if (use_tmem) CUDA_TRY(b2p_launch_sor_tmem(&P, nb, maxrows, st));
         else CUDA_TRY(b2p_launch_sor(&P, nb, maxrows, st));
         if (timing) CUDA_TRY(cudaEventRecord(a->ev[2], st));

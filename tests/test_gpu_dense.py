@@ -136,3 +136,48 @@ def test_dense_graph_launch_and_switching(cuda_lib):
         ar.close()
     assert np.isfinite(outs[0]).all()
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_dense_warp_kernel_equals_thread_kernel(cuda_lib):
+    """The two dense kernels (one warp per world in shared memory; one thread per world in global scratch, the
+    fallback for scenes beyond ~160 row slots) run the same pivoting sequence and differ only in the order of their
+    floating-point sums: after 200 steps of the rover scene (contacts, friction, index removals) and 40 steps of the
+    quadruped (84 rows, three position-vector elements per lane) the states agree to 1e-5 and both solve their
+    LCPs."""
+    import bench
+    outs = []
+    for tune in (0, 8):
+        ar = Arena(70)
+        sc = bench.build_rover_worlds(ar, 70)
+        ar.set_tune(tune)
+        ar.set_stepper(capi.STEPPER_DENSE)
+        for _ in range(200):
+            ar.collide()
+            ar.step(H)
+        assert ar.dense_failures() == 0
+        assert float(ar.dense_residual().max()) < 1e-9
+        outs.append(ar.state_download(len(sc["bodies"])).astype(np.float64))
+        ar.close()
+    d = np.abs(outs[0] - outs[1])
+    print("rover: warp kernel vs thread kernel", d[:, :7].max(), d[:, 7:].max())
+    assert d[:, :7].max() < 1e-5 and d[:, 7:].max() < 1e-3
+    outs = []
+    for tune in (0, 8):
+        ar = Arena(9)
+        sc = scenes.quadruped(ar)
+        ar.set_tune(tune)
+        ar.set_stepper(capi.STEPPER_DENSE)
+        t = 0.0
+        for _ in range(40):
+            ar.contacts_clear()
+            for w in range(9):
+                scenes.quadruped_control(ar, sc, t, w, 0.37 * w)
+                scenes.sphere_plane_contacts(ar, sc["feet"], sc["foot_radius"], w, mu=0.0)
+            ar.step(H)
+            t += H
+        assert ar.dense_failures() == 0
+        outs.append(ar.state_download(len(sc["bodies"])).astype(np.float64))
+        ar.close()
+    d = np.abs(outs[0] - outs[1])
+    print("quadruped: warp kernel vs thread kernel", d[:, :7].max(), d[:, 7:].max())
+    assert d[:, :7].max() < 1e-6 and d[:, 7:].max() < 1e-4
