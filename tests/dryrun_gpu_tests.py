@@ -19,6 +19,7 @@ class FakeArena(orc.OracleBatch):
     def set_sor_kernel(self, k): self._kernel = k
     def sor_kernel_used(self): return self._kernel
     def set_sor_warps(self, n): pass
+    def set_tune(self, bits): pass
     def set_stepper(self, s): self._stepper = s; super().set_stepper(s)
     def stepper(self): return getattr(self, '_stepper', 0)
     def dense_failures(self): return sum(self.last_lcp_error(w) for w in range(self.num_worlds))

@@ -8,6 +8,9 @@ These are NOT reference outputs (the reference stores no golden vectors and libo
                                      the universal's angles / rates, per-step row counts
   sampled_colliders_oracle_f64.npz : contact records of the sample-point colliders (capsule / cylinder pairs) on
                                      fixed seeded poses
+  dense_stepper_oracle_f64.npz     : dWorldStep (fast_step == false): rover on the heightfield (4 worlds, 320 cycles:
+                                     state, per-step contact and row counts) and friction-less quadruped (3 worlds,
+                                     60 steps: state)
 """
 import os
 import sys
@@ -99,3 +102,39 @@ for pi, (ca, da, cb, db) in enumerate(pairs):
     poses.append(pose)
 np.savez_compressed(os.path.join(HERE, "sampled_colliders_oracle_f64.npz"), records=np.array(recs), poses=np.array(poses))
 print("golden fixtures written")
+
+# ---- dWorldStep (dense stepper, orc_lcp.c): the rover on the heightfield, 4 worlds, 320 collide+step cycles from the
+# drop (the wheels land after about 160), and the friction-less quadruped, 3 worlds, 60 steps
+W = 4
+oc = orc.OracleBatch(W)
+sc = scenes.rover(oc, with_geoms=True)
+oc.geom_create_heightfield(h, 0.1, x0, y0, surface={"mu": 1.0, "mu2": 1.0, "soft_erp": 0.2, "soft_cfm": 1e-5})
+oc.set_stepper(1)
+for w in range(W):
+    for b in sc["bodies"]:
+        p = oc.body_get_position(b, w)
+        oc.body_set_position(b, (p[0] + 0.7 * w, p[1] - 0.4 * w, p[2] + 0.1), w)
+    for j in sc["joints"]:
+        oc.joint_set_param(j, scenes.capi.PARAM_VEL | scenes.capi.PARAM_GROUP2, 2.0 + w, w)
+counts, rows = [], []
+for _ in range(320):
+    oc.collide()
+    counts.append([oc.contact_count(w) for w in range(W)])
+    oc.step(0.001)
+    rows.append([oc.last_num_rows(w) for w in range(W)])
+rover_state = oc.state_download(5)
+W = 3
+oc = orc.OracleBatch(W)
+sc = scenes.quadruped(oc)
+oc.set_stepper(1)
+t = 0.0
+for _ in range(60):
+    oc.contacts_clear()
+    for w in range(W):
+        scenes.quadruped_control(oc, sc, t, w, 0.37 * w)
+        scenes.sphere_plane_contacts(oc, sc["feet"], sc["foot_radius"], w, mu=0.0)
+    oc.step(0.001)
+    t += 0.001
+np.savez_compressed(os.path.join(HERE, "dense_stepper_oracle_f64.npz"), rover_state=rover_state,
+                    rover_counts=np.array(counts, dtype=np.int32), rover_rows=np.array(rows, dtype=np.int32),
+                    quadruped_state=oc.state_download(13))

@@ -181,3 +181,98 @@ def test_dense_warp_kernel_equals_thread_kernel(cuda_lib):
     d = np.abs(outs[0] - outs[1])
     print("quadruped: warp kernel vs thread kernel", d[:, :7].max(), d[:, 7:].max())
     assert d[:, :7].max() < 1e-6 and d[:, 7:].max() < 1e-4
+
+
+def test_dense_against_committed_fixture(cuda_lib):
+    """The committed oracle fixture of the dense stepper (tests/golden/dense_stepper_oracle_f64.npz, generator
+    tests/golden/make_golden.py): the device reproduces the friction-less quadruped to fp32 rounding and the rover
+    on the heightfield -- 320 free-running steps with contacts coming and going -- within 1e-4, with the same contact
+    and row counts in at least 97 % of the (step, world) pairs (a wheel at depth ~ 0 may be in or out once the states
+    differ by 1e-5)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dense_stepper_oracle_f64.npz"))
+    W = 4
+    ar = Arena(W)
+    sc = scenes.rover(ar, with_geoms=True)
+    h, x0, y0 = scenes.terrain_heights()
+    ar.geom_create_heightfield(h, 0.1, x0, y0, surface={"mu": 1.0, "mu2": 1.0, "soft_erp": 0.2, "soft_cfm": 1e-5})
+    ar.set_stepper(capi.STEPPER_DENSE)
+    for w in range(W):
+        for b in sc["bodies"]:
+            p = ar.body_get_position(b, w)
+            ar.body_set_position(b, (p[0] + 0.7 * w, p[1] - 0.4 * w, p[2] + 0.1), w)
+        for j in sc["joints"]:
+            ar.joint_set_param(j, capi.PARAM_VEL | capi.PARAM_GROUP2, 2.0 + w, w)
+    same = total = 0
+    for k in range(320):
+        ar.collide()
+        cc = [ar.contact_count(w) for w in range(W)]
+        ar.step(H)
+        rr = [ar.last_num_rows(w) for w in range(W)]
+        same += sum(int(a == b) for a, b in zip(cc, g["rover_counts"][k])) + sum(int(a == b) for a, b in zip(rr, g["rover_rows"][k]))
+        total += 2 * W
+    assert ar.dense_failures() == 0
+    d = np.abs(ar.state_download(5).astype(np.float64) - g["rover_state"])
+    print("dense rover vs fixture: pose", d[:, :7].max(), "velocity", d[:, 7:].max(), "equal counts", same, "of", total)
+    assert same >= 0.97 * total
+    # observed on B200: pose 9.1e-6, velocity 1.3e-3, all 2560 counts equal
+    assert d[:, :7].max() < 1e-4 and d[:, 7:].max() < 1.5e-2
+    W = 3
+    ar = Arena(W)
+    sc = scenes.quadruped(ar)
+    ar.set_stepper(capi.STEPPER_DENSE)
+    t = 0.0
+    for _ in range(60):
+        ar.contacts_clear()
+        for w in range(W):
+            scenes.quadruped_control(ar, sc, t, w, 0.37 * w)
+            scenes.sphere_plane_contacts(ar, sc["feet"], sc["foot_radius"], w, mu=0.0)
+        ar.step(H)
+        t += H
+    d = np.abs(ar.state_download(13).astype(np.float64) - g["quadruped_state"])
+    print("dense quadruped vs fixture: pose", d[:, :7].max(), "velocity", d[:, 7:].max())
+    assert d[:, :7].max() < 1e-5 and d[:, 7:].max() < 3e-3
+
+
+def test_dense_edge_cases(cuda_lib):
+    """Worlds without any row (free bodies: the dense stepper must leave the ballistic motion of quickstep untouched,
+    bitwise), a batch in which only some worlds have rows, and a world count that leaves the last warp / CTA ragged."""
+    outs = []
+    for stepper in (capi.STEPPER_QUICK, capi.STEPPER_DENSE):
+        W = 37
+        ar = Arena(W)
+        scenes.setup_world(ar)
+        ar.set_max_contacts(4)
+        for i in range(3):
+            scenes.add_body(ar, 1.0 + i, scenes.inertia_box(1.0 + i, 0.3, 0.2, 0.1), (i, 0, 1))
+        for w in range(W):
+            for b in range(3):
+                ar.body_set_linear_vel(b, (0.1 * w, -0.2 * b, 1.0), w)
+                ar.body_set_angular_vel(b, (0.5 * b, 0.3 * w, -1.0), w)
+        ar.set_stepper(stepper)
+        for _ in range(50):
+            ar.step(H)
+        outs.append(ar.state_download(3).copy())
+        ar.close()
+    assert np.array_equal(outs[0], outs[1])
+    # contacts in every third world only: a body resting on one frictional contact is held, the others fall freely
+    W = 37
+    ar, oc = Arena(W), orc.OracleBatch(W)
+    for be in (ar, oc):
+        scenes.setup_world(be)
+        be.set_max_contacts(4)
+        scenes.add_body(be, 2.0, scenes.inertia_box(2.0, 0.2, 0.2, 0.2), (0, 0, 0.1))
+        be.set_stepper(capi.STEPPER_DENSE)
+    for _ in range(30):
+        for be in (ar, oc):
+            be.contacts_clear()
+            for w in range(0, W, 3):
+                be.contact_add(w, 0, -1, pos=(0, 0, 0.0), normal=(0, 0, 1), depth=0.001, mode=scenes.CONTACT_MODE,
+                               mu=0.8, mu2=0.8, soft_erp=0.2, soft_cfm=1e-5)
+        ar.step(H)
+        oc.step(H)
+    assert ar.dense_failures() == 0
+    assert [ar.last_num_rows(w) for w in range(W)] == [3 if w % 3 == 0 else 0 for w in range(W)]
+    e = _err(ar, oc, 1)
+    print("dense, ragged batch:", e)
+    assert e["pos"] < 1e-6 and e["lvel"] < 1e-5, e
