@@ -15,8 +15,9 @@
 //     reached all of them get their bounds +-|mu' lam'_n| from the friction-less solution found so far (ODE:
 //     hit_first_friction_index); every further row is driven until it is in C or at a bound, rows changing set as
 //     the step length dictates (cases 1..6 of lcp.cpp);
-//   * ODE updates an LDL^T factor of A(C,C) row by row; here it is a Cholesky factor that grows by one row when an
-//     index enters C and is rebuilt when one leaves;
+//   * ODE updates an LDL^T factor of A(C,C) row by row; so does the warp kernel (a row is appended when an index
+//     enters C, the rows behind the position of an index that leaves are rebuilt); the thread-per-world kernel and the
+//     oracle keep a Cholesky factor -- the same solves up to rounding;
 //   * islands: A is block diagonal over a world's islands, so one problem per world has the same solution as one
 //     per island, whichever row order (world block / ODE islands) the assemble kernel used.
 // Arithmetic in FP64 (ODE's dWorldStep is used with dDOUBLE; a Cholesky factor of a constraint matrix whose only
@@ -441,39 +442,67 @@ __global__ void __launch_bounds__(32) b2p_dense_warp_kernel(const StepParams P, 
 
         int nC = 0;
         bool failed = false;
-        // forward / backward substitution with the factor's first p rows on a position vector held one element per
-        // lane and 32 positions (in place)
+        // The factor is L D L^T (unit lower L, like ODE's): a column of a triangular solve is then one shuffle
+        // broadcast and one DFMA per element, with no multiplication by the diagonal on the dependent chain.
+        // Forward / backward substitution with the factor's first p rows on a position vector held one element per
+        // lane and 32 positions (in place); `invd` holds 1 / D.
+        int roff[K]; // offset of this lane's rows in the packed triangle
+#pragma unroll
+        for (int k = 0; k < K; k++) roff[k] = tri(lane + 32 * k, 0);
         auto fwd = [&](double(&y)[K], int p) {
             for (int q = 0; q < p; q++) {
                 const int kq = q >> 5, owner = q & 31;
-                double v = 0.0;
+                double v = y[0];
 #pragma unroll
-                for (int k = 0; k < K; k++)
+                for (int k = 1; k < K; k++)
                     if (k == kq) v = y[k];
-                v = __shfl_sync(FULLW, v, owner) * invd[q];
+                v = __shfl_sync(FULLW, v, owner);
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     const int r = lane + 32 * k;
-                    if (r == q) y[k] = v;
-                    else if (r > q && r < p) y[k] -= Ls[tri(r, q)] * v;
+                    if (r > q && r < p) y[k] -= Ls[roff[k] + q] * v;
                 }
             }
         };
         auto bwd = [&](double(&y)[K], int p) {
             for (int q = p - 1; q >= 0; q--) {
-                const int kq = q >> 5, owner = q & 31;
-                double v = 0.0;
+                const int kq = q >> 5, owner = q & 31, qoff = tri(q, 0);
+                double v = y[0];
 #pragma unroll
-                for (int k = 0; k < K; k++)
+                for (int k = 1; k < K; k++)
                     if (k == kq) v = y[k];
-                v = __shfl_sync(FULLW, v, owner) * invd[q];
+                v = __shfl_sync(FULLW, v, owner);
 #pragma unroll
                 for (int k = 0; k < K; k++) {
                     const int r = lane + 32 * k;
-                    if (r == q) y[k] = v;
-                    else if (r < q) y[k] -= Ls[tri(q, r)] * v;
+                    if (r < q) y[k] -= Ls[qoff + r] * v;
                 }
             }
+        };
+        // new last row of the factor from u = L^-1 A(C, idx) (by position): l = u / D, d = A(idx,idx) - u . l
+        auto chol_append_u = [&](int idx, const double(&u)[K]) {
+            const int p = nC;
+            double ss = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int r = lane + 32 * k;
+                if (r < p) {
+                    const double l = u[k] * invd[r];
+                    ss += u[k] * l;
+                    Ls[tri(p, r)] = l;
+                }
+            }
+            double d = As[tri(idx, idx)] - warp_sum(ss);
+            if (!(d > 0.0)) {
+                failed = true;
+                d = 1e-300;
+            }
+            if (lane == 0) {
+                invd[p] = 1.0 / d;
+                Cl[p] = (uint8_t)idx;
+            }
+            nC = p + 1;
+            __syncwarp();
         };
         auto chol_append = [&](int idx) {
             const int p = nC;
@@ -484,28 +513,7 @@ __global__ void __launch_bounds__(32) b2p_dense_warp_kernel(const StepParams P, 
                 y[k] = r < p ? Asym(idx, Cl[r]) : 0.0;
             }
             fwd(y, p);
-            double ss = 0.0;
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                const int r = lane + 32 * k;
-                if (r < p) {
-                    ss += y[k] * y[k];
-                    Ls[tri(p, r)] = y[k];
-                }
-            }
-            double d = As[tri(idx, idx)] - warp_sum(ss);
-            if (!(d > 0.0)) {
-                failed = true;
-                d = 1e-300;
-            }
-            if (lane == 0) {
-                const double l = sqrt(d);
-                Ls[tri(p, p)] = l;
-                invd[p] = 1.0 / l;
-                Cl[p] = (uint8_t)idx;
-            }
-            nC = p + 1;
-            __syncwarp();
+            chol_append_u(idx, y);
         };
         // an index leaves C: the factor's rows in front of its position stay, the ones behind are rebuilt
         auto chol_remove = [&](int idx) {
@@ -522,8 +530,15 @@ __global__ void __launch_bounds__(32) b2p_dense_warp_kernel(const StepParams P, 
             for (int q = pos + 1; q < old; q++) chol_append(Cold[q]);
         };
         // sp(C) = A(C,C)^-1 y, y by position (one element per lane and 32 positions)
+        double zfwd[K]; // L^-1 rhs of the last solve: if the driving index enters C next, that is its row of the factor
         auto solve_to_sp = [&](double(&y)[K]) {
             fwd(y, nC);
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const int r = lane + 32 * k;
+                zfwd[k] = y[k];
+                if (r < nC) y[k] *= invd[r];
+            }
             bwd(y, nC);
 #pragma unroll
             for (int k = 0; k < K; k++) {
@@ -673,8 +688,14 @@ __global__ void __launch_bounds__(32) b2p_dense_warp_kernel(const StepParams P, 
                     }
                 }
                 __syncwarp();
-                if (cmd == 1) chol_append(i);
-                else if (cmd == 4) chol_append(si);
+                if (cmd == 1) {
+                    // the solve above ran on rhs = -dir A(C,i) with the C that i now joins: its forward half is the
+                    // new row (ODE keeps `ell` from solve1 for the same reason)
+                    double u[K];
+#pragma unroll
+                    for (int kk = 0; kk < K; kk++) u[kk] = -dirf * zfwd[kk];
+                    chol_append_u(i, u);
+                } else if (cmd == 4) chol_append(si);
                 else if (cmd >= 5) chol_remove(si);
                 if (cmd <= 3) break;
             }
