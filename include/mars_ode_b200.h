@@ -326,7 +326,7 @@ int b2p_collide_record_pairs(b2p_arena *a, int on);
 /* broadphase pair list of one world, sorted by (min geom, max geom); returns pair count */
 int b2p_collide_get_pairs(b2p_arena *a, int world, int *pairs, int max_pairs);
 
-/* ---- the step (dWorldQuickStep: src/WorldPhysics.cpp:365) ---- */
+/* ---- the step (dWorldQuickStep: src/WorldPhysics.cpp:365; dWorldStep, :369, after b2p_arena_set_stepper) ---- */
 int b2p_step(b2p_arena *a, double step_size);
 int b2p_sync(b2p_arena *a);
 /* diagnostics of the last step */
