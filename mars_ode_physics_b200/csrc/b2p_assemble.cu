@@ -105,13 +105,20 @@ __device__ __forceinline__ float emit_row(const StepParams &P, const Smem &S, in
     o[1] = pc.sm0 * r.J[1];
     o[2] = pc.sm0 * r.J[2];
     sym_mul(o + 3, pc.S0, r.J + 3);
-    o[6] = pc.sm1 * r.J[6];
-    o[7] = pc.sm1 * r.J[7];
-    o[8] = pc.sm1 * r.J[8];
-    sym_mul(o + 9, pc.S1, r.J + 9);
     float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 12; k++) sum += o[k] * o[k];
+    for (int k = 0; k < 6; k++) sum += o[k] * o[k];
+    if (pc.b1 >= 0) { // (a one-body row's second half is zero: same sum, same row)
+        o[6] = pc.sm1 * r.J[6];
+        o[7] = pc.sm1 * r.J[7];
+        o[8] = pc.sm1 * r.J[8];
+        sym_mul(o + 9, pc.S1, r.J + 9);
+#pragma unroll
+        for (int k = 6; k < 12; k++) sum += o[k] * o[k];
+    } else {
+#pragma unroll
+        for (int k = 6; k < 12; k++) o[k] = 0.f;
+    }
     const float Ad = P.sor_w / (sum + cfm);
     const float sa = sqrtf(Ad), rsa = 1.0f / sa;
     // bound word b: the row is limited to [-b,b] with b = hi/sqrt(Ad) (+inf: unbounded); kind bit 0 / 1

@@ -126,12 +126,20 @@ template <int KR, int NW> __global__ void __launch_bounds__(NW * 32, 1) b2p_sor_
         __syncthreads();
         atomicAdd(&s_cnt[m0], 1);
         __syncthreads();
-        if (tid == 0) {
+        // exclusive prefix sums from the longest count down: warp 0, 32 counts per pass
+        if (warp == 0) {
             int acc = 0;
-            for (int i = R; i >= 0; i--) {
-                const int c = s_cnt[i];
-                s_cnt[i] = acc;
-                acc += c;
+            for (int base = R; base >= 0; base -= 32) {
+                const int i = base - lane;
+                const int c = i >= 0 ? s_cnt[i] : 0;
+                int incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (i >= 0) s_cnt[i] = acc + incl - c;
+                acc += __shfl_sync(0xffffffffu, incl, 31);
             }
         }
         __syncthreads();
