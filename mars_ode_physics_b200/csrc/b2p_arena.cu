@@ -25,6 +25,7 @@ extern "C" size_t b2p_sor_smem_bytes(int nb, int maxrows, int rows_resident);
 extern "C" int b2p_sor_register_rows(int maxrows, int wanted);
 extern "C" size_t b2p_sor_tmem_smem_bytes(int nb, int maxrows, int pool, int warps);
 extern "C" int b2p_sor_tmem_rows_on_chip(int kr, int warps);
+extern "C" int b2p_dense_fits_warp_kernel(int nb, int maxrows);
 extern "C" void b2p_dense_scratch_sizes(int nb, int maxrows, size_t *mat_doubles, size_t *vec_doubles, size_t *set_bytes);
 extern "C" cudaError_t b2p_launch_dense(const StepParams *P, const DenseScratch *D, int nb, int maxrows, int sm_count,
                                         int force_thread_kernel, cudaStream_t stream);
@@ -2290,7 +2291,9 @@ int prepare_step(b2p_arena *a, double step_size, StepParams &P, bool &use_tmem)
     P.stepper = a->stepper;
     if (a->stepper == B2P_STEPPER_DENSE) {
         if (maxrows > 254) return fail(B2P_ECAPACITY, "the dense stepper supports at most 254 rows per world");
-        if (a->dense_rows != maxrows || a->dense_nb != nb || !a->dense.A) {
+        // the per-world global scratch (2 x rows^2 doubles per world) only where the thread-per-world kernel runs
+        const bool need_scratch = (P.tune & 8) != 0 || !b2p_dense_fits_warp_kernel(nb, std::max(maxrows, 1));
+        if (need_scratch && (a->dense_rows != maxrows || a->dense_nb != nb || !a->dense.A)) {
             if (a->dense.A) cudaFree(a->dense.A);
             if (a->dense.L) cudaFree(a->dense.L);
             if (a->dense.vec) cudaFree(a->dense.vec);
@@ -2303,14 +2306,14 @@ int prepare_step(b2p_arena *a, double step_size, StepParams &P, bool &use_tmem)
             CUDA_TRY(cudaMalloc(&a->dense.L, sizeof(double) * md * (size_t)a->Wp));
             CUDA_TRY(cudaMalloc(&a->dense.vec, sizeof(double) * vd * (size_t)a->Wp));
             CUDA_TRY(cudaMalloc(&a->dense.sets, sb * (size_t)a->Wp));
-            if (!a->dense.failures) {
-                CUDA_TRY(cudaMalloc(&a->dense.failures, sizeof(int)));
-                CUDA_TRY(cudaMemsetAsync(a->dense.failures, 0, sizeof(int), a->stream));
-            }
-            if (!a->dense.residual) CUDA_TRY(cudaMalloc(&a->dense.residual, sizeof(float) * (size_t)a->Wp));
             a->dense_rows = maxrows;
             a->dense_nb = nb;
         }
+        if (!a->dense.failures) {
+            CUDA_TRY(cudaMalloc(&a->dense.failures, sizeof(int)));
+            CUDA_TRY(cudaMemsetAsync(a->dense.failures, 0, sizeof(int), a->stream));
+        }
+        if (!a->dense.residual) CUDA_TRY(cudaMalloc(&a->dense.residual, sizeof(float) * (size_t)a->Wp));
     }
     if (a->order_mode == B2P_ORDER_ODE_ISLANDS && a->maxc > 64)
         return fail(B2P_ECAPACITY, "the island row order supports at most 64 contacts per world");

@@ -752,13 +752,21 @@ extern "C" void b2p_dense_scratch_sizes(int nb, int maxrows, size_t *mat_doubles
     *set_bytes = (size_t)maxrows * 5;
 }
 
+// does the warp kernel (all of a world in shared memory) run for this scene?  Otherwise the thread-per-world kernel,
+// which needs the per-world global scratch of b2p_dense_scratch_sizes
+extern "C" int b2p_dense_fits_warp_kernel(int nb, int maxrows)
+{
+    const int K = (maxrows + 31) / 32;
+    return dense_warp_smem(nb, maxrows) + 1024 <= 227 * 1024 && K >= 1 && K <= 5;
+}
+
 // `force_thread_kernel`: the one-world-per-thread kernel even where the warp kernel fits (tests compare the two)
 extern "C" cudaError_t b2p_launch_dense(const StepParams *P, const DenseScratch *D, int nb, int maxrows, int sm_count,
                                         int force_thread_kernel, cudaStream_t stream)
 {
     const size_t smem = dense_warp_smem(nb, maxrows);
     const int K = (maxrows + 31) / 32;
-    if (!force_thread_kernel && smem + 1024 <= 227 * 1024 && K >= 1 && K <= 5) {
+    if (!force_thread_kernel && b2p_dense_fits_warp_kernel(nb, maxrows)) {
         void (*kern)(const StepParams, const DenseScratch) = nullptr;
         switch (K) {
         case 1: kern = b2p_dense_warp_kernel<1>; break;
