@@ -22,7 +22,7 @@
 
 namespace {
 
-constexpr int CBD = 128;
+constexpr int CBD = 64;
 constexpr int MAXPC = 4; // contacts per pair
 
 #define G(arr, field) (arr)[(size_t)(field) * Wp + w]
@@ -1000,7 +1000,7 @@ __device__ __forceinline__ int narrowphase(const CollideParams &P, const DevHeig
 
 // SAMPLED: the scene has geom pairs handled by the sample-point colliders (cylinders; capsule against box or
 // heightfield).  Scenes without them run the variant that does not carry that code's registers and stack.
-template <bool SAMPLED> __global__ void __launch_bounds__(CBD) b2p_collide_kernel(const CollideParams P)
+template <bool SAMPLED> __global__ void __launch_bounds__(CBD, SAMPLED ? 6 : 8) b2p_collide_kernel(const CollideParams P)
 {
     extern __shared__ float saabb[]; // [ng*6][CBD]: centre, half extents
     const DevTemplate *__restrict__ T = P.T;
