@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(32) b2p_dense_warp_kernel(const StepParams P, 
             }
         };
         // new last row of the factor from u = L^-1 A(C, idx) (by position): l = u / D, d = A(idx,idx) - u . l
-        auto chol_append_u = [&](int idx, const double(&u)[K]) {
+        auto factor_append_row = [&](int idx, const double(&u)[K]) {
             const int p = nC;
             double ss = 0.0;
 #pragma unroll
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(32) b2p_dense_warp_kernel(const StepParams P, 
             nC = p + 1;
             __syncwarp();
         };
-        auto chol_append = [&](int idx) {
+        auto factor_append = [&](int idx) {
             const int p = nC;
             double y[K];
 #pragma unroll
@@ -513,10 +513,10 @@ __global__ void __launch_bounds__(32) b2p_dense_warp_kernel(const StepParams P, 
                 y[k] = r < p ? Asym(idx, Cl[r]) : 0.0;
             }
             fwd(y, p);
-            chol_append_u(idx, y);
+            factor_append_row(idx, y);
         };
         // an index leaves C: the factor's rows in front of its position stay, the ones behind are rebuilt
-        auto chol_remove = [&](int idx) {
+        auto factor_remove = [&](int idx) {
             const int old = nC;
             int pos = old;
             for (int base = 0; base < old; base += 32) {
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(32) b2p_dense_warp_kernel(const StepParams P, 
             for (int q = pos + 1 + lane; q < old; q += 32) Cold[q] = Cl[q];
             __syncwarp();
             nC = pos;
-            for (int q = pos + 1; q < old; q++) chol_append(Cold[q]);
+            for (int q = pos + 1; q < old; q++) factor_append(Cold[q]);
         };
         // sp(C) = A(C,C)^-1 y, y by position (one element per lane and 32 positions)
         double zfwd[K]; // L^-1 rhs of the last solve: if the driving index enters C next, that is its row of the factor
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(32) b2p_dense_warp_kernel(const StepParams P, 
 
         for (int k = 0; k < nub; k++) {
             const int i = perm[k];
-            chol_append(i);
+            factor_append(i);
             if (lane == 0) set[i] = 1;
         }
         __syncwarp();
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(32) b2p_dense_warp_kernel(const StepParams P, 
                 continue;
             }
             if (wi0 == 0.0) {
-                chol_append(i);
+                factor_append(i);
                 if (lane == 0) set[i] = 1;
                 __syncwarp();
                 continue;
@@ -694,9 +694,9 @@ __global__ void __launch_bounds__(32) b2p_dense_warp_kernel(const StepParams P, 
                     double u[K];
 #pragma unroll
                     for (int kk = 0; kk < K; kk++) u[kk] = -dirf * zfwd[kk];
-                    chol_append_u(i, u);
-                } else if (cmd == 4) chol_append(si);
-                else if (cmd >= 5) chol_remove(si);
+                    factor_append_row(i, u);
+                } else if (cmd == 4) factor_append(si);
+                else if (cmd >= 5) factor_remove(si);
                 if (cmd <= 3) break;
             }
         }
